@@ -1,0 +1,133 @@
+"""Pin the oracle (oracle/xrsd_oracle.py) to outputs of the unmodified reference.
+
+Golden files were produced by oracle/make_golden.py from /root/reference; the KAT
+literals are the ones recorded in SURVEY.md section 8c.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import xrsd_oracle as orc
+
+KAT = {
+    "kat1_sphere_ff_r20": [0.9960057100548318, 0.9035060368192702, 0.6530966624699874, -0.05705364484750247, 0.023540082539625463],
+    "kat2_rnormal": [0.9911295333768088, 0.7979995298136433, 0.3893063916599735, 0.004840404725041509, 0.00039084460962254586],
+    "kat3_gp": [0.9966722160545233, 0.9200444146293232, 0.7165313105737893, 0.12472499703086228, 0.007795312314428892],
+    "kat4_hs": [1.0193424920065466, 1.641236328751801, 8.296980400453025, 11.86683989249156, 10.94990394993525],
+    "kat5_al": [0.999988034771849, 0.999701035776391, 0.9988062202173962, 0.9926287277355802, 0.9717421215037889],
+    "kat6_voigt": [6.0650091194524975, 88.02669460116742, 119.11962704557587, 110.16380117040605, 0.2296811764228624],
+    "kat7_gauss": [6.999353160706541e-06, 117.42965983745641, 234.85931967491283, 197.49236000356038, 1.6867880224857846e-186],
+    "kat8_lorentz": [6.121343965072898, 79.57747154594767, 159.15494309189535, 127.3239544735163, 0.25424112314999253],
+}
+
+
+def test_survey_kats_match_golden_and_oracle(golden_kernels, golden_definitions):
+    g = golden_kernels
+    q5, x5 = g["q5"], g["x5"]
+    al = golden_definitions["atomic_params"]["Al"]
+    mine = {
+        "kat1_sphere_ff_r20": orc.sphere_ff(q5, 20),
+        "kat2_rnormal": orc.sphere_normal_intensity(q5, 20, 0.1, 2.5, 0.1),
+        "kat3_gp": orc.guinier_porod(q5, 10, 4),
+        "kat4_hs": orc.hard_sphere_sf(q5, 25, 0.3),
+        "kat5_al": orc.atomic_ff(q5, al["Z"], al["a"], al["b"]),
+        "kat6_voigt": orc.voigt(x5, 0.002, 0.0018),
+        "kat7_gauss": orc.gaussian(x5, 0.002),
+        "kat8_lorentz": orc.lorentzian(x5, 0.002),
+    }
+    for k, lit in KAT.items():
+        np.testing.assert_allclose(g[k], lit, rtol=1e-14, err_msg=k)       # golden == SURVEY literal
+        np.testing.assert_allclose(mine[k], g[k], rtol=1e-15, atol=0, err_msg=k)  # oracle == golden
+
+
+def test_elementary_sweeps(golden_kernels, golden_definitions):
+    g = golden_kernels
+    q, q0 = g["q"], g["q0"]
+    for r, ref in zip(g["sphere_r"], g["sphere_ff"]):
+        np.testing.assert_array_equal(orc.sphere_ff(q, r), ref)
+    for r, ref in zip(g["sphere_r"][:3], g["sphere_ff_q0"]):
+        np.testing.assert_array_equal(orc.sphere_ff(q0, r), ref)
+    for row, ref in zip(g["rnormal_args"], g["rnormal_I"]):
+        np.testing.assert_array_equal(orc.sphere_normal_intensity(q, *row), ref)
+    for row, ref in zip(g["gp_args"], g["gp_I"]):
+        np.testing.assert_array_equal(orc.guinier_porod(q, *row), ref)
+    for row, ref in zip(g["hs_args"], g["hs_S"]):
+        np.testing.assert_array_equal(orc.hard_sphere_sf(q, *row), ref)
+    for row, ref in zip(g["hs_args"][:2], g["hs_S_q0"]):
+        np.testing.assert_array_equal(orc.hard_sphere_sf(q0, *row), ref)
+    for sym, ref in zip(g["atomic_syms"], g["atomic_ff"]):
+        rec = golden_definitions["atomic_params"][str(sym)]
+        np.testing.assert_array_equal(orc.atomic_ff(g["qa"], rec["Z"], rec["a"], rec["b"]), ref)
+    for (hg, hl), ref in zip(g["voigt_args"], g["voigt"]):
+        np.testing.assert_array_equal(orc.voigt(g["px"], hg, hl), ref)
+    for h, ref in zip(g["hwhm"], g["gauss"]):
+        np.testing.assert_array_equal(orc.gaussian(g["px"], h), ref)
+    for h, ref in zip(g["hwhm"], g["lorentz"]):
+        np.testing.assert_array_equal(orc.lorentzian(g["px"], h), ref)
+
+
+def test_reflection_tables_bit_exact(golden_tables, golden_definitions):
+    pgs = golden_definitions["sg_point_groups"]
+    for case in golden_tables:
+        sg = case["space_group"]
+        pg = pgs[sg] if sg else None
+        hkl, mult, _ = orc.reflection_table(case["lattice"], case["latparams"], case["q_min"], case["q_max"],
+                                            pg, case["use_symmetry"])
+        assert hkl.astype(int).tolist() == case["hkl"], (case["lattice"], sg)
+        assert np.asarray(mult).astype(int).tolist() == case["mult"], (case["lattice"], sg)
+
+
+def test_kat12_table_sizes(golden_tables):
+    by = {(c["lattice"], c["space_group"], c["latparams"]["a"], c["q_max"]): c for c in golden_tables
+          if c["q_min"] == 0.0 and c["use_symmetry"]}
+    c = by[("P_cubic", "Pm-3m", 33.3, 1.0)]
+    assert c["n_all"] == 618 and len(c["hkl"]) == 40
+    pairs = {tuple(h): m for h, m in zip(c["hkl"], c["mult"])}
+    assert pairs[(2, 1, 0)] == 16 and pairs[(1, 0, 2)] == 8     # greedy, non-minimal (SURVEY KAT12)
+    c = by[("F_cubic", "Fm-3m", 60.0, 1.0)]
+    assert c["n_all"] == 3742 and len(c["hkl"]) == 198 and sum(c["mult"]) == 3742
+    assert c["hkl"][:0] == [] and [1, 0, 0] in c["hkl"] and [6, 0, 0] in c["hkl"]
+    c = by[("hcp", "P6(3)/mmc", 40.0, 1.0)]
+    assert c["n_all"] == 1520 and len(c["hkl"]) == 412
+
+
+def test_systems_intensity_and_residual(golden_systems, ref_tables):
+    meta, arrays = golden_systems
+    n_checked = 0
+    for m in meta:
+        key = m["key"]
+        q = arrays[m["q"]]
+        sysd = m["system"]
+        with np.errstate(all="ignore"):
+            I = orc.system_intensity(q, sysd, **ref_tables)
+        np.testing.assert_array_equal(I, arrays[key + "_I"], err_msg=m["name"])
+        # residuals: same five evaluations make_golden.py recorded
+        Iobs = arrays[key + "_Iobs"]
+        Ic = 1.01 * arrays[key + "_I"] + 1e-4
+        got = []
+        with np.errstate(all="ignore"):
+            for ew in (True, False):
+                for lw in (True, False):
+                    got.append(orc.residual(q, Iobs, Ic, None, ew, lw, sysd["fit_report"]["q_range"]))
+            got.append(orc.residual(q, Iobs, Ic, 0.1 * np.sqrt(np.abs(Iobs)) + 1e-3, True, True,
+                                    (q[len(q) // 8], q[-len(q) // 8])))
+        np.testing.assert_array_equal(np.array(got), arrays[key + "_res"], err_msg=m["name"])
+        n_checked += 1
+    assert n_checked >= 200
+
+
+def test_kat9_kat10_kat11(golden_systems, ref_tables):
+    meta, arrays = golden_systems
+    by = {m["name"]: m for m in meta}
+    I3 = arrays[by["cfg3"]["key"] + "_I"] - 1e-3   # the System adds the default flat noise
+    np.testing.assert_allclose(I3[[0, 1000, 4096, 8191]],
+                               [0.014925309254644302, 0.16112822886958977, 0.04013058041492159, 0.0048555369738168775],
+                               rtol=1e-12)
+    I1 = arrays[by["cfg1"]["key"] + "_I"]
+    np.testing.assert_allclose(I1[[0, 500, 1999]], [1.000920002744589, 0.24541646388521973, 0.0015541354859723796],
+                               rtol=1e-14)
+    # KAT11: residual of an r=21 system against KAT10*(1+0.02 randn)
+    q = arrays[by["cfg1"]["q"]]
+    Iobs = I1 * (1 + 0.02 * np.random.RandomState(0).randn(2000))
+    sysd = {"p": {"structure": "diffuse", "form": "spherical", "settings": {"distribution": "single"},
+                  "parameters": {"I0": 1.0, "r": 21.0}}}
+    Ic = orc.system_intensity(q, sysd, **ref_tables)
+    assert orc.residual(q, Iobs, Ic) == pytest.approx(0.011354578266228588, rel=1e-13)
