@@ -1,0 +1,201 @@
+/* xrsd_b200.h -- C ABI of the B200-native scattering-intensity engine.
+ *
+ * Drop-in boundary for xrsdkit's intensity path.  The reference has no FFI; its
+ * narrowest seams are Python functions.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference root):
+ *
+ *   xrsd_reflection_tables   <- scattering/__init__.py:240-297 (hkl enumeration, |q_hkl|)
+ *                               + scattering/symmetries.py:44-92 (symmetrize_points)
+ *                               + the geometric part of scattering/__init__.py:307-327
+ *   xrsd_intensity_batch     <- system/__init__.py:112-130 (System.compute_intensity)
+ *                               = system/noise.py:50-63 + scattering/__init__.py:12-66,
+ *                               69-161, 299-333 + structure_factors.py:3-47
+ *                               + form_factors.py:8-28 + tools/peak_math.py:24-47
+ *   xrsd_residual_batch      <- system/__init__.py:134-187 (System.evaluate_residual)
+ *                               + tools/__init__.py:104-125 (compute_chi2)
+ *   xrsd_jacobian_batch /
+ *   xrsd_lm_*                <- the per-evaluation work of system/__init__.py:220-278 (fit);
+ *                               the reference drives Nelder-Mead through lmfit, these
+ *                               provide the batched Levenberg-Marquardt replacement
+ *   xrsd_*_host              <- the same calls for callers that own HOST buffers
+ *                               (copies happen inside)
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  "d_" arguments are device
+ * pointers on the current device; `stream` is a cudaStream_t passed as void* (NULL =
+ * default stream).  All floating point is IEEE double.  Functions return 0 on success
+ * or a negative XRSD_E* code; xrsd_last_error() gives the message for the calling
+ * thread.  Numerical degeneracies are not errors: NaN/inf propagate exactly as in the
+ * reference (e.g. underflowing Gaussian normalisation).
+ */
+#ifndef XRSD_B200_H
+#define XRSD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XRSD_ABI_VERSION 1
+
+#define XRSD_MAX_POPS 6      /* noise model + up to 5 populations per system layout   */
+#define XRSD_MAX_SPECIES 4   /* species (atoms) per crystalline population             */
+#define XRSD_MAX_PAIRS 10    /* XRSD_MAX_SPECIES*(XRSD_MAX_SPECIES+1)/2                */
+#define XRSD_MAX_OPS 9       /* symmetry operations per point group (m-3m has 9)       */
+#define XRSD_MAX_PARAMS 64   /* flat parameter slots per system                        */
+#define XRSD_MAX_FREE 16     /* free (fitted) parameters per system                    */
+
+/* xrsd_pop_t.kind */
+enum { XRSD_POP_NONE = 0, XRSD_POP_NOISE_FLAT = 1, XRSD_POP_NOISE_LOW_Q = 2,
+       XRSD_POP_NONCRYSTALLINE = 3, XRSD_POP_CRYSTALLINE = 4 };
+/* xrsd_pop_t.form (non-crystalline) and species_form[] (crystalline) */
+enum { XRSD_FORM_ATOMIC = 0, XRSD_FORM_SPHERE = 1, XRSD_FORM_SPHERE_R_NORMAL = 2, XRSD_FORM_GUINIER_POROD = 3 };
+/* xrsd_pop_t.profile */
+enum { XRSD_PROFILE_VOIGT = 0, XRSD_PROFILE_GAUSSIAN = 1, XRSD_PROFILE_LORENTZIAN = 2 };
+/* xrsd_pop_t.lattice: geometry classes of definitions.py:504-551 */
+enum { XRSD_LAT_CUBIC = 0, XRSD_LAT_HCP = 1, XRSD_LAT_HEXAGONAL = 2, XRSD_LAT_ORTHORHOMBIC = 3,
+       XRSD_LAT_TETRAGONAL = 4, XRSD_LAT_MONOCLINIC = 5, XRSD_LAT_RHOMBOHEDRAL = 6, XRSD_LAT_TRICLINIC = 7 };
+/* symmetry operation ids (scattering/symmetries.py:10-21) */
+enum { XRSD_OP_INVERSION = 0, XRSD_OP_MIRROR_X = 1, XRSD_OP_MIRROR_Y = 2, XRSD_OP_MIRROR_Z = 3,
+       XRSD_OP_MIRROR_X_Y = 4, XRSD_OP_MIRROR_Y_Z = 5, XRSD_OP_MIRROR_Z_X = 6,
+       XRSD_OP_MIRROR_NX_Y = 7, XRSD_OP_MIRROR_NY_Z = 8, XRSD_OP_MIRROR_NZ_X = 9 };
+
+/* error codes */
+enum { XRSD_OK = 0, XRSD_EINVAL = -1, XRSD_ECUDA = -2, XRSD_ECAPACITY = -3, XRSD_ENOMEM = -4 };
+
+/* per-table status bits written by xrsd_reflection_tables */
+enum { XRSD_TABLE_OK = 0, XRSD_TABLE_GRID_OVERFLOW = 1, XRSD_TABLE_LIST_OVERFLOW = 2,
+       XRSD_TABLE_SHELL_OVERFLOW = 4, XRSD_TABLE_BAD_LATTICE = 8 };
+
+/* One population (or the noise model) of a system layout.  p_* are slots into the
+ * flat per-system parameter vector (-1 = not used).  Plain old data, 8-byte aligned. */
+typedef struct xrsd_pop {
+  int32_t kind;
+  int32_t disordered;          /* 1: multiply by the hard-sphere S(q) (structure 'disordered') */
+  int32_t form;
+  int32_t profile;
+  int32_t sf_radial;           /* structure_factor_mode == 'radial' */
+  int32_t polz, lorentz, use_symmetry;
+  int32_t lattice;
+  int32_t n_sites;             /* basis sites of the conventional cell (definitions.py:462-502) */
+  int32_t n_ops;
+  int32_t ops[XRSD_MAX_OPS];
+  int32_t n_species;
+  int32_t species_form[XRSD_MAX_SPECIES];
+  int32_t p_I0, p_r, p_sigma, p_rg, p_D, p_r_hard, p_v_fraction, p_flat_fraction;
+  int32_t p_lat[6];            /* a, b, c, alpha, beta, gamma */
+  int32_t p_hwhm, p_hwhm_g, p_hwhm_l;
+  int32_t p_uvw[XRSD_MAX_SPECIES][3];
+  int32_t table_slot;          /* index among the layout's crystalline populations */
+  int32_t prune_extinct;       /* drop shells whose geometric weight is < 1e-20 of the largest */
+  int32_t reserved0;
+  double sampling_width, sampling_step;
+  double q_min, q_max;         /* q_max already resolved (falsy -> q[-1], scattering/__init__.py:226) */
+  double sites[8][3];
+  double atom_Z[XRSD_MAX_SPECIES];
+  double atom_a[XRSD_MAX_SPECIES][4];
+  double atom_b[XRSD_MAX_SPECIES][4];
+} xrsd_pop_t;
+
+typedef struct xrsd_layout {
+  int32_t n_pops;              /* pops[0] is always the noise model */
+  int32_t n_params;
+  int32_t n_xtal;              /* number of crystalline populations (= table slots) */
+  int32_t q0_is_zero;          /* q[0] == 0: the only zero the reference special-cases */
+  double wavelength;
+  xrsd_pop_t pops[XRSD_MAX_POPS];
+} xrsd_layout_t;
+
+/* Reflection-table storage for `n_tables` = batch * layout.n_xtal tables, table index
+ * t = b * n_xtal + slot.  All arrays are device memory owned by the caller. */
+typedef struct xrsd_tables {
+  int32_t cap_shell;           /* shells per table the arrays below can hold            */
+  int32_t cap_refl;            /* reduced reflections per table (0: do not export)      */
+  int32_t n_pairs_max;         /* leading dimension of shell_geo (<= XRSD_MAX_PAIRS)    */
+  int32_t reserved0;
+  int32_t *n_shell;            /* [n_tables]                                             */
+  int32_t *n_refl;             /* [n_tables] reduced reflections (before shell merging)  */
+  int32_t *n_all;              /* [n_tables] reflections in the G_min..G_max shell       */
+  int32_t *status;             /* [n_tables] XRSD_TABLE_* bits                           */
+  int32_t *shell_hkl;          /* [n_tables][cap_shell][4]: representative h,k,l, sum of multiplicities */
+  double *shell_geo;           /* [n_tables][cap_shell][n_pairs_max]: sum mult*Re(G_a conj G_b)          */
+  int32_t *refl_hkl;           /* [n_tables][cap_refl][4]: h,k,l,mult in reference order (optional)       */
+} xrsd_tables_t;
+
+/* objective flags of xrsd_residual_batch (System.fit_report, system/__init__.py:23-28) */
+typedef struct xrsd_objective {
+  int32_t error_weighted;
+  int32_t logI_weighted;
+  int32_t has_dI;              /* 0: dI defaults to sqrt(I) on the fit mask (system/__init__.py:168-171) */
+  int32_t reserved0;
+  double q_lo, q_hi;           /* q_range */
+} xrsd_objective_t;
+
+const char *xrsd_last_error(void);
+int xrsd_abi_version(void);
+/* sizeof() of the structs above as compiled, so a binding can verify its mirror */
+int xrsd_struct_sizes(int32_t *sizeof_pop, int32_t *sizeof_layout, int32_t *sizeof_tables, int32_t *sizeof_objective);
+
+/* Dynamic shared memory the table builder needs for the largest candidate box of a
+ * batch, given the per-axis half-widths n1,n2,n3 (scattering/__init__.py:266-268). */
+int64_t xrsd_table_smem_bytes(int32_t n1, int32_t n2, int32_t n3);
+
+/* Build reflection tables for every crystalline population of every system of the batch. */
+int xrsd_reflection_tables(const xrsd_layout_t *layout, const double *d_params, int32_t ld_params,
+                           int32_t batch, const xrsd_tables_t *tables, int32_t max_cells, void *stream);
+
+/* I[b, :] for b < batch.  d_q[n_q], d_params[batch][ld_params], d_I[batch][ld_I]. */
+int xrsd_intensity_batch(const xrsd_layout_t *layout, const double *d_q, int32_t n_q,
+                         const double *d_params, int32_t ld_params, int32_t batch,
+                         const xrsd_tables_t *tables, double *d_I, int64_t ld_I, void *stream);
+
+/* chi2[b] of System.evaluate_residual for b < batch; d_Iobs / d_dI are [batch][ld_obs]
+ * (ld_obs == 0 broadcasts one pattern to the whole batch).  I(q) is computed in the same
+ * kernel and never written to memory. */
+int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj,
+                        const double *d_q, int32_t n_q, const double *d_params, int32_t ld_params,
+                        int32_t batch, const xrsd_tables_t *tables,
+                        const double *d_Iobs, const double *d_dI, int64_t ld_obs,
+                        double *d_chi2, void *stream);
+
+/* Forward-difference Jacobian of the weighted residual vector, reduced in-kernel to the
+ * normal equations: JTJ[b][n_free][n_free], JTr[b][n_free], chi2[b].  free_idx[n_free] are
+ * parameter slots; rel_step is the relative step (absolute for zero-valued parameters).
+ * Reflection tables are held fixed inside one evaluation. */
+int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj,
+                        const double *d_q, int32_t n_q, const double *d_params, int32_t ld_params,
+                        int32_t batch, const xrsd_tables_t *tables,
+                        const double *d_Iobs, const double *d_dI, int64_t ld_obs,
+                        const int32_t *free_idx, int32_t n_free, double rel_step,
+                        double *d_JTJ, double *d_JTr, double *d_chi2, void *stream);
+
+/* One damped Gauss-Newton (Levenberg-Marquardt) proposal per system:
+ * solve (JTJ + lambda*diag(JTJ)) delta = -JTr, project onto [lo, hi], write trial params. */
+int xrsd_lm_propose(const double *d_params, int32_t ld_params, int32_t batch,
+                    const int32_t *free_idx, int32_t n_free,
+                    const double *d_JTJ, const double *d_JTr, const double *d_lambda,
+                    const double *d_lo, const double *d_hi, const uint8_t *d_active,
+                    double *d_trial, void *stream);
+/* Accept/reject: where chi2_trial < chi2 copy trial -> params, lambda /= down, else lambda *= up;
+ * clears `active` for systems whose relative improvement fell below ftol or that hit lambda_max. */
+int xrsd_lm_update(double *d_params, int32_t ld_params, int32_t batch,
+                   const double *d_trial, double *d_chi2, const double *d_chi2_trial,
+                   double *d_lambda, uint8_t *d_active, int32_t *d_n_accept,
+                   double up, double down, double ftol, double lambda_max, void *stream);
+
+/* Host-buffer convenience call (what a non-Python caller binds): allocates / reuses an
+ * internal device workspace, copies q and params in, builds tables when the layout has
+ * crystalline populations, computes, copies I back.  Blocking. */
+int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int32_t n_q,
+                              const double *params, int32_t ld_params, int32_t batch,
+                              double *I_out, int64_t ld_I);
+void xrsd_release_workspace(void);
+
+/* FP64 pipe probe used by bench.py for the roofline denominator: runs a DFMA-bound
+ * kernel and returns the measured TFLOP/s (2 flop per DFMA) on the current device. */
+int xrsd_probe_fp64_peak(double *tflops, double *elapsed_ms, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XRSD_B200_H */

@@ -1,0 +1,377 @@
+// abi.cu -- the extern "C" boundary declared in include/xrsd_b200.h: argument checks,
+// launch-shape policy, error strings, and the host-buffer convenience path.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "../../include/xrsd_b200.h"
+
+extern "C" {
+int64_t xrsd_table_smem_layout(int32_t max_cells, int32_t cap_list);
+cudaError_t xrsd_launch_tables(const xrsd_layout_t *, const double *, int, int, const xrsd_tables_t *, int, int, cudaStream_t);
+cudaError_t xrsd_launch_intensity(const xrsd_layout_t *, const double *, int, const double *, int, int, const xrsd_tables_t *,
+                                  double *, long long, int, int, int, cudaStream_t);
+cudaError_t xrsd_launch_fp64_probe(double *, int, int, cudaStream_t);
+cudaError_t xrsd_launch_residual(const xrsd_layout_t *, const xrsd_objective_t *, const double *, int, const double *, int, int,
+                                 const xrsd_tables_t *, const double *, const double *, long long, double *, int, int,
+                                 cudaStream_t);
+size_t xrsd_jacobian_smem(int, int, int, int);
+cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *, const xrsd_objective_t *, const double *, int, const double *, int, int,
+                                 const xrsd_tables_t *, const double *, const double *, long long, const int32_t *, int, double,
+                                 double *, double *, double *, int, int, int, cudaStream_t);
+cudaError_t xrsd_launch_lm_propose(const double *, int, int, const int32_t *, int, const double *, const double *,
+                                   const double *, const double *, const double *, const uint8_t *, double *, cudaStream_t);
+cudaError_t xrsd_launch_lm_update(double *, int, int, const double *, double *, const double *, double *, uint8_t *, int *,
+                                  double, double, double, double, cudaStream_t);
+}
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+  return fail(XRSD_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+constexpr int kMaxSmem = 227 * 1024;
+constexpr int kStaticSmem = 2048;   // EvalShared / TableShared and friends
+
+int check_layout(const xrsd_layout_t *L) {
+  if (!L) return fail(XRSD_EINVAL, "layout is NULL");
+  if (L->n_pops < 1 || L->n_pops > XRSD_MAX_POPS) return fail(XRSD_EINVAL, "layout.n_pops=%d out of range", L->n_pops);
+  if (L->n_params < 1 || L->n_params > XRSD_MAX_PARAMS) return fail(XRSD_EINVAL, "layout.n_params=%d out of range", L->n_params);
+  int n_x = 0;
+  for (int i = 0; i < L->n_pops; ++i) {
+    const xrsd_pop_t &p = L->pops[i];
+    if (p.kind == XRSD_POP_CRYSTALLINE) {
+      if (p.n_species < 1 || p.n_species > XRSD_MAX_SPECIES)
+        return fail(XRSD_EINVAL, "population %d: n_species=%d (max %d)", i, p.n_species, XRSD_MAX_SPECIES);
+      if (p.n_sites < 1 || p.n_sites > 8) return fail(XRSD_EINVAL, "population %d: n_sites=%d", i, p.n_sites);
+      if (p.n_ops < 0 || p.n_ops > XRSD_MAX_OPS) return fail(XRSD_EINVAL, "population %d: n_ops=%d", i, p.n_ops);
+      if (!(L->wavelength != 0.0))   // scattering/__init__.py:224-225 raises ValueError
+        return fail(XRSD_EINVAL, "cannot compute diffraction with source wavelength of %g", L->wavelength);
+      if (p.table_slot != n_x) return fail(XRSD_EINVAL, "population %d: table_slot=%d, expected %d", i, p.table_slot, n_x);
+      ++n_x;
+    }
+  }
+  if (n_x != L->n_xtal) return fail(XRSD_EINVAL, "layout.n_xtal=%d but %d crystalline populations", L->n_xtal, n_x);
+  return XRSD_OK;
+}
+
+// scratch doubles accumulate_system() needs for this layout
+int scratch_doubles_for(const xrsd_layout_t *L, int *radial_multi) {
+  int need = 2 * 128 + 2;
+  *radial_multi = 0;
+  for (int i = 0; i < L->n_pops; ++i) {
+    const xrsd_pop_t &p = L->pops[i];
+    if (p.kind == XRSD_POP_NONCRYSTALLINE && p.form == XRSD_FORM_SPHERE_R_NORMAL) {
+      const double n = ceil(2.0 * p.sampling_width / p.sampling_step) + 2.0;
+      if (!(n >= 1.0) || n > 12000.0) return -1;
+      need = std::max(need, 2 * (int)n);
+    }
+    if (p.kind == XRSD_POP_CRYSTALLINE && p.sf_radial && p.n_species > 1) {
+      *radial_multi = 1;
+      const int np = p.n_species * (p.n_species + 1) / 2;
+      need = std::max(need, (1 + np) * 128);
+    }
+  }
+  return (need + 1) & ~1;
+}
+
+int check_tables(const xrsd_layout_t *L, const xrsd_tables_t *T) {
+  if (L->n_xtal == 0) return XRSD_OK;
+  if (!T) return fail(XRSD_EINVAL, "layout has crystalline populations but tables is NULL");
+  if (!T->n_shell || !T->shell_hkl || !T->shell_geo || !T->status || !T->n_refl || !T->n_all)
+    return fail(XRSD_EINVAL, "tables: missing device arrays");
+  if (T->cap_shell < 1) return fail(XRSD_EINVAL, "tables.cap_shell=%d", T->cap_shell);
+  for (int i = 0; i < L->n_pops; ++i) {
+    const xrsd_pop_t &p = L->pops[i];
+    if (p.kind == XRSD_POP_CRYSTALLINE && p.n_species * (p.n_species + 1) / 2 > T->n_pairs_max)
+      return fail(XRSD_EINVAL, "tables.n_pairs_max=%d too small for population %d", T->n_pairs_max, i);
+  }
+  return XRSD_OK;
+}
+
+const xrsd_tables_t kNoTables = {};
+
+}  // namespace
+
+extern "C" {
+
+const char *xrsd_last_error(void) { return g_err; }
+int xrsd_abi_version(void) { return XRSD_ABI_VERSION; }
+
+int xrsd_struct_sizes(int32_t *sp, int32_t *sl, int32_t *st, int32_t *so) {
+  if (sp) *sp = (int32_t)sizeof(xrsd_pop_t);
+  if (sl) *sl = (int32_t)sizeof(xrsd_layout_t);
+  if (st) *st = (int32_t)sizeof(xrsd_tables_t);
+  if (so) *so = (int32_t)sizeof(xrsd_objective_t);
+  return XRSD_OK;
+}
+
+int64_t xrsd_table_smem_bytes(int32_t n1, int32_t n2, int32_t n3) {
+  const int64_t cells = (int64_t)(2 * n1 - 1) * (2 * n2 - 1) * (2 * n3 - 1);
+  return xrsd_table_smem_layout((int32_t)std::min<int64_t>(cells, 1 << 30), 1024);
+}
+
+int xrsd_reflection_tables(const xrsd_layout_t *layout, const double *d_params, int32_t ld_params, int32_t batch,
+                           const xrsd_tables_t *tables, int32_t max_cells, void *stream) {
+  int rc = check_layout(layout);
+  if (rc) return rc;
+  if (layout->n_xtal == 0 || batch <= 0) return XRSD_OK;
+  rc = check_tables(layout, tables);
+  if (rc) return rc;
+  if (!d_params || ld_params < layout->n_params) return fail(XRSD_EINVAL, "params: NULL or ld_params < n_params");
+  if (max_cells < 1) return fail(XRSD_EINVAL, "max_cells=%d", max_cells);
+  // largest power-of-two reflection list that fits beside the candidate box
+  int cap_list = 4096;
+  while (cap_list > 64 && xrsd_table_smem_layout(max_cells, cap_list) + kStaticSmem > kMaxSmem) cap_list >>= 1;
+  if (xrsd_table_smem_layout(max_cells, cap_list) + kStaticSmem > kMaxSmem)
+    return fail(XRSD_ECAPACITY, "candidate box of %d cells does not fit in shared memory", max_cells);
+  // do not reserve more list than the box can hold
+  while (cap_list / 2 >= max_cells && cap_list > 64) cap_list >>= 1;
+  cudaError_t e = xrsd_launch_tables(layout, d_params, ld_params, batch, tables, max_cells, cap_list, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "reflection_table_kernel");
+  return XRSD_OK;
+}
+
+static int pick_q_per_cta(int n_q, int batch, int scratch) {
+  // whole-pattern CTAs when the batch alone fills the machine, else split q so that
+  // about 8 CTAs per SM exist; spans are multiples of 512 (256 threads x 2 q-points)
+  const long long want_ctas = 148LL * 8;
+  long long tiles = (want_ctas + batch - 1) / batch;
+  if (tiles < 1) tiles = 1;
+  long long per = ((long long)n_q + tiles - 1) / tiles;
+  per = ((per + 511) / 512) * 512;
+  const long long cap = std::max(512LL, ((long long)(96 * 1024 / 8 - scratch) / 512) * 512);   // <= 96 KB -> 2 CTAs/SM
+  per = std::min(per, cap);
+  per = std::min<long long>(per, ((long long)n_q + 511) / 512 * 512);
+  return (int)std::max(512LL, per);
+}
+
+int xrsd_intensity_batch(const xrsd_layout_t *layout, const double *d_q, int32_t n_q, const double *d_params,
+                         int32_t ld_params, int32_t batch, const xrsd_tables_t *tables, double *d_I, int64_t ld_I,
+                         void *stream) {
+  int rc = check_layout(layout);
+  if (rc) return rc;
+  if (batch <= 0 || n_q <= 0) return XRSD_OK;
+  rc = check_tables(layout, tables);
+  if (rc) return rc;
+  if (!d_q || !d_params || !d_I) return fail(XRSD_EINVAL, "NULL device pointer");
+  if (ld_params < layout->n_params) return fail(XRSD_EINVAL, "ld_params < n_params");
+  if (ld_I < n_q) return fail(XRSD_EINVAL, "ld_I < n_q");
+  int rm;
+  const int scratch = scratch_doubles_for(layout, &rm);
+  if (scratch < 0) return fail(XRSD_ECAPACITY, "size quadrature too fine for shared memory (sampling_width/sampling_step)");
+  const int per = pick_q_per_cta(n_q, batch, scratch);
+  cudaError_t e = xrsd_launch_intensity(layout, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables, d_I,
+                                        (long long)ld_I, per, scratch, rm, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "intensity_kernel");
+  return XRSD_OK;
+}
+
+int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q, int32_t n_q,
+                        const double *d_params, int32_t ld_params, int32_t batch, const xrsd_tables_t *tables,
+                        const double *d_Iobs, const double *d_dI, int64_t ld_obs, double *d_chi2, void *stream) {
+  int rc = check_layout(layout);
+  if (rc) return rc;
+  if (batch <= 0 || n_q <= 0) return XRSD_OK;
+  rc = check_tables(layout, tables);
+  if (rc) return rc;
+  if (!obj || !d_q || !d_params || !d_Iobs || !d_chi2) return fail(XRSD_EINVAL, "NULL pointer");
+  if (obj->has_dI && !d_dI) return fail(XRSD_EINVAL, "objective.has_dI set but d_dI is NULL");
+  if (ld_obs != 0 && ld_obs < n_q) return fail(XRSD_EINVAL, "ld_obs < n_q");
+  int rm;
+  const int scratch = scratch_doubles_for(layout, &rm);
+  if (scratch < 0) return fail(XRSD_ECAPACITY, "size quadrature too fine for shared memory");
+  if (((size_t)n_q + scratch + 2) * 8 + kStaticSmem > (size_t)kMaxSmem)
+    return fail(XRSD_ECAPACITY, "n_q=%d: a whole pattern must fit in shared memory for the fused residual", n_q);
+  cudaError_t e = xrsd_launch_residual(layout, obj, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables,
+                                       d_Iobs, obj->has_dI ? d_dI : nullptr, (long long)ld_obs, d_chi2, scratch, rm,
+                                       (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "residual_kernel");
+  return XRSD_OK;
+}
+
+int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q, int32_t n_q,
+                        const double *d_params, int32_t ld_params, int32_t batch, const xrsd_tables_t *tables,
+                        const double *d_Iobs, const double *d_dI, int64_t ld_obs, const int32_t *free_idx, int32_t n_free,
+                        double rel_step, double *d_JTJ, double *d_JTr, double *d_chi2, void *stream) {
+  int rc = check_layout(layout);
+  if (rc) return rc;
+  if (batch <= 0 || n_q <= 0) return XRSD_OK;
+  rc = check_tables(layout, tables);
+  if (rc) return rc;
+  if (!obj || !d_q || !d_params || !d_Iobs || !d_JTJ || !d_JTr || !d_chi2 || !free_idx) return fail(XRSD_EINVAL, "NULL pointer");
+  if (n_free < 1 || n_free > XRSD_MAX_FREE) return fail(XRSD_EINVAL, "n_free=%d (max %d)", n_free, XRSD_MAX_FREE);
+  for (int i = 0; i < n_free; ++i)
+    if (free_idx[i] < 0 || free_idx[i] >= layout->n_params) return fail(XRSD_EINVAL, "free_idx[%d]=%d", i, free_idx[i]);
+  if (obj->has_dI && !d_dI) return fail(XRSD_EINVAL, "objective.has_dI set but d_dI is NULL");
+  if (ld_obs != 0 && ld_obs < n_q) return fail(XRSD_EINVAL, "ld_obs < n_q");
+  if (!(rel_step > 0.0)) return fail(XRSD_EINVAL, "rel_step must be > 0");
+  int rm;
+  const int scratch = scratch_doubles_for(layout, &rm);
+  if (scratch < 0) return fail(XRSD_ECAPACITY, "size quadrature too fine for shared memory");
+  // q tile: as large as keeps two CTAs per SM resident (<= ~100 KB), multiple of 512
+  int tile_q = 2048;
+  while (tile_q > 512 && xrsd_jacobian_smem(layout->n_params, n_free, tile_q, scratch) + kStaticSmem > 100 * 1024) tile_q -= 512;
+  tile_q = std::min(tile_q, (n_q + 511) / 512 * 512);
+  if (xrsd_jacobian_smem(layout->n_params, n_free, tile_q, scratch) + kStaticSmem > (size_t)kMaxSmem)
+    return fail(XRSD_ECAPACITY, "jacobian working set does not fit in shared memory");
+  cudaError_t e = xrsd_launch_jacobian(layout, obj, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables, d_Iobs,
+                                       obj->has_dI ? d_dI : nullptr, (long long)ld_obs, free_idx, n_free, rel_step, d_JTJ,
+                                       d_JTr, d_chi2, tile_q, scratch, rm, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "jacobian_kernel");
+  return XRSD_OK;
+}
+
+int xrsd_lm_propose(const double *d_params, int32_t ld_params, int32_t batch, const int32_t *free_idx, int32_t n_free,
+                    const double *d_JTJ, const double *d_JTr, const double *d_lambda, const double *d_lo, const double *d_hi,
+                    const uint8_t *d_active, double *d_trial, void *stream) {
+  if (n_free < 1 || n_free > XRSD_MAX_FREE) return fail(XRSD_EINVAL, "n_free=%d (max %d)", n_free, XRSD_MAX_FREE);
+  if (!d_params || !free_idx || !d_JTJ || !d_JTr || !d_lambda || !d_lo || !d_hi || !d_trial) return fail(XRSD_EINVAL, "NULL pointer");
+  for (int i = 0; i < n_free; ++i)
+    if (free_idx[i] < 0 || free_idx[i] >= ld_params) return fail(XRSD_EINVAL, "free_idx[%d]=%d", i, free_idx[i]);
+  cudaError_t e = xrsd_launch_lm_propose(d_params, ld_params, batch, free_idx, n_free, d_JTJ, d_JTr, d_lambda, d_lo, d_hi,
+                                         d_active, d_trial, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "lm_propose_kernel");
+  return XRSD_OK;
+}
+
+int xrsd_lm_update(double *d_params, int32_t ld_params, int32_t batch, const double *d_trial, double *d_chi2,
+                   const double *d_chi2_trial, double *d_lambda, uint8_t *d_active, int32_t *d_n_accept, double up,
+                   double down, double ftol, double lambda_max, void *stream) {
+  if (!d_params || !d_trial || !d_chi2 || !d_chi2_trial || !d_lambda) return fail(XRSD_EINVAL, "NULL pointer");
+  cudaError_t e = xrsd_launch_lm_update(d_params, ld_params, batch, d_trial, d_chi2, d_chi2_trial, d_lambda, d_active,
+                                        d_n_accept, up, down, ftol, lambda_max, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "lm_update_kernel");
+  return XRSD_OK;
+}
+
+int xrsd_probe_fp64_peak(double *tflops, double *elapsed_ms, void *stream) {
+  double *d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_out, 8);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  cudaStream_t s = (cudaStream_t)stream;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 8, iters = 1 << 15;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  xrsd_launch_fp64_probe(d_out, blocks, 1024, s);   // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a, s);
+    xrsd_launch_fp64_probe(d_out, blocks, iters, s);
+    cudaEventRecord(b, s);
+    e = cudaEventSynchronize(b);
+    if (e != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    best = std::min(best, ms);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return cuda_fail(e, "fp64 probe");
+  const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+  if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+  if (elapsed_ms) *elapsed_ms = best;
+  return XRSD_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer convenience path
+namespace {
+struct Workspace {
+  void *base = nullptr;
+  size_t bytes = 0;
+  double *pinned = nullptr;
+  size_t pinned_bytes = 0;
+} g_ws;
+
+int ws_reserve(size_t bytes) {
+  if (bytes <= g_ws.bytes) return XRSD_OK;
+  if (g_ws.base) cudaFree(g_ws.base);
+  g_ws.base = nullptr;
+  g_ws.bytes = 0;
+  cudaError_t e = cudaMalloc(&g_ws.base, bytes);
+  if (e != cudaSuccess) return fail(XRSD_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  g_ws.bytes = bytes;
+  return XRSD_OK;
+}
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+}  // namespace
+
+void xrsd_release_workspace(void) {
+  if (g_ws.base) cudaFree(g_ws.base);
+  g_ws.base = nullptr;
+  g_ws.bytes = 0;
+}
+
+int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int32_t n_q, const double *params,
+                              int32_t ld_params, int32_t batch, double *I_out, int64_t ld_I) {
+  int rc = check_layout(layout);
+  if (rc) return rc;
+  if (batch <= 0 || n_q <= 0) return XRSD_OK;
+  if (!q || !params || !I_out) return fail(XRSD_EINVAL, "NULL host pointer");
+  if (ld_I < n_q) return fail(XRSD_EINVAL, "ld_I < n_q");
+  const int n_x = layout->n_xtal;
+  const size_t n_tab = (size_t)batch * n_x;
+  const int cap_shell = 512, n_pairs = XRSD_MAX_PAIRS;
+  // candidate-box bound from the host copy of the parameters is the caller's job in the device API;
+  // here use the largest box shared memory allows
+  int max_cells = 60000;
+  size_t off = 0;
+  const size_t o_q = off; off += align256((size_t)n_q * 8);
+  const size_t o_p = off; off += align256((size_t)batch * ld_params * 8);
+  const size_t o_I = off; off += align256((size_t)batch * n_q * 8);
+  const size_t o_ns = off; off += align256(n_tab * 4);
+  const size_t o_nr = off; off += align256(n_tab * 4);
+  const size_t o_na = off; off += align256(n_tab * 4);
+  const size_t o_st = off; off += align256(n_tab * 4);
+  const size_t o_sh = off; off += align256(n_tab * cap_shell * 4 * 4);
+  const size_t o_sg = off; off += align256(n_tab * cap_shell * n_pairs * 8);
+  rc = ws_reserve(off);
+  if (rc) return rc;
+  char *base = (char *)g_ws.base;
+  cudaStream_t s = 0;
+  cudaError_t e = cudaMemcpyAsync(base + o_q, q, (size_t)n_q * 8, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(base + o_p, params, (size_t)batch * ld_params * 8, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
+  xrsd_tables_t T = {};
+  if (n_x) {
+    T.cap_shell = cap_shell; T.cap_refl = 0; T.n_pairs_max = n_pairs;
+    T.n_shell = (int32_t *)(base + o_ns); T.n_refl = (int32_t *)(base + o_nr); T.n_all = (int32_t *)(base + o_na);
+    T.status = (int32_t *)(base + o_st); T.shell_hkl = (int32_t *)(base + o_sh); T.shell_geo = (double *)(base + o_sg);
+    rc = xrsd_reflection_tables(layout, (const double *)(base + o_p), ld_params, batch, &T, max_cells, s);
+    if (rc) return rc;
+    std::vector<int32_t> st(n_tab);
+    e = cudaMemcpyAsync(st.data(), T.status, n_tab * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return cuda_fail(e, "table status copy");
+    for (size_t i = 0; i < n_tab; ++i)
+      if (st[i]) return fail(XRSD_ECAPACITY, "reflection table %zu: status %d (capacity exceeded)", i, st[i]);
+  }
+  rc = xrsd_intensity_batch(layout, (const double *)(base + o_q), n_q, (const double *)(base + o_p), ld_params, batch,
+                            n_x ? &T : nullptr, (double *)(base + o_I), n_q, s);
+  if (rc) return rc;
+  e = cudaMemcpy2DAsync(I_out, (size_t)ld_I * 8, base + o_I, (size_t)n_q * 8, (size_t)n_q * 8, batch, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return cuda_fail(e, "D2H copy / kernel execution");
+  return XRSD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,344 @@
+// fit_kernels.cu -- batched fit objective, finite-difference normal equations and the
+// Levenberg-Marquardt step, one CTA (objective / Jacobian) or one thread (LM algebra) per
+// system.  I(q) is produced by accumulate_system() in shared memory and consumed in the same
+// kernel; it never goes to HBM.
+//
+//   residual_kernel  <- System.evaluate_residual, system/__init__.py:134-187, and
+//                       compute_chi2, tools/__init__.py:104-125 (scalar weighted chi^2,
+//                       including the reference's `wts *= dI**2` convention)
+//   jacobian_kernel  <- what one lmfit objective sweep would need (system/__init__.py:189-195
+//                       evaluates one parameter set per call; here n_free+1 sets per system)
+//   lm_*             <- replaces the lmfit Nelder-Mead driver of system/__init__.py:262-266
+//                       (no oracle in the reference; parity is defined on outcomes)
+#include "system_eval.cuh"
+
+namespace xrsd {
+
+struct FreeSet {
+  int n_free;
+  int idx[XRSD_MAX_FREE];
+};
+
+// weight and mask of one q-point (system/__init__.py:164-172)
+__device__ __forceinline__ bool fit_weight(const xrsd_objective_t &O, double qv, double Iobs, const double *dI, size_t k,
+                                           double &w) {
+  const bool fit = (Iobs > 0.0) && (qv >= O.q_lo) && (qv <= O.q_hi);
+  w = 1.0;
+  if (O.error_weighted) {
+    double d;
+    if (O.has_dI) d = dI[k];
+    else d = fit ? sqrt(Iobs) : NAN;
+    w = w * (d * d);
+  }
+  return fit;
+}
+
+template <bool RM>
+__global__ void __launch_bounds__(EVAL_THREADS, 2)
+residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t O, const double *__restrict__ q, int n_q,
+                const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
+                const double *__restrict__ Iobs, const double *__restrict__ dI, long long ld_obs,
+                double *__restrict__ chi2, int scratch_doubles) {
+  extern __shared__ __align__(16) double smem_d[];
+  __shared__ EvalShared S;
+  const int b = blockIdx.x;
+  if (b >= batch) return;
+  double *I_sm = smem_d;
+  double *scratch = smem_d + ((n_q + 1) & ~1);
+  accumulate_system<2, RM>(L, params + (size_t)b * ldp, T, b, q, n_q, 0, n_q, I_sm, scratch, scratch_doubles, &S);
+  const double *obs = Iobs + (size_t)b * ld_obs;
+  const double *err = dI ? dI + (size_t)b * ld_obs : nullptr;
+  double num = 0.0, den = 0.0;
+  for (int i = threadIdx.x; i < n_q; i += EVAL_THREADS) {
+    const double Io = obs[i], Ic = I_sm[i];
+    double w;
+    bool fit = fit_weight(O, q[i], Io, err, i, w);
+    double d;
+    if (O.logI_weighted) {
+      fit = fit && (Ic > 0.0);
+      d = fit ? (log(Ic) - log(Io)) : 0.0;
+    } else {
+      d = Ic - Io;
+    }
+    if (fit) { num += (d * d) * w; den += w; }
+  }
+  num = block_sum(num, &S);
+  den = block_sum(den, &S);
+  if (threadIdx.x == 0) chi2[b] = num / den;
+}
+
+// Normal equations by forward differences.  Shared memory: prm_var[(n_free+1)][ldp_s],
+// F[(n_free+1)][tile_q] (log I or I per variant), wts[tile_q], fobs[tile_q], scratch.
+template <bool RM>
+__global__ void __launch_bounds__(EVAL_THREADS, 2)
+jacobian_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t O, const double *__restrict__ q, int n_q,
+                const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
+                const double *__restrict__ Iobs, const double *__restrict__ dI, long long ld_obs,
+                const FreeSet F, double rel_step, double *__restrict__ JTJ, double *__restrict__ JTr,
+                double *__restrict__ chi2, int tile_q, int scratch_doubles) {
+  extern __shared__ __align__(16) double smem_d[];
+  __shared__ EvalShared S;
+  __shared__ double acc_sm[XRSD_MAX_FREE * (XRSD_MAX_FREE + 1) / 2 + XRSD_MAX_FREE + 2];
+  __shared__ double steps[XRSD_MAX_FREE];
+  const int b = blockIdx.x;
+  if (b >= batch) return;
+  const int tid = threadIdx.x;
+  const int nf = F.n_free, nv = nf + 1;
+  const int np = L.n_params;
+  const int ldp_s = (np + 1) & ~1;
+  double *prm_var = smem_d;
+  double *Fv = prm_var + (size_t)nv * ldp_s;
+  double *wts = Fv + (size_t)nv * tile_q;
+  double *fobs = wts + tile_q;
+  double *scratch = fobs + tile_q;
+  const double *prm = params + (size_t)b * ldp;
+  for (int i = tid; i < nv * ldp_s; i += EVAL_THREADS) {
+    const int v = i / ldp_s, k = i - v * ldp_s;
+    prm_var[i] = (k < np) ? prm[k] : 0.0;
+  }
+  const int n_acc = nf * (nf + 1) / 2 + nf + 2;
+  for (int i = tid; i < n_acc; i += EVAL_THREADS) acc_sm[i] = 0.0;
+  __syncthreads();
+  if (tid < nf) {
+    const double p0 = prm[F.idx[tid]];
+    const double h = (p0 != 0.0) ? fabs(p0) * rel_step : rel_step;
+    steps[tid] = h;
+    prm_var[(size_t)(tid + 1) * ldp_s + F.idx[tid]] = p0 + h;
+  }
+  __syncthreads();
+  const double *obs = Iobs + (size_t)b * ld_obs;
+  const double *err = dI ? dI + (size_t)b * ld_obs : nullptr;
+
+  for (int q0 = 0; q0 < n_q; q0 += tile_q) {
+    const int qc = min(tile_q, n_q - q0);
+    for (int v = 0; v < nv; ++v) {
+      accumulate_system<2, RM>(L, prm_var + (size_t)v * ldp_s, T, b, q, n_q, q0, qc, Fv + (size_t)v * tile_q, scratch,
+                               scratch_doubles, &S);
+    }
+    // weights, masks, transformed values
+    for (int i = tid; i < qc; i += EVAL_THREADS) {
+      const double Io = obs[q0 + i];
+      double w;
+      bool fit = fit_weight(O, q[q0 + i], Io, err, q0 + i, w);
+      const double I0v = Fv[i];
+      if (O.logI_weighted) fit = fit && (I0v > 0.0);
+      if (!fit) w = 0.0;
+      wts[i] = fit ? w : 0.0;
+      if (O.logI_weighted) {
+        fobs[i] = fit ? log(Io) : 0.0;
+        for (int v = 0; v < nv; ++v) {
+          const double x = Fv[(size_t)v * tile_q + i];
+          Fv[(size_t)v * tile_q + i] = (fit && x > 0.0) ? log(x) : NAN;
+        }
+      } else {
+        fobs[i] = Io;
+      }
+    }
+    __syncthreads();
+    // reductions: entry e of acc_sm handled by warp (e mod 8); lanes stride over the tile
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int e = warp; e < n_acc; e += EVAL_THREADS / 32) {
+      int j = -1, k = -1, kind;   // kind 0: JTJ(j,k)  1: JTr(j)  2: chi2 numerator  3: sum of weights
+      const int n_tri = nf * (nf + 1) / 2;
+      if (e < n_tri) {
+        kind = 0;
+        int r = e;
+        j = 0;
+        while (r >= nf - j) { r -= nf - j; ++j; }
+        k = j + r;
+      } else if (e < n_tri + nf) { kind = 1; j = e - n_tri; }
+      else if (e == n_tri + nf) kind = 2;
+      else kind = 3;
+      double sum = 0.0;
+      for (int i = lane; i < qc; i += 32) {
+        const double w = wts[i];
+        if (w == 0.0) continue;
+        const double f0 = Fv[i];
+        double term;
+        if (kind == 0) {
+          const double dj = Fv[(size_t)(j + 1) * tile_q + i] - f0, dk = Fv[(size_t)(k + 1) * tile_q + i] - f0;
+          term = (dj == dj && dk == dk) ? dj * dk : 0.0;
+        } else if (kind == 1) {
+          const double dj = Fv[(size_t)(j + 1) * tile_q + i] - f0;
+          term = (dj == dj) ? dj * (f0 - fobs[i]) : 0.0;
+        } else if (kind == 2) {
+          term = (f0 - fobs[i]) * (f0 - fobs[i]);
+        } else {
+          term = 1.0;
+        }
+        sum = fma(w, term, sum);
+      }
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) acc_sm[e] += sum;
+    }
+    __syncthreads();
+  }
+  // normalise by the sum of weights and the steps; write out (full symmetric JTJ)
+  const int n_tri = nf * (nf + 1) / 2;
+  const double sw = acc_sm[n_tri + nf + 1];
+  for (int e = tid; e < n_tri; e += EVAL_THREADS) {
+    int r = e, j = 0;
+    while (r >= nf - j) { r -= nf - j; ++j; }
+    const int k = j + r;
+    const double v = acc_sm[e] / (steps[j] * steps[k]) / sw;
+    JTJ[((size_t)b * nf + j) * nf + k] = v;
+    JTJ[((size_t)b * nf + k) * nf + j] = v;
+  }
+  if (tid < nf) JTr[(size_t)b * nf + tid] = acc_sm[n_tri + tid] / steps[tid] / sw;
+  if (tid == 0) chi2[b] = acc_sm[n_tri + nf] / sw;
+}
+
+// ---------------------------------------------------------------------------- LM algebra
+__global__ void lm_propose_kernel(const double *__restrict__ params, int ldp, int batch, const FreeSet F,
+                                  const double *__restrict__ JTJ, const double *__restrict__ JTr,
+                                  const double *__restrict__ lambda, const double *__restrict__ lo,
+                                  const double *__restrict__ hi, const uint8_t *__restrict__ active,
+                                  double *__restrict__ trial) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const int nf = F.n_free;
+  const double *p = params + (size_t)b * ldp;
+  double *t = trial + (size_t)b * ldp;
+  for (int k = 0; k < ldp; ++k) t[k] = p[k];
+  if (active && !active[b]) return;
+  double A[XRSD_MAX_FREE][XRSD_MAX_FREE], g[XRSD_MAX_FREE];
+  bool frozen[XRSD_MAX_FREE];
+  const double lam = lambda[b];
+  for (int j = 0; j < nf; ++j) {
+    g[j] = -JTr[(size_t)b * nf + j];
+    // a parameter sitting on a bound whose gradient pushes outward is held (projected LM)
+    const double pj = p[F.idx[j]];
+    const double l = lo[(size_t)b * nf + j], h = hi[(size_t)b * nf + j];
+    frozen[j] = (pj <= l && g[j] < 0.0) || (pj >= h && g[j] > 0.0);
+    for (int k = 0; k < nf; ++k) A[j][k] = JTJ[((size_t)b * nf + j) * nf + k];
+  }
+  for (int j = 0; j < nf; ++j) {
+    const double d = A[j][j];
+    A[j][j] = d + lam * (d > 0.0 ? d : 1.0);
+    if (frozen[j] || !(d > 0.0) || !(g[j] == g[j])) {
+      for (int k = 0; k < nf; ++k) { A[j][k] = 0.0; A[k][j] = 0.0; }
+      A[j][j] = 1.0;
+      g[j] = 0.0;
+    }
+  }
+  // Cholesky A = L L^T (in place, lower), then two triangular solves
+  bool ok = true;
+  for (int j = 0; j < nf && ok; ++j) {
+    double d = A[j][j];
+    for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k];
+    if (!(d > 0.0)) { ok = false; break; }
+    d = sqrt(d);
+    A[j][j] = d;
+    for (int i = j + 1; i < nf; ++i) {
+      double s = A[i][j];
+      for (int k = 0; k < j; ++k) s -= A[i][k] * A[j][k];
+      A[i][j] = s / d;
+    }
+  }
+  if (!ok) return;   // trial == params: the update kernel will raise lambda
+  for (int i = 0; i < nf; ++i) {
+    double s = g[i];
+    for (int k = 0; k < i; ++k) s -= A[i][k] * g[k];
+    g[i] = s / A[i][i];
+  }
+  for (int i = nf - 1; i >= 0; --i) {
+    double s = g[i];
+    for (int k = i + 1; k < nf; ++k) s -= A[k][i] * g[k];
+    g[i] = s / A[i][i];
+  }
+  for (int j = 0; j < nf; ++j) {
+    double v = p[F.idx[j]] + g[j];
+    const double l = lo[(size_t)b * nf + j], h = hi[(size_t)b * nf + j];
+    v = fmin(fmax(v, l), h);
+    if (v == v) t[F.idx[j]] = v;
+  }
+}
+
+__global__ void lm_update_kernel(double *__restrict__ params, int ldp, int batch, const double *__restrict__ trial,
+                                 double *__restrict__ chi2, const double *__restrict__ chi2_trial,
+                                 double *__restrict__ lambda, uint8_t *__restrict__ active, int *__restrict__ n_accept,
+                                 double up, double down, double ftol, double lambda_max) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  if (active && !active[b]) return;
+  const double c0 = chi2[b], c1 = chi2_trial[b];
+  if (c1 < c0) {   // false for NaN trials
+    for (int k = 0; k < ldp; ++k) params[(size_t)b * ldp + k] = trial[(size_t)b * ldp + k];
+    chi2[b] = c1;
+    lambda[b] = fmax(lambda[b] / down, 1.0e-12);
+    if (n_accept) n_accept[b] += 1;
+    if ((c0 - c1) <= ftol * c0 && active) active[b] = 0;
+  } else {
+    lambda[b] = lambda[b] * up;
+    if (lambda[b] > lambda_max && active) active[b] = 0;
+  }
+}
+
+}  // namespace xrsd
+
+using xrsd::FreeSet;
+
+extern "C" cudaError_t xrsd_launch_residual(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q,
+                                            int n_q, const double *d_params, int ldp, int batch,
+                                            const xrsd_tables_t *tables, const double *d_Iobs, const double *d_dI,
+                                            long long ld_obs, double *d_chi2, int scratch_doubles, int radial_multi,
+                                            cudaStream_t stream) {
+  using namespace xrsd;
+  const size_t smem = ((size_t)((n_q + 1) & ~1) + (size_t)scratch_doubles) * sizeof(double);
+  auto kern = radial_multi ? residual_kernel<true> : residual_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (batch <= 0) return cudaSuccess;
+  kern<<<batch, EVAL_THREADS, smem, stream>>>(*layout, *obj, d_q, n_q, d_params, ldp, batch, *tables, d_Iobs, d_dI, ld_obs,
+                                             d_chi2, scratch_doubles);
+  return cudaGetLastError();
+}
+
+extern "C" size_t xrsd_jacobian_smem(int n_params, int n_free, int tile_q, int scratch_doubles) {
+  const int ldp_s = (n_params + 1) & ~1;
+  return ((size_t)(n_free + 1) * ldp_s + (size_t)(n_free + 1) * tile_q + 2 * (size_t)tile_q + (size_t)scratch_doubles) *
+         sizeof(double);
+}
+
+extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q,
+                                            int n_q, const double *d_params, int ldp, int batch,
+                                            const xrsd_tables_t *tables, const double *d_Iobs, const double *d_dI,
+                                            long long ld_obs, const int32_t *free_idx, int n_free, double rel_step,
+                                            double *d_JTJ, double *d_JTr, double *d_chi2, int tile_q, int scratch_doubles,
+                                            int radial_multi, cudaStream_t stream) {
+  using namespace xrsd;
+  FreeSet F;
+  F.n_free = n_free;
+  for (int i = 0; i < XRSD_MAX_FREE; ++i) F.idx[i] = (i < n_free) ? free_idx[i] : 0;
+  const size_t smem = xrsd_jacobian_smem(layout->n_params, n_free, tile_q, scratch_doubles);
+  auto kern = radial_multi ? jacobian_kernel<true> : jacobian_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (batch <= 0) return cudaSuccess;
+  kern<<<batch, EVAL_THREADS, smem, stream>>>(*layout, *obj, d_q, n_q, d_params, ldp, batch, *tables, d_Iobs, d_dI, ld_obs, F,
+                                             rel_step, d_JTJ, d_JTr, d_chi2, tile_q, scratch_doubles);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t xrsd_launch_lm_propose(const double *d_params, int ldp, int batch, const int32_t *free_idx, int n_free,
+                                              const double *d_JTJ, const double *d_JTr, const double *d_lambda,
+                                              const double *d_lo, const double *d_hi, const uint8_t *d_active,
+                                              double *d_trial, cudaStream_t stream) {
+  FreeSet F;
+  F.n_free = n_free;
+  for (int i = 0; i < XRSD_MAX_FREE; ++i) F.idx[i] = (i < n_free) ? free_idx[i] : 0;
+  if (batch <= 0) return cudaSuccess;
+  xrsd::lm_propose_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(d_params, ldp, batch, F, d_JTJ, d_JTr, d_lambda, d_lo, d_hi,
+                                                                   d_active, d_trial);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t xrsd_launch_lm_update(double *d_params, int ldp, int batch, const double *d_trial, double *d_chi2,
+                                             const double *d_chi2_trial, double *d_lambda, uint8_t *d_active,
+                                             int *d_n_accept, double up, double down, double ftol, double lambda_max,
+                                             cudaStream_t stream) {
+  if (batch <= 0) return cudaSuccess;
+  xrsd::lm_update_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(d_params, ldp, batch, d_trial, d_chi2, d_chi2_trial,
+                                                                  d_lambda, d_active, d_n_accept, up, down, ftol, lambda_max);
+  return cudaGetLastError();
+}

@@ -1,0 +1,64 @@
+// intensity_kernel.cu -- batched I(q): grid = batch x q-tiles, one CTA per (system, q-span).
+// The pattern span is accumulated in shared memory by accumulate_system() and written
+// once, coalesced (8 B per (system, q) of HBM traffic; q and the parameter row are re-read
+// from L2).  Replaces System.compute_intensity, system/__init__.py:112-130.
+#include "system_eval.cuh"
+
+namespace xrsd {
+
+template <int QPT, bool RM>
+__global__ void __launch_bounds__(EVAL_THREADS, 2)
+intensity_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ q, int n_q,
+                 const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
+                 double *__restrict__ I_out, long long ldI, int q_per_cta, int n_tiles, int scratch_doubles) {
+  extern __shared__ __align__(16) double smem_d[];
+  __shared__ EvalShared S;
+  const long long bid = blockIdx.x;
+  const int b = (int)(bid / n_tiles);
+  const int tile = (int)(bid - (long long)b * n_tiles);
+  if (b >= batch) return;
+  const int q_begin = tile * q_per_cta;
+  const int q_count = min(q_per_cta, n_q - q_begin);
+  double *I_sm = smem_d;
+  double *scratch = smem_d + ((q_per_cta + 1) & ~1);
+  accumulate_system<QPT, RM>(L, params + (size_t)b * ldp, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S);
+  double *dst = I_out + (size_t)b * ldI + q_begin;
+  for (int i = threadIdx.x; i < q_count; i += EVAL_THREADS) dst[i] = I_sm[i];
+}
+
+// DFMA-bound probe: 8 independent chains per thread, 4096 DFMA each
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+  double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 123.456) out[0] = s;
+}
+
+}  // namespace xrsd
+
+extern "C" cudaError_t xrsd_launch_intensity(const xrsd_layout_t *layout, const double *d_q, int n_q, const double *d_params,
+                                             int ldp, int batch, const xrsd_tables_t *tables, double *d_I, long long ldI,
+                                             int q_per_cta, int scratch_doubles, int radial_multi, cudaStream_t stream) {
+  using namespace xrsd;
+  const int n_tiles = (n_q + q_per_cta - 1) / q_per_cta;
+  const size_t smem = ((size_t)((q_per_cta + 1) & ~1) + (size_t)scratch_doubles) * sizeof(double);
+  auto kern = radial_multi ? intensity_kernel<2, true> : intensity_kernel<2, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long long n_blocks = (long long)batch * n_tiles;
+  if (n_blocks <= 0) return cudaSuccess;
+  if (n_blocks > 2147483647LL) return cudaErrorInvalidConfiguration;
+  kern<<<(unsigned)n_blocks, EVAL_THREADS, smem, stream>>>(*layout, d_q, n_q, d_params, ldp, batch, *tables, d_I, ldI,
+                                                          q_per_cta, n_tiles, scratch_doubles);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t xrsd_launch_fp64_probe(double *d_out, int blocks, int iters, cudaStream_t stream) {
+  xrsd::fp64_probe_kernel<<<blocks, 256, 0, stream>>>(d_out, iters);
+  return cudaGetLastError();
+}

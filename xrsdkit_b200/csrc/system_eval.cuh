@@ -1,0 +1,383 @@
+// system_eval.cuh -- I(q) of one system (noise model + populations) for a span of q held
+// by one CTA, accumulated into a shared-memory pattern buffer.
+//
+// Replaces System.compute_intensity (system/__init__.py:112-130) and everything below it:
+//   system/noise.py:50-63, scattering/__init__.py:12-66 (dispatcher), :69-108 (Guinier-Porod),
+//   :111-161 (normal size distribution), :286-333 (per-reflection factors, profiles, sum),
+//   scattering/structure_factors.py:3-47, scattering/form_factors.py:8-28,
+//   tools/peak_math.py:24-47.
+//
+// One CTA owns q[q_begin, q_begin+q_count) of system b.  Populations are processed in
+// layout order (the reference's dict order), each in two steps: a cooperative prologue
+// that stages what depends on the parameters only (size quadrature, shell weights,
+// Voigt constants, the I(0) normalisation) in shared memory, then a loop in which each
+// thread evaluates QPT q-points against the staged table.
+//
+// Hot loops:
+//  * r_normal: radii are equally spaced, so sin/cos(q r_i) are advanced by a rotation
+//    (4 DP ops) instead of a sincos per (q, r); for x = q r < 0.5, where the closed form
+//    cancels, the Maclaurin series is used instead (forms.cuh).  Weights carry 1/r^6 so
+//    the loop has no division: 8 DP instructions per (q, r) pair.
+//  * crystalline: sum over |G|-shells of W_s * profile(q - q_s); Voigt via faddeeva.cuh.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "../../include/xrsd_b200.h"
+#include "faddeeva.cuh"
+#include "forms.cuh"
+#include "lattice.cuh"
+
+namespace xrsd {
+
+constexpr int EVAL_THREADS = 256;
+constexpr int SHELL_CHUNK = 128;
+
+// shared-memory working set of one CTA (besides the pattern buffer)
+struct EvalShared {
+  VoigtConst vc;
+  Cell cell;
+  double red[EVAL_THREADS / 32];
+  double bcast[4];
+  int ibcast[4];
+};
+
+__device__ __forceinline__ double block_sum(double v, EvalShared *S) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) S->red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < EVAL_THREADS / 32; ++w) t += S->red[w];
+  return t;
+}
+
+// peak profiles: tools/peak_math.py:24-47
+struct Profile {
+  int kind;
+  double h;          // gaussian / lorentzian hwhm
+  double sigma;      // voigt
+  double norm;       // gaussian: sqrt(ln2/pi)/h
+};
+
+__device__ __forceinline__ double profile_eval(const Profile &P, const VoigtConst *vc, double x) {
+  if (P.kind == XRSD_PROFILE_VOIGT) {
+    const double zr = x / P.sigma / M_SQRT2;                       // (x + i gamma)/sigma/sqrt(2)
+    return rew(zr, vc) / P.sigma / 2.5066282746310002;             // /sigma/sqrt(2 pi)
+  } else if (P.kind == XRSD_PROFILE_GAUSSIAN) {
+    const double u = x / P.h;
+    return P.norm * exp(-(u * u) * 0.6931471805599453);            // exp(-(x/h)**2 * ln 2)
+  }
+  return P.h / M_PI / (x * x + P.h * P.h);
+}
+
+// form factor of species `a` of a crystalline population at q
+__device__ __forceinline__ double species_ff(const xrsd_pop_t &pop, int a, const double *prm, double q) {
+  if (pop.species_form[a] == XRSD_FORM_SPHERE) return sphere_ff(q, prm[pop.p_r]);   // q == 0 -> NaN, as the reference
+  return atomic_ff(q, pop.atom_Z[a], pop.atom_a[a], pop.atom_b[a]);
+}
+
+__device__ __forceinline__ int pair_index(int n_sp, int a, int b) { return a * n_sp - a * (a - 1) / 2 + (b - a); }
+
+// ------------------------------------------------------------------------------------------
+// Accumulate I(q) of system `b` for q[q_begin .. q_begin+q_count) into I_sm[0 .. q_count).
+// All EVAL_THREADS threads of the CTA must call this.  `scratch` holds scratch_doubles doubles.
+// ------------------------------------------------------------------------------------------
+template <int QPT, bool RADIAL_MULTI>
+__device__ void accumulate_system(const xrsd_layout_t &L, const double *__restrict__ prm, const xrsd_tables_t &T, int b,
+                                  const double *__restrict__ q, int n_q, int q_begin, int q_count,
+                                  double *__restrict__ I_sm, double *__restrict__ scratch, int scratch_doubles,
+                                  EvalShared *S) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < q_count; i += EVAL_THREADS) I_sm[i] = 0.0;
+  const int span = EVAL_THREADS * QPT;
+
+  for (int ip = 0; ip < L.n_pops; ++ip) {
+    const xrsd_pop_t &pop = L.pops[ip];
+    __syncthreads();
+    switch (pop.kind) {
+      // ---------------------------------------------------------------- noise (system/noise.py:50-63)
+      case XRSD_POP_NOISE_FLAT: {
+        const double I0 = prm[pop.p_I0];
+        for (int i = tid; i < q_count; i += EVAL_THREADS) I_sm[i] += I0 * 1.0;
+      } break;
+      case XRSD_POP_NOISE_LOW_Q: {
+        const double I0 = prm[pop.p_I0], f = prm[pop.p_flat_fraction];
+        const double beam = I0 * (1.0 - f);
+        const GPConst gp = gp_constants(prm[pop.p_rg], prm[pop.p_D]);
+        for (int i = tid; i < q_count; i += EVAL_THREADS) {
+          double v = I_sm[i];
+          v += beam * guinier_porod(q[q_begin + i], gp);
+          v += I0 * f * 1.0;
+          I_sm[i] = v;
+        }
+      } break;
+      // ---------------------------------------------------------------- diffuse / disordered
+      case XRSD_POP_NONCRYSTALLINE: {
+        const double I0 = prm[pop.p_I0];
+        HSConst hs;
+        if (pop.disordered) hs = hs_constants(prm[pop.p_r_hard], prm[pop.p_v_fraction]);
+        GPConst gp;
+        if (pop.form == XRSD_FORM_GUINIER_POROD) gp = gp_constants(prm[pop.p_rg], prm[pop.p_D]);
+        // size quadrature prologue (scattering/__init__.py:148-160, tools/__init__.py:168-173)
+        bool quad = false;
+        int n_r = 0;
+        double r0 = 0.0, dstep = 0.0, norm = 1.0, r_first = 0.0;
+        if (pop.form == XRSD_FORM_SPHERE || pop.form == XRSD_FORM_SPHERE_R_NORMAL) r0 = prm[pop.p_r];
+        if (pop.form == XRSD_FORM_SPHERE_R_NORMAL) {
+          const double sigma = prm[pop.p_sigma];
+          if (!(sigma < 1.0e-9)) {
+            quad = true;
+            // unfused arithmetic: a fused multiply-add here can flip ceil() and change the
+            // number of radii relative to numpy (tools/__init__.py:168-173, np.arange)
+            const double sigma_r = __dmul_rn(sigma, r0);
+            const double dr = __dmul_rn(sigma_r, pop.sampling_step);
+            const double r_min = fmax(__dsub_rn(r0, __dmul_rn(pop.sampling_width, sigma_r)), dr);
+            const double r_max = __dadd_rn(r0, __dmul_rn(pop.sampling_width, sigma_r));
+            // numpy.arange(r_min, r_max, dr): len = ceil((stop-start)/step), r_i = start + i*((start+step)-start)
+            const double len = ceil(__dsub_rn(r_max, r_min) / dr);
+            n_r = (len > 0.0) ? (int)fmin(len, (double)(scratch_doubles / 2)) : 0;
+            dstep = __dsub_rn(__dadd_rn(r_min, dr), r_min);
+            r_first = r_min;
+            const double two_s2 = 2.0 * (sigma_r * sigma_r);
+            double part = 0.0;
+            for (int i = tid; i < n_r; i += EVAL_THREADS) {
+              const double ri = __dadd_rn(r_min, __dmul_rn((double)i, dstep));   // unfused, as numpy.arange
+              const double rho = exp(-1.0 * ((r0 - ri) * (r0 - ri)) / two_s2);
+              scratch[2 * i] = ri;
+              scratch[2 * i + 1] = rho;
+              const double r3 = ri * ri * ri;
+              part += rho * (r3 * r3);
+            }
+            norm = block_sum(part, S);     // sum_i rho_i r_i^6  (common factors of I0_i cancel)
+          }
+        }
+        __syncthreads();
+        for (int off = 0; off < q_count; off += span) {
+          double qv[QPT], ff2[QPT];
+          bool ok[QPT], q0[QPT];
+#pragma unroll
+          for (int j = 0; j < QPT; ++j) {
+            const int i = off + tid + j * EVAL_THREADS;
+            ok[j] = i < q_count;
+            qv[j] = q[q_begin + (ok[j] ? i : q_count - 1)];
+            q0[j] = L.q0_is_zero && (q_begin + i == 0);
+            ff2[j] = 0.0;
+          }
+          if (pop.form == XRSD_FORM_ATOMIC) {
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) ff2[j] = sqr(atomic_ff(qv[j], pop.atom_Z[0], pop.atom_a[0], pop.atom_b[0]));
+          } else if (pop.form == XRSD_FORM_GUINIER_POROD) {
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) ff2[j] = guinier_porod(qv[j], gp);
+          } else if (!quad) {
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) ff2[j] = q0[j] ? 1.0 : sqr(sphere_ff(qv[j], r0));
+          } else {
+            // rotation recurrence over the radius grid
+            double s[QPT], c[QPT], sd[QPT], cd[QPT], acc[QPT];
+            double qmin_t = qv[0];
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) {
+              sincos(qv[j] * r_first, &s[j], &c[j]);
+              sincos(qv[j] * dstep, &sd[j], &cd[j]);
+              acc[j] = 0.0;
+              qmin_t = fmin(qmin_t, qv[j]);
+            }
+            for (int o = 16; o > 0; o >>= 1) qmin_t = fmin(qmin_t, __shfl_xor_sync(0xffffffffu, qmin_t, o));
+            int i = 0;
+            // phase A: some lane of the warp still has x < 0.5 -> series where needed
+            for (; i < n_r; ++i) {
+              const double ri = scratch[2 * i], rho = scratch[2 * i + 1];
+              if (!(qmin_t * ri < 0.5)) break;
+#pragma unroll
+              for (int j = 0; j < QPT; ++j) {
+                const double x = qv[j] * ri;
+                double t = fma(-x, c[j], s[j]);
+                if (x < 0.5) t = sphere_t_series(x);
+                acc[j] = fma(rho, t * t, acc[j]);
+                const double sn = fma(s[j], cd[j], c[j] * sd[j]);
+                c[j] = fma(c[j], cd[j], -(s[j] * sd[j]));
+                s[j] = sn;
+              }
+            }
+            // phase B: pure recurrence, 8 DP instructions per (q, r)
+#pragma unroll 2
+            for (; i < n_r; ++i) {
+              const double2 rr = *reinterpret_cast<const double2 *>(scratch + 2 * i);
+#pragma unroll
+              for (int j = 0; j < QPT; ++j) {
+                const double x = qv[j] * rr.x;
+                const double t = fma(-x, c[j], s[j]);
+                acc[j] = fma(rr.y, t * t, acc[j]);
+                const double sn = fma(s[j], cd[j], c[j] * sd[j]);
+                c[j] = fma(c[j], cd[j], -(s[j] * sd[j]));
+                s[j] = sn;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) {
+              const double q2 = qv[j] * qv[j];
+              ff2[j] = q0[j] ? 1.0 : 9.0 * acc[j] / ((q2 * q2 * q2) * norm);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < QPT; ++j) {
+            if (!ok[j]) continue;
+            const int i = off + tid + j * EVAL_THREADS;
+            double v;
+            if (pop.disordered) v = I0 * hard_sphere_sf(qv[j], hs, q0[j]) * ff2[j];   // I0 * sf * ff_sqr
+            else v = I0 * ff2[j];
+            I_sm[i] += v;
+          }
+        }
+      } break;
+      // ---------------------------------------------------------------- crystalline
+      case XRSD_POP_CRYSTALLINE: {
+        const int t = b * L.n_xtal + pop.table_slot;
+        const int n_shell = T.n_shell[t];
+        if (n_shell <= 0) break;                                   // scattering/__init__.py:277-278
+        const int n_sp = pop.n_species;
+        const int n_pairs = n_sp * (n_sp + 1) / 2;
+        const int32_t *sh_hkl = T.shell_hkl + (size_t)t * T.cap_shell * 4;
+        const double *sh_geo = T.shell_geo + (size_t)t * T.cap_shell * T.n_pairs_max;
+        const double wl = L.wavelength;
+        const bool radial = pop.sf_radial != 0;
+        const bool radial_multi = RADIAL_MULTI && radial && n_sp > 1;
+        Profile P;
+        P.kind = pop.profile;
+        P.h = 0.0; P.sigma = 1.0; P.norm = 0.0;
+        if (tid == 0) make_cell(pop, prm, &S->cell);
+        if (P.kind == XRSD_PROFILE_VOIGT) {
+          const double hg = prm[pop.p_hwhm_g], hl = prm[pop.p_hwhm_l];
+          P.sigma = hg / 1.1774100225154747;                        // sqrt(2 ln 2)
+          voigt_constants(&S->vc, hl / P.sigma / M_SQRT2, tid);
+        } else {
+          P.h = prm[pop.p_hwhm];
+          P.norm = 0.46971863934982566 / P.h;                       // sqrt(ln2/pi)/h
+        }
+        __syncthreads();
+        // pass A: normalisation I(0) = sum_s W0_s * profile(0 - q_s)   (scattering/__init__.py:305,331)
+        double part = 0.0;
+        for (int s = tid; s < n_shell; s += EVAL_THREADS) {
+          const double qs = 2.0 * M_PI * g_norm(S->cell.b, (double)sh_hkl[4 * s], (double)sh_hkl[4 * s + 1], (double)sh_hkl[4 * s + 2]);
+          double ltz = 1.0;
+          if (pop.lorentz) {
+            const double th = asin(wl * qs / (4.0 * M_PI));
+            ltz = 1.0 / (sin(th) * sin(2.0 * th));
+          }
+          double w0 = 0.0;
+          int ipq = 0;
+          for (int a = 0; a < n_sp; ++a)
+            for (int bb = a; bb < n_sp; ++bb, ++ipq) w0 += ((a == bb) ? 1.0 : 2.0) * sh_geo[(size_t)s * T.n_pairs_max + ipq];
+          part += ltz * w0 * profile_eval(P, &S->vc, 0.0 - qs);
+        }
+        const double norm = block_sum(part, S);
+        // pass B: chunks of shells staged as (q_s, W_s[...]) in scratch
+        const int wstride = radial_multi ? n_pairs : 1;
+        const int rec = 1 + wstride;
+        int chunk = scratch_doubles / rec;
+        if (chunk > SHELL_CHUNK) chunk = SHELL_CHUNK;
+        for (int off = 0; off < q_count; off += span) {
+          double qv[QPT], acc[QPT];
+          double accp[QPT][RADIAL_MULTI ? XRSD_MAX_PAIRS : 1];
+          bool ok[QPT];
+#pragma unroll
+          for (int j = 0; j < QPT; ++j) {
+            const int i = off + tid + j * EVAL_THREADS;
+            ok[j] = i < q_count;
+            qv[j] = q[q_begin + (ok[j] ? i : q_count - 1)];
+            acc[j] = 0.0;
+          }
+#pragma unroll
+          for (int j = 0; j < QPT; ++j)
+#pragma unroll
+            for (int k = 0; k < (RADIAL_MULTI ? XRSD_MAX_PAIRS : 1); ++k) accp[j][k] = 0.0;
+          for (int s0 = 0; s0 < n_shell; s0 += chunk) {
+            const int ns = min(chunk, n_shell - s0);
+            __syncthreads();
+            for (int sl = tid; sl < ns; sl += EVAL_THREADS) {
+              const int s = s0 + sl;
+              const double qs = 2.0 * M_PI * g_norm(S->cell.b, (double)sh_hkl[4 * s], (double)sh_hkl[4 * s + 1], (double)sh_hkl[4 * s + 2]);
+              double ltz = 1.0;
+              if (pop.lorentz) {
+                const double th = asin(wl * qs / (4.0 * M_PI));
+                ltz = 1.0 / (sin(th) * sin(2.0 * th));
+              }
+              scratch[sl * rec] = qs;
+              if (radial_multi) {
+                int ipq = 0;
+                for (int a = 0; a < n_sp; ++a)
+                  for (int bb = a; bb < n_sp; ++bb, ++ipq)
+                    scratch[sl * rec + 1 + ipq] = ltz * ((a == bb) ? 1.0 : 2.0) * sh_geo[(size_t)s * T.n_pairs_max + ipq];
+              } else if (radial) {
+                scratch[sl * rec + 1] = ltz * sh_geo[(size_t)s * T.n_pairs_max];
+              } else {
+                double ffs[XRSD_MAX_SPECIES];
+                for (int a = 0; a < n_sp; ++a) ffs[a] = species_ff(pop, a, prm, qs);
+                double w = 0.0;
+                int ipq = 0;
+                for (int a = 0; a < n_sp; ++a)
+                  for (int bb = a; bb < n_sp; ++bb, ++ipq)
+                    w += ((a == bb) ? 1.0 : 2.0) * ffs[a] * ffs[bb] * sh_geo[(size_t)s * T.n_pairs_max + ipq];
+                scratch[sl * rec + 1] = ltz * w;
+              }
+            }
+            __syncthreads();
+            if (!radial_multi) {
+              for (int sl = 0; sl < ns; ++sl) {
+                const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
+#pragma unroll
+                for (int j = 0; j < QPT; ++j) acc[j] = fma(sw.y, profile_eval(P, &S->vc, qv[j] - sw.x), acc[j]);
+              }
+            } else {
+              for (int sl = 0; sl < ns; ++sl) {
+                const double qs = scratch[sl * rec];
+#pragma unroll
+                for (int j = 0; j < QPT; ++j) {
+                  const double v = profile_eval(P, &S->vc, qv[j] - qs);
+#pragma unroll
+                  for (int k = 0; k < (RADIAL_MULTI ? XRSD_MAX_PAIRS : 1); ++k)
+                    if (k < n_pairs) accp[j][k] = fma(scratch[sl * rec + 1 + k], v, accp[j][k]);
+                }
+              }
+            }
+          }
+          const double I0 = prm[pop.p_I0];
+#pragma unroll
+          for (int j = 0; j < QPT; ++j) {
+            if (!ok[j]) continue;
+            const int i = off + tid + j * EVAL_THREADS;
+            double a_sum = acc[j];
+            if (radial) {
+              double ffq[XRSD_MAX_SPECIES];
+              const bool q0 = L.q0_is_zero && (q_begin + i == 0);
+              for (int a = 0; a < n_sp; ++a) ffq[a] = (q0 && pop.species_form[a] == XRSD_FORM_SPHERE) ? 1.0 : species_ff(pop, a, prm, qv[j]);
+              if (radial_multi) {
+                a_sum = 0.0;
+#pragma unroll
+                for (int a = 0; a < XRSD_MAX_SPECIES; ++a)
+#pragma unroll
+                  for (int bb = a; bb < XRSD_MAX_SPECIES; ++bb)
+                    if (RADIAL_MULTI && bb < n_sp) a_sum += ffq[a] * ffq[bb] * accp[j][RADIAL_MULTI ? pair_index(n_sp, a, bb) : 0];
+              } else {
+                a_sum = acc[j] * (ffq[0] * ffq[0]);
+              }
+            }
+            double pz = 1.0;
+            if (pop.polz) {
+              const double th = asin(wl * qv[j] / (4.0 * M_PI));
+              const double c2 = cos(2.0 * th);
+              pz = 0.5 * (1.0 + c2 * c2);
+            }
+            I_sm[i] += I0 * (pz * a_sum / norm);                   // I0 * (pz*I/I0_norm)
+          }
+        }
+      } break;
+      default: break;
+    }
+  }
+  __syncthreads();
+}
+
+}  // namespace xrsd

@@ -1,0 +1,395 @@
+// table_kernel.cu -- reflection-table builder (one CTA per crystalline population of
+// one system of the batch), everything in shared memory.
+//
+// Replaces, bit-exactly on the hkl / multiplicity lists:
+//   scattering/__init__.py:248-278   hkl enumeration in the G_min < |G| <= G_max shell
+//   scattering/symmetries.py:44-92   greedy, order-dependent mirror reduction
+// and precomputes the parameter-independent part of scattering/__init__.py:307-331:
+// reflections are merged into shells of equal |G| and each shell carries
+// sum_hkl mult * Re(G_a conj G_b), G_a = sum_sites exp(2 pi i (site + xyz_a).hkl).
+//
+// The reference forms an N x N distance matrix per operation and takes the row-wise
+// argmin.  Every operation is an involutive signed permutation, so the only candidate
+// that can pass the `dist < symprec` test is the lattice point nearest to op.p_i, found
+// here by mapping back to integer hkl (O(N) per operation instead of O(N^2)); the
+// distance itself is then evaluated exactly as the reference does.  Points are kept on
+// the dense (2n1-1)(2n2-1)(2n3-1) candidate box as uint16 multiplicities (0 = absent),
+// which also preserves the reference's l-outer / k / h-inner ordering for free.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "lattice.cuh"
+
+namespace xrsd {
+
+constexpr int TABLE_THREADS = 256;
+
+struct TableShared {
+  Cell cell;
+  double g_min, g_max;
+  int n[3];
+  int dim[3];          // 2n-1
+  int cells;
+  int n_all, n_red, n_shell_raw, n_shell;
+  int hmin[3], hmax[3];
+  int status;
+  int scan_carry;
+  double max_geo;
+  int warp_tmp[TABLE_THREADS / 32];
+};
+
+__device__ __forceinline__ void cell_to_hkl(const TableShared &S, int c, int &h, int &k, int &l) {
+  const int d0 = S.dim[0], d1 = S.dim[1];
+  h = c % d0 - (S.n[0] - 1);
+  k = (c / d0) % d1 - (S.n[1] - 1);
+  l = c / (d0 * d1) - (S.n[2] - 1);
+}
+
+__device__ __forceinline__ int hkl_to_cell(const TableShared &S, int h, int k, int l) {
+  const int ih = h + S.n[0] - 1, ik = k + S.n[1] - 1, il = l + S.n[2] - 1;
+  if (ih < 0 || ih >= S.dim[0] || ik < 0 || ik >= S.dim[1] || il < 0 || il >= S.dim[2]) return -1;
+  return (il * S.dim[1] + ik) * S.dim[0] + ih;
+}
+
+// block-wide exclusive scan of one flag per thread; returns this thread's offset and adds the
+// block total to S.scan_carry (which callers read as the running base).
+__device__ __forceinline__ int block_flag_scan(TableShared &S, bool flag, int &base_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  const int within = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) S.warp_tmp[warp] = __popc(bal);
+  __syncthreads();
+  int wbase = 0, total = 0;
+  for (int w = 0; w < TABLE_THREADS / 32; ++w) {
+    const int c = S.warp_tmp[w];
+    if (w < warp) wbase += c;
+    total += c;
+  }
+  base_out = S.scan_carry;
+  __syncthreads();
+  if (threadIdx.x == 0) S.scan_carry += total;
+  __syncthreads();
+  return wbase + within;
+}
+
+__global__ void __launch_bounds__(TABLE_THREADS)
+reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ params, int ldp,
+                        int batch, const xrsd_tables_t T, int max_cells, int cap_list) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ TableShared S;
+
+  const int t = blockIdx.x;
+  const int b = t / L.n_xtal;
+  const int slot = t - b * L.n_xtal;
+  if (b >= batch) return;
+  int ipop = -1;
+  for (int i = 0; i < L.n_pops; ++i)
+    if (L.pops[i].kind == XRSD_POP_CRYSTALLINE && L.pops[i].table_slot == slot) ipop = i;
+  if (ipop < 0) return;
+  const xrsd_pop_t &pop = L.pops[ipop];
+  const double *prm = params + (size_t)b * ldp;
+  const int tid = threadIdx.x;
+
+  // shared-memory carve-up
+  uint16_t *grid = reinterpret_cast<uint16_t *>(smem_raw);
+  size_t off = ((size_t)max_cells * sizeof(uint16_t) + 15) & ~(size_t)15;
+  double *keys = reinterpret_cast<double *>(smem_raw + off);
+  off += (size_t)cap_list * sizeof(double);
+  int *list_cell = reinterpret_cast<int *>(smem_raw + off);
+  off += (size_t)cap_list * sizeof(int);
+  int *sidx = reinterpret_cast<int *>(smem_raw + off);
+  off += (size_t)cap_list * sizeof(int);
+  int *seg_start = reinterpret_cast<int *>(smem_raw + off);   // [cap_list + 1]
+
+  if (tid == 0) {
+    make_cell(pop, prm, &S.cell);
+    // scattering/__init__.py:248-268
+    const double q_max = pop.q_max, q_min = pop.q_min;
+    const double d_min = 2.0 * M_PI / q_max;
+    S.g_max = 1.0 / d_min;
+    S.g_min = 0.0;
+    if (q_min > 0.0) {
+      const double d_max = 2.0 * M_PI / q_min;
+      S.g_min = 1.0 / d_max;
+    }
+    int st = 0;
+    long long cells = 1;
+    for (int i = 0; i < 3; ++i) {
+      const double *a = S.cell.a[i];
+      const double *bb = S.cell.b[i];
+      const double absa = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+      const double bdota = bb[0] * a[0] + bb[1] * a[1] + bb[2] * a[2];
+      const double nf = ceil(S.g_max * absa / bdota);
+      if (!(nf >= 1.0) || !(nf < 1.0e4)) { st |= XRSD_TABLE_BAD_LATTICE; S.n[i] = 1; }
+      else S.n[i] = (int)nf;
+      S.dim[i] = 2 * S.n[i] - 1;
+      cells *= S.dim[i];
+    }
+    if (cells > (long long)max_cells) { st |= XRSD_TABLE_GRID_OVERFLOW; cells = 0; }
+    S.cells = (int)cells;
+    S.status = st;
+    S.n_all = 0; S.n_red = 0; S.n_shell_raw = 0; S.n_shell = 0;
+    for (int i = 0; i < 3; ++i) { S.hmin[i] = 1 << 30; S.hmax[i] = -(1 << 30); }
+    S.scan_carry = 0;
+    S.max_geo = 0.0;
+  }
+  __syncthreads();
+
+  auto finish = [&](int n_shell) {
+    if (tid == 0) {
+      T.n_shell[t] = n_shell;
+      T.n_refl[t] = S.n_red;
+      T.n_all[t] = S.n_all;
+      T.status[t] = S.status;
+    }
+  };
+  if (S.status != 0) { finish(0); return; }
+
+  // ---- 1. candidates in the shell G_min < |G| <= G_max (scattering/__init__.py:275-276)
+  {
+    int cnt = 0, lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-(1 << 30), -(1 << 30), -(1 << 30)};
+    for (int c = tid; c < S.cells; c += TABLE_THREADS) {
+      int h, k, l;
+      cell_to_hkl(S, c, h, k, l);
+      const double g = g_norm(S.cell.b, (double)h, (double)k, (double)l);
+      const bool in = (S.g_min < g) && (g <= S.g_max);
+      grid[c] = in ? 1 : 0;
+      if (in) {
+        ++cnt;
+        lo[0] = min(lo[0], h); hi[0] = max(hi[0], h);
+        lo[1] = min(lo[1], k); hi[1] = max(hi[1], k);
+        lo[2] = min(lo[2], l); hi[2] = max(hi[2], l);
+      }
+    }
+    if (cnt) {
+      atomicAdd(&S.n_all, cnt);
+      for (int i = 0; i < 3; ++i) { atomicMin(&S.hmin[i], lo[i]); atomicMax(&S.hmax[i], hi[i]); }
+    }
+  }
+  __syncthreads();
+  if (S.n_all == 0) { finish(0); return; }   // scattering/__init__.py:277-278 -> zeros
+
+  // ---- 2. greedy reduction, one operation after the other (scattering/symmetries.py:61-90)
+  if (pop.use_symmetry) {
+    const int rk = S.hmax[1] - S.hmin[1] + 1, rl = S.hmax[2] - S.hmin[2] + 1;   // symmetries.py:54-55
+    for (int iop = 0; iop < pop.n_ops; ++iop) {
+      int perm[3];
+      double sgn[3];
+      sym_op(pop.ops[iop], perm, sgn);
+      for (int c = tid; c < S.cells; c += TABLE_THREADS) {
+        const unsigned mi = grid[c];
+        if (!mi) continue;
+        int h, k, l;
+        cell_to_hkl(S, c, h, k, l);
+        // lat_pts = all_hkl . rlat^T  (symmetries.py:52): p_m = b_m . (h,k,l)
+        double p[3], s[3];
+        for (int m = 0; m < 3; ++m)
+          p[m] = (double)h * S.cell.b[m][0] + (double)k * S.cell.b[m][1] + (double)l * S.cell.b[m][2];
+        for (int m = 0; m < 3; ++m) s[m] = sgn[m] * p[perm[m]];
+        // nearest lattice point to op.p_i: hkl_j = rlat^-1 s = A^T s
+        int hj[3];
+        for (int n = 0; n < 3; ++n)
+          hj[n] = (int)rint(S.cell.a[0][n] * s[0] + S.cell.a[1][n] * s[1] + S.cell.a[2][n] * s[2]);
+        const int cj = hkl_to_cell(S, hj[0], hj[1], hj[2]);
+        if (cj < 0 || cj == c) continue;
+        if (!grid[cj]) continue;
+        // distance |p_i - op.p_j| (symmetries.py:62-72)
+        double pj[3], d2 = 0.0;
+        for (int m = 0; m < 3; ++m)
+          pj[m] = (double)hj[0] * S.cell.b[m][0] + (double)hj[1] * S.cell.b[m][1] + (double)hj[2] * S.cell.b[m][2];
+        for (int m = 0; m < 3; ++m) {
+          const double df = p[m] - sgn[m] * pj[perm[m]];
+          d2 += df * df;
+        }
+        if (!(sqrt(d2) < 1.0e-6)) continue;
+        const int rank_i = (h * rk + k) * rl + l;
+        const int rank_j = (hj[0] * rk + hj[1]) * rl + hj[2];
+        if (rank_i < rank_j) {
+          // j keeps the point and collects i's multiplicity.  j cannot be dropped by this same
+          // operation (its image is i, of lower rank), and only i's thread writes grid[cj].
+          grid[cj] = (uint16_t)(grid[cj] + mi);
+          grid[c] = 0;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- 3. ordered compaction (l outer, k, h inner = cell order)
+  {
+    int32_t *out_refl = (T.refl_hkl && T.cap_refl > 0) ? T.refl_hkl + (size_t)t * T.cap_refl * 4 : nullptr;
+    for (int c0 = 0; c0 < S.cells; c0 += TABLE_THREADS) {
+      const int c = c0 + tid;
+      const unsigned m = (c < S.cells) ? grid[c] : 0u;
+      int base;
+      const int pos = block_flag_scan(S, m != 0, base) + base;
+      if (m) {
+        if (pos < cap_list) list_cell[pos] = c;
+        if (out_refl && pos < T.cap_refl) {
+          int h, k, l;
+          cell_to_hkl(S, c, h, k, l);
+          out_refl[pos * 4 + 0] = h; out_refl[pos * 4 + 1] = k; out_refl[pos * 4 + 2] = l; out_refl[pos * 4 + 3] = (int)m;
+        }
+      }
+    }
+    if (tid == 0) {
+      S.n_red = S.scan_carry;
+      S.scan_carry = 0;
+      if (S.n_red > cap_list) S.status |= XRSD_TABLE_LIST_OVERFLOW;
+    }
+    __syncthreads();
+    if (S.status != 0) { finish(0); return; }
+  }
+  const int n_red = S.n_red;
+
+  // ---- 4. sort reduced reflections by |G| (bitonic, shared memory)
+  int npow = 1;
+  while (npow < n_red) npow <<= 1;
+  for (int r = tid; r < npow; r += TABLE_THREADS) {
+    if (r < n_red) {
+      int h, k, l;
+      cell_to_hkl(S, list_cell[r], h, k, l);
+      keys[r] = g_norm(S.cell.b, (double)h, (double)k, (double)l);
+      sidx[r] = r;
+    } else {
+      keys[r] = INFINITY;
+      sidx[r] = r;
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= npow; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < npow / 2; i += TABLE_THREADS) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const double ka = keys[lo], kb = keys[hi];
+        const int ia = sidx[lo], ib = sidx[hi];
+        const bool gt = (ka > kb) || (ka == kb && ia > ib);
+        if (gt == up) { keys[lo] = kb; keys[hi] = ka; sidx[lo] = ib; sidx[hi] = ia; }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- 5. shells: runs of (numerically) equal |G|
+  for (int r0 = 0; r0 < n_red; r0 += TABLE_THREADS) {
+    const int r = r0 + tid;
+    bool head = false;
+    if (r < n_red) head = (r == 0) || (keys[r] - keys[r - 1] > 8.9e-16 * keys[r]);
+    int base;
+    const int pos = block_flag_scan(S, head, base) + base;
+    if (head && pos < cap_list) seg_start[pos] = r;
+  }
+  if (tid == 0) {
+    S.n_shell_raw = S.scan_carry;
+    S.scan_carry = 0;
+    if (S.n_shell_raw > T.cap_shell) S.status |= XRSD_TABLE_SHELL_OVERFLOW;
+    else seg_start[S.n_shell_raw] = n_red;
+  }
+  __syncthreads();
+  if (S.status != 0) { finish(0); return; }
+  const int n_raw = S.n_shell_raw;
+  const int n_sp = pop.n_species;
+  const int n_pairs = n_sp * (n_sp + 1) / 2;
+  int32_t *o_hkl = T.shell_hkl + (size_t)t * T.cap_shell * 4;
+  double *o_geo = T.shell_geo + (size_t)t * T.cap_shell * T.n_pairs_max;
+
+  // per-shell geometric weights: sum_members mult * Re(G_a conj G_b)  (scattering/__init__.py:312-331)
+  double my_max = 0.0;
+  for (int s = tid; s < n_raw; s += TABLE_THREADS) {
+    double acc[XRSD_MAX_PAIRS];
+    for (int i = 0; i < XRSD_MAX_PAIRS; ++i) acc[i] = 0.0;
+    int msum = 0;
+    int h0 = 0, k0 = 0, l0 = 0;
+    for (int r = seg_start[s]; r < seg_start[s + 1]; ++r) {
+      const int c = list_cell[sidx[r]];
+      int h, k, l;
+      cell_to_hkl(S, c, h, k, l);
+      if (r == seg_start[s]) { h0 = h; k0 = k; l0 = l; }
+      const double mult = (double)grid[c];
+      msum += (int)grid[c];
+      double gre[XRSD_MAX_SPECIES], gim[XRSD_MAX_SPECIES];
+      for (int a = 0; a < n_sp; ++a) {
+        double xyz[3] = {0.0, 0.0, 0.0};
+        for (int j = 0; j < 3; ++j)
+          if (pop.p_uvw[a][j] >= 0) xyz[j] = prm[pop.p_uvw[a][j]];
+        double re = 0.0, im = 0.0;
+        for (int site = 0; site < pop.n_sites; ++site) {
+          const double gdr = (pop.sites[site][0] + xyz[0]) * h + (pop.sites[site][1] + xyz[1]) * k +
+                             (pop.sites[site][2] + xyz[2]) * l;
+          double sn, cs;
+          sincos(2.0 * M_PI * gdr, &sn, &cs);     // np.exp(2j*np.pi*g_dot_r)
+          re += cs; im += sn;
+        }
+        gre[a] = re; gim[a] = im;
+      }
+      int ip = 0;
+      for (int a = 0; a < n_sp; ++a)
+        for (int bq = a; bq < n_sp; ++bq, ++ip) acc[ip] += mult * (gre[a] * gre[bq] + gim[a] * gim[bq]);
+    }
+    o_hkl[s * 4 + 0] = h0; o_hkl[s * 4 + 1] = k0; o_hkl[s * 4 + 2] = l0; o_hkl[s * 4 + 3] = msum;
+    for (int ip = 0; ip < n_pairs; ++ip) {
+      o_geo[(size_t)s * T.n_pairs_max + ip] = acc[ip];
+      my_max = fmax(my_max, fabs(acc[ip]));
+    }
+  }
+  if (!pop.prune_extinct) { finish(n_raw); return; }
+
+  // ---- 6. drop extinct shells (all pair weights < 1e-20 of the largest), in place
+  for (int o = 16; o > 0; o >>= 1) my_max = fmax(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
+  __shared__ double wmax[TABLE_THREADS / 32];
+  if ((tid & 31) == 0) wmax[tid >> 5] = my_max;
+  __syncthreads();
+  if (tid == 0) {
+    double m = 0.0;
+    for (int w = 0; w < TABLE_THREADS / 32; ++w) m = fmax(m, wmax[w]);
+    S.max_geo = m;
+  }
+  __syncthreads();
+  __threadfence_block();
+  const double thr = 1.0e-20 * S.max_geo;
+  for (int s0 = 0; s0 < n_raw; s0 += TABLE_THREADS) {
+    const int s = s0 + tid;
+    bool keep = false;
+    int hk[4];
+    double geo[XRSD_MAX_PAIRS];
+    if (s < n_raw) {
+      for (int j = 0; j < 4; ++j) hk[j] = o_hkl[s * 4 + j];
+      for (int ip = 0; ip < n_pairs; ++ip) {
+        geo[ip] = o_geo[(size_t)s * T.n_pairs_max + ip];
+        keep = keep || (fabs(geo[ip]) > thr);
+      }
+    }
+    int base;
+    const int pos = block_flag_scan(S, keep, base) + base;   // has __syncthreads: all reads precede writes
+    if (keep) {
+      for (int j = 0; j < 4; ++j) o_hkl[pos * 4 + j] = hk[j];
+      for (int ip = 0; ip < n_pairs; ++ip) o_geo[(size_t)pos * T.n_pairs_max + ip] = geo[ip];
+    }
+    __syncthreads();
+  }
+  finish(S.scan_carry);
+}
+
+}  // namespace xrsd
+
+extern "C" int64_t xrsd_table_smem_layout(int32_t max_cells, int32_t cap_list) {
+  size_t off = ((size_t)max_cells * sizeof(uint16_t) + 15) & ~(size_t)15;
+  off += (size_t)cap_list * sizeof(double);
+  off += (size_t)cap_list * sizeof(int) * 2;
+  off += ((size_t)cap_list + 1) * sizeof(int);
+  return (int64_t)((off + 15) & ~(size_t)15);
+}
+
+extern "C" cudaError_t xrsd_launch_tables(const xrsd_layout_t *layout, const double *d_params, int ldp, int batch,
+                                          const xrsd_tables_t *tables, int max_cells, int cap_list,
+                                          cudaStream_t stream) {
+  const size_t smem = (size_t)xrsd_table_smem_layout(max_cells, cap_list);
+  cudaError_t e = cudaFuncSetAttribute(xrsd::reflection_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int n_tables = batch * layout->n_xtal;
+  if (n_tables <= 0) return cudaSuccess;
+  xrsd::reflection_table_kernel<<<n_tables, xrsd::TABLE_THREADS, smem, stream>>>(*layout, d_params, ldp, batch, *tables,
+                                                                                 max_cells, cap_list);
+  return cudaGetLastError();
+}

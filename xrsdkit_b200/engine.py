@@ -1,0 +1,220 @@
+"""Host side of the CUDA engine: device buffers (torch tensors), launches through the C ABI.
+
+torch is used for device memory, streams and torch.distributed only; every number is
+produced by the kernels in csrc/ behind include/xrsd_b200.h.  There is no CPU fallback:
+without a CUDA device (or without the built library) the calls raise.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from . import lowering
+
+_engine = None
+
+
+def get_engine():
+    global _engine
+    if _engine is None:
+        _engine = Engine()
+    return _engine
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class TableSet(object):
+    """Device arrays of xrsd_tables_t for batch*n_xtal reflection tables."""
+
+    def __init__(self, torch, device, n_tables, cap_shell, n_pairs, cap_refl=0):
+        self.n_tables, self.cap_shell, self.n_pairs, self.cap_refl = n_tables, cap_shell, n_pairs, cap_refl
+        i32, f64 = torch.int32, torch.float64
+        self.n_shell = torch.zeros(n_tables, dtype=i32, device=device)
+        self.n_refl = torch.zeros(n_tables, dtype=i32, device=device)
+        self.n_all = torch.zeros(n_tables, dtype=i32, device=device)
+        self.status = torch.zeros(n_tables, dtype=i32, device=device)
+        self.shell_hkl = torch.zeros((n_tables, cap_shell, 4), dtype=i32, device=device)
+        self.shell_geo = torch.zeros((n_tables, cap_shell, n_pairs), dtype=f64, device=device)
+        self.refl_hkl = torch.zeros((n_tables, cap_refl, 4), dtype=i32, device=device) if cap_refl else None
+        c = abi.Tables()
+        c.cap_shell, c.cap_refl, c.n_pairs_max = cap_shell, cap_refl, n_pairs
+        c.n_shell, c.n_refl, c.n_all, c.status = (self.n_shell.data_ptr(), self.n_refl.data_ptr(),
+                                                  self.n_all.data_ptr(), self.status.data_ptr())
+        c.shell_hkl, c.shell_geo = self.shell_hkl.data_ptr(), self.shell_geo.data_ptr()
+        c.refl_hkl = self.refl_hkl.data_ptr() if cap_refl else None
+        self.c = c
+
+
+class Engine(object):
+
+    def __init__(self, device=None):
+        self.lib = abi.load()
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("xrsdkit_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.launches = 0     # kernels launched through this engine (bench.py reports it)
+
+    # -- helpers ------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def to_device(self, arr):
+        torch = self.torch
+        if isinstance(arr, torch.Tensor):
+            return arr.to(device=self.device, dtype=torch.float64).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
+
+    def _n_pairs(self, layout):
+        n = 1
+        for p in layout.crystalline_pops():
+            n = max(n, p.n_species * (p.n_species + 1) // 2)
+        return n
+
+    # -- reflection tables --------------------------------------------------------------
+    def build_tables(self, layout, d_params, batch, params_host=None, cap_shell=None, export_reflections=False,
+                     max_cells=None, check=True):
+        """Build the reflection tables of all crystalline populations for a batch.
+
+        `params_host` (numpy [batch, n_params]) is only used to bound the candidate box when
+        `max_cells` is not given.  With check=True the per-table status is read back (one small
+        device->host copy) and capacity overflows are retried with larger tables."""
+        if layout.n_xtal == 0:
+            return None
+        torch = self.torch
+        if max_cells is None:
+            if params_host is None:
+                params_host = d_params.detach().cpu().numpy()
+            max_cells = lowering.max_cells(layout, params_host)
+        has_ops = all(p.use_symmetry and p.n_ops > 0 for p in layout.crystalline_pops())
+        if cap_shell is None:
+            cap_shell = 128 if has_ops else 1024
+        n_tables = batch * layout.n_xtal
+        cap_refl = 4096 if export_reflections else 0
+        while True:
+            T = TableSet(torch, self.device, n_tables, cap_shell, self._n_pairs(layout), cap_refl)
+            abi.check(self.lib.xrsd_reflection_tables(C.byref(layout.c), d_params.data_ptr(), d_params.shape[1], batch,
+                                                      C.byref(T.c), max_cells, self._stream()))
+            self.launches += 1
+            if not check:
+                return T
+            st = int(T.status.max().item()) if n_tables else 0
+            if st == 0:
+                return T
+            if st & abi.TABLE_BAD_LATTICE:
+                raise ValueError("degenerate lattice parameters (cell volume or edge is zero / not finite)")
+            if st & abi.TABLE_GRID_OVERFLOW:
+                raise abi.XrsdError("candidate hkl box exceeds the shared-memory budget (q_max * cell edge too large)")
+            if st & abi.TABLE_LIST_OVERFLOW:
+                raise abi.XrsdError("more than 4096 reduced reflections in one table (no usable symmetry?)")
+            if st & abi.TABLE_SHELL_OVERFLOW and cap_shell < 4096:
+                cap_shell *= 4
+                continue
+            raise abi.XrsdError("reflection table build failed with status %d" % st)
+
+    # -- intensity ----------------------------------------------------------------------
+    def intensity(self, layout, q, params, tables=None, out=None):
+        """I[b, :] on the device.  q: [n_q]; params: [batch, n_params] (numpy or cuda tensors)."""
+        torch = self.torch
+        d_q = self.to_device(q)
+        host_params = None if isinstance(params, torch.Tensor) else np.atleast_2d(np.asarray(params, dtype=np.float64))
+        d_p = self.to_device(params if host_params is None else host_params)
+        if d_p.dim() == 1:
+            d_p = d_p.unsqueeze(0)
+        batch, n_q = d_p.shape[0], d_q.shape[0]
+        if out is None:
+            out = torch.empty((batch, n_q), dtype=torch.float64, device=self.device)
+        if layout.n_xtal and tables is None:
+            tables = self.build_tables(layout, d_p, batch, params_host=host_params)
+        abi.check(self.lib.xrsd_intensity_batch(C.byref(layout.c), d_q.data_ptr(), n_q, d_p.data_ptr(), d_p.shape[1], batch,
+                                                C.byref(tables.c) if tables is not None else None,
+                                                out.data_ptr(), out.shape[1], self._stream()))
+        self.launches += 1
+        return out
+
+    def intensity_single(self, layout, q):
+        """numpy in, numpy out: one system with the parameter values stored in its layout."""
+        q = np.asarray(q, dtype=np.float64)
+        if q.size == 0:
+            return np.zeros(0)
+        I = self.intensity(layout, q, layout.values[None, :])
+        return I[0].cpu().numpy()
+
+    # -- objective ----------------------------------------------------------------------
+    def objective(self, error_weighted=True, logI_weighted=True, q_range=(0., float('inf')), has_dI=False):
+        o = abi.Objective()
+        o.error_weighted, o.logI_weighted, o.has_dI = int(bool(error_weighted)), int(bool(logI_weighted)), int(bool(has_dI))
+        o.q_lo, o.q_hi = float(q_range[0]), float(q_range[1])
+        return o
+
+    def _obs(self, Iobs, dI, batch, n_q):
+        d_I = self.to_device(Iobs)
+        ld = 0
+        if d_I.dim() == 2:
+            ld = d_I.stride(0) if d_I.shape[0] > 1 else 0
+            assert d_I.shape[0] in (1, batch) and d_I.shape[1] == n_q
+        else:
+            assert d_I.shape[0] == n_q
+        d_dI = None
+        if dI is not None:
+            d_dI = self.to_device(dI)
+            if np.ndim(dI) == 0:
+                d_dI = d_dI.reshape(1).expand(n_q).contiguous()
+            if d_dI.dim() != d_I.dim():
+                if d_dI.dim() == 1:
+                    d_dI = d_dI.unsqueeze(0).expand_as(d_I).contiguous() if d_I.dim() == 2 else d_dI
+                else:
+                    d_I = d_I.unsqueeze(0).expand_as(d_dI).contiguous()
+                    ld = d_I.stride(0)
+            if d_dI.dim() == 2 and d_I.dim() == 2 and d_dI.shape[0] != d_I.shape[0]:
+                d_I = d_I.expand(batch, n_q).contiguous()
+                d_dI = d_dI.expand(batch, n_q).contiguous()
+                ld = d_I.stride(0)
+        return d_I, d_dI, ld
+
+    def residual(self, layout, obj, q, params, Iobs, dI=None, tables=None):
+        """chi2[b] of System.evaluate_residual for every parameter set of the batch."""
+        torch = self.torch
+        d_q = self.to_device(q)
+        host_params = None if isinstance(params, torch.Tensor) else np.atleast_2d(np.asarray(params, dtype=np.float64))
+        d_p = self.to_device(params if host_params is None else host_params)
+        if d_p.dim() == 1:
+            d_p = d_p.unsqueeze(0)
+        batch, n_q = d_p.shape[0], d_q.shape[0]
+        d_I, d_dI, ld = self._obs(Iobs, dI, batch, n_q)
+        obj.has_dI = int(d_dI is not None)
+        if layout.n_xtal and tables is None:
+            tables = self.build_tables(layout, d_p, batch, params_host=host_params)
+        chi2 = torch.empty(batch, dtype=torch.float64, device=self.device)
+        abi.check(self.lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_p.data_ptr(),
+                                               d_p.shape[1], batch, C.byref(tables.c) if tables is not None else None,
+                                               d_I.data_ptr(), d_dI.data_ptr() if d_dI is not None else None, ld,
+                                               chi2.data_ptr(), self._stream()))
+        self.launches += 1
+        return chi2
+
+    def jacobian(self, layout, obj, q, d_params, Iobs_dev, dI_dev, ld_obs, free_slots, tables, rel_step=1e-6, out=None):
+        """Normal equations (JTJ, JTr, chi2) of the weighted residual vector by forward differences."""
+        torch = self.torch
+        batch, nf = d_params.shape[0], len(free_slots)
+        if out is None:
+            out = (torch.empty((batch, nf, nf), dtype=torch.float64, device=self.device),
+                   torch.empty((batch, nf), dtype=torch.float64, device=self.device),
+                   torch.empty(batch, dtype=torch.float64, device=self.device))
+        idx = (C.c_int32 * nf)(*free_slots)
+        abi.check(self.lib.xrsd_jacobian_batch(C.byref(layout.c), C.byref(obj), q.data_ptr(), q.shape[0], d_params.data_ptr(),
+                                               d_params.shape[1], batch, C.byref(tables.c) if tables is not None else None,
+                                               Iobs_dev.data_ptr(), dI_dev.data_ptr() if dI_dev is not None else None, ld_obs,
+                                               idx, nf, float(rel_step), out[0].data_ptr(), out[1].data_ptr(),
+                                               out[2].data_ptr(), self._stream()))
+        self.launches += 1
+        return out
+
+    def probe_fp64_peak(self):
+        t, ms = C.c_double(), C.c_double()
+        abi.check(self.lib.xrsd_probe_fp64_peak(C.byref(t), C.byref(ms), self._stream()))
+        return t.value, ms.value

@@ -1,0 +1,309 @@
+"""Lowering: System / Population objects -> the flat descriptors the CUDA engine consumes.
+
+A *layout* is everything about a system that is not a parameter value: which populations
+exist, their settings, and which slot of the flat parameter vector each parameter lives in.
+Many systems that share a layout (a batch of parameter sets, the iterates of a fit) are then
+evaluated in one launch from a [batch, n_params] matrix.
+
+The slot order is the reference's flatten_params() order (system/__init__.py:211-218):
+noise parameters first, then each population's parameters in dict order, keyed
+'<population>__<parameter>'.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from . import definitions as xrsdefs
+
+# point group -> operations the reference applies, in order (scattering/symmetries.py:27-42).
+# Every other point group has no operations defined there and reduces nothing.
+POINT_GROUP_OPS = {
+    '1': [],
+    '-1': ['inversion'],
+    'm-3m': ['mirror_x', 'mirror_y', 'mirror_z', 'mirror_x_y', 'mirror_y_z', 'mirror_z_x',
+             'mirror_nx_y', 'mirror_ny_z', 'mirror_nz_x'],
+    '6/mmm': ['inversion', 'mirror_z', 'mirror_x_y', 'mirror_nx_y'],
+}
+
+_LATTICE_CLASS = {}
+for _l in ('P_cubic', 'I_cubic', 'F_cubic', 'diamond'):
+    _LATTICE_CLASS[_l] = abi.LAT_CUBIC
+_LATTICE_CLASS['hcp'] = abi.LAT_HCP
+_LATTICE_CLASS['hexagonal'] = abi.LAT_HEXAGONAL
+for _l in ('P_orthorhombic', 'C_orthorhombic', 'A_orthorhombic', 'I_orthorhombic', 'F_orthorhombic'):
+    _LATTICE_CLASS[_l] = abi.LAT_ORTHORHOMBIC
+for _l in ('P_tetragonal', 'I_tetragonal'):
+    _LATTICE_CLASS[_l] = abi.LAT_TETRAGONAL
+for _l in ('P_monoclinic', 'C_monoclinic'):
+    _LATTICE_CLASS[_l] = abi.LAT_MONOCLINIC
+_LATTICE_CLASS['rhombohedral'] = abi.LAT_RHOMBOHEDRAL
+_LATTICE_CLASS['triclinic'] = abi.LAT_TRICLINIC
+
+_LAT_SLOTS = ('a', 'b', 'c', 'alpha', 'beta', 'gamma')
+
+
+class SystemLayout(object):
+    """ctypes layout + the parameter bookkeeping that goes with it."""
+
+    def __init__(self, c_layout, names, values, records):
+        self.c = c_layout
+        self.names = names            # 'pop__param' per slot
+        self.values = values          # float64[n_params]
+        self.records = records        # the parameter dicts (shared with the System, like flatten_params)
+        self.n_params = len(names)
+        self.n_xtal = c_layout.n_xtal
+
+    def slot(self, key):
+        return self.names.index(key)
+
+    def free_slots(self):
+        """Slots lmfit would vary: not fixed and without a constraint expression
+        (reference system/__init__.py:197-209)."""
+        return [i for i, r in enumerate(self.records) if not r.get('fixed') and not r.get('constraint_expr')]
+
+    def bounds(self, slots):
+        lo = np.array([-np.inf if self.records[i]['bounds'][0] is None else self.records[i]['bounds'][0] for i in slots], float)
+        hi = np.array([np.inf if self.records[i]['bounds'][1] is None else self.records[i]['bounds'][1] for i in slots], float)
+        return lo, hi
+
+    def crystalline_pops(self):
+        return [p for p in self.c.pops[:self.c.n_pops] if p.kind == abi.POP_CRYSTALLINE]
+
+
+def _blank_pop():
+    p = abi.Pop()
+    for f in ('p_I0', 'p_r', 'p_sigma', 'p_rg', 'p_D', 'p_r_hard', 'p_v_fraction', 'p_flat_fraction',
+              'p_hwhm', 'p_hwhm_g', 'p_hwhm_l'):
+        setattr(p, f, -1)
+    for i in range(6):
+        p.p_lat[i] = -1
+    for a in range(abi.MAX_SPECIES):
+        for j in range(3):
+            p.p_uvw[a][j] = -1
+    return p
+
+
+def _set_atom(pop, idx, symbol):
+    rec = xrsdefs.atomic_params[symbol]     # KeyError for an unknown symbol, as the reference
+    pop.atom_Z[idx] = float(rec['Z'])
+    for j in range(4):
+        pop.atom_a[idx][j] = float(rec['a'][j])
+        pop.atom_b[idx][j] = float(rec['b'][j])
+
+
+def _val(rec):
+    return rec['value'] if isinstance(rec, dict) else rec
+
+
+def _lower_noise(model, slots):
+    p = _blank_pop()
+    if model == 'flat':
+        p.kind = abi.POP_NOISE_FLAT
+        p.p_I0 = slots['I0']
+    elif model == 'low_q_scatter':
+        p.kind = abi.POP_NOISE_LOW_Q
+        p.p_I0 = slots['I0']
+        p.p_flat_fraction = slots['I0_flat_fraction']
+        p.p_rg = slots['effective_rg']
+        p.p_D = slots['effective_D']
+    else:
+        raise ValueError('unsupported noise specification: {}'.format(model))
+    return p
+
+
+def _lower_population(structure, form, settings, slots, q_last, table_slot):
+    """One population -> abi.Pop.  Mirrors the dispatcher scattering/__init__.py:12-66."""
+    p = _blank_pop()
+    p.p_I0 = slots['I0']
+    if structure == 'crystalline':
+        p.kind = abi.POP_CRYSTALLINE
+        lattice = settings['lattice']
+        p.lattice = _LATTICE_CLASS[lattice]            # KeyError for an unknown lattice
+        sites = xrsdefs.lattice_coords(lattice)
+        p.n_sites = len(sites)
+        for i, s in enumerate(sites):
+            for j in range(3):
+                p.sites[i][j] = float(s[j])
+        sg = settings['space_group']
+        if sg and sg not in xrsdefs.lattice_space_groups[lattice].values():
+            raise ValueError('space group {} not valid for {} lattice'.format(sg, lattice))
+        ops = []
+        if sg:
+            ops = POINT_GROUP_OPS.get(xrsdefs.sg_point_groups[sg]) or []
+        p.n_ops = len(ops)
+        for i, nm in enumerate(ops):
+            p.ops[i] = abi.OPS[nm]
+        p.use_symmetry = 1 if settings['use_symmetry'] else 0
+        p.profile = abi.PROFILE[settings['profile']]
+        p.sf_radial = 1 if settings['structure_factor_mode'] == 'radial' else 0
+        p.polz = 1 if settings['polarization_correction'] else 0
+        p.lorentz = 1 if settings['lorentz_correction'] else 0
+        p.q_min = float(settings['q_min'])
+        q_max = settings['q_max']
+        p.q_max = float(q_max) if q_max else float(q_last)     # scattering/__init__.py:226
+        for i, nm in enumerate(_LAT_SLOTS):
+            if nm in xrsdefs.lattice_param_names(lattice):
+                p.p_lat[i] = slots[nm]
+        if not xrsdefs.lattice_param_names(lattice):
+            # the reference hands lattice_vectors() no parameters for this lattice and fails
+            raise TypeError('lattice {} defines no lattice parameters'.format(lattice))
+        if settings['profile'] == 'voigt':
+            p.p_hwhm_g, p.p_hwhm_l = slots['hwhm_g'], slots['hwhm_l']
+        else:
+            p.p_hwhm = slots['hwhm']
+        if form == 'spherical':
+            p.n_species = 1
+            p.species_form[0] = abi.FORM_SPHERE
+            p.p_r = slots['r']
+        elif form == 'atomic':
+            p.n_species = 1
+            p.species_form[0] = abi.FORM_ATOMIC
+            _set_atom(p, 0, settings['symbol'])
+        elif form == 'polyatomic':
+            n_at = settings['n_atoms']
+            if n_at > abi.MAX_SPECIES:
+                raise NotImplementedError('polyatomic populations are limited to {} atoms per cell'.format(abi.MAX_SPECIES))
+            p.n_species = n_at
+            for i in range(n_at):
+                p.species_form[i] = abi.FORM_ATOMIC
+                _set_atom(p, i, settings['symbol_%d' % i])
+                for j, ax in enumerate('uvw'):
+                    p.p_uvw[i][j] = slots['%s_%d' % (ax, i)]
+        p.table_slot = table_slot
+        # extinct shells (|S|^2 ~ 1e-31 of the allowed ones) are dropped when the profile has
+        # algebraic tails, where their contribution is < 1e-15 relative; kept for 'gaussian',
+        # whose tails underflow and would otherwise leave them as the only contribution
+        p.prune_extinct = 0 if settings['profile'] == 'gaussian' else 1
+        return p
+    p.kind = abi.POP_NONCRYSTALLINE
+    p.disordered = 1 if structure == 'disordered' else 0
+    if p.disordered:
+        p.p_r_hard, p.p_v_fraction = slots['r_hard'], slots['v_fraction']
+    if form == 'atomic':
+        p.form = abi.FORM_ATOMIC
+        _set_atom(p, 0, settings['symbol'])
+    elif form == 'spherical':
+        p.p_r = slots['r']
+        if settings['distribution'] == 'r_normal':
+            p.form = abi.FORM_SPHERE_R_NORMAL
+            p.p_sigma = slots['sigma']
+            p.sampling_width = float(settings['sampling_width'])
+            p.sampling_step = float(settings['sampling_step'])
+        else:
+            p.form = abi.FORM_SPHERE
+    elif form == 'guinier_porod':
+        p.form = abi.FORM_GUINIER_POROD
+        p.p_rg, p.p_D = slots['rg'], slots['D']
+    else:
+        raise ValueError('{} structure does not support {} forms'.format(structure, form))
+    return p
+
+
+def lower_system(system, q):
+    """System -> SystemLayout for the grid `q` (q is needed only for q[0]==0 and the q_max fallback)."""
+    q = np.asarray(q, dtype=float)
+    names, values, records = [], [], []
+    L = abi.Layout()
+
+    def take(prefix, params):
+        slots = {}
+        for nm, rec in params.items():
+            slots[nm] = len(names)
+            names.append(prefix + '__' + nm)
+            values.append(float(_val(rec)))
+            records.append(rec)
+        return slots
+
+    pops = [_lower_noise(system.noise_model.model, take('noise', system.noise_model.parameters))]
+    n_x = 0
+    for pop_name, pop in system.populations.items():
+        slots = take(pop_name, pop.parameters)
+        lp = _lower_population(pop.structure, pop.form, pop.settings, slots, q[-1] if len(q) else 0.0, n_x)
+        if lp.kind == abi.POP_CRYSTALLINE:
+            n_x += 1
+        pops.append(lp)
+    if len(pops) > abi.MAX_POPS:
+        raise NotImplementedError('a system layout holds at most {} populations'.format(abi.MAX_POPS - 1))
+    if len(names) > abi.MAX_PARAMS:
+        raise NotImplementedError('a system layout holds at most {} parameters'.format(abi.MAX_PARAMS))
+    L.n_pops = len(pops)
+    L.n_params = max(1, len(names))
+    L.n_xtal = n_x
+    L.q0_is_zero = 1 if (len(q) and q[0] == 0) else 0
+    wl = system.sample_metadata['source_wavelength']
+    if n_x and not wl:
+        raise ValueError('cannot compute diffraction with source wavelength of {}'.format(wl))
+    L.wavelength = float(wl) if wl else 0.0
+    for i, p in enumerate(pops):
+        L.pops[i] = p
+    if not names:
+        names, values, records = ['_unused'], [0.0], [dict(value=0.0, fixed=True, bounds=[None, None], constraint_expr=None)]
+    return SystemLayout(L, names, np.array(values, dtype=float), records)
+
+
+class _Shell(object):
+    """Minimal stand-in for a System around one population or one noise model."""
+
+    def __init__(self, noise_model, populations, wavelength):
+        self.noise_model = noise_model
+        self.populations = populations
+        self.sample_metadata = dict(source_wavelength=wavelength)
+
+
+class _ZeroNoise(object):
+    model = 'flat'
+    parameters = {'I0': {'value': 0.0, 'fixed': True, 'bounds': [0., None], 'constraint_expr': None}}
+
+
+def lower_population_only(structure, form, settings, parameters, q, wavelength):
+    class _P(object):
+        pass
+    pop = _P()
+    pop.structure, pop.form, pop.settings, pop.parameters = structure, form, settings, parameters
+    return lower_system(_Shell(_ZeroNoise(), {'pop': pop}, wavelength), q)
+
+
+def lower_noise_only(noise_model, q):
+    return lower_system(_Shell(noise_model, {}, 1.0), q)
+
+
+# ---------------------------------------------------------------------------------------
+# host-side bound on the candidate hkl box (sizes the table builder's shared memory)
+# ---------------------------------------------------------------------------------------
+def box_half_widths(c_pop, params):
+    """Upper bound of n1,n2,n3 = ceil(G_max |a_i| / (b_i.a_i)) (scattering/__init__.py:266-268)
+    over a [batch, n_params] matrix.  |a_i| are the cell edge lengths for every lattice class
+    and b_i.a_i = 1 up to rounding, so n_i <= ceil(G_max * edge_i) + 1."""
+    params = np.atleast_2d(params)
+
+    def col(i):
+        return params[:, c_pop.p_lat[i]] if c_pop.p_lat[i] >= 0 else None
+
+    a, b, c = col(0), col(1), col(2)
+    lat = c_pop.lattice
+    if lat == abi.LAT_CUBIC:
+        e = [a, a, a]
+    elif lat == abi.LAT_HCP:
+        e = [a, a, a * np.sqrt(8. / 3.)]
+    elif lat in (abi.LAT_HEXAGONAL, abi.LAT_TETRAGONAL):
+        e = [a, a, c]
+    elif lat == abi.LAT_RHOMBOHEDRAL:
+        e = [a, a, a]
+    else:
+        e = [a, b, c]
+    g_max = c_pop.q_max / (2 * np.pi)
+    out = []
+    for edge in e:
+        m = np.nanmax(np.abs(edge)) if edge is not None and len(edge) else 0.0
+        n = np.ceil(g_max * m * (1 + 1e-12)) + 1
+        out.append(int(max(1, min(n, 10000))))
+    return out
+
+
+def max_cells(layout, params):
+    cells = 1
+    for p in layout.crystalline_pops():
+        n1, n2, n3 = box_half_widths(p, params)
+        cells = max(cells, (2 * n1 - 1) * (2 * n2 - 1) * (2 * n3 - 1))
+    return int(cells)
