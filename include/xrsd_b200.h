@@ -191,6 +191,12 @@ int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int3
                               double *I_out, int64_t ld_I);
 void xrsd_release_workspace(void);
 
+/* Peak profiles on their own: out[i] = profile(x[i]) for kind = XRSD_PROFILE_* with
+ * (hwhm_g, hwhm_l) for voigt or (hwhm, unused) otherwise.  <- tools/peak_math.py:24-47
+ * (gaussian, lorentzian, voigt; the reference's voigt calls scipy.special.wofz). */
+int xrsd_peak_profile(int32_t kind, double hwhm_or_hwhm_g, double hwhm_l, const double *d_x, int32_t n,
+                      double *d_out, void *stream);
+
 /* FP64 pipe probe used by bench.py for the roofline denominator: runs a DFMA-bound
  * kernel and returns the measured TFLOP/s (2 flop per DFMA) on the current device. */
 int xrsd_probe_fp64_peak(double *tflops, double *elapsed_ms, void *stream);

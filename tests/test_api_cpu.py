@@ -1,0 +1,135 @@
+"""Host-side logic that needs no GPU: the System / Population / NoiseModel object model against the
+reference's own dict output, lowering to the flat descriptors, sharding arithmetic."""
+import copy
+
+import numpy as np
+import pytest
+
+from xrsdkit_b200 import abi, batch, lowering
+from xrsdkit_b200.system import System, Population, NoiseModel, unflatten_params
+
+
+def test_dict_round_trip_equals_reference(golden_systems):
+    """System(**d).to_dict() reproduces the reference's fully-populated dict (defaults, key sets, values)."""
+    meta, _ = golden_systems
+    for m in meta:
+        d = m["system"]
+        s = System(**copy.deepcopy(d))
+        out = s.to_dict()
+        assert set(out.keys()) == set(d.keys()), m["name"]
+        for k in d:
+            assert out[k] == d[k], (m["name"], k)
+        assert System.from_dict(out).to_dict() == out
+        assert s.clone().to_dict() == out
+
+
+def test_defaults_from_minimal_construction(golden_systems):
+    """Building from the user-level arguments only gives the same populated dict as the reference did."""
+    meta, _ = golden_systems
+    by = {m["name"]: m for m in meta}
+    s = System(p=dict(structure="diffuse", form="spherical", parameters={"r": {"value": 20.0}}))
+    assert s.to_dict() == by["cfg1"]["system"]
+    x = dict(structure="crystalline", form="spherical",
+             settings={"lattice": "F_cubic", "space_group": "Fm-3m", "q_max": 1.0, "profile": "voigt"},
+             parameters={"a": {"value": 60.0}, "r": {"value": 20.0}, "hwhm_g": {"value": 0.002}, "hwhm_l": {"value": 0.002}})
+    assert System(x=x, source_wavelength=0.8265617).to_dict() == by["cfg3"]["system"]
+
+
+def test_population_settings_and_parameter_rules():
+    p = Population("crystalline", "spherical", {"lattice": "hexagonal", "profile": "gaussian"})
+    assert list(p.parameters.keys()) == ["I0", "a", "r", "c", "hwhm"]      # same order as the reference
+    p.update_settings({"profile": "voigt", "lattice": "F_cubic"})
+    assert list(p.parameters.keys()) == ["I0", "a", "r", "hwhm_g", "hwhm_l"]
+    assert p.settings["q_max"] == 1.0 and p.settings["structure_factor_mode"] == "local"
+    with pytest.raises(ValueError):
+        p.update_parameters({"sigma": {"value": 0.1}})
+    with pytest.raises(ValueError):
+        p.update_settings({"distribution": "r_normal"})
+    with pytest.raises(ValueError):
+        Population("diffuse", "polyatomic")
+    q = Population("diffuse", "spherical", {"distribution": "r_normal"}, {"sigma": {"value": 0.2}})
+    assert q.settings["sampling_width"] == 3.5 and q.settings["sampling_step"] == 0.05
+    assert q.parameters["sigma"] == {"value": 0.2, "fixed": False, "bounds": [0., 2.], "constraint_expr": None}
+    n = NoiseModel("low_q_scatter")
+    assert list(n.parameters.keys()) == ["I0", "I0_flat_fraction", "effective_rg", "effective_D"]
+    with pytest.raises(ValueError):
+        n.update_parameters({"rg": {"value": 1.0}})
+    n.set_model("flat")
+    assert list(n.parameters.keys()) == ["I0"]
+
+
+def test_system_parameter_plumbing():
+    s = System(a=dict(structure="diffuse", form="guinier_porod"), b=dict(structure="disordered", form="spherical"))
+    flat = s.flatten_params()
+    assert list(flat.keys()) == ["noise__I0", "a__I0", "a__rg", "a__D", "b__I0", "b__r_hard", "b__v_fraction", "b__r"]
+    flat["a__rg"]["value"] = 3.0                     # shared by reference, like xrsdkit
+    assert s.populations["a"].parameters["rg"]["value"] == 3.0
+    s.update_params_from_dict(unflatten_params({"b__r": {"value": 7.0}, "noise__I0": {"value": 0.5}}))
+    assert s.populations["b"].parameters["r"]["value"] == 7.0 and s.noise_model.parameters["I0"]["value"] == 0.5
+    s.set_q_range(0.1, 0.4)
+    s.set_error_weighted(0)
+    assert s.fit_report["q_range"] == [0.1, 0.4] and s.fit_report["error_weighted"] is False
+    s.remove_population("a")
+    s.add_population("c", "diffuse", "atomic", {"symbol": "Au"})
+    assert list(s.populations.keys()) == ["b", "c"]
+    assert System(source_wavelength=0.7).sample_metadata["source_wavelength"] == 0.7
+
+
+def test_lowering_slots_and_descriptors():
+    s = System(
+        x=dict(structure="crystalline", form="polyatomic",
+               settings={"lattice": "F_cubic", "space_group": "Fm-3m", "q_max": 0.0, "n_atoms": 2,
+                         "symbol_0": "Na", "symbol_1": "Cl", "structure_factor_mode": "radial"},
+               parameters={"a": {"value": 5.64}, "u_1": {"value": 0.5}}),
+        g=dict(structure="disordered", form="spherical", settings={"distribution": "r_normal"}),
+        noise={"model": "low_q_scatter"}, source_wavelength=0.8265617)
+    q = np.linspace(0.0, 4.0, 50)
+    lay = lowering.lower_system(s, q)
+    assert lay.names == list(s.flatten_params().keys())
+    assert lay.c.n_pops == 3 and lay.c.n_xtal == 1 and lay.c.q0_is_zero == 1
+    nz, x, g = lay.c.pops[0], lay.c.pops[1], lay.c.pops[2]
+    assert nz.kind == abi.POP_NOISE_LOW_Q and nz.p_rg == lay.slot("noise__effective_rg")
+    assert x.kind == abi.POP_CRYSTALLINE and x.n_species == 2 and x.n_sites == 4 and x.n_ops == 9 and x.sf_radial == 1
+    assert x.q_max == 4.0                                   # falsy q_max -> q[-1]
+    assert x.atom_Z[0] == 11 and x.atom_Z[1] == 17 and x.p_uvw[1][0] == lay.slot("x__u_1")
+    assert x.p_lat[0] == lay.slot("x__a") and x.p_lat[1] == -1
+    assert g.kind == abi.POP_NONCRYSTALLINE and g.disordered == 1 and g.form == abi.FORM_SPHERE_R_NORMAL
+    assert g.sampling_width == 3.5 and g.p_sigma == lay.slot("g__sigma")
+    # lmfit-style free set: not fixed, no constraint expression
+    assert lay.slot("x__occupancy_0") not in lay.free_slots() and lay.slot("x__a") in lay.free_slots()
+    lo, hi = lay.bounds([lay.slot("g__v_fraction"), lay.slot("x__a")])
+    assert lo.tolist() == [0.01, 0.1] and hi[0] == 0.7405 and np.isinf(hi[1])
+    # candidate box bound: a = 5.64, q_max = 4 -> n = ceil(4*5.64/2pi)+1 = 5 -> 9^3
+    assert lowering.max_cells(lay, lay.values[None, :]) == 9 ** 3
+
+
+def test_lowering_errors():
+    with pytest.raises(ValueError):      # falsy wavelength with a crystalline population
+        lowering.lower_system(System(x=dict(structure="crystalline", form="spherical", parameters={"a": {"value": 9.}}),
+                                     source_wavelength=0), np.array([0.1]))
+    with pytest.raises(ValueError):      # space group of another lattice
+        lowering.lower_system(System(x=dict(structure="crystalline", form="spherical",
+                                            settings={"lattice": "hcp", "space_group": "Fm-3m"})), np.array([0.1]))
+    with pytest.raises(KeyError):
+        lowering.lower_system(System(x=dict(structure="diffuse", form="atomic", settings={"symbol": "Qq"})), np.array([0.1]))
+    with pytest.raises(NotImplementedError):
+        lowering.lower_system(System(x=dict(structure="crystalline", form="polyatomic", settings={"n_atoms": 5})),
+                              np.array([0.1]))
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 10000, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [batch.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_compute_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        System(p=dict(structure="diffuse", form="spherical")).compute_intensity(np.linspace(0.01, 0.5, 10))

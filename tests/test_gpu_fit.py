@@ -1,0 +1,160 @@
+"""GPU tests of the fit objective, the fused Jacobian and the batched Levenberg-Marquardt fit."""
+import numpy as np
+import pytest
+
+from helpers import rel_err, cfg2_system, cfg2_params, cfg4_system, cfg4_params, params_to_sysdict
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from xrsdkit_b200 import engine
+    return engine.get_engine()
+
+
+def test_residual_against_reference_values(golden_systems, eng):
+    """System.evaluate_residual: (a) with I_comp given, against the reference's recorded values for all four
+    weighting modes + explicit dI/q_range; (b) the fused kernel against the oracle's objective."""
+    from oracle import xrsd_oracle as orc
+    from xrsdkit_b200.system import System
+    meta, arr = golden_systems
+    for m in meta[::3]:
+        q = arr[m["q"]]
+        key = m["key"]
+        I, Iobs = arr[key + "_I"], arr[key + "_Iobs"]
+        if not np.isfinite(I).all():
+            continue
+        s = System(**m["system"])
+        saved = dict(s.fit_report)
+        got = []
+        for ew in (True, False):
+            for lw in (True, False):
+                s.set_error_weighted(ew)
+                s.set_logI_weighted(lw)
+                got.append(s.evaluate_residual(q, Iobs, None, 1.01 * I + 1e-4))
+        s.set_error_weighted(True)
+        s.set_logI_weighted(True)
+        s.set_q_range(q[len(q) // 8], q[-len(q) // 8])
+        got.append(s.evaluate_residual(q, Iobs, 0.1 * np.sqrt(np.abs(Iobs)) + 1e-3, 1.01 * I + 1e-4))
+        np.testing.assert_allclose(got, arr[key + "_res"], rtol=1e-11, err_msg=m["name"])
+        s.fit_report.update(saved)
+        # fused path: model intensity computed in the same kernel
+        for ew in (True, False):
+            for lw in (True, False):
+                s.set_error_weighted(ew)
+                s.set_logI_weighted(lw)
+                ref = orc.residual(q, Iobs, I, None, ew, lw, s.fit_report["q_range"])
+                assert s.evaluate_residual(q, Iobs) == pytest.approx(ref, rel=1e-9), (m["name"], ew, lw)
+        dI = 0.05 * Iobs + 0.01
+        s.set_error_weighted(True)
+        ref = orc.residual(q, Iobs, I, dI, True, False, s.fit_report["q_range"])
+        assert s.evaluate_residual(q, Iobs, dI) == pytest.approx(ref, rel=1e-9), m["name"]
+
+
+def test_kat11_residual(eng):
+    from xrsdkit_b200.system import System
+    q = np.linspace(0.001, 0.5, 2000)
+    I10 = System(p=dict(structure="diffuse", form="spherical", parameters={"r": {"value": 20.0}})).compute_intensity(q)
+    Iobs = I10 * (1 + 0.02 * np.random.RandomState(0).randn(2000))
+    s21 = System(p=dict(structure="diffuse", form="spherical", parameters={"r": {"value": 21.0}}))
+    assert s21.evaluate_residual(q, Iobs) == pytest.approx(0.011354578266228588, rel=1e-9)   # SURVEY KAT11
+
+
+def test_jacobian_normal_equations_vs_oracle_finite_differences(ref_tables, eng):
+    """JTJ / JTr / chi2 of the fused kernel against central differences of the oracle's residual vector
+    (the reference has no Jacobian: SURVEY H8)."""
+    from oracle import xrsd_oracle as orc
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg2_system(System)
+    # 2*width/step = 50.4: the number of radii does not flip under the finite-difference steps
+    # (at exactly 50 it is 50 or 51 by rounding luck and I(sigma) has steps)
+    s.populations["p"].update_settings({"sampling_width": 2.52})
+    q = np.linspace(0.01, 0.5, 1500)
+    lay = batch.layout_of(s, q)
+    P = cfg2_params(lay, 3, seed=3)
+    free = [lay.slot(k) for k in ("noise__I0", "p__I0", "p__r", "p__sigma", "p__r_hard", "p__v_fraction")]
+    truth = P.copy()
+    rs = np.random.RandomState(1)
+    Iobs = np.array([orc.system_intensity(q, params_to_sysdict(s, lay, truth[b]), **ref_tables) for b in range(3)])
+    Iobs *= 1 + 0.02 * rs.randn(*Iobs.shape)
+    P[:, lay.slot("p__r")] *= 1.03
+    d_q, d_p, d_I = eng.to_device(q), eng.to_device(P), eng.to_device(Iobs)
+    obj = eng.objective(True, True, (0.0, float("inf")))
+    JTJ, JTr, chi2 = eng.jacobian(lay, obj, d_q, d_p, d_I, None, d_I.shape[1], free, None, rel_step=1e-6)
+    JTJ, JTr, chi2 = JTJ.cpu().numpy(), JTr.cpu().numpy(), chi2.cpu().numpy()
+
+    def resvec(row):
+        Ic = orc.system_intensity(q, params_to_sysdict(s, lay, row), **ref_tables)
+        w = np.sqrt(Iobs_b) ** 2
+        w = w / w.sum()
+        return np.sqrt(w) * (np.log(Ic) - np.log(Iobs_b))
+
+    for b in range(3):
+        Iobs_b = Iobs[b]
+        r0 = resvec(P[b])
+        J = np.zeros((len(q), len(free)))
+        for j, sl in enumerate(free):
+            h = 1e-5 * abs(P[b, sl])
+            up, dn = P[b].copy(), P[b].copy()
+            up[sl] += h
+            dn[sl] -= h
+            J[:, j] = (resvec(up) - resvec(dn)) / (2 * h)
+        assert chi2[b] == pytest.approx(r0 @ r0, rel=1e-9)
+        np.testing.assert_allclose(JTr[b], J.T @ r0, rtol=2e-4, atol=1e-7 * np.abs(J.T @ r0).max())
+        ref = J.T @ J
+        np.testing.assert_allclose(JTJ[b], ref, rtol=2e-4, atol=1e-6 * np.abs(ref).max())
+
+
+def test_lm_recovers_sphere_systems(eng):
+    """Batched LM on cfg5-style sphere systems: starts 10% off, noise-free data -> parameters recovered."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg2_system(System)
+    s.populations["p"].update_settings({"sampling_width": 2.52})   # stable radius count, smooth objective
+    q = np.linspace(0.01, 0.5, 1024)
+    lay = batch.layout_of(s, q)
+    n = 64
+    truth = cfg2_params(lay, n, seed=11)
+    Iobs = batch.compute_intensity_batch(lay, q, truth)
+    rs = np.random.RandomState(2)
+    free = [lay.slot(k) for k in ("p__I0", "p__r", "p__sigma", "p__r_hard", "p__v_fraction")]
+    start = truth.copy()
+    start[:, free] *= 1 + 0.1 * rs.uniform(-1, 1, (n, len(free)))
+    res = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=40)
+    good = res.chi2 < 1e-10
+    print("LM sphere: frac<1e-10 %.2f  median chi2 %.2e  max %.2e  iters %d" % (good.mean(), np.median(res.chi2), res.chi2.max(), res.n_iter))
+    assert good.mean() >= 0.9, (good.mean(), np.sort(res.chi2)[-5:])
+    np.testing.assert_allclose(res.params[good][:, free], truth[good][:, free], rtol=1e-3)
+    assert np.all(res.chi2 <= res.chi2_init * (1 + 1e-12))
+
+
+def test_lm_recovers_crystal_systems_and_fit_api(eng):
+    from xrsdkit_b200.system import System, fit
+    from xrsdkit_b200 import batch
+    s = cfg4_system(System)
+    q = np.linspace(0.01, 1.0, 2048)
+    lay = batch.layout_of(s, q)
+    n = 12
+    truth = cfg4_params(lay, n, seed=12)
+    Iobs = batch.compute_intensity_batch(lay, q, truth)
+    rs = np.random.RandomState(3)
+    free = [lay.slot(k) for k in ("noise__I0", "x__I0", "x__a", "x__hwhm_g", "x__hwhm_l", "x__r", "gp__I0", "gp__rg")]
+    start = truth.copy()
+    start[:, free] *= 1 + 0.03 * rs.uniform(-1, 1, (n, len(free)))
+    res = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=40)
+    assert np.all(res.chi2 <= res.chi2_init * (1 + 1e-12))
+    assert np.median(res.chi2 / res.chi2_init) < 1e-3
+    # System-level fit(): reference contract (returns a new System, fills fit_report)
+    sph = System(p=dict(structure="diffuse", form="spherical", parameters={"r": {"value": 20.0}, "I0": {"value": 5.0}}),
+                 noise={"model": "flat", "parameters": {"I0": {"value": 1e-3}}})
+    qq = np.linspace(0.01, 0.5, 800)
+    I = sph.compute_intensity(qq) * (1 + 0.01 * np.random.RandomState(4).randn(800))
+    guess = System(p=dict(structure="diffuse", form="spherical", parameters={"r": {"value": 21.0}, "I0": {"value": 4.0}}),
+                   noise={"model": "flat", "parameters": {"I0": {"value": 2e-3}}})
+    out = fit(guess, qq, I)
+    assert out is not guess and guess.populations["p"].parameters["r"]["value"] == 21.0
+    assert out.populations["p"].parameters["r"]["value"] == pytest.approx(20.0, rel=2e-3)
+    rep = out.fit_report
+    assert rep["final_objective"] < rep["initial_objective"] and "fit_snr" in rep and "converged" in rep

@@ -1,0 +1,264 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the reference's outputs
+(tests/golden, produced by the unmodified reference) and against the oracle on seeded inputs.
+Tolerance: 1e-10 relative (BASELINE.json FP64 gate); reflection lists bit-exact."""
+import numpy as np
+import pytest
+
+from helpers import TOL_F64, rel_err, cfg2_system, cfg2_params, cfg3_system, cfg3_params, cfg4_system, cfg4_params, params_to_sysdict
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from xrsdkit_b200 import engine
+    return engine.get_engine()
+
+
+def test_library_is_the_loaded_native_code(eng):
+    import os
+    from xrsdkit_b200 import abi
+    assert os.path.exists(abi.LIB_PATH)
+    with open("/proc/self/maps") as f:
+        assert "libxrsd_b200.so" in f.read()
+
+
+def test_golden_systems_intensity(golden_systems, eng):
+    """Every golden System (reference test constructions, BASELINE configs, lattice/profile spread and
+    164 fitted fixture systems): total I(q), each population's I(q) and the noise term."""
+    from xrsdkit_b200.system import System
+    meta, arr = golden_systems
+    worst = 0.0
+    for m in meta:
+        q = arr[m["q"]]
+        s = System(**m["system"])
+        got = s.compute_intensity(q)
+        err, same = rel_err(got, arr[m["key"] + "_I"])
+        assert same, m["name"]
+        assert err <= TOL_F64, (m["name"], err)
+        worst = max(worst, err)
+        for pn, pop in s.populations.items():
+            gp = pop.compute_intensity(q, s.sample_metadata["source_wavelength"])
+            err, same = rel_err(gp, arr[m["key"] + "_pop_" + pn])
+            assert same and err <= TOL_F64, (m["name"], pn, err)
+        err, same = rel_err(s.noise_model.compute_intensity(q), arr[m["key"] + "_noise"])
+        assert same and err <= TOL_F64, (m["name"], "noise", err)
+    print("worst relative error over %d golden systems: %.2e" % (len(meta), worst))
+
+
+def test_golden_elementary_functions(golden_kernels, eng):
+    from xrsdkit_b200 import scattering
+    from xrsdkit_b200.tools import peak_math
+    g = golden_kernels
+    q = g["q"]
+    for row, ref in zip(g["rnormal_args"], g["rnormal_I"]):
+        err, same = rel_err(scattering.spherical_normal_intensity(q, *row), ref)
+        assert same and err <= TOL_F64, (row, err)
+    for row, ref in zip(g["gp_args"], g["gp_I"]):
+        err, same = rel_err(scattering.guinier_porod_intensity(q, *row), ref)
+        assert same and err <= TOL_F64, (row, err)
+    for r, ref in zip(g["sphere_r"], g["sphere_ff"]):
+        # ff^2 near the zeros of ff is compared on the scale of the pattern (floor), cf. SURVEY H2
+        err, same = rel_err(scattering.spherical_ff_squared(q, r), ref ** 2, floor_frac=1e-6)
+        assert same and err <= TOL_F64, (r, err)
+    for row, ref in zip(g["hs_args"], g["hs_S"]):
+        # mask the ill-conditioned small-qd points: the reference itself is only accurate to
+        # ~2e-16*(24/qd^6-ish cancellation) there: compare where qd >= 0.3
+        ok = q * 2 * row[0] >= 0.3
+        err, same = rel_err(scattering.hard_sphere_sf(q, *row)[ok], ref[ok])
+        assert same and err <= TOL_F64, (row, err)
+    x = g["px"]
+    for (hg, hl), ref in zip(g["voigt_args"], g["voigt"]):
+        # the argument (x/sigma/sqrt2) is rounded differently by 1 ulp at most: on the flank of a
+        # Gaussian core that is a relative change of 2 z^2 ulp, so allow 1e-10 there as everywhere
+        err, same = rel_err(peak_math.voigt(x, hg, hl), ref, floor_frac=0.0)
+        assert same and err <= TOL_F64, (hg, hl, err)
+    for h, ref in zip(g["hwhm"], g["gauss"]):
+        got = peak_math.gaussian(x, h)
+        big = ref > 1e-280      # denormal tail: relative comparison is meaningless there
+        err, _ = rel_err(got[big], ref[big], floor_frac=0.0)
+        assert err <= TOL_F64 and np.all(got[~big] <= 1e-279), (h, err)
+    for h, ref in zip(g["hwhm"], g["lorentz"]):
+        err, same = rel_err(peak_math.lorentzian(x, h), ref, floor_frac=0.0)
+        assert same and err <= TOL_F64, (h, err)
+
+
+def test_faddeeva_against_scipy(eng):
+    """Re w(x+iy) over the whole argument range the Voigt profile can reach."""
+    from scipy.special import wofz
+    from xrsdkit_b200.tools import peak_math
+    x = np.concatenate([np.linspace(0, 9, 3001), np.logspace(0.95, 7, 1500)])
+    for y in (1e-10, 1e-8, 1e-6, 1e-4, 1e-2, 0.1, 0.83, 1.0, 3.0, 7.0, 7.99, 8.0, 20.0, 1e3, 1e6):
+        # voigt(x', hg, hl) = Re w((x'+i hl)/(sigma sqrt2))/(sigma sqrt(2 pi)), sigma = hg/sqrt(2 ln2)
+        hg = 1.0
+        sigma = hg / np.sqrt(2 * np.log(2))
+        got = peak_math.voigt(x * sigma * np.sqrt(2), hg, y * sigma * np.sqrt(2)) * sigma * np.sqrt(2 * np.pi)
+        ref = np.real(wofz(x + 1j * y))
+        err = np.max(np.abs(got - ref) / np.abs(ref))
+        assert err <= 2e-12, (y, err)
+
+
+def test_reflection_tables_bit_exact(golden_tables, golden_definitions, eng):
+    """hkl lists and multiplicities of the reference (greedy symmetrisation) reproduced exactly."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import lowering
+    for case in golden_tables:
+        pars = dict((k, {"value": v}) for k, v in case["latparams"].items())
+        pars.update(r={"value": 5.0})
+        s = System(x=dict(structure="crystalline", form="spherical",
+                          settings={"lattice": case["lattice"], "space_group": case["space_group"],
+                                    "q_min": case["q_min"], "q_max": case["q_max"], "use_symmetry": case["use_symmetry"]},
+                          parameters=pars), source_wavelength=0.8265617)
+        lay = lowering.lower_system(s, np.array([0.1, 1.0]))
+        d_p = eng.to_device(lay.values[None, :])
+        if len(case["hkl"]) > 4096:
+            continue
+        T = eng.build_tables(lay, d_p, 1, params_host=lay.values[None, :], export_reflections=True)
+        n = int(T.n_refl[0].item())
+        got = T.refl_hkl[0, :n].cpu().numpy()
+        assert int(T.n_all[0].item()) == case["n_all"], (case["lattice"], case["space_group"])
+        assert n == len(case["hkl"]), (case["lattice"], case["space_group"], n, len(case["hkl"]))
+        assert got[:, :3].tolist() == case["hkl"], (case["lattice"], case["space_group"])
+        assert got[:, 3].tolist() == case["mult"], (case["lattice"], case["space_group"])
+        # shells conserve the total multiplicity unless extinct shells were pruned
+        ns = int(T.n_shell[0].item())
+        assert 0 < ns <= n
+
+
+def test_reflection_tables_random_lattice_parameters_vs_oracle(golden_definitions, eng):
+    """Seeded random cells per lattice class against the oracle's O(N^2) restatement."""
+    from oracle import xrsd_oracle as orc
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import lowering
+    rs = np.random.RandomState(5)
+    pgs = golden_definitions["sg_point_groups"]
+    cases = [("F_cubic", "Fm-3m"), ("I_cubic", "Im-3m"), ("P_cubic", "Pm-3m"), ("hcp", "P6(3)/mmc"),
+             ("hexagonal", "P6/mmm"), ("triclinic", "P-1"), ("P_orthorhombic", "Pmmm"), ("rhombohedral", "R-3m")]
+    for lat, sg in cases:
+        for _ in range(3):
+            lp = dict(a=rs.uniform(20, 45), b=rs.uniform(20, 45), c=rs.uniform(20, 45),
+                      alpha=rs.uniform(70, 110), beta=rs.uniform(70, 110), gamma=rs.uniform(70, 110))
+            lp = dict((k, lp[k]) for k in orc.lattice_param_names(lat))
+            q_max = rs.uniform(0.5, 0.9)
+            hkl, mult, _ = orc.reflection_table(lat, lp, 0.0, q_max, pgs[sg])
+            pars = dict((k, {"value": v}) for k, v in lp.items())
+            s = System(x=dict(structure="crystalline", form="spherical",
+                              settings={"lattice": lat, "space_group": sg, "q_max": q_max}, parameters=pars),
+                       source_wavelength=0.8265617)
+            lay = lowering.lower_system(s, np.array([0.1, 1.0]))
+            T = eng.build_tables(lay, eng.to_device(lay.values[None, :]), 1, params_host=lay.values[None, :],
+                                 export_reflections=True)
+            n = int(T.n_refl[0].item())
+            got = T.refl_hkl[0, :n].cpu().numpy()
+            assert got[:, :3].tolist() == hkl.astype(int).tolist(), (lat, lp)
+            assert got[:, 3].tolist() == np.asarray(mult).astype(int).tolist(), (lat, lp)
+
+
+def test_cfg2_batch_vs_oracle(ref_tables, eng):
+    """BASELINE cfg2 (polydisperse hard spheres), 48 seeded parameter sets on the full 4096-pt grid."""
+    from oracle import xrsd_oracle as orc
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg2_system(System)
+    q = np.linspace(0.01, 0.5, 4096)
+    lay = batch.layout_of(s, q)
+    P = cfg2_params(lay, 48)
+    I = batch.compute_intensity_batch(lay, q, P)
+    assert I.shape == (48, 4096)
+    for b in range(48):
+        ref = orc.system_intensity(q, params_to_sysdict(s, lay, P[b]), **ref_tables)
+        err, same = rel_err(I[b], ref)
+        assert same and err <= TOL_F64, (b, err, P[b])
+
+
+def test_cfg3_cfg4_batch_vs_oracle(ref_tables, eng):
+    """BASELINE cfg3/cfg4 (FCC Fm-3m voigt, + Guinier-Porod + noise): seeded lattice parameters, each
+    with its own reflection table, local and radial structure-factor modes."""
+    from oracle import xrsd_oracle as orc
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    q = np.linspace(0.01, 1.0, 2048)
+    for make, pars, n in ((lambda S: cfg3_system(S, "local"), cfg3_params, 6),
+                          (lambda S: cfg3_system(S, "radial"), cfg3_params, 3), (cfg4_system, cfg4_params, 4)):
+        s = make(System)
+        lay = batch.layout_of(s, q)
+        P = pars(lay, n)
+        I = batch.compute_intensity_batch(lay, q, P)
+        for b in range(n):
+            ref = orc.system_intensity(q, params_to_sysdict(s, lay, P[b]), **ref_tables)
+            err, same = rel_err(I[b], ref)
+            assert same and err <= TOL_F64, (b, err, P[b])
+
+
+def test_batch_properties_full_size(eng):
+    """Size-independent properties at BASELINE sizes: batched == one-by-one (bit-exact), idempotence,
+    row-permutation equivariance, linearity in I0."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg2_system(System)
+    q = np.linspace(0.01, 0.5, 4096)
+    lay = batch.layout_of(s, q)
+    P = cfg2_params(lay, 10000)
+    I = batch.compute_intensity_batch(lay, q, P, device_out=True)
+    I2 = batch.compute_intensity_batch(lay, q, P, device_out=True)
+    assert bool((I == I2).all())                                     # idempotent, deterministic
+    assert bool(eng.torch.isfinite(I).all())
+    perm = np.random.RandomState(0).permutation(10000)
+    Ip = batch.compute_intensity_batch(lay, q, P[perm], device_out=True)
+    assert bool((Ip == I[eng.torch.as_tensor(perm, device=I.device)]).all())
+    for b in (0, 777, 9999):                                         # single-system launches use other q spans
+        one = batch.compute_intensity_batch(lay, q, P[b:b + 1])
+        np.testing.assert_array_equal(one[0], I[b].cpu().numpy())
+    # linearity: doubling the population I0 doubles (I - noise)
+    P2 = P[:256].copy()
+    P2[:, lay.slot("p__I0")] *= 2
+    a = batch.compute_intensity_batch(lay, q, P[:256]) - 0.01
+    c = batch.compute_intensity_batch(lay, q, P2) - 0.01
+    np.testing.assert_allclose(c, 2 * a, rtol=1e-12, atol=1e-13)
+
+
+def test_ragged_and_edge_inputs(eng, ref_tables):
+    from oracle import xrsd_oracle as orc
+    from xrsdkit_b200.system import System
+    s = cfg2_system(System)
+    assert s.compute_intensity(np.zeros(0)).shape == (0,)
+    for n in (1, 2, 255, 257, 513, 1025):                             # spans that do not fill a CTA tile
+        q = np.linspace(0.02, 0.4, n) if n > 1 else np.array([0.1])
+        ref = orc.system_intensity(q, s.to_dict(), **ref_tables)
+        err, same = rel_err(s.compute_intensity(q), ref)
+        assert same and err <= TOL_F64, (n, err)
+    # q[0] == 0 is special-cased by the reference; a zero elsewhere propagates NaN
+    q = np.array([0.0, 0.1, 0.0, 0.2])
+    with np.errstate(all="ignore"):
+        ref = orc.system_intensity(q, s.to_dict(), **ref_tables)
+    got = s.compute_intensity(q)
+    assert np.isnan(ref[2]) and np.isnan(got[2])
+    err, same = rel_err(got, ref)
+    assert same and err <= TOL_F64
+    # empty reflection table -> zeros (scattering/__init__.py:277-278)
+    x = System(x=dict(structure="crystalline", form="spherical", settings={"lattice": "P_cubic", "q_max": 0.05},
+                      parameters={"a": {"value": 10.0}}), source_wavelength=1.0)
+    np.testing.assert_array_equal(x.compute_intensity(np.linspace(0.01, 0.05, 50)), np.full(50, 1e-3))
+    # narrow Gaussian: I(0) normalisation underflows -> non-finite everywhere, as the reference
+    gsys = System(x=dict(structure="crystalline", form="spherical",
+                         settings={"lattice": "F_cubic", "space_group": "Fm-3m", "q_max": 0.6, "profile": "gaussian"},
+                         parameters={"a": {"value": 40.0}, "hwhm": {"value": 0.002}}), source_wavelength=0.8265617)
+    qg = np.linspace(0.05, 0.6, 300)
+    with np.errstate(all="ignore"):
+        refg = orc.system_intensity(qg, gsys.to_dict(), **ref_tables)
+    gotg = gsys.compute_intensity(qg)
+    assert not np.isfinite(refg).any() and not np.isfinite(gotg).any()
+
+
+def test_error_behaviour(eng):
+    from xrsdkit_b200.system import System, Population
+    with pytest.raises(ValueError):
+        System(x=dict(structure="crystalline", form="spherical", settings={"lattice": "F_cubic"},
+                      parameters={"a": {"value": 40.0}}), source_wavelength=0).compute_intensity(np.linspace(0.1, 1, 10))
+    with pytest.raises(ValueError):
+        System(x=dict(structure="crystalline", form="spherical", settings={"lattice": "F_cubic", "space_group": "Pm-3m"},
+                      parameters={"a": {"value": 40.0}}), source_wavelength=1.0).compute_intensity(np.linspace(0.1, 1, 10))
+    with pytest.raises(ValueError):
+        Population("diffuse", "spherical", {}, {"nope": {"value": 1.0}})
+    with pytest.raises(KeyError):
+        System(p=dict(structure="diffuse", form="atomic", settings={"symbol": "Xx"})).compute_intensity(np.linspace(0.1, 1, 10))

@@ -73,3 +73,49 @@ def compute_intensity_sharded(layout, q, params, group=None, gather=True, eng=No
     if gather and world > 1:
         return gather_rows(local, len(params), group)
     return local
+
+
+_pinned_cache = {}
+
+
+def compute_intensity_pinned(layout, q_host, params_host, out_host, chunks=4, eng=None):
+    """Host-buffer path: params_host [B, n_params] and out_host [B, n_q] are PINNED host tensors.
+
+    The batch is cut into `chunks` slices that alternate between two CUDA streams, so the
+    host->device copy of slice c+1 and the device->host copy of slice c-1 overlap the kernels of
+    slice c.  Returns out_host after both streams have drained."""
+    eng = eng or _engine.get_engine()
+    torch = eng.torch
+    B, n_q = params_host.shape[0], q_host.shape[0]
+    chunks = max(1, min(chunks, B))
+    rows = (B + chunks - 1) // chunks
+    key = (str(eng.device), rows, n_q, params_host.shape[1])
+    if key not in _pinned_cache:
+        _pinned_cache.clear()
+        _pinned_cache[key] = dict(
+            streams=[torch.cuda.Stream(device=eng.device) for _ in range(2)],
+            d_p=[torch.empty((rows, params_host.shape[1]), dtype=torch.float64, device=eng.device) for _ in range(2)],
+            d_I=[torch.empty((rows, n_q), dtype=torch.float64, device=eng.device) for _ in range(2)],
+            d_q=torch.empty(n_q, dtype=torch.float64, device=eng.device))
+    ws = _pinned_cache[key]
+    cur = torch.cuda.current_stream(eng.device)
+    ws["d_q"].copy_(q_host, non_blocking=True)
+    p_np = params_host.numpy() if layout.n_xtal else None
+    for s in ws["streams"]:
+        s.wait_stream(cur)
+    for c in range(chunks):
+        lo, hi = c * rows, min(B, (c + 1) * rows)
+        if lo >= hi:
+            break
+        k = c % 2
+        with torch.cuda.stream(ws["streams"][k]):
+            d_p = ws["d_p"][k][:hi - lo]
+            d_p.copy_(params_host[lo:hi], non_blocking=True)
+            tables = eng.build_tables(layout, d_p, hi - lo, params_host=p_np[lo:hi]) if layout.n_xtal else None
+            d_I = ws["d_I"][k][:hi - lo]
+            eng.intensity(layout, ws["d_q"], d_p, tables=tables, out=d_I)
+            out_host[lo:hi].copy_(d_I, non_blocking=True)
+    for s in ws["streams"]:
+        cur.wait_stream(s)
+    cur.synchronize()
+    return out_host

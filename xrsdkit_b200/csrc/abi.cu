@@ -15,6 +15,7 @@ cudaError_t xrsd_launch_tables(const xrsd_layout_t *, const double *, int, int, 
 cudaError_t xrsd_launch_intensity(const xrsd_layout_t *, const double *, int, const double *, int, int, const xrsd_tables_t *,
                                   double *, long long, int, int, int, cudaStream_t);
 cudaError_t xrsd_launch_fp64_probe(double *, int, int, cudaStream_t);
+cudaError_t xrsd_launch_profile(int, double, double, const double *, int, double *, cudaStream_t);
 cudaError_t xrsd_launch_residual(const xrsd_layout_t *, const xrsd_objective_t *, const double *, int, const double *, int, int,
                                  const xrsd_tables_t *, const double *, const double *, long long, double *, int, int,
                                  cudaStream_t);
@@ -256,6 +257,15 @@ int xrsd_lm_update(double *d_params, int32_t ld_params, int32_t batch, const dou
   cudaError_t e = xrsd_launch_lm_update(d_params, ld_params, batch, d_trial, d_chi2, d_chi2_trial, d_lambda, d_active,
                                         d_n_accept, up, down, ftol, lambda_max, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "lm_update_kernel");
+  return XRSD_OK;
+}
+
+int xrsd_peak_profile(int32_t kind, double hwhm_or_hwhm_g, double hwhm_l, const double *d_x, int32_t n, double *d_out,
+                      void *stream) {
+  if (kind < XRSD_PROFILE_VOIGT || kind > XRSD_PROFILE_LORENTZIAN) return fail(XRSD_EINVAL, "profile kind %d", kind);
+  if (n > 0 && (!d_x || !d_out)) return fail(XRSD_EINVAL, "NULL pointer");
+  cudaError_t e = xrsd_launch_profile(kind, hwhm_or_hwhm_g, hwhm_l, d_x, n, d_out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "profile_kernel");
   return XRSD_OK;
 }
 

@@ -80,6 +80,7 @@ jacobian_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
   __shared__ EvalShared S;
   __shared__ double acc_sm[XRSD_MAX_FREE * (XRSD_MAX_FREE + 1) / 2 + XRSD_MAX_FREE + 2];
   __shared__ double steps[XRSD_MAX_FREE];
+  __shared__ int topo[XRSD_MAX_POPS];
   const int b = blockIdx.x;
   if (b >= batch) return;
   const int tid = threadIdx.x;
@@ -113,7 +114,7 @@ jacobian_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
     const int qc = min(tile_q, n_q - q0);
     for (int v = 0; v < nv; ++v) {
       accumulate_system<2, RM>(L, prm_var + (size_t)v * ldp_s, T, b, q, n_q, q0, qc, Fv + (size_t)v * tile_q, scratch,
-                               scratch_doubles, &S);
+                               scratch_doubles, &S, topo, v == 0 ? 1 : 2);
     }
     // weights, masks, transformed values
     for (int i = tid; i < qc; i += EVAL_THREADS) {

@@ -39,7 +39,29 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters)
   if (s == 123.456) out[0] = s;
 }
 
+// peak profiles on their own (tools/peak_math.py:24-47): out[i] = profile(x[i])
+__global__ void __launch_bounds__(EVAL_THREADS) profile_kernel(int kind, double p0, double p1, const double *__restrict__ x,
+                                                               int n, double *__restrict__ out) {
+  __shared__ VoigtConst vc;
+  Profile P;
+  P.kind = kind; P.h = p0; P.sigma = 1.0; P.norm = 0.46971863934982566 / p0;
+  if (kind == XRSD_PROFILE_VOIGT) {
+    P.sigma = p0 / 1.1774100225154747;
+    voigt_constants(&vc, p1 / P.sigma / M_SQRT2, threadIdx.x);
+  }
+  __syncthreads();
+  for (int i = blockIdx.x * EVAL_THREADS + threadIdx.x; i < n; i += gridDim.x * EVAL_THREADS) out[i] = profile_eval(P, &vc, x[i]);
+}
+
 }  // namespace xrsd
+
+extern "C" cudaError_t xrsd_launch_profile(int kind, double p0, double p1, const double *d_x, int n, double *d_out,
+                                           cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const int blocks = (n + xrsd::EVAL_THREADS - 1) / xrsd::EVAL_THREADS;
+  xrsd::profile_kernel<<<blocks < 1184 ? blocks : 1184, xrsd::EVAL_THREADS, 0, stream>>>(kind, p0, p1, d_x, n, d_out);
+  return cudaGetLastError();
+}
 
 extern "C" cudaError_t xrsd_launch_intensity(const xrsd_layout_t *layout, const double *d_q, int n_q, const double *d_params,
                                              int ldp, int batch, const xrsd_tables_t *tables, double *d_I, long long ldI,

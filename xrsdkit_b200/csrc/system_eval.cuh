@@ -87,7 +87,10 @@ template <int QPT, bool RADIAL_MULTI>
 __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restrict__ prm, const xrsd_tables_t &T, int b,
                                   const double *__restrict__ q, int n_q, int q_begin, int q_count,
                                   double *__restrict__ I_sm, double *__restrict__ scratch, int scratch_doubles,
-                                  EvalShared *S) {
+                                  EvalShared *S, int *topo = nullptr, int topo_mode = 0) {
+  // topo (shared memory, one int per population) pins the discrete part of the evaluation across
+  // the parameter variants of a finite-difference Jacobian: mode 1 records the number
+  // of radii of each size quadrature, mode 2 reuses the recorded value instead of recomputing ceil().
   const int tid = threadIdx.x;
   for (int i = tid; i < q_count; i += EVAL_THREADS) I_sm[i] = 0.0;
   const int span = EVAL_THREADS * QPT;
@@ -137,6 +140,8 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
             // numpy.arange(r_min, r_max, dr): len = ceil((stop-start)/step), r_i = start + i*((start+step)-start)
             const double len = ceil(__dsub_rn(r_max, r_min) / dr);
             n_r = (len > 0.0) ? (int)fmin(len, (double)(scratch_doubles / 2)) : 0;
+            if (topo_mode == 2) n_r = topo[ip];
+            else if (topo_mode == 1 && tid == 0) topo[ip] = n_r;
             dstep = __dsub_rn(__dadd_rn(r_min, dr), r_min);
             r_first = r_min;
             const double two_s2 = 2.0 * (sigma_r * sigma_r);

@@ -214,6 +214,15 @@ class Engine(object):
         self.launches += 1
         return out
 
+    def peak_profile(self, kind, x, p0, p1=0.0):
+        """gaussian / lorentzian / voigt of tools/peak_math.py evaluated on the device."""
+        d_x = self.to_device(x)
+        out = self.torch.empty_like(d_x)
+        abi.check(self.lib.xrsd_peak_profile(abi.PROFILE[kind], float(p0), float(p1), d_x.data_ptr(), d_x.numel(),
+                                             out.data_ptr(), self._stream()))
+        self.launches += 1
+        return out
+
     def probe_fp64_peak(self):
         t, ms = C.c_double(), C.c_double()
         abi.check(self.lib.xrsd_probe_fp64_peak(C.byref(t), C.byref(ms), self._stream()))
