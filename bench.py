@@ -261,11 +261,13 @@ def run_gpu_arm(args):
     rs = np.random.RandomState(1000 + rank)
     d_params = [eng.to_device(P[rs.permutation(B)]) for _ in range(4)]
     outs = [torch.empty((B, n_q), dtype=torch.float64, device=dev) for _ in range(2)]
+    from xrsdkit_b200 import lowering
+    max_cells = lowering.max_cells(lay, P) if lay.n_xtal else None
     tables = [eng.build_tables(lay, p, B, params_host=P) if lay.n_xtal else None for p in d_params]
 
     def step(i):
         if lay.n_xtal and args.workload == "cfg3":
-            t = eng.build_tables(lay, d_params[i % 4], B, params_host=P, check=False)   # table build is part of the step
+            t = eng.build_tables(lay, d_params[i % 4], B, max_cells=max_cells, check=False, reuse=tables[i % 4])   # table build is part of the step
         else:
             t = tables[i % 4]
         eng.intensity(lay, d_q, d_params[i % 4], tables=t, out=outs[i % 2])

@@ -112,7 +112,8 @@ typedef struct xrsd_tables {
   int32_t cap_shell;           /* shells per table the arrays below can hold            */
   int32_t cap_refl;            /* reduced reflections per table (0: do not export)      */
   int32_t n_pairs_max;         /* leading dimension of shell_geo (<= XRSD_MAX_PAIRS)    */
-  int32_t reserved0;
+  int32_t cap_list_hint;       /* reduced reflections the builder keeps in shared memory (0 = auto: 1024 or
+                                  4096; XRSD_TABLE_LIST_OVERFLOW asks for a retry with a larger value) */
   int32_t *n_shell;            /* [n_tables]                                             */
   int32_t *n_refl;             /* [n_tables] reduced reflections (before shell merging)  */
   int32_t *n_all;              /* [n_tables] reflections in the G_min..G_max shell       */

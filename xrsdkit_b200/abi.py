@@ -43,7 +43,7 @@ class Layout(C.Structure):
 
 
 class Tables(C.Structure):
-    _fields_ = [("cap_shell", i32), ("cap_refl", i32), ("n_pairs_max", i32), ("reserved0", i32),
+    _fields_ = [("cap_shell", i32), ("cap_refl", i32), ("n_pairs_max", i32), ("cap_list_hint", i32),
                 ("n_shell", C.c_void_p), ("n_refl", C.c_void_p), ("n_all", C.c_void_p), ("status", C.c_void_p),
                 ("shell_hkl", C.c_void_p), ("shell_geo", C.c_void_p), ("refl_hkl", C.c_void_p)]
 

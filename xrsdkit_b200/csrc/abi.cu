@@ -135,27 +135,38 @@ int xrsd_reflection_tables(const xrsd_layout_t *layout, const double *d_params, 
   if (rc) return rc;
   if (!d_params || ld_params < layout->n_params) return fail(XRSD_EINVAL, "params: NULL or ld_params < n_params");
   if (max_cells < 1) return fail(XRSD_EINVAL, "max_cells=%d", max_cells);
-  // largest power-of-two reflection list that fits beside the candidate box
-  int cap_list = 4096;
+  // reflection-list capacity (power of two): the caller's hint, else 1024 when every crystalline
+  // population is reduced by >= 3 operations (the reduced list is then a small fraction of the
+  // shell) and 4096 otherwise; shrunk until it fits beside the candidate box
+  int cap_list = tables->cap_list_hint;
+  if (cap_list <= 0) {
+    cap_list = 1024;
+    for (int i = 0; i < layout->n_pops; ++i) {
+      const xrsd_pop_t &p = layout->pops[i];
+      if (p.kind == XRSD_POP_CRYSTALLINE && !(p.use_symmetry && p.n_ops >= 3)) cap_list = 4096;
+    }
+  }
+  int pow2 = 64;
+  while (pow2 < cap_list && pow2 < 4096) pow2 <<= 1;
+  cap_list = pow2;
   while (cap_list > 64 && xrsd_table_smem_layout(max_cells, cap_list) + kStaticSmem > kMaxSmem) cap_list >>= 1;
   if (xrsd_table_smem_layout(max_cells, cap_list) + kStaticSmem > kMaxSmem)
     return fail(XRSD_ECAPACITY, "candidate box of %d cells does not fit in shared memory", max_cells);
-  // do not reserve more list than the box can hold
-  while (cap_list / 2 >= max_cells && cap_list > 64) cap_list >>= 1;
   cudaError_t e = xrsd_launch_tables(layout, d_params, ld_params, batch, tables, max_cells, cap_list, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "reflection_table_kernel");
   return XRSD_OK;
 }
 
 static int pick_q_per_cta(int n_q, int batch, int scratch) {
-  // whole-pattern CTAs when the batch alone fills the machine, else split q so that
-  // about 8 CTAs per SM exist; spans are multiples of 512 (256 threads x 2 q-points)
-  const long long want_ctas = 148LL * 8;
+  // One CTA holds a span of one pattern in shared memory.  Spans are multiples of 512 q-points;
+  // aim for >= 24 CTAs per SM in the grid (several waves, so the last partial wave costs little)
+  // and keep the span under 64 KB so that at least three CTAs stay resident per SM.
+  const long long want_ctas = 148LL * 24;
   long long tiles = (want_ctas + batch - 1) / batch;
   if (tiles < 1) tiles = 1;
   long long per = ((long long)n_q + tiles - 1) / tiles;
   per = ((per + 511) / 512) * 512;
-  const long long cap = std::max(512LL, ((long long)(96 * 1024 / 8 - scratch) / 512) * 512);   // <= 96 KB -> 2 CTAs/SM
+  const long long cap = std::max(512LL, ((long long)(64 * 1024 / 8 - scratch) / 512) * 512);
   per = std::min(per, cap);
   per = std::min<long long>(per, ((long long)n_q + 511) / 512 * 512);
   return (int)std::max(512LL, per);

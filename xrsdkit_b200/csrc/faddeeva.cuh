@@ -54,36 +54,40 @@ __device__ __forceinline__ void voigt_constants(VoigtConst *vc, double y, int ti
   }
 }
 
-// asymptotic branch, |z|^2 >= 64.  Coefficients c_k = (2k-1)!!/2^k.
+// asymptotic branch, |z|^2 >= 64.  Coefficients c_k = (2k-1)!!/2^k; the number of terms follows
+// from |z|^2 so that the first neglected term is < 1e-13 relative.
 __device__ __forceinline__ double rew_far(double x, double y, double z2) {
-  const double r2 = 1.0 / z2;
+  const double r2 = __drcp_rn(z2);
   const double r4 = r2 * r2;
   const double ur = (x * x - y * y) * r4;   // u = 1/z^2
   const double ui = -2.0 * x * y * r4;
   double pr, pi = 0.0;
 #define XRSD_H(ck) { const double t_ = fma(pr, ur, fma(-pi, ui, (ck))); pi = fma(pr, ui, pi * ur); pr = t_; }
-  if (z2 >= 16384.0) {          // 3 terms: (2k-1)!!/(2 z2)^k < 1e-13 from k=4
-    pr = 1.875;
-    XRSD_H(0.75) XRSD_H(0.5) XRSD_H(1.0)
-  } else if (z2 >= 1024.0) {    // 5 terms
-    pr = 29.53125;
-    XRSD_H(6.5625) XRSD_H(1.875) XRSD_H(0.75) XRSD_H(0.5) XRSD_H(1.0)
-  } else if (z2 >= 256.0) {     // 7 terms
-    pr = 1055.7421875;
-    XRSD_H(162.421875) XRSD_H(29.53125) XRSD_H(6.5625) XRSD_H(1.875) XRSD_H(0.75) XRSD_H(0.5) XRSD_H(1.0)
-  } else {                      // 12 terms down to |z| = 8
-    pr = 77205601.37329102;
-    XRSD_H(6713530.554199219) XRSD_H(639383.8623046875) XRSD_H(67303.564453125) XRSD_H(7918.06640625)
-    XRSD_H(1055.7421875) XRSD_H(162.421875) XRSD_H(29.53125) XRSD_H(6.5625) XRSD_H(1.875) XRSD_H(0.75)
-    XRSD_H(0.5) XRSD_H(1.0)
+  if (z2 >= 1024.0) {
+    if (z2 >= 16384.0) {        // 3 terms
+      pr = 1.875;
+    } else {                    // 5 terms
+      pr = 29.53125;
+      XRSD_H(6.5625) XRSD_H(1.875)
+    }
+  } else {
+    if (z2 >= 256.0) {          // 7 terms
+      pr = 1055.7421875;
+    } else {                    // 12 terms down to |z| = 8
+      pr = 77205601.37329102;
+      XRSD_H(6713530.554199219) XRSD_H(639383.8623046875) XRSD_H(67303.564453125) XRSD_H(7918.06640625)
+      XRSD_H(1055.7421875)
+    }
+    XRSD_H(162.421875) XRSD_H(29.53125) XRSD_H(6.5625) XRSD_H(1.875)
   }
+  XRSD_H(0.75) XRSD_H(0.5) XRSD_H(1.0)
 #undef XRSD_H
   // i/z = (y + i x)/|z|^2  ->  Re[(i/z) P] = (y Re P - x Im P)/|z|^2
   return r2 * (y * pr - x * pi) * 0.56418958354775628695;   // 1/sqrt(pi)
 }
 
 // exponential-series branch, |z|^2 < 64 (so |x| < 8).  x must be >= 0 (Re w is even in x).
-__device__ __forceinline__ double rew_near(double x, const VoigtConst *vc) {
+static __device__ __noinline__ double rew_near(double x, const VoigtConst *vc) {
   const double y = vc->y;
   const double ex2 = exp(-x * x);
   const double E = exp(2.0 * VOIGT_A * x);

@@ -33,8 +33,8 @@ __device__ __forceinline__ bool fit_weight(const xrsd_objective_t &O, double qv,
   return fit;
 }
 
-template <bool RM>
-__global__ void __launch_bounds__(EVAL_THREADS, 2)
+template <bool RM, bool HX>
+__global__ void __launch_bounds__(EVAL_THREADS, HX ? 4 : 6)
 residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t O, const double *__restrict__ q, int n_q,
                 const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
                 const double *__restrict__ Iobs, const double *__restrict__ dI, long long ld_obs,
@@ -45,7 +45,7 @@ residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
   if (b >= batch) return;
   double *I_sm = smem_d;
   double *scratch = smem_d + ((n_q + 1) & ~1);
-  accumulate_system<2, RM>(L, params + (size_t)b * ldp, T, b, q, n_q, 0, n_q, I_sm, scratch, scratch_doubles, &S);
+  accumulate_system<2, RM, HX>(L, params + (size_t)b * ldp, T, b, q, n_q, 0, n_q, I_sm, scratch, scratch_doubles, &S);
   const double *obs = Iobs + (size_t)b * ld_obs;
   const double *err = dI ? dI + (size_t)b * ld_obs : nullptr;
   double num = 0.0, den = 0.0;
@@ -69,8 +69,8 @@ residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
 
 // Normal equations by forward differences.  Shared memory: prm_var[(n_free+1)][ldp_s],
 // F[(n_free+1)][tile_q] (log I or I per variant), wts[tile_q], fobs[tile_q], scratch.
-template <bool RM>
-__global__ void __launch_bounds__(EVAL_THREADS, 2)
+template <bool RM, bool HX>
+__global__ void __launch_bounds__(EVAL_THREADS, HX ? 4 : 6)
 jacobian_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t O, const double *__restrict__ q, int n_q,
                 const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
                 const double *__restrict__ Iobs, const double *__restrict__ dI, long long ld_obs,
@@ -113,7 +113,7 @@ jacobian_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
   for (int q0 = 0; q0 < n_q; q0 += tile_q) {
     const int qc = min(tile_q, n_q - q0);
     for (int v = 0; v < nv; ++v) {
-      accumulate_system<2, RM>(L, prm_var + (size_t)v * ldp_s, T, b, q, n_q, q0, qc, Fv + (size_t)v * tile_q, scratch,
+      accumulate_system<2, RM, HX>(L, prm_var + (size_t)v * ldp_s, T, b, q, n_q, q0, qc, Fv + (size_t)v * tile_q, scratch,
                                scratch_doubles, &S, topo, v == 0 ? 1 : 2);
     }
     // weights, masks, transformed values
@@ -286,7 +286,8 @@ extern "C" cudaError_t xrsd_launch_residual(const xrsd_layout_t *layout, const x
                                             cudaStream_t stream) {
   using namespace xrsd;
   const size_t smem = ((size_t)((n_q + 1) & ~1) + (size_t)scratch_doubles) * sizeof(double);
-  auto kern = radial_multi ? residual_kernel<true> : residual_kernel<false>;
+  auto kern = radial_multi ? residual_kernel<true, true>
+                           : (layout->n_xtal ? residual_kernel<false, true> : residual_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (batch <= 0) return cudaSuccess;
@@ -312,7 +313,8 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
   F.n_free = n_free;
   for (int i = 0; i < XRSD_MAX_FREE; ++i) F.idx[i] = (i < n_free) ? free_idx[i] : 0;
   const size_t smem = xrsd_jacobian_smem(layout->n_params, n_free, tile_q, scratch_doubles);
-  auto kern = radial_multi ? jacobian_kernel<true> : jacobian_kernel<false>;
+  auto kern = radial_multi ? jacobian_kernel<true, true>
+                           : (layout->n_xtal ? jacobian_kernel<false, true> : jacobian_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (batch <= 0) return cudaSuccess;

@@ -15,16 +15,14 @@ __device__ __forceinline__ double sqr(double x) { return x * x; }
 // where the closed form cancels).  t = x^3 (1/3 - x^2/30 + x^4/840 - ...),
 // coefficient k: (-1)^(k+1) 2k/(2k+1)!
 __device__ __forceinline__ double sphere_t_series(double x) {
-  const double x2 = x * x;
-  double p = -4.498331606952833e-14;            // -16/17!  (k=8)
-  p = fma(p, x2, 1.0706029224547743e-11);      //  14/15!
-  p = fma(p, x2, -1.9270852604185937e-09);     // -12/13!
-  p = fma(p, x2, 2.505210838544172e-07);       //  10/11!
-  p = fma(p, x2, -2.2045855379188714e-05);     //  -8/9!
-  p = fma(p, x2, 1.1904761904761906e-03);      //   6/7!
-  p = fma(p, x2, -3.333333333333333e-02);      //  -4/5!
-  p = fma(p, x2, 3.333333333333333e-01);       //   2/3!
-  return p * x2 * x;
+  // Estrin evaluation (dependency depth 4 instead of 8): p(y) = sum_k c_k y^k, y = x^2
+  const double y = x * x, y2 = y * y, y4 = y2 * y2;
+  const double a0 = fma(-3.333333333333333e-02, y, 3.333333333333333e-01);      //  2/3!  - 4/5! y
+  const double a1 = fma(-2.2045855379188714e-05, y, 1.1904761904761906e-03);    //  6/7!  - 8/9! y
+  const double a2 = fma(-1.9270852604185937e-09, y, 2.505210838544172e-07);     // 10/11! - 12/13! y
+  const double a3 = fma(-4.498331606952833e-14, y, 1.0706029224547743e-11);     // 14/15! - 16/17! y
+  const double b0 = fma(a1, y2, a0), b1 = fma(a3, y2, a2);
+  return fma(b1, y4, b0) * y * x;
 }
 
 // sphere amplitude 3 (sin x - x cos x) / x^3 : scattering/form_factors.py:20-28.
@@ -83,36 +81,31 @@ __device__ __forceinline__ HSConst hs_constants(double r_hard, double v_fraction
   return k;
 }
 
-__device__ __forceinline__ double hard_sphere_sf(double q, const HSConst &k, bool is_q0_zero) {
-  double nc;
-  if (is_q0_zero) {
-    nc = k.nc0;
-  } else {
-    // unfused arithmetic in the reference's order: the three brackets cancel to O(qd^2)
-    // relative, so an FMA contraction here would move the result by more
-    // than the tolerance at small qd.
-    const double qd = q * k.d;
-    const double qd2 = __dmul_rn(qd, qd), qd3 = __dmul_rn(qd2, qd), qd4 = __dmul_rn(qd2, qd2), qd6 = __dmul_rn(qd3, qd3);
-    double s, c;
-    sincos(qd, &s, &c);
-    const double p = k.p;
-    const double x1 = __dsub_rn(s, __dmul_rn(qd, c)) / qd3;
-    double t2 = __dsub_rn(__dmul_rn(qd2, c), __dmul_rn(__dmul_rn(2.0, qd), s));
-    t2 = __dadd_rn(__dsub_rn(t2, __dmul_rn(2.0, c)), 2.0);
-    const double x2 = t2 / qd4;
-    double t3 = __dsub_rn(__dmul_rn(qd4, c), __dmul_rn(__dmul_rn(4.0, qd3), s));
-    t3 = __dsub_rn(t3, __dmul_rn(__dmul_rn(12.0, qd2), c));
-    t3 = __dadd_rn(t3, __dmul_rn(__dmul_rn(24.0, qd), s));
-    t3 = __dsub_rn(__dadd_rn(t3, __dmul_rn(24.0, c)), 24.0);
-    const double x3 = t3 / qd6;
-    double br = __dmul_rn(k.l1, x1);
-    br = __dsub_rn(br, __dmul_rn(__dmul_rn(__dmul_rn(6.0, p), k.l2), x2));
-    br = __dsub_rn(br, __dmul_rn(__dmul_rn(p, k.l1) / 2.0, x3));
-    nc = __dmul_rn(__dmul_rn(-24.0, p), br);
-  }
-  const double F = 1.0 / (1.0 - nc);
-  const double F0 = 1.0 / (1.0 - k.nc0);
-  return F / F0;
+// Returns nc(q d); S(q)/S(0) = (1 - nc0)/(1 - nc).  The three cancelling numerators are formed
+// unfused in the reference's order (an FMA contraction there would move the result
+// by more than the tolerance at small qd); their quotients by qd^3, qd^4, qd^6 are taken through
+// one reciprocal of qd, which perturbs each O(1) bracket by ~1 ulp and is not amplified.
+__device__ __forceinline__ double hard_sphere_nc(double q, const HSConst &k, bool is_q0_zero) {
+  if (is_q0_zero) return k.nc0;
+  const double qd = q * k.d;
+  const double qd2 = __dmul_rn(qd, qd), qd3 = __dmul_rn(qd2, qd), qd4 = __dmul_rn(qd2, qd2);
+  double s, c;
+  sincos(qd, &s, &c);
+  const double p = k.p;
+  const double r1 = 1.0 / qd, r2 = r1 * r1, r3 = r2 * r1, r4 = r2 * r2, r6 = r3 * r3;
+  const double x1 = __dsub_rn(s, __dmul_rn(qd, c)) * r3;
+  double t2 = __dsub_rn(__dmul_rn(qd2, c), __dmul_rn(__dmul_rn(2.0, qd), s));
+  t2 = __dadd_rn(__dsub_rn(t2, __dmul_rn(2.0, c)), 2.0);
+  const double x2 = t2 * r4;
+  double t3 = __dsub_rn(__dmul_rn(qd4, c), __dmul_rn(__dmul_rn(4.0, qd3), s));
+  t3 = __dsub_rn(t3, __dmul_rn(__dmul_rn(12.0, qd2), c));
+  t3 = __dadd_rn(t3, __dmul_rn(__dmul_rn(24.0, qd), s));
+  t3 = __dsub_rn(__dadd_rn(t3, __dmul_rn(24.0, c)), 24.0);
+  const double x3 = t3 * r6;
+  double br = __dmul_rn(k.l1, x1);
+  br = __dsub_rn(br, __dmul_rn(__dmul_rn(__dmul_rn(6.0, p), k.l2), x2));
+  br = __dsub_rn(br, __dmul_rn(__dmul_rn(p, k.l1) / 2.0, x3));
+  return __dmul_rn(__dmul_rn(-24.0, p), br);
 }
 
 }  // namespace xrsd

@@ -6,8 +6,8 @@
 
 namespace xrsd {
 
-template <int QPT, bool RM>
-__global__ void __launch_bounds__(EVAL_THREADS, 2)
+template <int QPT, bool RM, bool HX>
+__global__ void __launch_bounds__(EVAL_THREADS, HX ? 6 : 6)
 intensity_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ q, int n_q,
                  const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
                  double *__restrict__ I_out, long long ldI, int q_per_cta, int n_tiles, int scratch_doubles) {
@@ -21,7 +21,7 @@ intensity_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restri
   const int q_count = min(q_per_cta, n_q - q_begin);
   double *I_sm = smem_d;
   double *scratch = smem_d + ((q_per_cta + 1) & ~1);
-  accumulate_system<QPT, RM>(L, params + (size_t)b * ldp, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S);
+  accumulate_system<QPT, RM, HX>(L, params + (size_t)b * ldp, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S);
   double *dst = I_out + (size_t)b * ldI + q_begin;
   for (int i = threadIdx.x; i < q_count; i += EVAL_THREADS) dst[i] = I_sm[i];
 }
@@ -44,11 +44,8 @@ __global__ void __launch_bounds__(EVAL_THREADS) profile_kernel(int kind, double 
                                                                int n, double *__restrict__ out) {
   __shared__ VoigtConst vc;
   Profile P;
-  P.kind = kind; P.h = p0; P.sigma = 1.0; P.norm = 0.46971863934982566 / p0;
-  if (kind == XRSD_PROFILE_VOIGT) {
-    P.sigma = p0 / 1.1774100225154747;
-    voigt_constants(&vc, p1 / P.sigma / M_SQRT2, threadIdx.x);
-  }
+  const double y = make_profile(P, kind, p0, p1);
+  if (kind == XRSD_PROFILE_VOIGT) voigt_constants(&vc, y, threadIdx.x);
   __syncthreads();
   for (int i = blockIdx.x * EVAL_THREADS + threadIdx.x; i < n; i += gridDim.x * EVAL_THREADS) out[i] = profile_eval(P, &vc, x[i]);
 }
@@ -69,7 +66,8 @@ extern "C" cudaError_t xrsd_launch_intensity(const xrsd_layout_t *layout, const 
   using namespace xrsd;
   const int n_tiles = (n_q + q_per_cta - 1) / q_per_cta;
   const size_t smem = ((size_t)((q_per_cta + 1) & ~1) + (size_t)scratch_doubles) * sizeof(double);
-  auto kern = radial_multi ? intensity_kernel<2, true> : intensity_kernel<2, false>;
+  auto kern = radial_multi ? intensity_kernel<2, true, true>
+                           : (layout->n_xtal ? intensity_kernel<2, false, true> : intensity_kernel<2, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long long n_blocks = (long long)batch * n_tiles;

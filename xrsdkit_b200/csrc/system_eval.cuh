@@ -29,7 +29,7 @@
 
 namespace xrsd {
 
-constexpr int EVAL_THREADS = 256;
+constexpr int EVAL_THREADS = 128;
 constexpr int SHELL_CHUNK = 128;
 
 // shared-memory working set of one CTA (besides the pattern buffer)
@@ -52,23 +52,41 @@ __device__ __forceinline__ double block_sum(double v, EvalShared *S) {
   return t;
 }
 
-// peak profiles: tools/peak_math.py:24-47
+// peak profiles: tools/peak_math.py:24-47.  The per-pattern constants are folded into
+// reciprocals once (make_profile) so that the per-(q, shell) evaluation has no division except
+// the 1/|z|^2 of the Faddeeva far field; this reorders the reference's x/sigma/sqrt(2) by <= 2 ulp.
 struct Profile {
   int kind;
-  double h;          // gaussian / lorentzian hwhm
-  double sigma;      // voigt
-  double norm;       // gaussian: sqrt(ln2/pi)/h
+  double a;          // voigt: 1/(sigma sqrt 2)      gaussian: 1/h            lorentzian: h^2
+  double b;          // voigt: 1/(sigma sqrt(2 pi))  gaussian: sqrt(ln2/pi)/h lorentzian: h/pi
 };
 
-__device__ __forceinline__ double profile_eval(const Profile &P, const VoigtConst *vc, double x) {
-  if (P.kind == XRSD_PROFILE_VOIGT) {
-    const double zr = x / P.sigma / M_SQRT2;                       // (x + i gamma)/sigma/sqrt(2)
-    return rew(zr, vc) / P.sigma / 2.5066282746310002;             // /sigma/sqrt(2 pi)
-  } else if (P.kind == XRSD_PROFILE_GAUSSIAN) {
-    const double u = x / P.h;
-    return P.norm * exp(-(u * u) * 0.6931471805599453);            // exp(-(x/h)**2 * ln 2)
+// returns y = gamma/(sigma sqrt 2) for voigt (0 otherwise)
+__device__ __forceinline__ double make_profile(Profile &P, int kind, double p0, double p1) {
+  P.kind = kind;
+  if (kind == XRSD_PROFILE_VOIGT) {
+    const double sigma = p0 / 1.1774100225154747;                  // hwhm_g / sqrt(2 ln 2)
+    P.a = 1.0 / sigma / M_SQRT2;
+    P.b = 1.0 / sigma / 2.5066282746310002;                        // 1/sigma/sqrt(2 pi)
+    return p1 / sigma / M_SQRT2;
   }
-  return P.h / M_PI / (x * x + P.h * P.h);
+  if (kind == XRSD_PROFILE_GAUSSIAN) {
+    P.a = 1.0 / p0;
+    P.b = 0.46971863934982566 / p0;                                // sqrt(ln2/pi)/h
+  } else {
+    P.a = p0 * p0;
+    P.b = p0 / M_PI;
+  }
+  return 0.0;
+}
+
+__device__ __forceinline__ double profile_eval(const Profile &P, const VoigtConst *vc, double x) {
+  if (P.kind == XRSD_PROFILE_VOIGT) return rew(x * P.a, vc) * P.b;
+  if (P.kind == XRSD_PROFILE_GAUSSIAN) {
+    const double u = x * P.a;
+    return P.b * exp(-(u * u) * 0.6931471805599453);               // exp(-(x/h)**2 * ln 2)
+  }
+  return P.b / fma(x, x, P.a);
 }
 
 // form factor of species `a` of a crystalline population at q
@@ -83,7 +101,7 @@ __device__ __forceinline__ int pair_index(int n_sp, int a, int b) { return a * n
 // Accumulate I(q) of system `b` for q[q_begin .. q_begin+q_count) into I_sm[0 .. q_count).
 // All EVAL_THREADS threads of the CTA must call this.  `scratch` holds scratch_doubles doubles.
 // ------------------------------------------------------------------------------------------
-template <int QPT, bool RADIAL_MULTI>
+template <int QPT, bool RADIAL_MULTI, bool HAS_XTAL = true>
 __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restrict__ prm, const xrsd_tables_t &T, int b,
                                   const double *__restrict__ q, int n_q, int q_begin, int q_count,
                                   double *__restrict__ I_sm, double *__restrict__ scratch, int scratch_doubles,
@@ -159,7 +177,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         }
         __syncthreads();
         for (int off = 0; off < q_count; off += span) {
-          double qv[QPT], ff2[QPT];
+          double qv[QPT], ff2[QPT], den[QPT];
           bool ok[QPT], q0[QPT];
 #pragma unroll
           for (int j = 0; j < QPT; ++j) {
@@ -168,6 +186,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
             qv[j] = q[q_begin + (ok[j] ? i : q_count - 1)];
             q0[j] = L.q0_is_zero && (q_begin + i == 0);
             ff2[j] = 0.0;
+            den[j] = 1.0;
           }
           if (pop.form == XRSD_FORM_ATOMIC) {
 #pragma unroll
@@ -222,23 +241,27 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
             }
 #pragma unroll
             for (int j = 0; j < QPT; ++j) {
+              // ff2 = 9 acc / (q^6 norm), kept as numerator / denominator: one division below
               const double q2 = qv[j] * qv[j];
-              ff2[j] = q0[j] ? 1.0 : 9.0 * acc[j] / ((q2 * q2 * q2) * norm);
+              ff2[j] = q0[j] ? 1.0 : 9.0 * acc[j];
+              den[j] = q0[j] ? 1.0 : (q2 * q2 * q2) * norm;
             }
           }
 #pragma unroll
           for (int j = 0; j < QPT; ++j) {
             if (!ok[j]) continue;
             const int i = off + tid + j * EVAL_THREADS;
-            double v;
-            if (pop.disordered) v = I0 * hard_sphere_sf(qv[j], hs, q0[j]) * ff2[j];   // I0 * sf * ff_sqr
-            else v = I0 * ff2[j];
-            I_sm[i] += v;
+            double num = I0 * ff2[j], dn = den[j];
+            if (pop.disordered) {                                  // I0 * sf * ff_sqr, sf = (1-nc0)/(1-nc)
+              num *= (1.0 - hs.nc0);
+              dn *= (1.0 - hard_sphere_nc(qv[j], hs, q0[j]));
+            }
+            I_sm[i] += num / dn;
           }
         }
       } break;
       // ---------------------------------------------------------------- crystalline
-      case XRSD_POP_CRYSTALLINE: {
+      case XRSD_POP_CRYSTALLINE: if (HAS_XTAL) {
         const int t = b * L.n_xtal + pop.table_slot;
         const int n_shell = T.n_shell[t];
         if (n_shell <= 0) break;                                   // scattering/__init__.py:277-278
@@ -250,16 +273,12 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         const bool radial = pop.sf_radial != 0;
         const bool radial_multi = RADIAL_MULTI && radial && n_sp > 1;
         Profile P;
-        P.kind = pop.profile;
-        P.h = 0.0; P.sigma = 1.0; P.norm = 0.0;
         if (tid == 0) make_cell(pop, prm, &S->cell);
-        if (P.kind == XRSD_PROFILE_VOIGT) {
-          const double hg = prm[pop.p_hwhm_g], hl = prm[pop.p_hwhm_l];
-          P.sigma = hg / 1.1774100225154747;                        // sqrt(2 ln 2)
-          voigt_constants(&S->vc, hl / P.sigma / M_SQRT2, tid);
+        if (pop.profile == XRSD_PROFILE_VOIGT) {
+          const double y = make_profile(P, pop.profile, prm[pop.p_hwhm_g], prm[pop.p_hwhm_l]);
+          voigt_constants(&S->vc, y, tid);
         } else {
-          P.h = prm[pop.p_hwhm];
-          P.norm = 0.46971863934982566 / P.h;                       // sqrt(ln2/pi)/h
+          make_profile(P, pop.profile, prm[pop.p_hwhm], 0.0);
         }
         __syncthreads();
         // pass A: normalisation I(0) = sum_s W0_s * profile(0 - q_s)   (scattering/__init__.py:305,331)
@@ -283,6 +302,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         const int rec = 1 + wstride;
         int chunk = scratch_doubles / rec;
         if (chunk > SHELL_CHUNK) chunk = SHELL_CHUNK;
+        const bool stage_once = n_shell <= chunk;
         for (int off = 0; off < q_count; off += span) {
           double qv[QPT], acc[QPT];
           double accp[QPT][RADIAL_MULTI ? XRSD_MAX_PAIRS : 1];
@@ -300,6 +320,9 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
             for (int k = 0; k < (RADIAL_MULTI ? XRSD_MAX_PAIRS : 1); ++k) accp[j][k] = 0.0;
           for (int s0 = 0; s0 < n_shell; s0 += chunk) {
             const int ns = min(chunk, n_shell - s0);
+            // (q_s, W_s) of this chunk; when all shells fit in one chunk they are staged once per
+            // population instead of once per q-span
+            if (!(stage_once && off > 0)) {
             __syncthreads();
             for (int sl = tid; sl < ns; sl += EVAL_THREADS) {
               const int s = s0 + sl;
@@ -329,6 +352,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               }
             }
             __syncthreads();
+            }
             if (!radial_multi) {
               for (int sl = 0; sl < ns; ++sl) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);

@@ -169,13 +169,26 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
   if (S.n_all == 0) { finish(0); return; }   // scattering/__init__.py:277-278 -> zeros
 
   // ---- 2. greedy reduction, one operation after the other (scattering/symmetries.py:61-90)
-  if (pop.use_symmetry) {
+  if (pop.use_symmetry && pop.n_ops > 0) {
     const int rk = S.hmax[1] - S.hmin[1] + 1, rl = S.hmax[2] - S.hmin[2] + 1;   // symmetries.py:54-55
+    // visit only the points in the shell: an (unordered) list of their cells as uint16, laid over the
+    // sort/shell scratch (20 bytes per list slot, not yet in use), when cells and list fit
+    uint16_t *alive = reinterpret_cast<uint16_t *>(keys);
+    const bool use_list = S.cells <= 65535 && S.n_all <= 10 * cap_list;
+    if (use_list) {
+      for (int c = tid; c < S.cells; c += TABLE_THREADS)
+        if (grid[c]) alive[atomicAdd(&S.scan_carry, 1)] = (uint16_t)c;
+      __syncthreads();
+      if (tid == 0) S.scan_carry = 0;
+      __syncthreads();
+    }
+    const int n_visit = use_list ? S.n_all : S.cells;
     for (int iop = 0; iop < pop.n_ops; ++iop) {
       int perm[3];
       double sgn[3];
       sym_op(pop.ops[iop], perm, sgn);
-      for (int c = tid; c < S.cells; c += TABLE_THREADS) {
+      for (int iv = tid; iv < n_visit; iv += TABLE_THREADS) {
+        const int c = use_list ? (int)alive[iv] : iv;
         const unsigned mi = grid[c];
         if (!mi) continue;
         int h, k, l;
@@ -214,30 +227,43 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
     }
   }
 
-  // ---- 3. ordered compaction (l outer, k, h inner = cell order)
+  // ---- 3. ordered compaction (l outer, k, h inner = cell order): each thread owns a contiguous
+  //         run of cells, one block-wide scan of the per-thread counts gives the output offsets
   {
     int32_t *out_refl = (T.refl_hkl && T.cap_refl > 0) ? T.refl_hkl + (size_t)t * T.cap_refl * 4 : nullptr;
-    for (int c0 = 0; c0 < S.cells; c0 += TABLE_THREADS) {
-      const int c = c0 + tid;
-      const unsigned m = (c < S.cells) ? grid[c] : 0u;
-      int base;
-      const int pos = block_flag_scan(S, m != 0, base) + base;
-      if (m) {
-        if (pos < cap_list) list_cell[pos] = c;
-        if (out_refl && pos < T.cap_refl) {
-          int h, k, l;
-          cell_to_hkl(S, c, h, k, l);
-          out_refl[pos * 4 + 0] = h; out_refl[pos * 4 + 1] = k; out_refl[pos * 4 + 2] = l; out_refl[pos * 4 + 3] = (int)m;
-        }
-      }
+    const int run = (S.cells + TABLE_THREADS - 1) / TABLE_THREADS;
+    const int c_lo = min(tid * run, S.cells), c_hi = min(c_lo + run, S.cells);
+    int cnt = 0;
+    for (int c = c_lo; c < c_hi; ++c) cnt += grid[c] != 0;
+    // inclusive scan of cnt over the block
+    __shared__ int scan_sm[TABLE_THREADS];
+    scan_sm[tid] = cnt;
+    __syncthreads();
+    for (int o = 1; o < TABLE_THREADS; o <<= 1) {
+      const int v = (tid >= o) ? scan_sm[tid - o] : 0;
+      __syncthreads();
+      scan_sm[tid] += v;
+      __syncthreads();
     }
-    if (tid == 0) {
-      S.n_red = S.scan_carry;
-      S.scan_carry = 0;
+    int pos = scan_sm[tid] - cnt;
+    if (tid == TABLE_THREADS - 1) {
+      S.n_red = scan_sm[tid];
       if (S.n_red > cap_list) S.status |= XRSD_TABLE_LIST_OVERFLOW;
     }
     __syncthreads();
     if (S.status != 0) { finish(0); return; }
+    for (int c = c_lo; c < c_hi; ++c) {
+      const unsigned m = grid[c];
+      if (!m) continue;
+      list_cell[pos] = c;
+      if (out_refl && pos < T.cap_refl) {
+        int h, k, l;
+        cell_to_hkl(S, c, h, k, l);
+        out_refl[pos * 4 + 0] = h; out_refl[pos * 4 + 1] = k; out_refl[pos * 4 + 2] = l; out_refl[pos * 4 + 3] = (int)m;
+      }
+      ++pos;
+    }
+    __syncthreads();
   }
   const int n_red = S.n_red;
 

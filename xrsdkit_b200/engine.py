@@ -77,12 +77,13 @@ class Engine(object):
 
     # -- reflection tables --------------------------------------------------------------
     def build_tables(self, layout, d_params, batch, params_host=None, cap_shell=None, export_reflections=False,
-                     max_cells=None, check=True):
+                     max_cells=None, check=True, reuse=None):
         """Build the reflection tables of all crystalline populations for a batch.
 
         `params_host` (numpy [batch, n_params]) is only used to bound the candidate box when
         `max_cells` is not given.  With check=True the per-table status is read back (one small
-        device->host copy) and capacity overflows are retried with larger tables."""
+        device->host copy) and capacity overflows are retried with larger tables.  `reuse` is a
+        TableSet of the same shape to overwrite instead of allocating a new one."""
         if layout.n_xtal == 0:
             return None
         torch = self.torch
@@ -95,8 +96,14 @@ class Engine(object):
             cap_shell = 128 if has_ops else 1024
         n_tables = batch * layout.n_xtal
         cap_refl = 4096 if export_reflections else 0
+        cap_list = 0
         while True:
-            T = TableSet(torch, self.device, n_tables, cap_shell, self._n_pairs(layout), cap_refl)
+            if reuse is not None and reuse.n_tables == n_tables and reuse.cap_refl == cap_refl and reuse.cap_shell >= cap_shell:
+                T, cap_shell = reuse, reuse.cap_shell
+            else:
+                T = TableSet(torch, self.device, n_tables, cap_shell, self._n_pairs(layout), cap_refl)
+            reuse = None
+            T.c.cap_list_hint = cap_list
             abi.check(self.lib.xrsd_reflection_tables(C.byref(layout.c), d_params.data_ptr(), d_params.shape[1], batch,
                                                       C.byref(T.c), max_cells, self._stream()))
             self.launches += 1
@@ -110,6 +117,9 @@ class Engine(object):
             if st & abi.TABLE_GRID_OVERFLOW:
                 raise abi.XrsdError("candidate hkl box exceeds the shared-memory budget (q_max * cell edge too large)")
             if st & abi.TABLE_LIST_OVERFLOW:
+                if cap_list < 4096:
+                    cap_list = 4096
+                    continue
                 raise abi.XrsdError("more than 4096 reduced reflections in one table (no usable symmetry?)")
             if st & abi.TABLE_SHELL_OVERFLOW and cap_shell < 4096:
                 cap_shell *= 4

@@ -81,6 +81,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         max_cells = min(max_cells, 90000)
     tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells) if layout.n_xtal else None
     chi2_init = None
+    t_tables = None
     stream = eng._stream()
     n_iter = 0
     for it in range(max_iter):
@@ -91,7 +92,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         abi.check(lib.xrsd_lm_propose(d_p.data_ptr(), d_p.shape[1], batch, idx, nf, jout[0].data_ptr(), jout[1].data_ptr(),
                                       d_lambda.data_ptr(), d_lo.data_ptr(), d_hi.data_ptr(), d_active.data_ptr(),
                                       d_trial.data_ptr(), stream))
-        t_tables = eng.build_tables(layout, d_trial, batch, max_cells=max_cells) if layout.n_xtal else None
+        t_tables = eng.build_tables(layout, d_trial, batch, max_cells=max_cells, reuse=t_tables) if layout.n_xtal else None
         abi.check(lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_trial.data_ptr(),
                                           d_trial.shape[1], batch, C.byref(t_tables.c) if t_tables is not None else None,
                                           d_I.data_ptr(), d_dI.data_ptr() if d_dI is not None else None, ld_obs,
@@ -102,7 +103,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         eng.launches += 3
         if layout.n_xtal:
             # accepted systems now sit at `trial`: their tables are the trial tables
-            tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells)
+            tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=tables)
         if (it % 5 == 4) and not bool(d_active.any().item()):
             break
     # final objective at the accepted parameters
