@@ -232,6 +232,87 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+class Work(object):
+    """One workload instance on one GPU: device buffers + a step() closure."""
+
+    def __init__(self, eng, name, B, seed, lm_iters=20):
+        import torch
+        from xrsdkit_b200 import lowering
+        self.eng, self.name, self.B = eng, name, B
+        dev = eng.device
+        self.s, self.q, self.lay, self.P = make_workload(name, B)
+        self.n_q = len(self.q)
+        self.d_q = eng.to_device(self.q)
+        rs = np.random.RandomState(seed)
+        # 4 distinct parameter matrices and 2 output buffers are rotated: one step's output alone
+        # (8 B x B x n_q) exceeds the 126 MB L2 for the full-size batches
+        self.d_params = [eng.to_device(self.P[rs.permutation(B)]) for _ in range(4)]
+        self.max_cells = lowering.max_cells(self.lay, self.P) if self.lay.n_xtal else None
+        self.tables = [eng.build_tables(self.lay, p, B, params_host=self.P) if self.lay.n_xtal else None for p in self.d_params]
+        self.evals_per_unit = 1.0
+        self.metric, self.unit = "I(q) pattern evals/sec", "patterns/s"
+        self.lm_iters = lm_iters
+        if name in ("cfg4", "cfg5"):
+            lay = self.lay
+            self.free = [lay.slot(k) for k in ("noise__I0", "x__I0", "x__a", "x__hwhm_g", "x__hwhm_l", "x__r", "gp__I0", "gp__rg")]
+            g = torch.Generator(dev).manual_seed(seed + 5)
+            self.Iobs = eng.intensity(lay, self.d_q, self.d_params[0], tables=self.tables[0]).clone()
+            self.Iobs *= 1 + 0.02 * torch.randn(self.Iobs.shape, dtype=torch.float64, device=dev, generator=g)
+            self.obj = eng.objective(True, True, (0.0, float("inf")))
+            jit = 1 + 0.03 * (2 * torch.rand(self.d_params[0].shape, dtype=torch.float64, device=dev, generator=g) - 1)
+            mask = torch.zeros(lay.n_params, dtype=torch.bool, device=dev)
+            mask[self.free] = True
+            self.start = torch.where(mask[None, :], self.d_params[0] * jit, self.d_params[0]).contiguous()
+            self.jout = None
+            self.res = None
+            if name == "cfg4":
+                self.evals_per_unit = float(len(self.free) + 1)
+            else:
+                self.metric, self.unit = "batched LM fits/sec", "fits/s"
+        else:
+            self.outs = [torch.empty((B, self.n_q), dtype=torch.float64, device=dev) for _ in range(2)]
+
+    def step(self, i):
+        eng, lay, B = self.eng, self.lay, self.B
+        if self.name == "cfg4":      # residual + forward-difference Jacobian (9 evaluations per system, fused) + table build
+            t = eng.build_tables(lay, self.start, B, max_cells=self.max_cells, check=False, reuse=self.tables[1])
+            self.jout = eng.jacobian(lay, self.obj, self.d_q, self.start, self.Iobs, None, self.n_q, self.free, t, 1e-6,
+                                     out=self.jout)
+        elif self.name == "cfg5":    # a whole batched Levenberg-Marquardt fit
+            from xrsdkit_b200 import fitting
+            self.res = fitting.lm_fit_batch(lay, self.d_q, self.Iobs, self.start, self.free, max_iter=self.lm_iters,
+                                            eng=eng, return_device=True)
+        else:
+            k = i % 4
+            if self.name == "cfg3":  # the reflection tables are rebuilt every step: part of the pattern evaluation
+                t = eng.build_tables(lay, self.d_params[k], B, max_cells=self.max_cells, check=False, reuse=self.tables[k])
+            else:
+                t = self.tables[k]
+            eng.intensity(lay, self.d_q, self.d_params[k], tables=t, out=self.outs[i % 2])
+
+    def timed(self, steps, warmup, barrier=None):
+        import torch
+        for i in range(warmup):
+            self.step(i)
+        (barrier or torch.cuda.synchronize)()
+        n0 = self.eng.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            self.step(i)
+        e1.record()
+        (barrier or torch.cuda.synchronize)()
+        return e0.elapsed_time(e1), self.eng.launches - n0
+
+    def flops_per_unit(self):
+        """Algorithmic FP64 flops per (system, q) of ONE evaluation, DESIGN.md section 4."""
+        if self.name == "cfg2":
+            return FLOPS_PER_PAIR_RNORMAL * 50.5 + FLOPS_PER_Q_OVERHEAD_CFG2, SURVEY_FLOPS_PER_SETQ_CFG2
+        ns = float(np.mean([float(t.n_shell.float().mean().item()) for t in self.tables]))
+        extra = 80.0 + 45.0 if self.name in ("cfg4", "cfg5") else 0.0       # Guinier-Porod + log/residual
+        return 60.0 * ns + 150.0 + extra, 205.0 * ns + 150.0 + extra
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -247,111 +328,132 @@ def run_gpu_arm(args):
     eng = engine.get_engine()
     dev = eng.device
     B = args.batch
-    s, q, lay, P = make_workload(args.workload, B)
-    n_q = len(q)
+    warmup = max(3, args.warmup)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    d_q = eng.to_device(q)
-    # rotate over 4 distinct parameter matrices and 2 output buffers; the 328 MB output of one step
-    # already exceeds the 126 MB L2, so no step finds its data cached
-    rs = np.random.RandomState(1000 + rank)
-    d_params = [eng.to_device(P[rs.permutation(B)]) for _ in range(4)]
-    outs = [torch.empty((B, n_q), dtype=torch.float64, device=dev) for _ in range(2)]
-    from xrsdkit_b200 import lowering
-    max_cells = lowering.max_cells(lay, P) if lay.n_xtal else None
-    tables = [eng.build_tables(lay, p, B, params_host=P) if lay.n_xtal else None for p in d_params]
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def step(i):
-        if lay.n_xtal and args.workload == "cfg3":
-            t = eng.build_tables(lay, d_params[i % 4], B, max_cells=max_cells, check=False, reuse=tables[i % 4])   # table build is part of the step
-        else:
-            t = tables[i % 4]
-        eng.intensity(lay, d_q, d_params[i % 4], tables=t, out=outs[i % 2])
-
-    for i in range(max(3, args.warmup)):
-        step(i)
+    W = Work(eng, args.workload, B, 1000 + rank, args.lm_iters)
+    n_q, lay, P, q = W.n_q, W.lay, W.P, W.q
+    for i in range(warmup):
+        W.step(i)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = eng.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms, launches = W.timed(args.steps, 0, barrier)
     clocks = sampler.result()
-    launches = eng.launches - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * B * args.steps / (ms * 1e-3)
+    ms = max_over_ranks(ms)
+    value = world * B * args.steps * W.evals_per_unit / (ms * 1e-3)
 
-    # ---- e2e through the host-buffer API (pinned host memory, copies timed)
+    # ---- e2e through the host-buffer API (pinned host memory, copies inside the timed region)
+    e_steps = max(3, min(args.steps, 10))
     p_host = torch.as_tensor(P).pin_memory()
     q_host = torch.as_tensor(q).pin_memory()
-    I_host = torch.empty((B, n_q), dtype=torch.float64).pin_memory()
+    if args.workload in ("cfg2", "cfg3"):
+        I_host = torch.empty((B, n_q), dtype=torch.float64).pin_memory()
+        e2e_fn = lambda: xb.compute_intensity_pinned(lay, q_host, p_host, I_host, eng=eng)   # noqa: E731
+        h2d, d2h = int(P.nbytes + q.nbytes), int(8 * B * n_q)
+        api = "xrsdkit_b200.batch.compute_intensity_pinned (pinned host buffers, chunked copy/compute overlap)"
+        check = lambda: float(I_host[:: max(1, B // 7)].sum().item())   # noqa: E731
+    else:
+        Iobs_host = W.Iobs.cpu().pin_memory()
+        start_host = W.start.cpu().pin_memory()
+        nf = len(W.free)
+        out_host = torch.empty((B, nf * nf + nf + 1 if args.workload == "cfg4" else lay.n_params + 1), dtype=torch.float64).pin_memory()
+
+        def e2e_fn():
+            W.Iobs.copy_(Iobs_host, non_blocking=True)
+            W.start.copy_(start_host, non_blocking=True)
+            W.d_q.copy_(q_host, non_blocking=True)
+            W.step(0)
+            if args.workload == "cfg4":
+                JTJ, JTr, chi2 = W.jout
+                out_host.copy_(torch.cat([JTJ.reshape(B, -1), JTr, chi2[:, None]], dim=1), non_blocking=True)
+            else:
+                out_host.copy_(torch.cat([W.res.params, W.res.chi2[:, None]], dim=1), non_blocking=True)
+            torch.cuda.synchronize()
+        h2d, d2h = int(Iobs_host.numel() * 8 + start_host.numel() * 8 + q.nbytes), int(out_host.numel() * 8)
+        api = ("engine.jacobian" if args.workload == "cfg4" else "xrsdkit_b200.batch.fit_batch") + \
+              " with pinned host I_obs / start parameters in, normal equations or fitted parameters out"
+        check = lambda: float(out_host[:: max(1, B // 7)].nansum().item())   # noqa: E731
     for _ in range(2):
-        xb.compute_intensity_pinned(lay, q_host, p_host, I_host, eng=eng)
+        e2e_fn()
     barrier()
-    e_steps = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(e_steps):
-        xb.compute_intensity_pinned(lay, q_host, p_host, I_host, eng=eng)
+        e2e_fn()
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    te = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = world * B * e_steps / float(te.item())
-    checksum = float(I_host[:: max(1, B // 7)].sum().item())
+    dt = max_over_ranks(time.perf_counter() - t0)
+    e2e = world * B * e_steps * W.evals_per_unit / dt
+    checksum = check()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (intensity_kernel), timed alone with CUDA events
+    # ---- roofline of the dominant kernel, timed alone with CUDA events on the launching stream
     peaks, peaks_src = measured_peaks()
     fp64_tflops, probe_ms = eng.probe_fp64_peak()
+    reps = 10
+    if args.workload in ("cfg2", "cfg3"):
+        kname = "xrsd::intensity_kernel<2,false,%s>" % ("true" if lay.n_xtal else "false")
+        kfn = lambda i: eng.intensity(lay, W.d_q, W.d_params[i % 4], tables=W.tables[i % 4], out=W.outs[i % 2])   # noqa: E731
+        evals = 1.0
+    else:
+        kname = "xrsd::jacobian_kernel<false,true>"
+        kfn = lambda i: eng.jacobian(lay, W.obj, W.d_q, W.start, W.Iobs, None, n_q, W.free, W.tables[0], 1e-6, out=W.jout)   # noqa: E731
+        evals = float(len(W.free) + 1)
     for i in range(3):
-        eng.intensity(lay, d_q, d_params[i % 4], tables=tables[i % 4], out=outs[i % 2])
+        kfn(i)
     torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
     k0.record()
     for i in range(reps):
-        eng.intensity(lay, d_q, d_params[i % 4], tables=tables[i % 4], out=outs[i % 2])
+        kfn(i)
     k1.record()
     torch.cuda.synchronize()
     k_ms = k0.elapsed_time(k1) / reps
-    if args.workload == "cfg2":
-        n_r = 50.5     # 2*2.5/0.1 = 50 exactly: numpy.arange yields 50 or 51 radii depending on rounding
-        flops_unit = FLOPS_PER_PAIR_RNORMAL * n_r + FLOPS_PER_Q_OVERHEAD_CFG2
-        survey_unit = SURVEY_FLOPS_PER_SETQ_CFG2
-    else:
-        ns = float(np.mean([int(t_.n_shell.float().mean().item()) for t_ in tables if t_ is not None]))
-        flops_unit = 60.0 * ns + 150.0           # far-field Voigt ~60 flop per (q, shell)
-        survey_unit = 205.0 * ns + 150.0
-    flops = flops_unit * B * n_q
-    achieved = flops / (k_ms * 1e-3) / 1e12
-    hbm_bytes = 8.0 * B * n_q                     # the pattern is written once; q and params stay in L2
+    flops_unit, survey_unit = W.flops_per_unit()
+    units = B * n_q * evals
+    achieved = flops_unit * units / (k_ms * 1e-3) / 1e12
+    hbm_bytes = 8.0 * B * n_q     # intensity: the pattern is written once; fit kernels: I_obs is read once
     roofline = {
         "bound": "fp64", "achieved": achieved, "peak": fp64_tflops, "unit": "TFLOP/s", "frac": achieved / fp64_tflops,
-        "traffic": None,
-        "kernel": "xrsd::intensity_kernel<2,false>", "kernel_ms": k_ms,
-        "flops_per_unit": flops_unit, "units_per_launch": B * n_q,
+        "traffic": None, "kernel": kname, "kernel_ms": k_ms,
+        "flops_per_unit": flops_unit, "units_per_launch": units,
         "peak_source": "xrsd_probe_fp64_peak: DFMA-bound kernel timed in this run (%.3f ms); MEASURED_PEAKS.json has no FP64 figure" % probe_ms,
-        "achieved_survey_convention": survey_unit * B * n_q / (k_ms * 1e-3) / 1e12,
+        "achieved_survey_convention": survey_unit * units / (k_ms * 1e-3) / 1e12,
         "hbm": {"achieved": hbm_bytes / (k_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                 "frac": hbm_bytes / (k_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_source": peaks_src},
     }
+
+    # ---- short measurements of the other BASELINE configs (N=1, default workload only)
+    secondary = None
+    if args.workload == "cfg2" and world == 1 and not args.no_secondary:
+        secondary = {}
+        for name, b2, st in (("cfg3", 2000, 5), ("cfg4", 1000, 3), ("cfg5", 512, 1)):
+            try:
+                w2 = Work(eng, name, b2, 2000, args.lm_iters)
+                ms2, _ = w2.timed(st, 2)
+                secondary[name] = {"workload": workload_name(name), "metric": w2.metric, "unit": w2.unit, "batch": b2,
+                                   "value": b2 * st * w2.evals_per_unit / (ms2 * 1e-3), "ms_per_step": ms2 / st}
+                if name == "cfg5":
+                    r = w2.res
+                    secondary[name].update(lm_iterations=args.lm_iters,
+                                           median_chi2_ratio=float((r.chi2 / r.chi2_init).median().item()))
+                del w2
+                torch.cuda.empty_cache()
+            except Exception as e:      # a secondary measurement must not take the headline down
+                secondary[name] = {"error": repr(e)}
 
     # ---- CPU baseline: bounded sample on the host cores
     cores = host_cores()
@@ -363,26 +465,39 @@ def run_gpu_arm(args):
         n2, dt2 = arm.step(per_core, cores * per_core)
         arm.close()
         cpu_val = (n1 + n2) / (dt1 + dt2)
-        cpu = {"value": cpu_val, "unit": "patterns/s", "cores": cores, "kind": "port",
+        note = ""
+        if args.workload == "cfg5":
+            # the reference optimiser (lmfit Nelder-Mead) is not installable here; one LM fit costs
+            # lm_iters x (n_free + 2) objective evaluations, each one reference compute_intensity
+            cpu_val = cpu_val / (args.lm_iters * (len(W.free) + 2))
+            note = "; fits/s EXTRAPOLATED as pattern rate / (%d iterations x %d evaluations)" % (args.lm_iters, len(W.free) + 2)
+        cpu = {"value": cpu_val, "unit": W.unit, "cores": cores, "kind": "port",
                "sample": "2 x %d parameter sets (%d per core) of the same workload, numpy oracle port of the "
-                         "reference's path (reflection tables rebuilt per pattern, as the reference does)" % (cores * per_core, per_core),
+                         "reference's path (reflection tables rebuilt per pattern, as the reference does)%s"
+                         % (cores * per_core, per_core, note),
                "per_core": cpu_val / cores}
+        if secondary is not None:
+            arm3 = CpuArm("cfg3", cores)
+            n3, dt3 = arm3.step(1)
+            arm3.close()
+            secondary["cfg3"]["cpu_patterns_per_s"] = n3 / dt3
+            secondary["cfg4"]["cpu_patterns_per_s"] = n3 / dt3        # one evaluation = one crystalline pattern (+GP, noise)
+            secondary["cpu_note"] = "%d cores, %d cfg3 patterns, numpy oracle port; cfg4 evaluations cost the same per pattern" % (cores, n3)
 
     line = {
-        "metric": "I(q) pattern evals/sec", "value": value, "unit": "patterns/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": W.metric, "value": value, "unit": W.unit, "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.workload), "n_q": n_q, "sets_per_gpu_per_step": B,
-                   "q_evals_per_s": value * n_q,
-                   "l2": "each step writes %.0f MB (> 126 MB L2) and rotates over 4 parameter matrices" % (8e-6 * B * n_q),
+                   "evaluations_per_set": W.evals_per_unit, "q_evals_per_s": value * n_q,
+                   "l2": "each step writes or reads %.0f MB of patterns (L2 is 126 MB) and rotates over 4 parameter matrices" % (8e-6 * B * n_q),
                    "checksum": checksum},
-        "e2e": {"value": e2e, "unit": "patterns/s", "h2d_bytes_per_step": int(P.nbytes + q.nbytes),
-                "d2h_bytes_per_step": int(8 * B * n_q), "steps": e_steps,
-                "api": "xrsdkit_b200.batch.compute_intensity_pinned (pinned host buffers, chunked copy/compute overlap)"},
+        "e2e": {"value": e2e, "unit": W.unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps, "api": api},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "secondary": secondary,
     }
     print(json.dumps(line))
     if world > 1:
@@ -399,6 +514,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--batch", type=int, default=10000, help="parameter sets per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short cfg3/cfg4/cfg5 measurements")
+    ap.add_argument("--lm-iters", type=int, default=20, help="LM iterations per fit (cfg5)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

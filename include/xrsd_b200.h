@@ -160,15 +160,19 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
                         double *d_chi2, void *stream);
 
 /* Forward-difference Jacobian of the weighted residual vector, reduced in-kernel to the
- * normal equations: JTJ[b][n_free][n_free], JTr[b][n_free], chi2[b].  free_idx[n_free] are
- * parameter slots; rel_step is the relative step (absolute for zero-valued parameters).
- * Reflection tables are held fixed inside one evaluation. */
+ * normal equations: JTJ[b][n_free][n_free], JTr[b][n_free], chi2[b].  free_idx[n_free] (HOST
+ * array) are parameter slots; rel_step is the relative step (absolute for zero-valued
+ * parameters).  One launch: grid = batch x (n_free+1) variants x q-spans, the last CTA of a
+ * system reduces.  d_workspace holds xrsd_jacobian_workspace_bytes() bytes; its trailing
+ * ticket area must be zero before the FIRST call (the kernel re-zeroes it).  Reflection tables
+ * and the radius counts of size quadratures are held fixed inside one evaluation. */
+int64_t xrsd_jacobian_workspace_bytes(int32_t n_q, int32_t batch, int32_t n_free);
 int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj,
                         const double *d_q, int32_t n_q, const double *d_params, int32_t ld_params,
                         int32_t batch, const xrsd_tables_t *tables,
                         const double *d_Iobs, const double *d_dI, int64_t ld_obs,
                         const int32_t *free_idx, int32_t n_free, double rel_step,
-                        double *d_JTJ, double *d_JTr, double *d_chi2, void *stream);
+                        double *d_JTJ, double *d_JTr, double *d_chi2, void *d_workspace, void *stream);
 
 /* One damped Gauss-Newton (Levenberg-Marquardt) proposal per system:
  * solve (JTJ + lambda*diag(JTJ)) delta = -JTr, project onto [lo, hi], write trial params. */

@@ -19,10 +19,10 @@ cudaError_t xrsd_launch_profile(int, double, double, const double *, int, double
 cudaError_t xrsd_launch_residual(const xrsd_layout_t *, const xrsd_objective_t *, const double *, int, const double *, int, int,
                                  const xrsd_tables_t *, const double *, const double *, long long, double *, int, int,
                                  cudaStream_t);
-size_t xrsd_jacobian_smem(int, int, int, int);
+size_t xrsd_jacobian_smem(int, int, int, int, int *);
 cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *, const xrsd_objective_t *, const double *, int, const double *, int, int,
                                  const xrsd_tables_t *, const double *, const double *, long long, const int32_t *, int, double,
-                                 double *, double *, double *, int, int, int, cudaStream_t);
+                                 double *, double *, double *, double *, unsigned *, int, int, int, cudaStream_t);
 cudaError_t xrsd_launch_lm_propose(const double *, int, int, const int32_t *, int, const double *, const double *,
                                    const double *, const double *, const double *, const uint8_t *, double *, cudaStream_t);
 cudaError_t xrsd_launch_lm_update(double *, int, int, const double *, double *, const double *, double *, uint8_t *, int *,
@@ -160,13 +160,13 @@ int xrsd_reflection_tables(const xrsd_layout_t *layout, const double *d_params, 
 static int pick_q_per_cta(int n_q, int batch, int scratch) {
   // One CTA holds a span of one pattern in shared memory.  Spans are multiples of 512 q-points;
   // aim for >= 24 CTAs per SM in the grid (several waves, so the last partial wave costs little)
-  // and keep the span under 64 KB so that at least three CTAs stay resident per SM.
+  // and keep the span at <= 4096 q-points (32 KB) so that six 128-thread CTAs stay resident per SM.
   const long long want_ctas = 148LL * 24;
   long long tiles = (want_ctas + batch - 1) / batch;
   if (tiles < 1) tiles = 1;
   long long per = ((long long)n_q + tiles - 1) / tiles;
   per = ((per + 511) / 512) * 512;
-  const long long cap = std::max(512LL, ((long long)(64 * 1024 / 8 - scratch) / 512) * 512);
+  const long long cap = std::max(512LL, std::min(4096LL, ((long long)(36 * 1024 / 8 - scratch) / 512) * 512));
   per = std::min(per, cap);
   per = std::min<long long>(per, ((long long)n_q + 511) / 512 * 512);
   return (int)std::max(512LL, per);
@@ -216,16 +216,22 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   return XRSD_OK;
 }
 
+int64_t xrsd_jacobian_workspace_bytes(int32_t n_q, int32_t batch, int32_t n_free) {
+  // [batch][n_free+1][n_q] doubles of variant patterns + one ticket per system (zero-initialised)
+  return (int64_t)batch * (n_free + 1) * n_q * 8 + (((int64_t)batch * 4 + 255) & ~255LL);
+}
+
 int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q, int32_t n_q,
                         const double *d_params, int32_t ld_params, int32_t batch, const xrsd_tables_t *tables,
                         const double *d_Iobs, const double *d_dI, int64_t ld_obs, const int32_t *free_idx, int32_t n_free,
-                        double rel_step, double *d_JTJ, double *d_JTr, double *d_chi2, void *stream) {
+                        double rel_step, double *d_JTJ, double *d_JTr, double *d_chi2, void *d_workspace, void *stream) {
   int rc = check_layout(layout);
   if (rc) return rc;
   if (batch <= 0 || n_q <= 0) return XRSD_OK;
   rc = check_tables(layout, tables);
   if (rc) return rc;
-  if (!obj || !d_q || !d_params || !d_Iobs || !d_JTJ || !d_JTr || !d_chi2 || !free_idx) return fail(XRSD_EINVAL, "NULL pointer");
+  if (!obj || !d_q || !d_params || !d_Iobs || !d_JTJ || !d_JTr || !d_chi2 || !free_idx || !d_workspace)
+    return fail(XRSD_EINVAL, "NULL pointer");
   if (n_free < 1 || n_free > XRSD_MAX_FREE) return fail(XRSD_EINVAL, "n_free=%d (max %d)", n_free, XRSD_MAX_FREE);
   for (int i = 0; i < n_free; ++i)
     if (free_idx[i] < 0 || free_idx[i] >= layout->n_params) return fail(XRSD_EINVAL, "free_idx[%d]=%d", i, free_idx[i]);
@@ -235,15 +241,15 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   int rm;
   const int scratch = scratch_doubles_for(layout, &rm);
   if (scratch < 0) return fail(XRSD_ECAPACITY, "size quadrature too fine for shared memory");
-  // q tile: as large as keeps two CTAs per SM resident (<= ~100 KB), multiple of 512
-  int tile_q = 2048;
-  while (tile_q > 512 && xrsd_jacobian_smem(layout->n_params, n_free, tile_q, scratch) + kStaticSmem > 100 * 1024) tile_q -= 512;
-  tile_q = std::min(tile_q, (n_q + 511) / 512 * 512);
-  if (xrsd_jacobian_smem(layout->n_params, n_free, tile_q, scratch) + kStaticSmem > (size_t)kMaxSmem)
+  const int per = pick_q_per_cta(n_q, batch * (n_free + 1), scratch);
+  if (xrsd_jacobian_smem(layout->n_params, n_free, per, scratch, nullptr) + kStaticSmem > (size_t)kMaxSmem)
     return fail(XRSD_ECAPACITY, "jacobian working set does not fit in shared memory");
+  const int64_t fbytes = (int64_t)batch * (n_free + 1) * n_q * 8;
+  double *d_Fvar = (double *)d_workspace;
+  unsigned *d_tickets = (unsigned *)((char *)d_workspace + fbytes);
   cudaError_t e = xrsd_launch_jacobian(layout, obj, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables, d_Iobs,
                                        obj->has_dI ? d_dI : nullptr, (long long)ld_obs, free_idx, n_free, rel_step, d_JTJ,
-                                       d_JTr, d_chi2, tile_q, scratch, rm, (cudaStream_t)stream);
+                                       d_JTr, d_chi2, d_Fvar, d_tickets, per, scratch, rm, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "jacobian_kernel");
   return XRSD_OK;
 }

@@ -10,6 +10,7 @@
 //                       evaluates one parameter set per call; here n_free+1 sets per system)
 //   lm_*             <- replaces the lmfit Nelder-Mead driver of system/__init__.py:262-266
 //                       (no oracle in the reference; parity is defined on outcomes)
+#include <algorithm>
 #include "system_eval.cuh"
 
 namespace xrsd {
@@ -67,80 +68,92 @@ residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
   if (threadIdx.x == 0) chi2[b] = num / den;
 }
 
-// Normal equations by forward differences.  Shared memory: prm_var[(n_free+1)][ldp_s],
-// F[(n_free+1)][tile_q] (log I or I per variant), wts[tile_q], fobs[tile_q], scratch.
+// Normal equations by forward differences, ONE launch.  Grid = batch x (n_free+1) variants x q-spans:
+// every CTA evaluates one parameter variant of one system over one q-span exactly like the intensity
+// kernel does and parks f(I) (log I or I) in an HBM scratch [batch][n_free+1][n_q] (1.2 MB per system
+// at cfg4 sizes, written and read once: ~0.3 us of HBM time against ~10 us of FP64 work).  The CTA
+// that finishes last for a system (atomic ticket) reduces its variants to JTJ / JTr / chi2, staging
+// 256 q-points of all variants at a time in shared memory.
 template <bool RM, bool HX>
-__global__ void __launch_bounds__(EVAL_THREADS, HX ? 4 : 6)
+__global__ void __launch_bounds__(EVAL_THREADS, 6)
 jacobian_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t O, const double *__restrict__ q, int n_q,
                 const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
                 const double *__restrict__ Iobs, const double *__restrict__ dI, long long ld_obs,
                 const FreeSet F, double rel_step, double *__restrict__ JTJ, double *__restrict__ JTr,
-                double *__restrict__ chi2, int tile_q, int scratch_doubles) {
+                double *__restrict__ chi2, double *__restrict__ Fvar, unsigned *__restrict__ tickets,
+                int q_per_cta, int n_tiles, int pattern_doubles, int scratch_doubles) {
   extern __shared__ __align__(16) double smem_d[];
   __shared__ EvalShared S;
   __shared__ double acc_sm[XRSD_MAX_FREE * (XRSD_MAX_FREE + 1) / 2 + XRSD_MAX_FREE + 2];
   __shared__ double steps[XRSD_MAX_FREE];
-  __shared__ int topo[XRSD_MAX_POPS];
-  const int b = blockIdx.x;
-  if (b >= batch) return;
+  __shared__ int is_last;
   const int tid = threadIdx.x;
   const int nf = F.n_free, nv = nf + 1;
+  const long long bid = blockIdx.x;
+  const int per_sys = nv * n_tiles;
+  const int b = (int)(bid / per_sys);
+  const int rem = (int)(bid - (long long)b * per_sys);
+  const int v = rem / n_tiles, tile = rem - v * n_tiles;
+  if (b >= batch) return;
   const int np = L.n_params;
-  const int ldp_s = (np + 1) & ~1;
-  double *prm_var = smem_d;
-  double *Fv = prm_var + (size_t)nv * ldp_s;
-  double *wts = Fv + (size_t)nv * tile_q;
-  double *fobs = wts + tile_q;
-  double *scratch = fobs + tile_q;
+  double *I_sm = smem_d;
+  double *scratch = smem_d + pattern_doubles;
+  double *prm_s = scratch + scratch_doubles;
   const double *prm = params + (size_t)b * ldp;
-  for (int i = tid; i < nv * ldp_s; i += EVAL_THREADS) {
-    const int v = i / ldp_s, k = i - v * ldp_s;
-    prm_var[i] = (k < np) ? prm[k] : 0.0;
-  }
-  const int n_acc = nf * (nf + 1) / 2 + nf + 2;
-  for (int i = tid; i < n_acc; i += EVAL_THREADS) acc_sm[i] = 0.0;
-  __syncthreads();
+  for (int i = tid; i < np; i += EVAL_THREADS) prm_s[i] = prm[i];
   if (tid < nf) {
     const double p0 = prm[F.idx[tid]];
-    const double h = (p0 != 0.0) ? fabs(p0) * rel_step : rel_step;
-    steps[tid] = h;
-    prm_var[(size_t)(tid + 1) * ldp_s + F.idx[tid]] = p0 + h;
+    steps[tid] = (p0 != 0.0) ? fabs(p0) * rel_step : rel_step;
   }
   __syncthreads();
+  if (v > 0 && tid == 0) prm_s[F.idx[v - 1]] = prm[F.idx[v - 1]] + steps[v - 1];
+  __syncthreads();
+  const int q_begin = tile * q_per_cta;
+  const int q_count = min(q_per_cta, n_q - q_begin);
+  accumulate_system<2, RM, HX>(L, prm_s, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S, prm);
+  double *dst = Fvar + ((size_t)b * nv + v) * n_q + q_begin;
+  for (int i = tid; i < q_count; i += EVAL_THREADS) {
+    const double x = I_sm[i];
+    dst[i] = O.logI_weighted ? ((x > 0.0) ? log(x) : NAN) : x;
+  }
+  // ---- ticket: the last CTA of this system reduces
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(&tickets[b], 1u) == (unsigned)(per_sys - 1));
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int n_tri = nf * (nf + 1) / 2;
+  const int n_acc = n_tri + nf + 2;
+  for (int i = tid; i < n_acc; i += EVAL_THREADS) acc_sm[i] = 0.0;
   const double *obs = Iobs + (size_t)b * ld_obs;
   const double *err = dI ? dI + (size_t)b * ld_obs : nullptr;
-
-  for (int q0 = 0; q0 < n_q; q0 += tile_q) {
-    const int qc = min(tile_q, n_q - q0);
-    for (int v = 0; v < nv; ++v) {
-      accumulate_system<2, RM, HX>(L, prm_var + (size_t)v * ldp_s, T, b, q, n_q, q0, qc, Fv + (size_t)v * tile_q, scratch,
-                               scratch_doubles, &S, topo, v == 0 ? 1 : 2);
+  const double *Fb = Fvar + (size_t)b * nv * n_q;
+  constexpr int RT = 256;                       // q-points per reduction stage
+  double *Fv = smem_d;                          // [nv][RT]
+  double *wts = Fv + (size_t)nv * RT;
+  double *fobs = wts + RT;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int q0 = 0; q0 < n_q; q0 += RT) {
+    const int qc = min(RT, n_q - q0);
+    __syncthreads();
+    for (int i = tid; i < nv * qc; i += EVAL_THREADS) {
+      const int vv = i / qc, k = i - vv * qc;
+      Fv[vv * RT + k] = __ldcg(Fb + (size_t)vv * n_q + q0 + k);     // written by other CTAs: read through L2
     }
-    // weights, masks, transformed values
     for (int i = tid; i < qc; i += EVAL_THREADS) {
       const double Io = obs[q0 + i];
       double w;
       bool fit = fit_weight(O, q[q0 + i], Io, err, q0 + i, w);
-      const double I0v = Fv[i];
-      if (O.logI_weighted) fit = fit && (I0v > 0.0);
-      if (!fit) w = 0.0;
+      const double f0 = __ldcg(Fb + q0 + i);
+      if (O.logI_weighted) fit = fit && (f0 == f0);                  // I_comp > 0
       wts[i] = fit ? w : 0.0;
-      if (O.logI_weighted) {
-        fobs[i] = fit ? log(Io) : 0.0;
-        for (int v = 0; v < nv; ++v) {
-          const double x = Fv[(size_t)v * tile_q + i];
-          Fv[(size_t)v * tile_q + i] = (fit && x > 0.0) ? log(x) : NAN;
-        }
-      } else {
-        fobs[i] = Io;
-      }
+      fobs[i] = fit ? (O.logI_weighted ? log(Io) : Io) : 0.0;
     }
     __syncthreads();
-    // reductions: entry e of acc_sm handled by warp (e mod 8); lanes stride over the tile
-    const int warp = tid >> 5, lane = tid & 31;
+    // entry e of acc_sm is owned by warp (e mod n_warps); lanes stride over the stage
     for (int e = warp; e < n_acc; e += EVAL_THREADS / 32) {
       int j = -1, k = -1, kind;   // kind 0: JTJ(j,k)  1: JTr(j)  2: chi2 numerator  3: sum of weights
-      const int n_tri = nf * (nf + 1) / 2;
       if (e < n_tri) {
         kind = 0;
         int r = e;
@@ -157,10 +170,10 @@ jacobian_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
         const double f0 = Fv[i];
         double term;
         if (kind == 0) {
-          const double dj = Fv[(size_t)(j + 1) * tile_q + i] - f0, dk = Fv[(size_t)(k + 1) * tile_q + i] - f0;
+          const double dj = Fv[(j + 1) * RT + i] - f0, dk = Fv[(k + 1) * RT + i] - f0;
           term = (dj == dj && dk == dk) ? dj * dk : 0.0;
         } else if (kind == 1) {
-          const double dj = Fv[(size_t)(j + 1) * tile_q + i] - f0;
+          const double dj = Fv[(j + 1) * RT + i] - f0;
           term = (dj == dj) ? dj * (f0 - fobs[i]) : 0.0;
         } else if (kind == 2) {
           term = (f0 - fobs[i]) * (f0 - fobs[i]);
@@ -172,21 +185,23 @@ jacobian_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       if (lane == 0) acc_sm[e] += sum;
     }
-    __syncthreads();
   }
+  __syncthreads();
   // normalise by the sum of weights and the steps; write out (full symmetric JTJ)
-  const int n_tri = nf * (nf + 1) / 2;
   const double sw = acc_sm[n_tri + nf + 1];
   for (int e = tid; e < n_tri; e += EVAL_THREADS) {
     int r = e, j = 0;
     while (r >= nf - j) { r -= nf - j; ++j; }
     const int k = j + r;
-    const double v = acc_sm[e] / (steps[j] * steps[k]) / sw;
-    JTJ[((size_t)b * nf + j) * nf + k] = v;
-    JTJ[((size_t)b * nf + k) * nf + j] = v;
+    const double val = acc_sm[e] / (steps[j] * steps[k]) / sw;
+    JTJ[((size_t)b * nf + j) * nf + k] = val;
+    JTJ[((size_t)b * nf + k) * nf + j] = val;
   }
   if (tid < nf) JTr[(size_t)b * nf + tid] = acc_sm[n_tri + tid] / steps[tid] / sw;
-  if (tid == 0) chi2[b] = acc_sm[n_tri + nf] / sw;
+  if (tid == 0) {
+    chi2[b] = acc_sm[n_tri + nf] / sw;
+    tickets[b] = 0;                              // ready for the next launch
+  }
 }
 
 // ---------------------------------------------------------------------------- LM algebra
@@ -296,30 +311,37 @@ extern "C" cudaError_t xrsd_launch_residual(const xrsd_layout_t *layout, const x
   return cudaGetLastError();
 }
 
-extern "C" size_t xrsd_jacobian_smem(int n_params, int n_free, int tile_q, int scratch_doubles) {
-  const int ldp_s = (n_params + 1) & ~1;
-  return ((size_t)(n_free + 1) * ldp_s + (size_t)(n_free + 1) * tile_q + 2 * (size_t)tile_q + (size_t)scratch_doubles) *
-         sizeof(double);
+extern "C" size_t xrsd_jacobian_smem(int n_params, int n_free, int q_per_cta, int scratch_doubles, int *pattern_doubles) {
+  // pattern buffer: the q-span while evaluating, [(n_free+1)+2][256] while reducing
+  int pat = std::max((q_per_cta + 1) & ~1, (n_free + 3) * 256);
+  if (pattern_doubles) *pattern_doubles = pat;
+  return ((size_t)pat + (size_t)scratch_doubles + (size_t)((n_params + 1) & ~1)) * sizeof(double);
 }
 
 extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q,
                                             int n_q, const double *d_params, int ldp, int batch,
                                             const xrsd_tables_t *tables, const double *d_Iobs, const double *d_dI,
                                             long long ld_obs, const int32_t *free_idx, int n_free, double rel_step,
-                                            double *d_JTJ, double *d_JTr, double *d_chi2, int tile_q, int scratch_doubles,
-                                            int radial_multi, cudaStream_t stream) {
+                                            double *d_JTJ, double *d_JTr, double *d_chi2, double *d_Fvar,
+                                            unsigned *d_tickets, int q_per_cta, int scratch_doubles, int radial_multi,
+                                            cudaStream_t stream) {
   using namespace xrsd;
   FreeSet F;
   F.n_free = n_free;
   for (int i = 0; i < XRSD_MAX_FREE; ++i) F.idx[i] = (i < n_free) ? free_idx[i] : 0;
-  const size_t smem = xrsd_jacobian_smem(layout->n_params, n_free, tile_q, scratch_doubles);
+  int pat = 0;
+  const size_t smem = xrsd_jacobian_smem(layout->n_params, n_free, q_per_cta, scratch_doubles, &pat);
   auto kern = radial_multi ? jacobian_kernel<true, true>
                            : (layout->n_xtal ? jacobian_kernel<false, true> : jacobian_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (batch <= 0) return cudaSuccess;
-  kern<<<batch, EVAL_THREADS, smem, stream>>>(*layout, *obj, d_q, n_q, d_params, ldp, batch, *tables, d_Iobs, d_dI, ld_obs, F,
-                                             rel_step, d_JTJ, d_JTr, d_chi2, tile_q, scratch_doubles);
+  const int n_tiles = (n_q + q_per_cta - 1) / q_per_cta;
+  const long long n_blocks = (long long)batch * (n_free + 1) * n_tiles;
+  if (n_blocks > 2147483647LL) return cudaErrorInvalidConfiguration;
+  kern<<<(unsigned)n_blocks, EVAL_THREADS, smem, stream>>>(*layout, *obj, d_q, n_q, d_params, ldp, batch, *tables, d_Iobs, d_dI,
+                                                          ld_obs, F, rel_step, d_JTJ, d_JTr, d_chi2, d_Fvar, d_tickets,
+                                                          q_per_cta, n_tiles, pat, scratch_doubles);
   return cudaGetLastError();
 }
 

@@ -105,10 +105,12 @@ template <int QPT, bool RADIAL_MULTI, bool HAS_XTAL = true>
 __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restrict__ prm, const xrsd_tables_t &T, int b,
                                   const double *__restrict__ q, int n_q, int q_begin, int q_count,
                                   double *__restrict__ I_sm, double *__restrict__ scratch, int scratch_doubles,
-                                  EvalShared *S, int *topo = nullptr, int topo_mode = 0) {
-  // topo (shared memory, one int per population) pins the discrete part of the evaluation across
-  // the parameter variants of a finite-difference Jacobian: mode 1 records the number
-  // of radii of each size quadrature, mode 2 reuses the recorded value instead of recomputing ceil().
+                                  EvalShared *S, const double *__restrict__ prm_topo = nullptr) {
+  // prm_topo (optional) is the parameter row that decides the DISCRETE part of the evaluation --
+  // the number of radii of each size quadrature -- while `prm` supplies the values.  The variants of
+  // a finite-difference Jacobian pass their unperturbed row here so that a step in r or sigma cannot
+  // flip ceil() and put a jump into the difference quotient.
+  if (prm_topo == nullptr) prm_topo = prm;
   const int tid = threadIdx.x;
   for (int i = tid; i < q_count; i += EVAL_THREADS) I_sm[i] = 0.0;
   const int span = EVAL_THREADS * QPT;
@@ -157,9 +159,16 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
             const double r_max = __dadd_rn(r0, __dmul_rn(pop.sampling_width, sigma_r));
             // numpy.arange(r_min, r_max, dr): len = ceil((stop-start)/step), r_i = start + i*((start+step)-start)
             const double len = ceil(__dsub_rn(r_max, r_min) / dr);
-            n_r = (len > 0.0) ? (int)fmin(len, (double)(scratch_doubles / 2)) : 0;
-            if (topo_mode == 2) n_r = topo[ip];
-            else if (topo_mode == 1 && tid == 0) topo[ip] = n_r;
+            double len_t = len;
+            if (prm_topo != prm) {
+              const double r0t = prm_topo[pop.p_r];
+              const double srt = __dmul_rn(prm_topo[pop.p_sigma], r0t);
+              const double drt = __dmul_rn(srt, pop.sampling_step);
+              const double lo_t = fmax(__dsub_rn(r0t, __dmul_rn(pop.sampling_width, srt)), drt);
+              const double hi_t = __dadd_rn(r0t, __dmul_rn(pop.sampling_width, srt));
+              len_t = ceil(__dsub_rn(hi_t, lo_t) / drt);
+            }
+            n_r = (len_t > 0.0) ? (int)fmin(len_t, (double)(scratch_doubles / 2)) : 0;
             dstep = __dsub_rn(__dadd_rn(r_min, dr), r_min);
             r_first = r_min;
             const double two_s2 = 2.0 * (sigma_r * sigma_r);

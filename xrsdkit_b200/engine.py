@@ -216,12 +216,41 @@ class Engine(object):
                    torch.empty((batch, nf), dtype=torch.float64, device=self.device),
                    torch.empty(batch, dtype=torch.float64, device=self.device))
         idx = (C.c_int32 * nf)(*free_slots)
-        abi.check(self.lib.xrsd_jacobian_batch(C.byref(layout.c), C.byref(obj), q.data_ptr(), q.shape[0], d_params.data_ptr(),
-                                               d_params.shape[1], batch, C.byref(tables.c) if tables is not None else None,
-                                               Iobs_dev.data_ptr(), dI_dev.data_ptr() if dI_dev is not None else None, ld_obs,
-                                               idx, nf, float(rel_step), out[0].data_ptr(), out[1].data_ptr(),
-                                               out[2].data_ptr(), self._stream()))
-        self.launches += 1
+        n_q = q.shape[0]
+        # HBM scratch for the variant patterns: chunk the batch so it stays under ~4 GB
+        chunk = max(1, min(batch, int(4e9 // (8 * (nf + 1) * n_q))))
+        need = int(self.lib.xrsd_jacobian_workspace_bytes(n_q, chunk, nf))
+        ws = getattr(self, "_jac_ws", None)
+        if ws is None or ws.numel() < need:
+            ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+            self._jac_ws = ws
+            self._jac_ws_key = None
+        if self._jac_ws_key != (n_q, chunk, nf):      # ticket area moves with the shape: re-zero it
+            ws.zero_()
+            self._jac_ws_key = (n_q, chunk, nf)
+        nx = layout.n_xtal
+        for lo in range(0, batch, chunk):
+            hi = min(batch, lo + chunk)
+            if hi - lo != chunk:
+                ws.zero_()
+                self._jac_ws_key = None
+            tc = None
+            if tables is not None:
+                tc = abi.Tables()
+                C.memmove(C.byref(tc), C.byref(tables.c), C.sizeof(abi.Tables))
+                tc.n_shell = tables.n_shell.data_ptr() + 4 * lo * nx
+                tc.n_refl = tables.n_refl.data_ptr() + 4 * lo * nx
+                tc.n_all = tables.n_all.data_ptr() + 4 * lo * nx
+                tc.status = tables.status.data_ptr() + 4 * lo * nx
+                tc.shell_hkl = tables.shell_hkl.data_ptr() + 16 * lo * nx * tables.cap_shell
+                tc.shell_geo = tables.shell_geo.data_ptr() + 8 * lo * nx * tables.cap_shell * tables.n_pairs
+            abi.check(self.lib.xrsd_jacobian_batch(
+                C.byref(layout.c), C.byref(obj), q.data_ptr(), n_q, d_params[lo:hi].data_ptr(), d_params.shape[1], hi - lo,
+                C.byref(tc) if tc is not None else None,
+                Iobs_dev.data_ptr() + 8 * lo * ld_obs, (dI_dev.data_ptr() + 8 * lo * ld_obs) if dI_dev is not None else None,
+                ld_obs, idx, nf, float(rel_step), out[0][lo:hi].data_ptr(), out[1][lo:hi].data_ptr(), out[2][lo:hi].data_ptr(),
+                ws.data_ptr(), self._stream()))
+            self.launches += 1
         return out
 
     def peak_profile(self, kind, x, p0, p1=0.0):
