@@ -262,3 +262,25 @@ def test_error_behaviour(eng):
         Population("diffuse", "spherical", {}, {"nope": {"value": 1.0}})
     with pytest.raises(KeyError):
         System(p=dict(structure="diffuse", form="atomic", settings={"symbol": "Xx"})).compute_intensity(np.linspace(0.1, 1, 10))
+
+
+def test_host_buffer_c_abi_entry_point(eng, golden_systems):
+    """xrsd_intensity_batch_host: the call a non-Python caller binds (HOST pointers in and out)."""
+    import ctypes as C
+    from xrsdkit_b200 import abi, batch
+    from xrsdkit_b200.system import System
+    lib = abi.load()
+    q = np.linspace(0.01, 1.0, 1111)
+    for make, pars, n in ((cfg2_system, cfg2_params, 37), (cfg4_system, cfg4_params, 9)):
+        s = make(System)
+        lay = batch.layout_of(s, q)
+        P = np.ascontiguousarray(pars(lay, n))
+        out = np.full((n, q.size + 3), -7.0)                     # row stride larger than n_q
+        rc = lib.xrsd_intensity_batch_host(C.byref(lay.c), q.ctypes.data_as(C.c_void_p), q.size,
+                                           P.ctypes.data_as(C.c_void_p), P.shape[1], n,
+                                           out.ctypes.data_as(C.c_void_p), out.shape[1])
+        assert rc == 0, lib.xrsd_last_error()
+        ref = batch.compute_intensity_batch(lay, q, P)
+        np.testing.assert_array_equal(out[:, :q.size], ref)
+        assert np.all(out[:, q.size:] == -7.0)
+    lib.xrsd_release_workspace()

@@ -106,6 +106,39 @@ int check_tables(const xrsd_layout_t *L, const xrsd_tables_t *T) {
 
 const xrsd_tables_t kNoTables = {};
 
+// Upper bound of the candidate hkl box over a HOST parameter matrix: n_i <= ceil(G_max * edge_i) + 1
+// (scattering/__init__.py:266-268; |a_i| is the cell edge for every lattice class, b_i.a_i = 1).
+int host_max_cells(const xrsd_layout_t *L, const double *params, int ld, int batch) {
+  long long best = 1;
+  for (int ip = 0; ip < L->n_pops; ++ip) {
+    const xrsd_pop_t &p = L->pops[ip];
+    if (p.kind != XRSD_POP_CRYSTALLINE) continue;
+    double emax[3] = {0.0, 0.0, 0.0};
+    for (int b = 0; b < batch; ++b) {
+      const double *row = params + (size_t)b * ld;
+      const double a = p.p_lat[0] >= 0 ? fabs(row[p.p_lat[0]]) : 0.0;
+      const double bb = p.p_lat[1] >= 0 ? fabs(row[p.p_lat[1]]) : a;
+      const double c = p.p_lat[2] >= 0 ? fabs(row[p.p_lat[2]]) : a;
+      double e[3] = {a, bb, c};
+      if (p.lattice == XRSD_LAT_HCP) { e[1] = a; e[2] = a * sqrt(8.0 / 3.0); }
+      if (p.lattice == XRSD_LAT_HEXAGONAL || p.lattice == XRSD_LAT_TETRAGONAL) e[1] = a;
+      if (p.lattice == XRSD_LAT_CUBIC || p.lattice == XRSD_LAT_RHOMBOHEDRAL) { e[1] = a; e[2] = a; }
+      for (int i = 0; i < 3; ++i)
+        if (e[i] > emax[i]) emax[i] = e[i];
+    }
+    const double g_max = p.q_max / (2.0 * M_PI);
+    long long cells = 1;
+    for (int i = 0; i < 3; ++i) {
+      double n = ceil(g_max * emax[i] * (1.0 + 1e-12)) + 1.0;
+      if (!(n >= 1.0)) n = 1.0;
+      if (n > 10000.0) n = 10000.0;
+      cells *= (2 * (long long)n - 1);
+    }
+    if (cells > best) best = cells;
+  }
+  return (int)std::min<long long>(best, 1 << 30);
+}
+
 }  // namespace
 
 extern "C" {
@@ -357,10 +390,8 @@ int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int3
   if (ld_I < n_q) return fail(XRSD_EINVAL, "ld_I < n_q");
   const int n_x = layout->n_xtal;
   const size_t n_tab = (size_t)batch * n_x;
-  const int cap_shell = 512, n_pairs = XRSD_MAX_PAIRS;
-  // candidate-box bound from the host copy of the parameters is the caller's job in the device API;
-  // here use the largest box shared memory allows
-  int max_cells = 60000;
+  const int cap_shell = 1024, n_pairs = XRSD_MAX_PAIRS;
+  const int max_cells = n_x ? host_max_cells(layout, params, ld_params, batch) : 1;
   size_t off = 0;
   const size_t o_q = off; off += align256((size_t)n_q * 8);
   const size_t o_p = off; off += align256((size_t)batch * ld_params * 8);
