@@ -133,3 +133,30 @@ def test_compute_without_gpu_fails_loudly():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         System(p=dict(structure="diffuse", form="spherical")).compute_intensity(np.linspace(0.01, 0.5, 10))
+
+
+def test_yaml_round_trip_and_grouping(tmp_path, golden_systems):
+    """Files in the reference's YAML format load unchanged; systems are grouped by layout for batching."""
+    import yaml
+    from xrsdkit_b200.tools import ymltools
+    meta, arr = golden_systems
+    picks = [m for m in meta if m["name"].startswith("yml:")][:40]
+    paths = []
+    for i, m in enumerate(picks):
+        p = tmp_path / ("s%03d.yml" % i)
+        with open(p, "w") as f:
+            yaml.dump(m["system"], f)               # what xrsdkit's save_sys_to_yaml writes
+        paths.append(str(p))
+    q = arr["q_fixture"]
+    systems, groups = ymltools.load_batches(paths, q)
+    assert [s.to_dict() for s in systems] == [m["system"] for m in picks]
+    assert sorted(i for _, _, idx in groups for i in idx) == list(range(len(picks)))
+    assert len(groups) < len(picks)                 # fitted systems of one experiment share layouts
+    for lay, params, idx in groups:
+        assert params.shape == (len(idx), lay.n_params)
+        for row, i in zip(params, idx):
+            vals = [rec["value"] for rec in systems[i].flatten_params().values()]
+            np.testing.assert_array_equal(row, np.array(vals, dtype=float))
+    out = tmp_path / "again.yml"
+    ymltools.save_sys_to_yaml(str(out), systems[0])
+    assert ymltools.load_sys_from_yaml(str(out)).to_dict() == systems[0].to_dict()

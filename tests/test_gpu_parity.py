@@ -284,3 +284,21 @@ def test_host_buffer_c_abi_entry_point(eng, golden_systems):
         np.testing.assert_array_equal(out[:, :q.size], ref)
         assert np.all(out[:, q.size:] == -7.0)
     lib.xrsd_release_workspace()
+
+
+def test_mixed_layout_collection_in_batches(eng, golden_systems):
+    """All fixture systems evaluated through the layout-grouping loader: one launch per distinct layout."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200.tools import ymltools
+    meta, arr = golden_systems
+    picks = [m for m in meta if m["q"] == "q_fixture"]
+    systems = [System(**m["system"]) for m in picks]
+    q = arr["q_fixture"]
+    n0 = eng.launches
+    I = ymltools.compute_intensity_many(systems, q)
+    n_groups = len(ymltools.group_by_layout(systems, q))
+    assert n_groups < len(systems) / 3
+    for row, m in zip(I, picks):
+        err, same = rel_err(row, arr[m["key"] + "_I"])
+        assert same and err <= TOL_F64, (m["name"], err)
+    assert eng.launches - n0 <= 2 * n_groups + 2

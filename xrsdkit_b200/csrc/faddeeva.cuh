@@ -54,36 +54,54 @@ __device__ __forceinline__ void voigt_constants(VoigtConst *vc, double y, int ti
   }
 }
 
-// asymptotic branch, |z|^2 >= 64.  Coefficients c_k = (2k-1)!!/2^k; the number of terms follows
-// from |z|^2 so that the first neglected term is < 1e-13 relative.
+// asymptotic branch, |z|^2 >= 64:  w(z) ~ i/(sqrt(pi) z) P(u), P(u) = sum_k c_k u^k, u = 1/z^2,
+// c_k = (2k-1)!!/2^k, truncated where the first neglected term is < 1e-13 relative (5, 7 or 12 terms
+// by |z|^2).  P is evaluated in Estrin form: the dependency depth is 6..10 FP64 operations instead of
+// 2 per Horner step, which matters because this loop is latency- not throughput-bound (ncu: 45 % of
+// the stall samples were fixed-latency waits with the Horner form).
+struct Cplx { double r, i; };
+__device__ __forceinline__ Cplx c_lin(double c0, double c1, double ur, double ui) { return {fma(c1, ur, c0), c1 * ui}; }
+// a + u*b
+__device__ __forceinline__ Cplx c_fma(Cplx a, double ur, double ui, Cplx b) {
+  return {fma(ur, b.r, fma(-ui, b.i, a.r)), fma(ur, b.i, fma(ui, b.r, a.i))};
+}
+__device__ __forceinline__ void c_sqr(double ur, double ui, double &vr, double &vi) {
+  vr = fma(ur, ur, -(ui * ui));
+  vi = 2.0 * ur * ui;
+}
+
 __device__ __forceinline__ double rew_far(double x, double y, double z2) {
   const double r2 = __drcp_rn(z2);
   const double r4 = r2 * r2;
-  const double ur = (x * x - y * y) * r4;   // u = 1/z^2
+  const double ur = fma(x, x, -(y * y)) * r4;   // u = 1/z^2 = conj(z)^2/|z|^4
   const double ui = -2.0 * x * y * r4;
-  double pr, pi = 0.0;
-#define XRSD_H(ck) { const double t_ = fma(pr, ur, fma(-pi, ui, (ck))); pi = fma(pr, ui, pi * ur); pr = t_; }
-  if (z2 >= 1024.0) {
-    if (z2 >= 16384.0) {        // 3 terms
-      pr = 1.875;
-    } else {                    // 5 terms
-      pr = 29.53125;
-      XRSD_H(6.5625) XRSD_H(1.875)
-    }
+  double u2r, u2i;
+  c_sqr(ur, ui, u2r, u2i);
+  const Cplx L0 = c_lin(1.0, 0.5, ur, ui), L1 = c_lin(0.75, 1.875, ur, ui), L2 = c_lin(6.5625, 29.53125, ur, ui);
+  Cplx P;
+  if (z2 >= 1024.0) {                          // 5 terms
+    P = c_fma(L0, u2r, u2i, c_fma(L1, u2r, u2i, L2));
   } else {
-    if (z2 >= 256.0) {          // 7 terms
-      pr = 1055.7421875;
-    } else {                    // 12 terms down to |z| = 8
-      pr = 77205601.37329102;
-      XRSD_H(6713530.554199219) XRSD_H(639383.8623046875) XRSD_H(67303.564453125) XRSD_H(7918.06640625)
-      XRSD_H(1055.7421875)
+    double u4r, u4i;
+    c_sqr(u2r, u2i, u4r, u4i);
+    const Cplx L3 = c_lin(162.421875, 1055.7421875, ur, ui);
+    const Cplx A = c_fma(L0, u2r, u2i, L1);
+    const Cplx B = c_fma(L2, u2r, u2i, L3);
+    if (z2 >= 256.0) {                         // 7 terms
+      P = c_fma(A, u4r, u4i, B);
+    } else {                                   // 12 terms down to |z| = 8
+      double u8r, u8i;
+      c_sqr(u4r, u4i, u8r, u8i);
+      const Cplx L4 = c_lin(7918.06640625, 67303.564453125, ur, ui);
+      const Cplx L5 = c_lin(639383.8623046875, 6713530.554199219, ur, ui);
+      Cplx C = c_fma(L4, u2r, u2i, L5);
+      C.r = fma(u4r, 77205601.37329102, C.r);  // + c12 u^4 (inside the u^8 bracket)
+      C.i = fma(u4i, 77205601.37329102, C.i);
+      P = c_fma(c_fma(A, u4r, u4i, B), u8r, u8i, C);
     }
-    XRSD_H(162.421875) XRSD_H(29.53125) XRSD_H(6.5625) XRSD_H(1.875)
   }
-  XRSD_H(0.75) XRSD_H(0.5) XRSD_H(1.0)
-#undef XRSD_H
   // i/z = (y + i x)/|z|^2  ->  Re[(i/z) P] = (y Re P - x Im P)/|z|^2
-  return r2 * (y * pr - x * pi) * 0.56418958354775628695;   // 1/sqrt(pi)
+  return r2 * fma(y, P.r, -(x * P.i)) * 0.56418958354775628695;   // 1/sqrt(pi)
 }
 
 // exponential-series branch, |z|^2 < 64 (so |x| < 8).  x must be >= 0 (Re w is even in x).
