@@ -11,18 +11,17 @@ namespace xrsd {
 
 __device__ __forceinline__ double sqr(double x) { return x * x; }
 
-// sin(x) - x cos(x) for |x| < 0.5 by its Maclaurin series (relative accuracy ~1e-16,
-// where the closed form cancels).  t = x^3 (1/3 - x^2/30 + x^4/840 - ...),
-// coefficient k: (-1)^(k+1) 2k/(2k+1)!
+// sin(x) - x cos(x) for |x| < SPHERE_SERIES_X by its Maclaurin series (relative accuracy ~1e-16,
+// where the closed form cancels).  t = x^3 (1/3 - x^2/30 + x^4/840 - ...), coefficient k:
+// (-1)^(k+1) 2k/(2k+1)!; six terms suffice below x = 0.25 (next term < 1e-18 relative).
+constexpr double SPHERE_SERIES_X = 0.25;
 __device__ __forceinline__ double sphere_t_series(double x) {
-  // Estrin evaluation (dependency depth 4 instead of 8): p(y) = sum_k c_k y^k, y = x^2
+  // Estrin evaluation (dependency depth 3): p(y) = sum_k c_k y^k, y = x^2
   const double y = x * x, y2 = y * y, y4 = y2 * y2;
   const double a0 = fma(-3.333333333333333e-02, y, 3.333333333333333e-01);      //  2/3!  - 4/5! y
   const double a1 = fma(-2.2045855379188714e-05, y, 1.1904761904761906e-03);    //  6/7!  - 8/9! y
   const double a2 = fma(-1.9270852604185937e-09, y, 2.505210838544172e-07);     // 10/11! - 12/13! y
-  const double a3 = fma(-4.498331606952833e-14, y, 1.0706029224547743e-11);     // 14/15! - 16/17! y
-  const double b0 = fma(a1, y2, a0), b1 = fma(a3, y2, a2);
-  return fma(b1, y4, b0) * y * x;
+  return fma(a2, y4, fma(a1, y2, a0)) * y * x;
 }
 
 // sphere amplitude 3 (sin x - x cos x) / x^3 : scattering/form_factors.py:20-28.

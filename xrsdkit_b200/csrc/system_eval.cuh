@@ -219,15 +219,15 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
             }
             for (int o = 16; o > 0; o >>= 1) qmin_t = fmin(qmin_t, __shfl_xor_sync(0xffffffffu, qmin_t, o));
             int i = 0;
-            // phase A: some lane of the warp still has x < 0.5 -> series where needed
+            // phase A: some lane of the warp still has x < SPHERE_SERIES_X -> series where needed
             for (; i < n_r; ++i) {
               const double ri = scratch[2 * i], rho = scratch[2 * i + 1];
-              if (!(qmin_t * ri < 0.5)) break;
+              if (!(qmin_t * ri < SPHERE_SERIES_X)) break;
 #pragma unroll
               for (int j = 0; j < QPT; ++j) {
                 const double x = qv[j] * ri;
                 double t = fma(-x, c[j], s[j]);
-                if (x < 0.5) t = sphere_t_series(x);
+                if (x < SPHERE_SERIES_X) t = sphere_t_series(x);
                 acc[j] = fma(rho, t * t, acc[j]);
                 const double sn = fma(s[j], cd[j], c[j] * sd[j]);
                 c[j] = fma(c[j], cd[j], -(s[j] * sd[j]));
