@@ -71,7 +71,7 @@ __device__ __forceinline__ int block_flag_scan(TableShared &S, bool flag, int &b
   return wbase + within;
 }
 
-__global__ void __launch_bounds__(TABLE_THREADS)
+__global__ void __launch_bounds__(TABLE_THREADS, 3)
 reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ params, int ldp,
                         int batch, const xrsd_tables_t T, int max_cells, int cap_list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -99,6 +99,8 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
   int *sidx = reinterpret_cast<int *>(smem_raw + off);
   off += (size_t)cap_list * sizeof(int);
   int *seg_start = reinterpret_cast<int *>(smem_raw + off);   // [cap_list + 1]
+  off += ((size_t)cap_list + 1) * sizeof(int);
+  int *msum_s = reinterpret_cast<int *>(smem_raw + off);      // [cap_list]
 
   if (tid == 0) {
     make_cell(pop, prm, &S.cell);
@@ -171,24 +173,27 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
   // ---- 2. greedy reduction, one operation after the other (scattering/symmetries.py:61-90)
   if (pop.use_symmetry && pop.n_ops > 0) {
     const int rk = S.hmax[1] - S.hmin[1] + 1, rl = S.hmax[2] - S.hmin[2] + 1;   // symmetries.py:54-55
-    // visit only the points in the shell: an (unordered) list of their cells as uint16, laid over the
-    // sort/shell scratch (20 bytes per list slot, not yet in use), when cells and list fit
-    uint16_t *alive = reinterpret_cast<uint16_t *>(keys);
-    const bool use_list = S.cells <= 65535 && S.n_all <= 10 * cap_list;
+    // visit only the points still alive: two (unordered) uint16 cell lists laid over the sort/shell
+    // scratch (20 bytes per list slot, not yet in use) that are re-compacted after every operation,
+    // so the later operations do not walk over points the earlier ones dropped
+    uint16_t *alive[2] = {reinterpret_cast<uint16_t *>(keys), reinterpret_cast<uint16_t *>(keys) + 5 * cap_list};
+    const bool use_list = S.cells <= 65535 && S.n_all <= 5 * cap_list;
     if (use_list) {
       for (int c = tid; c < S.cells; c += TABLE_THREADS)
-        if (grid[c]) alive[atomicAdd(&S.scan_carry, 1)] = (uint16_t)c;
+        if (grid[c]) alive[0][atomicAdd(&S.scan_carry, 1)] = (uint16_t)c;
       __syncthreads();
       if (tid == 0) S.scan_carry = 0;
       __syncthreads();
     }
-    const int n_visit = use_list ? S.n_all : S.cells;
+    int n_visit = use_list ? S.n_all : S.cells;
     for (int iop = 0; iop < pop.n_ops; ++iop) {
       int perm[3];
       double sgn[3];
       sym_op(pop.ops[iop], perm, sgn);
+      const uint16_t *cur = alive[iop & 1];
+      uint16_t *nxt = alive[(iop + 1) & 1];
       for (int iv = tid; iv < n_visit; iv += TABLE_THREADS) {
-        const int c = use_list ? (int)alive[iv] : iv;
+        const int c = use_list ? (int)cur[iv] : iv;
         const unsigned mi = grid[c];
         if (!mi) continue;
         int h, k, l;
@@ -203,25 +208,36 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
         for (int n = 0; n < 3; ++n)
           hj[n] = (int)rint(S.cell.a[0][n] * s[0] + S.cell.a[1][n] * s[1] + S.cell.a[2][n] * s[2]);
         const int cj = hkl_to_cell(S, hj[0], hj[1], hj[2]);
-        if (cj < 0 || cj == c) continue;
-        if (!grid[cj]) continue;
-        // distance |p_i - op.p_j| (symmetries.py:62-72)
-        double pj[3], d2 = 0.0;
-        for (int m = 0; m < 3; ++m)
-          pj[m] = (double)hj[0] * S.cell.b[m][0] + (double)hj[1] * S.cell.b[m][1] + (double)hj[2] * S.cell.b[m][2];
-        for (int m = 0; m < 3; ++m) {
-          const double df = p[m] - sgn[m] * pj[perm[m]];
-          d2 += df * df;
+        bool drop = false;
+        if (cj >= 0 && cj != c && grid[cj]) {
+          // distance |p_i - op.p_j| (symmetries.py:62-72)
+          double pj[3], d2 = 0.0;
+          for (int m = 0; m < 3; ++m)
+            pj[m] = (double)hj[0] * S.cell.b[m][0] + (double)hj[1] * S.cell.b[m][1] + (double)hj[2] * S.cell.b[m][2];
+          for (int m = 0; m < 3; ++m) {
+            const double df = p[m] - sgn[m] * pj[perm[m]];
+            d2 += df * df;
+          }
+          if (sqrt(d2) < 1.0e-6) {
+            const int rank_i = (h * rk + k) * rl + l;
+            const int rank_j = (hj[0] * rk + hj[1]) * rl + hj[2];
+            drop = rank_i < rank_j;
+          }
         }
-        if (!(sqrt(d2) < 1.0e-6)) continue;
-        const int rank_i = (h * rk + k) * rl + l;
-        const int rank_j = (hj[0] * rk + hj[1]) * rl + hj[2];
-        if (rank_i < rank_j) {
+        if (drop) {
           // j keeps the point and collects i's multiplicity.  j cannot be dropped by this same
           // operation (its image is i, of lower rank), and only i's thread writes grid[cj].
           grid[cj] = (uint16_t)(grid[cj] + mi);
           grid[c] = 0;
+        } else if (use_list) {
+          nxt[atomicAdd(&S.scan_carry, 1)] = (uint16_t)c;
         }
+      }
+      __syncthreads();
+      if (use_list) {
+        n_visit = S.scan_carry;
+        __syncthreads();
+        if (tid == 0) S.scan_carry = 0;
       }
       __syncthreads();
     }
@@ -282,18 +298,39 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
     }
   }
   __syncthreads();
-  for (int size = 2; size <= npow; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < npow / 2; i += TABLE_THREADS) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool up = ((lo & size) == 0);
-        const double ka = keys[lo], kb = keys[hi];
-        const int ia = sidx[lo], ib = sidx[hi];
-        const bool gt = (ka > kb) || (ka == kb && ia > ib);
-        if (gt == up) { keys[lo] = kb; keys[hi] = ka; sidx[lo] = ib; sidx[hi] = ia; }
+  if (npow <= 1024) {
+    // small lists (the symmetric case): one warp sorts with __syncwarp only, the others wait once
+    if (tid < 32) {
+      for (int size = 2; size <= npow; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          for (int i = tid; i < npow / 2; i += 32) {
+            const int lo = 2 * i - (i & (stride - 1));
+            const int hi = lo + stride;
+            const bool up = ((lo & size) == 0);
+            const double ka = keys[lo], kb = keys[hi];
+            const int ia = sidx[lo], ib = sidx[hi];
+            const bool gt = (ka > kb) || (ka == kb && ia > ib);
+            if (gt == up) { keys[lo] = kb; keys[hi] = ka; sidx[lo] = ib; sidx[hi] = ia; }
+          }
+          __syncwarp();
+        }
       }
-      __syncthreads();
+    }
+    __syncthreads();
+  } else {
+    for (int size = 2; size <= npow; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = tid; i < npow / 2; i += TABLE_THREADS) {
+          const int lo = 2 * i - (i & (stride - 1));
+          const int hi = lo + stride;
+          const bool up = ((lo & size) == 0);
+          const double ka = keys[lo], kb = keys[hi];
+          const int ia = sidx[lo], ib = sidx[hi];
+          const bool gt = (ka > kb) || (ka == kb && ia > ib);
+          if (gt == up) { keys[lo] = kb; keys[hi] = ka; sidx[lo] = ib; sidx[hi] = ia; }
+        }
+        __syncthreads();
+      }
     }
   }
 
@@ -309,8 +346,11 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
   if (tid == 0) {
     S.n_shell_raw = S.scan_carry;
     S.scan_carry = 0;
-    if (S.n_shell_raw > T.cap_shell) S.status |= XRSD_TABLE_SHELL_OVERFLOW;
-    else seg_start[S.n_shell_raw] = n_red;
+    const int npair = pop.n_species * (pop.n_species + 1) / 2;
+    // shells are staged in shared memory (over the sort keys) and only the kept ones go to the output
+    // arrays; if they do not fit there, the raw list itself must fit the output capacity
+    if ((long long)S.n_shell_raw * npair > (long long)cap_list && S.n_shell_raw > T.cap_shell) S.status |= XRSD_TABLE_SHELL_OVERFLOW;
+    seg_start[S.n_shell_raw] = n_red;
   }
   __syncthreads();
   if (S.status != 0) { finish(0); return; }
@@ -321,17 +361,20 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
   double *o_geo = T.shell_geo + (size_t)t * T.cap_shell * T.n_pairs_max;
 
   // per-shell geometric weights: sum_members mult * Re(G_a conj G_b)  (scattering/__init__.py:312-331)
+  const bool staged = (long long)n_raw * n_pairs <= (long long)cap_list;
+  double *geo_s = keys;                         // the sort keys are no longer needed
   double my_max = 0.0;
   for (int s = tid; s < n_raw; s += TABLE_THREADS) {
     double acc[XRSD_MAX_PAIRS];
     for (int i = 0; i < XRSD_MAX_PAIRS; ++i) acc[i] = 0.0;
     int msum = 0;
     int h0 = 0, k0 = 0, l0 = 0;
-    for (int r = seg_start[s]; r < seg_start[s + 1]; ++r) {
+    const int r_lo = seg_start[s], r_hi = seg_start[s + 1];
+    for (int r = r_lo; r < r_hi; ++r) {
       const int c = list_cell[sidx[r]];
       int h, k, l;
       cell_to_hkl(S, c, h, k, l);
-      if (r == seg_start[s]) { h0 = h; k0 = k; l0 = l; }
+      if (r == r_lo) { h0 = h; k0 = k; l0 = l; }
       const double mult = (double)grid[c];
       msum += (int)grid[c];
       double gre[XRSD_MAX_SPECIES], gim[XRSD_MAX_SPECIES];
@@ -353,15 +396,25 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
       for (int a = 0; a < n_sp; ++a)
         for (int bq = a; bq < n_sp; ++bq, ++ip) acc[ip] += mult * (gre[a] * gre[bq] + gim[a] * gim[bq]);
     }
-    o_hkl[s * 4 + 0] = h0; o_hkl[s * 4 + 1] = k0; o_hkl[s * 4 + 2] = l0; o_hkl[s * 4 + 3] = msum;
+    if (staged) {
+      msum_s[s] = msum;
+    } else {
+      o_hkl[s * 4 + 0] = h0; o_hkl[s * 4 + 1] = k0; o_hkl[s * 4 + 2] = l0; o_hkl[s * 4 + 3] = msum;
+    }
     for (int ip = 0; ip < n_pairs; ++ip) {
-      o_geo[(size_t)s * T.n_pairs_max + ip] = acc[ip];
+      if (!staged) o_geo[(size_t)s * T.n_pairs_max + ip] = acc[ip];
       my_max = fmax(my_max, fabs(acc[ip]));
     }
+    if (staged) {
+      // every thread first finishes reading keys-independent data above; geo_s aliases keys, which
+      // nobody reads any more after the shell boundaries were found
+      for (int ip = 0; ip < n_pairs; ++ip) geo_s[(size_t)s * n_pairs + ip] = acc[ip];
+    }
   }
-  if (!pop.prune_extinct) { finish(n_raw); return; }
+  if (!pop.prune_extinct && !staged) { finish(n_raw); return; }
 
-  // ---- 6. drop extinct shells (all pair weights < 1e-20 of the largest), in place
+  // ---- 6. keep shells with a pair weight above 1e-20 of the largest (all of them when pruning is
+  //         off) and write them, compacted, to the output arrays
   for (int o = 16; o > 0; o >>= 1) my_max = fmax(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
   __shared__ double wmax[TABLE_THREADS / 32];
   if ((tid & 31) == 0) wmax[tid >> 5] = my_max;
@@ -372,17 +425,39 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
     S.max_geo = m;
   }
   __syncthreads();
-  __threadfence_block();
-  const double thr = 1.0e-20 * S.max_geo;
+  const double thr = pop.prune_extinct ? 1.0e-20 * S.max_geo : -1.0;
+  if (staged) {
+    // count first so that a capacity overflow leaves the output untouched
+    int cnt = 0;
+    for (int s = tid; s < n_raw; s += TABLE_THREADS) {
+      bool keep = false;
+      for (int ip = 0; ip < n_pairs; ++ip) keep = keep || (fabs(geo_s[(size_t)s * n_pairs + ip]) > thr);
+      cnt += keep;
+    }
+    if (cnt) atomicAdd(&S.n_shell, cnt);
+    __syncthreads();
+    if (S.n_shell > T.cap_shell) {
+      if (tid == 0) S.status |= XRSD_TABLE_SHELL_OVERFLOW;
+      __syncthreads();
+      finish(0);
+      return;
+    }
+  }
   for (int s0 = 0; s0 < n_raw; s0 += TABLE_THREADS) {
     const int s = s0 + tid;
     bool keep = false;
-    int hk[4];
+    int hk[4] = {0, 0, 0, 0};
     double geo[XRSD_MAX_PAIRS];
     if (s < n_raw) {
-      for (int j = 0; j < 4; ++j) hk[j] = o_hkl[s * 4 + j];
+      if (staged) {
+        int h, k, l;
+        cell_to_hkl(S, list_cell[sidx[seg_start[s]]], h, k, l);
+        hk[0] = h; hk[1] = k; hk[2] = l; hk[3] = msum_s[s];
+      } else {
+        for (int j = 0; j < 4; ++j) hk[j] = o_hkl[s * 4 + j];
+      }
       for (int ip = 0; ip < n_pairs; ++ip) {
-        geo[ip] = o_geo[(size_t)s * T.n_pairs_max + ip];
+        geo[ip] = staged ? geo_s[(size_t)s * n_pairs + ip] : o_geo[(size_t)s * T.n_pairs_max + ip];
         keep = keep || (fabs(geo[ip]) > thr);
       }
     }
@@ -404,6 +479,7 @@ extern "C" int64_t xrsd_table_smem_layout(int32_t max_cells, int32_t cap_list) {
   off += (size_t)cap_list * sizeof(double);
   off += (size_t)cap_list * sizeof(int) * 2;
   off += ((size_t)cap_list + 1) * sizeof(int);
+  off += (size_t)cap_list * sizeof(int);
   return (int64_t)((off + 15) & ~(size_t)15);
 }
 

@@ -92,7 +92,9 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         abi.check(lib.xrsd_lm_propose(d_p.data_ptr(), d_p.shape[1], batch, idx, nf, jout[0].data_ptr(), jout[1].data_ptr(),
                                       d_lambda.data_ptr(), d_lo.data_ptr(), d_hi.data_ptr(), d_active.data_ptr(),
                                       d_trial.data_ptr(), stream))
-        t_tables = eng.build_tables(layout, d_trial, batch, max_cells=max_cells, reuse=t_tables) if layout.n_xtal else None
+        # in-loop table builds do not read their status back (no host sync); it is checked every 5 iterations
+        t_tables = eng.build_tables(layout, d_trial, batch, max_cells=max_cells, reuse=t_tables,
+                                    check=t_tables is None) if layout.n_xtal else None
         abi.check(lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_trial.data_ptr(),
                                           d_trial.shape[1], batch, C.byref(t_tables.c) if t_tables is not None else None,
                                           d_I.data_ptr(), d_dI.data_ptr() if d_dI is not None else None, ld_obs,
@@ -103,9 +105,20 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         eng.launches += 3
         if layout.n_xtal:
             # accepted systems now sit at `trial`: their tables are the trial tables
-            tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=tables)
-        if (it % 5 == 4) and not bool(d_active.any().item()):
-            break
+            tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=tables, check=False)
+        if it % 5 == 4:
+            flags = torch.stack([d_active.any().to(torch.int32),
+                                 tables.status.max() if tables is not None else torch.zeros((), dtype=torch.int32, device=eng.device),
+                                 t_tables.status.max() if t_tables is not None else torch.zeros((), dtype=torch.int32, device=eng.device)])
+            any_active, st_a, st_b = [int(v) for v in flags.cpu().tolist()]      # the only host sync of the loop
+            if st_a or st_b:
+                # a table outgrew its storage since the last check: rebuild both sets with the checked
+                # (self-growing) path and resynchronise chi2 with the accepted parameters
+                tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells)
+                t_tables = None
+                d_chi2.copy_(eng.residual(layout, obj, d_q, d_p, d_I, d_dI, tables=tables))
+            if not any_active:
+                break
     # final objective at the accepted parameters
     chi2 = eng.residual(layout, obj, d_q, d_p, d_I, d_dI, tables=tables)
     res = FitResult(d_p, chi2_init, chi2, n_iter, d_nacc, d_active.bool())
