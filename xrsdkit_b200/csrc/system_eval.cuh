@@ -33,12 +33,18 @@ constexpr int EVAL_THREADS = 128;
 constexpr int SHELL_CHUNK = 128;
 
 // shared-memory working set of one CTA (besides the pattern buffer)
+constexpr int CHEB_N = 17;                       // Chebyshev nodes of the far-field interpolant (degree 16)
+constexpr int CHEB_GROUPS = EVAL_THREADS / CHEB_N;  // thread groups that share the shells of one node
+
 struct EvalShared {
   VoigtConst vc;
   Cell cell;
   double red[EVAL_THREADS / 32];
   double bcast[4];
   int ibcast[4];
+  double cheb_cos[CHEB_N * CHEB_N];              // cos(pi k (m + 1/2) / N)
+  double cheb_part[CHEB_GROUPS * CHEB_N];
+  double cheb_coef[CHEB_N];
 };
 
 __device__ __forceinline__ double block_sum(double v, EvalShared *S) {
@@ -114,6 +120,15 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
   const int tid = threadIdx.x;
   for (int i = tid; i < q_count; i += EVAL_THREADS) I_sm[i] = 0.0;
   const int span = EVAL_THREADS * QPT;
+  // strictly ascending q over the span enables the far-field interpolation of crystalline sums
+  bool q_sorted = false;
+  if (HAS_XTAL && L.n_xtal > 0) {
+    bool mine = true;
+    for (int i = tid; i + 1 < q_count; i += EVAL_THREADS) mine = mine && (q[q_begin + i] < q[q_begin + i + 1]);
+    q_sorted = __syncthreads_and(mine) != 0;
+    for (int i = tid; i < CHEB_N * CHEB_N; i += EVAL_THREADS)
+      S->cheb_cos[i] = cospi((double)(i / CHEB_N) * ((double)(i % CHEB_N) + 0.5) / (double)CHEB_N);
+  }
 
   for (int ip = 0; ip < L.n_pops; ++ip) {
     const xrsd_pop_t &pop = L.pops[ip];
@@ -312,6 +327,125 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         int chunk = scratch_doubles / rec;
         if (chunk > SHELL_CHUNK) chunk = SHELL_CHUNK;
         const bool stage_once = n_shell <= chunk;
+        // (q_s, W_s[...]) of shells [s0, s0+ns) into scratch
+        auto stage_shells = [&](int s0, int ns) {
+            for (int sl = tid; sl < ns; sl += EVAL_THREADS) {
+            const int s = s0 + sl;
+            const double qs = 2.0 * M_PI * g_norm(S->cell.b, (double)sh_hkl[4 * s], (double)sh_hkl[4 * s + 1], (double)sh_hkl[4 * s + 2]);
+            double ltz = 1.0;
+            if (pop.lorentz) {
+              const double th = asin(wl * qs / (4.0 * M_PI));
+              ltz = 1.0 / (sin(th) * sin(2.0 * th));
+            }
+            scratch[sl * rec] = qs;
+            if (radial_multi) {
+              int ipq = 0;
+              for (int a = 0; a < n_sp; ++a)
+                for (int bb = a; bb < n_sp; ++bb, ++ipq)
+                  scratch[sl * rec + 1 + ipq] = ltz * ((a == bb) ? 1.0 : 2.0) * sh_geo[(size_t)s * T.n_pairs_max + ipq];
+            } else if (radial) {
+              scratch[sl * rec + 1] = ltz * sh_geo[(size_t)s * T.n_pairs_max];
+            } else {
+              double ffs[XRSD_MAX_SPECIES];
+              for (int a = 0; a < n_sp; ++a) ffs[a] = species_ff(pop, a, prm, qs);
+              double w = 0.0;
+              int ipq = 0;
+              for (int a = 0; a < n_sp; ++a)
+                for (int bb = a; bb < n_sp; ++bb, ++ipq)
+                  w += ((a == bb) ? 1.0 : 2.0) * ffs[a] * ffs[bb] * sh_geo[(size_t)s * T.n_pairs_max + ipq];
+              scratch[sl * rec + 1] = ltz * w;
+            }
+          }
+        };
+        const double I0 = prm[pop.p_I0];
+        // per-q finish shared by both paths: radial form factor, polarisation, normalisation, I0
+        auto finish_q = [&](int i, double qi, double a_sum) {
+          if (radial && !radial_multi) {
+            const bool q0 = L.q0_is_zero && (q_begin + i == 0);
+            const double f = (q0 && pop.species_form[0] == XRSD_FORM_SPHERE) ? 1.0 : species_ff(pop, 0, prm, qi);
+            a_sum *= f * f;
+          }
+          double pz = 1.0;
+          if (pop.polz) {
+            const double th = asin(wl * qi / (4.0 * M_PI));
+            const double c2 = cos(2.0 * th);
+            pz = 0.5 * (1.0 + c2 * c2);
+          }
+          I_sm[i] += I0 * (pz * a_sum / norm);                     // I0 * (pz*I/I0_norm)
+        };
+        // ---- far-field interpolation path ------------------------------------------------------
+        // For a run of EVAL_THREADS consecutive q-points (centre c, half-width H) every shell with
+        // |q_s - c| >= max(8 H, H + 12 core widths) is "far": the sum of all far shells is smooth over
+        // the run (nearest singular structure >= 7 H away), so it is evaluated at CHEB_N Chebyshev
+        // nodes only and interpolated (degree 16: truncation < 1e-13 relative, tests/test_gpu_parity.py),
+        // while the few near shells are summed directly.  This cuts the profile evaluations per q from
+        // n_shell to about n_near + CHEB_N n_far / EVAL_THREADS.
+        const bool interp = HAS_XTAL && stage_once && !radial_multi && q_sorted && pop.profile != XRSD_PROFILE_GAUSSIAN &&
+                            n_shell >= 8 && q_count >= 32;
+        if (interp) {
+          __syncthreads();
+          stage_shells(0, n_shell);
+          __syncthreads();
+          const double core = (pop.profile == XRSD_PROFILE_VOIGT) ? fmax(1.0, S->vc.y) / P.a : sqrt(P.a);
+          for (int i0 = 0; i0 < q_count; i0 += EVAL_THREADS) {
+            const int i1 = min(q_count, i0 + EVAL_THREADS);
+            const double qa = q[q_begin + i0], qb = q[q_begin + i1 - 1];
+            const double c = 0.5 * (qa + qb), H = 0.5 * (qb - qa);
+            const double dn = fmax(8.0 * H, H + 12.0 * core);
+            // near shells form one contiguous range (the table is sorted by |G|)
+            if (tid == 0) { S->ibcast[0] = n_shell; S->ibcast[1] = 0; }
+            __syncthreads();
+            if (tid < n_shell && fabs(scratch[2 * tid] - c) < dn) {
+              atomicMin(&S->ibcast[0], tid);
+              atomicMax(&S->ibcast[1], tid + 1);
+            }
+            // far shells at the Chebyshev nodes: node m, shells g, g+G, ...
+            if (tid < CHEB_GROUPS * CHEB_N) {
+              const int g = tid / CHEB_N, m = tid - g * CHEB_N;
+              const double xm = (i1 - i0 > 1) ? fma(H, S->cheb_cos[CHEB_N + m], c) : c;   // row k=1: cos(pi (m+1/2)/N)
+              double part = 0.0;
+              for (int sl = g; sl < n_shell; sl += CHEB_GROUPS) {
+                const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
+                if (fabs(sw.x - c) >= dn) part = fma(sw.y, profile_eval(P, &S->vc, xm - sw.x), part);
+              }
+              S->cheb_part[tid] = part;
+            }
+            __syncthreads();
+            if (tid < CHEB_N) {
+              // coefficient k = tid: a_k = 2/N sum_m B_m cos(pi k (m+1/2)/N)
+              double ak = 0.0;
+              for (int m = 0; m < CHEB_N; ++m) {
+                double bm = 0.0;
+                for (int g = 0; g < CHEB_GROUPS; ++g) bm += S->cheb_part[g * CHEB_N + m];
+                ak = fma(bm, S->cheb_cos[tid * CHEB_N + m], ak);
+              }
+              S->cheb_coef[tid] = ak * (2.0 / CHEB_N);
+            }
+            __syncthreads();
+            const int i = i0 + tid;
+            if (i < i1) {
+              const double qi = q[q_begin + i];
+              // Clenshaw for sum_k' a_k T_k(t), t in [-1, 1]
+              const double t = (H > 0.0) ? (qi - c) / H : 0.0;
+              double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+              for (int k = CHEB_N - 1; k >= 1; --k) {
+                const double b0 = fma(2.0 * t, b1, S->cheb_coef[k] - b2);
+                b2 = b1;
+                b1 = b0;
+              }
+              double a_sum = fma(t, b1, 0.5 * S->cheb_coef[0] - b2);
+              const int s_lo = S->ibcast[0], s_hi = S->ibcast[1];
+              for (int sl = s_lo; sl < s_hi; ++sl) {
+                const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
+                a_sum = fma(sw.y, profile_eval(P, &S->vc, qi - sw.x), a_sum);
+              }
+              finish_q(i, qi, a_sum);
+            }
+            __syncthreads();
+          }
+          break;
+        }
         for (int off = 0; off < q_count; off += span) {
           double qv[QPT], acc[QPT];
           double accp[QPT][RADIAL_MULTI ? XRSD_MAX_PAIRS : 1];
@@ -333,33 +467,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
             // population instead of once per q-span
             if (!(stage_once && off > 0)) {
             __syncthreads();
-            for (int sl = tid; sl < ns; sl += EVAL_THREADS) {
-              const int s = s0 + sl;
-              const double qs = 2.0 * M_PI * g_norm(S->cell.b, (double)sh_hkl[4 * s], (double)sh_hkl[4 * s + 1], (double)sh_hkl[4 * s + 2]);
-              double ltz = 1.0;
-              if (pop.lorentz) {
-                const double th = asin(wl * qs / (4.0 * M_PI));
-                ltz = 1.0 / (sin(th) * sin(2.0 * th));
-              }
-              scratch[sl * rec] = qs;
-              if (radial_multi) {
-                int ipq = 0;
-                for (int a = 0; a < n_sp; ++a)
-                  for (int bb = a; bb < n_sp; ++bb, ++ipq)
-                    scratch[sl * rec + 1 + ipq] = ltz * ((a == bb) ? 1.0 : 2.0) * sh_geo[(size_t)s * T.n_pairs_max + ipq];
-              } else if (radial) {
-                scratch[sl * rec + 1] = ltz * sh_geo[(size_t)s * T.n_pairs_max];
-              } else {
-                double ffs[XRSD_MAX_SPECIES];
-                for (int a = 0; a < n_sp; ++a) ffs[a] = species_ff(pop, a, prm, qs);
-                double w = 0.0;
-                int ipq = 0;
-                for (int a = 0; a < n_sp; ++a)
-                  for (int bb = a; bb < n_sp; ++bb, ++ipq)
-                    w += ((a == bb) ? 1.0 : 2.0) * ffs[a] * ffs[bb] * sh_geo[(size_t)s * T.n_pairs_max + ipq];
-                scratch[sl * rec + 1] = ltz * w;
-              }
-            }
+            stage_shells(s0, ns);
             __syncthreads();
             }
             if (!radial_multi) {
@@ -381,7 +489,6 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               }
             }
           }
-          const double I0 = prm[pop.p_I0];
 #pragma unroll
           for (int j = 0; j < QPT; ++j) {
             if (!ok[j]) continue;
