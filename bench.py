@@ -310,7 +310,17 @@ class Work(object):
             return FLOPS_PER_PAIR_RNORMAL * 50.5 + FLOPS_PER_Q_OVERHEAD_CFG2, SURVEY_FLOPS_PER_SETQ_CFG2
         ns = float(np.mean([float(t.n_shell.float().mean().item()) for t in self.tables]))
         extra = 80.0 + 45.0 if self.name in ("cfg4", "cfg5") else 0.0       # Guinier-Porod + log/residual
-        return 60.0 * ns + 150.0 + extra, 205.0 * ns + 150.0 + extra
+        # far-field interpolation: per q only the shells within dn = max(8H, H + 12 core) of
+        # its 128-point run are evaluated directly, the rest through 17 Chebyshev nodes per run
+        lay, P = self.lay, self.P
+        H = 0.5 * 127 * (self.q[-1] - self.q[0]) / (self.n_q - 1)
+        hg, hl = P[:, lay.slot("x__hwhm_g")], P[:, lay.slot("x__hwhm_l")]
+        s2 = hg / np.sqrt(2 * np.log(2)) * np.sqrt(2)
+        core = np.maximum(1.0, hl / s2) * s2
+        dn = np.maximum(8 * H, H + 12 * core)
+        n_near = float(np.mean(np.minimum(ns, ns * 2 * dn / (self.q[-1] - self.q[0]))))
+        per_q = 60.0 * n_near + 17.0 * 60.0 * (ns - n_near) / 128.0 + 2.0 * 17.0 + 150.0 + extra
+        return per_q, 205.0 * ns + 150.0 + extra
 
 
 def run_gpu_arm(args):
