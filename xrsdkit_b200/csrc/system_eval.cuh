@@ -34,7 +34,7 @@ constexpr int SHELL_CHUNK = 128;
 
 // shared-memory working set of one CTA (besides the pattern buffer)
 constexpr int CHEB_N = 17;                       // Chebyshev nodes of the far-field interpolant (degree 16)
-constexpr int CHEB_GROUPS = EVAL_THREADS / CHEB_N;  // thread groups that share the shells of one node
+constexpr int CHEB_ROUND = 16;                   // runs of EVAL_THREADS q-points handled between two barriers
 
 struct EvalShared {
   VoigtConst vc;
@@ -43,8 +43,9 @@ struct EvalShared {
   double bcast[4];
   int ibcast[4];
   double cheb_cos[CHEB_N * CHEB_N];              // cos(pi k (m + 1/2) / N)
-  double cheb_part[CHEB_GROUPS * CHEB_N];
-  double cheb_coef[CHEB_N];
+  double cheb_part[2 * CHEB_ROUND * CHEB_N];     // node sums, two shell-parity halves per node
+  double cheb_coef[CHEB_ROUND * CHEB_N];
+  int near_lo[CHEB_ROUND], near_hi[CHEB_ROUND];
 };
 
 __device__ __forceinline__ double block_sum(double v, EvalShared *S) {
@@ -387,55 +388,73 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
           stage_shells(0, n_shell);
           __syncthreads();
           const double core = (pop.profile == XRSD_PROFILE_VOIGT) ? fmax(1.0, S->vc.y) / P.a : sqrt(P.a);
-          for (int i0 = 0; i0 < q_count; i0 += EVAL_THREADS) {
-            const int i1 = min(q_count, i0 + EVAL_THREADS);
-            const double qa = q[q_begin + i0], qb = q[q_begin + i1 - 1];
-            const double c = 0.5 * (qa + qb), H = 0.5 * (qb - qa);
-            const double dn = fmax(8.0 * H, H + 12.0 * core);
-            // near shells form one contiguous range (the table is sorted by |G|)
-            if (tid == 0) { S->ibcast[0] = n_shell; S->ibcast[1] = 0; }
-            __syncthreads();
-            if (tid < n_shell && fabs(scratch[2 * tid] - c) < dn) {
-              atomicMin(&S->ibcast[0], tid);
-              atomicMax(&S->ibcast[1], tid + 1);
-            }
-            // far shells at the Chebyshev nodes: node m, shells g, g+G, ...
-            if (tid < CHEB_GROUPS * CHEB_N) {
-              const int g = tid / CHEB_N, m = tid - g * CHEB_N;
-              const double xm = (i1 - i0 > 1) ? fma(H, S->cheb_cos[CHEB_N + m], c) : c;   // row k=1: cos(pi (m+1/2)/N)
+          // rounds of CHEB_ROUND runs: (1) node sums of all runs, (2) coefficients, (3) per-q evaluation;
+          // three barriers per round instead of four per run
+          for (int r0 = 0; r0 < q_count; r0 += CHEB_ROUND * EVAL_THREADS) {
+            const int n_run = min(CHEB_ROUND, (q_count - r0 + EVAL_THREADS - 1) / EVAL_THREADS);
+            // (1) item = (run, node m, shell parity g)
+            for (int item = tid; item < n_run * CHEB_N * 2; item += EVAL_THREADS) {
+              const int run = item / (2 * CHEB_N), rem = item - run * 2 * CHEB_N;
+              const int g = rem / CHEB_N, m = rem - g * CHEB_N;
+              const int i0 = r0 + run * EVAL_THREADS, i1 = min(q_count, i0 + EVAL_THREADS);
+              const double qa = q[q_begin + i0], qb = q[q_begin + i1 - 1];
+              const double c = 0.5 * (qa + qb), H = 0.5 * (qb - qa);
+              const double dn = fmax(8.0 * H, H + 12.0 * core);
+              const double xm = fma(H, S->cheb_cos[CHEB_N + m], c);       // row k=1: cos(pi (m+1/2)/N)
               double part = 0.0;
-              for (int sl = g; sl < n_shell; sl += CHEB_GROUPS) {
+              int lo = n_shell, hi = 0;
+              for (int sl = g; sl < n_shell; sl += 2) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
                 if (fabs(sw.x - c) >= dn) part = fma(sw.y, profile_eval(P, &S->vc, xm - sw.x), part);
+                else { lo = min(lo, sl); hi = max(hi, sl + 1); }
               }
-              S->cheb_part[tid] = part;
+              S->cheb_part[item] = part;
+              // near shells form one contiguous range (the table is sorted by |G|); even-parity half here
+              if (m == 0 && g == 0) { S->near_lo[run] = lo; S->near_hi[run] = hi; }
             }
             __syncthreads();
-            if (tid < CHEB_N) {
-              // coefficient k = tid: a_k = 2/N sum_m B_m cos(pi k (m+1/2)/N)
+            if (tid < n_run) {           // merge the odd-parity half of the near range
+              const int run = tid;
+              int lo = S->near_lo[run], hi = S->near_hi[run];
+              const int i0 = r0 + run * EVAL_THREADS, i1 = min(q_count, i0 + EVAL_THREADS);
+              const double qa = q[q_begin + i0], qb = q[q_begin + i1 - 1];
+              const double c = 0.5 * (qa + qb), H = 0.5 * (qb - qa);
+              const double dn = fmax(8.0 * H, H + 12.0 * core);
+              for (int sl = 1; sl < n_shell; sl += 2)
+                if (fabs(scratch[2 * sl] - c) < dn) { lo = min(lo, sl); hi = max(hi, sl + 1); }
+              S->near_lo[run] = lo;
+              S->near_hi[run] = hi;
+            }
+            // (2) coefficient (run, k): a_k = 2/N sum_m B_m cos(pi k (m+1/2)/N)
+            for (int item = tid; item < n_run * CHEB_N; item += EVAL_THREADS) {
+              const int run = item / CHEB_N, k = item - run * CHEB_N;
+              const double *pa = S->cheb_part + run * 2 * CHEB_N;
               double ak = 0.0;
-              for (int m = 0; m < CHEB_N; ++m) {
-                double bm = 0.0;
-                for (int g = 0; g < CHEB_GROUPS; ++g) bm += S->cheb_part[g * CHEB_N + m];
-                ak = fma(bm, S->cheb_cos[tid * CHEB_N + m], ak);
-              }
-              S->cheb_coef[tid] = ak * (2.0 / CHEB_N);
+#pragma unroll
+              for (int m = 0; m < CHEB_N; ++m) ak = fma(pa[m] + pa[CHEB_N + m], S->cheb_cos[k * CHEB_N + m], ak);
+              S->cheb_coef[item] = ak * (2.0 / CHEB_N);
             }
             __syncthreads();
-            const int i = i0 + tid;
-            if (i < i1) {
+            // (3) one q-point per thread and run
+            for (int run = 0; run < n_run; ++run) {
+              const int i0 = r0 + run * EVAL_THREADS, i1 = min(q_count, i0 + EVAL_THREADS);
+              const int i = i0 + tid;
+              if (i >= i1) continue;
+              const double qa = q[q_begin + i0], qb = q[q_begin + i1 - 1];
+              const double c = 0.5 * (qa + qb), H = 0.5 * (qb - qa);
               const double qi = q[q_begin + i];
-              // Clenshaw for sum_k' a_k T_k(t), t in [-1, 1]
+              // Clenshaw for a_0/2 + sum_k a_k T_k(t), t in [-1, 1]
               const double t = (H > 0.0) ? (qi - c) / H : 0.0;
+              const double *ck = S->cheb_coef + run * CHEB_N;
               double b1 = 0.0, b2 = 0.0;
 #pragma unroll
               for (int k = CHEB_N - 1; k >= 1; --k) {
-                const double b0 = fma(2.0 * t, b1, S->cheb_coef[k] - b2);
+                const double b0 = fma(2.0 * t, b1, ck[k] - b2);
                 b2 = b1;
                 b1 = b0;
               }
-              double a_sum = fma(t, b1, 0.5 * S->cheb_coef[0] - b2);
-              const int s_lo = S->ibcast[0], s_hi = S->ibcast[1];
+              double a_sum = fma(t, b1, 0.5 * ck[0] - b2);
+              const int s_lo = S->near_lo[run], s_hi = S->near_hi[run];
               for (int sl = s_lo; sl < s_hi; ++sl) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
                 a_sum = fma(sw.y, profile_eval(P, &S->vc, qi - sw.x), a_sum);
