@@ -499,7 +499,11 @@ def run_gpu_arm(args):
         "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.workload), "n_q": n_q, "sets_per_gpu_per_step": B,
-                   "evaluations_per_set": W.evals_per_unit, "q_evals_per_s": value * n_q,
+                   "evaluations_per_set": W.evals_per_unit,
+                   "evaluations_note": ("reference-equivalent: a forward-difference Jacobian of 8 parameters costs the "
+                                        "reference 9 pattern evaluations per system; 6 are executed here, the three I0 "
+                                        "derivatives are analytic") if args.workload == "cfg4" else None,
+                   "q_evals_per_s": value * n_q,
                    "l2": "each step writes or reads %.0f MB of patterns (L2 is 126 MB) and rotates over 4 parameter matrices" % (8e-6 * B * n_q),
                    "checksum": checksum},
         "e2e": {"value": e2e, "unit": W.unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps, "api": api},

@@ -302,3 +302,35 @@ def test_mixed_layout_collection_in_batches(eng, golden_systems):
         err, same = rel_err(row, arr[m["key"] + "_I"])
         assert same and err <= TOL_F64, (m["name"], err)
     assert eng.launches - n0 <= 2 * n_groups + 2
+
+
+def test_far_field_interpolation_over_extreme_widths(ref_tables, eng):
+    """The crystalline sum interpolates the far shells.  Peak widths from 1e-8 to 5e-2,
+    Voigt and Lorentzian, sorted and unsorted q (unsorted disables the interpolation): all against the oracle."""
+    from oracle import xrsd_oracle as orc
+    from xrsdkit_b200.system import System
+    rs = np.random.RandomState(77)
+    q = np.linspace(0.02, 0.9, 1536)
+    q_shuffled = q[rs.permutation(q.size)]
+    for trial in range(14):
+        a = rs.uniform(25, 55)
+        prof = "voigt" if trial % 3 else "lorentzian"
+        pars = {"a": {"value": a}, "r": {"value": a * rs.uniform(0.2, 0.35)}, "I0": {"value": 3.0}}
+        if prof == "voigt":
+            pars["hwhm_g"] = {"value": 10 ** rs.uniform(-8, np.log10(5e-2))}
+            pars["hwhm_l"] = {"value": 10 ** rs.uniform(-8, np.log10(5e-2))}
+        else:
+            pars["hwhm"] = {"value": 10 ** rs.uniform(-6, np.log10(5e-2))}
+        s = System(x=dict(structure="crystalline", form="spherical",
+                          settings={"lattice": "F_cubic", "space_group": "Fm-3m", "q_max": 0.9, "profile": prof,
+                                    "structure_factor_mode": "radial" if trial % 2 else "local"},
+                          parameters=pars), source_wavelength=0.8265617)
+        ref = orc.system_intensity(q, s.to_dict(), **ref_tables)
+        got = s.compute_intensity(q)
+        err, same = rel_err(got, ref, floor_frac=0.0)
+        assert same and err <= TOL_F64, (trial, prof, pars, err)
+        # the same points in random order take the direct path; the two paths must agree with each other
+        got_u = s.compute_intensity(q_shuffled)
+        ref_u = orc.system_intensity(q_shuffled, s.to_dict(), **ref_tables)
+        err_u, same_u = rel_err(got_u, ref_u, floor_frac=0.0)
+        assert same_u and err_u <= TOL_F64, (trial, prof, pars, err_u)

@@ -250,8 +250,9 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
 }
 
 int64_t xrsd_jacobian_workspace_bytes(int32_t n_q, int32_t batch, int32_t n_free) {
-  // [batch][n_free+1][n_q] doubles of variant patterns + one ticket per system (zero-initialised)
-  return (int64_t)batch * (n_free + 1) * n_q * 8 + (((int64_t)batch * 4 + 255) & ~255LL);
+  // [batch][(n_free+1) variants + XRSD_MAX_POPS running totals][n_q] doubles (upper bound: linear
+  // parameters need no variant slab) + one ticket per system (zero-initialised)
+  return (int64_t)batch * (n_free + 1 + XRSD_MAX_POPS) * n_q * 8 + (((int64_t)batch * 4 + 255) & ~255LL);
 }
 
 int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q, int32_t n_q,
@@ -277,7 +278,7 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   const int per = pick_q_per_cta(n_q, batch * (n_free + 1), scratch);
   if (xrsd_jacobian_smem(layout->n_params, n_free, per, scratch, nullptr) + kStaticSmem > (size_t)kMaxSmem)
     return fail(XRSD_ECAPACITY, "jacobian working set does not fit in shared memory");
-  const int64_t fbytes = (int64_t)batch * (n_free + 1) * n_q * 8;
+  const int64_t fbytes = (int64_t)batch * (n_free + 1 + XRSD_MAX_POPS) * n_q * 8;
   double *d_Fvar = (double *)d_workspace;
   unsigned *d_tickets = (unsigned *)((char *)d_workspace + fbytes);
   cudaError_t e = xrsd_launch_jacobian(layout, obj, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables, d_Iobs,

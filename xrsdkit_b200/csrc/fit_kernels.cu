@@ -10,6 +10,7 @@
 //                       evaluates one parameter set per call; here n_free+1 sets per system)
 //   lm_*             <- replaces the lmfit Nelder-Mead driver of system/__init__.py:262-266
 //                       (no oracle in the reference; parity is defined on outcomes)
+#include <string.h>
 #include <algorithm>
 #include "system_eval.cuh"
 
@@ -17,8 +18,43 @@ namespace xrsd {
 
 struct FreeSet {
   int n_free;
-  int idx[XRSD_MAX_FREE];
+  int idx[XRSD_MAX_FREE];       // parameter slot of free parameter j
+  int n_var;                    // evaluated variants: 1 (base) + number of non-linear free parameters
+  int var_of[XRSD_MAX_FREE];    // variant index (>= 1) of a non-linear parameter, 0 for a linear one
+  int pop_of[XRSD_MAX_FREE];    // linear parameter (an I0): index of its population, else -1
+  int free_of_var[XRSD_MAX_FREE + 1];   // inverse of var_of
 };
+
+// An I0 multiplies its whole population (scattering/__init__.py:48,64,66; system/noise.py:56-62), so
+// dI/dI0 = I_pop / I0 needs no extra evaluation: the base variant records the running total after
+// each population and the reducer forms f(I + h I_pop / I0) from it.
+static FreeSet make_free_set(const xrsd_layout_t *L, const int32_t *free_idx, int n_free) {
+  FreeSet F;
+  memset(&F, 0, sizeof(F));
+  F.n_free = n_free;
+  F.n_var = 1;
+  for (int j = 0; j < XRSD_MAX_FREE; ++j) { F.pop_of[j] = -1; }
+  for (int j = 0; j < n_free; ++j) {
+    F.idx[j] = free_idx[j];
+    int pop = -1;
+    if (L)
+      for (int k = 0; k < L->n_pops; ++k)
+        if (L->pops[k].kind != XRSD_POP_NONE && L->pops[k].p_I0 == free_idx[j]) pop = k;
+    // a slot shared by two populations (not produced by the lowering) would not be linear in one term
+    int uses = 0;
+    if (L)
+      for (int k = 0; k < L->n_pops; ++k) uses += (L->pops[k].p_I0 == free_idx[j]);
+    if (pop >= 0 && uses == 1) {
+      F.pop_of[j] = pop;
+      F.var_of[j] = 0;
+    } else {
+      F.var_of[j] = F.n_var;
+      F.free_of_var[F.n_var] = j;
+      ++F.n_var;
+    }
+  }
+  return F;
+}
 
 // weight and mask of one q-point (system/__init__.py:164-172)
 __device__ __forceinline__ bool fit_weight(const xrsd_objective_t &O, double qv, double Iobs, const double *dI, size_t k,
@@ -88,7 +124,7 @@ jacobian_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
   __shared__ double steps[XRSD_MAX_FREE];
   __shared__ int is_last;
   const int tid = threadIdx.x;
-  const int nf = F.n_free, nv = nf + 1;
+  const int nf = F.n_free, nv = F.n_var, n_slab = nv + L.n_pops;
   const long long bid = blockIdx.x;
   const int per_sys = nv * n_tiles;
   const int b = (int)(bid / per_sys);
@@ -106,15 +142,22 @@ jacobian_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
     steps[tid] = (p0 != 0.0) ? fabs(p0) * rel_step : rel_step;
   }
   __syncthreads();
-  if (v > 0 && tid == 0) prm_s[F.idx[v - 1]] = prm[F.idx[v - 1]] + steps[v - 1];
+  if (v > 0 && tid == 0) {
+    const int j = F.free_of_var[v];
+    prm_s[F.idx[j]] = prm[F.idx[j]] + steps[j];
+  }
   __syncthreads();
   const int q_begin = tile * q_per_cta;
   const int q_count = min(q_per_cta, n_q - q_begin);
-  accumulate_system<2, RM, HX>(L, prm_s, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S, prm);
-  double *dst = Fvar + ((size_t)b * nv + v) * n_q + q_begin;
+  // slabs of this system in the scratch: [0, nv) variants (slab 0 = base, raw I), [nv, nv+n_pops) the
+  // base variant's running totals after each population
+  double *slab0 = Fvar + (size_t)b * n_slab * n_q;
+  accumulate_system<2, RM, HX>(L, prm_s, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S, prm,
+                               v == 0 ? slab0 + (size_t)nv * n_q + q_begin : nullptr, n_q);
+  double *dst = slab0 + (size_t)v * n_q + q_begin;
   for (int i = tid; i < q_count; i += EVAL_THREADS) {
     const double x = I_sm[i];
-    dst[i] = O.logI_weighted ? ((x > 0.0) ? log(x) : NAN) : x;
+    dst[i] = (v > 0 && O.logI_weighted) ? ((x > 0.0) ? log(x) : NAN) : x;
   }
   // ---- ticket: the last CTA of this system reduces
   __threadfence();
@@ -128,24 +171,39 @@ jacobian_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
   for (int i = tid; i < n_acc; i += EVAL_THREADS) acc_sm[i] = 0.0;
   const double *obs = Iobs + (size_t)b * ld_obs;
   const double *err = dI ? dI + (size_t)b * ld_obs : nullptr;
-  const double *Fb = Fvar + (size_t)b * nv * n_q;
+  const double *Fb = slab0;
   constexpr int RT = 256;                       // q-points per reduction stage
-  double *Fv = smem_d;                          // [nv][RT]
-  double *wts = Fv + (size_t)nv * RT;
+  double *Fv = smem_d;                          // [nf + 1][RT]: f of the base and of one variant per free parameter
+  double *wts = Fv + (size_t)(nf + 1) * RT;
   double *fobs = wts + RT;
   const int warp = tid >> 5, lane = tid & 31;
   for (int q0 = 0; q0 < n_q; q0 += RT) {
     const int qc = min(RT, n_q - q0);
     __syncthreads();
-    for (int i = tid; i < nv * qc; i += EVAL_THREADS) {
-      const int vv = i / qc, k = i - vv * qc;
-      Fv[vv * RT + k] = __ldcg(Fb + (size_t)vv * n_q + q0 + k);     // written by other CTAs: read through L2
+    for (int i = tid; i < (nf + 1) * qc; i += EVAL_THREADS) {
+      const int jj = i / qc, k = i - jj * qc;        // jj = 0: base, jj = j + 1: free parameter j
+      const double I0v = __ldcg(Fb + q0 + k);        // written by other CTAs: read through L2
+      double val;
+      if (jj == 0) {
+        val = O.logI_weighted ? ((I0v > 0.0) ? log(I0v) : NAN) : I0v;
+      } else if (F.var_of[jj - 1] > 0) {
+        val = __ldcg(Fb + (size_t)F.var_of[jj - 1] * n_q + q0 + k);
+      } else {
+        const int kp = F.pop_of[jj - 1];
+        double Ik = __ldcg(Fb + (size_t)(nv + kp) * n_q + q0 + k);
+        if (kp > 0) Ik -= __ldcg(Fb + (size_t)(nv + kp - 1) * n_q + q0 + k);
+        const double pj = prm[F.idx[jj - 1]];
+        const double Iv = (pj != 0.0) ? fma(steps[jj - 1] / pj, Ik, I0v) : I0v;
+        val = O.logI_weighted ? ((Iv > 0.0) ? log(Iv) : NAN) : Iv;
+      }
+      Fv[jj * RT + k] = val;
     }
+    __syncthreads();
     for (int i = tid; i < qc; i += EVAL_THREADS) {
       const double Io = obs[q0 + i];
       double w;
       bool fit = fit_weight(O, q[q0 + i], Io, err, q0 + i, w);
-      const double f0 = __ldcg(Fb + q0 + i);
+      const double f0 = Fv[i];
       if (O.logI_weighted) fit = fit && (f0 == f0);                  // I_comp > 0
       wts[i] = fit ? w : 0.0;
       fobs[i] = fit ? (O.logI_weighted ? log(Io) : Io) : 0.0;
@@ -326,9 +384,7 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
                                             unsigned *d_tickets, int q_per_cta, int scratch_doubles, int radial_multi,
                                             cudaStream_t stream) {
   using namespace xrsd;
-  FreeSet F;
-  F.n_free = n_free;
-  for (int i = 0; i < XRSD_MAX_FREE; ++i) F.idx[i] = (i < n_free) ? free_idx[i] : 0;
+  const FreeSet F = make_free_set(layout, free_idx, n_free);
   int pat = 0;
   const size_t smem = xrsd_jacobian_smem(layout->n_params, n_free, q_per_cta, scratch_doubles, &pat);
   auto kern = radial_multi ? jacobian_kernel<true, true>
@@ -337,7 +393,7 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
   if (e != cudaSuccess) return e;
   if (batch <= 0) return cudaSuccess;
   const int n_tiles = (n_q + q_per_cta - 1) / q_per_cta;
-  const long long n_blocks = (long long)batch * (n_free + 1) * n_tiles;
+  const long long n_blocks = (long long)batch * F.n_var * n_tiles;
   if (n_blocks > 2147483647LL) return cudaErrorInvalidConfiguration;
   kern<<<(unsigned)n_blocks, EVAL_THREADS, smem, stream>>>(*layout, *obj, d_q, n_q, d_params, ldp, batch, *tables, d_Iobs, d_dI,
                                                           ld_obs, F, rel_step, d_JTJ, d_JTr, d_chi2, d_Fvar, d_tickets,
@@ -349,9 +405,7 @@ extern "C" cudaError_t xrsd_launch_lm_propose(const double *d_params, int ldp, i
                                               const double *d_JTJ, const double *d_JTr, const double *d_lambda,
                                               const double *d_lo, const double *d_hi, const uint8_t *d_active,
                                               double *d_trial, cudaStream_t stream) {
-  FreeSet F;
-  F.n_free = n_free;
-  for (int i = 0; i < XRSD_MAX_FREE; ++i) F.idx[i] = (i < n_free) ? free_idx[i] : 0;
+  const FreeSet F = xrsd::make_free_set(nullptr, free_idx, n_free);
   if (batch <= 0) return cudaSuccess;
   xrsd::lm_propose_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(d_params, ldp, batch, F, d_JTJ, d_JTr, d_lambda, d_lo, d_hi,
                                                                    d_active, d_trial);

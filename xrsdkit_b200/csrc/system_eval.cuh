@@ -112,7 +112,11 @@ template <int QPT, bool RADIAL_MULTI, bool HAS_XTAL = true>
 __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restrict__ prm, const xrsd_tables_t &T, int b,
                                   const double *__restrict__ q, int n_q, int q_begin, int q_count,
                                   double *__restrict__ I_sm, double *__restrict__ scratch, int scratch_doubles,
-                                  EvalShared *S, const double *__restrict__ prm_topo = nullptr) {
+                                  EvalShared *S, const double *__restrict__ prm_topo = nullptr,
+                                  double *__restrict__ cum_out = nullptr, long long cum_stride = 0) {
+  // cum_out (optional, global memory): after population ip has been added, the running total of this
+  // CTA's span is written to cum_out[ip * cum_stride + i].  The Jacobian uses the differences as the
+  // per-population contributions, which give the derivatives of the linear parameters (I0) for free.
   // prm_topo (optional) is the parameter row that decides the DISCRETE part of the evaluation --
   // the number of radii of each size quadrature -- while `prm` supplies the values.  The variants of
   // a finite-difference Jacobian pass their unperturbed row here so that a step in r or sigma cannot
@@ -539,6 +543,10 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         }
       } break;
       default: break;
+    }
+    if (cum_out != nullptr) {
+      double *dst = cum_out + (size_t)ip * cum_stride;
+      for (int i = tid; i < q_count; i += EVAL_THREADS) dst[i] = I_sm[i];   // each thread owns i = tid (mod EVAL_THREADS)
     }
   }
   __syncthreads();

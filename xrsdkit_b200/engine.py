@@ -218,7 +218,7 @@ class Engine(object):
         idx = (C.c_int32 * nf)(*free_slots)
         n_q = q.shape[0]
         # HBM scratch for the variant patterns: chunk the batch so it stays under ~4 GB
-        chunk = max(1, min(batch, int(4e9 // (8 * (nf + 1) * n_q))))
+        chunk = max(1, min(batch, int(4e9 // (8 * (nf + 1 + abi.MAX_POPS) * n_q))))
         need = int(self.lib.xrsd_jacobian_workspace_bytes(n_q, chunk, nf))
         ws = getattr(self, "_jac_ws", None)
         if ws is None or ws.numel() < need:
