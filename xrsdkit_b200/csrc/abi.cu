@@ -190,16 +190,17 @@ int xrsd_reflection_tables(const xrsd_layout_t *layout, const double *d_params, 
   return XRSD_OK;
 }
 
-static int pick_q_per_cta(int n_q, int batch, int scratch) {
+static int pick_q_per_cta(int n_q, int batch, int scratch, bool has_xtal) {
   // One CTA holds a span of one pattern in shared memory.  Spans are multiples of 512 q-points;
   // aim for >= 24 CTAs per SM in the grid (several waves, so the last partial wave costs little)
-  // and keep the span at <= 4096 q-points (32 KB) so that six 128-thread CTAs stay resident per SM.
+  // and keep the span small enough for six 128-thread CTAs per SM: 4096 q-points (32 KB), or 3072 for
+  // layouts with crystalline populations, whose kernels carry ~7 KB of static shared memory.
   const long long want_ctas = 148LL * 24;
   long long tiles = (want_ctas + batch - 1) / batch;
   if (tiles < 1) tiles = 1;
   long long per = ((long long)n_q + tiles - 1) / tiles;
   per = ((per + 511) / 512) * 512;
-  const long long cap = std::max(512LL, std::min(4096LL, ((long long)(36 * 1024 / 8 - scratch) / 512) * 512));
+  const long long cap = std::max(512LL, std::min(has_xtal ? 3072LL : 4096LL, ((long long)(36 * 1024 / 8 - scratch) / 512) * 512));
   per = std::min(per, cap);
   per = std::min<long long>(per, ((long long)n_q + 511) / 512 * 512);
   return (int)std::max(512LL, per);
@@ -219,7 +220,7 @@ int xrsd_intensity_batch(const xrsd_layout_t *layout, const double *d_q, int32_t
   int rm;
   const int scratch = scratch_doubles_for(layout, &rm);
   if (scratch < 0) return fail(XRSD_ECAPACITY, "size quadrature too fine for shared memory (sampling_width/sampling_step)");
-  const int per = pick_q_per_cta(n_q, batch, scratch);
+  const int per = pick_q_per_cta(n_q, batch, scratch, layout->n_xtal > 0);
   cudaError_t e = xrsd_launch_intensity(layout, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables, d_I,
                                         (long long)ld_I, per, scratch, rm, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "intensity_kernel");
@@ -275,7 +276,7 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   int rm;
   const int scratch = scratch_doubles_for(layout, &rm);
   if (scratch < 0) return fail(XRSD_ECAPACITY, "size quadrature too fine for shared memory");
-  const int per = pick_q_per_cta(n_q, batch * (n_free + 1), scratch);
+  const int per = pick_q_per_cta(n_q, batch * (n_free + 1), scratch, false);   // measured: 4096-point spans win here
   if (xrsd_jacobian_smem(layout->n_params, n_free, per, scratch, nullptr) + kStaticSmem > (size_t)kMaxSmem)
     return fail(XRSD_ECAPACITY, "jacobian working set does not fit in shared memory");
   const int64_t fbytes = (int64_t)batch * (n_free + 1 + XRSD_MAX_POPS) * n_q * 8;

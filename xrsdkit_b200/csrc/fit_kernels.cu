@@ -77,7 +77,7 @@ residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
                 const double *__restrict__ Iobs, const double *__restrict__ dI, long long ld_obs,
                 double *__restrict__ chi2, int scratch_doubles) {
   extern __shared__ __align__(16) double smem_d[];
-  __shared__ EvalShared S;
+  __shared__ EvalSharedT<HX> S;
   const int b = blockIdx.x;
   if (b >= batch) return;
   double *I_sm = smem_d;
@@ -119,7 +119,7 @@ jacobian_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
                 double *__restrict__ chi2, double *__restrict__ Fvar, unsigned *__restrict__ tickets,
                 int q_per_cta, int n_tiles, int pattern_doubles, int scratch_doubles) {
   extern __shared__ __align__(16) double smem_d[];
-  __shared__ EvalShared S;
+  __shared__ EvalSharedT<HX> S;
   __shared__ double acc_sm[XRSD_MAX_FREE * (XRSD_MAX_FREE + 1) / 2 + XRSD_MAX_FREE + 2];
   __shared__ double steps[XRSD_MAX_FREE];
   __shared__ int is_last;

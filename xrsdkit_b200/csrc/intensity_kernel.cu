@@ -12,7 +12,7 @@ intensity_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restri
                  const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
                  double *__restrict__ I_out, long long ldI, int q_per_cta, int n_tiles, int scratch_doubles) {
   extern __shared__ __align__(16) double smem_d[];
-  __shared__ EvalShared S;
+  __shared__ EvalSharedT<HX> S;
   const long long bid = blockIdx.x;
   const int b = (int)(bid / n_tiles);
   const int tile = (int)(bid - (long long)b * n_tiles);

@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <type_traits>
 #include "../../include/xrsd_b200.h"
 #include "faddeeva.cuh"
 #include "forms.cuh"
@@ -34,19 +35,26 @@ constexpr int SHELL_CHUNK = 128;
 
 // shared-memory working set of one CTA (besides the pattern buffer)
 constexpr int CHEB_N = 17;                       // Chebyshev nodes of the far-field interpolant (degree 16)
-constexpr int CHEB_ROUND = 16;                   // runs of EVAL_THREADS q-points handled between two barriers
+constexpr int CHEB_ROUND = 8;                    // runs of EVAL_THREADS q-points handled between two barriers
 
-struct EvalShared {
-  VoigtConst vc;
-  Cell cell;
-  double red[EVAL_THREADS / 32];
-  double bcast[4];
-  int ibcast[4];
+struct ChebShared {                               // only in kernels that can meet a crystalline population
   double cheb_cos[CHEB_N * CHEB_N];              // cos(pi k (m + 1/2) / N)
   double cheb_part[2 * CHEB_ROUND * CHEB_N];     // node sums, two shell-parity halves per node
   double cheb_coef[CHEB_ROUND * CHEB_N];
   int near_lo[CHEB_ROUND], near_hi[CHEB_ROUND];
 };
+struct NoCheb {};
+
+struct EvalCore {
+  VoigtConst vc;
+  Cell cell;
+  double red[EVAL_THREADS / 32];
+  double bcast[4];
+  int ibcast[4];
+};
+template <bool HAS_XTAL>
+struct EvalSharedT : EvalCore, std::conditional<HAS_XTAL, ChebShared, NoCheb>::type {};
+using EvalShared = EvalCore;                     // what the helpers below need
 
 __device__ __forceinline__ double block_sum(double v, EvalShared *S) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -112,7 +120,7 @@ template <int QPT, bool RADIAL_MULTI, bool HAS_XTAL = true>
 __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restrict__ prm, const xrsd_tables_t &T, int b,
                                   const double *__restrict__ q, int n_q, int q_begin, int q_count,
                                   double *__restrict__ I_sm, double *__restrict__ scratch, int scratch_doubles,
-                                  EvalShared *S, const double *__restrict__ prm_topo = nullptr,
+                                  EvalSharedT<HAS_XTAL> *S, const double *__restrict__ prm_topo = nullptr,
                                   double *__restrict__ cum_out = nullptr, long long cum_stride = 0) {
   // cum_out (optional, global memory): after population ip has been added, the running total of this
   // CTA's span is written to cum_out[ip * cum_stride + i].  The Jacobian uses the differences as the
@@ -127,7 +135,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
   const int span = EVAL_THREADS * QPT;
   // strictly ascending q over the span enables the far-field interpolation of crystalline sums
   bool q_sorted = false;
-  if (HAS_XTAL && L.n_xtal > 0) {
+  if constexpr (HAS_XTAL) {
     bool mine = true;
     for (int i = tid; i + 1 < q_count; i += EVAL_THREADS) mine = mine && (q[q_begin + i] < q[q_begin + i + 1]);
     q_sorted = __syncthreads_and(mine) != 0;
@@ -290,7 +298,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         }
       } break;
       // ---------------------------------------------------------------- crystalline
-      case XRSD_POP_CRYSTALLINE: if (HAS_XTAL) {
+      case XRSD_POP_CRYSTALLINE: if constexpr (HAS_XTAL) {
         const int t = b * L.n_xtal + pop.table_slot;
         const int n_shell = T.n_shell[t];
         if (n_shell <= 0) break;                                   // scattering/__init__.py:277-278
@@ -385,7 +393,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         // nodes only and interpolated (degree 16: truncation < 1e-13 relative, tests/test_gpu_parity.py),
         // while the few near shells are summed directly.  This cuts the profile evaluations per q from
         // n_shell to about n_near + CHEB_N n_far / EVAL_THREADS.
-        const bool interp = HAS_XTAL && stage_once && !radial_multi && q_sorted && pop.profile != XRSD_PROFILE_GAUSSIAN &&
+        const bool interp = stage_once && !radial_multi && q_sorted && pop.profile != XRSD_PROFILE_GAUSSIAN &&
                             n_shell >= 8 && q_count >= 32;
         if (interp) {
           __syncthreads();

@@ -67,7 +67,10 @@ class Engine(object):
         torch = self.torch
         if isinstance(arr, torch.Tensor):
             return arr.to(device=self.device, dtype=torch.float64).contiguous()
-        return torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        if not a.flags.writeable:      # e.g. arrays that come out of an .npz: torch wants a writable buffer
+            a = a.copy()
+        return torch.from_numpy(a).to(self.device)
 
     def _n_pairs(self, layout):
         n = 1
