@@ -467,7 +467,7 @@ def run_gpu_arm(args):
 
     # ---- CPU baseline: bounded sample on the host cores
     cores = host_cores()
-    per_core = {"cfg2": 24, "cfg3": 2, "cfg4": 2, "cfg5": 2}[args.workload]
+    per_core = {"cfg2": 256, "cfg3": 4, "cfg4": 4, "cfg5": 4}[args.workload]     # ~10-30 core-seconds per core in total
     cpu = None
     if not args.no_cpu:
         arm = CpuArm(args.workload, cores)
