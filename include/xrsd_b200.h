@@ -162,9 +162,11 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
 /* Forward-difference Jacobian of the weighted residual vector, reduced in-kernel to the
  * normal equations: JTJ[b][n_free][n_free], JTr[b][n_free], chi2[b].  free_idx[n_free] (HOST
  * array) are parameter slots; rel_step is the relative step (absolute for zero-valued
- * parameters).  One launch: grid = batch x (n_free+1) variants x q-spans, the last CTA of a
- * system reduces.  d_workspace holds xrsd_jacobian_workspace_bytes() bytes; its trailing
- * ticket area must be zero before the FIRST call (the kernel re-zeroes it).  Reflection tables
+ * parameters).  Two launches: variants (grid = batch x evaluated variants x q-spans; an I0 is
+ * linear and needs no variant) and a chunked reduction.  d_workspace holds
+ * xrsd_jacobian_workspace_bytes() bytes; the accumulator / ticket area behind the variant slabs
+ * must be zero before the FIRST call with a given (n_q, batch, n_free) (the reduction re-zeroes
+ * it; zeroing the whole workspace once is the simple way).  Reflection tables
  * and the radius counts of size quadratures are held fixed inside one evaluation. */
 int64_t xrsd_jacobian_workspace_bytes(int32_t n_q, int32_t batch, int32_t n_free);
 int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj,

@@ -22,7 +22,8 @@ cudaError_t xrsd_launch_residual(const xrsd_layout_t *, const xrsd_objective_t *
 size_t xrsd_jacobian_smem(int, int, int, int, int *);
 cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *, const xrsd_objective_t *, const double *, int, const double *, int, int,
                                  const xrsd_tables_t *, const double *, const double *, long long, const int32_t *, int, double,
-                                 double *, double *, double *, double *, unsigned *, int, int, int, cudaStream_t);
+                                 double *, double *, double *, double *, double *, unsigned *, int, int, int, cudaStream_t);
+size_t xrsd_jacobian_acc_doubles(int);
 cudaError_t xrsd_launch_lm_propose(const double *, int, int, const int32_t *, int, const double *, const double *,
                                    const double *, const double *, const double *, const uint8_t *, double *, cudaStream_t);
 cudaError_t xrsd_launch_lm_update(double *, int, int, const double *, double *, const double *, double *, uint8_t *, int *,
@@ -252,8 +253,11 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
 
 int64_t xrsd_jacobian_workspace_bytes(int32_t n_q, int32_t batch, int32_t n_free) {
   // [batch][(n_free+1) variants + XRSD_MAX_POPS running totals][n_q] doubles (upper bound: linear
-  // parameters need no variant slab) + one ticket per system (zero-initialised)
-  return (int64_t)batch * (n_free + 1 + XRSD_MAX_POPS) * n_q * 8 + (((int64_t)batch * 4 + 255) & ~255LL);
+  // parameters need no variant slab), then per system the normal-equation accumulators and one ticket
+  // (both zero-initialised by the caller once; the reduce kernel re-zeroes them)
+  const int64_t fbytes = (int64_t)batch * (n_free + 1 + XRSD_MAX_POPS) * n_q * 8;
+  const int64_t abytes = (((int64_t)batch * (int64_t)xrsd_jacobian_acc_doubles(n_free) * 8) + 255) & ~255LL;
+  return fbytes + abytes + (((int64_t)batch * 4 + 255) & ~255LL);
 }
 
 int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q, int32_t n_q,
@@ -280,11 +284,13 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   if (xrsd_jacobian_smem(layout->n_params, n_free, per, scratch, nullptr) + kStaticSmem > (size_t)kMaxSmem)
     return fail(XRSD_ECAPACITY, "jacobian working set does not fit in shared memory");
   const int64_t fbytes = (int64_t)batch * (n_free + 1 + XRSD_MAX_POPS) * n_q * 8;
+  const int64_t abytes = (((int64_t)batch * (int64_t)xrsd_jacobian_acc_doubles(n_free) * 8) + 255) & ~255LL;
   double *d_Fvar = (double *)d_workspace;
-  unsigned *d_tickets = (unsigned *)((char *)d_workspace + fbytes);
+  double *d_acc = (double *)((char *)d_workspace + fbytes);
+  unsigned *d_tickets = (unsigned *)((char *)d_workspace + fbytes + abytes);
   cudaError_t e = xrsd_launch_jacobian(layout, obj, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables, d_Iobs,
                                        obj->has_dI ? d_dI : nullptr, (long long)ld_obs, free_idx, n_free, rel_step, d_JTJ,
-                                       d_JTr, d_chi2, d_Fvar, d_tickets, per, scratch, rm, (cudaStream_t)stream);
+                                       d_JTr, d_chi2, d_Fvar, d_acc, d_tickets, per, scratch, rm, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "jacobian_kernel");
   return XRSD_OK;
 }

@@ -104,27 +104,29 @@ residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
   if (threadIdx.x == 0) chi2[b] = num / den;
 }
 
-// Normal equations by forward differences, ONE launch.  Grid = batch x (n_free+1) variants x q-spans:
-// every CTA evaluates one parameter variant of one system over one q-span exactly like the intensity
-// kernel does and parks f(I) (log I or I) in an HBM scratch [batch][n_free+1][n_q] (1.2 MB per system
-// at cfg4 sizes, written and read once: ~0.3 us of HBM time against ~10 us of FP64 work).  The CTA
-// that finishes last for a system (atomic ticket) reduces its variants to JTJ / JTr / chi2, staging
-// 256 q-points of all variants at a time in shared memory.
+// Normal equations by forward differences: two launches.
+//
+// (1) jacobian_variants_kernel, grid = batch x evaluated variants x q-spans: every CTA evaluates one
+//     parameter variant of one system over one q-span exactly like the intensity kernel does and parks
+//     the raw I(q) in an HBM scratch [batch][n_var + n_pops][n_q] (the base variant also writes its
+//     running total after each population).  At cfg4 sizes that is ~0.6 MB per system, written and
+//     read once: ~0.2 us of HBM time against ~6 us of FP64 work.
+// (2) jacobian_reduce_kernel, grid = batch x q-chunks: forms the weighted residual r and the difference
+//     quotients D_j per q-point (log mode: D_j = log1p((I_j - I_0)/I_0), no cancellation between two
+//     logarithms), accumulates JTJ / JTr / chi2 in registers, folds them per CTA and adds them to a
+//     per-system accumulator with FP64 atomics; the chunk that takes the last ticket normalises and
+//     writes the outputs.  (A first version reduced inside the variant kernel by the last-finishing
+//     CTA of each system: that serial tail cost 25 % of the whole Jacobian.)
 template <bool RM, bool HX>
 __global__ void __launch_bounds__(EVAL_THREADS, 6)
-jacobian_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t O, const double *__restrict__ q, int n_q,
-                const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
-                const double *__restrict__ Iobs, const double *__restrict__ dI, long long ld_obs,
-                const FreeSet F, double rel_step, double *__restrict__ JTJ, double *__restrict__ JTr,
-                double *__restrict__ chi2, double *__restrict__ Fvar, unsigned *__restrict__ tickets,
-                int q_per_cta, int n_tiles, int pattern_doubles, int scratch_doubles) {
+jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ q, int n_q,
+                         const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T, const FreeSet F,
+                         double rel_step, double *__restrict__ Fvar, int q_per_cta, int n_tiles, int pattern_doubles,
+                         int scratch_doubles) {
   extern __shared__ __align__(16) double smem_d[];
   __shared__ EvalSharedT<HX> S;
-  __shared__ double acc_sm[XRSD_MAX_FREE * (XRSD_MAX_FREE + 1) / 2 + XRSD_MAX_FREE + 2];
-  __shared__ double steps[XRSD_MAX_FREE];
-  __shared__ int is_last;
   const int tid = threadIdx.x;
-  const int nf = F.n_free, nv = F.n_var, n_slab = nv + L.n_pops;
+  const int nv = F.n_var, n_slab = nv + L.n_pops;
   const long long bid = blockIdx.x;
   const int per_sys = nv * n_tiles;
   const int b = (int)(bid / per_sys);
@@ -137,129 +139,174 @@ jacobian_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
   double *prm_s = scratch + scratch_doubles;
   const double *prm = params + (size_t)b * ldp;
   for (int i = tid; i < np; i += EVAL_THREADS) prm_s[i] = prm[i];
-  if (tid < nf) {
-    const double p0 = prm[F.idx[tid]];
-    steps[tid] = (p0 != 0.0) ? fabs(p0) * rel_step : rel_step;
-  }
   __syncthreads();
   if (v > 0 && tid == 0) {
     const int j = F.free_of_var[v];
-    prm_s[F.idx[j]] = prm[F.idx[j]] + steps[j];
+    const double p0 = prm[F.idx[j]];
+    prm_s[F.idx[j]] = p0 + ((p0 != 0.0) ? fabs(p0) * rel_step : rel_step);
   }
   __syncthreads();
   const int q_begin = tile * q_per_cta;
   const int q_count = min(q_per_cta, n_q - q_begin);
-  // slabs of this system in the scratch: [0, nv) variants (slab 0 = base, raw I), [nv, nv+n_pops) the
-  // base variant's running totals after each population
+  // slabs of this system: [0, nv) variants (slab 0 = base), [nv, nv+n_pops) the base variant's running
+  // totals after each population
   double *slab0 = Fvar + (size_t)b * n_slab * n_q;
   accumulate_system<2, RM, HX>(L, prm_s, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S, prm,
                                v == 0 ? slab0 + (size_t)nv * n_q + q_begin : nullptr, n_q);
   double *dst = slab0 + (size_t)v * n_q + q_begin;
-  for (int i = tid; i < q_count; i += EVAL_THREADS) {
-    const double x = I_sm[i];
-    dst[i] = (v > 0 && O.logI_weighted) ? ((x > 0.0) ? log(x) : NAN) : x;
+  for (int i = tid; i < q_count; i += EVAL_THREADS) dst[i] = I_sm[i];
+}
+
+constexpr int JR_THREADS = 128;
+
+// RB rows of JTJ are accumulated per pass over the chunk (RB * NF accumulators live in registers)
+template <int NF, int RB>
+__global__ void __launch_bounds__(JR_THREADS)
+jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__restrict__ q, int n_q,
+                       const double *__restrict__ params, int ldp, int batch, const double *__restrict__ Iobs,
+                       const double *__restrict__ dI, long long ld_obs, const FreeSet F, double rel_step,
+                       const double *__restrict__ Fvar, double *__restrict__ acc_g, unsigned *__restrict__ tickets,
+                       double *__restrict__ JTJ, double *__restrict__ JTr, double *__restrict__ chi2, int chunk_q,
+                       int n_chunks) {
+  constexpr int NACC = NF * NF + NF + 2;          // full square (upper part used), JTr, chi2 numerator, sum w
+  __shared__ double fold[JR_THREADS / 32][RB * NF + NF + 2];
+  __shared__ int is_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks;
+  if (b >= batch) return;
+  const int nf = F.n_free, nv = F.n_var, n_slab = nv + n_pops;
+  const double *prm = params + (size_t)b * ldp;
+  const double *obs = Iobs + (size_t)b * ld_obs;
+  const double *err = dI ? dI + (size_t)b * ld_obs : nullptr;
+  const double *Fb = Fvar + (size_t)b * n_slab * n_q;
+  double step[NF], lin[NF];
+#pragma unroll
+  for (int j = 0; j < NF; ++j) {
+    const double p0 = (j < nf) ? prm[F.idx[j]] : 1.0;
+    step[j] = (p0 != 0.0) ? fabs(p0) * rel_step : rel_step;
+    lin[j] = (p0 != 0.0) ? step[j] / p0 : 0.0;     // h / I0 for a linear parameter
   }
-  // ---- ticket: the last CTA of this system reduces
+  const int q_lo = chunk * chunk_q, q_hi = min(n_q, q_lo + chunk_q);
+  double *accb = acc_g + (size_t)b * NACC;
+  for (int row0 = 0; row0 < nf; row0 += RB) {
+    double aJ[RB][NF], ar[RB], c2 = 0.0, sw = 0.0;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      ar[r] = 0.0;
+#pragma unroll
+      for (int k = 0; k < NF; ++k) aJ[r][k] = 0.0;
+    }
+    for (int i = q_lo + tid; i < q_hi; i += JR_THREADS) {
+      const double Io = obs[i];
+      double w;
+      bool fit = fit_weight(O, q[i], Io, err, i, w);
+      const double I0v = Fb[i];
+      if (O.logI_weighted) fit = fit && (I0v > 0.0);
+      if (!fit) continue;
+      const double f0 = O.logI_weighted ? log(I0v) : I0v;
+      const double fo = O.logI_weighted ? log(Io) : Io;
+      const double res = f0 - fo;
+      const double inv = O.logI_weighted ? 1.0 / I0v : 1.0;
+      double D[NF];
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        double d = 0.0;
+        if (j < nf) {
+          if (F.var_of[j] > 0) {
+            d = Fb[(size_t)F.var_of[j] * n_q + i] - I0v;
+          } else {
+            const int kp = F.pop_of[j];
+            double Ik = Fb[(size_t)(nv + kp) * n_q + i];
+            if (kp > 0) Ik -= Fb[(size_t)(nv + kp - 1) * n_q + i];
+            d = lin[j] * Ik;
+          }
+          if (O.logI_weighted) {
+            const double x = d * inv;
+            if (!(x > -1.0)) d = 0.0;                                  // variant intensity <= 0: no information
+            else if (fabs(x) < 1.0e-3) d = x * fma(x, fma(x, fma(x, -0.25, 1.0 / 3.0), -0.5), 1.0);
+            else d = log1p(x);
+          }
+          if (!(d == d)) d = 0.0;
+        }
+        D[j] = d;
+      }
+      if (row0 == 0) { c2 = fma(w, res * res, c2); sw += w; }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int j = row0 + r;
+        if (j < nf) {
+          double dj = 0.0;
+#pragma unroll
+          for (int k = 0; k < NF; ++k) if (k == j) dj = D[k];
+          const double wdj = w * dj;
+          ar[r] = fma(wdj, res, ar[r]);
+#pragma unroll
+          for (int k = 0; k < NF; ++k) aJ[r][k] = fma(wdj, D[k], aJ[r][k]);
+        }
+      }
+    }
+    // fold over the CTA: warp shuffles, then one atomic per entry
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+#pragma unroll
+      for (int k = 0; k < NF; ++k) {
+        double v = aJ[r][k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) fold[warp][r * NF + k] = v;
+      }
+      double v = ar[r];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) fold[warp][RB * NF + r] = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) { c2 += __shfl_xor_sync(0xffffffffu, c2, o); sw += __shfl_xor_sync(0xffffffffu, sw, o); }
+    if (lane == 0) { fold[warp][RB * NF + NF] = c2; fold[warp][RB * NF + NF + 1] = sw; }
+    __syncthreads();
+    for (int e = tid; e < RB * NF + RB + 2; e += JR_THREADS) {
+      double v = 0.0;
+      int src = e, dst = -1;
+      if (e < RB * NF) {
+        const int r = e / NF, k = e - r * NF, j = row0 + r;
+        if (j < nf && k >= j && k < nf) dst = j * NF + k;
+      } else if (e < RB * NF + RB) {
+        const int j = row0 + (e - RB * NF);
+        if (j < nf) dst = NF * NF + j;
+      } else if (row0 == 0) {
+        src = RB * NF + NF + (e - RB * NF - RB);
+        dst = NF * NF + NF + (e - RB * NF - RB);
+      }
+      if (dst >= 0) {
+        for (int wv = 0; wv < JR_THREADS / 32; ++wv) v += fold[wv][src];
+        atomicAdd(&accb[dst], v);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- the last chunk of this system normalises and writes the outputs
   __threadfence();
   __syncthreads();
-  if (tid == 0) is_last = (atomicAdd(&tickets[b], 1u) == (unsigned)(per_sys - 1));
+  if (tid == 0) is_last = (atomicAdd(&tickets[b], 1u) == (unsigned)(n_chunks - 1));
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  const int n_tri = nf * (nf + 1) / 2;
-  const int n_acc = n_tri + nf + 2;
-  for (int i = tid; i < n_acc; i += EVAL_THREADS) acc_sm[i] = 0.0;
-  const double *obs = Iobs + (size_t)b * ld_obs;
-  const double *err = dI ? dI + (size_t)b * ld_obs : nullptr;
-  const double *Fb = slab0;
-  constexpr int RT = 256;                       // q-points per reduction stage
-  double *Fv = smem_d;                          // [nf + 1][RT]: f of the base and of one variant per free parameter
-  double *wts = Fv + (size_t)(nf + 1) * RT;
-  double *fobs = wts + RT;
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int q0 = 0; q0 < n_q; q0 += RT) {
-    const int qc = min(RT, n_q - q0);
-    __syncthreads();
-    for (int i = tid; i < (nf + 1) * qc; i += EVAL_THREADS) {
-      const int jj = i / qc, k = i - jj * qc;        // jj = 0: base, jj = j + 1: free parameter j
-      const double I0v = __ldcg(Fb + q0 + k);        // written by other CTAs: read through L2
-      double val;
-      if (jj == 0) {
-        val = O.logI_weighted ? ((I0v > 0.0) ? log(I0v) : NAN) : I0v;
-      } else if (F.var_of[jj - 1] > 0) {
-        val = __ldcg(Fb + (size_t)F.var_of[jj - 1] * n_q + q0 + k);
-      } else {
-        const int kp = F.pop_of[jj - 1];
-        double Ik = __ldcg(Fb + (size_t)(nv + kp) * n_q + q0 + k);
-        if (kp > 0) Ik -= __ldcg(Fb + (size_t)(nv + kp - 1) * n_q + q0 + k);
-        const double pj = prm[F.idx[jj - 1]];
-        const double Iv = (pj != 0.0) ? fma(steps[jj - 1] / pj, Ik, I0v) : I0v;
-        val = O.logI_weighted ? ((Iv > 0.0) ? log(Iv) : NAN) : Iv;
-      }
-      Fv[jj * RT + k] = val;
-    }
-    __syncthreads();
-    for (int i = tid; i < qc; i += EVAL_THREADS) {
-      const double Io = obs[q0 + i];
-      double w;
-      bool fit = fit_weight(O, q[q0 + i], Io, err, q0 + i, w);
-      const double f0 = Fv[i];
-      if (O.logI_weighted) fit = fit && (f0 == f0);                  // I_comp > 0
-      wts[i] = fit ? w : 0.0;
-      fobs[i] = fit ? (O.logI_weighted ? log(Io) : Io) : 0.0;
-    }
-    __syncthreads();
-    // entry e of acc_sm is owned by warp (e mod n_warps); lanes stride over the stage
-    for (int e = warp; e < n_acc; e += EVAL_THREADS / 32) {
-      int j = -1, k = -1, kind;   // kind 0: JTJ(j,k)  1: JTr(j)  2: chi2 numerator  3: sum of weights
-      if (e < n_tri) {
-        kind = 0;
-        int r = e;
-        j = 0;
-        while (r >= nf - j) { r -= nf - j; ++j; }
-        k = j + r;
-      } else if (e < n_tri + nf) { kind = 1; j = e - n_tri; }
-      else if (e == n_tri + nf) kind = 2;
-      else kind = 3;
-      double sum = 0.0;
-      for (int i = lane; i < qc; i += 32) {
-        const double w = wts[i];
-        if (w == 0.0) continue;
-        const double f0 = Fv[i];
-        double term;
-        if (kind == 0) {
-          const double dj = Fv[(j + 1) * RT + i] - f0, dk = Fv[(k + 1) * RT + i] - f0;
-          term = (dj == dj && dk == dk) ? dj * dk : 0.0;
-        } else if (kind == 1) {
-          const double dj = Fv[(j + 1) * RT + i] - f0;
-          term = (dj == dj) ? dj * (f0 - fobs[i]) : 0.0;
-        } else if (kind == 2) {
-          term = (f0 - fobs[i]) * (f0 - fobs[i]);
-        } else {
-          term = 1.0;
-        }
-        sum = fma(w, term, sum);
-      }
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      if (lane == 0) acc_sm[e] += sum;
-    }
+  const double swt = __ldcg(&accb[NF * NF + NF + 1]);
+  for (int e = tid; e < nf * nf; e += JR_THREADS) {
+    const int j = e / nf, k = e - j * nf;
+    const int jj = min(j, k), kk = max(j, k);
+    double sj = 1.0, sk = 1.0;
+#pragma unroll
+    for (int m = 0; m < NF; ++m) { if (m == jj) sj = step[m]; if (m == kk) sk = step[m]; }
+    JTJ[((size_t)b * nf + j) * nf + k] = __ldcg(&accb[jj * NF + kk]) / (sj * sk) / swt;
   }
+  if (tid < nf) {
+    double sj = 1.0;
+#pragma unroll
+    for (int m = 0; m < NF; ++m) if (m == tid) sj = step[m];
+    JTr[(size_t)b * nf + tid] = __ldcg(&accb[NF * NF + tid]) / sj / swt;
+  }
+  if (tid == 0) chi2[b] = __ldcg(&accb[NF * NF + NF]) / swt;
   __syncthreads();
-  // normalise by the sum of weights and the steps; write out (full symmetric JTJ)
-  const double sw = acc_sm[n_tri + nf + 1];
-  for (int e = tid; e < n_tri; e += EVAL_THREADS) {
-    int r = e, j = 0;
-    while (r >= nf - j) { r -= nf - j; ++j; }
-    const int k = j + r;
-    const double val = acc_sm[e] / (steps[j] * steps[k]) / sw;
-    JTJ[((size_t)b * nf + j) * nf + k] = val;
-    JTJ[((size_t)b * nf + k) * nf + j] = val;
-  }
-  if (tid < nf) JTr[(size_t)b * nf + tid] = acc_sm[n_tri + tid] / steps[tid] / sw;
-  if (tid == 0) {
-    chi2[b] = acc_sm[n_tri + nf] / sw;
-    tickets[b] = 0;                              // ready for the next launch
-  }
+  for (int e = tid; e < NACC; e += JR_THREADS) accb[e] = 0.0;       // ready for the next launch
+  if (tid == 0) tickets[b] = 0;
 }
 
 // ---------------------------------------------------------------------------- LM algebra
@@ -370,34 +417,50 @@ extern "C" cudaError_t xrsd_launch_residual(const xrsd_layout_t *layout, const x
 }
 
 extern "C" size_t xrsd_jacobian_smem(int n_params, int n_free, int q_per_cta, int scratch_doubles, int *pattern_doubles) {
-  // pattern buffer: the q-span while evaluating, [(n_free+1)+2][256] while reducing
-  int pat = std::max((q_per_cta + 1) & ~1, (n_free + 3) * 256);
+  const int pat = (q_per_cta + 1) & ~1;
   if (pattern_doubles) *pattern_doubles = pat;
   return ((size_t)pat + (size_t)scratch_doubles + (size_t)((n_params + 1) & ~1)) * sizeof(double);
+}
+
+extern "C" size_t xrsd_jacobian_acc_doubles(int n_free) {
+  const int NF = n_free <= 8 ? 8 : XRSD_MAX_FREE;
+  return (size_t)(NF * NF + NF + 2);
 }
 
 extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q,
                                             int n_q, const double *d_params, int ldp, int batch,
                                             const xrsd_tables_t *tables, const double *d_Iobs, const double *d_dI,
                                             long long ld_obs, const int32_t *free_idx, int n_free, double rel_step,
-                                            double *d_JTJ, double *d_JTr, double *d_chi2, double *d_Fvar,
+                                            double *d_JTJ, double *d_JTr, double *d_chi2, double *d_Fvar, double *d_acc,
                                             unsigned *d_tickets, int q_per_cta, int scratch_doubles, int radial_multi,
                                             cudaStream_t stream) {
   using namespace xrsd;
   const FreeSet F = make_free_set(layout, free_idx, n_free);
   int pat = 0;
   const size_t smem = xrsd_jacobian_smem(layout->n_params, n_free, q_per_cta, scratch_doubles, &pat);
-  auto kern = radial_multi ? jacobian_kernel<true, true>
-                           : (layout->n_xtal ? jacobian_kernel<false, true> : jacobian_kernel<false, false>);
+  auto kern = radial_multi ? jacobian_variants_kernel<true, true>
+                           : (layout->n_xtal ? jacobian_variants_kernel<false, true> : jacobian_variants_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (batch <= 0) return cudaSuccess;
   const int n_tiles = (n_q + q_per_cta - 1) / q_per_cta;
   const long long n_blocks = (long long)batch * F.n_var * n_tiles;
   if (n_blocks > 2147483647LL) return cudaErrorInvalidConfiguration;
-  kern<<<(unsigned)n_blocks, EVAL_THREADS, smem, stream>>>(*layout, *obj, d_q, n_q, d_params, ldp, batch, *tables, d_Iobs, d_dI,
-                                                          ld_obs, F, rel_step, d_JTJ, d_JTr, d_chi2, d_Fvar, d_tickets,
+  kern<<<(unsigned)n_blocks, EVAL_THREADS, smem, stream>>>(*layout, d_q, n_q, d_params, ldp, batch, *tables, F, rel_step, d_Fvar,
                                                           q_per_cta, n_tiles, pat, scratch_doubles);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int chunk_q = 1024;
+  const int n_chunks = (n_q + chunk_q - 1) / chunk_q;
+  if ((long long)batch * n_chunks > 2147483647LL) return cudaErrorInvalidConfiguration;
+  if (n_free <= 8)
+    jacobian_reduce_kernel<8, 8><<<batch * n_chunks, JR_THREADS, 0, stream>>>(
+        layout->n_pops, *obj, d_q, n_q, d_params, ldp, batch, d_Iobs, d_dI, ld_obs, F, rel_step, d_Fvar, d_acc, d_tickets, d_JTJ,
+        d_JTr, d_chi2, chunk_q, n_chunks);
+  else
+    jacobian_reduce_kernel<XRSD_MAX_FREE, 4><<<batch * n_chunks, JR_THREADS, 0, stream>>>(
+        layout->n_pops, *obj, d_q, n_q, d_params, ldp, batch, d_Iobs, d_dI, ld_obs, F, rel_step, d_Fvar, d_acc, d_tickets, d_JTJ,
+        d_JTr, d_chi2, chunk_q, n_chunks);
   return cudaGetLastError();
 }
 
