@@ -141,9 +141,12 @@ int xrsd_struct_sizes(int32_t *sizeof_pop, int32_t *sizeof_layout, int32_t *size
  * batch, given the per-axis half-widths n1,n2,n3 (scattering/__init__.py:266-268). */
 int64_t xrsd_table_smem_bytes(int32_t n1, int32_t n2, int32_t n3);
 
-/* Build reflection tables for every crystalline population of every system of the batch. */
+/* Build reflection tables for every crystalline population of every system of the batch.
+ * d_active (optional, [batch] bytes): systems with a zero byte are skipped -- used by the fit loop
+ * for converged systems; the same convention applies to the residual and Jacobian calls below. */
 int xrsd_reflection_tables(const xrsd_layout_t *layout, const double *d_params, int32_t ld_params,
-                           int32_t batch, const xrsd_tables_t *tables, int32_t max_cells, void *stream);
+                           int32_t batch, const xrsd_tables_t *tables, int32_t max_cells,
+                           const uint8_t *d_active, void *stream);
 
 /* I[b, :] for b < batch.  d_q[n_q], d_params[batch][ld_params], d_I[batch][ld_I]. */
 int xrsd_intensity_batch(const xrsd_layout_t *layout, const double *d_q, int32_t n_q,
@@ -157,7 +160,7 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
                         const double *d_q, int32_t n_q, const double *d_params, int32_t ld_params,
                         int32_t batch, const xrsd_tables_t *tables,
                         const double *d_Iobs, const double *d_dI, int64_t ld_obs,
-                        double *d_chi2, void *stream);
+                        double *d_chi2, const uint8_t *d_active, void *stream);
 
 /* Forward-difference Jacobian of the weighted residual vector, reduced in-kernel to the
  * normal equations: JTJ[b][n_free][n_free], JTr[b][n_free], chi2[b].  free_idx[n_free] (HOST
@@ -174,7 +177,8 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
                         int32_t batch, const xrsd_tables_t *tables,
                         const double *d_Iobs, const double *d_dI, int64_t ld_obs,
                         const int32_t *free_idx, int32_t n_free, double rel_step,
-                        double *d_JTJ, double *d_JTr, double *d_chi2, void *d_workspace, void *stream);
+                        double *d_JTJ, double *d_JTr, double *d_chi2, void *d_workspace,
+                        const uint8_t *d_active, void *stream);
 
 /* One damped Gauss-Newton (Levenberg-Marquardt) proposal per system:
  * solve (JTJ + lambda*diag(JTJ)) delta = -JTr, project onto [lo, hi], write trial params. */

@@ -59,13 +59,13 @@ _SIGNATURES = {
     "xrsd_abi_version": (C.c_int, []),
     "xrsd_struct_sizes": (C.c_int, [C.POINTER(i32)] * 4),
     "xrsd_table_smem_bytes": (C.c_int64, [i32, i32, i32]),
-    "xrsd_reflection_tables": (C.c_int, [C.POINTER(Layout), vp, i32, i32, C.POINTER(Tables), i32, vp]),
+    "xrsd_reflection_tables": (C.c_int, [C.POINTER(Layout), vp, i32, i32, C.POINTER(Tables), i32, vp, vp]),
     "xrsd_intensity_batch": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, C.POINTER(Tables), vp, C.c_int64, vp]),
     "xrsd_residual_batch": (C.c_int, [C.POINTER(Layout), C.POINTER(Objective), vp, i32, vp, i32, i32,
-                                      C.POINTER(Tables), vp, vp, C.c_int64, vp, vp]),
+                                      C.POINTER(Tables), vp, vp, C.c_int64, vp, vp, vp]),
     "xrsd_jacobian_workspace_bytes": (C.c_int64, [i32, i32, i32]),
     "xrsd_jacobian_batch": (C.c_int, [C.POINTER(Layout), C.POINTER(Objective), vp, i32, vp, i32, i32,
-                                      C.POINTER(Tables), vp, vp, C.c_int64, C.POINTER(i32), i32, f64, vp, vp, vp, vp, vp]),
+                                      C.POINTER(Tables), vp, vp, C.c_int64, C.POINTER(i32), i32, f64, vp, vp, vp, vp, vp, vp]),
     "xrsd_lm_propose": (C.c_int, [vp, i32, i32, C.POINTER(i32), i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "xrsd_lm_update": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, vp, f64, f64, f64, f64, vp]),
     "xrsd_intensity_batch_host": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, vp, C.c_int64]),

@@ -11,18 +11,20 @@
 
 extern "C" {
 int64_t xrsd_table_smem_layout(int32_t max_cells, int32_t cap_list);
-cudaError_t xrsd_launch_tables(const xrsd_layout_t *, const double *, int, int, const xrsd_tables_t *, int, int, cudaStream_t);
+cudaError_t xrsd_launch_tables(const xrsd_layout_t *, const double *, int, int, const xrsd_tables_t *, int, int, const uint8_t *,
+                               cudaStream_t);
 cudaError_t xrsd_launch_intensity(const xrsd_layout_t *, const double *, int, const double *, int, int, const xrsd_tables_t *,
                                   double *, long long, int, int, int, cudaStream_t);
 cudaError_t xrsd_launch_fp64_probe(double *, int, int, cudaStream_t);
 cudaError_t xrsd_launch_profile(int, double, double, const double *, int, double *, cudaStream_t);
 cudaError_t xrsd_launch_residual(const xrsd_layout_t *, const xrsd_objective_t *, const double *, int, const double *, int, int,
                                  const xrsd_tables_t *, const double *, const double *, long long, double *, int, int,
-                                 cudaStream_t);
+                                 const uint8_t *, cudaStream_t);
 size_t xrsd_jacobian_smem(int, int, int, int, int *);
 cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *, const xrsd_objective_t *, const double *, int, const double *, int, int,
                                  const xrsd_tables_t *, const double *, const double *, long long, const int32_t *, int, double,
-                                 double *, double *, double *, double *, double *, unsigned *, int, int, int, cudaStream_t);
+                                 double *, double *, double *, double *, double *, unsigned *, int, int, int, const uint8_t *,
+                                 cudaStream_t);
 size_t xrsd_jacobian_acc_doubles(int);
 cudaError_t xrsd_launch_lm_propose(const double *, int, int, const int32_t *, int, const double *, const double *,
                                    const double *, const double *, const double *, const uint8_t *, double *, cudaStream_t);
@@ -161,7 +163,7 @@ int64_t xrsd_table_smem_bytes(int32_t n1, int32_t n2, int32_t n3) {
 }
 
 int xrsd_reflection_tables(const xrsd_layout_t *layout, const double *d_params, int32_t ld_params, int32_t batch,
-                           const xrsd_tables_t *tables, int32_t max_cells, void *stream) {
+                           const xrsd_tables_t *tables, int32_t max_cells, const uint8_t *d_active, void *stream) {
   int rc = check_layout(layout);
   if (rc) return rc;
   if (layout->n_xtal == 0 || batch <= 0) return XRSD_OK;
@@ -186,7 +188,7 @@ int xrsd_reflection_tables(const xrsd_layout_t *layout, const double *d_params, 
   while (cap_list > 64 && xrsd_table_smem_layout(max_cells, cap_list) + kStaticSmem > kMaxSmem) cap_list >>= 1;
   if (xrsd_table_smem_layout(max_cells, cap_list) + kStaticSmem > kMaxSmem)
     return fail(XRSD_ECAPACITY, "candidate box of %d cells does not fit in shared memory", max_cells);
-  cudaError_t e = xrsd_launch_tables(layout, d_params, ld_params, batch, tables, max_cells, cap_list, (cudaStream_t)stream);
+  cudaError_t e = xrsd_launch_tables(layout, d_params, ld_params, batch, tables, max_cells, cap_list, d_active, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "reflection_table_kernel");
   return XRSD_OK;
 }
@@ -230,7 +232,8 @@ int xrsd_intensity_batch(const xrsd_layout_t *layout, const double *d_q, int32_t
 
 int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q, int32_t n_q,
                         const double *d_params, int32_t ld_params, int32_t batch, const xrsd_tables_t *tables,
-                        const double *d_Iobs, const double *d_dI, int64_t ld_obs, double *d_chi2, void *stream) {
+                        const double *d_Iobs, const double *d_dI, int64_t ld_obs, double *d_chi2, const uint8_t *d_active,
+                        void *stream) {
   int rc = check_layout(layout);
   if (rc) return rc;
   if (batch <= 0 || n_q <= 0) return XRSD_OK;
@@ -245,7 +248,7 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   if (((size_t)n_q + scratch + 2) * 8 + kStaticSmem > (size_t)kMaxSmem)
     return fail(XRSD_ECAPACITY, "n_q=%d: a whole pattern must fit in shared memory for the fused residual", n_q);
   cudaError_t e = xrsd_launch_residual(layout, obj, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables,
-                                       d_Iobs, obj->has_dI ? d_dI : nullptr, (long long)ld_obs, d_chi2, scratch, rm,
+                                       d_Iobs, obj->has_dI ? d_dI : nullptr, (long long)ld_obs, d_chi2, scratch, rm, d_active,
                                        (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "residual_kernel");
   return XRSD_OK;
@@ -263,7 +266,8 @@ int64_t xrsd_jacobian_workspace_bytes(int32_t n_q, int32_t batch, int32_t n_free
 int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q, int32_t n_q,
                         const double *d_params, int32_t ld_params, int32_t batch, const xrsd_tables_t *tables,
                         const double *d_Iobs, const double *d_dI, int64_t ld_obs, const int32_t *free_idx, int32_t n_free,
-                        double rel_step, double *d_JTJ, double *d_JTr, double *d_chi2, void *d_workspace, void *stream) {
+                        double rel_step, double *d_JTJ, double *d_JTr, double *d_chi2, void *d_workspace,
+                        const uint8_t *d_active, void *stream) {
   int rc = check_layout(layout);
   if (rc) return rc;
   if (batch <= 0 || n_q <= 0) return XRSD_OK;
@@ -290,7 +294,7 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   unsigned *d_tickets = (unsigned *)((char *)d_workspace + fbytes + abytes);
   cudaError_t e = xrsd_launch_jacobian(layout, obj, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables, d_Iobs,
                                        obj->has_dI ? d_dI : nullptr, (long long)ld_obs, free_idx, n_free, rel_step, d_JTJ,
-                                       d_JTr, d_chi2, d_Fvar, d_acc, d_tickets, per, scratch, rm, (cudaStream_t)stream);
+                                       d_JTr, d_chi2, d_Fvar, d_acc, d_tickets, per, scratch, rm, d_active, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "jacobian_kernel");
   return XRSD_OK;
 }
@@ -422,7 +426,7 @@ int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int3
     T.cap_shell = cap_shell; T.cap_refl = 0; T.n_pairs_max = n_pairs;
     T.n_shell = (int32_t *)(base + o_ns); T.n_refl = (int32_t *)(base + o_nr); T.n_all = (int32_t *)(base + o_na);
     T.status = (int32_t *)(base + o_st); T.shell_hkl = (int32_t *)(base + o_sh); T.shell_geo = (double *)(base + o_sg);
-    rc = xrsd_reflection_tables(layout, (const double *)(base + o_p), ld_params, batch, &T, max_cells, s);
+    rc = xrsd_reflection_tables(layout, (const double *)(base + o_p), ld_params, batch, &T, max_cells, nullptr, s);
     if (rc) return rc;
     std::vector<int32_t> st(n_tab);
     e = cudaMemcpyAsync(st.data(), T.status, n_tab * 4, cudaMemcpyDeviceToHost, s);

@@ -75,11 +75,12 @@ __global__ void __launch_bounds__(EVAL_THREADS, HX ? 4 : 6)
 residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t O, const double *__restrict__ q, int n_q,
                 const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
                 const double *__restrict__ Iobs, const double *__restrict__ dI, long long ld_obs,
-                double *__restrict__ chi2, int scratch_doubles) {
+                double *__restrict__ chi2, int scratch_doubles, const uint8_t *__restrict__ active) {
   extern __shared__ __align__(16) double smem_d[];
   __shared__ EvalSharedT<HX> S;
   const int b = blockIdx.x;
   if (b >= batch) return;
+  if (active != nullptr && !active[b]) return;
   double *I_sm = smem_d;
   double *scratch = smem_d + ((n_q + 1) & ~1);
   accumulate_system<2, RM, HX>(L, params + (size_t)b * ldp, T, b, q, n_q, 0, n_q, I_sm, scratch, scratch_doubles, &S);
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, 6)
 jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ q, int n_q,
                          const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T, const FreeSet F,
                          double rel_step, double *__restrict__ Fvar, int q_per_cta, int n_tiles, int pattern_doubles,
-                         int scratch_doubles) {
+                         int scratch_doubles, const uint8_t *__restrict__ active) {
   extern __shared__ __align__(16) double smem_d[];
   __shared__ EvalSharedT<HX> S;
   const int tid = threadIdx.x;
@@ -133,6 +134,7 @@ jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *
   const int rem = (int)(bid - (long long)b * per_sys);
   const int v = rem / n_tiles, tile = rem - v * n_tiles;
   if (b >= batch) return;
+  if (active != nullptr && !active[b]) return;
   const int np = L.n_params;
   double *I_sm = smem_d;
   double *scratch = smem_d + pattern_doubles;
@@ -167,13 +169,14 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
                        const double *__restrict__ dI, long long ld_obs, const FreeSet F, double rel_step,
                        const double *__restrict__ Fvar, double *__restrict__ acc_g, unsigned *__restrict__ tickets,
                        double *__restrict__ JTJ, double *__restrict__ JTr, double *__restrict__ chi2, int chunk_q,
-                       int n_chunks) {
+                       int n_chunks, const uint8_t *__restrict__ active) {
   constexpr int NACC = NF * NF + NF + 2;          // full square (upper part used), JTr, chi2 numerator, sum w
   __shared__ double fold[JR_THREADS / 32][RB * NF + NF + 2];
   __shared__ int is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks;
   if (b >= batch) return;
+  if (active != nullptr && !active[b]) return;       // outputs of a converged system keep their last values
   const int nf = F.n_free, nv = F.n_var, n_slab = nv + n_pops;
   const double *prm = params + (size_t)b * ldp;
   const double *obs = Iobs + (size_t)b * ld_obs;
@@ -403,7 +406,7 @@ extern "C" cudaError_t xrsd_launch_residual(const xrsd_layout_t *layout, const x
                                             int n_q, const double *d_params, int ldp, int batch,
                                             const xrsd_tables_t *tables, const double *d_Iobs, const double *d_dI,
                                             long long ld_obs, double *d_chi2, int scratch_doubles, int radial_multi,
-                                            cudaStream_t stream) {
+                                            const uint8_t *d_active, cudaStream_t stream) {
   using namespace xrsd;
   const size_t smem = ((size_t)((n_q + 1) & ~1) + (size_t)scratch_doubles) * sizeof(double);
   auto kern = radial_multi ? residual_kernel<true, true>
@@ -412,7 +415,7 @@ extern "C" cudaError_t xrsd_launch_residual(const xrsd_layout_t *layout, const x
   if (e != cudaSuccess) return e;
   if (batch <= 0) return cudaSuccess;
   kern<<<batch, EVAL_THREADS, smem, stream>>>(*layout, *obj, d_q, n_q, d_params, ldp, batch, *tables, d_Iobs, d_dI, ld_obs,
-                                             d_chi2, scratch_doubles);
+                                             d_chi2, scratch_doubles, d_active);
   return cudaGetLastError();
 }
 
@@ -433,7 +436,7 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
                                             long long ld_obs, const int32_t *free_idx, int n_free, double rel_step,
                                             double *d_JTJ, double *d_JTr, double *d_chi2, double *d_Fvar, double *d_acc,
                                             unsigned *d_tickets, int q_per_cta, int scratch_doubles, int radial_multi,
-                                            cudaStream_t stream) {
+                                            const uint8_t *d_active, cudaStream_t stream) {
   using namespace xrsd;
   const FreeSet F = make_free_set(layout, free_idx, n_free);
   int pat = 0;
@@ -447,7 +450,7 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
   const long long n_blocks = (long long)batch * F.n_var * n_tiles;
   if (n_blocks > 2147483647LL) return cudaErrorInvalidConfiguration;
   kern<<<(unsigned)n_blocks, EVAL_THREADS, smem, stream>>>(*layout, d_q, n_q, d_params, ldp, batch, *tables, F, rel_step, d_Fvar,
-                                                          q_per_cta, n_tiles, pat, scratch_doubles);
+                                                          q_per_cta, n_tiles, pat, scratch_doubles, d_active);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int chunk_q = 1024;
@@ -456,11 +459,11 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
   if (n_free <= 8)
     jacobian_reduce_kernel<8, 8><<<batch * n_chunks, JR_THREADS, 0, stream>>>(
         layout->n_pops, *obj, d_q, n_q, d_params, ldp, batch, d_Iobs, d_dI, ld_obs, F, rel_step, d_Fvar, d_acc, d_tickets, d_JTJ,
-        d_JTr, d_chi2, chunk_q, n_chunks);
+        d_JTr, d_chi2, chunk_q, n_chunks, d_active);
   else
     jacobian_reduce_kernel<XRSD_MAX_FREE, 4><<<batch * n_chunks, JR_THREADS, 0, stream>>>(
         layout->n_pops, *obj, d_q, n_q, d_params, ldp, batch, d_Iobs, d_dI, ld_obs, F, rel_step, d_Fvar, d_acc, d_tickets, d_JTJ,
-        d_JTr, d_chi2, chunk_q, n_chunks);
+        d_JTr, d_chi2, chunk_q, n_chunks, d_active);
   return cudaGetLastError();
 }
 

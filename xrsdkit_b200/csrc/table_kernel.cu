@@ -73,7 +73,8 @@ __device__ __forceinline__ int block_flag_scan(TableShared &S, bool flag, int &b
 
 __global__ void __launch_bounds__(TABLE_THREADS, 3)
 reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ params, int ldp,
-                        int batch, const xrsd_tables_t T, int max_cells, int cap_list) {
+                        int batch, const xrsd_tables_t T, int max_cells, int cap_list,
+                        const uint8_t *__restrict__ active) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ TableShared S;
 
@@ -81,6 +82,7 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
   const int b = t / L.n_xtal;
   const int slot = t - b * L.n_xtal;
   if (b >= batch) return;
+  if (active != nullptr && !active[b]) return;      // converged system of a fit: its table is left as it is
   int ipop = -1;
   for (int i = 0; i < L.n_pops; ++i)
     if (L.pops[i].kind == XRSD_POP_CRYSTALLINE && L.pops[i].table_slot == slot) ipop = i;
@@ -485,13 +487,13 @@ extern "C" int64_t xrsd_table_smem_layout(int32_t max_cells, int32_t cap_list) {
 
 extern "C" cudaError_t xrsd_launch_tables(const xrsd_layout_t *layout, const double *d_params, int ldp, int batch,
                                           const xrsd_tables_t *tables, int max_cells, int cap_list,
-                                          cudaStream_t stream) {
+                                          const uint8_t *d_active, cudaStream_t stream) {
   const size_t smem = (size_t)xrsd_table_smem_layout(max_cells, cap_list);
   cudaError_t e = cudaFuncSetAttribute(xrsd::reflection_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int n_tables = batch * layout->n_xtal;
   if (n_tables <= 0) return cudaSuccess;
   xrsd::reflection_table_kernel<<<n_tables, xrsd::TABLE_THREADS, smem, stream>>>(*layout, d_params, ldp, batch, *tables,
-                                                                                 max_cells, cap_list);
+                                                                                 max_cells, cap_list, d_active);
   return cudaGetLastError();
 }

@@ -80,7 +80,7 @@ class Engine(object):
 
     # -- reflection tables --------------------------------------------------------------
     def build_tables(self, layout, d_params, batch, params_host=None, cap_shell=None, export_reflections=False,
-                     max_cells=None, check=True, reuse=None):
+                     max_cells=None, check=True, reuse=None, active=None):
         """Build the reflection tables of all crystalline populations for a batch.
 
         `params_host` (numpy [batch, n_params]) is only used to bound the candidate box when
@@ -108,7 +108,8 @@ class Engine(object):
             reuse = None
             T.c.cap_list_hint = cap_list
             abi.check(self.lib.xrsd_reflection_tables(C.byref(layout.c), d_params.data_ptr(), d_params.shape[1], batch,
-                                                      C.byref(T.c), max_cells, self._stream()))
+                                                      C.byref(T.c), max_cells,
+                                                      active.data_ptr() if active is not None else None, self._stream()))
             self.launches += 1
             if not check:
                 return T
@@ -150,12 +151,19 @@ class Engine(object):
         return out
 
     def intensity_single(self, layout, q):
-        """numpy in, numpy out: one system with the parameter values stored in its layout."""
-        q = np.asarray(q, dtype=np.float64)
+        """numpy in, numpy out: one system with the parameter values stored in its layout.  Goes through
+        the host-buffer C entry point (xrsd_intensity_batch_host): for a single pattern the cost is launch
+        and copy latency, and that path has the fewest host-side steps."""
+        q = np.ascontiguousarray(q, dtype=np.float64)
         if q.size == 0:
             return np.zeros(0)
-        I = self.intensity(layout, q, layout.values[None, :])
-        return I[0].cpu().numpy()
+        vals = np.ascontiguousarray(layout.values, dtype=np.float64)
+        out = np.empty(q.size)
+        self.torch.cuda.set_device(self.device)
+        abi.check(self.lib.xrsd_intensity_batch_host(C.byref(layout.c), q.ctypes.data, q.size, vals.ctypes.data, vals.size, 1,
+                                                     out.ctypes.data, q.size))
+        self.launches += 1 + (1 if layout.n_xtal else 0)
+        return out
 
     # -- objective ----------------------------------------------------------------------
     def objective(self, error_weighted=True, logI_weighted=True, q_range=(0., float('inf')), has_dI=False):
@@ -189,7 +197,7 @@ class Engine(object):
                 ld = d_I.stride(0)
         return d_I, d_dI, ld
 
-    def residual(self, layout, obj, q, params, Iobs, dI=None, tables=None):
+    def residual(self, layout, obj, q, params, Iobs, dI=None, tables=None, active=None, out=None):
         """chi2[b] of System.evaluate_residual for every parameter set of the batch."""
         torch = self.torch
         d_q = self.to_device(q)
@@ -202,15 +210,17 @@ class Engine(object):
         obj.has_dI = int(d_dI is not None)
         if layout.n_xtal and tables is None:
             tables = self.build_tables(layout, d_p, batch, params_host=host_params)
-        chi2 = torch.empty(batch, dtype=torch.float64, device=self.device)
+        chi2 = out if out is not None else torch.empty(batch, dtype=torch.float64, device=self.device)
         abi.check(self.lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_p.data_ptr(),
                                                d_p.shape[1], batch, C.byref(tables.c) if tables is not None else None,
                                                d_I.data_ptr(), d_dI.data_ptr() if d_dI is not None else None, ld,
-                                               chi2.data_ptr(), self._stream()))
+                                               chi2.data_ptr(), active.data_ptr() if active is not None else None,
+                                               self._stream()))
         self.launches += 1
         return chi2
 
-    def jacobian(self, layout, obj, q, d_params, Iobs_dev, dI_dev, ld_obs, free_slots, tables, rel_step=1e-6, out=None):
+    def jacobian(self, layout, obj, q, d_params, Iobs_dev, dI_dev, ld_obs, free_slots, tables, rel_step=1e-6, out=None,
+                 active=None):
         """Normal equations (JTJ, JTr, chi2) of the weighted residual vector by forward differences."""
         torch = self.torch
         batch, nf = d_params.shape[0], len(free_slots)
@@ -252,8 +262,8 @@ class Engine(object):
                 C.byref(tc) if tc is not None else None,
                 Iobs_dev.data_ptr() + 8 * lo * ld_obs, (dI_dev.data_ptr() + 8 * lo * ld_obs) if dI_dev is not None else None,
                 ld_obs, idx, nf, float(rel_step), out[0][lo:hi].data_ptr(), out[1][lo:hi].data_ptr(), out[2][lo:hi].data_ptr(),
-                ws.data_ptr(), self._stream()))
-            self.launches += 1
+                ws.data_ptr(), (active.data_ptr() + lo) if active is not None else None, self._stream()))
+            self.launches += 2
         return out
 
     def peak_profile(self, kind, x, p0, p1=0.0):

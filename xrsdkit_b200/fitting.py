@@ -86,7 +86,8 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     n_iter = 0
     for it in range(max_iter):
         n_iter = it + 1
-        _, _, d_chi2 = eng.jacobian(layout, obj, d_q, d_p, d_I, d_dI, ld_obs, free_slots, tables, rel_step, out=jout)
+        _, _, d_chi2 = eng.jacobian(layout, obj, d_q, d_p, d_I, d_dI, ld_obs, free_slots, tables, rel_step, out=jout,
+                                    active=d_active if it > 0 else None)
         if chi2_init is None:
             chi2_init = d_chi2.clone()
         abi.check(lib.xrsd_lm_propose(d_p.data_ptr(), d_p.shape[1], batch, idx, nf, jout[0].data_ptr(), jout[1].data_ptr(),
@@ -94,18 +95,18 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
                                       d_trial.data_ptr(), stream))
         # in-loop table builds do not read their status back (no host sync); it is checked every 5 iterations
         t_tables = eng.build_tables(layout, d_trial, batch, max_cells=max_cells, reuse=t_tables,
-                                    check=t_tables is None) if layout.n_xtal else None
+                                    check=t_tables is None, active=d_active if t_tables is not None else None) if layout.n_xtal else None
         abi.check(lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_trial.data_ptr(),
                                           d_trial.shape[1], batch, C.byref(t_tables.c) if t_tables is not None else None,
                                           d_I.data_ptr(), d_dI.data_ptr() if d_dI is not None else None, ld_obs,
-                                          d_chi2_t.data_ptr(), stream))
+                                          d_chi2_t.data_ptr(), d_active.data_ptr(), stream))
         abi.check(lib.xrsd_lm_update(d_p.data_ptr(), d_p.shape[1], batch, d_trial.data_ptr(), d_chi2.data_ptr(),
                                      d_chi2_t.data_ptr(), d_lambda.data_ptr(), d_active.data_ptr(), d_nacc.data_ptr(),
                                      float(up), float(down), float(ftol), float(lambda_max), stream))
         eng.launches += 3
         if layout.n_xtal:
             # accepted systems now sit at `trial`: their tables are the trial tables
-            tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=tables, check=False)
+            tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=tables, check=False, active=d_active)
         if it % 5 == 4:
             flags = torch.stack([d_active.any().to(torch.int32),
                                  tables.status.max() if tables is not None else torch.zeros((), dtype=torch.int32, device=eng.device),
@@ -119,7 +120,10 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
                 d_chi2.copy_(eng.residual(layout, obj, d_q, d_p, d_I, d_dI, tables=tables))
             if not any_active:
                 break
-    # final objective at the accepted parameters
+    # final objective at the accepted parameters (tables rebuilt for every system: converged ones were
+    # skipped by the masked in-loop builds after their last accepted step)
+    if layout.n_xtal:
+        tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=tables)
     chi2 = eng.residual(layout, obj, d_q, d_p, d_I, d_dI, tables=tables)
     res = FitResult(d_p, chi2_init, chi2, n_iter, d_nacc, d_active.bool())
     if return_device:
