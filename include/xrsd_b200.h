@@ -153,6 +153,15 @@ int xrsd_intensity_batch(const xrsd_layout_t *layout, const double *d_q, int32_t
                          const double *d_params, int32_t ld_params, int32_t batch,
                          const xrsd_tables_t *tables, double *d_I, int64_t ld_I, void *stream);
 
+/* Same launch, additionally writing the running totals d_cum[batch][layout.n_pops][n_q] after the
+ * noise model (index 0) and after each population: differences of consecutive rows are the
+ * per-population patterns.  <- the (2 + n_pop) separate evaluations of visualization/__init__.py:23-31
+ * (plot decomposition) and the I0 rescaling of models/predict.py:372-378, in one pass. */
+int xrsd_intensity_components_batch(const xrsd_layout_t *layout, const double *d_q, int32_t n_q,
+                                    const double *d_params, int32_t ld_params, int32_t batch,
+                                    const xrsd_tables_t *tables, double *d_I, int64_t ld_I, double *d_cum,
+                                    void *stream);
+
 /* chi2[b] of System.evaluate_residual for b < batch; d_Iobs / d_dI are [batch][ld_obs]
  * (ld_obs == 0 broadcasts one pattern to the whole batch).  I(q) is computed in the same
  * kernel and never written to memory. */

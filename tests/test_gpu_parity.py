@@ -334,3 +334,25 @@ def test_far_field_interpolation_over_extreme_widths(ref_tables, eng):
         ref_u = orc.system_intensity(q_shuffled, s.to_dict(), **ref_tables)
         err_u, same_u = rel_err(got_u, ref_u, floor_frac=0.0)
         assert same_u and err_u <= TOL_F64, (trial, prof, pars, err_u)
+
+
+def test_components_in_one_launch(golden_systems, eng):
+    """Per-population decomposition (noise, each population, total) from one launch against the reference's
+    separate per-population evaluations."""
+    from xrsdkit_b200.system import System
+    meta, arr = golden_systems
+    for m in meta[:54:3] + meta[60::25]:
+        q = arr[m["q"]]
+        s = System(**m["system"])
+        n0 = eng.launches
+        parts = s.compute_intensity_components(q)
+        assert eng.launches - n0 <= 2
+        err, same = rel_err(parts["total"], arr[m["key"] + "_I"])
+        assert same and err <= TOL_F64, m["name"]
+        scale = np.nanmax(np.abs(arr[m["key"] + "_I"]))
+        np.testing.assert_allclose(parts["noise"], arr[m["key"] + "_noise"], rtol=1e-10, atol=1e-13 * scale)
+        for pn in s.populations:
+            ref = arr[m["key"] + "_pop_" + pn]
+            fin = np.isfinite(ref)
+            # a difference of running totals: absolute accuracy is that of the total
+            np.testing.assert_allclose(parts[pn][fin], ref[fin], rtol=1e-10, atol=1e-12 * scale, err_msg=m["name"] + ":" + pn)

@@ -14,7 +14,7 @@ int64_t xrsd_table_smem_layout(int32_t max_cells, int32_t cap_list);
 cudaError_t xrsd_launch_tables(const xrsd_layout_t *, const double *, int, int, const xrsd_tables_t *, int, int, const uint8_t *,
                                cudaStream_t);
 cudaError_t xrsd_launch_intensity(const xrsd_layout_t *, const double *, int, const double *, int, int, const xrsd_tables_t *,
-                                  double *, long long, int, int, int, cudaStream_t);
+                                  double *, long long, int, int, int, double *, cudaStream_t);
 cudaError_t xrsd_launch_fp64_probe(double *, int, int, cudaStream_t);
 cudaError_t xrsd_launch_profile(int, double, double, const double *, int, double *, cudaStream_t);
 cudaError_t xrsd_launch_residual(const xrsd_layout_t *, const xrsd_objective_t *, const double *, int, const double *, int, int,
@@ -209,9 +209,9 @@ static int pick_q_per_cta(int n_q, int batch, int scratch, bool has_xtal) {
   return (int)std::max(512LL, per);
 }
 
-int xrsd_intensity_batch(const xrsd_layout_t *layout, const double *d_q, int32_t n_q, const double *d_params,
-                         int32_t ld_params, int32_t batch, const xrsd_tables_t *tables, double *d_I, int64_t ld_I,
-                         void *stream) {
+static int intensity_impl(const xrsd_layout_t *layout, const double *d_q, int32_t n_q, const double *d_params,
+                          int32_t ld_params, int32_t batch, const xrsd_tables_t *tables, double *d_I, int64_t ld_I,
+                          double *d_cum, void *stream) {
   int rc = check_layout(layout);
   if (rc) return rc;
   if (batch <= 0 || n_q <= 0) return XRSD_OK;
@@ -225,9 +225,22 @@ int xrsd_intensity_batch(const xrsd_layout_t *layout, const double *d_q, int32_t
   if (scratch < 0) return fail(XRSD_ECAPACITY, "size quadrature too fine for shared memory (sampling_width/sampling_step)");
   const int per = pick_q_per_cta(n_q, batch, scratch, layout->n_xtal > 0);
   cudaError_t e = xrsd_launch_intensity(layout, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables, d_I,
-                                        (long long)ld_I, per, scratch, rm, (cudaStream_t)stream);
+                                        (long long)ld_I, per, scratch, rm, d_cum, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "intensity_kernel");
   return XRSD_OK;
+}
+
+int xrsd_intensity_batch(const xrsd_layout_t *layout, const double *d_q, int32_t n_q, const double *d_params,
+                         int32_t ld_params, int32_t batch, const xrsd_tables_t *tables, double *d_I, int64_t ld_I,
+                         void *stream) {
+  return intensity_impl(layout, d_q, n_q, d_params, ld_params, batch, tables, d_I, ld_I, nullptr, stream);
+}
+
+int xrsd_intensity_components_batch(const xrsd_layout_t *layout, const double *d_q, int32_t n_q, const double *d_params,
+                                    int32_t ld_params, int32_t batch, const xrsd_tables_t *tables, double *d_I,
+                                    int64_t ld_I, double *d_cum, void *stream) {
+  if (!d_cum) return fail(XRSD_EINVAL, "d_cum is NULL");
+  return intensity_impl(layout, d_q, n_q, d_params, ld_params, batch, tables, d_I, ld_I, d_cum, stream);
 }
 
 int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q, int32_t n_q,

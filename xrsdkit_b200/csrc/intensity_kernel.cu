@@ -10,7 +10,8 @@ template <int QPT, bool RM, bool HX>
 __global__ void __launch_bounds__(EVAL_THREADS, HX ? 6 : 6)
 intensity_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ q, int n_q,
                  const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
-                 double *__restrict__ I_out, long long ldI, int q_per_cta, int n_tiles, int scratch_doubles) {
+                 double *__restrict__ I_out, long long ldI, int q_per_cta, int n_tiles, int scratch_doubles,
+                 double *__restrict__ cum_out) {
   extern __shared__ __align__(16) double smem_d[];
   __shared__ EvalSharedT<HX> S;
   const long long bid = blockIdx.x;
@@ -21,7 +22,10 @@ intensity_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restri
   const int q_count = min(q_per_cta, n_q - q_begin);
   double *I_sm = smem_d;
   double *scratch = smem_d + ((q_per_cta + 1) & ~1);
-  accumulate_system<QPT, RM, HX>(L, params + (size_t)b * ldp, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S);
+  // cum_out (optional): [batch][n_pops][n_q] running totals after the noise model and after each
+  // population -- their differences are the per-population patterns (plot decomposition, I0 rescaling)
+  accumulate_system<QPT, RM, HX>(L, params + (size_t)b * ldp, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S,
+                                 nullptr, cum_out ? cum_out + (size_t)b * L.n_pops * n_q + q_begin : nullptr, n_q);
   double *dst = I_out + (size_t)b * ldI + q_begin;
   for (int i = threadIdx.x; i < q_count; i += EVAL_THREADS) dst[i] = I_sm[i];
 }
@@ -62,7 +66,8 @@ extern "C" cudaError_t xrsd_launch_profile(int kind, double p0, double p1, const
 
 extern "C" cudaError_t xrsd_launch_intensity(const xrsd_layout_t *layout, const double *d_q, int n_q, const double *d_params,
                                              int ldp, int batch, const xrsd_tables_t *tables, double *d_I, long long ldI,
-                                             int q_per_cta, int scratch_doubles, int radial_multi, cudaStream_t stream) {
+                                             int q_per_cta, int scratch_doubles, int radial_multi, double *d_cum,
+                                             cudaStream_t stream) {
   using namespace xrsd;
   const int n_tiles = (n_q + q_per_cta - 1) / q_per_cta;
   const size_t smem = ((size_t)((q_per_cta + 1) & ~1) + (size_t)scratch_doubles) * sizeof(double);
@@ -74,7 +79,7 @@ extern "C" cudaError_t xrsd_launch_intensity(const xrsd_layout_t *layout, const 
   if (n_blocks <= 0) return cudaSuccess;
   if (n_blocks > 2147483647LL) return cudaErrorInvalidConfiguration;
   kern<<<(unsigned)n_blocks, EVAL_THREADS, smem, stream>>>(*layout, d_q, n_q, d_params, ldp, batch, *tables, d_I, ldI,
-                                                          q_per_cta, n_tiles, scratch_doubles);
+                                                          q_per_cta, n_tiles, scratch_doubles, d_cum);
   return cudaGetLastError();
 }
 

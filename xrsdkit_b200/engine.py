@@ -150,6 +150,28 @@ class Engine(object):
         self.launches += 1
         return out
 
+    def intensity_components(self, layout, q, params, tables=None):
+        """(I[b, :], parts[b, n_pops, :]) where parts[:, 0] is the noise term and parts[:, k] population k
+        (layout order), all from one launch."""
+        torch = self.torch
+        d_q = self.to_device(q)
+        host_params = None if isinstance(params, torch.Tensor) else np.atleast_2d(np.asarray(params, dtype=np.float64))
+        d_p = self.to_device(params if host_params is None else host_params)
+        if d_p.dim() == 1:
+            d_p = d_p.unsqueeze(0)
+        batch, n_q, n_pops = d_p.shape[0], d_q.shape[0], layout.c.n_pops
+        out = torch.empty((batch, n_q), dtype=torch.float64, device=self.device)
+        cum = torch.empty((batch, n_pops, n_q), dtype=torch.float64, device=self.device)
+        if layout.n_xtal and tables is None:
+            tables = self.build_tables(layout, d_p, batch, params_host=host_params)
+        abi.check(self.lib.xrsd_intensity_components_batch(
+            C.byref(layout.c), d_q.data_ptr(), n_q, d_p.data_ptr(), d_p.shape[1], batch,
+            C.byref(tables.c) if tables is not None else None, out.data_ptr(), out.shape[1], cum.data_ptr(), self._stream()))
+        self.launches += 1
+        parts = cum.clone()
+        parts[:, 1:] -= cum[:, :-1]
+        return out, parts
+
     def intensity_single(self, layout, q):
         """numpy in, numpy out: one system with the parameter values stored in its layout.  Goes through
         the host-buffer C entry point (xrsd_intensity_batch_host): for a single pattern the cost is launch

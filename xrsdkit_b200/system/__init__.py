@@ -110,6 +110,18 @@ class System(object):
         q = np.asarray(q, dtype=float)
         return engine.get_engine().intensity_single(lowering.lower_system(self, q), q)
 
+    def compute_intensity_components(self, q):
+        """{'total': I, 'noise': ..., <population name>: ...} from ONE launch -- what the reference's
+        plotting helper computes with 2 + n_populations separate evaluations (visualization/__init__.py:23-31)."""
+        from .. import engine, lowering
+        q = np.asarray(q, dtype=float)
+        lay = lowering.lower_system(self, q)
+        total, parts = engine.get_engine().intensity_components(lay, q, lay.values[None, :])
+        out = {'total': total[0].cpu().numpy(), 'noise': parts[0, 0].cpu().numpy()}
+        for k, name in enumerate(self.populations.keys()):
+            out[name] = parts[0, k + 1].cpu().numpy()
+        return out
+
     def evaluate_residual(self, q, I, dI=None, I_comp=None):
         """Scalar weighted chi^2 between the model and (q, I) (reference :134-187)."""
         from .. import engine, lowering
