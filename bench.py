@@ -469,7 +469,7 @@ def run_gpu_arm(args):
     cores = host_cores()
     per_core = {"cfg2": 256, "cfg3": 4, "cfg4": 4, "cfg5": 4}[args.workload]     # ~10-30 core-seconds per core in total
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:      # the CPU sample is taken at N=1 only
         arm = CpuArm(args.workload, cores)
         n1, dt1 = arm.step(per_core)
         n2, dt2 = arm.step(per_core, cores * per_core)

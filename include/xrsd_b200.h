@@ -103,6 +103,9 @@ typedef struct xrsd_layout {
   int32_t n_xtal;              /* number of crystalline populations (= table slots) */
   int32_t q0_is_zero;          /* q[0] == 0: the only zero the reference special-cases */
   double wavelength;
+  double q_step;               /* > 0: q[i] == q[0] + i*q_step to within a few ulp (a linspace grid), which lets the
+                                  size-quadrature loop advance its starting phases by a rotation from one 256-point
+                                  span to the next instead of calling sincos; 0: no assumption about q */
   xrsd_pop_t pops[XRSD_MAX_POPS];
 } xrsd_layout_t;
 

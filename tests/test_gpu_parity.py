@@ -191,8 +191,8 @@ def test_cfg3_cfg4_batch_vs_oracle(ref_tables, eng):
 
 
 def test_batch_properties_full_size(eng):
-    """Size-independent properties at BASELINE sizes: batched == one-by-one (bit-exact), idempotence,
-    row-permutation equivariance, linearity in I0."""
+    """Size-independent properties at BASELINE sizes: batched == one-by-one, idempotence (bit-exact),
+    row-permutation equivariance (bit-exact), linearity in I0."""
     from xrsdkit_b200.system import System
     from xrsdkit_b200 import batch
     s = cfg2_system(System)
@@ -206,9 +206,11 @@ def test_batch_properties_full_size(eng):
     perm = np.random.RandomState(0).permutation(10000)
     Ip = batch.compute_intensity_batch(lay, q, P[perm], device_out=True)
     assert bool((Ip == I[eng.torch.as_tensor(perm, device=I.device)]).all())
-    for b in (0, 777, 9999):                                         # single-system launches use other q spans
+    for b in (0, 777, 9999):
+        # a single-system launch uses shorter q spans, so its size-quadrature phases are not carried from span
+        # to span by rotation: equal to rounding, not bit for bit
         one = batch.compute_intensity_batch(lay, q, P[b:b + 1])
-        np.testing.assert_array_equal(one[0], I[b].cpu().numpy())
+        np.testing.assert_allclose(one[0], I[b].cpu().numpy(), rtol=1e-12, atol=0)
     # linearity: doubling the population I0 doubles (I - noise)
     P2 = P[:256].copy()
     P2[:, lay.slot("p__I0")] *= 2

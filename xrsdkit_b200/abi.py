@@ -39,7 +39,7 @@ class Pop(C.Structure):
 
 class Layout(C.Structure):
     _fields_ = [("n_pops", i32), ("n_params", i32), ("n_xtal", i32), ("q0_is_zero", i32),
-                ("wavelength", f64), ("pops", Pop * MAX_POPS)]
+                ("wavelength", f64), ("q_step", f64), ("pops", Pop * MAX_POPS)]
 
 
 class Tables(C.Structure):

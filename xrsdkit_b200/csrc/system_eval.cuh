@@ -213,6 +213,16 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
           }
         }
         __syncthreads();
+        // On a uniform q grid consecutive spans of one thread differ by span*q_step, so the starting
+        // phases (q r_first, q dstep) of the next span follow from the previous ones by a fixed rotation
+        double s0[QPT], c0[QPT], sd0[QPT], cd0[QPT];
+        double rot_s = 0.0, rot_c = 1.0, rotd_s = 0.0, rotd_c = 1.0;
+        const bool carry = quad && (L.q_step > 0.0);
+        if (carry) {
+          const double dq = (double)span * L.q_step;
+          sincos(dq * r_first, &rot_s, &rot_c);
+          sincos(dq * dstep, &rotd_s, &rotd_c);
+        }
         for (int off = 0; off < q_count; off += span) {
           double qv[QPT], ff2[QPT], den[QPT];
           bool ok[QPT], q0[QPT];
@@ -240,8 +250,18 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
             double qmin_t = qv[0];
 #pragma unroll
             for (int j = 0; j < QPT; ++j) {
-              sincos(qv[j] * r_first, &s[j], &c[j]);
-              sincos(qv[j] * dstep, &sd[j], &cd[j]);
+              if (carry && off > 0) {
+                const double sn = fma(s0[j], rot_c, c0[j] * rot_s);
+                c0[j] = fma(c0[j], rot_c, -(s0[j] * rot_s));
+                s0[j] = sn;
+                const double sdn = fma(sd0[j], rotd_c, cd0[j] * rotd_s);
+                cd0[j] = fma(cd0[j], rotd_c, -(sd0[j] * rotd_s));
+                sd0[j] = sdn;
+              } else {
+                sincos(qv[j] * r_first, &s0[j], &c0[j]);
+                sincos(qv[j] * dstep, &sd0[j], &cd0[j]);
+              }
+              s[j] = s0[j]; c[j] = c0[j]; sd[j] = sd0[j]; cd[j] = cd0[j];
               acc[j] = 0.0;
               qmin_t = fmin(qmin_t, qv[j]);
             }

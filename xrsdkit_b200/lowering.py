@@ -200,6 +200,20 @@ def _lower_population(structure, form, settings, slots, q_last, table_slot):
     return p
 
 
+def uniform_step(q):
+    """Step of q if it is a linspace-like grid (every point within 4 ulp of q[0] + i*step), else 0."""
+    n = len(q)
+    if n < 3:
+        return 0.0
+    step = (q[-1] - q[0]) / (n - 1)
+    if not (step > 0):
+        return 0.0
+    tol = 4 * np.finfo(float).eps * max(abs(q[0]), abs(q[-1]))
+    if np.max(np.abs(q - (q[0] + np.arange(n) * step))) <= tol:
+        return float(step)
+    return 0.0
+
+
 def lower_system(system, q):
     """System -> SystemLayout for the grid `q` (q is needed only for q[0]==0 and the q_max fallback)."""
     q = np.asarray(q, dtype=float)
@@ -231,6 +245,7 @@ def lower_system(system, q):
     L.n_params = max(1, len(names))
     L.n_xtal = n_x
     L.q0_is_zero = 1 if (len(q) and q[0] == 0) else 0
+    L.q_step = uniform_step(q)
     wl = system.sample_metadata['source_wavelength']
     if n_x and not wl:
         raise ValueError('cannot compute diffraction with source wavelength of {}'.format(wl))
