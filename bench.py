@@ -35,9 +35,11 @@ WL = 0.8265617
 
 # Algorithmic FP64 work per unit, as stated in DESIGN.md section 4 (FMA = 2, mul/add = 1, div = 10,
 # sincos pair = 40, exp = 30, Re w = the series actually needed):
-#   cfg2: per (set, q): n_r * 13 (rotation 4 ops = 6 flop, x 1, t 2, t^2 1, acc 2 ... = 13) + 250
+#   cfg2: per (set, q): n_r * 13 (rotation 4 ops = 6 flop, x 1, t 2, t^2 1, acc 2 ... = 13) + 185
+#         (hard-sphere sincos 40 + brackets 60 + two divisions 20 + epilogue 15 + the starting phases of
+#          the quadrature: two rotations 24 on a uniform q grid, with a sincos pair only in the first span)
 FLOPS_PER_PAIR_RNORMAL = 13.0
-FLOPS_PER_Q_OVERHEAD_CFG2 = 250.0
+FLOPS_PER_Q_OVERHEAD_CFG2 = 185.0
 SURVEY_FLOPS_PER_SETQ_CFG2 = 2630.0          # SURVEY.md 8d convention (sincos per (q,r) pair)
 
 
