@@ -400,8 +400,11 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
           }
           double pz = 1.0;
           if (pop.polz) {
-            const double th = asin(wl * qi / (4.0 * M_PI));
-            const double c2 = cos(2.0 * th);
+            // 0.5 (1 + cos^2(2 theta)), theta = asin(lambda q / 4 pi)  (scattering/__init__.py:234-238):
+            // cos(2 theta) = 1 - 2 sin^2(theta), so no transcendental is needed; |sin| > 1 gives the
+            // reference's NaN
+            const double st = wl * qi / (4.0 * M_PI);
+            const double c2 = (fabs(st) <= 1.0) ? fma(-2.0 * st, st, 1.0) : NAN;
             pz = 0.5 * (1.0 + c2 * c2);
           }
           I_sm[i] += I0 * (pz * a_sum / norm);                     // I0 * (pz*I/I0_norm)
@@ -562,8 +565,8 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
             }
             double pz = 1.0;
             if (pop.polz) {
-              const double th = asin(wl * qv[j] / (4.0 * M_PI));
-              const double c2 = cos(2.0 * th);
+              const double st = wl * qv[j] / (4.0 * M_PI);          // see finish_q
+              const double c2 = (fabs(st) <= 1.0) ? fma(-2.0 * st, st, 1.0) : NAN;
               pz = 0.5 * (1.0 + c2 * c2);
             }
             I_sm[i] += I0 * (pz * a_sum / norm);                   // I0 * (pz*I/I0_norm)
