@@ -158,3 +158,29 @@ def test_lm_recovers_crystal_systems_and_fit_api(eng):
     assert out.populations["p"].parameters["r"]["value"] == pytest.approx(20.0, rel=2e-3)
     rep = out.fit_report
     assert rep["final_objective"] < rep["initial_objective"] and "fit_snr" in rep and "converged" in rep
+
+
+def test_observation_shapes_for_batched_residual(eng):
+    """I_obs / dI as one shared pattern, one row per system, scalar dI; wrong shapes raise."""
+    from oracle import xrsd_oracle as orc
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg2_system(System)
+    q = np.linspace(0.02, 0.5, 300)
+    lay = batch.layout_of(s, q)
+    P = cfg2_params(lay, 5, seed=9)
+    I = batch.compute_intensity_batch(lay, q, P)
+    Iobs = I * (1 + 0.05 * np.random.RandomState(1).randn(*I.shape))
+    dI = 0.1 * Iobs + 0.01
+    want = np.array([orc.residual(q, Iobs[b], I[b], dI[b]) for b in range(5)])
+    np.testing.assert_allclose(batch.evaluate_residual_batch(lay, q, Iobs, P, dI=dI), want, rtol=1e-9)
+    want1 = np.array([orc.residual(q, Iobs[0], I[b], dI[0]) for b in range(5)])
+    np.testing.assert_allclose(batch.evaluate_residual_batch(lay, q, Iobs[0], P, dI=dI[0]), want1, rtol=1e-9)
+    np.testing.assert_allclose(batch.evaluate_residual_batch(lay, q, Iobs[0], P, dI=dI), 
+                               np.array([orc.residual(q, Iobs[0], I[b], dI[b]) for b in range(5)]), rtol=1e-9)
+    want_s = np.array([orc.residual(q, Iobs[b], I[b], np.full(q.shape, 0.7)) for b in range(5)])
+    np.testing.assert_allclose(batch.evaluate_residual_batch(lay, q, Iobs, P, dI=0.7), want_s, rtol=1e-9)
+    with pytest.raises(ValueError):
+        batch.evaluate_residual_batch(lay, q, Iobs[:3], P)
+    with pytest.raises(ValueError):
+        batch.evaluate_residual_batch(lay, q, Iobs[:, :-1], P)

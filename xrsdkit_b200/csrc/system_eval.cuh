@@ -49,8 +49,6 @@ struct EvalCore {
   VoigtConst vc;
   Cell cell;
   double red[EVAL_THREADS / 32];
-  double bcast[4];
-  int ibcast[4];
 };
 template <bool HAS_XTAL>
 struct EvalSharedT : EvalCore, std::conditional<HAS_XTAL, ChebShared, NoCheb>::type {};

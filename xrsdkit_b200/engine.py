@@ -195,29 +195,27 @@ class Engine(object):
         return o
 
     def _obs(self, Iobs, dI, batch, n_q):
+        """Device copies of the observed pattern(s) and their error estimates plus the row stride the
+        kernels use: 0 when ONE pattern [n_q] is shared by the whole batch, n_q for one row per system.
+        I_obs and dI always end up with the same shape."""
         d_I = self.to_device(Iobs)
-        ld = 0
-        if d_I.dim() == 2:
-            ld = d_I.stride(0) if d_I.shape[0] > 1 else 0
-            assert d_I.shape[0] in (1, batch) and d_I.shape[1] == n_q
-        else:
-            assert d_I.shape[0] == n_q
-        d_dI = None
-        if dI is not None:
-            d_dI = self.to_device(dI)
-            if np.ndim(dI) == 0:
-                d_dI = d_dI.reshape(1).expand(n_q).contiguous()
-            if d_dI.dim() != d_I.dim():
-                if d_dI.dim() == 1:
-                    d_dI = d_dI.unsqueeze(0).expand_as(d_I).contiguous() if d_I.dim() == 2 else d_dI
-                else:
-                    d_I = d_I.unsqueeze(0).expand_as(d_dI).contiguous()
-                    ld = d_I.stride(0)
-            if d_dI.dim() == 2 and d_I.dim() == 2 and d_dI.shape[0] != d_I.shape[0]:
-                d_I = d_I.expand(batch, n_q).contiguous()
-                d_dI = d_dI.expand(batch, n_q).contiguous()
-                ld = d_I.stride(0)
-        return d_I, d_dI, ld
+        d_dI = None if dI is None else self.to_device(np.broadcast_to(np.asarray(dI, dtype=np.float64), (n_q,))
+                                                      if np.ndim(dI) == 0 else dI)
+        for name, t in (("I", d_I), ("dI", d_dI)):
+            if t is not None and (t.shape[-1] != n_q or t.dim() > 2 or (t.dim() == 2 and t.shape[0] not in (1, batch))):
+                raise ValueError("%s has shape %s, expected [n_q] or [batch, n_q] with n_q=%d, batch=%d"
+                                 % (name, tuple(t.shape), n_q, batch))
+        per_system = any(t is not None and t.dim() == 2 and t.shape[0] > 1 for t in (d_I, d_dI))
+        shape = (batch, n_q) if per_system else (n_q,)
+
+        def fit_shape(t):
+            if t is None:
+                return None
+            return t.reshape(-1, n_q).expand(batch, n_q).contiguous() if per_system else t.reshape(n_q).contiguous()
+
+        d_I, d_dI = fit_shape(d_I), fit_shape(d_dI)
+        assert tuple(d_I.shape) == shape
+        return d_I, d_dI, (n_q if per_system else 0)
 
     def residual(self, layout, obj, q, params, Iobs, dI=None, tables=None, active=None, out=None):
         """chi2[b] of System.evaluate_residual for every parameter set of the batch."""
