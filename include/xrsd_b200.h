@@ -44,6 +44,7 @@ extern "C" {
 #define XRSD_MAX_OPS 9       /* symmetry operations per point group (m-3m has 9)       */
 #define XRSD_MAX_PARAMS 64   /* flat parameter slots per system                        */
 #define XRSD_MAX_FREE 16     /* free (fitted) parameters per system                    */
+#define XRSD_MAX_TIES 8      /* equality constraints between parameters per system     */
 
 /* xrsd_pop_t.kind */
 enum { XRSD_POP_NONE = 0, XRSD_POP_NOISE_FLAT = 1, XRSD_POP_NOISE_LOW_Q = 2,
@@ -181,21 +182,23 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
  * linear and needs no variant) and a chunked reduction.  d_workspace holds
  * xrsd_jacobian_workspace_bytes() bytes; the accumulator / ticket area behind the variant slabs
  * must be zero before the FIRST call with a given (n_q, batch, n_free) (the reduction re-zeroes
- * it; zeroing the whole workspace once is the simple way).  Reflection tables
+ * it; zeroing the whole workspace once is the simple way).  ties[n_tie][2] (HOST, may be NULL) are
+ * equality constraints (dst slot, src slot): the form of constraint_expr found in xrsdkit's own
+ * fitted systems ("particle__r"); the tied slot follows its source in every variant.  Reflection tables
  * and the radius counts of size quadratures are held fixed inside one evaluation. */
 int64_t xrsd_jacobian_workspace_bytes(int32_t n_q, int32_t batch, int32_t n_free);
 int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj,
                         const double *d_q, int32_t n_q, const double *d_params, int32_t ld_params,
                         int32_t batch, const xrsd_tables_t *tables,
                         const double *d_Iobs, const double *d_dI, int64_t ld_obs,
-                        const int32_t *free_idx, int32_t n_free, double rel_step,
-                        double *d_JTJ, double *d_JTr, double *d_chi2, void *d_workspace,
+                        const int32_t *free_idx, int32_t n_free, const int32_t *ties, int32_t n_tie,
+                        double rel_step, double *d_JTJ, double *d_JTr, double *d_chi2, void *d_workspace,
                         const uint8_t *d_active, void *stream);
 
 /* One damped Gauss-Newton (Levenberg-Marquardt) proposal per system:
  * solve (JTJ + lambda*diag(JTJ)) delta = -JTr, project onto [lo, hi], write trial params. */
 int xrsd_lm_propose(const double *d_params, int32_t ld_params, int32_t batch,
-                    const int32_t *free_idx, int32_t n_free,
+                    const int32_t *free_idx, int32_t n_free, const int32_t *ties, int32_t n_tie,
                     const double *d_JTJ, const double *d_JTr, const double *d_lambda,
                     const double *d_lo, const double *d_hi, const uint8_t *d_active,
                     double *d_trial, void *stream);

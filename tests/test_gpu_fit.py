@@ -184,3 +184,35 @@ def test_observation_shapes_for_batched_residual(eng):
         batch.evaluate_residual_batch(lay, q, Iobs[:3], P)
     with pytest.raises(ValueError):
         batch.evaluate_residual_batch(lay, q, Iobs[:, :-1], P)
+
+
+def test_fit_with_equality_constraint(eng):
+    """constraint_expr naming another parameter (the form in xrsdkit's fitted superlattice systems:
+    superlattice r tied to particle__r): the tied value follows its source through the fit."""
+    from xrsdkit_b200.system import System, fit
+    q = np.linspace(0.02, 0.45, 900)
+
+    def make(r, a, tie=True):
+        sl = {"a": {"value": a}, "r": {"value": r if not tie else 1.0, "constraint_expr": "particle__r" if tie else None},
+              "hwhm_g": {"value": 0.003, "fixed": True}, "hwhm_l": {"value": 0.003, "fixed": True}, "I0": {"value": 0.5}}
+        return System(particle=dict(structure="diffuse", form="spherical", settings={"distribution": "r_normal"},
+                                    parameters={"r": {"value": r}, "sigma": {"value": 0.08, "fixed": True}, "I0": {"value": 800.0}}),
+                      superlattice=dict(structure="crystalline", form="spherical",
+                                        settings={"lattice": "F_cubic", "space_group": "Fm-3m", "q_max": 0.45},
+                                        parameters=sl),
+                      noise={"model": "flat", "parameters": {"I0": {"value": 0.3}}}, source_wavelength=0.8265617)
+
+    truth = make(33.0, 110.0, tie=False)
+    I = truth.compute_intensity(q) * (1 + 0.01 * np.random.RandomState(8).randn(q.size))
+    start = make(34.5, 112.0)
+    out = fit(start, q, I)
+    rp = out.populations["particle"].parameters["r"]["value"]
+    rs = out.populations["superlattice"].parameters["r"]["value"]
+    assert rs == rp                                                    # the tie holds exactly
+    assert rp == pytest.approx(33.0, rel=5e-3)
+    assert out.populations["superlattice"].parameters["a"]["value"] == pytest.approx(110.0, rel=2e-3)
+    assert out.fit_report["final_objective"] < 0.05 * out.fit_report["initial_objective"]
+    # anything that is not a plain parameter name needs lmfit's asteval: rejected, not silently ignored
+    start.populations["superlattice"].parameters["r"]["constraint_expr"] = "particle__r * 2"
+    with pytest.raises(NotImplementedError):
+        fit(start, q, I)

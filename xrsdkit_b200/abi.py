@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libxrsd_b200.so")
 
-MAX_POPS, MAX_SPECIES, MAX_PAIRS, MAX_OPS, MAX_PARAMS, MAX_FREE = 6, 4, 10, 9, 64, 16
+MAX_POPS, MAX_SPECIES, MAX_PAIRS, MAX_OPS, MAX_PARAMS, MAX_FREE, MAX_TIES = 6, 4, 10, 9, 64, 16, 8
 
 POP_NONE, POP_NOISE_FLAT, POP_NOISE_LOW_Q, POP_NONCRYSTALLINE, POP_CRYSTALLINE = range(5)
 FORM_ATOMIC, FORM_SPHERE, FORM_SPHERE_R_NORMAL, FORM_GUINIER_POROD = range(4)
@@ -67,8 +67,9 @@ _SIGNATURES = {
                                       C.POINTER(Tables), vp, vp, C.c_int64, vp, vp, vp]),
     "xrsd_jacobian_workspace_bytes": (C.c_int64, [i32, i32, i32]),
     "xrsd_jacobian_batch": (C.c_int, [C.POINTER(Layout), C.POINTER(Objective), vp, i32, vp, i32, i32,
-                                      C.POINTER(Tables), vp, vp, C.c_int64, C.POINTER(i32), i32, f64, vp, vp, vp, vp, vp, vp]),
-    "xrsd_lm_propose": (C.c_int, [vp, i32, i32, C.POINTER(i32), i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+                                      C.POINTER(Tables), vp, vp, C.c_int64, C.POINTER(i32), i32, C.POINTER(i32), i32, f64,
+                                      vp, vp, vp, vp, vp, vp]),
+    "xrsd_lm_propose": (C.c_int, [vp, i32, i32, C.POINTER(i32), i32, C.POINTER(i32), i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "xrsd_lm_update": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, vp, f64, f64, f64, f64, vp]),
     "xrsd_intensity_batch_host": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, vp, C.c_int64]),
     "xrsd_release_workspace": (None, []),

@@ -23,16 +23,21 @@ struct FreeSet {
   int var_of[XRSD_MAX_FREE];    // variant index (>= 1) of a non-linear parameter, 0 for a linear one
   int pop_of[XRSD_MAX_FREE];    // linear parameter (an I0): index of its population, else -1
   int free_of_var[XRSD_MAX_FREE + 1];   // inverse of var_of
+  int n_tie;                    // equality constraints "dst = src" (constraint_expr naming one parameter)
+  int tie_dst[XRSD_MAX_TIES], tie_src[XRSD_MAX_TIES];
 };
 
 // An I0 multiplies its whole population (scattering/__init__.py:48,64,66; system/noise.py:56-62), so
 // dI/dI0 = I_pop / I0 needs no extra evaluation: the base variant records the running total after
 // each population and the reducer forms f(I + h I_pop / I0) from it.
-static FreeSet make_free_set(const xrsd_layout_t *L, const int32_t *free_idx, int n_free) {
+static FreeSet make_free_set(const xrsd_layout_t *L, const int32_t *free_idx, int n_free, const int32_t *ties = nullptr,
+                             int n_tie = 0) {
   FreeSet F;
   memset(&F, 0, sizeof(F));
   F.n_free = n_free;
   F.n_var = 1;
+  F.n_tie = (ties && n_tie > 0) ? std::min(n_tie, (int)XRSD_MAX_TIES) : 0;
+  for (int t = 0; t < F.n_tie; ++t) { F.tie_dst[t] = ties[2 * t]; F.tie_src[t] = ties[2 * t + 1]; }
   for (int j = 0; j < XRSD_MAX_FREE; ++j) { F.pop_of[j] = -1; }
   for (int j = 0; j < n_free; ++j) {
     F.idx[j] = free_idx[j];
@@ -44,7 +49,9 @@ static FreeSet make_free_set(const xrsd_layout_t *L, const int32_t *free_idx, in
     int uses = 0;
     if (L)
       for (int k = 0; k < L->n_pops; ++k) uses += (L->pops[k].p_I0 == free_idx[j]);
-    if (pop >= 0 && uses == 1) {
+    bool tied = false;      // a parameter that drives another one is not linear in a single term
+    for (int t = 0; t < F.n_tie; ++t) tied = tied || (F.tie_src[t] == free_idx[j]);
+    if (pop >= 0 && uses == 1 && !tied) {
       F.pop_of[j] = pop;
       F.var_of[j] = 0;
     } else {
@@ -146,6 +153,7 @@ jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *
     const int j = F.free_of_var[v];
     const double p0 = prm[F.idx[j]];
     prm_s[F.idx[j]] = p0 + ((p0 != 0.0) ? fabs(p0) * rel_step : rel_step);
+    for (int t = 0; t < F.n_tie; ++t) prm_s[F.tie_dst[t]] = prm_s[F.tie_src[t]];   // tied parameters move along
   }
   __syncthreads();
   const int q_begin = tile * q_per_cta;
@@ -376,6 +384,7 @@ __global__ void lm_propose_kernel(const double *__restrict__ params, int ldp, in
     v = fmin(fmax(v, l), h);
     if (v == v) t[F.idx[j]] = v;
   }
+  for (int k = 0; k < F.n_tie; ++k) t[F.tie_dst[k]] = t[F.tie_src[k]];
 }
 
 __global__ void lm_update_kernel(double *__restrict__ params, int ldp, int batch, const double *__restrict__ trial,
@@ -433,12 +442,13 @@ extern "C" size_t xrsd_jacobian_acc_doubles(int n_free) {
 extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q,
                                             int n_q, const double *d_params, int ldp, int batch,
                                             const xrsd_tables_t *tables, const double *d_Iobs, const double *d_dI,
-                                            long long ld_obs, const int32_t *free_idx, int n_free, double rel_step,
+                                            long long ld_obs, const int32_t *free_idx, int n_free, const int32_t *ties,
+                                            int n_tie, double rel_step,
                                             double *d_JTJ, double *d_JTr, double *d_chi2, double *d_Fvar, double *d_acc,
                                             unsigned *d_tickets, int q_per_cta, int scratch_doubles, int radial_multi,
                                             const uint8_t *d_active, cudaStream_t stream) {
   using namespace xrsd;
-  const FreeSet F = make_free_set(layout, free_idx, n_free);
+  const FreeSet F = make_free_set(layout, free_idx, n_free, ties, n_tie);
   int pat = 0;
   const size_t smem = xrsd_jacobian_smem(layout->n_params, n_free, q_per_cta, scratch_doubles, &pat);
   auto kern = radial_multi ? jacobian_variants_kernel<true, true>
@@ -468,10 +478,11 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
 }
 
 extern "C" cudaError_t xrsd_launch_lm_propose(const double *d_params, int ldp, int batch, const int32_t *free_idx, int n_free,
+                                              const int32_t *ties, int n_tie,
                                               const double *d_JTJ, const double *d_JTr, const double *d_lambda,
                                               const double *d_lo, const double *d_hi, const uint8_t *d_active,
                                               double *d_trial, cudaStream_t stream) {
-  const FreeSet F = xrsd::make_free_set(nullptr, free_idx, n_free);
+  const FreeSet F = xrsd::make_free_set(nullptr, free_idx, n_free, ties, n_tie);
   if (batch <= 0) return cudaSuccess;
   xrsd::lm_propose_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(d_params, ldp, batch, F, d_JTJ, d_JTr, d_lambda, d_lo, d_hi,
                                                                    d_active, d_trial);

@@ -31,7 +31,7 @@ class FitResult(object):
 
 def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weighted=True, logI_weighted=True,
                  q_range=(0., float('inf')), max_iter=30, ftol=1e-8, lambda0=1e-2, up=8.0, down=4.0,
-                 lambda_max=1e10, rel_step=1e-6, lo=None, hi=None, eng=None, return_device=False):
+                 lambda_max=1e10, rel_step=1e-6, lo=None, hi=None, eng=None, return_device=False, ties=None):
     """Fit every row of params0 ([batch, n_params]) to the matching row of Iobs ([batch, n_q] or [n_q]).
 
     Returns a FitResult of device tensors (return_device=True) or numpy arrays."""
@@ -40,6 +40,10 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     lib = eng.lib
     if free_slots is None:
         free_slots = layout.free_slots()
+    if ties is None:
+        ties = layout.ties()
+    free_slots = [s for s in free_slots if s not in [d for d, _ in ties]]      # a tied parameter is not varied
+    tie_c, n_tie = eng.tie_array(ties)
     nf = len(free_slots)
     if nf == 0:
         raise ValueError("no free parameters to fit")
@@ -51,6 +55,8 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     if d_p.dim() == 1:
         d_p = d_p.unsqueeze(0)
     batch, n_q = d_p.shape[0], d_q.shape[0]
+    for dst, src in ties:                       # lmfit evaluates the expression before the first objective call
+        d_p[:, dst] = d_p[:, src]
     d_I, d_dI, ld_obs = eng._obs(Iobs, dI, batch, n_q)
     obj = eng.objective(error_weighted, logI_weighted, q_range, has_dI=d_dI is not None)
     blo, bhi = layout.bounds(free_slots)
@@ -87,10 +93,10 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     for it in range(max_iter):
         n_iter = it + 1
         _, _, d_chi2 = eng.jacobian(layout, obj, d_q, d_p, d_I, d_dI, ld_obs, free_slots, tables, rel_step, out=jout,
-                                    active=d_active if it > 0 else None)
+                                    active=d_active if it > 0 else None, ties=ties)
         if chi2_init is None:
             chi2_init = d_chi2.clone()
-        abi.check(lib.xrsd_lm_propose(d_p.data_ptr(), d_p.shape[1], batch, idx, nf, jout[0].data_ptr(), jout[1].data_ptr(),
+        abi.check(lib.xrsd_lm_propose(d_p.data_ptr(), d_p.shape[1], batch, idx, nf, tie_c, n_tie, jout[0].data_ptr(), jout[1].data_ptr(),
                                       d_lambda.data_ptr(), d_lo.data_ptr(), d_hi.data_ptr(), d_active.data_ptr(),
                                       d_trial.data_ptr(), stream))
         # in-loop table builds do not read their status back (no host sync); it is checked every 5 iterations
@@ -147,8 +153,9 @@ def fit_system_inplace(system, q, I, dI=None):
         return system
     res = lm_fit_batch(lay, q, I, lay.values[None, :], free, dI=dI, error_weighted=rep['error_weighted'],
                        logI_weighted=rep['logI_weighted'], q_range=rep['q_range'], max_iter=60, eng=eng)
+    tied = [d for d, _ in lay.ties()]
     for slot, rec in enumerate(lay.records):
-        if slot in free:
+        if slot in free or slot in tied:
             rec['value'] = float(res.params[0, slot])
     I_opt = system.compute_intensity(q)
     I_bg = I - I_opt

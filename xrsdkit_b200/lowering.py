@@ -62,6 +62,24 @@ class SystemLayout(object):
         (reference system/__init__.py:197-209)."""
         return [i for i, r in enumerate(self.records) if not r.get('fixed') and not r.get('constraint_expr')]
 
+    def ties(self):
+        """[(dst_slot, src_slot)] for parameters whose constraint_expr names another parameter
+        ('particle__r': the only form found in xrsdkit's fitted systems).  Any other expression would need
+        lmfit's asteval and is rejected when a fit is requested."""
+        out = []
+        for i, r in enumerate(self.records):
+            expr = r.get('constraint_expr')
+            if not expr:
+                continue
+            key = str(expr).strip()
+            if key not in self.names:
+                raise NotImplementedError("constraint_expr %r: only '<population>__<parameter>' equality "
+                                          "constraints are supported" % expr)
+            out.append((i, self.names.index(key)))
+        if len(out) > abi.MAX_TIES:
+            raise NotImplementedError("at most %d constrained parameters per system" % abi.MAX_TIES)
+        return out
+
     def bounds(self, slots):
         lo = np.array([-np.inf if self.records[i]['bounds'][0] is None else self.records[i]['bounds'][0] for i in slots], float)
         hi = np.array([np.inf if self.records[i]['bounds'][1] is None else self.records[i]['bounds'][1] for i in slots], float)
