@@ -325,6 +325,23 @@ class Work(object):
         return per_q, 205.0 * ns + 150.0 + extra
 
 
+def ncu_traffic_bytes(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full
+    summary of this round (profiles/), per launch; None when no capture matches the workload."""
+    name = {"cfg2": "r01_final_ncu_cfg2_intensity.txt"}.get(workload)
+    if name is None:
+        return None
+    try:
+        tot = 0.0
+        for line in open(os.path.join(ROOT, "profiles", name)):
+            f = line.split()
+            if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[2]) * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}[f[1]]
+        return tot or None
+    except Exception:
+        return None
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -440,7 +457,10 @@ def run_gpu_arm(args):
     hbm_bytes = 8.0 * B * n_q     # intensity: the pattern is written once; fit kernels: I_obs is read once
     roofline = {
         "bound": "fp64", "achieved": achieved, "peak": fp64_tflops, "unit": "TFLOP/s", "frac": achieved / fp64_tflops,
-        "traffic": None, "kernel": kname, "kernel_ms": k_ms,
+        "traffic": ncu_traffic_bytes(args.workload) if B == 10000 else None,
+        "traffic_note": "ncu --set full capture of the same launch shape, profiles/r01_final_ncu_cfg2_intensity.txt; "
+                        "algorithmic bytes per launch = %.0f (the rest of the pattern is still in L2 when the kernel ends)" % hbm_bytes,
+        "kernel": kname, "kernel_ms": k_ms,
         "flops_per_unit": flops_unit, "units_per_launch": units,
         "peak_source": "xrsd_probe_fp64_peak: DFMA-bound kernel timed in this run (%.3f ms); MEASURED_PEAKS.json has no FP64 figure" % probe_ms,
         "achieved_survey_convention": survey_unit * units / (k_ms * 1e-3) / 1e12,

@@ -358,3 +358,30 @@ def test_components_in_one_launch(golden_systems, eng):
             fin = np.isfinite(ref)
             # a difference of running totals: absolute accuracy is that of the total
             np.testing.assert_allclose(parts[pn][fin], ref[fin], rtol=1e-10, atol=1e-12 * scale, err_msg=m["name"] + ":" + pn)
+
+
+def test_crystal_batch_properties_full_size(eng):
+    """cfg3 / cfg4 at BASELINE sizes (8192 q, 2000 systems, each with its own reflection table):
+    determinism, row-permutation equivariance, linearity in the crystal's I0, and I(q) > 0."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    q = np.linspace(0.01, 1.0, 8192)
+    s = cfg4_system(System)
+    lay = batch.layout_of(s, q)
+    P = cfg4_params(lay, 2000)
+    I = batch.compute_intensity_batch(lay, q, P, device_out=True)
+    assert bool((I == batch.compute_intensity_batch(lay, q, P, device_out=True)).all())
+    assert bool(eng.torch.isfinite(I).all()) and bool((I > 0).all())
+    perm = np.random.RandomState(1).permutation(2000)
+    Ip = batch.compute_intensity_batch(lay, q, P[perm], device_out=True)
+    assert bool((Ip == I[eng.torch.as_tensor(perm, device=I.device)]).all())
+    # population-wise linearity through the one-launch decomposition: total = noise + crystal + gp
+    tot, parts = eng.intensity_components(lay, q, P[:64])
+    np.testing.assert_allclose(parts.sum(dim=1).cpu().numpy(), tot.cpu().numpy(), rtol=1e-13)
+    P2 = P[:64].copy()
+    P2[:, lay.slot("x__I0")] *= 3.0
+    _, parts2 = eng.intensity_components(lay, q, P2)
+    np.testing.assert_allclose(parts2[:, 1].cpu().numpy(), 3.0 * parts[:, 1].cpu().numpy(), rtol=1e-12, atol=1e-300)
+    # parts are differences of running totals: the untouched population agrees to the rounding of the totals
+    np.testing.assert_allclose(parts2[:, 2].cpu().numpy(), parts[:, 2].cpu().numpy(), rtol=0,
+                               atol=1e-13 * float(tot.max()) * 3)

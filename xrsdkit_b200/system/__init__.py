@@ -183,7 +183,8 @@ def fit(sys, q, I, dI=None, error_weighted=None, logI_weighted=None, q_range=Non
     Same contract as xrsdkit.system.fit -- bounds, `fixed`, and the fit_report keys
     converged / initial_objective / final_objective / fit_snr -- but the optimiser is the
     batched GPU Levenberg-Marquardt of xrsdkit_b200.fitting (batch of one) instead of
-    lmfit's Nelder-Mead.  Parameters with a constraint_expr are held fixed.  The reference
+    lmfit's Nelder-Mead.  A constraint_expr that names another parameter ('particle__r') is kept as an
+    equality tie; other expressions raise NotImplementedError.  The reference
     stores `error_weighted` into logI_weighted here (a bug, :255-256); this keeps the
     documented meaning."""
     from .. import fitting
