@@ -197,14 +197,15 @@ int xrsd_reflection_tables(const xrsd_layout_t *layout, const double *d_params, 
 static int pick_q_per_cta(int n_q, int batch, int scratch, bool has_xtal) {
   // One CTA holds a span of one pattern in shared memory.  Spans are multiples of 512 q-points;
   // aim for >= 24 CTAs per SM in the grid (several waves, so the last partial wave costs little)
-  // and keep the span small enough for six 128-thread CTAs per SM: 4096 q-points (32 KB), or 3072 for
-  // layouts with crystalline populations, whose kernels carry ~7 KB of static shared memory.
+  // and keep the span small enough for the resident CTAs: 4096 q-points (32 KB, six CTAs per SM), or 2048
+  // for layouts with crystalline populations, whose intensity kernel is compiled for eight CTAs per SM
+  // (64 registers; measured 7 % faster than six) and carries ~6 KB of static shared memory.
   const long long want_ctas = 148LL * 24;
   long long tiles = (want_ctas + batch - 1) / batch;
   if (tiles < 1) tiles = 1;
   long long per = ((long long)n_q + tiles - 1) / tiles;
   per = ((per + 511) / 512) * 512;
-  const long long cap = std::max(512LL, std::min(has_xtal ? 3072LL : 4096LL, ((long long)(36 * 1024 / 8 - scratch) / 512) * 512));
+  const long long cap = std::max(512LL, std::min(has_xtal ? 2048LL : 4096LL, ((long long)(36 * 1024 / 8 - scratch) / 512) * 512));
   per = std::min(per, cap);
   per = std::min<long long>(per, ((long long)n_q + 511) / 512 * 512);
   return (int)std::max(512LL, per);
@@ -302,7 +303,7 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   int rm;
   const int scratch = scratch_doubles_for(layout, &rm);
   if (scratch < 0) return fail(XRSD_ECAPACITY, "size quadrature too fine for shared memory");
-  const int per = pick_q_per_cta(n_q, batch * (n_free + 1), scratch, false);   // measured: 4096-point spans win here
+  const int per = pick_q_per_cta(n_q, batch * (n_free + 1), scratch, false);   // measured: 4096-point spans, 6 CTAs/SM win here
   if (xrsd_jacobian_smem(layout->n_params, n_free, per, scratch, nullptr) + kStaticSmem > (size_t)kMaxSmem)
     return fail(XRSD_ECAPACITY, "jacobian working set does not fit in shared memory");
   const int64_t fbytes = (int64_t)batch * (n_free + 1 + XRSD_MAX_POPS) * n_q * 8;
