@@ -168,12 +168,15 @@ int xrsd_intensity_components_batch(const xrsd_layout_t *layout, const double *d
 
 /* chi2[b] of System.evaluate_residual for b < batch; d_Iobs / d_dI are [batch][ld_obs]
  * (ld_obs == 0 broadcasts one pattern to the whole batch).  I(q) is computed in the same
- * kernel and never written to memory. */
+ * kernel (grid = batch x q-spans) and never written to memory; the spans of a system meet in
+ * d_workspace (xrsd_residual_workspace_bytes(batch) bytes, zero before the first call, re-zeroed
+ * by the kernel). */
+int64_t xrsd_residual_workspace_bytes(int32_t batch);
 int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj,
                         const double *d_q, int32_t n_q, const double *d_params, int32_t ld_params,
                         int32_t batch, const xrsd_tables_t *tables,
                         const double *d_Iobs, const double *d_dI, int64_t ld_obs,
-                        double *d_chi2, const uint8_t *d_active, void *stream);
+                        double *d_chi2, void *d_workspace, const uint8_t *d_active, void *stream);
 
 /* Forward-difference Jacobian of the weighted residual vector, reduced in-kernel to the
  * normal equations: JTJ[b][n_free][n_free], JTr[b][n_free], chi2[b].  free_idx[n_free] (HOST

@@ -18,8 +18,8 @@ cudaError_t xrsd_launch_intensity(const xrsd_layout_t *, const double *, int, co
 cudaError_t xrsd_launch_fp64_probe(double *, int, int, cudaStream_t);
 cudaError_t xrsd_launch_profile(int, double, double, const double *, int, double *, cudaStream_t);
 cudaError_t xrsd_launch_residual(const xrsd_layout_t *, const xrsd_objective_t *, const double *, int, const double *, int, int,
-                                 const xrsd_tables_t *, const double *, const double *, long long, double *, int, int,
-                                 const uint8_t *, cudaStream_t);
+                                 const xrsd_tables_t *, const double *, const double *, long long, double *, int, int, int,
+                                 const uint8_t *, double *, unsigned *, cudaStream_t);
 size_t xrsd_jacobian_smem(int, int, int, int, int *);
 cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *, const xrsd_objective_t *, const double *, int, const double *, int, int,
                                  const xrsd_tables_t *, const double *, const double *, long long, const int32_t *, int,
@@ -245,26 +245,32 @@ int xrsd_intensity_components_batch(const xrsd_layout_t *layout, const double *d
   return intensity_impl(layout, d_q, n_q, d_params, ld_params, batch, tables, d_I, ld_I, d_cum, stream);
 }
 
+int64_t xrsd_residual_workspace_bytes(int32_t batch) {
+  // per system: two FP64 accumulators (sum w d^2, sum w), then one ticket each; zero-initialised once
+  return (int64_t)batch * 16 + (((int64_t)batch * 4 + 255) & ~255LL);
+}
+
 int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q, int32_t n_q,
                         const double *d_params, int32_t ld_params, int32_t batch, const xrsd_tables_t *tables,
-                        const double *d_Iobs, const double *d_dI, int64_t ld_obs, double *d_chi2, const uint8_t *d_active,
-                        void *stream) {
+                        const double *d_Iobs, const double *d_dI, int64_t ld_obs, double *d_chi2, void *d_workspace,
+                        const uint8_t *d_active, void *stream) {
   int rc = check_layout(layout);
   if (rc) return rc;
   if (batch <= 0 || n_q <= 0) return XRSD_OK;
   rc = check_tables(layout, tables);
   if (rc) return rc;
-  if (!obj || !d_q || !d_params || !d_Iobs || !d_chi2) return fail(XRSD_EINVAL, "NULL pointer");
+  if (!obj || !d_q || !d_params || !d_Iobs || !d_chi2 || !d_workspace) return fail(XRSD_EINVAL, "NULL pointer");
   if (obj->has_dI && !d_dI) return fail(XRSD_EINVAL, "objective.has_dI set but d_dI is NULL");
   if (ld_obs != 0 && ld_obs < n_q) return fail(XRSD_EINVAL, "ld_obs < n_q");
   int rm;
   const int scratch = scratch_doubles_for(layout, &rm);
   if (scratch < 0) return fail(XRSD_ECAPACITY, "size quadrature too fine for shared memory");
-  if (((size_t)n_q + scratch + 2) * 8 + kStaticSmem > (size_t)kMaxSmem)
-    return fail(XRSD_ECAPACITY, "n_q=%d: a whole pattern must fit in shared memory for the fused residual", n_q);
+  const int per = pick_q_per_cta(n_q, batch, scratch, layout->n_xtal > 0);
+  double *d_acc = (double *)d_workspace;
+  unsigned *d_tickets = (unsigned *)((char *)d_workspace + (int64_t)batch * 16);
   cudaError_t e = xrsd_launch_residual(layout, obj, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables,
-                                       d_Iobs, obj->has_dI ? d_dI : nullptr, (long long)ld_obs, d_chi2, scratch, rm, d_active,
-                                       (cudaStream_t)stream);
+                                       d_Iobs, obj->has_dI ? d_dI : nullptr, (long long)ld_obs, d_chi2, per, scratch, rm, d_active,
+                                       d_acc, d_tickets, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "residual_kernel");
   return XRSD_OK;
 }

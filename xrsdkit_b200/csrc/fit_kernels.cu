@@ -77,27 +77,37 @@ __device__ __forceinline__ bool fit_weight(const xrsd_objective_t &O, double qv,
   return fit;
 }
 
+// Grid = batch x q-spans (same span policy as the intensity kernel).  Each CTA evaluates its span into
+// shared memory, reduces its part of sum(w d^2) and sum(w), adds both to a per-system accumulator with
+// FP64 atomics; the span that takes the last ticket of a system writes chi2 = num/den and re-zeroes the
+// accumulator.  I(q) never goes to HBM.
 template <bool RM, bool HX>
-__global__ void __launch_bounds__(EVAL_THREADS, HX ? 4 : 6)
+__global__ void __launch_bounds__(EVAL_THREADS, 6)
 residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t O, const double *__restrict__ q, int n_q,
                 const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
                 const double *__restrict__ Iobs, const double *__restrict__ dI, long long ld_obs,
-                double *__restrict__ chi2, int scratch_doubles, const uint8_t *__restrict__ active) {
+                double *__restrict__ chi2, int scratch_doubles, const uint8_t *__restrict__ active,
+                double *__restrict__ acc_g, unsigned *__restrict__ tickets, int q_per_cta, int n_tiles) {
   extern __shared__ __align__(16) double smem_d[];
   __shared__ EvalSharedT<HX> S;
-  const int b = blockIdx.x;
+  __shared__ int is_last;
+  const long long bid = blockIdx.x;
+  const int b = (int)(bid / n_tiles);
+  const int tile = (int)(bid - (long long)b * n_tiles);
   if (b >= batch) return;
   if (active != nullptr && !active[b]) return;
+  const int q_begin = tile * q_per_cta;
+  const int q_count = min(q_per_cta, n_q - q_begin);
   double *I_sm = smem_d;
-  double *scratch = smem_d + ((n_q + 1) & ~1);
-  accumulate_system<2, RM, HX>(L, params + (size_t)b * ldp, T, b, q, n_q, 0, n_q, I_sm, scratch, scratch_doubles, &S);
-  const double *obs = Iobs + (size_t)b * ld_obs;
-  const double *err = dI ? dI + (size_t)b * ld_obs : nullptr;
+  double *scratch = smem_d + ((q_per_cta + 1) & ~1);
+  accumulate_system<2, RM, HX>(L, params + (size_t)b * ldp, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S);
+  const double *obs = Iobs + (size_t)b * ld_obs + q_begin;
+  const double *err = dI ? dI + (size_t)b * ld_obs + q_begin : nullptr;
   double num = 0.0, den = 0.0;
-  for (int i = threadIdx.x; i < n_q; i += EVAL_THREADS) {
+  for (int i = threadIdx.x; i < q_count; i += EVAL_THREADS) {
     const double Io = obs[i], Ic = I_sm[i];
     double w;
-    bool fit = fit_weight(O, q[i], Io, err, i, w);
+    bool fit = fit_weight(O, q[q_begin + i], Io, err, i, w);
     double d;
     if (O.logI_weighted) {
       fit = fit && (Ic > 0.0);
@@ -109,7 +119,20 @@ residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
   }
   num = block_sum(num, &S);
   den = block_sum(den, &S);
-  if (threadIdx.x == 0) chi2[b] = num / den;
+  if (threadIdx.x == 0) {
+    atomicAdd(&acc_g[2 * (size_t)b], num);
+    atomicAdd(&acc_g[2 * (size_t)b + 1], den);
+    __threadfence();
+    is_last = (atomicAdd(&tickets[b], 1u) == (unsigned)(n_tiles - 1));
+    if (is_last) {
+      __threadfence();
+      const double n_ = __ldcg(&acc_g[2 * (size_t)b]), d_ = __ldcg(&acc_g[2 * (size_t)b + 1]);
+      chi2[b] = n_ / d_;
+      acc_g[2 * (size_t)b] = 0.0;
+      acc_g[2 * (size_t)b + 1] = 0.0;
+      tickets[b] = 0;
+    }
+  }
 }
 
 // Normal equations by forward differences: two launches.
@@ -414,17 +437,22 @@ using xrsd::FreeSet;
 extern "C" cudaError_t xrsd_launch_residual(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q,
                                             int n_q, const double *d_params, int ldp, int batch,
                                             const xrsd_tables_t *tables, const double *d_Iobs, const double *d_dI,
-                                            long long ld_obs, double *d_chi2, int scratch_doubles, int radial_multi,
-                                            const uint8_t *d_active, cudaStream_t stream) {
+                                            long long ld_obs, double *d_chi2, int q_per_cta, int scratch_doubles,
+                                            int radial_multi, const uint8_t *d_active, double *d_acc, unsigned *d_tickets,
+                                            cudaStream_t stream) {
   using namespace xrsd;
-  const size_t smem = ((size_t)((n_q + 1) & ~1) + (size_t)scratch_doubles) * sizeof(double);
+  const size_t smem = ((size_t)((q_per_cta + 1) & ~1) + (size_t)scratch_doubles) * sizeof(double);
   auto kern = radial_multi ? residual_kernel<true, true>
                            : (layout->n_xtal ? residual_kernel<false, true> : residual_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (batch <= 0) return cudaSuccess;
-  kern<<<batch, EVAL_THREADS, smem, stream>>>(*layout, *obj, d_q, n_q, d_params, ldp, batch, *tables, d_Iobs, d_dI, ld_obs,
-                                             d_chi2, scratch_doubles, d_active);
+  const int n_tiles = (n_q + q_per_cta - 1) / q_per_cta;
+  const long long n_blocks = (long long)batch * n_tiles;
+  if (n_blocks > 2147483647LL) return cudaErrorInvalidConfiguration;
+  kern<<<(unsigned)n_blocks, EVAL_THREADS, smem, stream>>>(*layout, *obj, d_q, n_q, d_params, ldp, batch, *tables, d_Iobs, d_dI,
+                                                          ld_obs, d_chi2, scratch_doubles, d_active, d_acc, d_tickets, q_per_cta,
+                                                          n_tiles);
   return cudaGetLastError();
 }
 

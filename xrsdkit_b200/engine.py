@@ -217,6 +217,16 @@ class Engine(object):
         assert tuple(d_I.shape) == shape
         return d_I, d_dI, (n_q if per_system else 0)
 
+    def residual_workspace(self, batch):
+        """Zero-initialised accumulator / ticket area of xrsd_residual_batch, kept per batch size (the layout
+        of the area depends on it; the kernel leaves it zeroed after every launch)."""
+        cache = self.__dict__.setdefault("_res_ws", {})
+        if batch not in cache:
+            cache.clear()
+            cache[batch] = self.torch.zeros(int(self.lib.xrsd_residual_workspace_bytes(batch)), dtype=self.torch.uint8,
+                                            device=self.device)
+        return cache[batch]
+
     def residual(self, layout, obj, q, params, Iobs, dI=None, tables=None, active=None, out=None):
         """chi2[b] of System.evaluate_residual for every parameter set of the batch."""
         torch = self.torch
@@ -231,11 +241,12 @@ class Engine(object):
         if layout.n_xtal and tables is None:
             tables = self.build_tables(layout, d_p, batch, params_host=host_params)
         chi2 = out if out is not None else torch.empty(batch, dtype=torch.float64, device=self.device)
+        ws = self.residual_workspace(batch)
         abi.check(self.lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_p.data_ptr(),
                                                d_p.shape[1], batch, C.byref(tables.c) if tables is not None else None,
                                                d_I.data_ptr(), d_dI.data_ptr() if d_dI is not None else None, ld,
-                                               chi2.data_ptr(), active.data_ptr() if active is not None else None,
-                                               self._stream()))
+                                               chi2.data_ptr(), ws.data_ptr(),
+                                               active.data_ptr() if active is not None else None, self._stream()))
         self.launches += 1
         return chi2
 

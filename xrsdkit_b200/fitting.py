@@ -88,6 +88,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells) if layout.n_xtal else None
     chi2_init = None
     t_tables = None
+    res_ws = eng.residual_workspace(batch)
     stream = eng._stream()
     n_iter = 0
     for it in range(max_iter):
@@ -105,7 +106,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         abi.check(lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_trial.data_ptr(),
                                           d_trial.shape[1], batch, C.byref(t_tables.c) if t_tables is not None else None,
                                           d_I.data_ptr(), d_dI.data_ptr() if d_dI is not None else None, ld_obs,
-                                          d_chi2_t.data_ptr(), d_active.data_ptr(), stream))
+                                          d_chi2_t.data_ptr(), res_ws.data_ptr(), d_active.data_ptr(), stream))
         abi.check(lib.xrsd_lm_update(d_p.data_ptr(), d_p.shape[1], batch, d_trial.data_ptr(), d_chi2.data_ptr(),
                                      d_chi2_t.data_ptr(), d_lambda.data_ptr(), d_active.data_ptr(), d_nacc.data_ptr(),
                                      float(up), float(down), float(ftol), float(lambda_max), stream))
