@@ -354,6 +354,8 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from xrsdkit_b200 import engine, batch as xb
+    if world > 1:
+        xb.bind_to_gpu_numa(local)      # host buffers of the e2e path next to this rank's GPU
     eng = engine.get_engine()
     dev = eng.device
     B = args.batch
