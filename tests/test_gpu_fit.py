@@ -216,3 +216,58 @@ def test_fit_with_equality_constraint(eng):
     start.populations["superlattice"].parameters["r"]["constraint_expr"] = "particle__r * 2"
     with pytest.raises(NotImplementedError):
         fit(start, q, I)
+
+
+def test_nelder_mead_like_for_like(eng):
+    """The reference's optimiser (Nelder-Mead on the scalar objective, lmfit's bound transform), batched:
+    reaches the same optimum as the LM fitter on noisy sphere data, and agrees with scipy's Nelder-Mead run
+    on the oracle objective for one system."""
+    from scipy.optimize import minimize
+    from oracle import xrsd_oracle as orc
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch, definitions as d
+    s = System(p=dict(structure="diffuse", form="spherical", settings={"distribution": "r_normal", "sampling_width": 2.52,
+                                                                      "sampling_step": 0.1},
+                      parameters={"r": {"value": 30.0}, "sigma": {"value": 0.1}, "I0": {"value": 100.0}}),
+               noise={"model": "flat", "parameters": {"I0": {"value": 0.05}}})
+    q = np.linspace(0.02, 0.5, 400)
+    lay = batch.layout_of(s, q)
+    free = [lay.slot(k) for k in ("noise__I0", "p__I0", "p__r", "p__sigma")]
+    rs = np.random.RandomState(5)
+    n = 16
+    truth = np.tile(lay.values, (n, 1))
+    truth[:, lay.slot("p__r")] = rs.uniform(20, 40, n)
+    truth[:, lay.slot("p__sigma")] = rs.uniform(0.05, 0.2, n)
+    Iobs = batch.compute_intensity_batch(lay, q, truth) * (1 + 0.02 * rs.randn(n, q.size))
+    start = truth.copy()
+    start[:, free] *= 1 + 0.08 * rs.uniform(-1, 1, (n, len(free)))
+    nm = batch.fit_batch(lay, q, Iobs, start, method="nelder-mead", free_slots=free)
+    lm = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=40)
+    assert np.all(nm.chi2 <= nm.chi2_init)
+    np.testing.assert_allclose(nm.chi2, lm.chi2, rtol=2e-2)
+    np.testing.assert_allclose(nm.params[:, lay.slot("p__r")], lm.params[:, lay.slot("p__r")], rtol=5e-3)
+    # scipy's Nelder-Mead on the oracle objective, same start, no bounds active at the optimum
+    tables = dict(atomic_table=d.atomic_params, sg_point_groups=d.sg_point_groups, lattice_space_groups=d.lattice_space_groups)
+
+    def objective(x):
+        row = start[0].copy()
+        row[free] = x
+        if np.any(x <= 0):
+            return 1e30
+        return orc.residual(q, Iobs[0], orc.system_intensity(q, params_to_sysdict(s, lay, row), **tables))
+
+    ref = minimize(objective, start[0][free], method="Nelder-Mead", options=dict(xatol=1e-4, fatol=1e-4, maxiter=800))
+    assert nm.chi2[0] == pytest.approx(ref.fun, rel=2e-2)
+
+
+def test_fit_api_nelder_mead_mode(eng):
+    from xrsdkit_b200.system import System, fit
+    q = np.linspace(0.01, 0.5, 500)
+    sph = System(p=dict(structure="diffuse", form="spherical", parameters={"r": {"value": 20.0}, "I0": {"value": 5.0}}))
+    I = sph.compute_intensity(q) * (1 + 0.01 * np.random.RandomState(4).randn(q.size))
+    guess = System(p=dict(structure="diffuse", form="spherical", parameters={"r": {"value": 21.0}, "I0": {"value": 4.0}}))
+    a, b = fit(guess, q, I), fit(guess, q, I, method="nelder-mead")
+    assert b.populations["p"].parameters["r"]["value"] == pytest.approx(a.populations["p"].parameters["r"]["value"], rel=1e-3)
+    assert b.fit_report["final_objective"] == pytest.approx(a.fit_report["final_objective"], rel=1e-2)
+    with pytest.raises(ValueError):
+        fit(guess, q, I, method="simplex?")

@@ -60,7 +60,13 @@ def evaluate_residual_batch(layout, q, Iobs, params, dI=None, error_weighted=Tru
     return chi2 if device_out else chi2.cpu().numpy()
 
 
-def fit_batch(layout, q, Iobs, params0, **kw):
+def fit_batch(layout, q, Iobs, params0, method='lm', **kw):
+    """Fit every row of params0.  method='lm' (default): batched Levenberg-Marquardt;
+    method='nelder-mead': the reference's optimiser, batched, for like-for-like comparison."""
+    if method in ('nelder-mead', 'nelder', 'nm'):
+        return fitting.nm_fit_batch(layout, q, Iobs, params0, **kw)
+    if method != 'lm':
+        raise ValueError("unknown fit method %r" % (method,))
     return fitting.lm_fit_batch(layout, q, Iobs, params0, **kw)
 
 

@@ -139,7 +139,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
                      d_nacc.cpu().numpy(), d_active.bool().cpu().numpy())
 
 
-def fit_system_inplace(system, q, I, dI=None):
+def fit_system_inplace(system, q, I, dI=None, method='lm'):
     """fit() backend: optimise `system`'s free parameters in place and fill its fit_report with the
     keys the reference writes (system/__init__.py:268-275)."""
     eng = _engine.get_engine()
@@ -152,8 +152,13 @@ def fit_system_inplace(system, q, I, dI=None):
         obj0 = system.evaluate_residual(q, I, dI)
         rep.update(converged=True, initial_objective=obj0, final_objective=obj0)
         return system
-    res = lm_fit_batch(lay, q, I, lay.values[None, :], free, dI=dI, error_weighted=rep['error_weighted'],
-                       logI_weighted=rep['logI_weighted'], q_range=rep['q_range'], max_iter=60, eng=eng)
+    kw = dict(dI=dI, error_weighted=rep['error_weighted'], logI_weighted=rep['logI_weighted'], q_range=rep['q_range'], eng=eng)
+    if method in ('nelder-mead', 'nelder', 'nm'):
+        res = nm_fit_batch(lay, q, I, lay.values[None, :], free, **kw)
+    elif method == 'lm':
+        res = lm_fit_batch(lay, q, I, lay.values[None, :], free, max_iter=60, **kw)
+    else:
+        raise ValueError("unknown fit method %r" % (method,))
     tied = [d for d, _ in lay.ties()]
     for slot, rec in enumerate(lay.records):
         if slot in free or slot in tied:
@@ -165,3 +170,159 @@ def fit_system_inplace(system, q, I, dI=None):
     rep['final_objective'] = float(res.chi2[0])
     rep['fit_snr'] = float(np.mean(I_opt) / np.std(I_bg))
     return system
+
+
+# ---------------------------------------------------------------------------------------------
+# Nelder-Mead, batched: the reference's own optimiser (lmfit.minimize(method='nelder-mead'),
+# system/__init__.py:262-266), for like-for-like comparison with the LM fitter above.
+# ---------------------------------------------------------------------------------------------
+class _BoundTransform(object):
+    """lmfit's MINUIT-style mapping between bounded parameter values and the unbounded internal
+    variables the simplex moves in: both bounds  x = lo + (sin(u) + 1)(hi - lo)/2;
+    lower only  x = lo - 1 + sqrt(u^2 + 1);  upper only  x = hi + 1 - sqrt(u^2 + 1)."""
+
+    def __init__(self, torch, lo, hi, device):
+        self.t = torch
+        self.lo = torch.as_tensor(lo, dtype=torch.float64, device=device)
+        self.hi = torch.as_tensor(hi, dtype=torch.float64, device=device)
+        fin_lo, fin_hi = torch.isfinite(self.lo), torch.isfinite(self.hi)
+        self.both, self.only_lo, self.only_hi = fin_lo & fin_hi, fin_lo & ~fin_hi, ~fin_lo & fin_hi
+
+    def to_internal(self, x):
+        t = self.t
+        lo = torch_nan_to(self.t, self.lo)
+        hi = torch_nan_to(self.t, self.hi)
+        u = x.clone()
+        arg = (2 * (x - lo) / (hi - lo) - 1).clamp(-1, 1)
+        u = t.where(self.both, t.asin(arg), u)
+        u = t.where(self.only_lo, t.sqrt(((x - lo + 1) ** 2 - 1).clamp(min=0)), u)
+        u = t.where(self.only_hi, t.sqrt(((hi - x + 1) ** 2 - 1).clamp(min=0)), u)
+        return u
+
+    def to_external(self, u):
+        t = self.t
+        lo = torch_nan_to(self.t, self.lo)
+        hi = torch_nan_to(self.t, self.hi)
+        x = u.clone()
+        x = t.where(self.both, lo + (t.sin(u) + 1) * (hi - lo) / 2, x)
+        x = t.where(self.only_lo, lo - 1 + t.sqrt(u * u + 1), x)
+        x = t.where(self.only_hi, hi + 1 - t.sqrt(u * u + 1), x)
+        return x
+
+
+def torch_nan_to(torch, v):
+    return torch.where(torch.isfinite(v), v, torch.zeros_like(v))
+
+
+def nm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weighted=True, logI_weighted=True,
+                 q_range=(0., float('inf')), max_iter=None, xatol=1e-4, fatol=1e-4, eng=None, return_device=False,
+                 ties=None):
+    """Batched Nelder-Mead on the reference's scalar objective (scipy's algorithm with its default
+    coefficients and initial simplex, lmfit's bound transform).  Every objective evaluation of the whole
+    batch is one residual launch (plus a masked table build for crystalline layouts); the simplex
+    bookkeeping is elementwise tensor work on the device."""
+    eng = eng or _engine.get_engine()
+    torch = eng.torch
+    if free_slots is None:
+        free_slots = layout.free_slots()
+    if ties is None:
+        ties = layout.ties()
+    free_slots = [s for s in free_slots if s not in [d for d, _ in ties]]
+    nf = len(free_slots)
+    if nf == 0:
+        raise ValueError("no free parameters to fit")
+    d_q = eng.to_device(q)
+    host_p0 = None if isinstance(params0, torch.Tensor) else np.atleast_2d(np.asarray(params0, dtype=np.float64))
+    d_p = eng.to_device(params0 if host_p0 is None else host_p0).clone()
+    if d_p.dim() == 1:
+        d_p = d_p.unsqueeze(0)
+    batch, n_q = d_p.shape[0], d_q.shape[0]
+    for dst, src in ties:
+        d_p[:, dst] = d_p[:, src]
+    d_I, d_dI, _ = eng._obs(Iobs, dI, batch, n_q)
+    obj = eng.objective(error_weighted, logI_weighted, q_range, has_dI=d_dI is not None)
+    blo, bhi = layout.bounds(free_slots)
+    tr = _BoundTransform(torch, blo, bhi, eng.device)
+    fidx = torch.as_tensor(free_slots, dtype=torch.long, device=eng.device)
+    max_cells = None
+    if layout.n_xtal:
+        hp = d_p.cpu().numpy()
+        max_cells = min(90000, int(lowering.max_cells(layout, 1.5 * np.abs(hp))))
+    state = dict(tables=None, n_eval=0)
+    inf = torch.full((batch,), float('inf'), dtype=torch.float64, device=eng.device)
+
+    def evaluate(u, mask=None):
+        """chi2 of every system at internal coordinates u [batch, nf]; systems outside `mask` give +inf."""
+        p = d_p.clone()
+        p[:, fidx] = tr.to_external(u)
+        for dst, src in ties:
+            p[:, dst] = p[:, src]
+        act = None if mask is None else mask.to(torch.uint8)
+        if layout.n_xtal:
+            state['tables'] = eng.build_tables(layout, p, batch, max_cells=max_cells, reuse=state['tables'],
+                                               check=state['tables'] is None, active=act if state['tables'] is not None else None)
+        out = inf.clone()
+        eng.residual(layout, obj, d_q, p, d_I, d_dI, tables=state['tables'], active=act, out=out)
+        state['n_eval'] += 1
+        out = torch.where(torch.isnan(out), inf, out)
+        return out if mask is None else torch.where(mask, out, inf)
+
+    u0 = tr.to_internal(d_p[:, fidx])
+    U = u0.unsqueeze(1).repeat(1, nf + 1, 1)
+    for k in range(nf):                                   # scipy: nonzdelt = 0.05, zdelt = 0.00025
+        col = U[:, k + 1, k]
+        U[:, k + 1, k] = torch.where(col != 0, 1.05 * col, torch.full_like(col, 0.00025))
+    F = torch.stack([evaluate(U[:, k]) for k in range(nf + 1)], dim=1)
+    chi2_init = F[:, 0].clone()
+    if max_iter is None:
+        max_iter = 200 * nf                               # scipy's default maxiter
+    done = torch.zeros(batch, dtype=torch.bool, device=eng.device)
+    n_iter = 0
+    rows = torch.arange(batch, device=eng.device)
+    for it in range(max_iter):
+        n_iter = it + 1
+        order = torch.argsort(F, dim=1)
+        F = torch.gather(F, 1, order)
+        U = torch.gather(U, 1, order.unsqueeze(-1).expand(-1, -1, nf))
+        small_x = (U[:, 1:] - U[:, :1]).abs().amax(dim=(1, 2)) <= xatol
+        small_f = (F[:, 1:] - F[:, :1]).abs().amax(dim=1) <= fatol
+        done = done | (small_x & small_f)
+        if it % 10 == 9 and bool(done.all().item()):
+            break
+        act = ~done
+        xbar = U[:, :-1].mean(dim=1)
+        xw = U[:, -1]
+        xr = 2 * xbar - xw
+        fr = evaluate(xr, act)
+        c_exp = act & (fr < F[:, 0])
+        c_acc = act & ~c_exp & (fr < F[:, -2])
+        c_oc = act & ~c_exp & ~c_acc & (fr < F[:, -1])
+        c_ic = act & ~c_exp & ~c_acc & ~c_oc
+        x2 = torch.where(c_exp.unsqueeze(1), 3 * xbar - 2 * xw,
+                         torch.where(c_oc.unsqueeze(1), 1.5 * xbar - 0.5 * xw, 0.5 * xbar + 0.5 * xw))
+        f2 = evaluate(x2, c_exp | c_oc | c_ic)
+        take2 = (c_exp & (f2 < fr)) | (c_oc & (f2 <= fr)) | (c_ic & (f2 < F[:, -1]))
+        take_r = (c_exp & ~take2) | c_acc
+        shrink = (c_oc | c_ic) & ~take2
+        new_x = torch.where(take2.unsqueeze(1), x2, torch.where(take_r.unsqueeze(1), xr, xw))
+        new_f = torch.where(take2, f2, torch.where(take_r, fr, F[:, -1]))
+        U[:, -1] = new_x
+        F[:, -1] = new_f
+        if bool(shrink.any().item()):
+            for k in range(1, nf + 1):
+                xs = U[:, 0] + 0.5 * (U[:, k] - U[:, 0])
+                fs = evaluate(xs, shrink)
+                U[:, k] = torch.where(shrink.unsqueeze(1), xs, U[:, k])
+                F[:, k] = torch.where(shrink, fs, F[:, k])
+    best = torch.argmin(F, dim=1)
+    ub = U[rows, best]
+    p = d_p.clone()
+    p[:, fidx] = tr.to_external(ub)
+    for dst, src in ties:
+        p[:, dst] = p[:, src]
+    chi2 = F[rows, best]
+    res = FitResult(p, chi2_init, chi2, n_iter, torch.full((batch,), state['n_eval'], dtype=torch.int32, device=eng.device), ~done)
+    if return_device:
+        return res
+    return FitResult(p.cpu().numpy(), chi2_init.cpu().numpy(), chi2.cpu().numpy(), n_iter, res.n_accept.cpu().numpy(),
+                     (~done).cpu().numpy())

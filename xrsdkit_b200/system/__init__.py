@@ -177,13 +177,14 @@ def eng_chi2_given_intensity(eng, q, I, dI, I_comp, rep):
     return float(((y1 - y2) ** 2 * w).sum().item())
 
 
-def fit(sys, q, I, dI=None, error_weighted=None, logI_weighted=None, q_range=None):
+def fit(sys, q, I, dI=None, error_weighted=None, logI_weighted=None, q_range=None, method='lm'):
     """Fit I(q) and return a System with optimised parameters (reference :220-278).
 
     Same contract as xrsdkit.system.fit -- bounds, `fixed`, and the fit_report keys
     converged / initial_objective / final_objective / fit_snr -- but the optimiser is the
     batched GPU Levenberg-Marquardt of xrsdkit_b200.fitting (batch of one) instead of
-    lmfit's Nelder-Mead.  A constraint_expr that names another parameter ('particle__r') is kept as an
+    lmfit's Nelder-Mead; method='nelder-mead' runs the reference's algorithm (scipy's Nelder-Mead
+    coefficients, lmfit's bound transform) on the same GPU objective.  A constraint_expr that names another parameter ('particle__r') is kept as an
     equality tie; other expressions raise NotImplementedError.  The reference
     stores `error_weighted` into logI_weighted here (a bug, :255-256); this keeps the
     documented meaning."""
@@ -195,7 +196,7 @@ def fit(sys, q, I, dI=None, error_weighted=None, logI_weighted=None, q_range=Non
         sys_opt.fit_report.update(logI_weighted=logI_weighted)
     if q_range is not None:
         sys_opt.fit_report.update(q_range=q_range)
-    fitting.fit_system_inplace(sys_opt, np.asarray(q, dtype=float), np.asarray(I, dtype=float), dI)
+    fitting.fit_system_inplace(sys_opt, np.asarray(q, dtype=float), np.asarray(I, dtype=float), dI, method=method)
     return sys_opt
 
 
