@@ -2,6 +2,7 @@
 import copy
 
 from .. import definitions as xrsdefs
+from ._records import reconcile, snapshot
 
 
 class NoiseModel(object):
@@ -12,30 +13,18 @@ class NoiseModel(object):
         self.update_parameters(parameters)
 
     def to_dict(self):
-        return dict(model=copy.copy(self.model),
-                    parameters=dict((k, copy.deepcopy(v)) for k, v in self.parameters.items()))
+        return dict(model=copy.copy(self.model), parameters=snapshot(self.parameters))
 
     def set_model(self, new_model):
         self.model = new_model
         self.update_parameters()
 
     def update_parameters(self, new_params={}):
-        valid = copy.deepcopy(xrsdefs.noise_params[self.model])
-        for name in new_params:
-            if name not in valid:
-                raise ValueError('Parameter {} is not valid for noise model {}'.format(name, self.model))
-        for name in list(self.parameters.keys()):
-            if name in valid:
-                valid[name].update(self.parameters[name])
-            else:
-                self.parameters.pop(name)
-        for name, rec in new_params.items():
-            valid[name].update(rec)
-        self.parameters.update(valid)
+        reconcile(self.parameters, copy.deepcopy(xrsdefs.noise_params[self.model]), new_params,
+                  lambda nm: 'Parameter {} is not valid for noise model {}'.format(nm, self.model))
 
     def compute_intensity(self, q):
         if self.model not in xrsdefs.noise_model_names:
             raise ValueError('unsupported noise specification: {}'.format(self.model))
         from .. import lowering, engine
-        lay = lowering.lower_noise_only(self, q)
-        return engine.get_engine().intensity_single(lay, q)
+        return engine.get_engine().intensity_single(lowering.lower_noise_only(self, q), q)

@@ -8,32 +8,35 @@ import copy
 from collections import OrderedDict
 
 from .. import definitions as xrsdefs
+from ._records import reconcile, snapshot
 
 
 class Population(object):
 
     def __init__(self, structure, form, settings={}, parameters={}):
-        self.structure = None
-        self.form = None
-        self.settings = OrderedDict()
-        self.parameters = OrderedDict()
-        self.set_structure(structure)
-        self.set_form(form)
+        self.structure, self.form = None, None
+        self.settings, self.parameters = OrderedDict(), OrderedDict()
+        self._reconfigure(structure=structure)
+        self._reconfigure(form=form)
         self.update_settings(settings)
         self.update_parameters(parameters)
 
     # -- structure / form ---------------------------------------------------------------
-    def set_structure(self, structure):
-        xrsdefs.validate(structure, self.form, self.settings)
-        self.structure = structure
+    def _reconfigure(self, **change):
+        """Switch structure or form: validate against the other one and the current settings first
+        (an illegal combination must leave the object untouched), then rebuild settings and parameters."""
+        target = dict(structure=self.structure, form=self.form)
+        target.update(change)
+        xrsdefs.validate(target['structure'], target['form'], self.settings)
+        self.structure, self.form = target['structure'], target['form']
         self.update_settings()
         self.update_parameters()
 
+    def set_structure(self, structure):
+        self._reconfigure(structure=structure)
+
     def set_form(self, form):
-        xrsdefs.validate(self.structure, form, self.settings)
-        self.form = form
-        self.update_settings()
-        self.update_parameters()
+        self._reconfigure(form=form)
 
     # -- settings -----------------------------------------------------------------------
     def update_settings(self, new_settings={}):
@@ -66,37 +69,23 @@ class Population(object):
     def update_parameters(self, new_params={}):
         """Keep exactly the parameters valid for the current settings (reference
         population.py:63-82); unknown names raise ValueError."""
-        valid = xrsdefs.all_params(self.structure, self.form, self.settings)
-        for name in new_params:
-            if name not in valid:
-                raise ValueError('Parameter {} is not valid for structure: {}, form: {}, settings: {}'.format(
-                    name, self.structure, self.form, self.settings))
-        for name in list(self.parameters.keys()):
-            if name in valid:
-                valid[name].update(self.parameters[name])
-            else:
-                self.parameters.pop(name)
-        for name, rec in new_params.items():
-            valid[name].update(rec)
-        self.parameters.update(valid)
+        reconcile(self.parameters, xrsdefs.all_params(self.structure, self.form, self.settings), new_params,
+                  lambda nm: 'Parameter {} is not valid for structure: {}, form: {}, settings: {}'.format(
+                      nm, self.structure, self.form, self.settings))
 
     # -- (de)serialisation --------------------------------------------------------------
+    _APPLY = (('structure', 'set_structure'), ('form', 'set_form'),
+              ('settings', 'update_settings'), ('parameters', 'update_parameters'))
+
     def to_dict(self):
-        return dict(
-            structure=copy.copy(self.structure),
-            form=copy.copy(self.form),
-            settings=dict((k, copy.copy(v)) for k, v in self.settings.items()),
-            parameters=dict((k, copy.deepcopy(v)) for k, v in self.parameters.items()))
+        return {'structure': self.structure, 'form': self.form,
+                'settings': {k: copy.copy(v) for k, v in self.settings.items()},
+                'parameters': snapshot(self.parameters)}
 
     def update_from_dict(self, d):
-        if 'structure' in d:
-            self.set_structure(d['structure'])
-        if 'form' in d:
-            self.set_form(d['form'])
-        if 'settings' in d:
-            self.update_settings(d['settings'])
-        if 'parameters' in d:
-            self.update_parameters(d['parameters'])
+        for key, method in self._APPLY:     # in this order: each step narrows what the next may contain
+            if key in d:
+                getattr(self, method)(d[key])
 
     @classmethod
     def from_dict(cls, d):
