@@ -416,7 +416,7 @@ def dump_systems():
     np.savez_compressed(os.path.join(OUT, "systems.npz"), **arrays)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--all-fixtures" not in sys.argv:
     os.makedirs(OUT, exist_ok=True)
     dump_definitions()
     dump_kernels()
@@ -424,3 +424,29 @@ if __name__ == "__main__":
     dump_systems()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
+
+
+def dump_all_fixtures():
+    """tests/golden/fixtures_all.{json.gz,npz}: every fitted System of the reference's
+    tests/test_data/dataset_*/ (753 files) with the reference's I(q) on the 560-point fixture grid.
+    Run with `python oracle/make_golden.py --all-fixtures` (about 25 s)."""
+    import gzip
+    paths = sorted(glob.glob(os.path.join(ref_shim.REFERENCE_ROOT, "tests", "test_data", "dataset_*", "*", "*.yml")))
+    q = np.loadtxt(os.path.join(ref_shim.REFERENCE_ROOT, "tests", "test_data", "solution_saxs", "spheres", "spheres_0.dat"),
+                   skiprows=1)[:, 0]
+    meta, arrs = [], {"q": q}
+    for i, p in enumerate(paths):
+        with open(p) as f:
+            s = System(**yaml.safe_load(f))
+        with np.errstate(all="ignore"):
+            arrs["I%04d" % i] = s.compute_intensity(q)
+        d = jsonable(s.to_dict())
+        d.pop("features", None)
+        meta.append(dict(name=os.path.relpath(p, os.path.join(ref_shim.REFERENCE_ROOT, "tests", "test_data")), system=d))
+    with gzip.open(os.path.join(OUT, "fixtures_all.json.gz"), "wt") as f:
+        json.dump(meta, f, separators=(",", ":"))
+    np.savez_compressed(os.path.join(OUT, "fixtures_all.npz"), **arrs)
+
+
+if __name__ == "__main__" and "--all-fixtures" in sys.argv:
+    dump_all_fixtures()

@@ -385,3 +385,32 @@ def test_crystal_batch_properties_full_size(eng):
     # parts are differences of running totals: the untouched population agrees to the rounding of the totals
     np.testing.assert_allclose(parts2[:, 2].cpu().numpy(), parts[:, 2].cpu().numpy(), rtol=0,
                                atol=1e-13 * float(tot.max()) * 3)
+
+
+def test_all_753_fixture_systems(eng):
+    """The reference's whole corpus of fitted systems (tests/test_data/dataset_1 and _2, 753 files: diffuse /
+    disordered / crystalline mixes, both noise models, sigma from 8e-10 to 1.95, hwhm from 1e-9): I(q) one by
+    one through System.compute_intensity, and once more through the layout-grouping batch loader."""
+    import gzip
+    import json
+    import os
+    from conftest import GOLDEN, _unjson
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200.tools import ymltools
+    with gzip.open(os.path.join(GOLDEN, "fixtures_all.json.gz"), "rt") as f:
+        meta = _unjson(json.load(f))
+    arr = np.load(os.path.join(GOLDEN, "fixtures_all.npz"))
+    q = arr["q"]
+    assert len(meta) == 753
+    systems, worst = [], 0.0
+    for i, m in enumerate(meta):
+        s = System(**m["system"])
+        systems.append(s)
+        err, same = rel_err(s.compute_intensity(q), arr["I%04d" % i])
+        assert same and err <= TOL_F64, (m["name"], err)
+        worst = max(worst, err)
+    I = ymltools.compute_intensity_many(systems, q)
+    for i in range(len(meta)):
+        err, same = rel_err(I[i], arr["I%04d" % i])
+        assert same and err <= TOL_F64, (meta[i]["name"], err)
+    print("753 fixture systems: worst relative error %.2e" % worst)

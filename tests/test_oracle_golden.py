@@ -131,3 +131,20 @@ def test_kat9_kat10_kat11(golden_systems, ref_tables):
                   "parameters": {"I0": 1.0, "r": 21.0}}}
     Ic = orc.system_intensity(q, sysd, **ref_tables)
     assert orc.residual(q, Iobs, Ic) == pytest.approx(0.011354578266228588, rel=1e-13)
+
+
+def test_oracle_on_the_full_fixture_corpus(ref_tables):
+    """Every 5th of the 753 fitted fixture systems (all of them are checked against the CUDA engine in the
+    GPU suite): the oracle reproduces the reference's I(q) bit for bit."""
+    import gzip
+    import json
+    import os
+    from conftest import GOLDEN, _unjson
+    with gzip.open(os.path.join(GOLDEN, "fixtures_all.json.gz"), "rt") as f:
+        meta = _unjson(json.load(f))
+    arr = np.load(os.path.join(GOLDEN, "fixtures_all.npz"))
+    q = arr["q"]
+    for i in range(0, len(meta), 5):
+        with np.errstate(all="ignore"):
+            I = orc.system_intensity(q, meta[i]["system"], **ref_tables)
+        np.testing.assert_array_equal(I, arr["I%04d" % i], err_msg=meta[i]["name"])
