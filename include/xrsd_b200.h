@@ -125,6 +125,10 @@ typedef struct xrsd_tables {
   int32_t *shell_hkl;          /* [n_tables][cap_shell][4]: representative h,k,l, sum of multiplicities */
   double *shell_geo;           /* [n_tables][cap_shell][n_pairs_max]: sum mult*Re(G_a conj G_b)          */
   int32_t *refl_hkl;           /* [n_tables][cap_refl][4]: h,k,l,mult in reference order (optional)       */
+  void *big_scratch;           /* optional: [n_tables] regions of xrsd_table_scratch_bytes(cap_big) bytes in global
+                                  memory, used by a table whose reduced list exceeds the shared-memory capacity
+                                  (large cells without usable symmetry); cap_big is a power of two              */
+  int64_t cap_big;
 } xrsd_tables_t;
 
 /* objective flags of xrsd_residual_batch (System.fit_report, system/__init__.py:23-28) */
@@ -140,6 +144,9 @@ const char *xrsd_last_error(void);
 int xrsd_abi_version(void);
 /* sizeof() of the structs above as compiled, so a binding can verify its mirror */
 int xrsd_struct_sizes(int32_t *sizeof_pop, int32_t *sizeof_layout, int32_t *sizeof_tables, int32_t *sizeof_objective);
+
+/* Bytes of one table's region in xrsd_tables_t.big_scratch for a reduced list of up to cap_big reflections. */
+int64_t xrsd_table_scratch_bytes(int64_t cap_big);
 
 /* Dynamic shared memory the table builder needs for the largest candidate box of a
  * batch, given the per-axis half-widths n1,n2,n3 (scattering/__init__.py:266-268). */

@@ -414,3 +414,27 @@ def test_all_753_fixture_systems(eng):
         err, same = rel_err(I[i], arr["I%04d" % i])
         assert same and err <= TOL_F64, (meta[i]["name"], err)
     print("753 fixture systems: worst relative error %.2e" % worst)
+
+
+def test_large_cell_without_usable_symmetry(ref_tables, eng):
+    """> 4096 reflections in the reduced list (orthorhombic cell, point group mmm: the reference defines no
+    operations for it): the table builder moves its sort / shell arrays to global memory; thousands of shells
+    take the chunked direct sum.  Against the oracle, intensity and reflection count."""
+    from oracle import xrsd_oracle as orc
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import lowering
+    s = System(x=dict(structure="crystalline", form="spherical",
+                      settings={"lattice": "P_orthorhombic", "space_group": "Pmmm", "q_max": 0.9, "profile": "voigt"},
+                      parameters={"a": {"value": 60.0}, "b": {"value": 70.0}, "c": {"value": 80.0}, "r": {"value": 12.0},
+                                  "hwhm_g": {"value": 0.004}, "hwhm_l": {"value": 0.003}}),
+               source_wavelength=0.8265617)
+    q = np.linspace(0.05, 0.9, 500)
+    lay = lowering.lower_system(s, q)
+    T = eng.build_tables(lay, eng.to_device(lay.values[None, :]), 1, params_host=lay.values[None, :])
+    hkl, mult, _ = orc.reflection_table("P_orthorhombic", dict(a=60.0, b=70.0, c=80.0), 0.0, 0.9, "mmm")
+    assert hkl.shape[0] > 4096
+    assert int(T.n_refl[0].item()) == hkl.shape[0] == int(T.n_all[0].item())
+    assert int(T.n_shell[0].item()) > 400          # 8 sign combinations share each |G|
+    ref = orc.system_intensity(q, s.to_dict(), **ref_tables)
+    err, same = rel_err(s.compute_intensity(q), ref)
+    assert same and err <= TOL_F64, err

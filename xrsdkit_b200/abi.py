@@ -45,7 +45,8 @@ class Layout(C.Structure):
 class Tables(C.Structure):
     _fields_ = [("cap_shell", i32), ("cap_refl", i32), ("n_pairs_max", i32), ("cap_list_hint", i32),
                 ("n_shell", C.c_void_p), ("n_refl", C.c_void_p), ("n_all", C.c_void_p), ("status", C.c_void_p),
-                ("shell_hkl", C.c_void_p), ("shell_geo", C.c_void_p), ("refl_hkl", C.c_void_p)]
+                ("shell_hkl", C.c_void_p), ("shell_geo", C.c_void_p), ("refl_hkl", C.c_void_p),
+                ("big_scratch", C.c_void_p), ("cap_big", C.c_int64)]
 
 
 class Objective(C.Structure):
@@ -59,6 +60,7 @@ _SIGNATURES = {
     "xrsd_abi_version": (C.c_int, []),
     "xrsd_struct_sizes": (C.c_int, [C.POINTER(i32)] * 4),
     "xrsd_table_smem_bytes": (C.c_int64, [i32, i32, i32]),
+    "xrsd_table_scratch_bytes": (C.c_int64, [C.c_int64]),
     "xrsd_reflection_tables": (C.c_int, [C.POINTER(Layout), vp, i32, i32, C.POINTER(Tables), i32, vp, vp]),
     "xrsd_intensity_batch": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, C.POINTER(Tables), vp, C.c_int64, vp]),
     "xrsd_intensity_components_batch": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, C.POINTER(Tables), vp, C.c_int64,

@@ -11,6 +11,7 @@
 
 extern "C" {
 int64_t xrsd_table_smem_layout(int32_t max_cells, int32_t cap_list);
+int64_t xrsd_table_scratch_bytes(int64_t cap_big);
 cudaError_t xrsd_launch_tables(const xrsd_layout_t *, const double *, int, int, const xrsd_tables_t *, int, int, const uint8_t *,
                                cudaStream_t);
 cudaError_t xrsd_launch_intensity(const xrsd_layout_t *, const double *, int, const double *, int, int, const xrsd_tables_t *,
@@ -454,14 +455,34 @@ int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int3
     T.cap_shell = cap_shell; T.cap_refl = 0; T.n_pairs_max = n_pairs;
     T.n_shell = (int32_t *)(base + o_ns); T.n_refl = (int32_t *)(base + o_nr); T.n_all = (int32_t *)(base + o_na);
     T.status = (int32_t *)(base + o_st); T.shell_hkl = (int32_t *)(base + o_sh); T.shell_geo = (double *)(base + o_sg);
-    rc = xrsd_reflection_tables(layout, (const double *)(base + o_p), ld_params, batch, &T, max_cells, nullptr, s);
+    void *big = nullptr;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      rc = xrsd_reflection_tables(layout, (const double *)(base + o_p), ld_params, batch, &T, max_cells, nullptr, s);
+      if (rc) break;
+      std::vector<int32_t> st(n_tab), na(n_tab);
+      e = cudaMemcpyAsync(st.data(), T.status, n_tab * 4, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(na.data(), T.n_all, n_tab * 4, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) { rc = cuda_fail(e, "table status copy"); break; }
+      int worst = 0, n_max = 0;
+      for (size_t i = 0; i < n_tab; ++i) { worst |= st[i]; n_max = std::max(n_max, na[i]); }
+      if (worst == 0) break;
+      if (worst == XRSD_TABLE_LIST_OVERFLOW && attempt == 0) {
+        // large cell without usable symmetry: give the builder global scratch for its sort / shell arrays
+        int64_t cap_big = 8192;
+        while (cap_big < n_max) cap_big <<= 1;
+        e = cudaMalloc(&big, (size_t)(n_tab * xrsd_table_scratch_bytes(cap_big)));
+        if (e != cudaSuccess) { rc = fail(XRSD_ENOMEM, "cudaMalloc(table scratch): %s", cudaGetErrorString(e)); break; }
+        T.big_scratch = big;
+        T.cap_big = cap_big;
+        T.cap_list_hint = 4096;
+        continue;
+      }
+      rc = fail(XRSD_ECAPACITY, "reflection table: status %d (capacity exceeded)", worst);
+      break;
+    }
+    if (big) { cudaStreamSynchronize(s); cudaFree(big); }
     if (rc) return rc;
-    std::vector<int32_t> st(n_tab);
-    e = cudaMemcpyAsync(st.data(), T.status, n_tab * 4, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) return cuda_fail(e, "table status copy");
-    for (size_t i = 0; i < n_tab; ++i)
-      if (st[i]) return fail(XRSD_ECAPACITY, "reflection table %zu: status %d (capacity exceeded)", i, st[i]);
   }
   rc = xrsd_intensity_batch(layout, (const double *)(base + o_q), n_q, (const double *)(base + o_p), ld_params, batch,
                             n_x ? &T : nullptr, (double *)(base + o_I), n_q, s);

@@ -23,6 +23,11 @@ namespace xrsd {
 
 constexpr int TABLE_THREADS = 256;
 
+__host__ __device__ inline long long xrsd_scratch_bytes(long long cap_big) {
+  // keys f64[cap] + list_cell i32[cap] + sidx i32[cap] + seg_start i32[cap + 2] + msum i32[cap], 16-byte multiple
+  return ((cap_big * 24 + 8) + 15) & ~15LL;
+}
+
 struct TableShared {
   Cell cell;
   double g_min, g_max;
@@ -103,6 +108,7 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
   int *seg_start = reinterpret_cast<int *>(smem_raw + off);   // [cap_list + 1]
   off += ((size_t)cap_list + 1) * sizeof(int);
   int *msum_s = reinterpret_cast<int *>(smem_raw + off);      // [cap_list]
+  long long cap_eff = cap_list;                                // capacity of the five arrays above
 
   if (tid == 0) {
     make_cell(pop, prm, &S.cell);
@@ -266,10 +272,26 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
     int pos = scan_sm[tid] - cnt;
     if (tid == TABLE_THREADS - 1) {
       S.n_red = scan_sm[tid];
-      if (S.n_red > cap_list) S.status |= XRSD_TABLE_LIST_OVERFLOW;
+      if (S.n_red > cap_list && !(T.big_scratch != nullptr && (long long)S.n_red <= T.cap_big))
+        S.status |= XRSD_TABLE_LIST_OVERFLOW;
     }
     __syncthreads();
     if (S.status != 0) { finish(0); return; }
+    if (S.n_red > cap_list) {
+      // a reduced list too long for shared memory (large cell, no usable symmetry): the same arrays in this
+      // table's region of the caller's global scratch -- slow, but correct and rare
+      unsigned char *g = reinterpret_cast<unsigned char *>(T.big_scratch) + (size_t)t * (size_t)xrsd_scratch_bytes(T.cap_big);
+      keys = reinterpret_cast<double *>(g);
+      g += (size_t)T.cap_big * sizeof(double);
+      list_cell = reinterpret_cast<int *>(g);
+      g += (size_t)T.cap_big * sizeof(int);
+      sidx = reinterpret_cast<int *>(g);
+      g += (size_t)T.cap_big * sizeof(int);
+      seg_start = reinterpret_cast<int *>(g);
+      g += ((size_t)T.cap_big + 2) * sizeof(int);
+      msum_s = reinterpret_cast<int *>(g);
+      cap_eff = T.cap_big;
+    }
     for (int c = c_lo; c < c_hi; ++c) {
       const unsigned m = grid[c];
       if (!m) continue;
@@ -343,7 +365,7 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
     if (r < n_red) head = (r == 0) || (keys[r] - keys[r - 1] > 8.9e-16 * keys[r]);
     int base;
     const int pos = block_flag_scan(S, head, base) + base;
-    if (head && pos < cap_list) seg_start[pos] = r;
+    if (head && pos < cap_eff) seg_start[pos] = r;
   }
   if (tid == 0) {
     S.n_shell_raw = S.scan_carry;
@@ -351,7 +373,7 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
     const int npair = pop.n_species * (pop.n_species + 1) / 2;
     // shells are staged in shared memory (over the sort keys) and only the kept ones go to the output
     // arrays; if they do not fit there, the raw list itself must fit the output capacity
-    if ((long long)S.n_shell_raw * npair > (long long)cap_list && S.n_shell_raw > T.cap_shell) S.status |= XRSD_TABLE_SHELL_OVERFLOW;
+    if ((long long)S.n_shell_raw * npair > cap_eff && S.n_shell_raw > T.cap_shell) S.status |= XRSD_TABLE_SHELL_OVERFLOW;
     seg_start[S.n_shell_raw] = n_red;
   }
   __syncthreads();
@@ -363,7 +385,7 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
   double *o_geo = T.shell_geo + (size_t)t * T.cap_shell * T.n_pairs_max;
 
   // per-shell geometric weights: sum_members mult * Re(G_a conj G_b)  (scattering/__init__.py:312-331)
-  const bool staged = (long long)n_raw * n_pairs <= (long long)cap_list;
+  const bool staged = (long long)n_raw * n_pairs <= cap_eff;
   double *geo_s = keys;                         // the sort keys are no longer needed
   double my_max = 0.0;
   for (int s = tid; s < n_raw; s += TABLE_THREADS) {
@@ -475,6 +497,8 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
 }
 
 }  // namespace xrsd
+
+extern "C" int64_t xrsd_table_scratch_bytes(int64_t cap_big) { return (int64_t)xrsd::xrsd_scratch_bytes(cap_big); }
 
 extern "C" int64_t xrsd_table_smem_layout(int32_t max_cells, int32_t cap_list) {
   size_t off = ((size_t)max_cells * sizeof(uint16_t) + 15) & ~(size_t)15;

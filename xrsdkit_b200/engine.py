@@ -100,6 +100,7 @@ class Engine(object):
         n_tables = batch * layout.n_xtal
         cap_refl = 4096 if export_reflections else 0
         cap_list = 0
+        cap_big = 0
         while True:
             if reuse is not None and reuse.n_tables == n_tables and reuse.cap_refl == cap_refl and reuse.cap_shell >= cap_shell:
                 T, cap_shell = reuse, reuse.cap_shell
@@ -107,6 +108,9 @@ class Engine(object):
                 T = TableSet(torch, self.device, n_tables, cap_shell, self._n_pairs(layout), cap_refl)
             reuse = None
             T.c.cap_list_hint = cap_list
+            if cap_big:
+                T.big = torch.empty(n_tables * int(self.lib.xrsd_table_scratch_bytes(cap_big)), dtype=torch.uint8, device=self.device)
+                T.c.big_scratch, T.c.cap_big = T.big.data_ptr(), cap_big
             abi.check(self.lib.xrsd_reflection_tables(C.byref(layout.c), d_params.data_ptr(), d_params.shape[1], batch,
                                                       C.byref(T.c), max_cells,
                                                       active.data_ptr() if active is not None else None, self._stream()))
@@ -124,8 +128,14 @@ class Engine(object):
                 if cap_list < 4096:
                     cap_list = 4096
                     continue
-                raise abi.XrsdError("more than 4096 reduced reflections in one table (no usable symmetry?)")
-            if st & abi.TABLE_SHELL_OVERFLOW and cap_shell < 4096:
+                if not cap_big and cap_refl == 0:
+                    # large cell without usable symmetry: sort / shell arrays of those tables go to global memory
+                    n_max = int(T.n_all.max().item())
+                    cap_big = 1 << max(13, (n_max - 1).bit_length())
+                    if cap_big <= (1 << 18):
+                        continue
+                raise abi.XrsdError("reduced reflection list too long (%d reflections in the shell)" % int(T.n_all.max().item()))
+            if st & abi.TABLE_SHELL_OVERFLOW and cap_shell < 65536:
                 cap_shell *= 4
                 continue
             raise abi.XrsdError("reflection table build failed with status %d" % st)
@@ -182,8 +192,12 @@ class Engine(object):
         vals = np.ascontiguousarray(layout.values, dtype=np.float64)
         out = np.empty(q.size)
         self.torch.cuda.set_device(self.device)
-        abi.check(self.lib.xrsd_intensity_batch_host(C.byref(layout.c), q.ctypes.data, q.size, vals.ctypes.data, vals.size, 1,
-                                                     out.ctypes.data, q.size))
+        rc = self.lib.xrsd_intensity_batch_host(C.byref(layout.c), q.ctypes.data, q.size, vals.ctypes.data, vals.size, 1,
+                                                out.ctypes.data, q.size)
+        if rc == abi.ECAPACITY and layout.n_xtal:
+            # the host path's fixed table capacities were exceeded (very many shells): the device API grows them
+            return self.intensity(layout, q, vals[None, :])[0].cpu().numpy()
+        abi.check(rc)
         self.launches += 1 + (1 if layout.n_xtal else 0)
         return out
 
