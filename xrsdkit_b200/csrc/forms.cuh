@@ -90,12 +90,11 @@ __device__ __forceinline__ HSConst hs_constants(double r_hard, double v_fraction
 // unfused in the reference's order (an FMA contraction there would move the result
 // by more than the tolerance at small qd); their quotients by qd^3, qd^4, qd^6 are taken through
 // one reciprocal of qd, which perturbs each O(1) bracket by ~1 ulp and is not amplified.
-__device__ __forceinline__ double hard_sphere_nc(double q, const HSConst &k, bool is_q0_zero) {
+// (s, c) = sin, cos of q d, supplied by the caller (who may carry them from span to span by rotation)
+__device__ __forceinline__ double hard_sphere_nc(double q, const HSConst &k, bool is_q0_zero, double s, double c) {
   if (is_q0_zero) return k.nc0;
   const double qd = q * k.d;
   const double qd2 = __dmul_rn(qd, qd), qd3 = __dmul_rn(qd2, qd), qd4 = __dmul_rn(qd2, qd2);
-  double s, c;
-  sincos(qd, &s, &c);
   const double p = k.p;
   const double r1 = 1.0 / qd, r2 = r1 * r1, r3 = r2 * r1, r4 = r2 * r2, r6 = r3 * r3;
   const double x1 = __dsub_rn(s, __dmul_rn(qd, c)) * r3;

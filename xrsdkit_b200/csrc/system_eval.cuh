@@ -213,14 +213,16 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         __syncthreads();
         // On a uniform q grid consecutive spans of one thread differ by span*q_step, so the starting
         // phases (q r_first, q dstep) of the next span follow from the previous ones by a fixed rotation
-        double s0[QPT], c0[QPT], sd0[QPT], cd0[QPT];
-        double rot_s = 0.0, rot_c = 1.0, rotd_s = 0.0, rotd_c = 1.0;
+        double s0[QPT], c0[QPT], sd0[QPT], cd0[QPT], sh[QPT], ch[QPT];
+        double rot_s = 0.0, rot_c = 1.0, rotd_s = 0.0, rotd_c = 1.0, roth_s = 0.0, roth_c = 1.0;
         const bool carry = quad && (L.q_step > 0.0);
+        const bool carry_hs = pop.disordered && (L.q_step > 0.0);     // same for sin/cos(q d) of the hard-sphere S(q)
         if (carry) {
           const double dq = (double)span * L.q_step;
           sincos(dq * r_first, &rot_s, &rot_c);
           sincos(dq * dstep, &rotd_s, &rotd_c);
         }
+        if (carry_hs) sincos((double)span * L.q_step * hs.d, &roth_s, &roth_c);
         for (int off = 0; off < q_count; off += span) {
           double qv[QPT], ff2[QPT], den[QPT];
           bool ok[QPT], q0[QPT];
@@ -302,6 +304,18 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               den[j] = q0[j] ? 1.0 : (q2 * q2 * q2) * norm;
             }
           }
+          if (pop.disordered) {
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) {
+              if (carry_hs && off > 0) {
+                const double sn = fma(sh[j], roth_c, ch[j] * roth_s);
+                ch[j] = fma(ch[j], roth_c, -(sh[j] * roth_s));
+                sh[j] = sn;
+              } else {
+                sincos(qv[j] * hs.d, &sh[j], &ch[j]);
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < QPT; ++j) {
             if (!ok[j]) continue;
@@ -309,7 +323,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
             double num = I0 * ff2[j], dn = den[j];
             if (pop.disordered) {                                  // I0 * sf * ff_sqr, sf = (1-nc0)/(1-nc)
               num *= (1.0 - hs.nc0);
-              dn *= (1.0 - hard_sphere_nc(qv[j], hs, q0[j]));
+              dn *= (1.0 - hard_sphere_nc(qv[j], hs, q0[j], sh[j], ch[j]));
             }
             I_sm[i] += num / dn;
           }
