@@ -489,6 +489,33 @@ def run_gpu_arm(args):
             except Exception as e:      # a secondary measurement must not take the headline down
                 secondary[name] = {"error": repr(e)}
 
+        try:        # featuriser over this workload's own patterns, with 2 % noise
+            g = torch.Generator(eng.device).manual_seed(7)
+            pats = W.outs[0] * (1 + 0.02 * torch.randn(W.outs[0].shape, dtype=torch.float64, device=eng.device, generator=g))
+            f_out = eng.features(W.d_q, pats)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                eng.features(W.d_q, pats, out=f_out)
+            e1.record()
+            torch.cuda.synchronize()
+            msf = e0.elapsed_time(e1) / 3
+            secondary["features"] = {"workload": "profile_pattern (21 features) of %d noisy cfg2 patterns, n_q=%d" % (B, n_q),
+                                     "unit": "patterns/s", "value": B / (msf * 1e-3), "ms_per_step": msf,
+                                     "read_GBps": B * n_q * 8 / (msf * 1e-3) / 1e9}
+            if not args.no_cpu:
+                from oracle import xrsd_oracle as xo
+                hp = pats[:2].cpu().numpy()
+                t0 = time.perf_counter()
+                ref_f = np.stack([xo.profile_pattern(W.q, row) for row in hp])
+                secondary["features"]["cpu_patterns_per_s_1core"] = 2 / (time.perf_counter() - t0)
+                secondary["features"]["max_rel_diff_vs_oracle"] = float(np.max(
+                    np.abs(f_out[:2].cpu().numpy() - ref_f)[:, :13] / np.abs(ref_f[:, :13])))
+            del pats
+        except Exception as e:
+            secondary["features"] = {"error": repr(e)}
+
     # ---- CPU baseline: bounded sample on the host cores
     cores = host_cores()
     per_core = {"cfg2": 256, "cfg3": 4, "cfg4": 4, "cfg5": 4}[args.workload]     # ~10-30 core-seconds per core in total

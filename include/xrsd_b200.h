@@ -233,6 +233,18 @@ void xrsd_release_workspace(void);
 int xrsd_peak_profile(int32_t kind, double hwhm_or_hwhm_g, double hwhm_l, const double *d_x, int32_t n,
                       double *d_out, void *stream);
 
+/* Pattern featuriser: the 21 scale-free features of a pattern (q, I), in the order of
+ * XRSD_N_FEATURES / the reference's profile_keys.  <- tools/profiler.py:64-221 (profile_pattern),
+ * tools/peak_math.py:87-123 (humpness), tools/__init__.py:83-102 (pearson); the reference calls it
+ * after every fit (system/__init__.py:276).  q[n_q] is shared by the batch; pattern b is
+ * d_I + b*ld_I; features of pattern b go to d_features + b*ld_features (>= 21 doubles).
+ * 8 <= n_q <= XRSD_FEATURE_MAX_Q (the pattern is held in shared memory, 26 bytes per point).
+ * Degenerate patterns give NaN features where the reference raises or warns. */
+#define XRSD_N_FEATURES 21
+#define XRSD_FEATURE_MAX_Q 8192
+int xrsd_feature_batch(const double *d_q, int32_t n_q, const double *d_I, int64_t ld_I, int32_t batch,
+                       double *d_features, int64_t ld_features, void *stream);
+
 /* FP64 pipe probe used by bench.py for the roofline denominator: runs a DFMA-bound
  * kernel and returns the measured TFLOP/s (2 flop per DFMA) on the current device. */
 int xrsd_probe_fp64_peak(double *tflops, double *elapsed_ms, void *stream);

@@ -416,7 +416,7 @@ def dump_systems():
     np.savez_compressed(os.path.join(OUT, "systems.npz"), **arrays)
 
 
-if __name__ == "__main__" and "--all-fixtures" not in sys.argv:
+if __name__ == "__main__" and "--all-fixtures" not in sys.argv and "--features" not in sys.argv:
     os.makedirs(OUT, exist_ok=True)
     dump_definitions()
     dump_kernels()
@@ -450,3 +450,42 @@ def dump_all_fixtures():
 
 if __name__ == "__main__" and "--all-fixtures" in sys.argv:
     dump_all_fixtures()
+
+
+def dump_features():
+    """tests/golden/features.npz: the reference's profile_pattern (tools/profiler.py:64) on the seven
+    measured patterns of tests/test_data/solution_saxs (stored with their q, I) and on the clean and
+    noisy I(q) of every case in systems.npz.  Run with `python oracle/make_golden.py --features`."""
+    import warnings
+    from xrsdkit.tools import profiler
+    warnings.simplefilter("ignore")
+    arrs = {}
+    files = sorted(glob.glob(os.path.join(ref_shim.REFERENCE_ROOT, "tests", "test_data", "solution_saxs", "*", "*.dat")))
+    for i, p in enumerate(files):
+        a = np.loadtxt(p)
+        arrs["meas%d_q" % i], arrs["meas%d_I" % i] = a[:, 0], a[:, 1]
+        arrs["meas%d_f" % i] = np.array(list(profiler.profile_pattern(a[:, 0], a[:, 1]).values()), dtype=float)
+    Z = np.load(os.path.join(OUT, "systems.npz"))
+    with open(os.path.join(OUT, "systems.json")) as f:
+        meta = json.load(f)
+    n = 0
+    for m in meta:
+        q = Z[m["q"]]
+        for tag in ("I", "Iobs"):
+            I = Z[m["key"] + "_" + tag]
+            if not np.all(np.isfinite(I)) or np.sum(I > 0) < 8:
+                continue
+            with np.errstate(all="ignore"):
+                try:
+                    f = np.array(list(profiler.profile_pattern(q, I).values()), dtype=float)
+                except Exception as e:           # degenerate patterns the reference itself cannot profile
+                    print("skip", m["key"], tag, type(e).__name__)
+                    continue
+            arrs[m["key"] + "_f" + tag] = f
+            n += 1
+    np.savez_compressed(os.path.join(OUT, "features.npz"), **arrs)
+    print("features:", len(files), "measured +", n, "computed patterns")
+
+
+if __name__ == "__main__" and "--features" in sys.argv:
+    dump_features()

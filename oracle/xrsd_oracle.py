@@ -561,3 +561,110 @@ def residual(q, I, I_comp, dI=None, error_weighted=True, logI_weighted=True,
         fit = fit & (I_comp > 0)
         return chi2(np.log(I_comp[fit]), np.log(I[fit]), wts[fit])
     return chi2(I_comp[fit], I[fit], wts[fit])
+
+
+# --------------------------------------------------------------------------------------
+# pattern featuriser (reference: tools/profiler.py:64-221, tools/peak_math.py:87-123,
+#                     tools/__init__.py:83-102); called by fit() at system/__init__.py:276
+# --------------------------------------------------------------------------------------
+
+PROFILE_KEYS = (
+    "Imax_over_Imean", "Ilowq_over_Imean", "Imax_sharpness", "I_fluctuation", "logI_fluctuation",
+    "logI_max_over_std", "r_fftIcentroid", "q_Icentroid", "q_logIcentroid", "pearson_q", "pearson_q2",
+    "pearson_expq", "pearson_invexpq", "q_best_hump", "q_best_trough", "best_hump_qwidth",
+    "best_trough_qwidth", "q_best_hump_log", "q_best_trough_log", "best_hump_qwidth_log",
+    "best_trough_qwidth_log")
+
+
+def pearson_r(u, v):
+    """reference: tools/__init__.py:83-102 (centred sums, no 1/n factors)."""
+    du = u - np.mean(u)
+    dv = v - np.mean(v)
+    return np.sum(du * dv) / (np.sqrt(np.sum(du ** 2)) * np.sqrt(np.sum(dv ** 2)))
+
+
+def _trapezoid_centroid(x, y):
+    """(sum of x_mid*dx*y_mid) / (sum of dx*y_mid); reference: profiler.py:124-137."""
+    dx = np.diff(x)
+    ym = 0.5 * (y[1:] + y[:-1])
+    xm = 0.5 * (x[1:] + x[:-1])
+    return np.sum(xm * dx * ym) / np.sum(dx * ym)
+
+
+def _turning_sum(y):
+    """Sum of |first differences| at the first point and wherever the difference changes
+    sign against its predecessor; reference: profiler.py:140-150."""
+    d = np.diff(y)
+    keep = np.ones(len(d), dtype=bool)
+    keep[1:] = d[1:] * d[:-1] < 0
+    return np.sum(np.abs(d[keep]))
+
+
+def hump_trough_scores(x, y, w=50):
+    """reference: tools/peak_math.py:87-123.  For every point, the Pearson correlation of the
+    values in a +-w window with the squared distance from the point; hump score = -y*r,
+    trough score = std(window)*r."""
+    n = len(y)
+    hump = np.zeros(n)
+    trough = np.zeros(n)
+    for i in range(n):
+        lo, hi = max(0, i - w), min(n, i + w + 1)
+        yw = y[lo:hi]
+        r = pearson_r(yw, (x[lo:hi] - x[i]) ** 2)
+        hump[i] = -1 * y[i] * r
+        trough[i] = np.std(yw) * r
+    return hump, trough
+
+
+def _parabola(x, y):
+    """Vertex abscissa and focal width of the degree-2 least-squares fit (np.polyfit as in the
+    reference, profiler.py:181-196)."""
+    p = np.polyfit(x, y, 2)
+    return -1 * p[1] / (2 * p[0]), abs(1.0 / p[0])
+
+
+def profile_pattern(q, I):
+    """The 21 features of reference tools/profiler.py:64-221, as an array in PROFILE_KEYS order."""
+    q = np.asarray(q, dtype=float)
+    I = np.asarray(I, dtype=float)
+    with np.errstate(all="ignore"):
+        i_max = int(np.argmax(I))
+        I_max, I_min = I[i_max], I[int(np.argmin(I))]
+        I_mean, I_std = np.mean(I), np.std(I)
+        q_mean, q_std = np.mean(q), np.std(q)
+        Is = (I - I_mean) / I_std
+        qs = (q - q_mean) / q_std
+        low = q < q[0] + 0.1 * (q[-1] - q[0])
+        pos = I > 0
+        q_p, qs_p, Is_p = q[pos], qs[pos], Is[pos]
+        L = np.log(I[pos])
+        L_max, L_min, L_std, L_mean = np.max(L), np.min(L), np.std(L), np.mean(L)
+        Ls = (L - L_mean) / L_std
+        near_max = (q > 0.9 * q[i_max]) & (q < 1.1 * q[i_max])
+
+        amp = np.abs(np.fft.fft(I))
+        r = np.fft.fftfreq(q.shape[-1])
+        rp = r > 0
+
+        hump, trough = hump_trough_scores(qs_p, Ls)
+        i_h, i_t = int(np.argmax(hump)), int(np.argmax(trough))
+        sel_h = (q_p > q_p[i_h] - 0.1 * q_std) & (q_p < q_p[i_h] + 0.1 * q_std)
+        sel_t = (q_p > q_p[i_t] - 0.1 * q_std) & (q_p < q_p[i_t] + 0.1 * q_std)
+        vh, wh = _parabola(qs_p[sel_h], Is_p[sel_h])
+        vt, wt = _parabola(qs_p[sel_t], Is_p[sel_t])
+        vhl, whl = _parabola(qs_p[sel_h], Ls[sel_h])
+        vtl, wtl = _parabola(qs_p[sel_t], Ls[sel_t])
+
+        return np.array([
+            I_max / I_mean,
+            np.mean(I[low]) / I_mean,
+            I_max / np.mean(I[near_max]),
+            _turning_sum(I) / (I_max - I_min),
+            _turning_sum(L) / (L_max - L_min),
+            L_max / L_std,
+            _trapezoid_centroid(r[rp], amp[rp]),
+            _trapezoid_centroid(q, I),
+            _trapezoid_centroid(q_p, L),
+            pearson_r(q, I), pearson_r(q ** 2, I), pearson_r(np.exp(q), I), pearson_r(np.exp(-1 * q), I),
+            vh * q_std + q_mean, vt * q_std + q_mean, wh * q_std, wt * q_std,
+            vhl * q_std + q_mean, vtl * q_std + q_mean, whl * q_std, wtl * q_std])

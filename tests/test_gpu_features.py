@@ -1,0 +1,106 @@
+"""Featuriser parity: xrsd_feature_batch against the reference's
+profile_pattern outputs (tests/golden/features.npz, written by oracle/make_golden.py --features)
+and against the oracle restatement on power-of-two and odd pattern lengths."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+# The first 13 features are plain reductions: the FP64 gate of the intensity path (1e-10) applies.
+# The last 8 come from a quadratic least-squares fit through ~30-500 points (vertex -b/2a, width 1/a): on noisy
+# patterns the curvature a is nearly zero and BOTH implementations' round-off (numpy's SVD on the raw Vandermonde
+# matrix, ours on orthogonal polynomials) is amplified; observed worst 1.2e-9, median 1e-13.
+TOL_REDUCTION = 1e-10
+TOL_FIT = 1e-8
+TOL = np.array([TOL_REDUCTION] * 13 + [TOL_FIT] * 8)
+
+
+def _cases():
+    Z = np.load(os.path.join(GOLD, "features.npz"))
+    S = np.load(os.path.join(GOLD, "systems.npz"))
+    import json
+    with open(os.path.join(GOLD, "systems.json")) as f:
+        meta = json.load(f)
+    out = []
+    for i in range(7):
+        out.append(("meas%d" % i, Z["meas%d_q" % i], Z["meas%d_I" % i], Z["meas%d_f" % i]))
+    for m in meta:
+        for tag in ("I", "Iobs"):
+            k = m["key"] + "_f" + tag
+            if k in Z.files:
+                out.append((m["name"] + ":" + tag, S[m["q"]], S[m["key"] + "_" + tag], Z[k]))
+    return out
+
+
+def _feature_errors(row, ref, q, I):
+    """Per-feature error |got - ref| / max(|ref|, floor).  The four vertex features are x*std(q) + mean(q) and
+    cancel to ~0 for Guinier-like patterns (parabola centred on q = 0), so their floor is the q range.  For a
+    constant pattern (flat-noise-only fixtures) the reference's own correlation / Fourier / hump features are
+    rounding noise (0/0), so only the features that stay defined are compared."""
+    floor = np.zeros(21)
+    floor[[13, 14, 17, 18]] = q[-1]
+    err = np.abs(row - ref) / np.maximum(np.abs(ref), np.maximum(floor, 1e-300))
+    keep = np.isfinite(ref)
+    if np.ptp(I) <= 1e-12 * np.max(np.abs(I)):
+        keep &= np.isin(np.arange(21), [0, 1, 2, 7, 8])
+    return np.where(keep, err, 0.0)
+
+
+def test_features_match_reference_outputs():
+    from xrsdkit_b200.tools import profiler
+    cases = _cases()
+    assert len(cases) > 400
+    groups = {}
+    for name, q, I, f in cases:
+        groups.setdefault(q.tobytes(), []).append((name, q, I, f))
+    worst = (0.0, None, None)
+    worst_red = 0.0
+    for g in groups.values():
+        q = g[0][1]
+        got = profiler.profile_batch(q, np.stack([c[2] for c in g])).cpu().numpy()
+        for row, (name, _, I, ref) in zip(got, g):
+            err = _feature_errors(row, ref, q, I)
+            assert np.all(err < TOL), (name, err)
+            j = int(np.argmax(err))
+            worst_red = max(worst_red, float(np.max(err[:13])))
+            if err[j] > worst[0]:
+                worst = (float(err[j]), name, profiler.profile_keys[j])
+    print("worst feature error", worst, "reductions", worst_red, "over", len(cases), "patterns")
+
+
+@pytest.mark.parametrize("n", [8, 64, 560, 1001, 1024, 4096, 8192])
+def test_features_match_oracle_any_length(n):
+    from oracle import xrsd_oracle as xo
+    from xrsdkit_b200.tools import profiler
+    rs = np.random.RandomState(n)
+    q = np.linspace(0.01, 0.6, n)
+    I = np.stack([(3.0 + np.sin(40 * q + p) ** 2) * np.exp(-4 * q) * (1 + 0.05 * rs.randn(n)) + 0.02 for p in (0.0, 1.0, 2.0)])
+    I[1, n // 3] = 0.0                    # a non-positive point: dropped from the log features
+    I[2, ::7] *= -1.0 if n > 64 else 1.0  # many of them
+    got = profiler.profile_batch(q, I).cpu().numpy()
+    for row, Ii in zip(got, I):
+        ref = xo.profile_pattern(q, Ii)
+        ok = np.isfinite(ref)
+        if n <= 64:                       # fit windows hold < 4 points: np.polyfit is rank deficient (RankWarning); reductions still agree
+            ok[13:] = False
+        assert np.all((_feature_errors(row, ref, q, Ii) < TOL)[ok]), (row, ref)
+
+
+def test_profile_pattern_single_call_returns_reference_keys():
+    from xrsdkit_b200.tools import profiler
+    Z = np.load(os.path.join(GOLD, "features.npz"))
+    f = profiler.profile_pattern(Z["meas4_q"], Z["meas4_I"])
+    assert list(f.keys()) == list(profiler.profile_keys)
+    ref = Z["meas4_f"]
+    assert max(abs(f[k] - r) / abs(r) for k, r in zip(profiler.profile_keys, ref)) < TOL_FIT
+
+
+def test_feature_batch_rejects_bad_sizes():
+    from xrsdkit_b200.tools import profiler
+    with pytest.raises(ValueError):
+        profiler.profile_batch(np.linspace(0.1, 1, 9000), np.ones((1, 9000)))
+    with pytest.raises(ValueError):
+        profiler.profile_batch(np.linspace(0.1, 1, 4), np.ones((1, 4)))

@@ -158,6 +158,11 @@ def test_lm_recovers_crystal_systems_and_fit_api(eng):
     assert out.populations["p"].parameters["r"]["value"] == pytest.approx(20.0, rel=2e-3)
     rep = out.fit_report
     assert rep["final_objective"] < rep["initial_objective"] and "fit_snr" in rep and "converged" in rep
+    # fit() also profiles the measured pattern (reference system/__init__.py:276)
+    from oracle import xrsd_oracle as xo
+    feats = np.array([out.features[k] for k in xo.PROFILE_KEYS])
+    want = xo.profile_pattern(qq, I)
+    assert np.max(np.abs(feats - want) / np.maximum(np.abs(want), 1e-3)) < 1e-8
 
 
 def test_observation_shapes_for_batched_residual(eng):

@@ -148,3 +148,26 @@ def test_oracle_on_the_full_fixture_corpus(ref_tables):
         with np.errstate(all="ignore"):
             I = orc.system_intensity(q, meta[i]["system"], **ref_tables)
         np.testing.assert_array_equal(I, arr["I%04d" % i], err_msg=meta[i]["name"])
+
+
+def test_featuriser_oracle_matches_reference_outputs():
+    """oracle.profile_pattern vs the reference's profile_pattern (golden features.npz): the seven measured
+    patterns and every eighth computed pattern (the hump score is a Python loop in both)."""
+    import json
+    import os
+    import warnings
+    warnings.simplefilter("ignore")
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    Z = np.load(os.path.join(gold, "features.npz"))
+    S = np.load(os.path.join(gold, "systems.npz"))
+    with open(os.path.join(gold, "systems.json")) as f:
+        meta = json.load(f)
+    pats = [(Z["meas%d_q" % i], Z["meas%d_I" % i], Z["meas%d_f" % i]) for i in range(7)]
+    keys = [(m, t) for m in meta for t in ("I", "Iobs") if m["key"] + "_f" + t in Z.files]
+    for m, t in keys[::8]:
+        pats.append((S[m["q"]], S[m["key"] + "_" + t], Z[m["key"] + "_f" + t]))
+    for q, I, ref in pats:
+        got = orc.profile_pattern(q, I)
+        ok = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(got), ok)
+        assert np.max(np.abs(got[ok] - ref[ok]) / np.abs(ref[ok])) < 1e-12

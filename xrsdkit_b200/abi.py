@@ -20,6 +20,7 @@ TABLE_GRID_OVERFLOW, TABLE_LIST_OVERFLOW, TABLE_SHELL_OVERFLOW, TABLE_BAD_LATTIC
 OK, EINVAL, ECUDA, ECAPACITY, ENOMEM = 0, -1, -2, -3, -4
 
 i32, f64 = C.c_int32, C.c_double
+N_FEATURES, FEATURE_MAX_Q = 21, 8192
 
 
 class Pop(C.Structure):
@@ -55,6 +56,7 @@ class Objective(C.Structure):
 
 
 vp = C.c_void_p
+i64 = C.c_int64
 _SIGNATURES = {
     "xrsd_last_error": (C.c_char_p, []),
     "xrsd_abi_version": (C.c_int, []),
@@ -77,6 +79,7 @@ _SIGNATURES = {
     "xrsd_intensity_batch_host": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, vp, C.c_int64]),
     "xrsd_release_workspace": (None, []),
     "xrsd_peak_profile": (C.c_int, [i32, f64, f64, vp, i32, vp, vp]),
+    "xrsd_feature_batch": (C.c_int, [vp, i32, vp, i64, i32, vp, i64, vp]),
     "xrsd_probe_fp64_peak": (C.c_int, [C.POINTER(f64), C.POINTER(f64), vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -18,6 +18,7 @@ cudaError_t xrsd_launch_intensity(const xrsd_layout_t *, const double *, int, co
                                   double *, long long, int, int, int, double *, cudaStream_t);
 cudaError_t xrsd_launch_fp64_probe(double *, int, int, cudaStream_t);
 cudaError_t xrsd_launch_profile(int, double, double, const double *, int, double *, cudaStream_t);
+cudaError_t xrsd_launch_features(const double *, int, const double *, int64_t, int, double *, int64_t, cudaStream_t);
 cudaError_t xrsd_launch_residual(const xrsd_layout_t *, const xrsd_objective_t *, const double *, int, const double *, int, int,
                                  const xrsd_tables_t *, const double *, const double *, long long, double *, int, int, int,
                                  const uint8_t *, double *, unsigned *, cudaStream_t);
@@ -357,6 +358,19 @@ int xrsd_peak_profile(int32_t kind, double hwhm_or_hwhm_g, double hwhm_l, const 
   if (n > 0 && (!d_x || !d_out)) return fail(XRSD_EINVAL, "NULL pointer");
   cudaError_t e = xrsd_launch_profile(kind, hwhm_or_hwhm_g, hwhm_l, d_x, n, d_out, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "profile_kernel");
+  return XRSD_OK;
+}
+
+int xrsd_feature_batch(const double *d_q, int32_t n_q, const double *d_I, int64_t ld_I, int32_t batch, double *d_features,
+                       int64_t ld_features, void *stream) {
+  if (batch < 0) return fail(XRSD_EINVAL, "batch %d", batch);
+  if (batch == 0) return XRSD_OK;
+  if (!d_q || !d_I || !d_features) return fail(XRSD_EINVAL, "NULL pointer");
+  if (n_q < 8 || n_q > XRSD_FEATURE_MAX_Q)
+    return fail(XRSD_EINVAL, "n_q %d outside [8, %d]", n_q, XRSD_FEATURE_MAX_Q);
+  if (ld_I < n_q || ld_features < XRSD_N_FEATURES) return fail(XRSD_EINVAL, "leading dimension too small");
+  cudaError_t e = xrsd_launch_features(d_q, n_q, d_I, ld_I, batch, d_features, ld_features, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "feature_kernel");
   return XRSD_OK;
 }
 

@@ -7,7 +7,7 @@
 namespace xrsd {
 
 template <int QPT, bool RM, bool HX>
-__global__ void __launch_bounds__(EVAL_THREADS, HX ? 8 : 6)
+__global__ void __launch_bounds__(EVAL_THREADS, HX ? 8 : 5)
 intensity_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ q, int n_q,
                  const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
                  double *__restrict__ I_out, long long ldI, int q_per_cta, int n_tiles, int scratch_doubles,

@@ -329,6 +329,16 @@ class Engine(object):
         self.launches += 1
         return out
 
+    def features(self, d_q, d_I, out=None):
+        """Featuriser (reference tools/profiler.py:64): d_I [B, n_q] on the device -> [B, 21] features."""
+        B, n_q = d_I.shape
+        if out is None:
+            out = self.torch.empty((B, abi.N_FEATURES), dtype=self.torch.float64, device=self.device)
+        abi.check(self.lib.xrsd_feature_batch(d_q.data_ptr(), n_q, d_I.data_ptr(), d_I.stride(0) if B > 1 else n_q, B,
+                                              out.data_ptr(), out.stride(0) if B > 1 else abi.N_FEATURES, self._stream()))
+        self.launches += 1
+        return out
+
     def probe_fp64_peak(self):
         t, ms = C.c_double(), C.c_double()
         abi.check(self.lib.xrsd_probe_fp64_peak(C.byref(t), C.byref(ms), self._stream()))

@@ -196,7 +196,11 @@ def fit(sys, q, I, dI=None, error_weighted=None, logI_weighted=None, q_range=Non
         sys_opt.fit_report.update(logI_weighted=logI_weighted)
     if q_range is not None:
         sys_opt.fit_report.update(q_range=q_range)
-    fitting.fit_system_inplace(sys_opt, np.asarray(q, dtype=float), np.asarray(I, dtype=float), dI, method=method)
+    q, I = np.asarray(q, dtype=float), np.asarray(I, dtype=float)
+    fitting.fit_system_inplace(sys_opt, q, I, dI, method=method)
+    if 8 <= q.size <= 8192:                      # the measured pattern's numerical profile (reference :276)
+        from ..tools import profiler
+        sys_opt.features = profiler.profile_pattern(q, I)
     return sys_opt
 
 
