@@ -126,13 +126,57 @@ static __device__ __noinline__ double rew_near(double x, const VoigtConst *vc) {
   return ex2 * (vc->head * cos2 + VOIGT_C * x * sxy * sinc + vc->cy_half * (sp + sm));
 }
 
-// Re w(x + i y) with y = vc->y >= 0.
-__device__ __forceinline__ double rew(double x, const VoigtConst *vc) {
+// Per-pattern table of the near branch: y is fixed, so Re w(x + i y), 0 <= x < 8, is ONE smooth function of
+// x for the whole pattern.  It is tabulated as a degree-16 Chebyshev expansion on each of 16 intervals of
+// width 1/2 (17 x 16 evaluations of rew_near per pattern instead of one per (q, shell) pair near a peak
+// core); max relative deviation from scipy's wofz 6e-14 for y in [1e-4, 8) (narrow intervals keep the
+// dynamic range of e^{-x^2} inside one interval small, so the error stays relative).
+constexpr int VOIGT_TAB_N = 17;          // nodes per interval (= CHEB_N of system_eval.cuh: shares its cosine table)
+constexpr int VOIGT_TAB_INTERVALS = 16;
+constexpr double VOIGT_TAB_MIN_Y = 1.0e-4;     // below: e^{-x^2} dominates out to x ~ 4.5 and the table loses relative accuracy
+constexpr int VOIGT_TAB_DOUBLES = VOIGT_TAB_N * VOIGT_TAB_INTERVALS;
+
+// Cooperative build (all `nthreads` threads): cos_tab[k*N + m] = cos(pi k (m + 1/2)/N); tmp holds
+// VOIGT_TAB_DOUBLES doubles; tab receives the coefficients (a_0 .. a_16 per interval, a_0 not yet halved).
+__device__ __forceinline__ void voigt_table(double *tab, double *tmp, const double *cos_tab, const VoigtConst *vc,
+                                            int tid, int nthreads) {
+  for (int it = tid; it < VOIGT_TAB_DOUBLES; it += nthreads) {
+    const int k = it / VOIGT_TAB_N, m = it - k * VOIGT_TAB_N;
+    tmp[it] = rew_near(0.5 * ((double)k + 0.5 + 0.5 * cos_tab[VOIGT_TAB_N + m]), vc);
+  }
+  __syncthreads();
+  for (int it = tid; it < VOIGT_TAB_DOUBLES; it += nthreads) {
+    const int k = it / VOIGT_TAB_N, j = it - k * VOIGT_TAB_N;
+    double a = 0.0;
+#pragma unroll
+    for (int m = 0; m < VOIGT_TAB_N; ++m) a = fma(tmp[k * VOIGT_TAB_N + m], cos_tab[j * VOIGT_TAB_N + m], a);
+    tab[it] = a * (2.0 / VOIGT_TAB_N);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ double rew_table(double x, const double *tab) {
+  const double x2 = x + x;                               // 0 <= x < 8: interval k = floor(2x), t = 2(2x - k) - 1
+  const int k = (int)x2;
+  const double t = 2.0 * (x2 - (double)k) - 1.0;
+  const double *ck = tab + k * VOIGT_TAB_N;
+  double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+  for (int j = VOIGT_TAB_N - 1; j >= 1; --j) {
+    const double b0 = fma(2.0 * t, b1, ck[j] - b2);
+    b2 = b1;
+    b1 = b0;
+  }
+  return fma(t, b1, 0.5 * ck[0] - b2);
+}
+
+// Re w(x + i y) with y = vc->y >= 0; `tab` (optional) is the pattern's near-branch table.
+__device__ __forceinline__ double rew(double x, const VoigtConst *vc, const double *tab = nullptr) {
   x = fabs(x);
   const double y = vc->y;
   const double z2 = fma(x, x, y * y);
   if (z2 >= 64.0) return (y == 0.0) ? exp(-x * x) : rew_far(x, y, z2);
-  return rew_near(x, vc);
+  return tab ? rew_table(x, tab) : rew_near(x, vc);
 }
 
 }  // namespace xrsd

@@ -191,6 +191,16 @@ jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *
 }
 
 constexpr int JR_THREADS = 128;
+constexpr int JR_STAGES = 4;      // q-points in flight per thread (ring of cp.async groups)
+
+// 8-byte asynchronous global -> shared copy (LDGSTS) and its group primitives
+__device__ __forceinline__ void cp_async8(double *dst_smem, const double *src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // RB rows of JTJ are accumulated per pass over the chunk (RB * NF accumulators live in registers)
 template <int NF, int RB>
@@ -202,6 +212,11 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
                        double *__restrict__ JTJ, double *__restrict__ JTr, double *__restrict__ chi2, int chunk_q,
                        int n_chunks, const uint8_t *__restrict__ active) {
   constexpr int NACC = NF * NF + NF + 2;          // full square (upper part used), JTr, chi2 numerator, sum w
+  // ring[stage][row][tid]: every thread streams its own q-points, JR_STAGES deep, through private slots --
+  // rows 0..n_slab-1 are the variant / running-total slabs, then I_obs, then dI.  The copies are asynchronous
+  // (LDGSTS), so a thread has JR_STAGES * n_rows * 8 B in flight instead of the few loads the compiler can hoist
+  // around 150 live accumulators (the first version was latency-bound at 0.45 TB/s).
+  extern __shared__ __align__(16) double ring[];
   __shared__ double fold[JR_THREADS / 32][RB * NF + NF + 2];
   __shared__ int is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -222,6 +237,18 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
   }
   const int q_lo = chunk * chunk_q, q_hi = min(n_q, q_lo + chunk_q);
   double *accb = acc_g + (size_t)b * NACC;
+  const int n_rows = n_slab + 1 + (err ? 1 : 0);
+  const int n_it = (q_hi - q_lo + JR_THREADS - 1) / JR_THREADS;
+  auto issue = [&](int it) {             // stage the q-point of iteration `it` (if any); always closes a group
+    const int i = q_lo + it * JR_THREADS + tid;
+    if (it < n_it && i < q_hi) {
+      double *slot = ring + (size_t)(it % JR_STAGES) * n_rows * JR_THREADS + tid;
+      for (int r = 0; r < n_slab; ++r) cp_async8(slot + r * JR_THREADS, Fb + (size_t)r * n_q + i);
+      cp_async8(slot + n_slab * JR_THREADS, obs + i);
+      if (err) cp_async8(slot + (n_slab + 1) * JR_THREADS, err + i);
+    }
+    cp_async_commit();
+  };
   for (int row0 = 0; row0 < nf; row0 += RB) {
     double aJ[RB][NF], ar[RB], c2 = 0.0, sw = 0.0;
 #pragma unroll
@@ -230,13 +257,21 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
 #pragma unroll
       for (int k = 0; k < NF; ++k) aJ[r][k] = 0.0;
     }
-    for (int i = q_lo + tid; i < q_hi; i += JR_THREADS) {
-      const double Io = obs[i];
-      double w;
-      bool fit = fit_weight(O, q[i], Io, err, i, w);
-      const double I0v = Fb[i];
-      if (O.logI_weighted) fit = fit && (I0v > 0.0);
-      if (!fit) continue;
+#pragma unroll
+    for (int st = 0; st < JR_STAGES; ++st) issue(st);
+    for (int it = 0; it < n_it; ++it) {
+      cp_async_wait<JR_STAGES - 1>();                 // the group of iteration `it` has landed
+      const int i = q_lo + it * JR_THREADS + tid;
+      const double *Fs = ring + (size_t)(it % JR_STAGES) * n_rows * JR_THREADS + tid;   // row r at Fs[r * JR_THREADS]
+      bool fit = i < q_hi;
+      double w = 0.0, Io = 0.0, I0v = 0.0;
+      if (fit) {
+        Io = Fs[n_slab * JR_THREADS];
+        fit = fit_weight(O, q[i], Io, err ? Fs + (n_slab + 1) * JR_THREADS : nullptr, 0, w);
+        I0v = Fs[0];
+        if (O.logI_weighted) fit = fit && (I0v > 0.0);
+      }
+      if (!fit) { issue(it + JR_STAGES); continue; }
       const double f0 = O.logI_weighted ? log(I0v) : I0v;
       const double fo = O.logI_weighted ? log(Io) : Io;
       const double res = f0 - fo;
@@ -247,11 +282,11 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
         double d = 0.0;
         if (j < nf) {
           if (F.var_of[j] > 0) {
-            d = Fb[(size_t)F.var_of[j] * n_q + i] - I0v;
+            d = Fs[F.var_of[j] * JR_THREADS] - I0v;
           } else {
             const int kp = F.pop_of[j];
-            double Ik = Fb[(size_t)(nv + kp) * n_q + i];
-            if (kp > 0) Ik -= Fb[(size_t)(nv + kp - 1) * n_q + i];
+            double Ik = Fs[(nv + kp) * JR_THREADS];
+            if (kp > 0) Ik -= Fs[(nv + kp - 1) * JR_THREADS];
             d = lin[j] * Ik;
           }
           if (O.logI_weighted) {
@@ -264,6 +299,7 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
         }
         D[j] = d;
       }
+      issue(it + JR_STAGES);                          // the slot is free again: refill it
       if (row0 == 0) { c2 = fma(w, res * res, c2); sw += w; }
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
@@ -279,6 +315,7 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
         }
       }
     }
+    cp_async_wait<0>();
     // fold over the CTA: warp shuffles, then one atomic per entry
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
@@ -494,12 +531,21 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
   const int chunk_q = 1024;
   const int n_chunks = (n_q + chunk_q - 1) / chunk_q;
   if ((long long)batch * n_chunks > 2147483647LL) return cudaErrorInvalidConfiguration;
+  const size_t ring_bytes = (size_t)JR_STAGES * (F.n_var + layout->n_pops + 2) * JR_THREADS * sizeof(double);
+  static size_t ring_set[2] = {0, 0};
+  const int which = n_free <= 8 ? 0 : 1;
+  if (ring_bytes > 48 * 1024 && ring_bytes > ring_set[which]) {
+    e = which == 0 ? cudaFuncSetAttribute(jacobian_reduce_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)
+                   : cudaFuncSetAttribute(jacobian_reduce_kernel<XRSD_MAX_FREE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
+    if (e != cudaSuccess) return e;
+    ring_set[which] = ring_bytes;
+  }
   if (n_free <= 8)
-    jacobian_reduce_kernel<8, 8><<<batch * n_chunks, JR_THREADS, 0, stream>>>(
+    jacobian_reduce_kernel<8, 8><<<batch * n_chunks, JR_THREADS, ring_bytes, stream>>>(
         layout->n_pops, *obj, d_q, n_q, d_params, ldp, batch, d_Iobs, d_dI, ld_obs, F, rel_step, d_Fvar, d_acc, d_tickets, d_JTJ,
         d_JTr, d_chi2, chunk_q, n_chunks, d_active);
   else
-    jacobian_reduce_kernel<XRSD_MAX_FREE, 4><<<batch * n_chunks, JR_THREADS, 0, stream>>>(
+    jacobian_reduce_kernel<XRSD_MAX_FREE, 4><<<batch * n_chunks, JR_THREADS, ring_bytes, stream>>>(
         layout->n_pops, *obj, d_q, n_q, d_params, ldp, batch, d_Iobs, d_dI, ld_obs, F, rel_step, d_Fvar, d_acc, d_tickets, d_JTJ,
         d_JTr, d_chi2, chunk_q, n_chunks, d_active);
   return cudaGetLastError();

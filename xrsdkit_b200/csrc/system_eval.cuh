@@ -42,7 +42,10 @@ struct ChebShared {                               // only in kernels that can me
   double cheb_part[2 * CHEB_ROUND * CHEB_N];     // node sums, two shell-parity halves per node
   double cheb_coef[CHEB_ROUND * CHEB_N];
   int near_lo[CHEB_ROUND], near_hi[CHEB_ROUND];
+  double voigt_tab[VOIGT_TAB_DOUBLES];           // near-branch Faddeeva table of the current population (faddeeva.cuh)
 };
+static_assert(VOIGT_TAB_N == CHEB_N, "the Voigt table shares the far-field cosine table");
+static_assert(VOIGT_TAB_DOUBLES <= 2 * CHEB_ROUND * CHEB_N, "cheb_part doubles as the table's node buffer");
 struct NoCheb {};
 
 struct EvalCore {
@@ -93,8 +96,8 @@ __device__ __forceinline__ double make_profile(Profile &P, int kind, double p0, 
   return 0.0;
 }
 
-__device__ __forceinline__ double profile_eval(const Profile &P, const VoigtConst *vc, double x) {
-  if (P.kind == XRSD_PROFILE_VOIGT) return rew(x * P.a, vc) * P.b;
+__device__ __forceinline__ double profile_eval(const Profile &P, const VoigtConst *vc, double x, const double *vtab = nullptr) {
+  if (P.kind == XRSD_PROFILE_VOIGT) return rew(x * P.a, vc, vtab) * P.b;
   if (P.kind == XRSD_PROFILE_GAUSSIAN) {
     const double u = x * P.a;
     return P.b * exp(-(u * u) * 0.6931471805599453);               // exp(-(x/h)**2 * ln 2)
@@ -352,6 +355,11 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         __syncthreads();
         // pass A: normalisation I(0) = sum_s W0_s * profile(0 - q_s)   (scattering/__init__.py:305,331)
         double part = 0.0;
+        // does any peak core (|q - q_s| < 8 sigma sqrt2, the Faddeeva near branch) reach into this span?
+        const bool voigt_near_possible = pop.profile == XRSD_PROFILE_VOIGT && S->vc.y < 8.0 && S->vc.y >= VOIGT_TAB_MIN_Y;
+        const double core_reach = voigt_near_possible ? 8.0 / P.a : 0.0;
+        const double span_lo = q_sorted ? q[q_begin] : -INFINITY, span_hi = q_sorted ? q[q_begin + q_count - 1] : INFINITY;
+        bool core_here = false;
         for (int s = tid; s < n_shell; s += EVAL_THREADS) {
           const double qs = 2.0 * M_PI * g_norm(S->cell.b, (double)sh_hkl[4 * s], (double)sh_hkl[4 * s + 1], (double)sh_hkl[4 * s + 2]);
           double ltz = 1.0;
@@ -364,8 +372,14 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
           for (int a = 0; a < n_sp; ++a)
             for (int bb = a; bb < n_sp; ++bb, ++ipq) w0 += ((a == bb) ? 1.0 : 2.0) * sh_geo[(size_t)s * T.n_pairs_max + ipq];
           part += ltz * w0 * profile_eval(P, &S->vc, 0.0 - qs);
+          core_here = core_here || (qs > span_lo - core_reach && qs < span_hi + core_reach);
         }
         const double norm = block_sum(part, S);
+        const double *vtab = nullptr;
+        if (voigt_near_possible && __syncthreads_or(core_here)) {
+          voigt_table(S->voigt_tab, S->cheb_part, S->cheb_cos, &S->vc, tid, EVAL_THREADS);
+          vtab = S->voigt_tab;
+        }
         // pass B: chunks of shells staged as (q_s, W_s[...]) in scratch
         const int wstride = radial_multi ? n_pairs : 1;
         const int rec = 1 + wstride;
@@ -452,7 +466,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               int lo = n_shell, hi = 0;
               for (int sl = g; sl < n_shell; sl += 2) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
-                if (fabs(sw.x - c) >= dn) part = fma(sw.y, profile_eval(P, &S->vc, xm - sw.x), part);
+                if (fabs(sw.x - c) >= dn) part = fma(sw.y, profile_eval(P, &S->vc, xm - sw.x, vtab), part);
                 else { lo = min(lo, sl); hi = max(hi, sl + 1); }
               }
               S->cheb_part[item] = part;
@@ -504,7 +518,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               const int s_lo = S->near_lo[run], s_hi = S->near_hi[run];
               for (int sl = s_lo; sl < s_hi; ++sl) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
-                a_sum = fma(sw.y, profile_eval(P, &S->vc, qi - sw.x), a_sum);
+                a_sum = fma(sw.y, profile_eval(P, &S->vc, qi - sw.x, vtab), a_sum);
               }
               finish_q(i, qi, a_sum);
             }
@@ -540,14 +554,14 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               for (int sl = 0; sl < ns; ++sl) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
 #pragma unroll
-                for (int j = 0; j < QPT; ++j) acc[j] = fma(sw.y, profile_eval(P, &S->vc, qv[j] - sw.x), acc[j]);
+                for (int j = 0; j < QPT; ++j) acc[j] = fma(sw.y, profile_eval(P, &S->vc, qv[j] - sw.x, vtab), acc[j]);
               }
             } else {
               for (int sl = 0; sl < ns; ++sl) {
                 const double qs = scratch[sl * rec];
 #pragma unroll
                 for (int j = 0; j < QPT; ++j) {
-                  const double v = profile_eval(P, &S->vc, qv[j] - qs);
+                  const double v = profile_eval(P, &S->vc, qv[j] - qs, vtab);
 #pragma unroll
                   for (int k = 0; k < (RADIAL_MULTI ? XRSD_MAX_PAIRS : 1); ++k)
                     if (k < n_pairs) accp[j][k] = fma(scratch[sl * rec + 1 + k], v, accp[j][k]);
