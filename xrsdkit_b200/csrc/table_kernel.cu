@@ -33,6 +33,7 @@ struct TableShared {
   double g_min, g_max;
   int n[3];
   int dim[3];          // 2n-1
+  float rcp_d0, rcp_d01;   // 1/dim[0], 1/(dim[0] dim[1])
   int cells;
   int n_all, n_red, n_shell_raw, n_shell;
   int hmin[3], hmax[3];
@@ -42,11 +43,24 @@ struct TableShared {
   int warp_tmp[TABLE_THREADS / 32];
 };
 
+// c / d for 0 <= c < 2^24 with a float reciprocal and a +-1 correction (an integer division by a run-time
+// divisor costs ~25 instructions; this was 30 % of the kernel's instructions)
+__device__ __forceinline__ int fast_div(int c, int d, float rcp) {
+  int qd = (int)((float)c * rcp);
+  const int r = c - qd * d;
+  if (r < 0) --qd;
+  else if (r >= d) ++qd;
+  return qd;
+}
+
 __device__ __forceinline__ void cell_to_hkl(const TableShared &S, int c, int &h, int &k, int &l) {
-  const int d0 = S.dim[0], d1 = S.dim[1];
-  h = c % d0 - (S.n[0] - 1);
-  k = (c / d0) % d1 - (S.n[1] - 1);
-  l = c / (d0 * d1) - (S.n[2] - 1);
+  const int d0 = S.dim[0], d01 = S.dim[0] * S.dim[1];
+  const int il = fast_div(c, d01, S.rcp_d01);
+  const int rem = c - il * d01;
+  const int ik = fast_div(rem, d0, S.rcp_d0);
+  h = rem - ik * d0 - (S.n[0] - 1);
+  k = ik - (S.n[1] - 1);
+  l = il - (S.n[2] - 1);
 }
 
 __device__ __forceinline__ int hkl_to_cell(const TableShared &S, int h, int k, int l) {
@@ -136,6 +150,8 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
     }
     if (cells > (long long)max_cells) { st |= XRSD_TABLE_GRID_OVERFLOW; cells = 0; }
     S.cells = (int)cells;
+    S.rcp_d0 = 1.0f / (float)S.dim[0];
+    S.rcp_d01 = 1.0f / ((float)S.dim[0] * (float)S.dim[1]);
     S.status = st;
     S.n_all = 0; S.n_red = 0; S.n_shell_raw = 0; S.n_shell = 0;
     for (int i = 0; i < 3; ++i) { S.hmin[i] = 1 << 30; S.hmax[i] = -(1 << 30); }
@@ -322,24 +338,30 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
     }
   }
   __syncthreads();
-  if (npow <= 1024) {
-    // small lists (the symmetric case): one warp sorts with __syncwarp only, the others wait once
-    if (tid < 32) {
-      for (int size = 2; size <= npow; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-          for (int i = tid; i < npow / 2; i += 32) {
-            const int lo = 2 * i - (i & (stride - 1));
-            const int hi = lo + stride;
-            const bool up = ((lo & size) == 0);
-            const double ka = keys[lo], kb = keys[hi];
-            const int ia = sidx[lo], ib = sidx[hi];
-            const bool gt = (ka > kb) || (ka == kb && ia > ib);
-            if (gt == up) { keys[lo] = kb; keys[hi] = ka; sidx[lo] = ib; sidx[hi] = ia; }
-          }
-          __syncwarp();
+  if (n_red <= 2 * TABLE_THREADS) {
+    // short lists (the symmetric case, cfg3: 198): rank sort -- every element counts the elements ordered before
+    // it (n^2 broadcast reads, all warps busy, two barriers) instead of ~40 dependent bitonic stages
+    double my_key[2];
+    int my_rank[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = tid + e * TABLE_THREADS;
+      my_rank[e] = -1;
+      if (i < n_red) {
+        const double ki = keys[i];
+        int rank = 0;
+        for (int j = 0; j < n_red; ++j) {
+          const double kj = keys[j];
+          rank += (kj < ki) || (kj == ki && j < i);
         }
+        my_key[e] = ki;
+        my_rank[e] = rank;
       }
     }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      if (my_rank[e] >= 0) { keys[my_rank[e]] = my_key[e]; sidx[my_rank[e]] = tid + e * TABLE_THREADS; }
     __syncthreads();
   } else {
     for (int size = 2; size <= npow; size <<= 1) {
