@@ -106,7 +106,8 @@ typedef struct xrsd_layout {
   double wavelength;
   double q_step;               /* > 0: q[i] == q[0] + i*q_step to within a few ulp (a linspace grid), which lets the
                                   size-quadrature loop advance its starting phases by a rotation from one 256-point
-                                  span to the next instead of calling sincos; 0: no assumption about q */
+                                  span to the next instead of calling sincos, and tells the crystalline
+                                  branch that q is strictly ascending without testing it; 0: no assumption about q */
   xrsd_pop_t pops[XRSD_MAX_POPS];
 } xrsd_layout_t;
 

@@ -15,7 +15,7 @@ int64_t xrsd_table_scratch_bytes(int64_t cap_big);
 cudaError_t xrsd_launch_tables(const xrsd_layout_t *, const double *, int, int, const xrsd_tables_t *, int, int, const uint8_t *,
                                cudaStream_t);
 cudaError_t xrsd_launch_intensity(const xrsd_layout_t *, const double *, int, const double *, int, int, const xrsd_tables_t *,
-                                  double *, long long, int, int, int, double *, cudaStream_t);
+                                  double *, long long, int, int, int, double *, int, cudaStream_t);
 cudaError_t xrsd_launch_fp64_probe(double *, int, int, cudaStream_t);
 cudaError_t xrsd_launch_profile(int, double, double, const double *, int, double *, cudaStream_t);
 cudaError_t xrsd_launch_features(const double *, int, const double *, int64_t, int, double *, int64_t, cudaStream_t);
@@ -213,6 +213,18 @@ static int pick_q_per_cta(int n_q, int batch, int scratch, bool has_xtal) {
   return (int)std::max(512LL, per);
 }
 
+static int pick_direct_span(int n_q, long long units) {
+  // Direct mode (crystalline layouts): the span is accumulated in the output row, so shared memory does not
+  // bound it.  Whole patterns per CTA when the grid still holds >= 16 waves of 8 CTAs per SM (the prologue of
+  // every population is then paid once per pattern); otherwise split, down to 512-point spans.
+  const long long want = 16LL * 148 * 8;
+  long long tiles = (want + units - 1) / std::max(1LL, units);
+  tiles = std::max(1LL, std::min(tiles, ((long long)n_q + 511) / 512));
+  long long per = ((long long)n_q + tiles - 1) / tiles;
+  per = ((per + 255) / 256) * 256;
+  return (int)per;
+}
+
 static int intensity_impl(const xrsd_layout_t *layout, const double *d_q, int32_t n_q, const double *d_params,
                           int32_t ld_params, int32_t batch, const xrsd_tables_t *tables, double *d_I, int64_t ld_I,
                           double *d_cum, void *stream) {
@@ -227,9 +239,10 @@ static int intensity_impl(const xrsd_layout_t *layout, const double *d_q, int32_
   int rm;
   const int scratch = scratch_doubles_for(layout, &rm);
   if (scratch < 0) return fail(XRSD_ECAPACITY, "size quadrature too fine for shared memory (sampling_width/sampling_step)");
-  const int per = pick_q_per_cta(n_q, batch, scratch, layout->n_xtal > 0);
+  const int direct = layout->n_xtal > 0;
+  const int per = direct ? pick_direct_span(n_q, batch) : pick_q_per_cta(n_q, batch, scratch, false);
   cudaError_t e = xrsd_launch_intensity(layout, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables, d_I,
-                                        (long long)ld_I, per, scratch, rm, d_cum, (cudaStream_t)stream);
+                                        (long long)ld_I, per, scratch, rm, d_cum, direct, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "intensity_kernel");
   return XRSD_OK;
 }
@@ -311,7 +324,9 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   int rm;
   const int scratch = scratch_doubles_for(layout, &rm);
   if (scratch < 0) return fail(XRSD_ECAPACITY, "size quadrature too fine for shared memory");
-  const int per = pick_q_per_cta(n_q, batch * (n_free + 1), scratch, false);   // measured: 4096-point spans, 6 CTAs/SM win here
+  // crystalline layouts accumulate straight into the variant slabs (negative span = direct mode)
+  const int per = layout->n_xtal > 0 ? -pick_direct_span(n_q, (long long)batch * (n_free + 1))
+                                     : pick_q_per_cta(n_q, batch * (n_free + 1), scratch, false);
   if (xrsd_jacobian_smem(layout->n_params, n_free, per, scratch, nullptr) + kStaticSmem > (size_t)kMaxSmem)
     return fail(XRSD_ECAPACITY, "jacobian working set does not fit in shared memory");
   const int64_t fbytes = (int64_t)batch * (n_free + 1 + XRSD_MAX_POPS) * n_q * 8;

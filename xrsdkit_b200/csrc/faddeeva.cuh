@@ -38,19 +38,19 @@ struct VoigtConst {
 
 // fills `vc` cooperatively: call with all threads of the CTA, then __syncthreads().
 __device__ __forceinline__ void voigt_constants(VoigtConst *vc, double y, int tid) {
-  if (tid < VOIGT_NPOS) {
+  static_assert(VOIGT_NPOS == 32, "one warp computes the K_n and their sum");
+  if (tid < VOIGT_NPOS) {                               // warp 0, all lanes
     const double an = VOIGT_A * (tid + 1);
-    vc->K[tid] = exp(-an * an) / (an * an + y * y);
-  }
-  if (tid == 32) {
-    double s1 = 0.0;
-    for (int n = VOIGT_NPOS; n >= 1; --n) {
-      const double an = VOIGT_A * n;
-      s1 += exp(-an * an) / (an * an + y * y);
+    const double kn = exp(-an * an) / (an * an + y * y);
+    vc->K[tid] = kn;
+    double s1 = kn;                                      // S1 = sum_n K_n by a shuffle tree
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    if (tid == 0) {
+      vc->y = y;
+      vc->head = erfcx(y) - VOIGT_C * y * s1;
+      vc->cy_half = 0.5 * VOIGT_C * y;
     }
-    vc->y = y;
-    vc->head = erfcx(y) - VOIGT_C * y * s1;
-    vc->cy_half = 0.5 * VOIGT_C * y;
   }
 }
 

@@ -149,11 +149,12 @@ residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
 //     writes the outputs.  (A first version reduced inside the variant kernel by the last-finishing
 //     CTA of each system: that serial tail cost 25 % of the whole Jacobian.)
 template <bool RM, bool HX>
-__global__ void __launch_bounds__(EVAL_THREADS, 6)
+__global__ void __launch_bounds__(EVAL_THREADS, HX ? 8 : 6)
 jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ q, int n_q,
                          const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T, const FreeSet F,
                          double rel_step, double *__restrict__ Fvar, int q_per_cta, int n_tiles, int pattern_doubles,
                          int scratch_doubles, const uint8_t *__restrict__ active) {
+  // pattern_doubles == 0: direct mode, the variant's slab in HBM is the accumulation buffer (see intensity_kernel.cu)
   extern __shared__ __align__(16) double smem_d[];
   __shared__ EvalSharedT<HX> S;
   const int tid = threadIdx.x;
@@ -184,10 +185,12 @@ jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *
   // slabs of this system: [0, nv) variants (slab 0 = base), [nv, nv+n_pops) the base variant's running
   // totals after each population
   double *slab0 = Fvar + (size_t)b * n_slab * n_q;
+  double *dst = slab0 + (size_t)v * n_q + q_begin;
+  if (pattern_doubles == 0) I_sm = dst;
   accumulate_system<2, RM, HX>(L, prm_s, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S, prm,
                                v == 0 ? slab0 + (size_t)nv * n_q + q_begin : nullptr, n_q);
-  double *dst = slab0 + (size_t)v * n_q + q_begin;
-  for (int i = tid; i < q_count; i += EVAL_THREADS) dst[i] = I_sm[i];
+  if (pattern_doubles != 0)
+    for (int i = tid; i < q_count; i += EVAL_THREADS) dst[i] = I_sm[i];
 }
 
 constexpr int JR_THREADS = 128;
@@ -494,7 +497,7 @@ extern "C" cudaError_t xrsd_launch_residual(const xrsd_layout_t *layout, const x
 }
 
 extern "C" size_t xrsd_jacobian_smem(int n_params, int n_free, int q_per_cta, int scratch_doubles, int *pattern_doubles) {
-  const int pat = (q_per_cta + 1) & ~1;
+  const int pat = q_per_cta < 0 ? 0 : (q_per_cta + 1) & ~1;        // q_per_cta < 0: direct mode, span = -q_per_cta
   if (pattern_doubles) *pattern_doubles = pat;
   return ((size_t)pat + (size_t)scratch_doubles + (size_t)((n_params + 1) & ~1)) * sizeof(double);
 }
@@ -521,6 +524,7 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (batch <= 0) return cudaSuccess;
+  if (q_per_cta < 0) q_per_cta = -q_per_cta;
   const int n_tiles = (n_q + q_per_cta - 1) / q_per_cta;
   const long long n_blocks = (long long)batch * F.n_var * n_tiles;
   if (n_blocks > 2147483647LL) return cudaErrorInvalidConfiguration;

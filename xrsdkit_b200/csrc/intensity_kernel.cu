@@ -1,7 +1,11 @@
 // intensity_kernel.cu -- batched I(q): grid = batch x q-tiles, one CTA per (system, q-span).
-// The pattern span is accumulated in shared memory by accumulate_system() and written
-// once, coalesced (8 B per (system, q) of HBM traffic; q and the parameter row are re-read
-// from L2).  Replaces System.compute_intensity, system/__init__.py:112-130.
+// Staged mode: the pattern span is accumulated in shared memory by accumulate_system() and written
+// once, coalesced (8 B per (system, q) of HBM traffic; q and the parameter row are re-read from L2).
+// Direct mode (layouts with crystalline populations): the span is accumulated in place in the output
+// row (an L2-resident read-modify-write per population, ~1 % of the arithmetic), so the span length is
+// not tied to shared memory and one CTA can take a whole pattern -- the per-population prologue
+// (cell, shells, Voigt tables) is then paid once per pattern instead of once per 2048 q-points.
+// Replaces System.compute_intensity, system/__init__.py:112-130.
 #include "system_eval.cuh"
 
 namespace xrsd {
@@ -11,7 +15,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, HX ? 8 : 5)
 intensity_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ q, int n_q,
                  const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
                  double *__restrict__ I_out, long long ldI, int q_per_cta, int n_tiles, int scratch_doubles,
-                 double *__restrict__ cum_out) {
+                 double *__restrict__ cum_out, int direct) {
   extern __shared__ __align__(16) double smem_d[];
   __shared__ EvalSharedT<HX> S;
   const long long bid = blockIdx.x;
@@ -20,14 +24,15 @@ intensity_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restri
   if (b >= batch) return;
   const int q_begin = tile * q_per_cta;
   const int q_count = min(q_per_cta, n_q - q_begin);
-  double *I_sm = smem_d;
-  double *scratch = smem_d + ((q_per_cta + 1) & ~1);
+  double *dst = I_out + (size_t)b * ldI + q_begin;
+  double *I_sm = direct ? dst : smem_d;
+  double *scratch = direct ? smem_d : smem_d + ((q_per_cta + 1) & ~1);
   // cum_out (optional): [batch][n_pops][n_q] running totals after the noise model and after each
   // population -- their differences are the per-population patterns (plot decomposition, I0 rescaling)
   accumulate_system<QPT, RM, HX>(L, params + (size_t)b * ldp, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S,
                                  nullptr, cum_out ? cum_out + (size_t)b * L.n_pops * n_q + q_begin : nullptr, n_q);
-  double *dst = I_out + (size_t)b * ldI + q_begin;
-  for (int i = threadIdx.x; i < q_count; i += EVAL_THREADS) dst[i] = I_sm[i];
+  if (!direct)
+    for (int i = threadIdx.x; i < q_count; i += EVAL_THREADS) dst[i] = I_sm[i];
 }
 
 // DFMA-bound probe: 8 independent chains per thread, 4096 DFMA each
@@ -67,10 +72,10 @@ extern "C" cudaError_t xrsd_launch_profile(int kind, double p0, double p1, const
 extern "C" cudaError_t xrsd_launch_intensity(const xrsd_layout_t *layout, const double *d_q, int n_q, const double *d_params,
                                              int ldp, int batch, const xrsd_tables_t *tables, double *d_I, long long ldI,
                                              int q_per_cta, int scratch_doubles, int radial_multi, double *d_cum,
-                                             cudaStream_t stream) {
+                                             int direct, cudaStream_t stream) {
   using namespace xrsd;
   const int n_tiles = (n_q + q_per_cta - 1) / q_per_cta;
-  const size_t smem = ((size_t)((q_per_cta + 1) & ~1) + (size_t)scratch_doubles) * sizeof(double);
+  const size_t smem = ((direct ? 0 : (size_t)((q_per_cta + 1) & ~1)) + (size_t)scratch_doubles) * sizeof(double);
   auto kern = radial_multi ? intensity_kernel<2, true, true>
                            : (layout->n_xtal ? intensity_kernel<2, false, true> : intensity_kernel<2, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -79,7 +84,7 @@ extern "C" cudaError_t xrsd_launch_intensity(const xrsd_layout_t *layout, const 
   if (n_blocks <= 0) return cudaSuccess;
   if (n_blocks > 2147483647LL) return cudaErrorInvalidConfiguration;
   kern<<<(unsigned)n_blocks, EVAL_THREADS, smem, stream>>>(*layout, d_q, n_q, d_params, ldp, batch, *tables, d_I, ldI,
-                                                          q_per_cta, n_tiles, scratch_doubles, d_cum);
+                                                          q_per_cta, n_tiles, scratch_doubles, d_cum, direct);
   return cudaGetLastError();
 }
 

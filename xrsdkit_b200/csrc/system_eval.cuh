@@ -137,9 +137,13 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
   // strictly ascending q over the span enables the far-field interpolation of crystalline sums
   bool q_sorted = false;
   if constexpr (HAS_XTAL) {
-    bool mine = true;
-    for (int i = tid; i + 1 < q_count; i += EVAL_THREADS) mine = mine && (q[q_begin + i] < q[q_begin + i + 1]);
-    q_sorted = __syncthreads_and(mine) != 0;
+    if (L.q_step > 0.0) {                       // a uniform ascending grid (checked on the host): nothing to test
+      q_sorted = true;
+    } else {
+      bool mine = true;
+      for (int i = tid; i + 1 < q_count; i += EVAL_THREADS) mine = mine && (q[q_begin + i] < q[q_begin + i + 1]);
+      q_sorted = __syncthreads_and(mine) != 0;
+    }
     for (int i = tid; i < CHEB_N * CHEB_N; i += EVAL_THREADS)
       S->cheb_cos[i] = cospi((double)(i / CHEB_N) * ((double)(i % CHEB_N) + 0.5) / (double)CHEB_N);
   }

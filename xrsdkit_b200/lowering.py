@@ -227,7 +227,7 @@ def uniform_step(q):
     if not (step > 0):
         return 0.0
     tol = 4 * np.finfo(float).eps * max(abs(q[0]), abs(q[-1]))
-    if np.max(np.abs(q - (q[0] + np.arange(n) * step))) <= tol:
+    if np.max(np.abs(q - (q[0] + np.arange(n) * step))) <= tol and np.all(np.diff(q) > 0):
         return float(step)
     return 0.0
 
