@@ -215,9 +215,10 @@ static int pick_q_per_cta(int n_q, int batch, int scratch, bool has_xtal) {
 
 static int pick_direct_span(int n_q, long long units) {
   // Direct mode (crystalline layouts): the span is accumulated in the output row, so shared memory does not
-  // bound it.  Whole patterns per CTA when the grid still holds >= 16 waves of 8 CTAs per SM (the prologue of
-  // every population is then paid once per pattern); otherwise split, down to 512-point spans.
-  const long long want = 16LL * 148 * 8;
+  // bound it.  Whole patterns per CTA when the grid still holds >= 4 waves of 8 CTAs per SM (the prologue of
+  // every population is then paid once per pattern); otherwise split, down to 512-point spans.  Measured on
+  // cfg3: 2-4 waves are within 1 % of each other, 16 waves cost 10-30 % (B = 10^4 ... 2000).
+  const long long want = 4LL * 148 * 8;
   long long tiles = (want + units - 1) / std::max(1LL, units);
   tiles = std::max(1LL, std::min(tiles, ((long long)n_q + 511) / 512));
   long long per = ((long long)n_q + tiles - 1) / tiles;
