@@ -532,7 +532,11 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
                                                           q_per_cta, n_tiles, pat, scratch_doubles, d_active);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const int chunk_q = 1024;
+  // q-chunk per reduction CTA: every CTA pays a prologue and a 74-value fold, so chunks are as long as the grid
+  // allows -- whole patterns once the batch alone fills the GPU (2 CTAs/SM by registers), 1024 points for small batches
+  int chunks_per_sys = (int)((4LL * 148 * 2 + batch - 1) / batch);
+  chunks_per_sys = std::max(1, std::min(chunks_per_sys, (n_q + 1023) / 1024));
+  const int chunk_q = (((n_q + chunks_per_sys - 1) / chunks_per_sys) + JR_THREADS - 1) / JR_THREADS * JR_THREADS;
   const int n_chunks = (n_q + chunk_q - 1) / chunk_q;
   if ((long long)batch * n_chunks > 2147483647LL) return cudaErrorInvalidConfiguration;
   const size_t ring_bytes = (size_t)JR_STAGES * (F.n_var + layout->n_pops + 2) * JR_THREADS * sizeof(double);

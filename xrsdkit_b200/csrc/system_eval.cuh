@@ -464,7 +464,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               const int i0 = r0 + run * EVAL_THREADS, i1 = min(q_count, i0 + EVAL_THREADS);
               const double qa = q[q_begin + i0], qb = q[q_begin + i1 - 1];
               const double c = 0.5 * (qa + qb), H = 0.5 * (qb - qa);
-              const double dn = fmax(8.0 * H, H + 12.0 * core);
+              const double dn = fmax(4.0 * H, H + 12.0 * core);
               const double xm = fma(H, S->cheb_cos[CHEB_N + m], c);       // row k=1: cos(pi (m+1/2)/N)
               double part = 0.0;
               int lo = n_shell, hi = 0;
@@ -484,7 +484,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               const int i0 = r0 + run * EVAL_THREADS, i1 = min(q_count, i0 + EVAL_THREADS);
               const double qa = q[q_begin + i0], qb = q[q_begin + i1 - 1];
               const double c = 0.5 * (qa + qb), H = 0.5 * (qb - qa);
-              const double dn = fmax(8.0 * H, H + 12.0 * core);
+              const double dn = fmax(4.0 * H, H + 12.0 * core);
               for (int sl = 1; sl < n_shell; sl += 2)
                 if (fabs(scratch[2 * sl] - c) < dn) { lo = min(lo, sl); hi = max(hi, sl + 1); }
               S->near_lo[run] = lo;
