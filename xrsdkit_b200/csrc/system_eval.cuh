@@ -441,8 +441,8 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         };
         // ---- far-field interpolation path ------------------------------------------------------
         // For a run of EVAL_THREADS consecutive q-points (centre c, half-width H) every shell with
-        // |q_s - c| >= max(8 H, H + 12 core widths) is "far": the sum of all far shells is smooth over
-        // the run (nearest singular structure >= 7 H away), so it is evaluated at CHEB_N Chebyshev
+        // |q_s - c| >= max(4 H, H + 12 core widths) is "far": the sum of all far shells is smooth over
+        // the run (nearest singular structure >= 3 H from its edge: Bernstein parameter rho >= 7.9, rho^-17 < 1e-15), so it is evaluated at CHEB_N Chebyshev
         // nodes only and interpolated (degree 16: truncation < 1e-13 relative, tests/test_gpu_parity.py),
         // while the few near shells are summed directly.  This cuts the profile evaluations per q from
         // n_shell to about n_near + CHEB_N n_far / EVAL_THREADS.
