@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libxrsd_b200.so")
+LIB_PATH = os.environ.get("XRSD_B200_LIB") or os.path.join(HERE, "libxrsd_b200.so")   # override: A/B timing of two builds
 
 MAX_POPS, MAX_SPECIES, MAX_PAIRS, MAX_OPS, MAX_PARAMS, MAX_FREE, MAX_TIES = 6, 4, 10, 9, 64, 16, 8
 
