@@ -314,7 +314,7 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
           const double wdj = w * dj;
           ar[r] = fma(wdj, res, ar[r]);
 #pragma unroll
-          for (int k = 0; k < NF; ++k) aJ[r][k] = fma(wdj, D[k], aJ[r][k]);
+          for (int k = (RB == NF ? r : 0); k < NF; ++k) aJ[r][k] = fma(wdj, D[k], aJ[r][k]);   // single pass: upper triangle only
         }
       }
     }

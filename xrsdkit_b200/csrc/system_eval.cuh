@@ -35,7 +35,8 @@ constexpr int SHELL_CHUNK = 128;
 
 // shared-memory working set of one CTA (besides the pattern buffer)
 constexpr int CHEB_N = 17;                       // Chebyshev nodes of the far-field interpolant (degree 16)
-constexpr int CHEB_ROUND = 8;                    // runs of EVAL_THREADS q-points handled between two barriers
+constexpr int CHEB_ROUND = 16;                   // runs of EVAL_THREADS q-points handled between two barriers
+                                                 // (measured: 8 -> 16 +3.5 %, 32 the same, 64 loses occupancy)
 
 struct ChebShared {                               // only in kernels that can meet a crystalline population
   double cheb_cos[CHEB_N * CHEB_N];              // cos(pi k (m + 1/2) / N)
