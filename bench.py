@@ -39,7 +39,7 @@ WL = 0.8265617
 #         (hard-sphere sincos 40 + brackets 60 + two divisions 20 + epilogue 15 + the starting phases of
 #          the quadrature: two rotations 24 on a uniform q grid, with a sincos pair only in the first span)
 FLOPS_PER_PAIR_RNORMAL = 13.0
-FLOPS_PER_Q_OVERHEAD_CFG2 = 185.0
+FLOPS_PER_Q_OVERHEAD_CFG2 = 151.0        # PY brackets ~100, two divisions 20, three span-to-span rotations 18, epilogue ~13
 SURVEY_FLOPS_PER_SETQ_CFG2 = 2630.0          # SURVEY.md 8d convention (sincos per (q,r) pair)
 
 
@@ -312,14 +312,14 @@ class Work(object):
             return FLOPS_PER_PAIR_RNORMAL * 50.5 + FLOPS_PER_Q_OVERHEAD_CFG2, SURVEY_FLOPS_PER_SETQ_CFG2
         ns = float(np.mean([float(t.n_shell.float().mean().item()) for t in self.tables]))
         extra = 80.0 + 45.0 if self.name in ("cfg4", "cfg5") else 0.0       # Guinier-Porod + log/residual
-        # far-field interpolation: per q only the shells within dn = max(8H, H + 12 core) of
+        # far-field interpolation: per q only the shells within dn = max(4H, H + 12 core) of
         # its 128-point run are evaluated directly, the rest through 17 Chebyshev nodes per run
         lay, P = self.lay, self.P
         H = 0.5 * 127 * (self.q[-1] - self.q[0]) / (self.n_q - 1)
         hg, hl = P[:, lay.slot("x__hwhm_g")], P[:, lay.slot("x__hwhm_l")]
         s2 = hg / np.sqrt(2 * np.log(2)) * np.sqrt(2)
         core = np.maximum(1.0, hl / s2) * s2
-        dn = np.maximum(8 * H, H + 12 * core)
+        dn = np.maximum(4 * H, H + 12 * core)
         n_near = float(np.mean(np.minimum(ns, ns * 2 * dn / (self.q[-1] - self.q[0]))))
         per_q = 60.0 * n_near + 17.0 * 60.0 * (ns - n_near) / 128.0 + 2.0 * 17.0 + 150.0 + extra
         return per_q, 205.0 * ns + 150.0 + extra
@@ -328,7 +328,7 @@ class Work(object):
 def ncu_traffic_bytes(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full
     summary of this round (profiles/), per launch; None when no capture matches the workload."""
-    name = {"cfg2": "r01_final_ncu_cfg2_intensity.txt"}.get(workload)
+    name = {"cfg2": "r01b_ncu_cfg2_intensity.txt"}.get(workload)
     if name is None:
         return None
     try:
