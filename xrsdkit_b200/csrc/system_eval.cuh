@@ -43,6 +43,7 @@ struct ChebShared {                               // only in kernels that can me
   double cheb_part[2 * CHEB_ROUND * CHEB_N];     // node sums, two shell-parity halves per node
   double cheb_coef[CHEB_ROUND * CHEB_N];
   int near_lo[CHEB_ROUND], near_hi[CHEB_ROUND];
+  double run_c[CHEB_ROUND], run_invH[CHEB_ROUND];   // centre and 1/half-width of each run of the round
   double voigt_tab[VOIGT_TAB_DOUBLES];           // near-branch Faddeeva table of the current population (faddeeva.cuh)
 };
 static_assert(VOIGT_TAB_N == CHEB_N, "the Voigt table shares the far-field cosine table");
@@ -422,6 +423,8 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
           }
         };
         const double I0 = prm[pop.p_I0];
+        // per-pattern reciprocals: the per-q finish has no division (<= 2 ulp from the reference's order)
+        const double inv_norm = 1.0 / norm, wl_4pi = wl / (4.0 * M_PI);
         // per-q finish shared by both paths: radial form factor, polarisation, normalisation, I0
         auto finish_q = [&](int i, double qi, double a_sum) {
           if (radial && !radial_multi) {
@@ -434,11 +437,11 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
             // 0.5 (1 + cos^2(2 theta)), theta = asin(lambda q / 4 pi)  (scattering/__init__.py:234-238):
             // cos(2 theta) = 1 - 2 sin^2(theta), so no transcendental is needed; |sin| > 1 gives the
             // reference's NaN
-            const double st = wl * qi / (4.0 * M_PI);
+            const double st = wl_4pi * qi;
             const double c2 = (fabs(st) <= 1.0) ? fma(-2.0 * st, st, 1.0) : NAN;
             pz = 0.5 * (1.0 + c2 * c2);
           }
-          I_sm[i] += I0 * (pz * a_sum / norm);                     // I0 * (pz*I/I0_norm)
+          I_sm[i] += I0 * (pz * a_sum * inv_norm);                 // I0 * (pz*I/I0_norm)
         };
         // ---- far-field interpolation path ------------------------------------------------------
         // For a run of EVAL_THREADS consecutive q-points (centre c, half-width H) every shell with
@@ -490,6 +493,8 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
                 if (fabs(scratch[2 * sl] - c) < dn) { lo = min(lo, sl); hi = max(hi, sl + 1); }
               S->near_lo[run] = lo;
               S->near_hi[run] = hi;
+              S->run_c[run] = c;
+              S->run_invH[run] = (H > 0.0) ? 1.0 / H : 0.0;
             }
             // (2) coefficient (run, k): a_k = 2/N sum_m B_m cos(pi k (m+1/2)/N)
             for (int item = tid; item < n_run * CHEB_N; item += EVAL_THREADS) {
@@ -506,11 +511,9 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               const int i0 = r0 + run * EVAL_THREADS, i1 = min(q_count, i0 + EVAL_THREADS);
               const int i = i0 + tid;
               if (i >= i1) continue;
-              const double qa = q[q_begin + i0], qb = q[q_begin + i1 - 1];
-              const double c = 0.5 * (qa + qb), H = 0.5 * (qb - qa);
               const double qi = q[q_begin + i];
               // Clenshaw for a_0/2 + sum_k a_k T_k(t), t in [-1, 1]
-              const double t = (H > 0.0) ? (qi - c) / H : 0.0;
+              const double t = (qi - S->run_c[run]) * S->run_invH[run];
               const double *ck = S->cheb_coef + run * CHEB_N;
               double b1 = 0.0, b2 = 0.0;
 #pragma unroll
