@@ -39,6 +39,7 @@ struct TableShared {
   int hmin[3], hmax[3];
   int status;
   int scan_carry;
+  int alive_cnt[3];        // rotating counters of the alive lists (one barrier per operation)
   double max_geo;
   int warp_tmp[TABLE_THREADS / 32];
 };
@@ -67,6 +68,18 @@ __device__ __forceinline__ int hkl_to_cell(const TableShared &S, int h, int k, i
   const int ih = h + S.n[0] - 1, ik = k + S.n[1] - 1, il = l + S.n[2] - 1;
   if (ih < 0 || ih >= S.dim[0] || ik < 0 || ik >= S.dim[1] || il < 0 || il >= S.dim[2]) return -1;
   return (il * S.dim[1] + ik) * S.dim[0] + ih;
+}
+
+// Appends `value` to list[] for every lane with `take` set: one shared-memory atomic per warp instead of one per lane.
+// Must be called by all lanes of the warp (converged).
+__device__ __forceinline__ void warp_append(bool take, uint16_t value, uint16_t *list, int *counter) {
+  const unsigned m = __ballot_sync(0xffffffffu, take);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (take) list[base + __popc(m & ((1u << lane) - 1))] = value;
 }
 
 // block-wide exclusive scan of one flag per thread; returns this thread's offset and adds the
@@ -203,67 +216,75 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
     uint16_t *alive[2] = {reinterpret_cast<uint16_t *>(keys), reinterpret_cast<uint16_t *>(keys) + 5 * cap_list};
     const bool use_list = S.cells <= 65535 && S.n_all <= 5 * cap_list;
     if (use_list) {
-      for (int c = tid; c < S.cells; c += TABLE_THREADS)
-        if (grid[c]) alive[0][atomicAdd(&S.scan_carry, 1)] = (uint16_t)c;
+      if (tid < 3) S.alive_cnt[tid] = 0;
       __syncthreads();
-      if (tid == 0) S.scan_carry = 0;
+      for (int c0 = 0; c0 < S.cells; c0 += TABLE_THREADS) {
+        const int c = c0 + tid;
+        warp_append(c < S.cells && grid[c] != 0, (uint16_t)c, alive[0], &S.alive_cnt[2]);
+      }
       __syncthreads();
     }
-    int n_visit = use_list ? S.n_all : S.cells;
+    int n_visit = use_list ? S.alive_cnt[2] : S.cells;
     for (int iop = 0; iop < pop.n_ops; ++iop) {
       int perm[3];
       double sgn[3];
       sym_op(pop.ops[iop], perm, sgn);
       const uint16_t *cur = alive[iop & 1];
       uint16_t *nxt = alive[(iop + 1) & 1];
-      for (int iv = tid; iv < n_visit; iv += TABLE_THREADS) {
-        const int c = use_list ? (int)cur[iv] : iv;
-        const unsigned mi = grid[c];
-        if (!mi) continue;
-        int h, k, l;
-        cell_to_hkl(S, c, h, k, l);
-        // lat_pts = all_hkl . rlat^T  (symmetries.py:52): p_m = b_m . (h,k,l)
-        double p[3], s[3];
-        for (int m = 0; m < 3; ++m)
-          p[m] = (double)h * S.cell.b[m][0] + (double)k * S.cell.b[m][1] + (double)l * S.cell.b[m][2];
-        for (int m = 0; m < 3; ++m) s[m] = sgn[m] * p[perm[m]];
-        // nearest lattice point to op.p_i: hkl_j = rlat^-1 s = A^T s
-        int hj[3];
-        for (int n = 0; n < 3; ++n)
-          hj[n] = (int)rint(S.cell.a[0][n] * s[0] + S.cell.a[1][n] * s[1] + S.cell.a[2][n] * s[2]);
-        const int cj = hkl_to_cell(S, hj[0], hj[1], hj[2]);
-        bool drop = false;
-        if (cj >= 0 && cj != c && grid[cj]) {
-          // distance |p_i - op.p_j| (symmetries.py:62-72)
-          double pj[3], d2 = 0.0;
-          for (int m = 0; m < 3; ++m)
-            pj[m] = (double)hj[0] * S.cell.b[m][0] + (double)hj[1] * S.cell.b[m][1] + (double)hj[2] * S.cell.b[m][2];
-          for (int m = 0; m < 3; ++m) {
-            const double df = p[m] - sgn[m] * pj[perm[m]];
-            d2 += df * df;
-          }
-          if (sqrt(d2) < 1.0e-6) {
-            const int rank_i = (h * rk + k) * rl + l;
-            const int rank_j = (hj[0] * rk + hj[1]) * rl + hj[2];
-            drop = rank_i < rank_j;
+      // survivors of operation iop are counted in alive_cnt[iop % 3]; the counter of the next operation is
+      // cleared here -- every thread read it (as n_visit) before the barrier that ended the previous operation
+      int *cnt = &S.alive_cnt[iop % 3];
+      if (tid == 0) S.alive_cnt[(iop + 1) % 3] = 0;
+      for (int iv0 = 0; iv0 < n_visit; iv0 += TABLE_THREADS) {
+        const int iv = iv0 + tid;
+        bool keep = false;
+        int c = 0;
+        if (iv < n_visit) {
+          c = use_list ? (int)cur[iv] : iv;
+          const unsigned mi = grid[c];
+          if (mi) {
+            int h, k, l;
+            cell_to_hkl(S, c, h, k, l);
+            // lat_pts = all_hkl . rlat^T  (symmetries.py:52): p_m = b_m . (h,k,l)
+            double p[3], s[3];
+            for (int m = 0; m < 3; ++m)
+              p[m] = (double)h * S.cell.b[m][0] + (double)k * S.cell.b[m][1] + (double)l * S.cell.b[m][2];
+            for (int m = 0; m < 3; ++m) s[m] = sgn[m] * p[perm[m]];
+            // nearest lattice point to op.p_i: hkl_j = rlat^-1 s = A^T s
+            int hj[3];
+            for (int n = 0; n < 3; ++n)
+              hj[n] = (int)rint(S.cell.a[0][n] * s[0] + S.cell.a[1][n] * s[1] + S.cell.a[2][n] * s[2]);
+            const int cj = hkl_to_cell(S, hj[0], hj[1], hj[2]);
+            bool drop = false;
+            if (cj >= 0 && cj != c && grid[cj]) {
+              // distance |p_i - op.p_j| (symmetries.py:62-72)
+              double pj[3], d2 = 0.0;
+              for (int m = 0; m < 3; ++m)
+                pj[m] = (double)hj[0] * S.cell.b[m][0] + (double)hj[1] * S.cell.b[m][1] + (double)hj[2] * S.cell.b[m][2];
+              for (int m = 0; m < 3; ++m) {
+                const double df = p[m] - sgn[m] * pj[perm[m]];
+                d2 += df * df;
+              }
+              if (d2 < 1.0e-12) {                    // dist < 1e-6 (the distances met are ~1e-16 or >~ 1e-3)
+                const int rank_i = (h * rk + k) * rl + l;
+                const int rank_j = (hj[0] * rk + hj[1]) * rl + hj[2];
+                drop = rank_i < rank_j;
+              }
+            }
+            if (drop) {
+              // j keeps the point and collects i's multiplicity.  j cannot be dropped by this same
+              // operation (its image is i, of lower rank), and only i's thread writes grid[cj].
+              grid[cj] = (uint16_t)(grid[cj] + mi);
+              grid[c] = 0;
+            } else {
+              keep = true;
+            }
           }
         }
-        if (drop) {
-          // j keeps the point and collects i's multiplicity.  j cannot be dropped by this same
-          // operation (its image is i, of lower rank), and only i's thread writes grid[cj].
-          grid[cj] = (uint16_t)(grid[cj] + mi);
-          grid[c] = 0;
-        } else if (use_list) {
-          nxt[atomicAdd(&S.scan_carry, 1)] = (uint16_t)c;
-        }
+        if (use_list) warp_append(keep, (uint16_t)c, nxt, cnt);
       }
       __syncthreads();
-      if (use_list) {
-        n_visit = S.scan_carry;
-        __syncthreads();
-        if (tid == 0) S.scan_carry = 0;
-      }
-      __syncthreads();
+      if (use_list) n_visit = *cnt;
     }
   }
 
