@@ -206,8 +206,10 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // RB rows of JTJ are accumulated per pass over the chunk (RB * NF accumulators live in registers)
+// n_free <= 8: capped at 128 registers (4 CTAs/SM; the compiler otherwise takes 232 for 2 -- measured +8 % on cfg4
+// with 140 bytes of spills); the 16-parameter instantiation spills 1.5 KB under that cap and keeps 2 CTAs/SM.
 template <int NF, int RB>
-__global__ void __launch_bounds__(JR_THREADS)
+__global__ void __launch_bounds__(JR_THREADS, NF <= 8 ? 4 : 2)
 jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__restrict__ q, int n_q,
                        const double *__restrict__ params, int ldp, int batch, const double *__restrict__ Iobs,
                        const double *__restrict__ dI, long long ld_obs, const FreeSet F, double rel_step,
