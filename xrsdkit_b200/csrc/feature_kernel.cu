@@ -90,7 +90,7 @@ __device__ __forceinline__ double vertex_of(const Parabola &p) { return p.xbar -
 
 }  // namespace
 
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(512, 2)     // 64 registers: two CTAs per SM up to 4096 q-points (measured +19 %)
 feature_kernel(const double *__restrict__ q, int n, const double *__restrict__ I_all, int64_t ld_I, int batch,
                double *__restrict__ feat, int64_t ld_f) {
   extern __shared__ __align__(16) double smem[];

@@ -149,7 +149,7 @@ residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
 //     writes the outputs.  (A first version reduced inside the variant kernel by the last-finishing
 //     CTA of each system: that serial tail cost 25 % of the whole Jacobian.)
 template <bool RM, bool HX>
-__global__ void __launch_bounds__(EVAL_THREADS, HX ? 10 : 6)   // measured (cfg4): 6 x 80 regs 14.1 ms, 8 x 64 13.0, 10 x 48 (spills) 11.5, 12 x 40 14.4
+__global__ void __launch_bounds__(EVAL_THREADS, HX ? 10 : 6)   // measured on cfg4 (same box): 8 CTAs x 64 regs 11.8 ms, 10 x 48 (spills) 11.5, 12 x 40 14.4; 6 x 80 was 7 % behind 8
 jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ q, int n_q,
                          const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T, const FreeSet F,
                          double rel_step, double *__restrict__ Fvar, int q_per_cta, int n_tiles, int pattern_doubles,
