@@ -328,7 +328,7 @@ class Work(object):
 def ncu_traffic_bytes(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full
     summary of this round (profiles/), per launch; None when no capture matches the workload."""
-    name = {"cfg2": "r01b_ncu_cfg2_intensity.txt"}.get(workload)
+    name = {"cfg2": "r01c_ncu_cfg2_intensity.txt"}.get(workload)
     if name is None:
         return None
     try:
@@ -460,7 +460,7 @@ def run_gpu_arm(args):
     roofline = {
         "bound": "fp64", "achieved": achieved, "peak": fp64_tflops, "unit": "TFLOP/s", "frac": achieved / fp64_tflops,
         "traffic": ncu_traffic_bytes(args.workload) if B == 10000 else None,
-        "traffic_note": "ncu --set full capture of the same launch shape, profiles/r01_final_ncu_cfg2_intensity.txt; "
+        "traffic_note": "ncu --set full capture of the same launch shape, profiles/r01c_ncu_cfg2_intensity.txt; "
                         "algorithmic bytes per launch = %.0f (the rest of the pattern is still in L2 when the kernel ends)" % hbm_bytes,
         "kernel": kname, "kernel_ms": k_ms,
         "flops_per_unit": flops_unit, "units_per_launch": units,

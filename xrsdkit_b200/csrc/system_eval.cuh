@@ -134,7 +134,11 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
   // flip ceil() and put a jump into the difference quotient.
   if (prm_topo == nullptr) prm_topo = prm;
   const int tid = threadIdx.x;
-  for (int i = tid; i < q_count; i += EVAL_THREADS) I_sm[i] = 0.0;
+  // the noise model comes first in every layout the host lowers: it initialises the accumulator (one pass less
+  // over I_sm, which in direct mode is a global-memory round trip); any other first population starts from zero
+  const bool noise_first = L.n_pops > 0 && (L.pops[0].kind == XRSD_POP_NOISE_FLAT || L.pops[0].kind == XRSD_POP_NOISE_LOW_Q);
+  if (!noise_first)
+    for (int i = tid; i < q_count; i += EVAL_THREADS) I_sm[i] = 0.0;
   const int span = EVAL_THREADS * QPT;
   // strictly ascending q over the span enables the far-field interpolation of crystalline sums
   bool q_sorted = false;
@@ -157,14 +161,18 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
       // ---------------------------------------------------------------- noise (system/noise.py:50-63)
       case XRSD_POP_NOISE_FLAT: {
         const double I0 = prm[pop.p_I0];
-        for (int i = tid; i < q_count; i += EVAL_THREADS) I_sm[i] += I0 * 1.0;
+        if (ip == 0) {
+          for (int i = tid; i < q_count; i += EVAL_THREADS) I_sm[i] = I0 * 1.0;
+        } else {
+          for (int i = tid; i < q_count; i += EVAL_THREADS) I_sm[i] += I0 * 1.0;
+        }
       } break;
       case XRSD_POP_NOISE_LOW_Q: {
         const double I0 = prm[pop.p_I0], f = prm[pop.p_flat_fraction];
         const double beam = I0 * (1.0 - f);
         const GPConst gp = gp_constants(prm[pop.p_rg], prm[pop.p_D]);
         for (int i = tid; i < q_count; i += EVAL_THREADS) {
-          double v = I_sm[i];
+          double v = (ip == 0) ? 0.0 : I_sm[i];
           v += beam * guinier_porod(q[q_begin + i], gp);
           v += I0 * f * 1.0;
           I_sm[i] = v;
