@@ -71,7 +71,7 @@ def test_features_match_reference_outputs():
     print("worst feature error", worst, "reductions", worst_red, "over", len(cases), "patterns")
 
 
-@pytest.mark.parametrize("n", [8, 64, 560, 1001, 1024, 4096, 8192])
+@pytest.mark.parametrize("n", [8, 64, 560, 1001, 1024, 1800, 4096, 8192])   # 1800: dynamic + static smem straddles 48 KB
 def test_features_match_oracle_any_length(n):
     from oracle import xrsd_oracle as xo
     from xrsdkit_b200.tools import profiler

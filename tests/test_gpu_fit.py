@@ -276,3 +276,56 @@ def test_fit_api_nelder_mead_mode(eng):
     assert b.fit_report["final_objective"] == pytest.approx(a.fit_report["final_objective"], rel=1e-2)
     with pytest.raises(ValueError):
         fit(guess, q, I, method="simplex?")
+
+
+@pytest.mark.parametrize("log_mode,n_extra", [(True, 0), (False, 0), (True, 1)])
+def test_jacobian_crystal_layout_matches_forward_differences_of_the_intensity_path(eng, log_mode, n_extra):
+    """cfg4 layout (crystal + Guinier-Porod + noise): the variants accumulate in place in their slabs and the
+    reduction streams them through its cp.async ring.  JTJ / JTr / chi2 must equal what forward differences of the
+    (oracle-checked) batched intensity path give with the same relative step -- with explicit dI, a q_range that
+    cuts both ends, a pattern length that is no multiple of the CTA width, and 8 or 9 free parameters (the 9th,
+    gp.D, selects the 16-parameter instantiation of the reduction)."""
+    from helpers import cfg4_system, cfg4_params
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg4_system(System)
+    q = np.linspace(0.01, 1.0, 1237)
+    lay = batch.layout_of(s, q)
+    B = 5
+    P = cfg4_params(lay, B, seed=21)
+    names = ["noise__I0", "x__I0", "x__a", "x__hwhm_g", "x__hwhm_l", "x__r", "gp__I0", "gp__rg"] + ["gp__D"] * n_extra
+    if n_extra:
+        P[:, lay.slot("gp__D")] = 3.7
+    free = [lay.slot(k) for k in names]
+    rs = np.random.RandomState(2)
+    I_true = batch.compute_intensity_batch(lay, q, P)
+    Iobs = I_true * (1 + 0.02 * rs.randn(*I_true.shape))
+    dI = 0.05 * Iobs + 0.01
+    P0 = P.copy()
+    P0[:, free] *= 1 + 0.01 * rs.uniform(-1, 1, (B, len(free)))
+    q_range = (0.05, 0.9)
+    obj = eng.objective(True, log_mode, q_range, has_dI=True)
+    d_q, d_p, d_I, d_dI = eng.to_device(q), eng.to_device(P0), eng.to_device(Iobs), eng.to_device(dI)
+    tables = eng.build_tables(lay, d_p, B, params_host=P0)
+    JTJ, JTr, chi2 = eng.jacobian(lay, obj, d_q, d_p, d_I, d_dI, len(q), free, tables, rel_step=1e-6)
+    JTJ, JTr, chi2 = JTJ.cpu().numpy(), JTr.cpu().numpy(), chi2.cpu().numpy()
+    # the same forward differences from the intensity path; the base system's table serves every variant (H9)
+    fit = (Iobs > 0) & (q >= q_range[0]) & (q <= q_range[1])
+    f = (lambda x: np.log(x)) if log_mode else (lambda x: x)
+    I0 = eng.intensity(lay, d_q, d_p, tables=tables).cpu().numpy()
+    for b in range(B):
+        m = fit[b] & ((I0[b] > 0) if log_mode else True)
+        w = dI[b] ** 2
+        w = np.where(m, w, 0.0) / np.sum(w[m])
+        r = np.where(m, f(np.where(m, I0[b], 1.0)) - f(np.where(m, Iobs[b], 1.0)), 0.0)
+        J = np.zeros((len(q), len(free)))
+        for j, sl in enumerate(free):
+            row = P0.copy()
+            h = abs(row[b, sl]) * 1e-6
+            row[b, sl] += h
+            Ij = eng.intensity(lay, d_q, eng.to_device(row), tables=tables).cpu().numpy()[b]
+            J[:, j] = np.where(m, (f(np.where(m, Ij, 1.0)) - f(np.where(m, I0[b], 1.0))) / h, 0.0)
+        assert chi2[b] == pytest.approx(np.sum(w * r * r), rel=1e-9)
+        want_r, want_J = J.T @ (w * r), J.T @ (w[:, None] * J)
+        np.testing.assert_allclose(JTr[b], want_r, rtol=2e-5, atol=1e-8 * np.abs(want_r).max())
+        np.testing.assert_allclose(JTJ[b], want_J, rtol=2e-5, atol=1e-8 * np.abs(want_J).max())

@@ -422,7 +422,7 @@ extern "C" cudaError_t xrsd_launch_features(const double *d_q, int n_q, const do
                                  double *d_feat, int64_t ld_f, cudaStream_t stream) {
   const size_t smem = xrsd_feature_smem_bytes_impl(n_q);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > configured) {      // static shared memory counts against the 48 KB default too: always opt in
     cudaError_t e = cudaFuncSetAttribute(feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;

@@ -544,7 +544,7 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
   const size_t ring_bytes = (size_t)JR_STAGES * (F.n_var + layout->n_pops + 2) * JR_THREADS * sizeof(double);
   static size_t ring_set[2] = {0, 0};
   const int which = n_free <= 8 ? 0 : 1;
-  if (ring_bytes > 48 * 1024 && ring_bytes > ring_set[which]) {
+  if (ring_bytes > ring_set[which]) {      // (static shared memory counts against the 48 KB default too: always opt in)
     e = which == 0 ? cudaFuncSetAttribute(jacobian_reduce_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)
                    : cudaFuncSetAttribute(jacobian_reduce_kernel<XRSD_MAX_FREE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
     if (e != cudaSuccess) return e;
