@@ -329,3 +329,23 @@ def test_jacobian_crystal_layout_matches_forward_differences_of_the_intensity_pa
         want_r, want_J = J.T @ (w * r), J.T @ (w[:, None] * J)
         np.testing.assert_allclose(JTr[b], want_r, rtol=2e-5, atol=1e-8 * np.abs(want_r).max())
         np.testing.assert_allclose(JTJ[b], want_J, rtol=2e-5, atol=1e-8 * np.abs(want_J).max())
+
+
+def test_lm_with_nine_free_parameters(eng):
+    """More than 8 free parameters: the 16-wide instantiations of the reduction and the Cholesky step."""
+    from helpers import cfg4_system, cfg4_params
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg4_system(System)
+    q = np.linspace(0.01, 1.0, 2048)
+    lay = batch.layout_of(s, q)
+    n = 6
+    truth = cfg4_params(lay, n, seed=33)
+    truth[:, lay.slot("gp__D")] = 3.6
+    Iobs = batch.compute_intensity_batch(lay, q, truth)
+    free = [lay.slot(k) for k in ("noise__I0", "x__I0", "x__a", "x__hwhm_g", "x__hwhm_l", "x__r", "gp__I0", "gp__rg", "gp__D")]
+    start = truth.copy()
+    start[:, free] *= 1 + 0.02 * np.random.RandomState(8).uniform(-1, 1, (n, len(free)))
+    res = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=40)
+    assert np.all(res.chi2 <= res.chi2_init * (1 + 1e-12))
+    assert np.median(res.chi2 / res.chi2_init) < 1e-2

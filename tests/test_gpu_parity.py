@@ -438,3 +438,24 @@ def test_large_cell_without_usable_symmetry(ref_tables, eng):
     ref = orc.system_intensity(q, s.to_dict(), **ref_tables)
     err, same = rel_err(s.compute_intensity(q), ref)
     assert same and err <= TOL_F64, err
+
+
+def test_reflection_table_long_candidate_list_with_symmetry(golden_definitions, eng):
+    """F_cubic a = 80, q_max = 1: 8870 candidates, more than the alive-list capacity, so the greedy reduction walks
+    the candidate box itself (the path cfg3-sized cells never take); reduced list and multiplicities bit-exact
+    against the oracle's O(N^2) restatement."""
+    from oracle import xrsd_oracle as orc
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import lowering
+    pgs = golden_definitions["sg_point_groups"]
+    hkl, mult, _ = orc.reflection_table("F_cubic", dict(a=80.0), 0.0, 1.0, pgs["Fm-3m"])
+    s = System(x=dict(structure="crystalline", form="spherical",
+                      settings={"lattice": "F_cubic", "space_group": "Fm-3m", "q_max": 1.0},
+                      parameters={"a": {"value": 80.0}, "r": {"value": 20.0}}), source_wavelength=0.8265617)
+    lay = lowering.lower_system(s, np.array([0.1, 1.0]))
+    T = eng.build_tables(lay, eng.to_device(lay.values[None, :]), 1, params_host=lay.values[None, :], export_reflections=True)
+    assert int(T.n_all[0].item()) == int(np.sum(mult)) > 5 * 1024
+    n = int(T.n_refl[0].item())
+    got = T.refl_hkl[0, :n].cpu().numpy()
+    assert got[:, :3].tolist() == hkl.astype(int).tolist()
+    assert got[:, 3].tolist() == np.asarray(mult).astype(int).tolist()
