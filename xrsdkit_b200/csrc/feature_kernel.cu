@@ -12,7 +12,7 @@
 // i.e. 26 bytes per q point, 208 KB at the 8192-point limit.  Every feature is a reduction over
 // the pattern (sums, arg-extrema, windowed correlations), so HBM traffic is one read of I per
 // pattern and 168 bytes out; the arithmetic is dominated by the windowed correlations
-// (n x 101 x 2 passes).
+// (n x 101).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -310,19 +310,17 @@ feature_kernel(const double *__restrict__ q, int n, const double *__restrict__ I
     for (int k = tid; k < m; k += NT) {
       const int lo = max(0, k - HUMP_W), hi = min(m, k + HUMP_W + 1);
       const double xk = B_s[k], cntw = (double)(hi - lo);
-      double sy = 0.0, sx = 0.0;
+      // one pass over the window with the values taken relative to the centre point (y - y_k, (x - x_k)^2): the
+      // centred sums follow from the raw ones with a cancellation factor of order one
+      const double yk = A_s[k];
+      double sy = 0.0, sx = 0.0, syy = 0.0, sxx = 0.0, sxy = 0.0;
       for (int j = lo; j < hi; ++j) {
-        const double dx = B_s[j] - xk;
-        sy += A_s[j];
-        sx += dx * dx;
+        const double dx = B_s[j] - xk, x2 = dx * dx, yy = A_s[j] - yk;
+        sy += yy; sx += x2;
+        syy = fma(yy, yy, syy); sxx = fma(x2, x2, sxx); sxy = fma(yy, x2, sxy);
       }
-      const double my = sy / cntw, mx = sx / cntw;
-      double syy = 0.0, sxx = 0.0, sxy = 0.0;
-      for (int j = lo; j < hi; ++j) {
-        const double dx = B_s[j] - xk;
-        const double ey = A_s[j] - my, ex = dx * dx - mx;
-        syy += ey * ey; sxx += ex * ex; sxy += ey * ex;
-      }
+      syy -= sy * sy / cntw; sxx -= sx * sx / cntw; sxy -= sy * sx / cntw;
+      if (syy < 0.0) syy = 0.0;
       const double r = sxy / (sqrt(syy) * sqrt(sxx));
       const double hump = -1.0 * A_s[k] * r, trough = sqrt(syy / cntw) * r;
       if (beats(hump, k, hbest, hidx)) { hbest = hump; hidx = k; }
