@@ -47,6 +47,20 @@ class TableSet(object):
         c.refl_hkl = self.refl_hkl.data_ptr() if cap_refl else None
         self.c = c
 
+    def take_rows_from(self, other, rows):
+        """Overwrite the tables of the systems flagged in `rows` (bool [n_tables]) with `other`'s, in place (the
+        device pointers in self.c stay valid).  Used by the LM loop: an accepted trial step makes the trial tables
+        the system's tables, so nothing has to be rebuilt.  Returns False when the two sets are not congruent."""
+        if (other.n_tables, other.cap_shell, other.n_pairs) != (self.n_tables, self.cap_shell, self.n_pairs):
+            return False
+        for name in ("n_shell", "n_refl", "n_all", "status"):
+            a, b = getattr(self, name), getattr(other, name)
+            a.copy_(b.where(rows, a))
+        m3 = rows[:, None, None]
+        self.shell_hkl.copy_(other.shell_hkl.where(m3, self.shell_hkl))
+        self.shell_geo.copy_(other.shell_geo.where(m3, self.shell_geo))
+        return True
+
 
 class Engine(object):
 

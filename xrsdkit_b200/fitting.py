@@ -107,13 +107,18 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
                                           d_trial.shape[1], batch, C.byref(t_tables.c) if t_tables is not None else None,
                                           d_I.data_ptr(), d_dI.data_ptr() if d_dI is not None else None, ld_obs,
                                           d_chi2_t.data_ptr(), res_ws.data_ptr(), d_active.data_ptr(), stream))
+        if layout.n_xtal:
+            nacc_before = d_nacc.clone()
         abi.check(lib.xrsd_lm_update(d_p.data_ptr(), d_p.shape[1], batch, d_trial.data_ptr(), d_chi2.data_ptr(),
                                      d_chi2_t.data_ptr(), d_lambda.data_ptr(), d_active.data_ptr(), d_nacc.data_ptr(),
                                      float(up), float(down), float(ftol), float(lambda_max), stream))
         eng.launches += 3
         if layout.n_xtal:
-            # accepted systems now sit at `trial`: their tables are the trial tables
-            tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=tables, check=False, active=d_active)
+            # accepted systems now sit at `trial`: their tables are the trial tables -- copy those rows (3 KB per
+            # system) instead of building them again
+            accepted = (d_nacc != nacc_before).repeat_interleave(layout.n_xtal)
+            if not tables.take_rows_from(t_tables, accepted):
+                tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=tables, check=False, active=d_active)
         if it % 5 == 4:
             flags = torch.stack([d_active.any().to(torch.int32),
                                  tables.status.max() if tables is not None else torch.zeros((), dtype=torch.int32, device=eng.device),
