@@ -419,12 +419,9 @@ extern "C" size_t xrsd_feature_smem_bytes_impl(int n_q) { return (((size_t)n_q +
 extern "C" cudaError_t xrsd_launch_features(const double *d_q, int n_q, const double *d_I, int64_t ld_I, int batch,
                                  double *d_feat, int64_t ld_f, cudaStream_t stream) {
   const size_t smem = xrsd_feature_smem_bytes_impl(n_q);
-  static size_t configured = 0;
-  if (smem > configured) {      // static shared memory counts against the 48 KB default too: always opt in
-    cudaError_t e = cudaFuncSetAttribute(feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  // opt in on every launch: the attribute is per device and static shared memory counts against the 48 KB default too
+  cudaError_t e = cudaFuncSetAttribute(feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   const int threads = n_q >= 2048 ? 512 : 256;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -542,14 +542,11 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
   const int n_chunks = (n_q + chunk_q - 1) / chunk_q;
   if ((long long)batch * n_chunks > 2147483647LL) return cudaErrorInvalidConfiguration;
   const size_t ring_bytes = (size_t)JR_STAGES * (F.n_var + layout->n_pops + 2) * JR_THREADS * sizeof(double);
-  static size_t ring_set[2] = {0, 0};
-  const int which = n_free <= 8 ? 0 : 1;
-  if (ring_bytes > ring_set[which]) {      // (static shared memory counts against the 48 KB default too: always opt in)
-    e = which == 0 ? cudaFuncSetAttribute(jacobian_reduce_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)
-                   : cudaFuncSetAttribute(jacobian_reduce_kernel<XRSD_MAX_FREE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
-    if (e != cudaSuccess) return e;
-    ring_set[which] = ring_bytes;
-  }
+  // opt in on every launch (microseconds; the attribute is per device and static shared memory counts against the
+  // 48 KB default too)
+  e = n_free <= 8 ? cudaFuncSetAttribute(jacobian_reduce_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)
+                  : cudaFuncSetAttribute(jacobian_reduce_kernel<XRSD_MAX_FREE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
+  if (e != cudaSuccess) return e;
   if (n_free <= 8)
     jacobian_reduce_kernel<8, 8><<<batch * n_chunks, JR_THREADS, ring_bytes, stream>>>(
         layout->n_pops, *obj, d_q, n_q, d_params, ldp, batch, d_Iobs, d_dI, ld_obs, F, rel_step, d_Fvar, d_acc, d_tickets, d_JTJ,
