@@ -50,7 +50,7 @@ def make_workload(name, batch):
     from helpers import cfg2_system, cfg2_params, cfg3_system, cfg3_params, cfg4_system, cfg4_params
     from xrsdkit_b200.system import System
     from xrsdkit_b200 import batch as xb
-    if name == "cfg2":
+    if name in ("cfg2", "cfg5s"):
         s = cfg2_system(System)
         q = np.linspace(0.01, 0.5, 4096)
         lay = xb.layout_of(s, q)
@@ -159,7 +159,9 @@ def workload_name(w):
         "cfg2": "cfg2: polydisperse spheres (r_normal, 50-pt quadrature) + hard_spheres S(q), 4096-pt q, 10k parameter sets per GPU",
         "cfg3": "cfg3: crystalline FCC Fm-3m, spherical form, voigt, q_max=1.0, 8192-pt q, table build + profile sum",
         "cfg4": "cfg4: FCC crystal + guinier_porod + flat noise, 8192-pt q, residual + FD Jacobian (8 free parameters)",
-        "cfg5": "cfg5: batched Levenberg-Marquardt fit of cfg4-like crystal systems",
+        "cfg5": "cfg5: batched Levenberg-Marquardt fit of cfg4-like crystal systems (the expensive half of the mixed batch; "
+                "the sphere half and the 50/50 figure are in config.mixed)",
+        "cfg5s": "cfg5 sphere half: batched Levenberg-Marquardt fit of cfg2-like hard-sphere systems, 4096-pt q",
     }[w]
 
 
@@ -254,9 +256,11 @@ class Work(object):
         self.evals_per_unit = 1.0
         self.metric, self.unit = "I(q) pattern evals/sec", "patterns/s"
         self.lm_iters = lm_iters
-        if name in ("cfg4", "cfg5"):
+        if name in ("cfg4", "cfg5", "cfg5s"):
             lay = self.lay
-            self.free = [lay.slot(k) for k in ("noise__I0", "x__I0", "x__a", "x__hwhm_g", "x__hwhm_l", "x__r", "gp__I0", "gp__rg")]
+            names = ("noise__I0", "x__I0", "x__a", "x__hwhm_g", "x__hwhm_l", "x__r", "gp__I0", "gp__rg") if lay.n_xtal else \
+                    ("noise__I0", "p__I0", "p__r", "p__sigma", "p__r_hard", "p__v_fraction")
+            self.free = [lay.slot(k) for k in names]
             g = torch.Generator(dev).manual_seed(seed + 5)
             self.Iobs = eng.intensity(lay, self.d_q, self.d_params[0], tables=self.tables[0]).clone()
             self.Iobs *= 1 + 0.02 * torch.randn(self.Iobs.shape, dtype=torch.float64, device=dev, generator=g)
@@ -280,7 +284,7 @@ class Work(object):
             t = eng.build_tables(lay, self.start, B, max_cells=self.max_cells, check=False, reuse=self.tables[1])
             self.jout = eng.jacobian(lay, self.obj, self.d_q, self.start, self.Iobs, None, self.n_q, self.free, t, 1e-6,
                                      out=self.jout)
-        elif self.name == "cfg5":    # a whole batched Levenberg-Marquardt fit
+        elif self.name in ("cfg5", "cfg5s"):    # a whole batched Levenberg-Marquardt fit
             from xrsdkit_b200 import fitting
             self.res = fitting.lm_fit_batch(lay, self.d_q, self.Iobs, self.start, self.free, max_iter=self.lm_iters,
                                             eng=eng, return_device=True)
@@ -545,6 +549,27 @@ def run_gpu_arm(args):
             secondary["cfg4"]["cpu_patterns_per_s"] = n3 / dt3        # one evaluation = one crystalline pattern (+GP, noise)
             secondary["cpu_note"] = "%d cores, %d cfg3 patterns, numpy oracle port; cfg4 evaluations cost the same per pattern" % (cores, n3)
 
+    mixed = None
+    if args.workload == "cfg5":
+        # BASELINE config 5 is a 50/50 mix of sphere and crystal systems; the headline above is the crystal half
+        # alone (the expensive one).  Time the sphere half on this GPU and combine: a mixed batch of B fits takes
+        # B/2 / f_sphere + B/2 / f_crystal.
+        try:
+            del W.Iobs, W.start
+            torch.cuda.empty_cache()
+            Ws = Work(eng, "cfg5s", B, 2000, args.lm_iters)
+            ms_s, _ = Ws.timed(max(1, min(args.steps, 3)), 1)
+            f_s = B * max(1, min(args.steps, 3)) / (ms_s * 1e-3)
+            f_x = value / world
+            r = Ws.res
+            mixed = {"sphere_fits_per_s_per_gpu": f_s, "crystal_fits_per_s_per_gpu": f_x,
+                     "mixed_50_50_fits_per_s": world * 2.0 / (1.0 / f_s + 1.0 / f_x),
+                     "sphere_median_chi2_ratio": float((r.chi2 / r.chi2_init).median().item()),
+                     "note": "sphere half: cfg2-like hard-sphere systems, 4096-pt q, 6 free parameters, same LM settings; "
+                             "measured on rank 0 and scaled by the GPU count"}
+        except Exception as e:
+            mixed = {"error": repr(e)}
+
     line = {
         "metric": W.metric, "value": value, "unit": W.unit, "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -556,7 +581,7 @@ def run_gpu_arm(args):
                                         "derivatives are analytic") if args.workload == "cfg4" else None,
                    "q_evals_per_s": value * n_q,
                    "l2": "each step writes or reads %.0f MB of patterns (L2 is 126 MB) and rotates over 4 parameter matrices" % (8e-6 * B * n_q),
-                   "checksum": checksum},
+                   "checksum": checksum, "mixed": mixed},
         "e2e": {"value": e2e, "unit": W.unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps, "api": api},
         "gpu_launches": launches,
         "clocks": clocks,
