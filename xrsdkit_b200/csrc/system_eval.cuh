@@ -134,11 +134,11 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
   // flip ceil() and put a jump into the difference quotient.
   if (prm_topo == nullptr) prm_topo = prm;
   const int tid = threadIdx.x;
-  // the noise model comes first in every layout the host lowers: it initialises the accumulator (one pass less
-  // over I_sm, which in direct mode is a global-memory round trip); any other first population starts from zero
-  const bool noise_first = L.n_pops > 0 && (L.pops[0].kind == XRSD_POP_NOISE_FLAT || L.pops[0].kind == XRSD_POP_NOISE_LOW_Q);
-  if (!noise_first)
-    for (int i = tid; i < q_count; i += EVAL_THREADS) I_sm[i] = 0.0;
+  // Nothing is written until a population has per-q values: a leading flat noise level is carried as a constant
+  // (`pending`) and folded into the first per-q write, which is then a plain store -- no zero fill, no separate
+  // noise pass, and in direct mode (I_sm in global memory) no read for the first population.
+  double pending = 0.0;
+  bool fresh = true;                   // CTA-uniform: I_sm holds nothing yet
   const int span = EVAL_THREADS * QPT;
   // strictly ascending q over the span enables the far-field interpolation of crystalline sums
   bool q_sorted = false;
@@ -157,12 +157,13 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
   for (int ip = 0; ip < L.n_pops; ++ip) {
     const xrsd_pop_t &pop = L.pops[ip];
     __syncthreads();
+    bool wrote = false;                // this population stored per-q values for the whole span
     switch (pop.kind) {
       // ---------------------------------------------------------------- noise (system/noise.py:50-63)
       case XRSD_POP_NOISE_FLAT: {
         const double I0 = prm[pop.p_I0];
-        if (ip == 0) {
-          for (int i = tid; i < q_count; i += EVAL_THREADS) I_sm[i] = I0 * 1.0;
+        if (fresh) {
+          pending += I0 * 1.0;
         } else {
           for (int i = tid; i < q_count; i += EVAL_THREADS) I_sm[i] += I0 * 1.0;
         }
@@ -172,14 +173,16 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         const double beam = I0 * (1.0 - f);
         const GPConst gp = gp_constants(prm[pop.p_rg], prm[pop.p_D]);
         for (int i = tid; i < q_count; i += EVAL_THREADS) {
-          double v = (ip == 0) ? 0.0 : I_sm[i];
+          double v = fresh ? pending : I_sm[i];
           v += beam * guinier_porod(q[q_begin + i], gp);
           v += I0 * f * 1.0;
           I_sm[i] = v;
         }
+        wrote = true;
       } break;
       // ---------------------------------------------------------------- diffuse / disordered
       case XRSD_POP_NONCRYSTALLINE: {
+        wrote = true;
         const double I0 = prm[pop.p_I0];
         HSConst hs;
         if (pop.disordered) hs = hs_constants(prm[pop.p_r_hard], prm[pop.p_v_fraction]);
@@ -342,7 +345,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               num *= (1.0 - hs.nc0);
               dn *= (1.0 - hard_sphere_nc(qv[j], hs, q0[j], sh[j], ch[j]));
             }
-            I_sm[i] += num / dn;
+            I_sm[i] = (fresh ? pending : I_sm[i]) + num / dn;
           }
         }
       } break;
@@ -351,6 +354,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         const int t = b * L.n_xtal + pop.table_slot;
         const int n_shell = T.n_shell[t];
         if (n_shell <= 0) break;                                   // scattering/__init__.py:277-278
+        wrote = true;
         const int n_sp = pop.n_species;
         const int n_pairs = n_sp * (n_sp + 1) / 2;
         const int32_t *sh_hkl = T.shell_hkl + (size_t)t * T.cap_shell * 4;
@@ -449,7 +453,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
             const double c2 = (fabs(st) <= 1.0) ? fma(-2.0 * st, st, 1.0) : NAN;
             pz = 0.5 * (1.0 + c2 * c2);
           }
-          I_sm[i] += I0 * (pz * a_sum * inv_norm);                 // I0 * (pz*I/I0_norm)
+          I_sm[i] = (fresh ? pending : I_sm[i]) + I0 * (pz * a_sum * inv_norm);   // I0 * (pz*I/I0_norm)
         };
         // ---- far-field interpolation path ------------------------------------------------------
         // For a run of EVAL_THREADS consecutive q-points (centre c, half-width H) every shell with
@@ -611,17 +615,20 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               const double c2 = (fabs(st) <= 1.0) ? fma(-2.0 * st, st, 1.0) : NAN;
               pz = 0.5 * (1.0 + c2 * c2);
             }
-            I_sm[i] += I0 * (pz * a_sum / norm);                   // I0 * (pz*I/I0_norm)
+            I_sm[i] = (fresh ? pending : I_sm[i]) + I0 * (pz * a_sum / norm);     // I0 * (pz*I/I0_norm)
           }
         }
       } break;
       default: break;
     }
+    if (wrote) { fresh = false; pending = 0.0; }
     if (cum_out != nullptr) {
       double *dst = cum_out + (size_t)ip * cum_stride;
-      for (int i = tid; i < q_count; i += EVAL_THREADS) dst[i] = I_sm[i];   // each thread owns i = tid (mod EVAL_THREADS)
+      for (int i = tid; i < q_count; i += EVAL_THREADS) dst[i] = fresh ? pending : I_sm[i];   // each thread owns i = tid (mod EVAL_THREADS)
     }
   }
+  if (fresh)                           // no population wrote (noise only, or every table empty)
+    for (int i = tid; i < q_count; i += EVAL_THREADS) I_sm[i] = pending;
   __syncthreads();
 }
 
