@@ -105,7 +105,7 @@ def compute_intensity_sharded(layout, q, params, group=None, gather=True, eng=No
 _pinned_cache = {}
 
 
-def compute_intensity_pinned(layout, q_host, params_host, out_host, chunks=4, eng=None):
+def compute_intensity_pinned(layout, q_host, params_host, out_host, chunks=None, eng=None):
     """Host-buffer path: params_host [B, n_params] and out_host [B, n_q] are PINNED host tensors.
 
     The batch is cut into `chunks` slices that alternate between two CUDA streams, so the
@@ -114,6 +114,8 @@ def compute_intensity_pinned(layout, q_host, params_host, out_host, chunks=4, en
     eng = eng or _engine.get_engine()
     torch = eng.torch
     B, n_q = params_host.shape[0], q_host.shape[0]
+    if chunks is None:       # measured on cfg2 (10^4 x 4096): 2 slices 49 GB/s of D2H, 4: 52, 8: 54.0, 16: 54.6, 32: 54.4
+        chunks = min(16, max(1, B // 512))
     chunks = max(1, min(chunks, B))
     rows = (B + chunks - 1) // chunks
     key = (str(eng.device), rows, n_q, params_host.shape[1])
