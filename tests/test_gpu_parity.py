@@ -459,3 +459,40 @@ def test_reflection_table_long_candidate_list_with_symmetry(golden_definitions, 
     got = T.refl_hkl[0, :n].cpu().numpy()
     assert got[:, :3].tolist() == hkl.astype(int).tolist()
     assert got[:, 3].tolist() == np.asarray(mult).astype(int).tolist()
+
+
+def test_pinned_host_pipeline_matches_the_device_path(eng):
+    """batch.compute_intensity_pinned (slices alternating over two streams, tables built without per-slice status
+    read-back) against compute_intensity_batch: a sphere layout, a crystal layout, and a crystal layout whose
+    tables outgrow the default capacities (the flags OR-ed on the device send the batch through the checked path)."""
+    import torch
+    from helpers import cfg2_system, cfg2_params, cfg4_system, cfg4_params
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    cases = []
+    s = cfg2_system(System)
+    q = np.linspace(0.01, 0.5, 777)
+    lay = batch.layout_of(s, q)
+    cases.append((lay, q, cfg2_params(lay, 1500)))
+    s = cfg4_system(System)
+    q = np.linspace(0.01, 1.0, 1100)
+    lay = batch.layout_of(s, q)
+    cases.append((lay, q, cfg4_params(lay, 1300)))
+    big = System(x=dict(structure="crystalline", form="spherical",
+                        settings={"lattice": "P_orthorhombic", "space_group": "Pmmm", "q_max": 0.9},
+                        parameters={"a": {"value": 60.0}, "b": {"value": 70.0}, "c": {"value": 80.0}, "r": {"value": 20.0}}),
+                 source_wavelength=0.8265617)
+    q = np.linspace(0.05, 0.9, 600)
+    lay = batch.layout_of(big, q)
+    P = np.repeat(lay.values[None, :], 3, axis=0)
+    P[:, lay.slot("x__a")] = [60.0, 61.0, 59.0]
+    cases.append((lay, q, P))
+    for lay, q, P in cases:
+        want = batch.compute_intensity_batch(lay, q, P)
+        p_host = torch.as_tensor(P).pin_memory()
+        q_host = torch.as_tensor(q).pin_memory()
+        out = torch.empty((len(P), len(q)), dtype=torch.float64).pin_memory()
+        for chunks in (None, 3):
+            out.zero_()
+            batch.compute_intensity_pinned(lay, q_host, p_host, out, chunks=chunks, eng=eng)
+            np.testing.assert_allclose(out.numpy(), want, rtol=1e-12, atol=0)

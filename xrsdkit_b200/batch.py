@@ -8,6 +8,8 @@
 Multi-GPU: the batch is independent per row, so each rank of a torch.distributed job takes a
 contiguous slice (shard_bounds) and the results meet in one all_gather at the end.
 """
+import os
+
 import numpy as np
 
 from . import engine as _engine, fitting, lowering
@@ -115,7 +117,7 @@ def compute_intensity_pinned(layout, q_host, params_host, out_host, chunks=None,
     torch = eng.torch
     B, n_q = params_host.shape[0], q_host.shape[0]
     if chunks is None:       # measured on cfg2 (10^4 x 4096): 2 slices 49 GB/s of D2H, 4: 52, 8: 54.0, 16: 54.6, 32: 54.4
-        chunks = min(16, max(1, B // 512))
+        chunks = int(os.environ.get("XRSD_PINNED_CHUNKS", 0)) or min(16, max(1, B // 512))
     chunks = max(1, min(chunks, B))
     rows = (B + chunks - 1) // chunks
     key = (str(eng.device), rows, n_q, params_host.shape[1])
@@ -129,7 +131,15 @@ def compute_intensity_pinned(layout, q_host, params_host, out_host, chunks=None,
     ws = _pinned_cache[key]
     cur = torch.cuda.current_stream(eng.device)
     ws["d_q"].copy_(q_host, non_blocking=True)
-    p_np = params_host.numpy() if layout.n_xtal else None
+    max_cells = bad = None
+    if layout.n_xtal:
+        # one candidate-box bound for the whole batch; the slices build their tables without reading the status
+        # back (that read would drain the pipeline once per slice): overflow flags are OR-ed on the device and
+        # looked at once, after the last slice
+        max_cells = lowering.max_cells(layout, params_host.numpy())
+        bad = ws.setdefault("bad", torch.zeros(2, dtype=torch.int32, device=eng.device))    # one flag per stream
+        bad.zero_()
+        ws.setdefault("tables", [None, None])
     for s in ws["streams"]:
         s.wait_stream(cur)
     for c in range(chunks):
@@ -140,11 +150,22 @@ def compute_intensity_pinned(layout, q_host, params_host, out_host, chunks=None,
         with torch.cuda.stream(ws["streams"][k]):
             d_p = ws["d_p"][k][:hi - lo]
             d_p.copy_(params_host[lo:hi], non_blocking=True)
-            tables = eng.build_tables(layout, d_p, hi - lo, params_host=p_np[lo:hi]) if layout.n_xtal else None
+            tables = None
+            if layout.n_xtal:
+                reuse = ws["tables"][k] if hi - lo == rows else None
+                tables = eng.build_tables(layout, d_p, hi - lo, max_cells=max_cells, check=False, reuse=reuse)
+                if hi - lo == rows:
+                    ws["tables"][k] = tables
+                bad[k:k + 1].copy_(torch.maximum(bad[k:k + 1], tables.status.max().reshape(1)))
             d_I = ws["d_I"][k][:hi - lo]
             eng.intensity(layout, ws["d_q"], d_p, tables=tables, out=d_I)
             out_host[lo:hi].copy_(d_I, non_blocking=True)
     for s in ws["streams"]:
         cur.wait_stream(s)
     cur.synchronize()
+    if bad is not None and int(bad.max().item()) != 0:
+        # a table outgrew the default capacities: redo the batch through the checked, self-growing path
+        d_p = eng.to_device(params_host)
+        tables = eng.build_tables(layout, d_p, B, params_host=params_host.numpy())
+        out_host.copy_(eng.intensity(layout, ws["d_q"], d_p, tables=tables))
     return out_host
