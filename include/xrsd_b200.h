@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define XRSD_ABI_VERSION 1
+#define XRSD_ABI_VERSION 2
 
 #define XRSD_MAX_POPS 6      /* noise model + up to 5 populations per system layout   */
 #define XRSD_MAX_SPECIES 4   /* species (atoms) per crystalline population             */
@@ -194,23 +194,25 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
  * xrsd_jacobian_workspace_bytes() bytes; the accumulator / ticket area behind the variant slabs
  * must be zero before the FIRST call with a given (n_q, batch, n_free) (the reduction re-zeroes
  * it; zeroing the whole workspace once is the simple way).  ties[n_tie][2] (HOST, may be NULL) are
- * equality constraints (dst slot, src slot): the form of constraint_expr found in xrsdkit's own
- * fitted systems ("particle__r"); the tied slot follows its source in every variant.  Reflection tables
+ * constraints (dst slot, src slot) with tie_coef[n_tie][2] = (scale, offset) (HOST; NULL = identity):
+ * params[dst] = scale * params[src] + offset -- constraint_expr values that are affine in one other
+ * parameter (xrsdkit's own fitted systems use the plain name, "particle__r"); the tied slot follows
+ * its source in every variant.  Reflection tables
  * and the radius counts of size quadratures are held fixed inside one evaluation. */
 int64_t xrsd_jacobian_workspace_bytes(int32_t n_q, int32_t batch, int32_t n_free);
 int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj,
                         const double *d_q, int32_t n_q, const double *d_params, int32_t ld_params,
                         int32_t batch, const xrsd_tables_t *tables,
                         const double *d_Iobs, const double *d_dI, int64_t ld_obs,
-                        const int32_t *free_idx, int32_t n_free, const int32_t *ties, int32_t n_tie,
-                        double rel_step, double *d_JTJ, double *d_JTr, double *d_chi2, void *d_workspace,
+                        const int32_t *free_idx, int32_t n_free, const int32_t *ties, const double *tie_coef,
+                        int32_t n_tie, double rel_step, double *d_JTJ, double *d_JTr, double *d_chi2, void *d_workspace,
                         const uint8_t *d_active, void *stream);
 
 /* One damped Gauss-Newton (Levenberg-Marquardt) proposal per system:
  * solve (JTJ + lambda*diag(JTJ)) delta = -JTr, project onto [lo, hi], write trial params. */
 int xrsd_lm_propose(const double *d_params, int32_t ld_params, int32_t batch,
-                    const int32_t *free_idx, int32_t n_free, const int32_t *ties, int32_t n_tie,
-                    const double *d_JTJ, const double *d_JTr, const double *d_lambda,
+                    const int32_t *free_idx, int32_t n_free, const int32_t *ties, const double *tie_coef,
+                    int32_t n_tie, const double *d_JTJ, const double *d_JTr, const double *d_lambda,
                     const double *d_lo, const double *d_hi, const uint8_t *d_active,
                     double *d_trial, void *stream);
 /* Accept/reject: where chi2_trial < chi2 copy trial -> params, lambda /= down, else lambda *= up;

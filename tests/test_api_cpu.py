@@ -160,3 +160,20 @@ def test_yaml_round_trip_and_grouping(tmp_path, golden_systems):
     out = tmp_path / "again.yml"
     ymltools.save_sys_to_yaml(str(out), systems[0])
     assert ymltools.load_sys_from_yaml(str(out)).to_dict() == systems[0].to_dict()
+
+
+def test_affine_constraint_expressions_are_parsed_and_others_rejected():
+    """constraint_expr (reference system/__init__.py:197-209 hands it to lmfit): expressions affine in one other
+    parameter lower to (source slot, scale, offset); everything else raises NotImplementedError."""
+    from xrsdkit_b200 import lowering
+    names = ["noise__I0", "particle__r", "shell__r", "shell__a"]
+    ok = {"particle__r": (1, 1.0, 0.0), " particle__r ": (1, 1.0, 0.0), "2*particle__r": (1, 2.0, 0.0),
+          "particle__r*2 + 5": (1, 2.0, 5.0), "(shell__a - 3) / 2": (3, 0.5, -1.5), "-particle__r + 1e1": (1, -1.0, 10.0),
+          "particle__r + particle__r": (1, 2.0, 0.0)}
+    for expr, want in ok.items():
+        got = lowering.parse_affine_constraint(expr, names)
+        assert got[0] == want[0] and got[1] == pytest.approx(want[1]) and got[2] == pytest.approx(want[2]), expr
+    for expr in ("particle__r**2", "particle__r*shell__r", "1/particle__r", "sqrt(particle__r)", "unknown__r", "3.0",
+                 "particle__r +", "particle__r if 1 else 2"):
+        with pytest.raises(NotImplementedError):
+            lowering.parse_affine_constraint(expr, names)

@@ -217,10 +217,23 @@ def test_fit_with_equality_constraint(eng):
     assert rp == pytest.approx(33.0, rel=5e-3)
     assert out.populations["superlattice"].parameters["a"]["value"] == pytest.approx(110.0, rel=2e-3)
     assert out.fit_report["final_objective"] < 0.05 * out.fit_report["initial_objective"]
-    # anything that is not a plain parameter name needs lmfit's asteval: rejected, not silently ignored
-    start.populations["superlattice"].parameters["r"]["constraint_expr"] = "particle__r * 2"
-    with pytest.raises(NotImplementedError):
-        fit(start, q, I)
+    # an expression that is affine in one parameter works too: the superlattice sphere is 0.9 x the particle + 1
+    truth2 = make(33.0, 110.0, tie=False)
+    truth2.populations["superlattice"].parameters["r"]["value"] = 0.9 * 33.0 + 1.0
+    I2 = truth2.compute_intensity(q) * (1 + 0.01 * np.random.RandomState(9).randn(q.size))
+    start2 = make(34.5, 112.0)
+    start2.populations["superlattice"].parameters["r"]["constraint_expr"] = "0.9*particle__r + 1"
+    for method in ("lm", "nelder-mead"):
+        out2 = fit(start2, q, I2, method=method)
+        rp2 = out2.populations["particle"].parameters["r"]["value"]
+        assert out2.populations["superlattice"].parameters["r"]["value"] == pytest.approx(0.9 * rp2 + 1.0, rel=1e-14)
+        assert rp2 == pytest.approx(33.0, rel=1e-2), method
+        assert out2.fit_report["final_objective"] < 0.1 * out2.fit_report["initial_objective"], method
+    # anything beyond that needs lmfit's asteval: rejected, not silently ignored
+    for expr in ("particle__r ** 2", "particle__r * superlattice__a", "sqrt(particle__r)", "nonsense__r"):
+        start.populations["superlattice"].parameters["r"]["constraint_expr"] = expr
+        with pytest.raises(NotImplementedError):
+            fit(start, q, I)
 
 
 def test_nelder_mead_like_for_like(eng):

@@ -21,6 +21,7 @@ OK, EINVAL, ECUDA, ECAPACITY, ENOMEM = 0, -1, -2, -3, -4
 
 i32, f64 = C.c_int32, C.c_double
 N_FEATURES, FEATURE_MAX_Q = 21, 8192
+ABI_VERSION = 2
 
 
 class Pop(C.Structure):
@@ -72,9 +73,9 @@ _SIGNATURES = {
                                       C.POINTER(Tables), vp, vp, C.c_int64, vp, vp, vp, vp]),
     "xrsd_jacobian_workspace_bytes": (C.c_int64, [i32, i32, i32]),
     "xrsd_jacobian_batch": (C.c_int, [C.POINTER(Layout), C.POINTER(Objective), vp, i32, vp, i32, i32,
-                                      C.POINTER(Tables), vp, vp, C.c_int64, C.POINTER(i32), i32, C.POINTER(i32), i32, f64,
+                                      C.POINTER(Tables), vp, vp, C.c_int64, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(f64), i32, f64,
                                       vp, vp, vp, vp, vp, vp]),
-    "xrsd_lm_propose": (C.c_int, [vp, i32, i32, C.POINTER(i32), i32, C.POINTER(i32), i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "xrsd_lm_propose": (C.c_int, [vp, i32, i32, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(f64), i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "xrsd_lm_update": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, vp, f64, f64, f64, f64, vp]),
     "xrsd_intensity_batch_host": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, vp, C.c_int64]),
     "xrsd_release_workspace": (None, []),
@@ -107,7 +108,7 @@ def load():
     if [s.value for s in sizes] != mine:
         raise ImportError("xrsdkit_b200: struct layout mismatch between abi.py %r and the library %r"
                           % (mine, [s.value for s in sizes]))
-    if lib.xrsd_abi_version() != 1:
+    if lib.xrsd_abi_version() != ABI_VERSION:
         raise ImportError("xrsdkit_b200: ABI version mismatch")
     _lib = lib
     return lib

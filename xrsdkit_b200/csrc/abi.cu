@@ -25,11 +25,11 @@ cudaError_t xrsd_launch_residual(const xrsd_layout_t *, const xrsd_objective_t *
 size_t xrsd_jacobian_smem(int, int, int, int, int *);
 cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *, const xrsd_objective_t *, const double *, int, const double *, int, int,
                                  const xrsd_tables_t *, const double *, const double *, long long, const int32_t *, int,
-                                 const int32_t *, int, double,
+                                 const int32_t *, const double *, int, double,
                                  double *, double *, double *, double *, double *, unsigned *, int, int, int, const uint8_t *,
                                  cudaStream_t);
 size_t xrsd_jacobian_acc_doubles(int);
-cudaError_t xrsd_launch_lm_propose(const double *, int, int, const int32_t *, int, const int32_t *, int, const double *, const double *,
+cudaError_t xrsd_launch_lm_propose(const double *, int, int, const int32_t *, int, const int32_t *, const double *, int, const double *, const double *,
                                    const double *, const double *, const double *, const uint8_t *, double *, cudaStream_t);
 cudaError_t xrsd_launch_lm_update(double *, int, int, const double *, double *, const double *, double *, uint8_t *, int *,
                                   double, double, double, double, cudaStream_t);
@@ -303,7 +303,7 @@ int64_t xrsd_jacobian_workspace_bytes(int32_t n_q, int32_t batch, int32_t n_free
 int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q, int32_t n_q,
                         const double *d_params, int32_t ld_params, int32_t batch, const xrsd_tables_t *tables,
                         const double *d_Iobs, const double *d_dI, int64_t ld_obs, const int32_t *free_idx, int32_t n_free,
-                        const int32_t *ties, int32_t n_tie, double rel_step, double *d_JTJ, double *d_JTr, double *d_chi2,
+                        const int32_t *ties, const double *tie_coef, int32_t n_tie, double rel_step, double *d_JTJ, double *d_JTr, double *d_chi2,
                         void *d_workspace,
                         const uint8_t *d_active, void *stream) {
   int rc = check_layout(layout);
@@ -336,14 +336,14 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   double *d_acc = (double *)((char *)d_workspace + fbytes);
   unsigned *d_tickets = (unsigned *)((char *)d_workspace + fbytes + abytes);
   cudaError_t e = xrsd_launch_jacobian(layout, obj, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables, d_Iobs,
-                                       obj->has_dI ? d_dI : nullptr, (long long)ld_obs, free_idx, n_free, ties, n_tie, rel_step, d_JTJ,
+                                       obj->has_dI ? d_dI : nullptr, (long long)ld_obs, free_idx, n_free, ties, tie_coef, n_tie, rel_step, d_JTJ,
                                        d_JTr, d_chi2, d_Fvar, d_acc, d_tickets, per, scratch, rm, d_active, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "jacobian_kernel");
   return XRSD_OK;
 }
 
 int xrsd_lm_propose(const double *d_params, int32_t ld_params, int32_t batch, const int32_t *free_idx, int32_t n_free,
-                    const int32_t *ties, int32_t n_tie, const double *d_JTJ, const double *d_JTr, const double *d_lambda, const double *d_lo, const double *d_hi,
+                    const int32_t *ties, const double *tie_coef, int32_t n_tie, const double *d_JTJ, const double *d_JTr, const double *d_lambda, const double *d_lo, const double *d_hi,
                     const uint8_t *d_active, double *d_trial, void *stream) {
   if (n_free < 1 || n_free > XRSD_MAX_FREE) return fail(XRSD_EINVAL, "n_free=%d (max %d)", n_free, XRSD_MAX_FREE);
   if (!d_params || !free_idx || !d_JTJ || !d_JTr || !d_lambda || !d_lo || !d_hi || !d_trial) return fail(XRSD_EINVAL, "NULL pointer");
@@ -352,7 +352,7 @@ int xrsd_lm_propose(const double *d_params, int32_t ld_params, int32_t batch, co
   if (n_tie < 0 || n_tie > XRSD_MAX_TIES || (n_tie > 0 && !ties)) return fail(XRSD_EINVAL, "n_tie=%d (max %d)", n_tie, XRSD_MAX_TIES);
   for (int i = 0; i < 2 * n_tie; ++i)
     if (ties[i] < 0 || ties[i] >= ld_params) return fail(XRSD_EINVAL, "ties[%d]=%d", i, ties[i]);
-  cudaError_t e = xrsd_launch_lm_propose(d_params, ld_params, batch, free_idx, n_free, ties, n_tie, d_JTJ, d_JTr, d_lambda, d_lo, d_hi,
+  cudaError_t e = xrsd_launch_lm_propose(d_params, ld_params, batch, free_idx, n_free, ties, tie_coef, n_tie, d_JTJ, d_JTr, d_lambda, d_lo, d_hi,
                                          d_active, d_trial, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "lm_propose_kernel");
   return XRSD_OK;

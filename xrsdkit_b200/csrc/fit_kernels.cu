@@ -23,21 +23,27 @@ struct FreeSet {
   int var_of[XRSD_MAX_FREE];    // variant index (>= 1) of a non-linear parameter, 0 for a linear one
   int pop_of[XRSD_MAX_FREE];    // linear parameter (an I0): index of its population, else -1
   int free_of_var[XRSD_MAX_FREE + 1];   // inverse of var_of
-  int n_tie;                    // equality constraints "dst = src" (constraint_expr naming one parameter)
+  int n_tie;                    // constraints "dst = scale * src + offset" (constraint_expr affine in one parameter)
   int tie_dst[XRSD_MAX_TIES], tie_src[XRSD_MAX_TIES];
+  double tie_scale[XRSD_MAX_TIES], tie_off[XRSD_MAX_TIES];
 };
 
 // An I0 multiplies its whole population (scattering/__init__.py:48,64,66; system/noise.py:56-62), so
 // dI/dI0 = I_pop / I0 needs no extra evaluation: the base variant records the running total after
 // each population and the reducer forms f(I + h I_pop / I0) from it.
 static FreeSet make_free_set(const xrsd_layout_t *L, const int32_t *free_idx, int n_free, const int32_t *ties = nullptr,
-                             int n_tie = 0) {
+                             const double *tie_coef = nullptr, int n_tie = 0) {
   FreeSet F;
   memset(&F, 0, sizeof(F));
   F.n_free = n_free;
   F.n_var = 1;
   F.n_tie = (ties && n_tie > 0) ? std::min(n_tie, (int)XRSD_MAX_TIES) : 0;
-  for (int t = 0; t < F.n_tie; ++t) { F.tie_dst[t] = ties[2 * t]; F.tie_src[t] = ties[2 * t + 1]; }
+  for (int t = 0; t < F.n_tie; ++t) {
+    F.tie_dst[t] = ties[2 * t];
+    F.tie_src[t] = ties[2 * t + 1];
+    F.tie_scale[t] = tie_coef ? tie_coef[2 * t] : 1.0;
+    F.tie_off[t] = tie_coef ? tie_coef[2 * t + 1] : 0.0;
+  }
   for (int j = 0; j < XRSD_MAX_FREE; ++j) { F.pop_of[j] = -1; }
   for (int j = 0; j < n_free; ++j) {
     F.idx[j] = free_idx[j];
@@ -177,7 +183,8 @@ jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *
     const int j = F.free_of_var[v];
     const double p0 = prm[F.idx[j]];
     prm_s[F.idx[j]] = p0 + ((p0 != 0.0) ? fabs(p0) * rel_step : rel_step);
-    for (int t = 0; t < F.n_tie; ++t) prm_s[F.tie_dst[t]] = prm_s[F.tie_src[t]];   // tied parameters move along
+    for (int t = 0; t < F.n_tie; ++t)                                              // tied parameters move along
+      prm_s[F.tie_dst[t]] = fma(F.tie_scale[t], prm_s[F.tie_src[t]], F.tie_off[t]);
   }
   __syncthreads();
   const int q_begin = tile * q_per_cta;
@@ -449,7 +456,7 @@ __global__ void lm_propose_kernel(const double *__restrict__ params, int ldp, in
     v = fmin(fmax(v, l), h);
     if (v == v) t[F.idx[j]] = v;
   }
-  for (int k = 0; k < F.n_tie; ++k) t[F.tie_dst[k]] = t[F.tie_src[k]];
+  for (int k = 0; k < F.n_tie; ++k) t[F.tie_dst[k]] = fma(F.tie_scale[k], t[F.tie_src[k]], F.tie_off[k]);
 }
 
 __global__ void lm_update_kernel(double *__restrict__ params, int ldp, int batch, const double *__restrict__ trial,
@@ -513,12 +520,12 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
                                             int n_q, const double *d_params, int ldp, int batch,
                                             const xrsd_tables_t *tables, const double *d_Iobs, const double *d_dI,
                                             long long ld_obs, const int32_t *free_idx, int n_free, const int32_t *ties,
-                                            int n_tie, double rel_step,
+                                            const double *tie_coef, int n_tie, double rel_step,
                                             double *d_JTJ, double *d_JTr, double *d_chi2, double *d_Fvar, double *d_acc,
                                             unsigned *d_tickets, int q_per_cta, int scratch_doubles, int radial_multi,
                                             const uint8_t *d_active, cudaStream_t stream) {
   using namespace xrsd;
-  const FreeSet F = make_free_set(layout, free_idx, n_free, ties, n_tie);
+  const FreeSet F = make_free_set(layout, free_idx, n_free, ties, tie_coef, n_tie);
   int pat = 0;
   const size_t smem = xrsd_jacobian_smem(layout->n_params, n_free, q_per_cta, scratch_doubles, &pat);
   auto kern = radial_multi ? jacobian_variants_kernel<true, true>
@@ -559,11 +566,11 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
 }
 
 extern "C" cudaError_t xrsd_launch_lm_propose(const double *d_params, int ldp, int batch, const int32_t *free_idx, int n_free,
-                                              const int32_t *ties, int n_tie,
+                                              const int32_t *ties, const double *tie_coef, int n_tie,
                                               const double *d_JTJ, const double *d_JTr, const double *d_lambda,
                                               const double *d_lo, const double *d_hi, const uint8_t *d_active,
                                               double *d_trial, cudaStream_t stream) {
-  const FreeSet F = xrsd::make_free_set(nullptr, free_idx, n_free, ties, n_tie);
+  const FreeSet F = xrsd::make_free_set(nullptr, free_idx, n_free, ties, tie_coef, n_tie);
   if (batch <= 0) return cudaSuccess;
   xrsd::lm_propose_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(d_params, ldp, batch, F, d_JTJ, d_JTr, d_lambda, d_lo, d_hi,
                                                                    d_active, d_trial);

@@ -280,11 +280,13 @@ class Engine(object):
 
     @staticmethod
     def tie_array(ties):
-        """[(dst, src), ...] -> (ctypes int32 array or None, count) for the C calls."""
+        """[(dst, src[, scale, offset]), ...] -> (int32 slot pairs, float64 (scale, offset) pairs, count) for the C
+        calls; (None, None, 0) without constraints."""
         if not ties:
-            return None, 0
-        flat = [int(v) for pair in ties for v in pair]
-        return (C.c_int32 * len(flat))(*flat), len(ties)
+            return None, None, 0
+        flat = [int(v) for t in ties for v in t[:2]]
+        coef = [float(v) for t in ties for v in ((t[2], t[3]) if len(t) >= 4 else (1.0, 0.0))]
+        return (C.c_int32 * len(flat))(*flat), (C.c_double * len(coef))(*coef), len(ties)
 
     def jacobian(self, layout, obj, q, d_params, Iobs_dev, dI_dev, ld_obs, free_slots, tables, rel_step=1e-6, out=None,
                  active=None, ties=None):
@@ -296,7 +298,7 @@ class Engine(object):
                    torch.empty((batch, nf), dtype=torch.float64, device=self.device),
                    torch.empty(batch, dtype=torch.float64, device=self.device))
         idx = (C.c_int32 * nf)(*free_slots)
-        tie_c, n_tie = self.tie_array(ties)
+        tie_c, coef_c, n_tie = self.tie_array(ties)
         n_q = q.shape[0]
         # HBM scratch for the variant patterns: chunk the batch so it stays under ~4 GB
         chunk = max(1, min(batch, int(4e9 // (8 * (nf + 1 + abi.MAX_POPS) * n_q))))
@@ -329,7 +331,7 @@ class Engine(object):
                 C.byref(layout.c), C.byref(obj), q.data_ptr(), n_q, d_params[lo:hi].data_ptr(), d_params.shape[1], hi - lo,
                 C.byref(tc) if tc is not None else None,
                 Iobs_dev.data_ptr() + 8 * lo * ld_obs, (dI_dev.data_ptr() + 8 * lo * ld_obs) if dI_dev is not None else None,
-                ld_obs, idx, nf, tie_c, n_tie, float(rel_step), out[0][lo:hi].data_ptr(), out[1][lo:hi].data_ptr(), out[2][lo:hi].data_ptr(),
+                ld_obs, idx, nf, tie_c, coef_c, n_tie, float(rel_step), out[0][lo:hi].data_ptr(), out[1][lo:hi].data_ptr(), out[2][lo:hi].data_ptr(),
                 ws.data_ptr(), (active.data_ptr() + lo) if active is not None else None, self._stream()))
             self.launches += 2
         return out

@@ -29,6 +29,13 @@ class FitResult(object):
         return ~self.active
 
 
+def _apply_ties(params, ties):
+    """params[..., dst] = scale * params[..., src] + offset for every constraint (dst, src[, scale, offset])."""
+    for t in ties:
+        scale, off = (t[2], t[3]) if len(t) >= 4 else (1.0, 0.0)
+        params[..., t[0]] = params[..., t[1]] * scale + off
+
+
 def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weighted=True, logI_weighted=True,
                  q_range=(0., float('inf')), max_iter=30, ftol=1e-8, lambda0=1e-2, up=8.0, down=4.0,
                  lambda_max=1e10, rel_step=1e-6, lo=None, hi=None, eng=None, return_device=False, ties=None):
@@ -42,8 +49,8 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         free_slots = layout.free_slots()
     if ties is None:
         ties = layout.ties()
-    free_slots = [s for s in free_slots if s not in [d for d, _ in ties]]      # a tied parameter is not varied
-    tie_c, n_tie = eng.tie_array(ties)
+    free_slots = [s for s in free_slots if s not in [t[0] for t in ties]]      # a tied parameter is not varied
+    tie_c, coef_c, n_tie = eng.tie_array(ties)
     nf = len(free_slots)
     if nf == 0:
         raise ValueError("no free parameters to fit")
@@ -55,8 +62,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     if d_p.dim() == 1:
         d_p = d_p.unsqueeze(0)
     batch, n_q = d_p.shape[0], d_q.shape[0]
-    for dst, src in ties:                       # lmfit evaluates the expression before the first objective call
-        d_p[:, dst] = d_p[:, src]
+    _apply_ties(d_p, ties)                      # lmfit evaluates the expression before the first objective call
     d_I, d_dI, ld_obs = eng._obs(Iobs, dI, batch, n_q)
     obj = eng.objective(error_weighted, logI_weighted, q_range, has_dI=d_dI is not None)
     blo, bhi = layout.bounds(free_slots)
@@ -97,7 +103,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
                                     active=d_active if it > 0 else None, ties=ties)
         if chi2_init is None:
             chi2_init = d_chi2.clone()
-        abi.check(lib.xrsd_lm_propose(d_p.data_ptr(), d_p.shape[1], batch, idx, nf, tie_c, n_tie, jout[0].data_ptr(), jout[1].data_ptr(),
+        abi.check(lib.xrsd_lm_propose(d_p.data_ptr(), d_p.shape[1], batch, idx, nf, tie_c, coef_c, n_tie, jout[0].data_ptr(), jout[1].data_ptr(),
                                       d_lambda.data_ptr(), d_lo.data_ptr(), d_hi.data_ptr(), d_active.data_ptr(),
                                       d_trial.data_ptr(), stream))
         # in-loop table builds do not read their status back (no host sync); it is checked every 5 iterations
@@ -164,7 +170,7 @@ def fit_system_inplace(system, q, I, dI=None, method='lm'):
         res = lm_fit_batch(lay, q, I, lay.values[None, :], free, max_iter=60, **kw)
     else:
         raise ValueError("unknown fit method %r" % (method,))
-    tied = [d for d, _ in lay.ties()]
+    tied = [t[0] for t in lay.ties()]
     for slot, rec in enumerate(lay.records):
         if slot in free or slot in tied:
             rec['value'] = float(res.params[0, slot])
@@ -232,7 +238,7 @@ def nm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         free_slots = layout.free_slots()
     if ties is None:
         ties = layout.ties()
-    free_slots = [s for s in free_slots if s not in [d for d, _ in ties]]
+    free_slots = [s for s in free_slots if s not in [t[0] for t in ties]]
     nf = len(free_slots)
     if nf == 0:
         raise ValueError("no free parameters to fit")
@@ -242,8 +248,7 @@ def nm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     if d_p.dim() == 1:
         d_p = d_p.unsqueeze(0)
     batch, n_q = d_p.shape[0], d_q.shape[0]
-    for dst, src in ties:
-        d_p[:, dst] = d_p[:, src]
+    _apply_ties(d_p, ties)
     d_I, d_dI, _ = eng._obs(Iobs, dI, batch, n_q)
     obj = eng.objective(error_weighted, logI_weighted, q_range, has_dI=d_dI is not None)
     blo, bhi = layout.bounds(free_slots)
@@ -260,8 +265,7 @@ def nm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         """chi2 of every system at internal coordinates u [batch, nf]; systems outside `mask` give +inf."""
         p = d_p.clone()
         p[:, fidx] = tr.to_external(u)
-        for dst, src in ties:
-            p[:, dst] = p[:, src]
+        _apply_ties(p, ties)
         act = None if mask is None else mask.to(torch.uint8)
         if layout.n_xtal:
             state['tables'] = eng.build_tables(layout, p, batch, max_cells=max_cells, reuse=state['tables'],
@@ -323,8 +327,7 @@ def nm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     ub = U[rows, best]
     p = d_p.clone()
     p[:, fidx] = tr.to_external(ub)
-    for dst, src in ties:
-        p[:, dst] = p[:, src]
+    _apply_ties(p, ties)
     chi2 = F[rows, best]
     res = FitResult(p, chi2_init, chi2, n_iter, torch.full((batch,), state['n_eval'], dtype=torch.int32, device=eng.device), ~done)
     if return_device:

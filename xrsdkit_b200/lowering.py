@@ -63,21 +63,25 @@ class SystemLayout(object):
         return [i for i, r in enumerate(self.records) if not r.get('fixed') and not r.get('constraint_expr')]
 
     def ties(self):
-        """[(dst_slot, src_slot)] for parameters whose constraint_expr names another parameter
-        ('particle__r': the only form found in xrsdkit's fitted systems).  Any other expression would need
-        lmfit's asteval and is rejected when a fit is requested."""
+        """[(dst_slot, src_slot, scale, offset)] for parameters whose constraint_expr is affine in ONE other
+        parameter: value[dst] = scale * value[src] + offset.  'particle__r' -- the only form found in xrsdkit's
+        fitted systems -- gives (1, 0); '2*particle__r', 'particle__r + 5', '(shell__r - 3) / 2' work as well.
+        Anything else (several parameters, non-linear functions: the rest of lmfit's asteval language) is rejected
+        when a fit is requested."""
         out = []
         for i, r in enumerate(self.records):
             expr = r.get('constraint_expr')
             if not expr:
                 continue
-            key = str(expr).strip()
-            if key not in self.names:
-                raise NotImplementedError("constraint_expr %r: only '<population>__<parameter>' equality "
-                                          "constraints are supported" % expr)
-            out.append((i, self.names.index(key)))
+            src, scale, off = parse_affine_constraint(str(expr), self.names)
+            if src == i:
+                raise NotImplementedError("constraint_expr %r refers to its own parameter" % expr)
+            out.append((i, src, scale, off))
         if len(out) > abi.MAX_TIES:
             raise NotImplementedError("at most %d constrained parameters per system" % abi.MAX_TIES)
+        dsts = [t[0] for t in out]
+        if any(t[1] in dsts for t in out):
+            raise NotImplementedError("chained constraints (a constrained parameter used in another constraint_expr)")
         return out
 
     def bounds(self, slots):
@@ -216,6 +220,53 @@ def _lower_population(structure, form, settings, slots, q_last, table_slot):
     else:
         raise ValueError('{} structure does not support {} forms'.format(structure, form))
     return p
+
+
+def parse_affine_constraint(expr, names):
+    """(source slot, scale, offset) of a constraint expression that is affine in exactly one parameter name;
+    raises NotImplementedError otherwise.  The expression is parsed with `ast` (numbers, one name, + - * /,
+    unary minus, parentheses) and evaluated at three points of the source to establish linearity."""
+    import ast
+    try:
+        tree = ast.parse(expr.strip(), mode='eval')
+    except SyntaxError:
+        raise NotImplementedError("constraint_expr %r is not an arithmetic expression" % expr)
+    used = set()
+
+    def ev(node, x):
+        if isinstance(node, ast.Expression):
+            return ev(node.body, x)
+        if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)) and not isinstance(node.value, bool):
+            return float(node.value)
+        if isinstance(node, ast.Name):
+            if node.id not in names:
+                raise NotImplementedError("constraint_expr %r: unknown parameter %r" % (expr, node.id))
+            used.add(node.id)
+            return x
+        if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd)):
+            v = ev(node.operand, x)
+            return -v if isinstance(node.op, ast.USub) else v
+        if isinstance(node, ast.BinOp) and isinstance(node.op, (ast.Add, ast.Sub, ast.Mult, ast.Div)):
+            a, b = ev(node.left, x), ev(node.right, x)
+            if isinstance(node.op, ast.Add):
+                return a + b
+            if isinstance(node.op, ast.Sub):
+                return a - b
+            if isinstance(node.op, ast.Mult):
+                return a * b
+            return a / b
+        raise NotImplementedError("constraint_expr %r: only + - * / of numbers and one parameter are supported" % expr)
+
+    try:
+        f0, f1, f2 = ev(tree, 0.0), ev(tree, 1.0), ev(tree, 2.0)
+    except ZeroDivisionError:
+        raise NotImplementedError("constraint_expr %r is not affine in its parameter" % expr)
+    if len(used) != 1:
+        raise NotImplementedError("constraint_expr %r must name exactly one other parameter" % expr)
+    scale, off = f1 - f0, f0
+    if not np.isfinite([f0, f1, f2]).all() or abs((f2 - f0) - 2.0 * scale) > 1e-12 * max(1.0, abs(f2), abs(f0)):
+        raise NotImplementedError("constraint_expr %r is not affine in %s" % (expr, next(iter(used))))
+    return names.index(next(iter(used))), float(scale), float(off)
 
 
 def uniform_step(q):

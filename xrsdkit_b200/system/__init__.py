@@ -184,8 +184,9 @@ def fit(sys, q, I, dI=None, error_weighted=None, logI_weighted=None, q_range=Non
     converged / initial_objective / final_objective / fit_snr -- but the optimiser is the
     batched GPU Levenberg-Marquardt of xrsdkit_b200.fitting (batch of one) instead of
     lmfit's Nelder-Mead; method='nelder-mead' runs the reference's algorithm (scipy's Nelder-Mead
-    coefficients, lmfit's bound transform) on the same GPU objective.  A constraint_expr that names another parameter ('particle__r') is kept as an
-    equality tie; other expressions raise NotImplementedError.  The reference
+    coefficients, lmfit's bound transform) on the same GPU objective.  A constraint_expr that is affine in one other parameter
+    ('particle__r', '2*particle__r + 1') is kept as a tie dst = scale*src + offset; other expressions raise
+    NotImplementedError.  The reference
     stores `error_weighted` into logI_weighted here (a bug, :255-256); this keeps the
     documented meaning."""
     from .. import fitting
