@@ -52,7 +52,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 }
 
 constexpr int kMaxSmem = 227 * 1024;
-constexpr int kStaticSmem = 2048;   // EvalShared / TableShared and friends
+constexpr int kStaticSmem = 16 * 1024;   // upper bound of the kernels' static shared memory (EvalShared with the Chebyshev / Voigt tables: 11.9 KB)
 
 int check_layout(const xrsd_layout_t *L) {
   if (!L) return fail(XRSD_EINVAL, "layout is NULL");
@@ -199,9 +199,9 @@ int xrsd_reflection_tables(const xrsd_layout_t *layout, const double *d_params, 
 static int pick_q_per_cta(int n_q, int batch, int scratch, bool has_xtal) {
   // One CTA holds a span of one pattern in shared memory.  Spans are multiples of 512 q-points;
   // aim for >= 24 CTAs per SM in the grid (several waves, so the last partial wave costs little)
-  // and keep the span small enough for the resident CTAs: 4096 q-points (32 KB, six CTAs per SM), or 2048
-  // for layouts with crystalline populations, whose intensity kernel is compiled for eight CTAs per SM
-  // (64 registers; measured 7 % faster than six) and carries ~6 KB of static shared memory.
+  // and keep the span small enough for the resident CTAs: 4096 q-points (32 KB, five or six CTAs per SM), or 2048
+  // for the residual kernel of layouts with crystalline populations (~12 KB of static shared memory on top).
+  // (The intensity and Jacobian kernels of crystalline layouts accumulate in place: pick_direct_span.)
   const long long want_ctas = 148LL * 24;
   long long tiles = (want_ctas + batch - 1) / batch;
   if (tiles < 1) tiles = 1;
