@@ -52,7 +52,8 @@ int cuda_fail(cudaError_t e, const char *what) {
 }
 
 constexpr int kMaxSmem = 227 * 1024;
-constexpr int kStaticSmem = 16 * 1024;   // upper bound of the kernels' static shared memory (EvalShared with the Chebyshev / Voigt tables: 11.9 KB)
+constexpr int kStaticSmem = 2048;        // static shared memory of the table kernel (TableShared: 1.4 KB)
+constexpr int kStaticSmemEval = 16 * 1024;   // upper bound for the evaluation kernels (EvalShared with the Chebyshev / Voigt tables: 11.9 KB)
 
 int check_layout(const xrsd_layout_t *L) {
   if (!L) return fail(XRSD_EINVAL, "layout is NULL");
@@ -328,7 +329,7 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   // crystalline layouts accumulate straight into the variant slabs (negative span = direct mode)
   const int per = layout->n_xtal > 0 ? -pick_direct_span(n_q, (long long)batch * (n_free + 1))
                                      : pick_q_per_cta(n_q, batch * (n_free + 1), scratch, false);
-  if (xrsd_jacobian_smem(layout->n_params, n_free, per, scratch, nullptr) + kStaticSmem > (size_t)kMaxSmem)
+  if (xrsd_jacobian_smem(layout->n_params, n_free, per, scratch, nullptr) + kStaticSmemEval > (size_t)kMaxSmem)
     return fail(XRSD_ECAPACITY, "jacobian working set does not fit in shared memory");
   const int64_t fbytes = (int64_t)batch * (n_free + 1 + XRSD_MAX_POPS) * n_q * 8;
   const int64_t abytes = (((int64_t)batch * (int64_t)xrsd_jacobian_acc_doubles(n_free) * 8) + 255) & ~255LL;
