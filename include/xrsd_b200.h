@@ -160,7 +160,9 @@ int xrsd_reflection_tables(const xrsd_layout_t *layout, const double *d_params, 
                            int32_t batch, const xrsd_tables_t *tables, int32_t max_cells,
                            const uint8_t *d_active, void *stream);
 
-/* I[b, :] for b < batch.  d_q[n_q], d_params[batch][ld_params], d_I[batch][ld_I]. */
+/* I[b, :] for b < batch.  d_q[n_q], d_params[batch][ld_params], d_I[batch][ld_I] (device memory; every element of
+ * the rows is overwritten -- layouts with crystalline populations accumulate the populations in place in d_I,
+ * the others stage a span in shared memory and write it once).  <- System.compute_intensity, system/__init__.py:112-130 */
 int xrsd_intensity_batch(const xrsd_layout_t *layout, const double *d_q, int32_t n_q,
                          const double *d_params, int32_t ld_params, int32_t batch,
                          const xrsd_tables_t *tables, double *d_I, int64_t ld_I, void *stream);
