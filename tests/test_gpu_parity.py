@@ -496,3 +496,23 @@ def test_pinned_host_pipeline_matches_the_device_path(eng):
             out.zero_()
             batch.compute_intensity_pinned(lay, q_host, p_host, out, chunks=chunks, eng=eng)
             np.testing.assert_allclose(out.numpy(), want, rtol=1e-12, atol=0)
+
+
+def test_whole_pattern_ctas_equal_split_spans_at_full_size(ref_tables, eng):
+    """Direct mode takes a whole 8192-point pattern per CTA once the batch fills the GPU and 512-point spans for a
+    handful of systems: both must give the same bits (the span length only changes who computes what), and the
+    full-size result must still match the oracle."""
+    from oracle import xrsd_oracle as orc
+    from helpers import cfg4_system, cfg4_params, params_to_sysdict
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg4_system(System)
+    q = np.linspace(0.01, 1.0, 8192)
+    lay = batch.layout_of(s, q)
+    P = cfg4_params(lay, 5000, seed=77)
+    I = batch.compute_intensity_batch(lay, q, P)
+    rows = [0, 17, 999, 4999]
+    assert np.array_equal(I[rows], batch.compute_intensity_batch(lay, q, P[rows]))
+    for r in rows[:2]:
+        err, same = rel_err(I[r], orc.system_intensity(q, params_to_sysdict(s, lay, P[r]), **ref_tables))
+        assert same and err <= TOL_F64, (r, err)
