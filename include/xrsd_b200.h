@@ -232,6 +232,10 @@ int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int3
                               double *I_out, int64_t ld_I);
 void xrsd_release_workspace(void);
 
+/* Host helper: the step of q if it is a linspace-like grid (every point within 4 ulp of q[0] + i*step and strictly
+ * ascending), else 0 -- the value xrsd_layout_t.q_step expects. */
+double xrsd_uniform_step(const double *q, int32_t n);
+
 /* Peak profiles on their own: out[i] = profile(x[i]) for kind = XRSD_PROFILE_* with
  * (hwhm_g, hwhm_l) for voigt or (hwhm, unused) otherwise.  <- tools/peak_math.py:24-47
  * (gaussian, lorentzian, voigt; the reference's voigt calls scipy.special.wofz). */

@@ -80,6 +80,7 @@ _SIGNATURES = {
     "xrsd_intensity_batch_host": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, vp, C.c_int64]),
     "xrsd_release_workspace": (None, []),
     "xrsd_peak_profile": (C.c_int, [i32, f64, f64, vp, i32, vp, vp]),
+    "xrsd_uniform_step": (f64, [vp, i32]),
     "xrsd_feature_batch": (C.c_int, [vp, i32, vp, i64, i32, vp, i64, vp]),
     "xrsd_probe_fp64_peak": (C.c_int, [C.POINTER(f64), C.POINTER(f64), vp]),
 }

@@ -432,6 +432,8 @@ struct Workspace {
   size_t bytes = 0;
   double *pinned = nullptr;
   size_t pinned_bytes = 0;
+  std::vector<double> q_host;     // the grid currently resident at offset 0 of the workspace (skips its upload)
+  bool q_valid = false;
 } g_ws;
 
 int ws_reserve(size_t bytes) {
@@ -439,15 +441,48 @@ int ws_reserve(size_t bytes) {
   if (g_ws.base) cudaFree(g_ws.base);
   g_ws.base = nullptr;
   g_ws.bytes = 0;
+  g_ws.q_valid = false;
   cudaError_t e = cudaMalloc(&g_ws.base, bytes);
   if (e != cudaSuccess) return fail(XRSD_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
   g_ws.bytes = bytes;
   return XRSD_OK;
 }
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// small calls stage their parameters and their result through one pinned buffer (pageable copies of a few KB cost
+// ~10 us each in the driver); returns nullptr when the call is too large for it or the allocation fails
+constexpr size_t kPinnedMax = 4u << 20;
+double *pinned_reserve(size_t bytes) {
+  if (bytes > kPinnedMax) return nullptr;
+  if (bytes <= g_ws.pinned_bytes) return g_ws.pinned;
+  if (g_ws.pinned) cudaFreeHost(g_ws.pinned);
+  g_ws.pinned = nullptr;
+  g_ws.pinned_bytes = 0;
+  const size_t want = std::max(bytes, (size_t)256 << 10);
+  if (cudaMallocHost((void **)&g_ws.pinned, want) != cudaSuccess) { cudaGetLastError(); g_ws.pinned = nullptr; return nullptr; }
+  g_ws.pinned_bytes = want;
+  return g_ws.pinned;
+}
 }  // namespace
 
+double xrsd_uniform_step(const double *q, int32_t n) {
+  // step of a linspace-like grid: every point within 4 ulp of q[0] + i*step and strictly ascending; else 0
+  if (!q || n < 3) return 0.0;
+  const double step = (q[n - 1] - q[0]) / (double)(n - 1);
+  if (!(step > 0.0)) return 0.0;
+  const double tol = 4.0 * 2.220446049250313e-16 * std::max(fabs(q[0]), fabs(q[n - 1]));
+  for (int32_t i = 0; i < n; ++i) {
+    if (!(fabs(q[i] - (q[0] + (double)i * step)) <= tol)) return 0.0;
+    if (i > 0 && !(q[i] > q[i - 1])) return 0.0;
+  }
+  return step;
+}
+
 void xrsd_release_workspace(void) {
+  g_ws.q_valid = false;
+  if (g_ws.pinned) cudaFreeHost(g_ws.pinned);
+  g_ws.pinned = nullptr;
+  g_ws.pinned_bytes = 0;
   if (g_ws.base) cudaFree(g_ws.base);
   g_ws.base = nullptr;
   g_ws.bytes = 0;
@@ -478,9 +513,19 @@ int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int3
   if (rc) return rc;
   char *base = (char *)g_ws.base;
   cudaStream_t s = 0;
-  cudaError_t e = cudaMemcpyAsync(base + o_q, q, (size_t)n_q * 8, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(base + o_p, params, (size_t)batch * ld_params * 8, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
+  // repeated calls on the same grid (the usual case: one measured pattern, many evaluations) skip the upload of q
+  cudaError_t e = cudaSuccess;
+  const bool same_q = g_ws.q_valid && g_ws.q_host.size() == (size_t)n_q && memcmp(g_ws.q_host.data(), q, (size_t)n_q * 8) == 0;
+  if (!same_q) {
+    e = cudaMemcpyAsync(base + o_q, q, (size_t)n_q * 8, cudaMemcpyHostToDevice, s);
+    g_ws.q_host.assign(q, q + n_q);
+    g_ws.q_valid = (e == cudaSuccess);
+  }
+  const size_t p_bytes = (size_t)batch * ld_params * 8, I_bytes = (size_t)batch * n_q * 8;
+  double *pin = pinned_reserve(align256(p_bytes) + I_bytes);
+  if (pin) memcpy(pin, params, p_bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(base + o_p, pin ? (const void *)pin : (const void *)params, p_bytes, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) { g_ws.q_valid = false; return cuda_fail(e, "H2D copy"); }
   xrsd_tables_t T = {};
   if (n_x) {
     T.cap_shell = cap_shell; T.cap_refl = 0; T.n_pairs_max = n_pairs;
@@ -518,8 +563,19 @@ int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int3
   rc = xrsd_intensity_batch(layout, (const double *)(base + o_q), n_q, (const double *)(base + o_p), ld_params, batch,
                             n_x ? &T : nullptr, (double *)(base + o_I), n_q, s);
   if (rc) return rc;
-  e = cudaMemcpy2DAsync(I_out, (size_t)ld_I * 8, base + o_I, (size_t)n_q * 8, (size_t)n_q * 8, batch, cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (pin) {
+    double *pin_I = pin + align256(p_bytes) / 8;
+    e = cudaMemcpyAsync(pin_I, base + o_I, I_bytes, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess)
+      for (int32_t b = 0; b < batch; ++b) memcpy(I_out + (size_t)b * ld_I, pin_I + (size_t)b * n_q, (size_t)n_q * 8);
+  } else {
+    if (ld_I == n_q)
+      e = cudaMemcpyAsync(I_out, base + o_I, I_bytes, cudaMemcpyDeviceToHost, s);
+    else
+      e = cudaMemcpy2DAsync(I_out, (size_t)ld_I * 8, base + o_I, (size_t)n_q * 8, (size_t)n_q * 8, batch, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "D2H copy / kernel execution");
   return XRSD_OK;
 }

@@ -270,10 +270,18 @@ def parse_affine_constraint(expr, names):
 
 
 def uniform_step(q):
-    """Step of q if it is a linspace-like grid (every point within 4 ulp of q[0] + i*step), else 0."""
+    """Step of q if it is a linspace-like grid (every point within 4 ulp of q[0] + i*step, strictly ascending),
+    else 0.  Evaluated by the library's host helper (one pass in C: this sits on the single-pattern latency
+    path); the numpy statement of the same test serves when the library cannot be loaded."""
     n = len(q)
     if n < 3:
         return 0.0
+    try:
+        lib = abi.load()
+    except ImportError:
+        lib = None
+    if lib is not None and isinstance(q, np.ndarray) and q.dtype == np.float64 and q.flags.c_contiguous:
+        return float(lib.xrsd_uniform_step(q.ctypes.data, n))
     step = (q[-1] - q[0]) / (n - 1)
     if not (step > 0):
         return 0.0

@@ -107,7 +107,7 @@ class System(object):
     def compute_intensity(self, q):
         """I(q) = noise + sum of populations (reference :112-130), one kernel launch."""
         from .. import engine, lowering
-        q = np.asarray(q, dtype=float)
+        q = np.ascontiguousarray(q, dtype=np.float64)
         return engine.get_engine().intensity_single(lowering.lower_system(self, q), q)
 
     def compute_intensity_components(self, q):
