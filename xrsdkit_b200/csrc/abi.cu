@@ -531,52 +531,61 @@ int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int3
     T.cap_shell = cap_shell; T.cap_refl = 0; T.n_pairs_max = n_pairs;
     T.n_shell = (int32_t *)(base + o_ns); T.n_refl = (int32_t *)(base + o_nr); T.n_all = (int32_t *)(base + o_na);
     T.status = (int32_t *)(base + o_st); T.shell_hkl = (int32_t *)(base + o_sh); T.shell_geo = (double *)(base + o_sg);
-    void *big = nullptr;
-    for (int attempt = 0; attempt < 2; ++attempt) {
+  }
+  // tables -> intensity -> copies are queued back to back; the table status comes back with the result and is looked
+  // at after the one synchronisation (a capacity overflow, rare, repeats the sequence with global table scratch)
+  void *big = nullptr;
+  std::vector<int32_t> st(n_tab), na(n_tab);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (n_x) {
       rc = xrsd_reflection_tables(layout, (const double *)(base + o_p), ld_params, batch, &T, max_cells, nullptr, s);
       if (rc) break;
-      std::vector<int32_t> st(n_tab), na(n_tab);
+    }
+    rc = xrsd_intensity_batch(layout, (const double *)(base + o_q), n_q, (const double *)(base + o_p), ld_params, batch,
+                              n_x ? &T : nullptr, (double *)(base + o_I), n_q, s);
+    if (rc) break;
+    if (n_x) {
       e = cudaMemcpyAsync(st.data(), T.status, n_tab * 4, cudaMemcpyDeviceToHost, s);
       if (e == cudaSuccess) e = cudaMemcpyAsync(na.data(), T.n_all, n_tab * 4, cudaMemcpyDeviceToHost, s);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
       if (e != cudaSuccess) { rc = cuda_fail(e, "table status copy"); break; }
-      int worst = 0, n_max = 0;
-      for (size_t i = 0; i < n_tab; ++i) { worst |= st[i]; n_max = std::max(n_max, na[i]); }
-      if (worst == 0) break;
-      if (worst == XRSD_TABLE_LIST_OVERFLOW && attempt == 0) {
-        // large cell without usable symmetry: give the builder global scratch for its sort / shell arrays
-        int64_t cap_big = 8192;
-        while (cap_big < n_max) cap_big <<= 1;
-        e = cudaMalloc(&big, (size_t)(n_tab * xrsd_table_scratch_bytes(cap_big)));
-        if (e != cudaSuccess) { rc = fail(XRSD_ENOMEM, "cudaMalloc(table scratch): %s", cudaGetErrorString(e)); break; }
-        T.big_scratch = big;
-        T.cap_big = cap_big;
-        T.cap_list_hint = 4096;
-        continue;
+    }
+    if (pin) {
+      double *pin_I = pin + align256(p_bytes) / 8;
+      e = cudaMemcpyAsync(pin_I, base + o_I, I_bytes, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    } else {
+      if (ld_I == n_q)
+        e = cudaMemcpyAsync(I_out, base + o_I, I_bytes, cudaMemcpyDeviceToHost, s);
+      else
+        e = cudaMemcpy2DAsync(I_out, (size_t)ld_I * 8, base + o_I, (size_t)n_q * 8, (size_t)n_q * 8, batch, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+    if (e != cudaSuccess) { rc = cuda_fail(e, "D2H copy / kernel execution"); break; }
+    int worst = 0, n_max = 0;
+    for (size_t i = 0; i < n_tab; ++i) { worst |= st[i]; n_max = std::max(n_max, na[i]); }
+    if (worst == 0) {
+      if (pin) {
+        const double *pin_I = pin + align256(p_bytes) / 8;
+        for (int32_t b = 0; b < batch; ++b) memcpy(I_out + (size_t)b * ld_I, pin_I + (size_t)b * n_q, (size_t)n_q * 8);
       }
-      rc = fail(XRSD_ECAPACITY, "reflection table: status %d (capacity exceeded)", worst);
       break;
     }
-    if (big) { cudaStreamSynchronize(s); cudaFree(big); }
-    if (rc) return rc;
+    if (worst == XRSD_TABLE_LIST_OVERFLOW && attempt == 0) {
+      // large cell without usable symmetry: give the builder global scratch for its sort / shell arrays
+      int64_t cap_big = 8192;
+      while (cap_big < n_max) cap_big <<= 1;
+      e = cudaMalloc(&big, (size_t)(n_tab * xrsd_table_scratch_bytes(cap_big)));
+      if (e != cudaSuccess) { rc = fail(XRSD_ENOMEM, "cudaMalloc(table scratch): %s", cudaGetErrorString(e)); break; }
+      T.big_scratch = big;
+      T.cap_big = cap_big;
+      T.cap_list_hint = 4096;
+      continue;
+    }
+    rc = fail(XRSD_ECAPACITY, "reflection table: status %d (capacity exceeded)", worst);
+    break;
   }
-  rc = xrsd_intensity_batch(layout, (const double *)(base + o_q), n_q, (const double *)(base + o_p), ld_params, batch,
-                            n_x ? &T : nullptr, (double *)(base + o_I), n_q, s);
+  if (big) { cudaStreamSynchronize(s); cudaFree(big); }
   if (rc) return rc;
-  if (pin) {
-    double *pin_I = pin + align256(p_bytes) / 8;
-    e = cudaMemcpyAsync(pin_I, base + o_I, I_bytes, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e == cudaSuccess)
-      for (int32_t b = 0; b < batch; ++b) memcpy(I_out + (size_t)b * ld_I, pin_I + (size_t)b * n_q, (size_t)n_q * 8);
-  } else {
-    if (ld_I == n_q)
-      e = cudaMemcpyAsync(I_out, base + o_I, I_bytes, cudaMemcpyDeviceToHost, s);
-    else
-      e = cudaMemcpy2DAsync(I_out, (size_t)ld_I * 8, base + o_I, (size_t)n_q * 8, (size_t)n_q * 8, batch, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  }
-  if (e != cudaSuccess) return cuda_fail(e, "D2H copy / kernel execution");
   return XRSD_OK;
 }
 
