@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define XRSD_ABI_VERSION 2
+#define XRSD_ABI_VERSION 3
 
 #define XRSD_MAX_POPS 6      /* noise model + up to 5 populations per system layout   */
 #define XRSD_MAX_SPECIES 4   /* species (atoms) per crystalline population             */
@@ -207,8 +207,15 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
                         int32_t batch, const xrsd_tables_t *tables,
                         const double *d_Iobs, const double *d_dI, int64_t ld_obs,
                         const int32_t *free_idx, int32_t n_free, const int32_t *ties, const double *tie_coef,
-                        int32_t n_tie, double rel_step, double *d_JTJ, double *d_JTr, double *d_chi2, void *d_workspace,
-                        const uint8_t *d_active, void *stream);
+                        int32_t n_tie, double rel_step, int32_t base_ready, double *d_JTJ, double *d_JTr, double *d_chi2,
+                        void *d_workspace, const uint8_t *d_active, void *stream);
+/* Number of pattern slabs per system the call above evaluates and keeps at the head of d_workspace:
+ * [batch][n_variants + layout.n_pops][n_q] doubles -- slab 0 is the base pattern, slabs 1..n_variants-1 the
+ * perturbed ones (one per non-linear free parameter), the last n_pops the base pattern's running totals after
+ * each population.  With base_ready != 0 the call trusts slab 0 and the running totals already in the workspace
+ * (e.g. copied there from an accepted trial evaluation) and evaluates only the perturbed variants. */
+int32_t xrsd_jacobian_n_variants(const xrsd_layout_t *layout, const int32_t *free_idx, int32_t n_free,
+                                 const int32_t *ties, int32_t n_tie);
 
 /* One damped Gauss-Newton (Levenberg-Marquardt) proposal per system:
  * solve (JTJ + lambda*diag(JTJ)) delta = -JTr, project onto [lo, hi], write trial params. */

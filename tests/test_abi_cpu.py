@@ -29,7 +29,7 @@ def test_struct_mirror_matches_library():
     lib.xrsd_struct_sizes(*[ctypes.byref(s) for s in sizes])
     assert [s.value for s in sizes] == [ctypes.sizeof(abi.Pop), ctypes.sizeof(abi.Layout), ctypes.sizeof(abi.Tables),
                                         ctypes.sizeof(abi.Objective)]
-    assert lib.xrsd_abi_version() == 2
+    assert lib.xrsd_abi_version() == 3
     assert lib.xrsd_table_smem_bytes(10, 10, 10) > 2 * 19 ** 3
 
 

@@ -362,3 +362,93 @@ def test_lm_with_nine_free_parameters(eng):
     res = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=40)
     assert np.all(res.chi2 <= res.chi2_init * (1 + 1e-12))
     assert np.median(res.chi2 / res.chi2_init) < 1e-2
+
+
+def test_jacobian_resident_workspace_and_base_ready(eng):
+    """A resident workspace keeps the pattern slabs; a second call with base_ready=True evaluates only the
+    perturbed variants and must give the same normal equations bit for bit.  Slab 0 is the base pattern and the
+    last running total is the full pattern too."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg4_system(System)
+    q = np.linspace(0.01, 1.0, 1500)
+    lay = batch.layout_of(s, q)
+    B = 6
+    P = cfg4_params(lay, B, seed=41)
+    free = [lay.slot(k) for k in ("noise__I0", "x__I0", "x__a", "x__hwhm_g", "x__hwhm_l", "x__r", "gp__I0", "gp__rg")]
+    Iobs = batch.compute_intensity_batch(lay, q, P) * (1 + 0.02 * np.random.RandomState(3).randn(B, len(q)))
+    P0 = P.copy()
+    P0[:, free] *= 1.01
+    obj = eng.objective(True, True, (0.0, float("inf")))
+    d_q, d_p, d_I = eng.to_device(q), eng.to_device(P0), eng.to_device(Iobs)
+    tables = eng.build_tables(lay, d_p, B, params_host=P0)
+    key = ("test", 0)
+    with pytest.raises((RuntimeError, ValueError)):
+        eng.jacobian(lay, obj, d_q, d_p, d_I, None, len(q), free, tables, base_ready=True)            # no workspace
+    with pytest.raises(RuntimeError):
+        eng.jacobian(lay, obj, d_q, d_p, d_I, None, len(q), free, tables, resident=key, base_ready=True)   # nothing in it yet
+    first = [t.clone() for t in eng.jacobian(lay, obj, d_q, d_p, d_I, None, len(q), free, tables, resident=key)]
+    shared = [t.clone() for t in eng.jacobian(lay, obj, d_q, d_p, d_I, None, len(q), free, tables)]
+    n_var = eng.jacobian_variants(lay, free)
+    assert n_var == 1 + 5          # base + a, hwhm_g, hwhm_l, r, rg; the three I0 are linear and need no pattern
+    slabs = eng.jacobian_slabs(key, lay, B, len(q), n_var)
+    assert tuple(slabs.shape) == (B, n_var + 3, len(q))
+    I0 = eng.intensity(lay, d_q, d_p, tables=tables)
+    np.testing.assert_allclose(slabs[:, 0].cpu().numpy(), I0.cpu().numpy(), rtol=1e-13)
+    np.testing.assert_array_equal(slabs[:, -1].cpu().numpy(), slabs[:, 0].cpu().numpy())
+    again = eng.jacobian(lay, obj, d_q, d_p, d_I, None, len(q), free, tables, resident=key, base_ready=True)
+    for a, b, c in zip(first, again, shared):
+        np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
+        np.testing.assert_array_equal(a.cpu().numpy(), c.cpu().numpy())
+    eng.release_resident(key)
+    assert key not in eng._jac_resident
+
+
+@pytest.mark.parametrize("kind", ["sphere", "crystal"])
+def test_lm_resident_loop_matches_re_evaluating_loop(eng, kind):
+    """lm_fit_batch keeps the base pattern between iterations when the slabs fit in `resident_limit`; with the
+    limit at 0 every Jacobian evaluates the base again.  Both loops must walk the same path on noisy data."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    if kind == "sphere":
+        s = cfg2_system(System)
+        s.populations["p"].update_settings({"sampling_width": 2.52})
+        q = np.linspace(0.01, 0.5, 1024)
+        lay = batch.layout_of(s, q)
+        truth = cfg2_params(lay, 48, seed=51)
+        names, off = ("p__I0", "p__r", "p__sigma", "p__r_hard", "p__v_fraction"), 0.05
+    else:
+        s = cfg4_system(System)
+        q = np.linspace(0.01, 1.0, 2048)
+        lay = batch.layout_of(s, q)
+        truth = cfg4_params(lay, 10, seed=52)
+        names, off = ("noise__I0", "x__I0", "x__a", "x__hwhm_g", "x__hwhm_l", "x__r", "gp__I0", "gp__rg"), 0.02
+    free = [lay.slot(k) for k in names]
+    rs = np.random.RandomState(6)
+    Iobs = batch.compute_intensity_batch(lay, q, truth) * (1 + 0.02 * rs.randn(len(truth), len(q)))
+    start = truth.copy()
+    start[:, free] *= 1 + off * rs.uniform(-1, 1, (len(truth), len(free)))
+    a = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=25)
+    b = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=25, resident_limit=0)
+    assert not getattr(eng, "_jac_resident", {}), "resident workspaces are released at the end of the fit"
+    assert np.all(a.chi2 <= a.chi2_init * (1 + 1e-12))
+    np.testing.assert_allclose(a.chi2_init, b.chi2_init, rtol=1e-12)
+    np.testing.assert_allclose(a.chi2, b.chi2, rtol=1e-6)
+    np.testing.assert_allclose(a.params[:, free], b.params[:, free], rtol=1e-5)
+    # a batch whose slabs exceed the limit is fitted in row groups that fit (here 3 or more groups)
+    per_system = (eng.lib.xrsd_jacobian_workspace_bytes(len(q), len(truth), len(free))
+                  + eng.lib.xrsd_jacobian_workspace_bytes(len(q), len(truth), 1)) / len(truth)
+    g = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=25, resident_limit=per_system * (len(truth) // 3 + 0.5),
+                        min_group_rows=1)
+    assert g.params.shape == a.params.shape and g.active.shape == a.active.shape and g.n_accept.shape == a.n_accept.shape
+    np.testing.assert_allclose(g.chi2_init, a.chi2_init, rtol=1e-12)
+    np.testing.assert_allclose(g.chi2, a.chi2, rtol=1e-6)
+    np.testing.assert_allclose(g.params[:, free], a.params[:, free], rtol=1e-5)
+    # ... unless the groups would be too small to fill the GPU: then the whole batch takes the re-evaluating loop
+    h = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=25, resident_limit=per_system * 3.5)
+    np.testing.assert_array_equal(h.chi2, b.chi2)
+    np.testing.assert_array_equal(h.params, b.params)
+    # without a linear free parameter there is no cheap "pattern + chi2" call: the loop falls back by itself
+    nonlin = [sl for sl, k in zip(free, names) if not k.endswith("I0")]
+    c = batch.fit_batch(lay, q, Iobs, start, free_slots=nonlin, max_iter=5)
+    assert np.all(c.chi2 <= c.chi2_init * (1 + 1e-12))

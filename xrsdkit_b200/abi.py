@@ -21,7 +21,7 @@ OK, EINVAL, ECUDA, ECAPACITY, ENOMEM = 0, -1, -2, -3, -4
 
 i32, f64 = C.c_int32, C.c_double
 N_FEATURES, FEATURE_MAX_Q = 21, 8192
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Pop(C.Structure):
@@ -73,8 +73,9 @@ _SIGNATURES = {
                                       C.POINTER(Tables), vp, vp, C.c_int64, vp, vp, vp, vp]),
     "xrsd_jacobian_workspace_bytes": (C.c_int64, [i32, i32, i32]),
     "xrsd_jacobian_batch": (C.c_int, [C.POINTER(Layout), C.POINTER(Objective), vp, i32, vp, i32, i32,
-                                      C.POINTER(Tables), vp, vp, C.c_int64, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(f64), i32, f64,
+                                      C.POINTER(Tables), vp, vp, C.c_int64, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(f64), i32, f64, i32,
                                       vp, vp, vp, vp, vp, vp]),
+    "xrsd_jacobian_n_variants": (i32, [C.POINTER(Layout), C.POINTER(i32), i32, C.POINTER(i32), i32]),
     "xrsd_lm_propose": (C.c_int, [vp, i32, i32, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(f64), i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "xrsd_lm_update": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, vp, f64, f64, f64, f64, vp]),
     "xrsd_intensity_batch_host": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, vp, C.c_int64]),

@@ -25,10 +25,11 @@ cudaError_t xrsd_launch_residual(const xrsd_layout_t *, const xrsd_objective_t *
 size_t xrsd_jacobian_smem(int, int, int, int, int *);
 cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *, const xrsd_objective_t *, const double *, int, const double *, int, int,
                                  const xrsd_tables_t *, const double *, const double *, long long, const int32_t *, int,
-                                 const int32_t *, const double *, int, double,
+                                 const int32_t *, const double *, int, double, int,
                                  double *, double *, double *, double *, double *, unsigned *, int, int, int, const uint8_t *,
                                  cudaStream_t);
 size_t xrsd_jacobian_acc_doubles(int);
+int xrsd_jacobian_count_variants(const xrsd_layout_t *, const int32_t *, int, const int32_t *, int);
 cudaError_t xrsd_launch_lm_propose(const double *, int, int, const int32_t *, int, const int32_t *, const double *, int, const double *, const double *,
                                    const double *, const double *, const double *, const uint8_t *, double *, cudaStream_t);
 cudaError_t xrsd_launch_lm_update(double *, int, int, const double *, double *, const double *, double *, uint8_t *, int *,
@@ -304,7 +305,7 @@ int64_t xrsd_jacobian_workspace_bytes(int32_t n_q, int32_t batch, int32_t n_free
 int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q, int32_t n_q,
                         const double *d_params, int32_t ld_params, int32_t batch, const xrsd_tables_t *tables,
                         const double *d_Iobs, const double *d_dI, int64_t ld_obs, const int32_t *free_idx, int32_t n_free,
-                        const int32_t *ties, const double *tie_coef, int32_t n_tie, double rel_step, double *d_JTJ, double *d_JTr, double *d_chi2,
+                        const int32_t *ties, const double *tie_coef, int32_t n_tie, double rel_step, int32_t base_ready, double *d_JTJ, double *d_JTr, double *d_chi2,
                         void *d_workspace,
                         const uint8_t *d_active, void *stream) {
   int rc = check_layout(layout);
@@ -337,10 +338,16 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   double *d_acc = (double *)((char *)d_workspace + fbytes);
   unsigned *d_tickets = (unsigned *)((char *)d_workspace + fbytes + abytes);
   cudaError_t e = xrsd_launch_jacobian(layout, obj, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables, d_Iobs,
-                                       obj->has_dI ? d_dI : nullptr, (long long)ld_obs, free_idx, n_free, ties, tie_coef, n_tie, rel_step, d_JTJ,
+                                       obj->has_dI ? d_dI : nullptr, (long long)ld_obs, free_idx, n_free, ties, tie_coef, n_tie, rel_step, base_ready, d_JTJ,
                                        d_JTr, d_chi2, d_Fvar, d_acc, d_tickets, per, scratch, rm, d_active, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "jacobian_kernel");
   return XRSD_OK;
+}
+
+int32_t xrsd_jacobian_n_variants(const xrsd_layout_t *layout, const int32_t *free_idx, int32_t n_free, const int32_t *ties,
+                                 int32_t n_tie) {
+  if (check_layout(layout) || !free_idx || n_free < 1 || n_free > XRSD_MAX_FREE) return -1;
+  return xrsd_jacobian_count_variants(layout, free_idx, n_free, ties, n_tie);
 }
 
 int xrsd_lm_propose(const double *d_params, int32_t ld_params, int32_t batch, const int32_t *free_idx, int32_t n_free,

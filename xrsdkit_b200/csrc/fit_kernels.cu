@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, HX ? 10 : 6)   // measured on cf
 jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ q, int n_q,
                          const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T, const FreeSet F,
                          double rel_step, double *__restrict__ Fvar, int q_per_cta, int n_tiles, int pattern_doubles,
-                         int scratch_doubles, const uint8_t *__restrict__ active) {
+                         int scratch_doubles, const uint8_t *__restrict__ active, int skip_base) {
   // pattern_doubles == 0: direct mode, the variant's slab in HBM is the accumulation buffer (see intensity_kernel.cu)
   extern __shared__ __align__(16) double smem_d[];
   __shared__ EvalSharedT<HX> S;
@@ -172,6 +172,7 @@ jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *
   const int v = rem / n_tiles, tile = rem - v * n_tiles;
   if (b >= batch) return;
   if (active != nullptr && !active[b]) return;
+  if (skip_base && v == 0) return;            // base pattern and running totals are already in the workspace
   const int np = L.n_params;
   double *I_sm = smem_d;
   double *scratch = smem_d + pattern_doubles;
@@ -511,6 +512,11 @@ extern "C" size_t xrsd_jacobian_smem(int n_params, int n_free, int q_per_cta, in
   return ((size_t)pat + (size_t)scratch_doubles + (size_t)((n_params + 1) & ~1)) * sizeof(double);
 }
 
+extern "C" int xrsd_jacobian_count_variants(const xrsd_layout_t *layout, const int32_t *free_idx, int n_free, const int32_t *ties,
+                                            int n_tie) {
+  return xrsd::make_free_set(layout, free_idx, n_free, ties, nullptr, n_tie).n_var;
+}
+
 extern "C" size_t xrsd_jacobian_acc_doubles(int n_free) {
   const int NF = n_free <= 8 ? 8 : XRSD_MAX_FREE;
   return (size_t)(NF * NF + NF + 2);
@@ -520,7 +526,7 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
                                             int n_q, const double *d_params, int ldp, int batch,
                                             const xrsd_tables_t *tables, const double *d_Iobs, const double *d_dI,
                                             long long ld_obs, const int32_t *free_idx, int n_free, const int32_t *ties,
-                                            const double *tie_coef, int n_tie, double rel_step,
+                                            const double *tie_coef, int n_tie, double rel_step, int base_ready,
                                             double *d_JTJ, double *d_JTr, double *d_chi2, double *d_Fvar, double *d_acc,
                                             unsigned *d_tickets, int q_per_cta, int scratch_doubles, int radial_multi,
                                             const uint8_t *d_active, cudaStream_t stream) {
@@ -538,7 +544,7 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
   const long long n_blocks = (long long)batch * F.n_var * n_tiles;
   if (n_blocks > 2147483647LL) return cudaErrorInvalidConfiguration;
   kern<<<(unsigned)n_blocks, EVAL_THREADS, smem, stream>>>(*layout, d_q, n_q, d_params, ldp, batch, *tables, F, rel_step, d_Fvar,
-                                                          q_per_cta, n_tiles, pat, scratch_doubles, d_active);
+                                                          q_per_cta, n_tiles, pat, scratch_doubles, d_active, base_ready);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   // q-chunk per reduction CTA: every CTA pays a prologue and a 74-value fold, so chunks are as long as the grid

@@ -289,8 +289,14 @@ class Engine(object):
         return (C.c_int32 * len(flat))(*flat), (C.c_double * len(coef))(*coef), len(ties)
 
     def jacobian(self, layout, obj, q, d_params, Iobs_dev, dI_dev, ld_obs, free_slots, tables, rel_step=1e-6, out=None,
-                 active=None, ties=None):
-        """Normal equations (JTJ, JTr, chi2) of the weighted residual vector by forward differences."""
+                 active=None, ties=None, resident=None, base_ready=False):
+        """Normal equations (JTJ, JTr, chi2) of the weighted residual vector by forward differences.
+
+        By default the variant patterns go through a shared scratch, the batch cut into chunks of <= 4 GB.  With
+        `resident` (a key) the whole batch gets its own workspace that survives between calls, so the caller can
+        read the pattern slabs (`jacobian_slabs`) and, with base_ready=True, have the call trust the base pattern
+        and running totals already in it (the LM loop copies an accepted trial evaluation there instead of
+        evaluating the base again)."""
         torch = self.torch
         batch, nf = d_params.shape[0], len(free_slots)
         if out is None:
@@ -300,17 +306,31 @@ class Engine(object):
         idx = (C.c_int32 * nf)(*free_slots)
         tie_c, coef_c, n_tie = self.tie_array(ties)
         n_q = q.shape[0]
-        # HBM scratch for the variant patterns: chunk the batch so it stays under ~4 GB
-        chunk = max(1, min(batch, int(4e9 // (8 * (nf + 1 + abi.MAX_POPS) * n_q))))
-        need = int(self.lib.xrsd_jacobian_workspace_bytes(n_q, chunk, nf))
-        ws = getattr(self, "_jac_ws", None)
-        if ws is None or ws.numel() < need:
-            ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
-            self._jac_ws = ws
-            self._jac_ws_key = None
-        if self._jac_ws_key != (n_q, chunk, nf):      # ticket area moves with the shape: re-zero it
-            ws.zero_()
-            self._jac_ws_key = (n_q, chunk, nf)
+        if resident is not None:
+            chunk = batch
+            need = int(self.lib.xrsd_jacobian_workspace_bytes(n_q, chunk, nf))
+            store = self.__dict__.setdefault("_jac_resident", {})
+            ent = store.get(resident)
+            if ent is None or ent[0].numel() < need or ent[1] != (n_q, chunk, nf):
+                if base_ready:
+                    raise RuntimeError("base_ready needs the resident workspace of a previous call with the same shape")
+                ent = (torch.zeros(need, dtype=torch.uint8, device=self.device), (n_q, chunk, nf))
+                store[resident] = ent
+            ws = ent[0]
+        else:
+            if base_ready:
+                raise ValueError("base_ready requires a resident workspace")
+            # HBM scratch for the variant patterns: chunk the batch so it stays under ~4 GB
+            chunk = max(1, min(batch, int(4e9 // (8 * (nf + 1 + abi.MAX_POPS) * n_q))))
+            need = int(self.lib.xrsd_jacobian_workspace_bytes(n_q, chunk, nf))
+            ws = getattr(self, "_jac_ws", None)
+            if ws is None or ws.numel() < need:
+                ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+                self._jac_ws = ws
+                self._jac_ws_key = None
+            if self._jac_ws_key != (n_q, chunk, nf):      # ticket area moves with the shape: re-zero it
+                ws.zero_()
+                self._jac_ws_key = (n_q, chunk, nf)
         nx = layout.n_xtal
         for lo in range(0, batch, chunk):
             hi = min(batch, lo + chunk)
@@ -331,10 +351,32 @@ class Engine(object):
                 C.byref(layout.c), C.byref(obj), q.data_ptr(), n_q, d_params[lo:hi].data_ptr(), d_params.shape[1], hi - lo,
                 C.byref(tc) if tc is not None else None,
                 Iobs_dev.data_ptr() + 8 * lo * ld_obs, (dI_dev.data_ptr() + 8 * lo * ld_obs) if dI_dev is not None else None,
-                ld_obs, idx, nf, tie_c, coef_c, n_tie, float(rel_step), out[0][lo:hi].data_ptr(), out[1][lo:hi].data_ptr(), out[2][lo:hi].data_ptr(),
+                ld_obs, idx, nf, tie_c, coef_c, n_tie, float(rel_step), int(bool(base_ready)),
+                out[0][lo:hi].data_ptr(), out[1][lo:hi].data_ptr(), out[2][lo:hi].data_ptr(),
                 ws.data_ptr(), (active.data_ptr() + lo) if active is not None else None, self._stream()))
             self.launches += 2
         return out
+
+    def jacobian_variants(self, layout, free_slots, ties=None):
+        """Pattern slabs per system that jacobian() evaluates for this free set (base + non-linear parameters)."""
+        nf = len(free_slots)
+        idx = (C.c_int32 * nf)(*free_slots)
+        tie_c, _, n_tie = self.tie_array(ties)
+        n = int(self.lib.xrsd_jacobian_n_variants(C.byref(layout.c), idx, nf, tie_c, n_tie))
+        if n < 1:
+            raise ValueError("invalid free set")
+        return n
+
+    def jacobian_slabs(self, resident, layout, batch, n_q, n_var):
+        """[batch, n_var + n_pops, n_q] float64 view of a resident Jacobian workspace: slab 0 = base pattern,
+        1..n_var-1 = perturbed patterns, the last n_pops = running totals of the base after each population."""
+        ws = self._jac_resident[resident][0]
+        n_slab = n_var + int(layout.c.n_pops)
+        return ws[:batch * n_slab * n_q * 8].view(self.torch.float64).view(batch, n_slab, n_q)
+
+    def release_resident(self, *keys):
+        for k in keys:
+            self.__dict__.get("_jac_resident", {}).pop(k, None)
 
     def peak_profile(self, kind, x, p0, p1=0.0):
         """gaussian / lorentzian / voigt of tools/peak_math.py evaluated on the device."""

@@ -11,8 +11,11 @@ LM linearises.  One iteration for the whole batch is five launches:
     -> lm_update (accept / reject, damping update, convergence flags)
 
 No host synchronisation is needed inside the loop except the reflection-table capacity check.
+With a linear free parameter (an I0) the loop keeps the base pattern on the device between iterations
+(see lm_fit_batch): the trial evaluation is then a one-variant Jacobian launch instead of the residual kernel.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -38,8 +41,17 @@ def _apply_ties(params, ties):
 
 def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weighted=True, logI_weighted=True,
                  q_range=(0., float('inf')), max_iter=30, ftol=1e-8, lambda0=1e-2, up=8.0, down=4.0,
-                 lambda_max=1e10, rel_step=1e-6, lo=None, hi=None, eng=None, return_device=False, ties=None):
+                 lambda_max=1e10, rel_step=1e-6, lo=None, hi=None, eng=None, return_device=False, ties=None,
+                 resident_limit=24e9, min_group_rows=2048):
     """Fit every row of params0 ([batch, n_params]) to the matching row of Iobs ([batch, n_q] or [n_q]).
+
+    When the pattern slabs of the batch fit in `resident_limit` bytes, the loop keeps them on the device
+    between iterations: the trial evaluation writes its pattern (and per-population running totals) into a second
+    workspace, an accepted step copies those rows over the base rows, and the next Jacobian evaluates only the
+    perturbed variants -- one pattern evaluation per iteration and system less.  A larger batch is fitted in
+    row groups that fit (systems are independent; a group of `min_group_rows` systems or more still fills the
+    GPU many times over); if even such a group does not fit, or no free parameter is linear, the loop
+    re-evaluates the base inside every Jacobian (shared 4 GB scratch).
 
     Returns a FitResult of device tensors (return_device=True) or numpy arrays."""
     eng = eng or _engine.get_engine()
@@ -56,6 +68,35 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         raise ValueError("no free parameters to fit")
     if nf > abi.MAX_FREE:
         raise NotImplementedError("at most %d free parameters per system" % abi.MAX_FREE)
+    resident_limit = float(os.environ.get("XRSD_LM_RESIDENT_LIMIT", resident_limit))
+    # resident mode: a linear free parameter (an I0) makes "Jacobian with that one parameter" a plain evaluation
+    # of pattern + running totals + chi2, which is what the trial step needs
+    lin_slot = next((s for s in free_slots if eng.jacobian_variants(layout, [s], ties) == 1), None)
+    n_rows, n_pts = (int(np.shape(params0)[0]) if np.ndim(params0) == 2 else 1), int(np.shape(q)[0])
+
+    def resident_bytes(rows):
+        return int(lib.xrsd_jacobian_workspace_bytes(n_pts, rows, nf)) + int(lib.xrsd_jacobian_workspace_bytes(n_pts, rows, 1))
+
+    if lin_slot is not None and resident_bytes(n_rows) > resident_limit:
+        fit_rows = int(resident_limit // (resident_bytes(n_rows) / float(n_rows)))
+        if fit_rows >= max(1, min_group_rows):
+            n_groups = -(-n_rows // fit_rows)
+            step = -(-n_rows // n_groups)
+
+            def rows_of(x, a, b):      # per-system arrays are cut, shared ones ([n_q], scalars, None) pass through
+                return x[a:b] if x is not None and np.ndim(x) == 2 and np.shape(x)[0] == n_rows else x
+
+            parts = [lm_fit_batch(layout, q, rows_of(Iobs, a, min(a + step, n_rows)), params0[a:min(a + step, n_rows)],
+                                  free_slots=free_slots, dI=rows_of(dI, a, min(a + step, n_rows)),
+                                  error_weighted=error_weighted, logI_weighted=logI_weighted, q_range=q_range,
+                                  max_iter=max_iter, ftol=ftol, lambda0=lambda0, up=up, down=down, lambda_max=lambda_max,
+                                  rel_step=rel_step, lo=rows_of(lo, a, min(a + step, n_rows)),
+                                  hi=rows_of(hi, a, min(a + step, n_rows)), eng=eng, return_device=return_device, ties=ties,
+                                  resident_limit=resident_limit, min_group_rows=min_group_rows)
+                     for a in range(0, n_rows, step)]
+            cat = torch.cat if return_device else np.concatenate
+            return FitResult(cat([r.params for r in parts]), cat([r.chi2_init for r in parts]), cat([r.chi2 for r in parts]),
+                             max(r.n_iter for r in parts), cat([r.n_accept for r in parts]), cat([r.active for r in parts]))
     d_q = eng.to_device(q)
     host_p0 = None if isinstance(params0, torch.Tensor) else np.atleast_2d(np.asarray(params0, dtype=np.float64))
     d_p = eng.to_device(params0 if host_p0 is None else host_p0).clone()
@@ -97,10 +138,20 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     res_ws = eng.residual_workspace(batch)
     stream = eng._stream()
     n_iter = 0
+    n_var = eng.jacobian_variants(layout, free_slots, ties)
+    persist = lin_slot is not None and resident_bytes(batch) <= resident_limit
+    key0, key1 = ("lm", id(d_p), 0), ("lm", id(d_p), 1)
+    base_valid = False
+    jout_t = None
+    if persist:
+        jout_t = (torch.empty((batch, 1, 1), dtype=torch.float64, device=eng.device),
+                  torch.empty((batch, 1), dtype=torch.float64, device=eng.device), d_chi2_t)
     for it in range(max_iter):
         n_iter = it + 1
         _, _, d_chi2 = eng.jacobian(layout, obj, d_q, d_p, d_I, d_dI, ld_obs, free_slots, tables, rel_step, out=jout,
-                                    active=d_active if it > 0 else None, ties=ties)
+                                    active=d_active if it > 0 else None, ties=ties,
+                                    resident=key0 if persist else None, base_ready=persist and base_valid)
+        base_valid = persist
         if chi2_init is None:
             chi2_init = d_chi2.clone()
         abi.check(lib.xrsd_lm_propose(d_p.data_ptr(), d_p.shape[1], batch, idx, nf, tie_c, coef_c, n_tie, jout[0].data_ptr(), jout[1].data_ptr(),
@@ -109,19 +160,30 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         # in-loop table builds do not read their status back (no host sync); it is checked every 5 iterations
         t_tables = eng.build_tables(layout, d_trial, batch, max_cells=max_cells, reuse=t_tables,
                                     check=t_tables is None, active=d_active if t_tables is not None else None) if layout.n_xtal else None
-        abi.check(lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_trial.data_ptr(),
-                                          d_trial.shape[1], batch, C.byref(t_tables.c) if t_tables is not None else None,
-                                          d_I.data_ptr(), d_dI.data_ptr() if d_dI is not None else None, ld_obs,
-                                          d_chi2_t.data_ptr(), res_ws.data_ptr(), d_active.data_ptr(), stream))
-        if layout.n_xtal:
+        if persist:     # pattern, running totals and chi2 of the trial point, kept in the second resident workspace
+            eng.jacobian(layout, obj, d_q, d_trial, d_I, d_dI, ld_obs, [lin_slot], t_tables, rel_step, out=jout_t,
+                         active=d_active, ties=ties, resident=key1)
+        else:
+            abi.check(lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_trial.data_ptr(),
+                                              d_trial.shape[1], batch, C.byref(t_tables.c) if t_tables is not None else None,
+                                              d_I.data_ptr(), d_dI.data_ptr() if d_dI is not None else None, ld_obs,
+                                              d_chi2_t.data_ptr(), res_ws.data_ptr(), d_active.data_ptr(), stream))
+        if layout.n_xtal or persist:
             nacc_before = d_nacc.clone()
         abi.check(lib.xrsd_lm_update(d_p.data_ptr(), d_p.shape[1], batch, d_trial.data_ptr(), d_chi2.data_ptr(),
                                      d_chi2_t.data_ptr(), d_lambda.data_ptr(), d_active.data_ptr(), d_nacc.data_ptr(),
                                      float(up), float(down), float(ftol), float(lambda_max), stream))
         eng.launches += 3
+        if persist:
+            # accepted systems now sit at `trial`: the trial pattern and running totals become their base rows
+            acc = d_nacc != nacc_before
+            V0 = eng.jacobian_slabs(key0, layout, batch, n_q, n_var)
+            V1 = eng.jacobian_slabs(key1, layout, batch, n_q, 1)
+            V0[:, 0].copy_(torch.where(acc[:, None], V1[:, 0], V0[:, 0]))
+            V0[:, n_var:].copy_(torch.where(acc[:, None, None], V1[:, 1:], V0[:, n_var:]))
         if layout.n_xtal:
-            # accepted systems now sit at `trial`: their tables are the trial tables -- copy those rows (3 KB per
-            # system) instead of building them again
+            # ... and their tables are the trial tables -- copy those rows (3 KB per system) instead of building
+            # them again
             accepted = (d_nacc != nacc_before).repeat_interleave(layout.n_xtal)
             if not tables.take_rows_from(t_tables, accepted):
                 tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=tables, check=False, active=d_active)
@@ -135,6 +197,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
                 # (self-growing) path and resynchronise chi2 with the accepted parameters
                 tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells)
                 t_tables = None
+                base_valid = False          # the base rows were evaluated with the overflowed tables
                 d_chi2.copy_(eng.residual(layout, obj, d_q, d_p, d_I, d_dI, tables=tables))
             if not any_active:
                 break
@@ -143,6 +206,8 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     if layout.n_xtal:
         tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=tables)
     chi2 = eng.residual(layout, obj, d_q, d_p, d_I, d_dI, tables=tables)
+    if persist:
+        eng.release_resident(key0, key1)
     res = FitResult(d_p, chi2_init, chi2, n_iter, d_nacc, d_active.bool())
     if return_device:
         return res
