@@ -520,6 +520,35 @@ def run_gpu_arm(args):
         except Exception as e:
             secondary["features"] = {"error": repr(e)}
 
+        try:        # BASELINE configs[0]: ONE pattern through System.compute_intensity (numpy in, numpy out)
+            from xrsdkit_b200.system import System
+            s1 = System(p=dict(structure="diffuse", form="spherical", parameters={"r": {"value": 20.0}, "I0": {"value": 1.0}}))
+            q1 = np.linspace(0.001, 0.5, 2000)
+            for _ in range(200):
+                I1 = s1.compute_intensity(q1)
+            t0 = time.perf_counter()
+            for _ in range(2000):
+                I1 = s1.compute_intensity(q1)
+            us1 = (time.perf_counter() - t0) / 2000 * 1e6
+            secondary["cfg1"] = {"workload": "cfg1: single dilute spherical population (r=20), 2000-pt q, ONE pattern per call "
+                                             "through System.compute_intensity with host arrays (latency-bound)",
+                                 "unit": "us per call", "value": us1, "higher_is_better": False}
+            if not args.no_cpu:
+                from oracle import xrsd_oracle as xo
+                from xrsdkit_b200 import definitions as d1
+                tabs = dict(atomic_table=d1.atomic_params, sg_point_groups=d1.sg_point_groups,
+                            lattice_space_groups=d1.lattice_space_groups)
+                sd = s1.to_dict()
+                for _ in range(50):
+                    Ir = xo.system_intensity(q1, sd, **tabs)
+                t0 = time.perf_counter()
+                for _ in range(500):
+                    Ir = xo.system_intensity(q1, sd, **tabs)
+                secondary["cfg1"]["cpu_us_per_call_1core"] = (time.perf_counter() - t0) / 500 * 1e6
+                secondary["cfg1"]["max_rel_diff_vs_oracle"] = float(np.max(np.abs(I1 - Ir) / np.abs(Ir)))
+        except Exception as e:
+            secondary["cfg1"] = {"error": repr(e)}
+
     # ---- CPU baseline: bounded sample on the host cores
     cores = host_cores()
     per_core = {"cfg2": 256, "cfg3": 4, "cfg4": 4, "cfg5": 4}[args.workload]     # ~10-30 core-seconds per core in total

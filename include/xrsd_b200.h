@@ -231,6 +231,12 @@ int xrsd_lm_update(double *d_params, int32_t ld_params, int32_t batch,
                    double *d_lambda, uint8_t *d_active, int32_t *d_n_accept,
                    double up, double down, double ftol, double lambda_max, void *stream);
 
+/* dst[r*dst_stride + i] = src[r*src_stride + i], i < row_len, for every row r < n_rows with d_mask[r] != 0
+ * (strides and row_len in doubles).  An accepted LM step moves the trial pattern and its running totals over the
+ * base rows of a resident Jacobian workspace with it (see xrsd_jacobian_n_variants for the slab layout). */
+int xrsd_copy_rows_masked(double *d_dst, int64_t dst_stride, const double *d_src, int64_t src_stride, int64_t row_len,
+                          int32_t n_rows, const uint8_t *d_mask, void *stream);
+
 /* Host-buffer convenience call (what a non-Python caller binds): allocates / reuses an
  * internal device workspace, copies q and params in, builds tables when the layout has
  * crystalline populations, computes, copies I back.  Blocking. */

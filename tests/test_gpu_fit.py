@@ -452,3 +452,25 @@ def test_lm_resident_loop_matches_re_evaluating_loop(eng, kind):
     nonlin = [sl for sl, k in zip(free, names) if not k.endswith("I0")]
     c = batch.fit_batch(lay, q, Iobs, start, free_slots=nonlin, max_iter=5)
     assert np.all(c.chi2 <= c.chi2_init * (1 + 1e-12))
+
+
+@pytest.mark.parametrize("row_len", [1, 1237, 2048, 5000])
+def test_copy_rows_masked(eng, row_len):
+    """xrsd_copy_rows_masked: flagged rows are replaced, the others and the padding between rows stay untouched."""
+    import torch
+    from xrsdkit_b200 import abi
+    n_rows, ld_dst, ld_src = 37, row_len + 13, row_len + 3
+    g = torch.Generator(eng.device).manual_seed(row_len)
+    dst = torch.rand((n_rows, ld_dst), dtype=torch.float64, device=eng.device, generator=g)
+    src = torch.rand((n_rows, ld_src), dtype=torch.float64, device=eng.device, generator=g)
+    mask = torch.rand(n_rows, device=eng.device, generator=g) < 0.4
+    mask[0], mask[-1] = True, False
+    want = dst.clone()
+    want[mask, :row_len] = src[mask, :row_len]
+    abi.check(eng.lib.xrsd_copy_rows_masked(dst.data_ptr(), ld_dst, src.data_ptr(), ld_src, row_len, n_rows, mask.data_ptr(),
+                                            eng._stream()))
+    assert torch.equal(dst, want)
+    with pytest.raises(ValueError):
+        abi.check(eng.lib.xrsd_copy_rows_masked(dst.data_ptr(), row_len - 1, src.data_ptr(), ld_src, row_len, n_rows,
+                                                mask.data_ptr(), eng._stream()))
+    abi.check(eng.lib.xrsd_copy_rows_masked(None, 0, None, 0, 0, 0, None, eng._stream()))     # empty: no-op

@@ -76,6 +76,7 @@ _SIGNATURES = {
                                       C.POINTER(Tables), vp, vp, C.c_int64, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(f64), i32, f64, i32,
                                       vp, vp, vp, vp, vp, vp]),
     "xrsd_jacobian_n_variants": (i32, [C.POINTER(Layout), C.POINTER(i32), i32, C.POINTER(i32), i32]),
+    "xrsd_copy_rows_masked": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int64, i32, vp, vp]),
     "xrsd_lm_propose": (C.c_int, [vp, i32, i32, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(f64), i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "xrsd_lm_update": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, vp, f64, f64, f64, f64, vp]),
     "xrsd_intensity_batch_host": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, vp, C.c_int64]),

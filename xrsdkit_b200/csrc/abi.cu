@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -29,6 +30,8 @@ cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *, const xrsd_objective_t *
                                  double *, double *, double *, double *, double *, unsigned *, int, int, int, const uint8_t *,
                                  cudaStream_t);
 size_t xrsd_jacobian_acc_doubles(int);
+cudaError_t xrsd_launch_copy_rows_masked(double *, long long, const double *, long long, long long, int, const uint8_t *,
+                                         cudaStream_t);
 int xrsd_jacobian_count_variants(const xrsd_layout_t *, const int32_t *, int, const int32_t *, int);
 cudaError_t xrsd_launch_lm_propose(const double *, int, int, const int32_t *, int, const int32_t *, const double *, int, const double *, const double *,
                                    const double *, const double *, const double *, const uint8_t *, double *, cudaStream_t);
@@ -376,6 +379,18 @@ int xrsd_lm_update(double *d_params, int32_t ld_params, int32_t batch, const dou
   return XRSD_OK;
 }
 
+int xrsd_copy_rows_masked(double *d_dst, int64_t dst_stride, const double *d_src, int64_t src_stride, int64_t row_len,
+                          int32_t n_rows, const uint8_t *d_mask, void *stream) {
+  if (n_rows < 0 || row_len < 0) return fail(XRSD_EINVAL, "n_rows %d, row_len %lld", n_rows, (long long)row_len);
+  if (n_rows == 0 || row_len == 0) return XRSD_OK;
+  if (!d_dst || !d_src || !d_mask) return fail(XRSD_EINVAL, "NULL pointer");
+  if (dst_stride < row_len) return fail(XRSD_EINVAL, "dst_stride %lld < row_len %lld: rows would overlap", (long long)dst_stride, (long long)row_len);
+  cudaError_t e = xrsd_launch_copy_rows_masked(d_dst, (long long)dst_stride, d_src, (long long)src_stride, (long long)row_len,
+                                               n_rows, d_mask, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "copy_rows_masked_kernel");
+  return XRSD_OK;
+}
+
 int xrsd_peak_profile(int32_t kind, double hwhm_or_hwhm_g, double hwhm_l, const double *d_x, int32_t n, double *d_out,
                       void *stream) {
   if (kind < XRSD_PROFILE_VOIGT || kind > XRSD_PROFILE_LORENTZIAN) return fail(XRSD_EINVAL, "profile kind %d", kind);
@@ -438,6 +453,7 @@ struct Workspace {
   void *base = nullptr;
   size_t bytes = 0;
   double *pinned = nullptr;
+  double *pinned_dev = nullptr;   // the same buffer as the device addresses it (mapped pinned memory), or nullptr
   size_t pinned_bytes = 0;
   std::vector<double> q_host;     // the grid currently resident at offset 0 of the workspace (skips its upload)
   bool q_valid = false;
@@ -466,9 +482,20 @@ double *pinned_reserve(size_t bytes) {
   g_ws.pinned = nullptr;
   g_ws.pinned_bytes = 0;
   const size_t want = std::max(bytes, (size_t)256 << 10);
-  if (cudaMallocHost((void **)&g_ws.pinned, want) != cudaSuccess) { cudaGetLastError(); g_ws.pinned = nullptr; return nullptr; }
+  g_ws.pinned_dev = nullptr;
+  if (cudaHostAlloc((void **)&g_ws.pinned, want, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); g_ws.pinned = nullptr; return nullptr; }
   g_ws.pinned_bytes = want;
+  if (cudaHostGetDevicePointer((void **)&g_ws.pinned_dev, g_ws.pinned, 0) != cudaSuccess) { cudaGetLastError(); g_ws.pinned_dev = nullptr; }
   return g_ws.pinned;
+}
+// Small non-crystalline calls skip both copies: the kernel reads the parameter rows from the mapped pinned buffer
+// and writes I(q) straight into it (staged mode writes every value once, coalesced: posted PCIe writes), so the
+// call is launch + kernel + one synchronisation.  Crystalline layouts accumulate in place in the output row
+// (direct mode) and keep the device buffer.  XRSD_HOST_ZEROCOPY=0 turns it off (A/B timing).
+constexpr size_t kZeroCopyMax = 1u << 20;
+bool zero_copy_enabled() {
+  static const bool on = [] { const char *v = getenv("XRSD_HOST_ZEROCOPY"); return !(v && v[0] == '0'); }();
+  return on;
 }
 }  // namespace
 
@@ -489,6 +516,7 @@ void xrsd_release_workspace(void) {
   g_ws.q_valid = false;
   if (g_ws.pinned) cudaFreeHost(g_ws.pinned);
   g_ws.pinned = nullptr;
+  g_ws.pinned_dev = nullptr;
   g_ws.pinned_bytes = 0;
   if (g_ws.base) cudaFree(g_ws.base);
   g_ws.base = nullptr;
@@ -531,8 +559,12 @@ int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int3
   const size_t p_bytes = (size_t)batch * ld_params * 8, I_bytes = (size_t)batch * n_q * 8;
   double *pin = pinned_reserve(align256(p_bytes) + I_bytes);
   if (pin) memcpy(pin, params, p_bytes);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(base + o_p, pin ? (const void *)pin : (const void *)params, p_bytes, cudaMemcpyHostToDevice, s);
+  const bool zero_copy = pin && g_ws.pinned_dev && n_x == 0 && I_bytes <= kZeroCopyMax && zero_copy_enabled();
+  if (e == cudaSuccess && !zero_copy)
+    e = cudaMemcpyAsync(base + o_p, pin ? (const void *)pin : (const void *)params, p_bytes, cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) { g_ws.q_valid = false; return cuda_fail(e, "H2D copy"); }
+  const double *d_par = zero_copy ? g_ws.pinned_dev : (const double *)(base + o_p);
+  double *d_out = zero_copy ? g_ws.pinned_dev + align256(p_bytes) / 8 : (double *)(base + o_I);
   xrsd_tables_t T = {};
   if (n_x) {
     T.cap_shell = cap_shell; T.cap_refl = 0; T.n_pairs_max = n_pairs;
@@ -548,15 +580,17 @@ int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int3
       rc = xrsd_reflection_tables(layout, (const double *)(base + o_p), ld_params, batch, &T, max_cells, nullptr, s);
       if (rc) break;
     }
-    rc = xrsd_intensity_batch(layout, (const double *)(base + o_q), n_q, (const double *)(base + o_p), ld_params, batch,
-                              n_x ? &T : nullptr, (double *)(base + o_I), n_q, s);
+    rc = xrsd_intensity_batch(layout, (const double *)(base + o_q), n_q, d_par, ld_params, batch, n_x ? &T : nullptr, d_out,
+                              n_q, s);
     if (rc) break;
     if (n_x) {
       e = cudaMemcpyAsync(st.data(), T.status, n_tab * 4, cudaMemcpyDeviceToHost, s);
       if (e == cudaSuccess) e = cudaMemcpyAsync(na.data(), T.n_all, n_tab * 4, cudaMemcpyDeviceToHost, s);
       if (e != cudaSuccess) { rc = cuda_fail(e, "table status copy"); break; }
     }
-    if (pin) {
+    if (zero_copy) {
+      e = cudaStreamSynchronize(s);       // the kernel has written the pinned result itself
+    } else if (pin) {
       double *pin_I = pin + align256(p_bytes) / 8;
       e = cudaMemcpyAsync(pin_I, base + o_I, I_bytes, cudaMemcpyDeviceToHost, s);
       if (e == cudaSuccess) e = cudaStreamSynchronize(s);

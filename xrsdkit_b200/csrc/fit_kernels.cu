@@ -480,6 +480,32 @@ __global__ void lm_update_kernel(double *__restrict__ params, int ldp, int batch
   }
 }
 
+// Rows of `src` flagged in `mask` replace the same rows of `dst` (row r starts at r*stride; `row_len` doubles are
+// copied).  The LM loop uses it for accepted steps: the trial pattern and its running totals become the base rows
+// of the resident Jacobian workspace.  Unflagged rows cost one byte read; flagged ones stream at HBM/L2 speed
+// (each CTA copies COPY_CHUNK doubles with 8 independent loads per thread in flight).
+constexpr int COPY_THREADS = 256, COPY_CHUNK = 2048;
+__global__ void __launch_bounds__(COPY_THREADS)
+copy_rows_masked_kernel(double *__restrict__ dst, long long dst_stride, const double *__restrict__ src, long long src_stride,
+                        int row_len, int chunks, const uint8_t *__restrict__ mask) {
+  const int r = blockIdx.x / chunks, c = blockIdx.x - r * chunks;
+  if (!mask[r]) return;
+  double *__restrict__ d = dst + (size_t)r * dst_stride + (size_t)c * COPY_CHUNK;
+  const double *__restrict__ s = src + (size_t)r * src_stride + (size_t)c * COPY_CHUNK;
+  const int n = min(COPY_CHUNK, row_len - c * COPY_CHUNK);
+  double v[COPY_CHUNK / COPY_THREADS];
+#pragma unroll
+  for (int k = 0; k < COPY_CHUNK / COPY_THREADS; ++k) {
+    const int i = threadIdx.x + k * COPY_THREADS;
+    if (i < n) v[k] = s[i];
+  }
+#pragma unroll
+  for (int k = 0; k < COPY_CHUNK / COPY_THREADS; ++k) {
+    const int i = threadIdx.x + k * COPY_THREADS;
+    if (i < n) d[i] = v[k];
+  }
+}
+
 }  // namespace xrsd
 
 using xrsd::FreeSet;
@@ -590,5 +616,16 @@ extern "C" cudaError_t xrsd_launch_lm_update(double *d_params, int ldp, int batc
   if (batch <= 0) return cudaSuccess;
   xrsd::lm_update_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(d_params, ldp, batch, d_trial, d_chi2, d_chi2_trial,
                                                                   d_lambda, d_active, d_n_accept, up, down, ftol, lambda_max);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t xrsd_launch_copy_rows_masked(double *d_dst, long long dst_stride, const double *d_src,
+                                                    long long src_stride, long long row_len, int n_rows,
+                                                    const uint8_t *d_mask, cudaStream_t stream) {
+  if (n_rows <= 0 || row_len <= 0) return cudaSuccess;
+  const long long chunks = (row_len + xrsd::COPY_CHUNK - 1) / xrsd::COPY_CHUNK;
+  if (row_len > 2147483647LL || chunks * n_rows > 2147483647LL) return cudaErrorInvalidConfiguration;
+  xrsd::copy_rows_masked_kernel<<<(unsigned)(chunks * n_rows), xrsd::COPY_THREADS, 0, stream>>>(
+      d_dst, dst_stride, d_src, src_stride, (int)row_len, (int)chunks, d_mask);
   return cudaGetLastError();
 }

@@ -374,6 +374,17 @@ class Engine(object):
         n_slab = n_var + int(layout.c.n_pops)
         return ws[:batch * n_slab * n_q * 8].view(self.torch.float64).view(batch, n_slab, n_q)
 
+    def take_slab_rows(self, dst_key, src_key, layout, batch, n_q, n_var, mask):
+        """Rows flagged in `mask` (bool / uint8 [batch]): base pattern and running totals of the resident workspace
+        `dst_key` (n_var variants) are overwritten with those of `src_key` (a one-variant workspace)."""
+        n_pops = int(layout.c.n_pops)
+        dst, src = self._jac_resident[dst_key][0].data_ptr(), self._jac_resident[src_key][0].data_ptr()
+        ld_dst, ld_src = (n_var + n_pops) * n_q, (1 + n_pops) * n_q
+        for off_dst, off_src, row_len in ((0, 0, n_q), (n_var * n_q, n_q, n_pops * n_q)):
+            abi.check(self.lib.xrsd_copy_rows_masked(dst + 8 * off_dst, ld_dst, src + 8 * off_src, ld_src, row_len, batch,
+                                                     mask.data_ptr(), self._stream()))
+        self.launches += 2
+
     def release_resident(self, *keys):
         for k in keys:
             self.__dict__.get("_jac_resident", {}).pop(k, None)

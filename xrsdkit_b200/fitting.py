@@ -176,11 +176,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         eng.launches += 3
         if persist:
             # accepted systems now sit at `trial`: the trial pattern and running totals become their base rows
-            acc = d_nacc != nacc_before
-            V0 = eng.jacobian_slabs(key0, layout, batch, n_q, n_var)
-            V1 = eng.jacobian_slabs(key1, layout, batch, n_q, 1)
-            V0[:, 0].copy_(torch.where(acc[:, None], V1[:, 0], V0[:, 0]))
-            V0[:, n_var:].copy_(torch.where(acc[:, None, None], V1[:, 1:], V0[:, n_var:]))
+            eng.take_slab_rows(key0, key1, layout, batch, n_q, n_var, d_nacc != nacc_before)
         if layout.n_xtal:
             # ... and their tables are the trial tables -- copy those rows (3 KB per system) instead of building
             # them again
