@@ -207,13 +207,21 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
                         int32_t batch, const xrsd_tables_t *tables,
                         const double *d_Iobs, const double *d_dI, int64_t ld_obs,
                         const int32_t *free_idx, int32_t n_free, const int32_t *ties, const double *tie_coef,
-                        int32_t n_tie, double rel_step, int32_t base_ready, double *d_JTJ, double *d_JTr, double *d_chi2,
+                        int32_t n_tie, double rel_step, int32_t mode, double *d_JTJ, double *d_JTr, double *d_chi2,
                         void *d_workspace, const uint8_t *d_active, void *stream);
 /* Number of pattern slabs per system the call above evaluates and keeps at the head of d_workspace:
  * [batch][n_variants + layout.n_pops][n_q] doubles -- slab 0 is the base pattern, slabs 1..n_variants-1 the
  * perturbed ones (one per non-linear free parameter), the last n_pops the base pattern's running totals after
- * each population.  With base_ready != 0 the call trusts slab 0 and the running totals already in the workspace
- * (e.g. copied there from an accepted trial evaluation) and evaluates only the perturbed variants. */
+ * each population.  `mode` of xrsd_jacobian_batch:
+ *   XRSD_JAC_FULL           evaluate every slab, then reduce;
+ *   XRSD_JAC_BASE_READY     trust slab 0 and the running totals already in the workspace (e.g. copied there from
+ *                           an accepted trial evaluation), evaluate only the perturbed variants, then reduce;
+ *   XRSD_JAC_PATTERNS_ONLY  evaluate every slab and stop: no reduction, d_JTJ / d_JTr / d_chi2 / d_Iobs / d_dI are
+ *                           not touched (may be NULL).  With a single linear free parameter this is "pattern and
+ *                           running totals of every system, honouring d_active". */
+#define XRSD_JAC_FULL 0
+#define XRSD_JAC_BASE_READY 1
+#define XRSD_JAC_PATTERNS_ONLY 2
 int32_t xrsd_jacobian_n_variants(const xrsd_layout_t *layout, const int32_t *free_idx, int32_t n_free,
                                  const int32_t *ties, int32_t n_tie);
 
@@ -230,6 +238,12 @@ int xrsd_lm_update(double *d_params, int32_t ld_params, int32_t batch,
                    const double *d_trial, double *d_chi2, const double *d_chi2_trial,
                    double *d_lambda, uint8_t *d_active, int32_t *d_n_accept,
                    double up, double down, double ftol, double lambda_max, void *stream);
+
+/* chi2[b] of System.evaluate_residual for patterns that are already in device memory: d_I[batch][ld_I] against
+ * d_Iobs / d_dI [batch][ld_obs] (ld_obs == 0 broadcasts), same objective and masks as xrsd_residual_batch. */
+int xrsd_pattern_chi2_batch(const xrsd_objective_t *obj, const double *d_q, int32_t n_q, const double *d_I, int64_t ld_I,
+                            int32_t batch, const double *d_Iobs, const double *d_dI, int64_t ld_obs, double *d_chi2,
+                            const uint8_t *d_active, void *stream);
 
 /* dst[r*dst_stride + i] = src[r*src_stride + i], i < row_len, for every row r < n_rows with d_mask[r] != 0
  * (strides and row_len in doubles).  An accepted LM step moves the trial pattern and its running totals over the

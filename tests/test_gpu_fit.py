@@ -474,3 +474,107 @@ def test_copy_rows_masked(eng, row_len):
         abi.check(eng.lib.xrsd_copy_rows_masked(dst.data_ptr(), row_len - 1, src.data_ptr(), ld_src, row_len, n_rows,
                                                 mask.data_ptr(), eng._stream()))
     abi.check(eng.lib.xrsd_copy_rows_masked(None, 0, None, 0, 0, 0, None, eng._stream()))     # empty: no-op
+
+
+@pytest.mark.parametrize("log_mode,with_dI", [(True, False), (False, True), (True, True)])
+def test_pattern_chi2_matches_residual_path(eng, log_mode, with_dI):
+    """xrsd_pattern_chi2_batch on stored patterns = xrsd_residual_batch (oracle-checked above) on the parameters that
+    produce them: strided rows, q_range cutting both ends, non-positive observations, the active mask."""
+    import torch
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg2_system(System)
+    q = np.linspace(0.01, 0.5, 1237)
+    lay = batch.layout_of(s, q)
+    B = 9
+    P = cfg2_params(lay, B, seed=61)
+    rs = np.random.RandomState(4)
+    I = batch.compute_intensity_batch(lay, q, P)
+    Iobs = I * (1 + 0.05 * rs.randn(B, len(q)))
+    Iobs[:, 17] = 0.0
+    Iobs[2, 400:420] = -1.0
+    dI = (0.03 * np.abs(Iobs) + 1e-3) if with_dI else None
+    obj = eng.objective(True, log_mode, (0.05, 0.45), has_dI=with_dI)
+    d_q, d_p, d_I = eng.to_device(q), eng.to_device(P * 1.01), eng.to_device(Iobs)
+    d_dI = eng.to_device(dI) if with_dI else None
+    want = eng.residual(lay, obj, d_q, d_p, d_I, d_dI)
+    slabs = torch.full((B, 3, len(q)), float("nan"), dtype=torch.float64, device=eng.device)
+    slabs[:, 1] = eng.intensity(lay, d_q, d_p)
+    got = eng.pattern_chi2(obj, d_q, slabs[:, 1], d_I, d_dI, len(q))
+    np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-12)
+    active = torch.ones(B, dtype=torch.uint8, device=eng.device)
+    active[3] = 0
+    out = torch.full((B,), -1.0, dtype=torch.float64, device=eng.device)
+    eng.pattern_chi2(obj, d_q, slabs[:, 1], d_I, d_dI, len(q), out=out, active=active)
+    assert out[3].item() == -1.0 and torch.equal(out[active.bool()], got[active.bool()])
+    # one shared observed pattern (ld_obs = 0)
+    one = eng.pattern_chi2(obj, d_q, slabs[:, 1], d_I[0].contiguous(), d_dI[0].contiguous() if with_dI else None, 0)
+    want_one = eng.residual(lay, obj, d_q, d_p, d_I[0].contiguous(), d_dI[0].contiguous() if with_dI else None)
+    np.testing.assert_allclose(one.cpu().numpy(), want_one.cpu().numpy(), rtol=1e-12)
+
+
+def test_jacobian_patterns_only_mode(eng):
+    """XRSD_JAC_PATTERNS_ONLY leaves the same slabs as the full call and writes no normal equations."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg4_system(System)
+    q = np.linspace(0.01, 1.0, 1500)
+    lay = batch.layout_of(s, q)
+    B = 5
+    P = cfg4_params(lay, B, seed=43)
+    free = [lay.slot(k) for k in ("x__I0", "x__a", "gp__rg")]
+    obj = eng.objective(True, True, (0.0, float("inf")))
+    d_q, d_p = eng.to_device(q), eng.to_device(P)
+    d_I = eng.intensity(lay, d_q, d_p) * 1.02
+    tables = eng.build_tables(lay, d_p, B, params_host=P)
+    eng.jacobian(lay, obj, d_q, d_p, d_I, None, len(q), free, tables, resident=("t", 1))
+    assert eng.jacobian(lay, obj, d_q, d_p, None, None, 0, free, tables, resident=("t", 2), patterns_only=True) is None
+    n_var = eng.jacobian_variants(lay, free)
+    a = eng.jacobian_slabs(("t", 1), lay, B, len(q), n_var)
+    b = eng.jacobian_slabs(("t", 2), lay, B, len(q), n_var)
+    np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
+    with pytest.raises(ValueError):
+        eng.jacobian(lay, obj, d_q, d_p, None, None, 0, free, tables, patterns_only=True)         # needs a resident workspace
+    with pytest.raises(ValueError):
+        eng.jacobian(lay, obj, d_q, d_p, None, None, 0, free, tables, resident=("t", 2))          # full mode needs I_obs
+    eng.release_resident(("t", 1), ("t", 2))
+
+
+def test_lm_near_box_turns_long_lattice_steps_back_and_recentres(eng):
+    """In-loop reflection tables are built with the candidate box of the current parameters grown by `table_growth`;
+    a trial cell that does not fit is rejected (chi2 = inf) and the box re-centred at the next flag read.  Here the
+    first box is set too small for the larger half of the systems (`loop_cells`): all their trials are turned back
+    until the first flag read (iteration 5), after which they must still arrive where the fit with the full box
+    (table_growth=1.5: the near box is never smaller than it) arrives."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch, lowering
+    s = cfg4_system(System)
+    q = np.linspace(0.01, 1.0, 2048)
+    lay = batch.layout_of(s, q)
+    n = 16
+    truth = cfg4_params(lay, n, seed=71)
+    a = lay.slot("x__a")
+    truth[:, a] = np.where(np.arange(n) % 2, 45.0, 75.0) + np.arange(n)
+    Iobs = batch.compute_intensity_batch(lay, q, truth)
+    free = [lay.slot(k) for k in ("noise__I0", "x__I0", "x__a", "x__hwhm_g", "x__hwhm_l", "x__r", "gp__I0", "gp__rg")]
+    start = truth.copy()
+    rs = np.random.RandomState(9)
+    start[:, free] *= 1 + 0.01 * rs.uniform(-1, 1, (n, len(free)))
+    start[:, a] = truth[:, a] * (1 + 0.002 * rs.uniform(-1, 1, n))
+    small = lowering.max_cells(lay, start[1::2])            # holds the a ~ 45..61 systems only
+    assert small < lowering.max_cells(lay, start[0::2])
+    wide = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=40, table_growth=1.5)
+    near = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=60, loop_cells=small)
+    stuck = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=4, loop_cells=small)
+    for r in (wide, near, stuck):
+        assert np.all(r.chi2 <= r.chi2_init * (1 + 1e-12))
+    # before the first flag read the large systems can only have taken the step of iteration 0 (its tables are the
+    # checked build with the full box); the small ones move every iteration
+    assert np.all(stuck.n_accept[0::2] <= 1), stuck.n_accept
+    assert stuck.n_accept[1::2].mean() > stuck.n_accept[0::2].mean() + 1, stuck.n_accept
+    ok = wide.chi2 < 1e-6 * wide.chi2_init
+    print("near-box LM: wide converges for %d of %d, near for %d; accepted steps %s" %
+          (ok.sum(), n, (near.chi2 < 1e-6 * near.chi2_init).sum(), near.n_accept))
+    assert ok.mean() >= 0.5, wide.chi2 / wide.chi2_init
+    assert np.all(near.n_accept[0::2] > 1), near.n_accept
+    assert np.all(near.chi2[ok] < 1e-3 * near.chi2_init[ok]), near.chi2 / near.chi2_init

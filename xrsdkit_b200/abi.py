@@ -16,6 +16,7 @@ PROFILE = dict(voigt=0, gaussian=1, lorentzian=2)
 LAT_CUBIC, LAT_HCP, LAT_HEXAGONAL, LAT_ORTHORHOMBIC, LAT_TETRAGONAL, LAT_MONOCLINIC, LAT_RHOMBOHEDRAL, LAT_TRICLINIC = range(8)
 OPS = dict(inversion=0, mirror_x=1, mirror_y=2, mirror_z=3, mirror_x_y=4, mirror_y_z=5, mirror_z_x=6,
            mirror_nx_y=7, mirror_ny_z=8, mirror_nz_x=9)
+JAC_FULL, JAC_BASE_READY, JAC_PATTERNS_ONLY = 0, 1, 2      # mode of xrsd_jacobian_batch
 TABLE_GRID_OVERFLOW, TABLE_LIST_OVERFLOW, TABLE_SHELL_OVERFLOW, TABLE_BAD_LATTICE = 1, 2, 4, 8
 OK, EINVAL, ECUDA, ECAPACITY, ENOMEM = 0, -1, -2, -3, -4
 
@@ -76,6 +77,7 @@ _SIGNATURES = {
                                       C.POINTER(Tables), vp, vp, C.c_int64, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(f64), i32, f64, i32,
                                       vp, vp, vp, vp, vp, vp]),
     "xrsd_jacobian_n_variants": (i32, [C.POINTER(Layout), C.POINTER(i32), i32, C.POINTER(i32), i32]),
+    "xrsd_pattern_chi2_batch": (C.c_int, [C.POINTER(Objective), vp, i32, vp, C.c_int64, i32, vp, vp, C.c_int64, vp, vp, vp]),
     "xrsd_copy_rows_masked": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int64, i32, vp, vp]),
     "xrsd_lm_propose": (C.c_int, [vp, i32, i32, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(f64), i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "xrsd_lm_update": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, vp, f64, f64, f64, f64, vp]),

@@ -30,6 +30,8 @@ cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *, const xrsd_objective_t *
                                  double *, double *, double *, double *, double *, unsigned *, int, int, int, const uint8_t *,
                                  cudaStream_t);
 size_t xrsd_jacobian_acc_doubles(int);
+cudaError_t xrsd_launch_pattern_chi2(const xrsd_objective_t *, const double *, int, const double *, long long, int, const double *,
+                                     const double *, long long, double *, const uint8_t *, cudaStream_t);
 cudaError_t xrsd_launch_copy_rows_masked(double *, long long, const double *, long long, long long, int, const uint8_t *,
                                          cudaStream_t);
 int xrsd_jacobian_count_variants(const xrsd_layout_t *, const int32_t *, int, const int32_t *, int);
@@ -308,7 +310,7 @@ int64_t xrsd_jacobian_workspace_bytes(int32_t n_q, int32_t batch, int32_t n_free
 int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q, int32_t n_q,
                         const double *d_params, int32_t ld_params, int32_t batch, const xrsd_tables_t *tables,
                         const double *d_Iobs, const double *d_dI, int64_t ld_obs, const int32_t *free_idx, int32_t n_free,
-                        const int32_t *ties, const double *tie_coef, int32_t n_tie, double rel_step, int32_t base_ready, double *d_JTJ, double *d_JTr, double *d_chi2,
+                        const int32_t *ties, const double *tie_coef, int32_t n_tie, double rel_step, int32_t mode, double *d_JTJ, double *d_JTr, double *d_chi2,
                         void *d_workspace,
                         const uint8_t *d_active, void *stream) {
   int rc = check_layout(layout);
@@ -316,13 +318,16 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   if (batch <= 0 || n_q <= 0) return XRSD_OK;
   rc = check_tables(layout, tables);
   if (rc) return rc;
-  if (!obj || !d_q || !d_params || !d_Iobs || !d_JTJ || !d_JTr || !d_chi2 || !free_idx || !d_workspace)
+  if (mode != XRSD_JAC_FULL && mode != XRSD_JAC_BASE_READY && mode != XRSD_JAC_PATTERNS_ONLY)
+    return fail(XRSD_EINVAL, "mode=%d", mode);
+  const bool reduce = mode != XRSD_JAC_PATTERNS_ONLY;
+  if (!obj || !d_q || !d_params || !free_idx || !d_workspace || (reduce && (!d_Iobs || !d_JTJ || !d_JTr || !d_chi2)))
     return fail(XRSD_EINVAL, "NULL pointer");
   if (n_free < 1 || n_free > XRSD_MAX_FREE) return fail(XRSD_EINVAL, "n_free=%d (max %d)", n_free, XRSD_MAX_FREE);
   for (int i = 0; i < n_free; ++i)
     if (free_idx[i] < 0 || free_idx[i] >= layout->n_params) return fail(XRSD_EINVAL, "free_idx[%d]=%d", i, free_idx[i]);
-  if (obj->has_dI && !d_dI) return fail(XRSD_EINVAL, "objective.has_dI set but d_dI is NULL");
-  if (ld_obs != 0 && ld_obs < n_q) return fail(XRSD_EINVAL, "ld_obs < n_q");
+  if (reduce && obj->has_dI && !d_dI) return fail(XRSD_EINVAL, "objective.has_dI set but d_dI is NULL");
+  if (reduce && ld_obs != 0 && ld_obs < n_q) return fail(XRSD_EINVAL, "ld_obs < n_q");
   if (!(rel_step > 0.0)) return fail(XRSD_EINVAL, "rel_step must be > 0");
   if (n_tie < 0 || n_tie > XRSD_MAX_TIES || (n_tie > 0 && !ties)) return fail(XRSD_EINVAL, "n_tie=%d (max %d)", n_tie, XRSD_MAX_TIES);
   for (int i = 0; i < 2 * n_tie; ++i)
@@ -341,7 +346,7 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   double *d_acc = (double *)((char *)d_workspace + fbytes);
   unsigned *d_tickets = (unsigned *)((char *)d_workspace + fbytes + abytes);
   cudaError_t e = xrsd_launch_jacobian(layout, obj, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables, d_Iobs,
-                                       obj->has_dI ? d_dI : nullptr, (long long)ld_obs, free_idx, n_free, ties, tie_coef, n_tie, rel_step, base_ready, d_JTJ,
+                                       obj->has_dI ? d_dI : nullptr, (long long)ld_obs, free_idx, n_free, ties, tie_coef, n_tie, rel_step, mode, d_JTJ,
                                        d_JTr, d_chi2, d_Fvar, d_acc, d_tickets, per, scratch, rm, d_active, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "jacobian_kernel");
   return XRSD_OK;
@@ -376,6 +381,20 @@ int xrsd_lm_update(double *d_params, int32_t ld_params, int32_t batch, const dou
   cudaError_t e = xrsd_launch_lm_update(d_params, ld_params, batch, d_trial, d_chi2, d_chi2_trial, d_lambda, d_active,
                                         d_n_accept, up, down, ftol, lambda_max, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "lm_update_kernel");
+  return XRSD_OK;
+}
+
+int xrsd_pattern_chi2_batch(const xrsd_objective_t *obj, const double *d_q, int32_t n_q, const double *d_I, int64_t ld_I,
+                            int32_t batch, const double *d_Iobs, const double *d_dI, int64_t ld_obs, double *d_chi2,
+                            const uint8_t *d_active, void *stream) {
+  if (batch <= 0 || n_q <= 0) return XRSD_OK;
+  if (!obj || !d_q || !d_I || !d_Iobs || !d_chi2) return fail(XRSD_EINVAL, "NULL pointer");
+  if (obj->has_dI && !d_dI) return fail(XRSD_EINVAL, "objective.has_dI set but d_dI is NULL");
+  if (ld_I < n_q) return fail(XRSD_EINVAL, "ld_I < n_q");
+  if (ld_obs != 0 && ld_obs < n_q) return fail(XRSD_EINVAL, "ld_obs < n_q");
+  cudaError_t e = xrsd_launch_pattern_chi2(obj, d_q, n_q, d_I, (long long)ld_I, batch, d_Iobs, obj->has_dI ? d_dI : nullptr,
+                                           (long long)ld_obs, d_chi2, d_active, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "pattern_chi2_kernel");
   return XRSD_OK;
 }
 

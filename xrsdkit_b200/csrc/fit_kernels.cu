@@ -480,6 +480,51 @@ __global__ void lm_update_kernel(double *__restrict__ params, int ldp, int batch
   }
 }
 
+// chi2[b] of patterns that are already in memory (I[b][ld_I]): the objective of residual_kernel without the
+// evaluation.  The resident LM loop uses it for the trial point, whose pattern the variants kernel has just left
+// in the second workspace.  One CTA per system; 2 (3 with dI) streams of 8 B per q-point and two logs.
+constexpr int CHI2_THREADS = 256;
+__global__ void __launch_bounds__(CHI2_THREADS)
+pattern_chi2_kernel(const xrsd_objective_t O, const double *__restrict__ q, int n_q, const double *__restrict__ I, long long ld_I,
+                    int batch, const double *__restrict__ Iobs, const double *__restrict__ dI, long long ld_obs,
+                    double *__restrict__ chi2, const uint8_t *__restrict__ active) {
+  __shared__ double red[2][CHI2_THREADS / 32];
+  const int b = blockIdx.x;
+  if (b >= batch) return;
+  if (active != nullptr && !active[b]) return;
+  const double *pat = I + (size_t)b * ld_I;
+  const double *obs = Iobs + (size_t)b * ld_obs;
+  const double *err = dI ? dI + (size_t)b * ld_obs : nullptr;
+  double num = 0.0, den = 0.0;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n_q; i += CHI2_THREADS) {
+    const double Io = obs[i], Ic = pat[i];
+    double w;
+    bool fit = fit_weight(O, q[i], Io, err, i, w);
+    double d;
+    if (O.logI_weighted) {
+      fit = fit && (Ic > 0.0);
+      d = fit ? (log(Ic) - log(Io)) : 0.0;
+    } else {
+      d = Ic - Io;
+    }
+    if (fit) { num += (d * d) * w; den += w; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    num += __shfl_xor_sync(0xffffffffu, num, o);
+    den += __shfl_xor_sync(0xffffffffu, den, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = num; red[1][threadIdx.x >> 5] = den; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double n_ = 0.0, d_ = 0.0;
+#pragma unroll
+    for (int w = 0; w < CHI2_THREADS / 32; ++w) { n_ += red[0][w]; d_ += red[1][w]; }
+    chi2[b] = n_ / d_;
+  }
+}
+
 // Rows of `src` flagged in `mask` replace the same rows of `dst` (row r starts at r*stride; `row_len` doubles are
 // copied).  The LM loop uses it for accepted steps: the trial pattern and its running totals become the base rows
 // of the resident Jacobian workspace.  Unflagged rows cost one byte read; flagged ones stream at HBM/L2 speed
@@ -570,9 +615,11 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
   const long long n_blocks = (long long)batch * F.n_var * n_tiles;
   if (n_blocks > 2147483647LL) return cudaErrorInvalidConfiguration;
   kern<<<(unsigned)n_blocks, EVAL_THREADS, smem, stream>>>(*layout, d_q, n_q, d_params, ldp, batch, *tables, F, rel_step, d_Fvar,
-                                                          q_per_cta, n_tiles, pat, scratch_doubles, d_active, base_ready);
+                                                          q_per_cta, n_tiles, pat, scratch_doubles, d_active,
+                                                          base_ready == XRSD_JAC_BASE_READY);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if (base_ready == XRSD_JAC_PATTERNS_ONLY) return cudaSuccess;     // the caller only wants the slabs
   // q-chunk per reduction CTA: every CTA pays a prologue and a 74-value fold, so chunks are as long as the grid
   // allows -- whole patterns once the batch alone fills the GPU (2 CTAs/SM by registers), 1024 points for small batches
   int chunks_per_sys = (int)((4LL * 148 * 2 + batch - 1) / batch);
@@ -627,5 +674,14 @@ extern "C" cudaError_t xrsd_launch_copy_rows_masked(double *d_dst, long long dst
   if (row_len > 2147483647LL || chunks * n_rows > 2147483647LL) return cudaErrorInvalidConfiguration;
   xrsd::copy_rows_masked_kernel<<<(unsigned)(chunks * n_rows), xrsd::COPY_THREADS, 0, stream>>>(
       d_dst, dst_stride, d_src, src_stride, (int)row_len, (int)chunks, d_mask);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t xrsd_launch_pattern_chi2(const xrsd_objective_t *obj, const double *d_q, int n_q, const double *d_I,
+                                                long long ld_I, int batch, const double *d_Iobs, const double *d_dI,
+                                                long long ld_obs, double *d_chi2, const uint8_t *d_active, cudaStream_t stream) {
+  if (batch <= 0) return cudaSuccess;
+  xrsd::pattern_chi2_kernel<<<batch, xrsd::CHI2_THREADS, 0, stream>>>(*obj, d_q, n_q, d_I, ld_I, batch, d_Iobs, d_dI, ld_obs,
+                                                                      d_chi2, d_active);
   return cudaGetLastError();
 }

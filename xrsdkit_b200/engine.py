@@ -289,17 +289,22 @@ class Engine(object):
         return (C.c_int32 * len(flat))(*flat), (C.c_double * len(coef))(*coef), len(ties)
 
     def jacobian(self, layout, obj, q, d_params, Iobs_dev, dI_dev, ld_obs, free_slots, tables, rel_step=1e-6, out=None,
-                 active=None, ties=None, resident=None, base_ready=False):
+                 active=None, ties=None, resident=None, base_ready=False, patterns_only=False):
         """Normal equations (JTJ, JTr, chi2) of the weighted residual vector by forward differences.
 
         By default the variant patterns go through a shared scratch, the batch cut into chunks of <= 4 GB.  With
         `resident` (a key) the whole batch gets its own workspace that survives between calls, so the caller can
         read the pattern slabs (`jacobian_slabs`) and, with base_ready=True, have the call trust the base pattern
         and running totals already in it (the LM loop copies an accepted trial evaluation there instead of
-        evaluating the base again)."""
+        evaluating the base again).  patterns_only=True stops after the pattern slabs (no reduction, nothing is
+        written to `out`; Iobs_dev may be None): with one linear free parameter that is the pattern and the running
+        totals of every active system."""
         torch = self.torch
         batch, nf = d_params.shape[0], len(free_slots)
-        if out is None:
+        if patterns_only and (resident is None or base_ready):
+            raise ValueError("patterns_only needs a resident workspace (and excludes base_ready)")
+        mode = abi.JAC_PATTERNS_ONLY if patterns_only else (abi.JAC_BASE_READY if base_ready else abi.JAC_FULL)
+        if out is None and not patterns_only:
             out = (torch.empty((batch, nf, nf), dtype=torch.float64, device=self.device),
                    torch.empty((batch, nf), dtype=torch.float64, device=self.device),
                    torch.empty(batch, dtype=torch.float64, device=self.device))
@@ -350,11 +355,27 @@ class Engine(object):
             abi.check(self.lib.xrsd_jacobian_batch(
                 C.byref(layout.c), C.byref(obj), q.data_ptr(), n_q, d_params[lo:hi].data_ptr(), d_params.shape[1], hi - lo,
                 C.byref(tc) if tc is not None else None,
-                Iobs_dev.data_ptr() + 8 * lo * ld_obs, (dI_dev.data_ptr() + 8 * lo * ld_obs) if dI_dev is not None else None,
-                ld_obs, idx, nf, tie_c, coef_c, n_tie, float(rel_step), int(bool(base_ready)),
-                out[0][lo:hi].data_ptr(), out[1][lo:hi].data_ptr(), out[2][lo:hi].data_ptr(),
+                (Iobs_dev.data_ptr() + 8 * lo * ld_obs) if Iobs_dev is not None else None,
+                (dI_dev.data_ptr() + 8 * lo * ld_obs) if dI_dev is not None else None,
+                ld_obs, idx, nf, tie_c, coef_c, n_tie, float(rel_step), mode,
+                *([None, None, None] if patterns_only else [out[0][lo:hi].data_ptr(), out[1][lo:hi].data_ptr(), out[2][lo:hi].data_ptr()]),
                 ws.data_ptr(), (active.data_ptr() + lo) if active is not None else None, self._stream()))
-            self.launches += 2
+            self.launches += 1 if patterns_only else 2
+        return out
+
+    def pattern_chi2(self, obj, q, patterns, Iobs_dev, dI_dev, ld_obs, out=None, active=None):
+        """chi2 of patterns that are already on the device: `patterns` is a [batch, n_q] float64 tensor whose rows may
+        be strided (e.g. slab 0 of jacobian_slabs())."""
+        batch, n_q = patterns.shape
+        if patterns.stride(1) != 1:
+            raise ValueError("pattern rows must be contiguous")
+        if out is None:
+            out = self.torch.empty(batch, dtype=self.torch.float64, device=self.device)
+        abi.check(self.lib.xrsd_pattern_chi2_batch(C.byref(obj), q.data_ptr(), n_q, patterns.data_ptr(), patterns.stride(0) if batch > 1 else n_q,
+                                                   batch, Iobs_dev.data_ptr(), dI_dev.data_ptr() if dI_dev is not None else None,
+                                                   ld_obs, out.data_ptr(), active.data_ptr() if active is not None else None,
+                                                   self._stream()))
+        self.launches += 1
         return out
 
     def jacobian_variants(self, layout, free_slots, ties=None):

@@ -42,7 +42,7 @@ def _apply_ties(params, ties):
 def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weighted=True, logI_weighted=True,
                  q_range=(0., float('inf')), max_iter=30, ftol=1e-8, lambda0=1e-2, up=8.0, down=4.0,
                  lambda_max=1e10, rel_step=1e-6, lo=None, hi=None, eng=None, return_device=False, ties=None,
-                 resident_limit=24e9, min_group_rows=2048):
+                 resident_limit=24e9, min_group_rows=2048, table_growth=1.09, loop_cells=None):
     """Fit every row of params0 ([batch, n_params]) to the matching row of Iobs ([batch, n_q] or [n_q]).
 
     When the pattern slabs of the batch fit in `resident_limit` bytes, the loop keeps them on the device
@@ -52,6 +52,10 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     row groups that fit (systems are independent; a group of `min_group_rows` systems or more still fills the
     GPU many times over); if even such a group does not fit, or no free parameter is linear, the loop
     re-evaluates the base inside every Jacobian (shared 4 GB scratch).
+
+    Crystalline layouts: the reflection tables of the trial points are built with the candidate box of the current
+    parameters grown by `table_growth` (see the comment at `near_cells` below; `loop_cells` sets the first box
+    explicitly); lattice steps beyond it are turned back and the box follows the accepted parameters.
 
     Returns a FitResult of device tensors (return_device=True) or numpy arrays."""
     eng = eng or _engine.get_engine()
@@ -92,7 +96,8 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
                                   max_iter=max_iter, ftol=ftol, lambda0=lambda0, up=up, down=down, lambda_max=lambda_max,
                                   rel_step=rel_step, lo=rows_of(lo, a, min(a + step, n_rows)),
                                   hi=rows_of(hi, a, min(a + step, n_rows)), eng=eng, return_device=return_device, ties=ties,
-                                  resident_limit=resident_limit, min_group_rows=min_group_rows)
+                                  resident_limit=resident_limit, min_group_rows=min_group_rows, table_growth=table_growth,
+                                  loop_cells=loop_cells)
                      for a in range(0, n_rows, step)]
             cat = torch.cat if return_device else np.concatenate
             return FitResult(cat([r.params for r in parts]), cat([r.chi2_init for r in parts]), cat([r.chi2 for r in parts]),
@@ -132,6 +137,20 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
             grown[:, s] = np.where(np.isfinite(bhi[j]), np.minimum(bhi[j], 1.5 * np.abs(hp[:, s])), 1.5 * np.abs(hp[:, s]))
         max_cells = max(lowering.max_cells(layout, hp), lowering.max_cells(layout, grown))
         max_cells = min(max_cells, 90000)
+        # The table kernel's shared memory (2 B per candidate cell) sets its occupancy: sized for 1.5x growth it runs
+        # one CTA per SM, twice as slow as with the box the systems actually need.  In-loop builds therefore use the
+        # box of the current parameters grown by `table_growth`; a trial step that does not fit is turned back like
+        # any bad step (chi2 = inf: lambda grows, the next step is shorter), and when that has happened to an active
+        # system the periodic flag read below re-centres the box on the parameters accepted so far, so a lattice
+        # that really has to grow by more than that does so in stages.
+
+        def near_cells(now):
+            near = now.copy()
+            for j, s in enumerate(free_slots):
+                near[:, s] = np.minimum(grown[:, s], float(table_growth) * np.abs(now[:, s]))
+            return min(max_cells, max(lowering.max_cells(layout, now), lowering.max_cells(layout, near)))
+
+        loop_cells = near_cells(hp) if loop_cells is None else min(max_cells, int(loop_cells))
     tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells) if layout.n_xtal else None
     chi2_init = None
     t_tables = None
@@ -142,10 +161,8 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     persist = lin_slot is not None and resident_bytes(batch) <= resident_limit
     key0, key1 = ("lm", id(d_p), 0), ("lm", id(d_p), 1)
     base_valid = False
-    jout_t = None
-    if persist:
-        jout_t = (torch.empty((batch, 1, 1), dtype=torch.float64, device=eng.device),
-                  torch.empty((batch, 1), dtype=torch.float64, device=eng.device), d_chi2_t)
+    tight = bool(layout.n_xtal) and loop_cells < max_cells
+    grid_seen = torch.zeros((), dtype=torch.int32, device=eng.device)
     for it in range(max_iter):
         n_iter = it + 1
         _, _, d_chi2 = eng.jacobian(layout, obj, d_q, d_p, d_I, d_dI, ld_obs, free_slots, tables, rel_step, out=jout,
@@ -158,16 +175,23 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
                                       d_lambda.data_ptr(), d_lo.data_ptr(), d_hi.data_ptr(), d_active.data_ptr(),
                                       d_trial.data_ptr(), stream))
         # in-loop table builds do not read their status back (no host sync); it is checked every 5 iterations
-        t_tables = eng.build_tables(layout, d_trial, batch, max_cells=max_cells, reuse=t_tables,
-                                    check=t_tables is None, active=d_active if t_tables is not None else None) if layout.n_xtal else None
-        if persist:     # pattern, running totals and chi2 of the trial point, kept in the second resident workspace
-            eng.jacobian(layout, obj, d_q, d_trial, d_I, d_dI, ld_obs, [lin_slot], t_tables, rel_step, out=jout_t,
-                         active=d_active, ties=ties, resident=key1)
+        first = t_tables is None       # (re)allocation: checked build with the full box, which also sizes the capacities
+        t_tables = eng.build_tables(layout, d_trial, batch, max_cells=max_cells if first or not tight else loop_cells,
+                                    reuse=t_tables, check=first, active=None if first else d_active) if layout.n_xtal else None
+        if persist:     # pattern and running totals of the trial point, kept in the second resident workspace; its chi2
+            eng.jacobian(layout, obj, d_q, d_trial, None, None, 0, [lin_slot], t_tables, rel_step,
+                         active=d_active, ties=ties, resident=key1, patterns_only=True)
+            eng.pattern_chi2(obj, d_q, eng.jacobian_slabs(key1, layout, batch, n_q, 1)[:, 0], d_I, d_dI, ld_obs,
+                             out=d_chi2_t, active=d_active)
         else:
             abi.check(lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_trial.data_ptr(),
                                               d_trial.shape[1], batch, C.byref(t_tables.c) if t_tables is not None else None,
                                               d_I.data_ptr(), d_dI.data_ptr() if d_dI is not None else None, ld_obs,
                                               d_chi2_t.data_ptr(), res_ws.data_ptr(), d_active.data_ptr(), stream))
+        if tight and not first:
+            over = ((t_tables.status.view(batch, layout.n_xtal) & abi.TABLE_GRID_OVERFLOW) != 0).any(dim=1) & d_active.bool()
+            d_chi2_t.masked_fill_(over, float('inf'))
+            grid_seen.add_(over.any().to(torch.int32))
         if layout.n_xtal or persist:
             nacc_before = d_nacc.clone()
         abi.check(lib.xrsd_lm_update(d_p.data_ptr(), d_p.shape[1], batch, d_trial.data_ptr(), d_chi2.data_ptr(),
@@ -184,10 +208,18 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
             if not tables.take_rows_from(t_tables, accepted):
                 tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=tables, check=False, active=d_active)
         if it % 5 == 4:
-            flags = torch.stack([d_active.any().to(torch.int32),
-                                 tables.status.max() if tables is not None else torch.zeros((), dtype=torch.int32, device=eng.device),
-                                 t_tables.status.max() if t_tables is not None else torch.zeros((), dtype=torch.int32, device=eng.device)])
-            any_active, st_a, st_b = [int(v) for v in flags.cpu().tolist()]      # the only host sync of the loop
+            zero = torch.zeros((), dtype=torch.int32, device=eng.device)
+            st_trial = zero if t_tables is None else \
+                ((t_tables.status & ~abi.TABLE_GRID_OVERFLOW) if tight else t_tables.status).max()
+            flags = torch.stack([d_active.any().to(torch.int32), tables.status.max() if tables is not None else zero,
+                                 st_trial, grid_seen])
+            any_active, st_a, st_b, outgrown = [int(v) for v in flags.cpu().tolist()]      # the only host sync of the loop
+            if tight and outgrown:
+                # an active system proposed a cell beyond the near box and was turned back: re-centre the box
+                loop_cells = near_cells(d_p.cpu().numpy())
+                tight = loop_cells < max_cells
+                grid_seen.zero_()
+                t_tables.status.bitwise_and_(~abi.TABLE_GRID_OVERFLOW)
             if st_a or st_b:
                 # a table outgrew its storage since the last check: rebuild both sets with the checked
                 # (self-growing) path and resynchronise chi2 with the accepted parameters
