@@ -253,7 +253,12 @@ int xrsd_copy_rows_masked(double *d_dst, int64_t dst_stride, const double *d_src
 
 /* Host-buffer convenience call (what a non-Python caller binds): allocates / reuses an
  * internal device workspace, copies q and params in, builds tables when the layout has
- * crystalline populations, computes, copies I back.  Blocking. */
+ * crystalline populations, computes, copies I back.  Blocking.  Small calls without crystalline
+ * populations make no copies at all: the kernel reads the parameters from and writes I(q) to mapped
+ * pinned memory.
+ * Threading: the d_* entry points above keep no state between calls (xrsd_last_error is per thread)
+ * and may be called concurrently on different streams; this call and xrsd_release_workspace share one
+ * process-wide workspace on the current device and serialise on a mutex. */
 int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int32_t n_q,
                               const double *params, int32_t ld_params, int32_t batch,
                               double *I_out, int64_t ld_I);

@@ -288,6 +288,46 @@ def test_host_buffer_c_abi_entry_point(eng, golden_systems):
     lib.xrsd_release_workspace()
 
 
+def test_host_buffer_entry_point_from_several_threads(eng):
+    """The host-buffer call shares one process-wide workspace: concurrent callers (ctypes drops the GIL) serialise
+    on its mutex and every caller gets its own result -- small calls (mapped pinned memory, no copies), larger
+    ones (staged copies) and crystalline layouts mixed."""
+    import ctypes as C
+    import threading
+    from xrsdkit_b200 import abi, batch
+    from xrsdkit_b200.system import System
+    lib = abi.load()
+    jobs = []
+    for k, (make, pars, n, n_q) in enumerate(((cfg2_system, cfg2_params, 3, 900), (cfg2_system, cfg2_params, 200, 2048),
+                                               (cfg4_system, cfg4_params, 4, 1500), (cfg2_system, cfg2_params, 1, 4096))):
+        s = make(System)
+        q = np.linspace(0.01, 0.5 + 0.1 * k, n_q)
+        lay = batch.layout_of(s, q)
+        P = np.ascontiguousarray(pars(lay, n, seed=80 + k))
+        jobs.append((lay, q, P, batch.compute_intensity_batch(lay, q, P)))
+    errors = []
+
+    def work(lay, q, P, want):
+        try:
+            for _ in range(25):
+                out = np.empty((len(P), q.size))
+                rc = lib.xrsd_intensity_batch_host(C.byref(lay.c), q.ctypes.data_as(C.c_void_p), q.size,
+                                                   P.ctypes.data_as(C.c_void_p), P.shape[1], len(P),
+                                                   out.ctypes.data_as(C.c_void_p), q.size)
+                assert rc == 0, lib.xrsd_last_error()
+                np.testing.assert_array_equal(out, want)
+        except Exception as e:      # noqa: BLE001 -- reported in the main thread
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=j) for j in jobs for _ in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    lib.xrsd_release_workspace()
+
+
 def test_mixed_layout_collection_in_batches(eng, golden_systems):
     """All fixture systems evaluated through the layout-grouping loader: one launch per distinct layout."""
     from xrsdkit_b200.system import System

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <mutex>
 #include <vector>
 #include "../../include/xrsd_b200.h"
 
@@ -477,6 +478,7 @@ struct Workspace {
   std::vector<double> q_host;     // the grid currently resident at offset 0 of the workspace (skips its upload)
   bool q_valid = false;
 } g_ws;
+std::mutex g_ws_mutex;      // the host-buffer call and the release serialise on the one workspace
 
 int ws_reserve(size_t bytes) {
   if (bytes <= g_ws.bytes) return XRSD_OK;
@@ -532,6 +534,7 @@ double xrsd_uniform_step(const double *q, int32_t n) {
 }
 
 void xrsd_release_workspace(void) {
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
   g_ws.q_valid = false;
   if (g_ws.pinned) cudaFreeHost(g_ws.pinned);
   g_ws.pinned = nullptr;
@@ -549,6 +552,7 @@ int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int3
   if (batch <= 0 || n_q <= 0) return XRSD_OK;
   if (!q || !params || !I_out) return fail(XRSD_EINVAL, "NULL host pointer");
   if (ld_I < n_q) return fail(XRSD_EINVAL, "ld_I < n_q");
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
   const int n_x = layout->n_xtal;
   const size_t n_tab = (size_t)batch * n_x;
   const int cap_shell = 1024, n_pairs = XRSD_MAX_PAIRS;
