@@ -2,7 +2,6 @@
 import os
 import socket
 
-import numpy as np
 import pytest
 import torch
 import torch.distributed as dist

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from helpers import rel_err, cfg2_system, cfg2_params, cfg4_system, cfg4_params, params_to_sysdict
+from helpers import cfg2_system, cfg2_params, cfg4_system, cfg4_params, params_to_sysdict
 
 pytestmark = pytest.mark.gpu
 

@@ -10,8 +10,6 @@ contiguous slice (shard_bounds) and the results meet in one all_gather at the en
 """
 import os
 
-import numpy as np
-
 from . import engine as _engine, fitting, lowering
 
 

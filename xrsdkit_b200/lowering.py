@@ -9,7 +9,6 @@ The slot order is the reference's flatten_params() order (system/__init__.py:211
 noise parameters first, then each population's parameters in dict order, keyed
 '<population>__<parameter>'.
 """
-import ctypes as C
 
 import numpy as np
 

@@ -4,7 +4,6 @@ save_sys_to_yaml / load_sys_from_yaml keep the reference's file format
 (tools/ymltools.py:18-26: a plain `yaml.dump(System.to_dict())`), so files written by xrsdkit load here
 unchanged and vice versa.  load_batches() groups systems that share a layout (same populations,
 settings and noise model) so that each group is evaluated in one launch."""
-import os
 from collections import OrderedDict
 
 import numpy as np
