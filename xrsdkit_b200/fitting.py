@@ -160,6 +160,9 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     n_var = eng.jacobian_variants(layout, free_slots, ties)
     persist = lin_slot is not None and resident_bytes(batch) <= resident_limit
     key0, key1 = ("lm", id(d_p), 0), ("lm", id(d_p), 1)
+    # fits on one engine run one after the other: a workspace still registered here was left behind by a fit that
+    # ended in an exception
+    eng.release_resident(*[k for k in getattr(eng, "_jac_resident", {}) if isinstance(k, tuple) and k and k[0] == "lm"])
     base_valid = False
     tight = bool(layout.n_xtal) and loop_cells < max_cells
     grid_seen = torch.zeros((), dtype=torch.int32, device=eng.device)
