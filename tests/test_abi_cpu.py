@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import numpy as np
+
 from xrsdkit_b200 import abi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -41,3 +43,42 @@ def test_argument_errors_without_touching_the_gpu():
     assert rc == abi.EINVAL and b"n_pops" in lib.xrsd_last_error()
     rc = lib.xrsd_peak_profile(7, 1.0, 1.0, None, 0, None, None)
     assert rc == abi.EINVAL
+
+
+def test_uniform_step_host_helper_matches_its_numpy_statement():
+    """xrsd_uniform_step is plain host code (no device call): the C pass and the numpy statement in
+    lowering.uniform_step agree on linspace grids and on everything that is not one."""
+    import ctypes as C
+    from xrsdkit_b200 import abi, lowering
+    lib = abi.load()
+
+    def numpy_statement(q):
+        n = len(q)
+        if n < 3:
+            return 0.0
+        step = (q[-1] - q[0]) / (n - 1)
+        if not (step > 0):
+            return 0.0
+        tol = 4 * np.finfo(float).eps * max(abs(q[0]), abs(q[-1]))
+        ok = np.max(np.abs(q - (q[0] + np.arange(n) * step))) <= tol and np.all(np.diff(q) > 0)
+        return float(step) if ok else 0.0
+
+    rs = np.random.RandomState(0)
+    grids = [np.linspace(0.001, 0.5, 2000), np.linspace(0.0, 1.0, 8192), np.linspace(0.01, 1.0, 3), np.linspace(0, 1, 2),
+             np.logspace(-3, 0, 500), np.linspace(1.0, 0.0, 100), np.arange(0.0, 0.5, 0.001), np.sort(rs.rand(300)),
+             np.full(10, 0.3)]
+    bumped = np.linspace(0.01, 0.5, 1001)
+    bumped[777] += 1e-9
+    with_nan = np.linspace(0.01, 0.5, 1001)
+    with_nan[3] = np.nan
+    grids += [bumped, with_nan]
+    for q in grids:
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        want = numpy_statement(q)
+        got_c = float(lib.xrsd_uniform_step(q.ctypes.data_as(C.c_void_p), len(q)))
+        assert got_c == want, (len(q), got_c, want)
+        assert lowering.uniform_step(q) == want
+        ro = q.copy()
+        ro.flags.writeable = False                 # abi.ptr falls back to ndarray.ctypes for read-only buffers
+        assert lowering.uniform_step(ro) == want
+    assert numpy_statement(grids[0]) > 0 and numpy_statement(grids[4]) == 0.0

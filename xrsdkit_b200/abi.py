@@ -119,6 +119,15 @@ def load():
     return lib
 
 
+def ptr(a):
+    """Address of the data of a C-contiguous numpy array -- a quarter of the cost of ndarray.ctypes.data, which
+    matters on the single-pattern path (four arrays per call)."""
+    try:
+        return C.addressof(C.c_char.from_buffer(a))
+    except (TypeError, ValueError, BufferError):      # read-only or empty buffers
+        return a.ctypes.data
+
+
 class XrsdError(RuntimeError):
     pass
 

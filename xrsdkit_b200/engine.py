@@ -206,8 +206,8 @@ class Engine(object):
         vals = np.ascontiguousarray(layout.values, dtype=np.float64)
         out = np.empty(q.size)
         self.torch.cuda.set_device(self.device)
-        rc = self.lib.xrsd_intensity_batch_host(C.byref(layout.c), q.ctypes.data, q.size, vals.ctypes.data, vals.size, 1,
-                                                out.ctypes.data, q.size)
+        rc = self.lib.xrsd_intensity_batch_host(C.byref(layout.c), abi.ptr(q), q.size, abi.ptr(vals), vals.size, 1,
+                                                abi.ptr(out), q.size)
         if rc == abi.ECAPACITY and layout.n_xtal:
             # the host path's fixed table capacities were exceeded (very many shells): the device API grows them
             return self.intensity(layout, q, vals[None, :])[0].cpu().numpy()
