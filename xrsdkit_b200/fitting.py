@@ -12,7 +12,9 @@ LM linearises.  One iteration for the whole batch is five launches:
 
 No host synchronisation is needed inside the loop except the reflection-table capacity check.
 With a linear free parameter (an I0) the loop keeps the base pattern on the device between iterations
-(see lm_fit_batch): the trial evaluation is then a one-variant Jacobian launch instead of the residual kernel.
+(see lm_fit_batch): the trial evaluation is then a patterns-only variants launch plus the chi2 of the stored
+pattern (xrsd_pattern_chi2_batch) instead of the residual kernel, accepted rows move into the base workspace
+(xrsd_copy_rows_masked) and the next Jacobian evaluates the perturbed variants only.
 """
 import ctypes as C
 import os
