@@ -43,6 +43,31 @@ def test_argument_errors_without_touching_the_gpu():
     assert rc == abi.EINVAL and b"n_pops" in lib.xrsd_last_error()
     rc = lib.xrsd_peak_profile(7, 1.0, 1.0, None, 0, None, None)
     assert rc == abi.EINVAL
+    # entry points of the fit loop: every one of these is refused on the host, before any CUDA call
+    assert lib.xrsd_copy_rows_masked(None, 8, None, 8, 8, 4, None, None) == abi.EINVAL          # NULL pointers
+    assert lib.xrsd_copy_rows_masked(1 << 20, 4, 1 << 21, 8, 8, 4, 1 << 22, None) == abi.EINVAL    # rows would overlap
+    assert b"dst_stride" in lib.xrsd_last_error()
+    assert lib.xrsd_copy_rows_masked(None, 0, None, 0, 0, 0, None, None) == abi.OK                 # nothing to do
+    assert lib.xrsd_copy_rows_masked(None, 0, None, 0, 8, -1, None, None) == abi.EINVAL
+    O = abi.Objective()
+    assert lib.xrsd_pattern_chi2_batch(ctypes.byref(O), None, 16, None, 16, 2, None, None, 16, None, None, None) == abi.EINVAL
+    assert lib.xrsd_pattern_chi2_batch(ctypes.byref(O), 1 << 20, 16, 1 << 21, 8, 2, 1 << 22, None, 16, 1 << 23, None, None) == abi.EINVAL
+    assert b"ld_I" in lib.xrsd_last_error()
+    assert lib.xrsd_pattern_chi2_batch(ctypes.byref(O), None, 16, None, 16, 0, None, None, 16, None, None, None) == abi.OK
+    from helpers import cfg2_system
+    from xrsdkit_b200 import lowering
+    from xrsdkit_b200.system import System
+    q = np.linspace(0.01, 0.5, 64)
+    lay = lowering.lower_system(cfg2_system(System), q)
+    free = (ctypes.c_int32 * 2)(lay.slot("p__I0"), lay.slot("p__r"))
+    assert lib.xrsd_jacobian_n_variants(ctypes.byref(lay.c), free, 2, None, 0) == 2                # base + r; I0 is linear
+    assert lib.xrsd_jacobian_n_variants(ctypes.byref(lay.c), free, 0, None, 0) == -1
+    rc = lib.xrsd_jacobian_batch(ctypes.byref(lay.c), ctypes.byref(O), 1 << 20, 64, 1 << 21, lay.c.n_params, 3, None,
+                                 None, None, 0, free, 2, None, None, 0, 1e-6, 7, None, None, None, 1 << 22, None, None)
+    assert rc == abi.EINVAL and b"mode" in lib.xrsd_last_error()
+    rc = lib.xrsd_jacobian_batch(ctypes.byref(lay.c), ctypes.byref(O), 1 << 20, 64, 1 << 21, lay.c.n_params, 3, None,
+                                 None, None, 0, free, 2, None, None, 0, 1e-6, abi.JAC_FULL, None, None, None, 1 << 22, None, None)
+    assert rc == abi.EINVAL and b"NULL" in lib.xrsd_last_error()                                  # full mode needs I_obs and outputs
 
 
 def test_uniform_step_host_helper_matches_its_numpy_statement():
