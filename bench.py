@@ -505,7 +505,7 @@ def run_gpu_arm(args):
     secondary = None
     if args.workload == "cfg2" and world == 1 and not args.no_secondary:
         secondary = {}
-        for name, b2, st in (("cfg3", 2000, 5), ("cfg4", 1000, 3), ("cfg5", 512, 1)):
+        for name, b2, st in (("cfg3", 2000, 5), ("cfg4", 1000, 3), ("cfg5", 2048, 1)):
             try:
                 w2 = Work(eng, name, b2, 2000, args.lm_iters)
                 ms2, _ = w2.timed(st, 2)
