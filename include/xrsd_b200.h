@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define XRSD_ABI_VERSION 3
+#define XRSD_ABI_VERSION 4
 
 #define XRSD_MAX_POPS 6      /* noise model + up to 5 populations per system layout   */
 #define XRSD_MAX_SPECIES 4   /* species (atoms) per crystalline population             */
@@ -111,25 +111,49 @@ typedef struct xrsd_layout {
   xrsd_pop_t pops[XRSD_MAX_POPS];
 } xrsd_layout_t;
 
-/* Reflection-table storage for `n_tables` = batch * layout.n_xtal tables, table index
- * t = b * n_xtal + slot.  All arrays are device memory owned by the caller. */
+/* Reflection-table storage.  A batch has n_tables = batch * layout.n_xtal tables, table index
+ * t = b * n_xtal + slot; table t lives in storage ROW table_of[t] of the arrays below (row = own_base + t when
+ * table_of is NULL).  All arrays are device memory owned by the caller.
+ *
+ * Shared rows.  For a cubic cell without free atomic coordinates everything in a table -- the reduced hkl list,
+ * the multiplicities, the shells and their geometric weights -- depends on the cell edge only through WHICH
+ * integer shells N = h^2+k^2+l^2 pass the reference's  G_min < |G| <= G_max  test (scattering/__init__.py:276),
+ * so systems that agree on that set share one table: with n_shared > 0 the builder first derives each system's
+ * key (the largest passing N, decided with a 1e-13 guard band around the float comparison; undecidable, keyed
+ * beyond n_shared, or non-cubic systems keep their own row), claims row shared_base + key through shared_tag
+ * (0 = never built) and builds every distinct table ONCE; the other systems only get the row index.  Rows
+ * already built stay valid between calls as long as shared_tag is not cleared (the fit loop keeps them for the
+ * whole fit).  Several table sets (e.g. the accepted and the trial point of a fit) may be views of the same
+ * arrays with different own_base / table_of. */
 typedef struct xrsd_tables {
   int32_t cap_shell;           /* shells per table the arrays below can hold            */
   int32_t cap_refl;            /* reduced reflections per table (0: do not export)      */
   int32_t n_pairs_max;         /* leading dimension of shell_geo (<= XRSD_MAX_PAIRS)    */
   int32_t cap_list_hint;       /* reduced reflections the builder keeps in shared memory (0 = auto: 1024 or
                                   4096; XRSD_TABLE_LIST_OVERFLOW asks for a retry with a larger value) */
-  int32_t *n_shell;            /* [n_tables]                                             */
-  int32_t *n_refl;             /* [n_tables] reduced reflections (before shell merging)  */
-  int32_t *n_all;              /* [n_tables] reflections in the G_min..G_max shell       */
-  int32_t *status;             /* [n_tables] XRSD_TABLE_* bits                           */
-  int32_t *shell_hkl;          /* [n_tables][cap_shell][4]: representative h,k,l, sum of multiplicities */
-  double *shell_geo;           /* [n_tables][cap_shell][n_pairs_max]: sum mult*Re(G_a conj G_b)          */
-  int32_t *refl_hkl;           /* [n_tables][cap_refl][4]: h,k,l,mult in reference order (optional)       */
+  int32_t *n_shell;            /* [n_rows]                                               */
+  int32_t *n_refl;             /* [n_rows] reduced reflections (before shell merging)    */
+  int32_t *n_all;              /* [n_rows] reflections in the G_min..G_max shell         */
+  int32_t *status;             /* [n_rows] XRSD_TABLE_* bits                             */
+  int32_t *shell_hkl;          /* [n_rows][cap_shell][4]: representative h,k,l, sum of multiplicities */
+  double *shell_geo;           /* [n_rows][cap_shell][n_pairs_max]: sum mult*Re(G_a conj G_b)          */
+  int32_t *refl_hkl;           /* [n_rows][cap_refl][4]: h,k,l,mult in reference order (optional)       */
   void *big_scratch;           /* optional: [n_tables] regions of xrsd_table_scratch_bytes(cap_big) bytes in global
                                   memory, used by a table whose reduced list exceeds the shared-memory capacity
                                   (large cells without usable symmetry); cap_big is a power of two              */
   int64_t cap_big;
+  int32_t *table_of;           /* [n_tables] storage row of each table, written by the builder; NULL: row = own_base + t */
+  uint8_t *build_flag;         /* [n_tables] builder scratch (1 = this call builds the table's row); needed with table_of */
+  int32_t own_base;            /* first of this set's own rows */
+  int32_t shared_base;         /* first shared row */
+  int32_t n_shared;            /* shared rows (0: nothing is shared) */
+  int32_t n_grid_slots;        /* regions in grid_scratch */
+  int32_t *shared_tag;         /* [n_shared] 0 = row not built; else 1 + the G_min key it was built for */
+  void *grid_scratch;          /* optional: n_grid_slots regions of 2*cap_grid_cells bytes (global memory) for candidate
+                                  boxes beyond the shared-memory budget (`max_cells` of xrsd_reflection_tables); a table
+                                  that finds neither room is flagged XRSD_TABLE_GRID_OVERFLOW */
+  int64_t cap_grid_cells;
+  int32_t *grid_slot_counter;  /* one device int (set to zero by the call) handing out the regions */
 } xrsd_tables_t;
 
 /* objective flags of xrsd_residual_batch (System.fit_report, system/__init__.py:23-28) */
@@ -137,7 +161,8 @@ typedef struct xrsd_objective {
   int32_t error_weighted;
   int32_t logI_weighted;
   int32_t has_dI;              /* 0: dI defaults to sqrt(I) on the fit mask (system/__init__.py:168-171) */
-  int32_t reserved0;
+  int32_t prepared;            /* 1: the d_Iobs / d_dI arguments are the streams written by xrsd_objective_prepare
+                                  (f(I_obs) and the point weights, -1 on masked points) instead of raw I_obs / dI */
   double q_lo, q_hi;           /* q_range */
 } xrsd_objective_t;
 
@@ -190,7 +215,8 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
 
 /* Forward-difference Jacobian of the weighted residual vector, reduced in-kernel to the
  * normal equations: JTJ[b][n_free][n_free], JTr[b][n_free], chi2[b].  free_idx[n_free] (HOST
- * array) are parameter slots; rel_step is the relative step (absolute for zero-valued
+ * array) are parameter slots (an entry -(slot+1) forces a finite-difference variant for an I0, whose derivative is
+ * otherwise taken from the population's own pattern: needed where a system sits at I0 == 0); rel_step is the relative step (absolute for zero-valued
  * parameters).  Two launches: variants (grid = batch x evaluated variants x q-spans; an I0 is
  * linear and needs no variant) and a chunked reduction.  d_workspace holds
  * xrsd_jacobian_workspace_bytes() bytes; the accumulator / ticket area behind the variant slabs
@@ -226,18 +252,49 @@ int32_t xrsd_jacobian_n_variants(const xrsd_layout_t *layout, const int32_t *fre
                                  const int32_t *ties, int32_t n_tie);
 
 /* One damped Gauss-Newton (Levenberg-Marquardt) proposal per system:
- * solve (JTJ + lambda*diag(JTJ)) delta = -JTr, project onto [lo, hi], write trial params. */
+ * solve (JTJ + lambda*diag(JTJ)) delta = -JTr, limit every component to max_rel_step * |parameter| (a relative
+ * trust region; 0 = no limit), project onto [lo, hi], write trial params. */
 int xrsd_lm_propose(const double *d_params, int32_t ld_params, int32_t batch,
                     const int32_t *free_idx, int32_t n_free, const int32_t *ties, const double *tie_coef,
                     int32_t n_tie, const double *d_JTJ, const double *d_JTr, const double *d_lambda,
                     const double *d_lo, const double *d_hi, const uint8_t *d_active,
-                    double *d_trial, void *stream);
+                    double *d_trial, double max_rel_step, void *stream);
 /* Accept/reject: where chi2_trial < chi2 copy trial -> params, lambda /= down, else lambda *= up;
  * clears `active` for systems whose relative improvement fell below ftol or that hit lambda_max. */
 int xrsd_lm_update(double *d_params, int32_t ld_params, int32_t batch,
                    const double *d_trial, double *d_chi2, const double *d_chi2_trial,
                    double *d_lambda, uint8_t *d_active, int32_t *d_n_accept,
                    double up, double down, double ftol, double lambda_max, void *stream);
+
+/* Once per fit: d_fo[r][i] = f(I_obs) (log in log mode) and d_w[r][i] = the point's weight of the reference's objective
+ * (system/__init__.py:164-172), -1 where the point is outside the fit mask (I_obs <= 0 or q outside q_range), for
+ * r < rows (rows = 1 for one shared pattern).  A copy of `obj` with prepared = 1 then makes xrsd_residual_batch,
+ * xrsd_jacobian_batch, xrsd_pattern_chi2_batch and xrsd_lm_trial_update read these two streams in place of d_Iobs /
+ * d_dI (same leading dimension for both), which saves a logarithm, a square root and the mask tests per point and call. */
+int xrsd_objective_prepare(const xrsd_objective_t *obj, const double *d_q, int32_t n_q, const double *d_Iobs, const double *d_dI,
+                           int64_t ld_obs, int32_t rows, double *d_fo, double *d_w, int64_t ld_out, void *stream);
+
+/* One launch for the trial point of an LM iteration: chi2_trial[b] of the stored trial patterns d_I[batch][ld_I] (NULL:
+ * take the values already in d_chi2_trial), then accept / reject per system -- where chi2_trial < chi2 the trial row
+ * replaces the parameter row, chi2 and lambda /= down, else lambda *= up.  d_accepted[b] says which, d_needjac[b] which
+ * systems need a new Jacobian (accepted and still running), d_reason[b] why a system left the loop: 1 = converged
+ * (chi2 changed by <= ftol relative, or every parameter by <= xtol relative), 2 = lambda beyond lambda_max, 3 = objective
+ * not finite; d_active[b] is cleared with it.  A trial point whose reflection tables (trial_tables, optional) carry a
+ * non-zero status counts as chi2 = inf and ORs that status into d_flags[0] (optional). */
+int xrsd_lm_trial_update(const xrsd_objective_t *obj, const double *d_q, int32_t n_q, const double *d_I, int64_t ld_I,
+                         int32_t batch, const double *d_Iobs, const double *d_dI, int64_t ld_obs, double *d_params,
+                         int32_t ld_params, const double *d_trial, double *d_chi2, double *d_chi2_trial, double *d_lambda,
+                         uint8_t *d_active, uint8_t *d_accepted, uint8_t *d_needjac, uint8_t *d_reason, int32_t *d_n_accept,
+                         const xrsd_tables_t *trial_tables, int32_t n_xtal, int32_t *d_flags, double up, double down,
+                         double ftol, double xtol, double lambda_max, void *stream);
+
+/* Accepted systems (d_accepted[b] != 0) take over the trial evaluation: the 1 + n_pops slabs of the trial workspace
+ * (pattern, running totals; see xrsd_jacobian_n_variants) go to slab 0 and slabs n_var.. of the base workspace
+ * (d_dst / d_src may both be NULL), and the system's reflection tables become the trial tables -- a row index for
+ * shared tables, a row copy otherwise (tables / trial_tables may both be NULL; they must be views of equal capacity). */
+int xrsd_lm_accept(const uint8_t *d_accepted, int32_t batch, double *d_dst, int64_t dst_stride, const double *d_src,
+                   int64_t src_stride, int32_t n_q, int32_t n_var, int32_t n_pops, const xrsd_tables_t *tables,
+                   const xrsd_tables_t *trial_tables, int32_t n_xtal, void *stream);
 
 /* chi2[b] of System.evaluate_residual for patterns that are already in device memory: d_I[batch][ld_I] against
  * d_Iobs / d_dI [batch][ld_obs] (ld_obs == 0 broadcasts), same objective and masks as xrsd_residual_batch. */

@@ -1,9 +1,12 @@
 """TEST INFRASTRUCTURE ONLY -- import shim for the *unmodified* reference.
 
 Loads xrsdkit from /root/reference (read-only, exists only in the build container,
-never on the GPU box).  Used by oracle/make_golden.py to generate the committed
-fixtures under tests/golden/ and by tests/test_oracle_vs_reference.py (skipped when
-the tree is absent).  Nothing in the product package imports this.
+never on the GPU box) or from another root given by XRSD_REFERENCE_ROOT / load(root=...):
+__graft_entry__.build() copies the reference package, unmodified, to oracle/_ref/ (git-ignored,
+travels to the GPU box with the snapshot) so that bench.py's CPU arm can time the reference
+itself there.  Used by oracle/make_golden.py and oracle/make_workloads.py to generate the
+committed fixtures under tests/golden/, by tests/test_oracle_golden.py::test_oracle_equals_reference_*
+(skipped when no tree is present) and by oracle/cpu_arm.py.  Nothing in the product package imports this.
 
 Three blockers are patched, none of them on the numerical path:
   * xrsdkit/__init__.py:4 imports matplotlib        -> stub module
@@ -17,12 +20,15 @@ import types
 REFERENCE_ROOT = os.environ.get("XRSD_REFERENCE_ROOT", "/root/reference")
 
 
-def available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "xrsdkit"))
+def available(root=None):
+    return os.path.isdir(os.path.join(root or REFERENCE_ROOT, "xrsdkit"))
 
 
-def load():
+def load(root=None):
     """Return the imported reference package (raises ImportError when absent)."""
+    global REFERENCE_ROOT
+    if root is not None:
+        REFERENCE_ROOT = root
     if not available():
         raise ImportError("reference tree not present at %s" % REFERENCE_ROOT)
     if "xrsdkit" in sys.modules:

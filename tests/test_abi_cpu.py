@@ -31,7 +31,7 @@ def test_struct_mirror_matches_library():
     lib.xrsd_struct_sizes(*[ctypes.byref(s) for s in sizes])
     assert [s.value for s in sizes] == [ctypes.sizeof(abi.Pop), ctypes.sizeof(abi.Layout), ctypes.sizeof(abi.Tables),
                                         ctypes.sizeof(abi.Objective)]
-    assert lib.xrsd_abi_version() == 3
+    assert lib.xrsd_abi_version() == abi.ABI_VERSION == 4
     assert lib.xrsd_table_smem_bytes(10, 10, 10) > 2 * 19 ** 3
 
 
@@ -68,6 +68,44 @@ def test_argument_errors_without_touching_the_gpu():
     rc = lib.xrsd_jacobian_batch(ctypes.byref(lay.c), ctypes.byref(O), 1 << 20, 64, 1 << 21, lay.c.n_params, 3, None,
                                  None, None, 0, free, 2, None, None, 0, 1e-6, abi.JAC_FULL, None, None, None, 1 << 22, None, None)
     assert rc == abi.EINVAL and b"NULL" in lib.xrsd_last_error()                                  # full mode needs I_obs and outputs
+    # n_free == 0 ("pattern and running totals") is only legal without the reduction
+    rc = lib.xrsd_jacobian_batch(ctypes.byref(lay.c), ctypes.byref(O), 1 << 20, 64, 1 << 21, lay.c.n_params, 3, None,
+                                 1 << 23, None, 64, None, 0, None, None, 0, 1e-6, abi.JAC_FULL, 1 << 24, 1 << 25, 1 << 26, 1 << 22, None, None)
+    assert rc == abi.EINVAL and b"n_free" in lib.xrsd_last_error()
+    # a forced finite-difference variant: -(slot + 1)
+    forced = (ctypes.c_int32 * 2)(-(lay.slot("p__I0") + 1), lay.slot("p__r"))
+    assert lib.xrsd_jacobian_n_variants(ctypes.byref(lay.c), forced, 2, None, 0) == 3
+    # the fused loop kernels
+    assert lib.xrsd_objective_prepare(ctypes.byref(O), None, 16, None, None, 16, 2, None, None, 16, None) == abi.EINVAL
+    assert lib.xrsd_objective_prepare(ctypes.byref(O), 1 << 20, 16, 1 << 21, None, 8, 2, 1 << 22, 1 << 23, 16, None) == abi.EINVAL
+    assert b"leading dimension" in lib.xrsd_last_error()
+    assert lib.xrsd_objective_prepare(ctypes.byref(O), None, 16, None, None, 16, 0, None, None, 16, None) == abi.OK
+    Op = abi.Objective()
+    Op.prepared = 1
+    assert lib.xrsd_objective_prepare(ctypes.byref(Op), 1 << 20, 16, 1 << 21, None, 16, 2, 1 << 22, 1 << 23, 16, None) == abi.EINVAL
+    assert lib.xrsd_pattern_chi2_batch(ctypes.byref(Op), 1 << 20, 16, 1 << 21, 16, 2, 1 << 22, None, 16, 1 << 23, None, None) == abi.EINVAL
+    assert b"prepared" in lib.xrsd_last_error()                                                    # prepared needs the weight stream
+    args = [ctypes.byref(O), 1 << 20, 16, None, 0, 4, None, None, 0, 1 << 21, 6, 1 << 22, 1 << 23, 1 << 24, 1 << 25, 1 << 26,
+            1 << 27, 1 << 28, 1 << 29, 1 << 30, None, 0, None, 8.0, 4.0, 1e-8, 1e-10, 1e10, None]
+    bad = list(args)
+    bad[15] = None                                                                                 # d_active
+    assert lib.xrsd_lm_trial_update(*bad) == abi.EINVAL
+    bad = list(args)
+    bad[23] = 1.0                                                                                  # up must be > 1
+    assert lib.xrsd_lm_trial_update(*bad) == abi.EINVAL and b"up" in lib.xrsd_last_error()
+    bad = list(args)
+    bad[3], bad[4] = 1 << 19, 8                                                                    # a pattern, but ld_I < n_q and no I_obs
+    assert lib.xrsd_lm_trial_update(*bad) == abi.EINVAL
+    bad = list(args)
+    bad[5] = 0                                                                                     # nothing to do
+    assert lib.xrsd_lm_trial_update(*bad) == abi.OK
+    assert lib.xrsd_lm_accept(None, 4, None, 0, None, 0, 16, 2, 2, None, None, 0, None) == abi.EINVAL
+    assert lib.xrsd_lm_accept(1 << 20, 4, 1 << 21, 16, 1 << 22, 64, 16, 2, 2, None, None, 0, None) == abi.EINVAL
+    assert b"stride" in lib.xrsd_last_error()
+    assert lib.xrsd_lm_accept(1 << 20, 4, 1 << 21, 64, None, 64, 16, 2, 2, None, None, 0, None) == abi.EINVAL
+    assert lib.xrsd_lm_accept(1 << 20, 0, None, 0, None, 0, 16, 2, 2, None, None, 0, None) == abi.OK
+    rc = lib.xrsd_lm_propose(1 << 20, 6, 2, free, 2, None, None, 0, 1 << 21, 1 << 22, 1 << 23, 1 << 24, 1 << 25, None, 1 << 26, -1.0, None)
+    assert rc == abi.EINVAL and b"max_rel_step" in lib.xrsd_last_error()
 
 
 def test_uniform_step_host_helper_matches_its_numpy_statement():

@@ -1,0 +1,211 @@
+"""GPU tests of the fit loop's building blocks added in round 2: prepared objective streams, population-local
+Jacobian variants, the fused trial-update / accept kernels, stop reasons, and the corner cases the reference's
+objective defines (empty fit mask, parameters starting at zero)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import cfg2_system, cfg2_params, cfg4_system, cfg4_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from xrsdkit_b200 import engine
+    return engine.get_engine()
+
+
+@pytest.mark.parametrize("log_mode,err_mode,with_dI", [(True, True, False), (False, True, True), (True, False, False), (True, True, True)])
+def test_prepared_objective_equals_raw_objective(eng, log_mode, err_mode, with_dI):
+    """xrsd_objective_prepare + prepared = 1 gives the residual, the normal equations and the stored-pattern chi2 of the
+    raw objective (system/__init__.py:134-187): masks (I_obs <= 0, q_range), default dI = sqrt(I), given dI."""
+    import torch
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg2_system(System)
+    q = np.linspace(0.01, 0.5, 1100)
+    lay = batch.layout_of(s, q)
+    B = 7
+    P = cfg2_params(lay, B, seed=91)
+    rs = np.random.RandomState(5)
+    Iobs = batch.compute_intensity_batch(lay, q, P) * (1 + 0.05 * rs.randn(B, len(q)))
+    Iobs[:, 11] = 0.0
+    Iobs[3, 300:310] = -2.0
+    dI = (0.02 * np.abs(Iobs) + 1e-3) if with_dI else None
+    free = [lay.slot(k) for k in ("noise__I0", "p__I0", "p__r", "p__sigma")]
+    d_q, d_p, d_I = eng.to_device(q), eng.to_device(P * 1.02), eng.to_device(Iobs)
+    d_dI = eng.to_device(dI) if with_dI else None
+    obj = eng.objective(err_mode, log_mode, (0.04, 0.46), has_dI=with_dI)
+    objp, fo, w = eng.prepare_objective(obj, d_q, d_I, d_dI, len(q), B)
+    assert objp.prepared == 1 and obj.prepared == 0
+    assert bool((w[:, 11] == -1).all()) and bool((w[3, 300:310] == -1).all()) and bool((w[:, 0] == -1).all())
+    want = eng.residual(lay, obj, d_q, d_p, d_I, d_dI).clone()
+    got = eng.residual(lay, objp, d_q, d_p, fo, w).clone()
+    np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-13)
+    a = [t.clone() for t in eng.jacobian(lay, obj, d_q, d_p, d_I, d_dI, len(q), free, None)]
+    b = [t.clone() for t in eng.jacobian(lay, objp, d_q, d_p, fo, w, len(q), free, None)]
+    for x, y in zip(a, b):
+        np.testing.assert_allclose(y.cpu().numpy(), x.cpu().numpy(), rtol=1e-11, atol=1e-300)
+    pat = eng.intensity(lay, d_q, d_p)
+    np.testing.assert_allclose(eng.pattern_chi2(objp, d_q, pat, fo, w, len(q)).cpu().numpy(), want.cpu().numpy(), rtol=1e-13)
+    # one shared observed pattern: the streams are [n_q] and broadcast (ld = 0)
+    objs, fo1, w1 = eng.prepare_objective(obj, d_q, d_I[0].contiguous(), d_dI[0].contiguous() if with_dI else None, 0, B)
+    assert tuple(fo1.shape) == (len(q),)
+    np.testing.assert_allclose(eng.residual(lay, objs, d_q, d_p, fo1, w1).cpu().numpy(),
+                               eng.residual(lay, obj, d_q, d_p, d_I[0].contiguous(), d_dI[0].contiguous() if with_dI else None).cpu().numpy(),
+                               rtol=1e-13)
+
+
+def test_variant_slabs_of_one_population_parameters(eng):
+    """A finite-difference variant whose parameter belongs to one population evaluates that population alone
+    (xrsd_jacobian_n_variants): its slab equals the population's own pattern at the perturbed value, and the normal
+    equations agree with a Jacobian that takes whole-pattern differences (the parameter tied into a second population
+    forces those)."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg4_system(System)
+    q = np.linspace(0.01, 1.0, 1400)
+    lay = batch.layout_of(s, q)
+    B = 5
+    P = cfg4_params(lay, B, seed=47)
+    names = ("noise__I0", "x__I0", "x__a", "x__r", "gp__I0", "gp__rg")
+    free = [lay.slot(k) for k in names]
+    obj = eng.objective(True, True, (0.0, float("inf")))
+    d_q, d_p = eng.to_device(q), eng.to_device(P)
+    d_I = eng.intensity(lay, d_q, d_p) * (1 + 0.02 * eng.to_device(np.random.RandomState(2).randn(B, len(q))))
+    tables = eng.build_tables(lay, d_p, B, params_host=P)
+    key = ("t", "local")
+    out = [t.clone() for t in eng.jacobian(lay, obj, d_q, d_p, d_I, None, len(q), free, tables, resident=key)]
+    n_var = eng.jacobian_variants(lay, free)
+    assert n_var == 4                                   # base, a, r, rg
+    slabs = eng.jacobian_slabs(key, lay, B, len(q), n_var).clone()
+    eng.release_resident(key)
+    for v, name, pop in ((1, "x__a", 1), (2, "x__r", 1), (3, "gp__rg", 2)):
+        P1 = P.copy()
+        P1[:, lay.slot(name)] *= 1 + 1e-6
+        _, parts = eng.intensity_components(lay, d_q, eng.to_device(P1), tables=tables)      # tables held fixed
+        np.testing.assert_allclose(slabs[:, v].cpu().numpy(), parts[:, pop].cpu().numpy(), rtol=1e-12, atol=0)
+    # reference values: central differences of whole patterns with the tables held fixed
+    Ib = eng.intensity(lay, d_q, d_p, tables=tables)
+    w = d_I / d_I.sum(dim=1, keepdim=True)              # error_weighted with dI = sqrt(I): weights ~ I_obs, normalised
+    r = Ib.log() - d_I.log()
+    cols = []
+    for name in names:
+        h = 1e-6 * np.abs(P[:, lay.slot(name)])
+        Pp, Pm = P.copy(), P.copy()
+        Pp[:, lay.slot(name)] += h
+        Pm[:, lay.slot(name)] -= h
+        dlog = (eng.intensity(lay, d_q, eng.to_device(Pp), tables=tables).log() - eng.intensity(lay, d_q, eng.to_device(Pm), tables=tables).log())
+        cols.append(dlog / eng.to_device(2 * h)[:, None])
+    J = eng.torch.stack(cols, dim=2)                    # [B, n_q, nf]
+    JTJ = eng.torch.einsum("bq,bqi,bqj->bij", w, J, J)
+    JTr = eng.torch.einsum("bq,bqi,bq->bi", w, J, r)
+    scale = JTJ.diagonal(dim1=1, dim2=2).sqrt()
+    np.testing.assert_allclose((out[0] / (scale[:, :, None] * scale[:, None, :])).cpu().numpy(),
+                               (JTJ / (scale[:, :, None] * scale[:, None, :])).cpu().numpy(), atol=2e-5)
+    np.testing.assert_allclose((out[1] / scale).cpu().numpy(), (JTr / scale).cpu().numpy(), atol=2e-5 * float((JTr / scale).abs().max()))
+
+
+def test_empty_fit_mask_gives_zero_like_the_reference(eng):
+    """No q-point inside q_range (or no positive observation): compute_chi2 sums over nothing and returns 0.0
+    (tools/__init__.py:104-125); the kernels must not return 0/0."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    from oracle import xrsd_oracle as orc
+    s = cfg2_system(System)
+    q = np.linspace(0.01, 0.5, 600)
+    lay = batch.layout_of(s, q)
+    P = cfg2_params(lay, 3, seed=5)
+    Iobs = batch.compute_intensity_batch(lay, q, P)
+    assert orc.residual(q, Iobs[0], Iobs[0] * 1.1, q_range=(0.6, 0.7)) == 0.0
+    chi2 = batch.evaluate_residual_batch(lay, q, Iobs * 1.1, P, q_range=(0.6, 0.7))
+    assert chi2.tolist() == [0.0, 0.0, 0.0]
+    neg = -np.abs(Iobs)
+    assert batch.evaluate_residual_batch(lay, q, neg, P).tolist() == [0.0, 0.0, 0.0]
+    obj = eng.objective(True, True, (0.6, 0.7))
+    d_q, d_p, d_I = eng.to_device(q), eng.to_device(P), eng.to_device(Iobs)
+    assert eng.pattern_chi2(obj, d_q, d_I, d_I, None, len(q)).tolist() == [0.0, 0.0, 0.0]
+    free = [lay.slot("p__I0"), lay.slot("p__r")]
+    JTJ, JTr, c = eng.jacobian(lay, obj, d_q, d_p, d_I, None, len(q), free, None)
+    assert c.tolist() == [0.0, 0.0, 0.0] and float(JTJ.abs().max()) == 0.0 and float(JTr.abs().max()) == 0.0
+    s.set_q_range(0.6, 0.7)
+    assert s.evaluate_residual(q, Iobs[0]) == 0.0 == s.evaluate_residual(q, Iobs[0], I_comp=Iobs[0] * 1.2)
+    # a fit over an empty mask has nothing to improve: it stops at once, parameters untouched
+    res = batch.fit_batch(lay, q, Iobs, P * 1.05, free_slots=free, q_range=(0.6, 0.7), max_iter=5)
+    np.testing.assert_array_equal(res.params, P * 1.05)
+    assert not res.active.any() and res.chi2.tolist() == [0.0, 0.0, 0.0]
+
+
+def test_lm_moves_a_population_that_starts_at_zero_intensity(eng):
+    """A population (or noise level) that starts at I0 = 0 -- its lower bound and a legal value -- has no derivative in
+    I_pop / I0; the loop gives such parameters a finite-difference variant and never parks an I0 on the bound."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg4_system(System)
+    q = np.linspace(0.01, 1.0, 2048)
+    lay = batch.layout_of(s, q)
+    n = 12
+    truth = cfg4_params(lay, n, seed=33)
+    Iobs = batch.compute_intensity_batch(lay, q, truth)
+    free = [lay.slot(k) for k in ("noise__I0", "x__I0", "gp__I0", "gp__rg")]
+    start = truth.copy()
+    start[:, lay.slot("gp__I0")] = 0.0
+    start[::2, lay.slot("noise__I0")] = 0.0
+    start[:, lay.slot("gp__rg")] *= 1.03
+    res = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=60)
+    assert np.all(res.params[:, lay.slot("gp__I0")] > 0)
+    np.testing.assert_allclose(res.params[:, free], truth[:, free], rtol=2e-3)
+    assert np.all(res.chi2 < 1e-6 * res.chi2_init)
+    # ... and a population that should vanish shrinks towards the bound without landing on it
+    gone = truth.copy()
+    gone[:, lay.slot("gp__I0")] = 0.0
+    Iobs0 = batch.compute_intensity_batch(lay, q, gone)
+    res0 = batch.fit_batch(lay, q, Iobs0, truth, free_slots=free, max_iter=60)
+    g = res0.params[:, lay.slot("gp__I0")]
+    assert np.all(g > 0) and np.all(g < 1e-6 * truth[:, lay.slot("gp__I0")])
+
+
+def test_stop_reasons_and_converged_flag(eng):
+    """FitResult.reason: 1 = tolerance met, 2 = no acceptable step left, 0 = iteration cap; `converged` is the first
+    only (the reference reports the optimiser's success flag, system/__init__.py:268-275)."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg2_system(System)
+    q = np.linspace(0.01, 0.5, 1024)
+    lay = batch.layout_of(s, q)
+    n = 24
+    truth = cfg2_params(lay, n, seed=12)
+    rs = np.random.RandomState(3)
+    Iobs = batch.compute_intensity_batch(lay, q, truth) * (1 + 0.02 * rs.randn(n, len(q)))
+    free = [lay.slot(k) for k in ("noise__I0", "p__I0", "p__r", "p__sigma")]
+    start = truth.copy()
+    start[:, free] *= 1 + 0.05 * rs.uniform(-1, 1, (n, len(free)))
+    capped = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=2)
+    assert capped.active.all() and not capped.converged.any() and (capped.reason == 0).all()
+    done = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=200)
+    assert not done.active.any() and set(done.reason.tolist()) <= {1, 2}
+    assert done.converged.mean() > 0.7, done.reason
+    np.testing.assert_array_equal(done.converged, done.reason == 1)
+    # a NaN objective from the start (an error estimate that is not a number) is not a convergence
+    dI = np.sqrt(np.abs(Iobs))
+    dI[0, 100] = np.nan
+    r = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=200, dI=dI)
+    assert r.reason[0] == 3 and not r.converged[0] and r.converged[1:].any()
+
+
+def test_fit_that_starts_at_the_optimum_of_exact_data_stops_at_once(eng):
+    """chi2 = 0 at the start (I_obs produced by the same kernel at the start parameters): nothing to improve, no step
+    is taken, the parameters come back bit for bit and the systems count as converged."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch, fitting
+    s = cfg2_system(System)
+    q = np.linspace(0.01, 0.5, 512)
+    lay = batch.layout_of(s, q)
+    truth = cfg2_params(lay, 4, seed=2)
+    Iobs = batch.compute_intensity_batch(lay, q, truth)
+    free = [lay.slot("p__r"), lay.slot("p__sigma")]
+    res = fitting.lm_fit_batch(lay, q, Iobs, truth, free, max_iter=12, eng=eng)      # starts AT the optimum of noiseless data
+    assert np.all(res.n_accept == 0) and np.all(res.chi2 == 0.0) and res.converged.all() and res.n_iter <= 5
+    np.testing.assert_array_equal(res.params, truth)

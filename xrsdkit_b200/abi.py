@@ -22,7 +22,7 @@ OK, EINVAL, ECUDA, ECAPACITY, ENOMEM = 0, -1, -2, -3, -4
 
 i32, f64 = C.c_int32, C.c_double
 N_FEATURES, FEATURE_MAX_Q = 21, 8192
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class Pop(C.Structure):
@@ -49,11 +49,14 @@ class Tables(C.Structure):
     _fields_ = [("cap_shell", i32), ("cap_refl", i32), ("n_pairs_max", i32), ("cap_list_hint", i32),
                 ("n_shell", C.c_void_p), ("n_refl", C.c_void_p), ("n_all", C.c_void_p), ("status", C.c_void_p),
                 ("shell_hkl", C.c_void_p), ("shell_geo", C.c_void_p), ("refl_hkl", C.c_void_p),
-                ("big_scratch", C.c_void_p), ("cap_big", C.c_int64)]
+                ("big_scratch", C.c_void_p), ("cap_big", C.c_int64),
+                ("table_of", C.c_void_p), ("build_flag", C.c_void_p), ("own_base", i32), ("shared_base", i32),
+                ("n_shared", i32), ("n_grid_slots", i32), ("shared_tag", C.c_void_p), ("grid_scratch", C.c_void_p),
+                ("cap_grid_cells", C.c_int64), ("grid_slot_counter", C.c_void_p)]
 
 
 class Objective(C.Structure):
-    _fields_ = [("error_weighted", i32), ("logI_weighted", i32), ("has_dI", i32), ("reserved0", i32),
+    _fields_ = [("error_weighted", i32), ("logI_weighted", i32), ("has_dI", i32), ("prepared", i32),
                 ("q_lo", f64), ("q_hi", f64)]
 
 
@@ -78,8 +81,12 @@ _SIGNATURES = {
                                       vp, vp, vp, vp, vp, vp]),
     "xrsd_jacobian_n_variants": (i32, [C.POINTER(Layout), C.POINTER(i32), i32, C.POINTER(i32), i32]),
     "xrsd_pattern_chi2_batch": (C.c_int, [C.POINTER(Objective), vp, i32, vp, C.c_int64, i32, vp, vp, C.c_int64, vp, vp, vp]),
+    "xrsd_objective_prepare": (C.c_int, [C.POINTER(Objective), vp, i32, vp, vp, i64, i32, vp, vp, i64, vp]),
+    "xrsd_lm_trial_update": (C.c_int, [C.POINTER(Objective), vp, i32, vp, i64, i32, vp, vp, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp,
+                                       vp, vp, C.POINTER(Tables), i32, vp, f64, f64, f64, f64, f64, vp]),
+    "xrsd_lm_accept": (C.c_int, [vp, i32, vp, i64, vp, i64, i32, i32, i32, C.POINTER(Tables), C.POINTER(Tables), i32, vp]),
     "xrsd_copy_rows_masked": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int64, i32, vp, vp]),
-    "xrsd_lm_propose": (C.c_int, [vp, i32, i32, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(f64), i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "xrsd_lm_propose": (C.c_int, [vp, i32, i32, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(f64), i32, vp, vp, vp, vp, vp, vp, vp, f64, vp]),
     "xrsd_lm_update": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, vp, f64, f64, f64, f64, vp]),
     "xrsd_intensity_batch_host": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, vp, C.c_int64]),
     "xrsd_release_workspace": (None, []),

@@ -70,6 +70,42 @@ def fit_batch(layout, q, Iobs, params0, method='lm', **kw):
     return fitting.lm_fit_batch(layout, q, Iobs, params0, **kw)
 
 
+def fit_mixed(groups, eng=None, **kw):
+    """Fit a batch that mixes system layouts (BASELINE config 5: sphere and crystal systems side by side).
+
+    `groups` is a list of dicts with the keys of fit_batch (layout, q, Iobs, params0 and optionally free_slots, dI,
+    ...): the systems of one layout each.  Every group runs its Levenberg-Marquardt loop on its own CUDA stream,
+    driven by its own host thread, so the launches of the groups interleave on the GPU (the tail of one group's
+    launch is filled by the other's CTAs) and one group's flag reads do not stall the other.  Returns the
+    FitResults (device tensors) in the order of `groups`."""
+    import threading
+    eng = eng or _engine.get_engine()
+    torch = eng.torch
+    if len(groups) == 1:
+        return [fitting.lm_fit_batch(eng=eng, return_device=True, **dict(kw, **groups[0]))]
+    cur = torch.cuda.current_stream(eng.device)
+    results, errors = [None] * len(groups), []
+
+    def work(k, g, stream):
+        try:
+            torch.cuda.set_device(eng.device)
+            with torch.cuda.stream(stream):
+                stream.wait_stream(cur)
+                results[k] = fitting.lm_fit_batch(eng=eng, return_device=True, **dict(kw, **g))
+            stream.synchronize()
+        except BaseException as e:      # re-raised in the calling thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(k, g, torch.cuda.Stream(device=eng.device))) for k, g in enumerate(groups)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
 def gather_rows(local, n_total, group=None):
     """all_gather of per-rank row blocks produced with shard_bounds() into the full [n_total, ...] tensor.
     Works on any backend (nccl on GPUs, gloo on CPU); blocks may differ by one row, so they are padded."""

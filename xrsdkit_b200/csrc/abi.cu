@@ -37,9 +37,17 @@ cudaError_t xrsd_launch_copy_rows_masked(double *, long long, const double *, lo
                                          cudaStream_t);
 int xrsd_jacobian_count_variants(const xrsd_layout_t *, const int32_t *, int, const int32_t *, int);
 cudaError_t xrsd_launch_lm_propose(const double *, int, int, const int32_t *, int, const int32_t *, const double *, int, const double *, const double *,
-                                   const double *, const double *, const double *, const uint8_t *, double *, cudaStream_t);
+                                   const double *, const double *, const double *, const uint8_t *, double *, double, cudaStream_t);
 cudaError_t xrsd_launch_lm_update(double *, int, int, const double *, double *, const double *, double *, uint8_t *, int *,
                                   double, double, double, double, cudaStream_t);
+cudaError_t xrsd_launch_objective_prepare(const xrsd_objective_t *, const double *, int, const double *, const double *, long long,
+                                          int, double *, double *, long long, cudaStream_t);
+cudaError_t xrsd_launch_lm_trial_update(const xrsd_objective_t *, const double *, int, const double *, long long, int,
+                                        const double *, const double *, long long, double *, int, const double *, double *,
+                                        double *, double *, uint8_t *, uint8_t *, uint8_t *, uint8_t *, int *,
+                                        const xrsd_tables_t *, int, int *, double, double, double, double, double, cudaStream_t);
+cudaError_t xrsd_launch_lm_accept(const uint8_t *, int, double *, long long, const double *, long long, int, int, int,
+                                  const xrsd_tables_t *, const xrsd_tables_t *, int, cudaStream_t);
 }
 
 namespace {
@@ -284,7 +292,7 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   rc = check_tables(layout, tables);
   if (rc) return rc;
   if (!obj || !d_q || !d_params || !d_Iobs || !d_chi2 || !d_workspace) return fail(XRSD_EINVAL, "NULL pointer");
-  if (obj->has_dI && !d_dI) return fail(XRSD_EINVAL, "objective.has_dI set but d_dI is NULL");
+  if ((obj->has_dI || obj->prepared) && !d_dI) return fail(XRSD_EINVAL, "objective.has_dI / prepared set but d_dI is NULL");
   if (ld_obs != 0 && ld_obs < n_q) return fail(XRSD_EINVAL, "ld_obs < n_q");
   int rm;
   const int scratch = scratch_doubles_for(layout, &rm);
@@ -293,7 +301,7 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   double *d_acc = (double *)d_workspace;
   unsigned *d_tickets = (unsigned *)((char *)d_workspace + (int64_t)batch * 16);
   cudaError_t e = xrsd_launch_residual(layout, obj, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables,
-                                       d_Iobs, obj->has_dI ? d_dI : nullptr, (long long)ld_obs, d_chi2, per, scratch, rm, d_active,
+                                       d_Iobs, (obj->has_dI || obj->prepared) ? d_dI : nullptr, (long long)ld_obs, d_chi2, per, scratch, rm, d_active,
                                        d_acc, d_tickets, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "residual_kernel");
   return XRSD_OK;
@@ -322,12 +330,16 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   if (mode != XRSD_JAC_FULL && mode != XRSD_JAC_BASE_READY && mode != XRSD_JAC_PATTERNS_ONLY)
     return fail(XRSD_EINVAL, "mode=%d", mode);
   const bool reduce = mode != XRSD_JAC_PATTERNS_ONLY;
-  if (!obj || !d_q || !d_params || !free_idx || !d_workspace || (reduce && (!d_Iobs || !d_JTJ || !d_JTr || !d_chi2)))
+  if (!obj || !d_q || !d_params || (!free_idx && n_free > 0) || !d_workspace || (reduce && (!d_Iobs || !d_JTJ || !d_JTr || !d_chi2)))
     return fail(XRSD_EINVAL, "NULL pointer");
-  if (n_free < 1 || n_free > XRSD_MAX_FREE) return fail(XRSD_EINVAL, "n_free=%d (max %d)", n_free, XRSD_MAX_FREE);
-  for (int i = 0; i < n_free; ++i)
-    if (free_idx[i] < 0 || free_idx[i] >= layout->n_params) return fail(XRSD_EINVAL, "free_idx[%d]=%d", i, free_idx[i]);
-  if (reduce && obj->has_dI && !d_dI) return fail(XRSD_EINVAL, "objective.has_dI set but d_dI is NULL");
+  // n_free == 0 is "the pattern and its running totals" and only makes sense without the reduction
+  if (n_free < (reduce ? 1 : 0) || n_free > XRSD_MAX_FREE) return fail(XRSD_EINVAL, "n_free=%d (max %d)", n_free, XRSD_MAX_FREE);
+  for (int i = 0; i < n_free; ++i) {
+    const int slot = free_idx[i] < 0 ? -free_idx[i] - 1 : free_idx[i];      // -(slot+1): forced finite-difference variant
+    if (slot >= layout->n_params) return fail(XRSD_EINVAL, "free_idx[%d]=%d", i, free_idx[i]);
+  }
+  if (reduce && (obj->has_dI || obj->prepared) && !d_dI)
+    return fail(XRSD_EINVAL, "objective.has_dI / prepared set but d_dI is NULL");
   if (reduce && ld_obs != 0 && ld_obs < n_q) return fail(XRSD_EINVAL, "ld_obs < n_q");
   if (!(rel_step > 0.0)) return fail(XRSD_EINVAL, "rel_step must be > 0");
   if (n_tie < 0 || n_tie > XRSD_MAX_TIES || (n_tie > 0 && !ties)) return fail(XRSD_EINVAL, "n_tie=%d (max %d)", n_tie, XRSD_MAX_TIES);
@@ -347,7 +359,7 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   double *d_acc = (double *)((char *)d_workspace + fbytes);
   unsigned *d_tickets = (unsigned *)((char *)d_workspace + fbytes + abytes);
   cudaError_t e = xrsd_launch_jacobian(layout, obj, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables, d_Iobs,
-                                       obj->has_dI ? d_dI : nullptr, (long long)ld_obs, free_idx, n_free, ties, tie_coef, n_tie, rel_step, mode, d_JTJ,
+                                       (obj->has_dI || obj->prepared) ? d_dI : nullptr, (long long)ld_obs, free_idx, n_free, ties, tie_coef, n_tie, rel_step, mode, d_JTJ,
                                        d_JTr, d_chi2, d_Fvar, d_acc, d_tickets, per, scratch, rm, d_active, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "jacobian_kernel");
   return XRSD_OK;
@@ -361,16 +373,17 @@ int32_t xrsd_jacobian_n_variants(const xrsd_layout_t *layout, const int32_t *fre
 
 int xrsd_lm_propose(const double *d_params, int32_t ld_params, int32_t batch, const int32_t *free_idx, int32_t n_free,
                     const int32_t *ties, const double *tie_coef, int32_t n_tie, const double *d_JTJ, const double *d_JTr, const double *d_lambda, const double *d_lo, const double *d_hi,
-                    const uint8_t *d_active, double *d_trial, void *stream) {
+                    const uint8_t *d_active, double *d_trial, double max_rel_step, void *stream) {
   if (n_free < 1 || n_free > XRSD_MAX_FREE) return fail(XRSD_EINVAL, "n_free=%d (max %d)", n_free, XRSD_MAX_FREE);
+  if (!(max_rel_step >= 0.0)) return fail(XRSD_EINVAL, "max_rel_step must be >= 0 (0 = no limit)");
   if (!d_params || !free_idx || !d_JTJ || !d_JTr || !d_lambda || !d_lo || !d_hi || !d_trial) return fail(XRSD_EINVAL, "NULL pointer");
   for (int i = 0; i < n_free; ++i)
-    if (free_idx[i] < 0 || free_idx[i] >= ld_params) return fail(XRSD_EINVAL, "free_idx[%d]=%d", i, free_idx[i]);
+    if ((free_idx[i] < 0 ? -free_idx[i] - 1 : free_idx[i]) >= ld_params) return fail(XRSD_EINVAL, "free_idx[%d]=%d", i, free_idx[i]);
   if (n_tie < 0 || n_tie > XRSD_MAX_TIES || (n_tie > 0 && !ties)) return fail(XRSD_EINVAL, "n_tie=%d (max %d)", n_tie, XRSD_MAX_TIES);
   for (int i = 0; i < 2 * n_tie; ++i)
     if (ties[i] < 0 || ties[i] >= ld_params) return fail(XRSD_EINVAL, "ties[%d]=%d", i, ties[i]);
   cudaError_t e = xrsd_launch_lm_propose(d_params, ld_params, batch, free_idx, n_free, ties, tie_coef, n_tie, d_JTJ, d_JTr, d_lambda, d_lo, d_hi,
-                                         d_active, d_trial, (cudaStream_t)stream);
+                                         d_active, d_trial, max_rel_step, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "lm_propose_kernel");
   return XRSD_OK;
 }
@@ -390,12 +403,75 @@ int xrsd_pattern_chi2_batch(const xrsd_objective_t *obj, const double *d_q, int3
                             const uint8_t *d_active, void *stream) {
   if (batch <= 0 || n_q <= 0) return XRSD_OK;
   if (!obj || !d_q || !d_I || !d_Iobs || !d_chi2) return fail(XRSD_EINVAL, "NULL pointer");
-  if (obj->has_dI && !d_dI) return fail(XRSD_EINVAL, "objective.has_dI set but d_dI is NULL");
+  if ((obj->has_dI || obj->prepared) && !d_dI) return fail(XRSD_EINVAL, "objective.has_dI / prepared set but d_dI is NULL");
   if (ld_I < n_q) return fail(XRSD_EINVAL, "ld_I < n_q");
   if (ld_obs != 0 && ld_obs < n_q) return fail(XRSD_EINVAL, "ld_obs < n_q");
-  cudaError_t e = xrsd_launch_pattern_chi2(obj, d_q, n_q, d_I, (long long)ld_I, batch, d_Iobs, obj->has_dI ? d_dI : nullptr,
+  cudaError_t e = xrsd_launch_pattern_chi2(obj, d_q, n_q, d_I, (long long)ld_I, batch, d_Iobs, (obj->has_dI || obj->prepared) ? d_dI : nullptr,
                                            (long long)ld_obs, d_chi2, d_active, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "pattern_chi2_kernel");
+  return XRSD_OK;
+}
+
+int xrsd_objective_prepare(const xrsd_objective_t *obj, const double *d_q, int32_t n_q, const double *d_Iobs, const double *d_dI,
+                           int64_t ld_obs, int32_t rows, double *d_fo, double *d_w, int64_t ld_out, void *stream) {
+  if (rows <= 0 || n_q <= 0) return XRSD_OK;
+  if (!obj || !d_q || !d_Iobs || !d_fo || !d_w) return fail(XRSD_EINVAL, "NULL pointer");
+  if (obj->prepared) return fail(XRSD_EINVAL, "objective is already marked prepared");
+  if (obj->has_dI && !d_dI) return fail(XRSD_EINVAL, "objective.has_dI set but d_dI is NULL");
+  if ((rows > 1 && ld_obs < n_q) || ld_out < n_q) return fail(XRSD_EINVAL, "leading dimension < n_q");
+  cudaError_t e = xrsd_launch_objective_prepare(obj, d_q, n_q, d_Iobs, obj->has_dI ? d_dI : nullptr, (long long)ld_obs, rows, d_fo,
+                                                d_w, (long long)ld_out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "objective_prepare_kernel");
+  return XRSD_OK;
+}
+
+int xrsd_lm_trial_update(const xrsd_objective_t *obj, const double *d_q, int32_t n_q, const double *d_I, int64_t ld_I,
+                         int32_t batch, const double *d_Iobs, const double *d_dI, int64_t ld_obs, double *d_params,
+                         int32_t ld_params, const double *d_trial, double *d_chi2, double *d_chi2_trial, double *d_lambda,
+                         uint8_t *d_active, uint8_t *d_accepted, uint8_t *d_needjac, uint8_t *d_reason, int32_t *d_n_accept,
+                         const xrsd_tables_t *trial_tables, int32_t n_xtal, int32_t *d_flags, double up, double down,
+                         double ftol, double xtol, double lambda_max, void *stream) {
+  if (batch <= 0) return XRSD_OK;
+  if (!obj || !d_params || !d_trial || !d_chi2 || !d_chi2_trial || !d_lambda || !d_active || !d_accepted || !d_needjac ||
+      !d_reason || !d_n_accept)
+    return fail(XRSD_EINVAL, "NULL pointer");
+  if (d_I) {
+    if (!d_q || !d_Iobs || n_q <= 0) return fail(XRSD_EINVAL, "a trial pattern needs q, I_obs and n_q > 0");
+    if ((obj->has_dI || obj->prepared) && !d_dI) return fail(XRSD_EINVAL, "objective.has_dI / prepared set but d_dI is NULL");
+    if (ld_I < n_q || (ld_obs != 0 && ld_obs < n_q)) return fail(XRSD_EINVAL, "leading dimension < n_q");
+  }
+  if (ld_params < 1 || ld_params > XRSD_MAX_PARAMS) return fail(XRSD_EINVAL, "ld_params=%d", ld_params);
+  if (trial_tables && (n_xtal < 1 || !trial_tables->status)) return fail(XRSD_EINVAL, "trial tables without status / n_xtal");
+  if (!(up > 1.0) || !(down > 1.0)) return fail(XRSD_EINVAL, "up and down must be > 1");
+  cudaError_t e = xrsd_launch_lm_trial_update(obj, d_q, n_q, d_I, (long long)ld_I, batch, d_Iobs,
+                                              (obj->has_dI || obj->prepared) ? d_dI : nullptr, (long long)ld_obs, d_params, ld_params,
+                                              d_trial, d_chi2, d_chi2_trial, d_lambda, d_active, d_accepted, d_needjac, d_reason,
+                                              d_n_accept, trial_tables, n_xtal, d_flags, up, down, ftol, xtol, lambda_max,
+                                              (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "lm_trial_update_kernel");
+  return XRSD_OK;
+}
+
+int xrsd_lm_accept(const uint8_t *d_accepted, int32_t batch, double *d_dst, int64_t dst_stride, const double *d_src,
+                   int64_t src_stride, int32_t n_q, int32_t n_var, int32_t n_pops, const xrsd_tables_t *tables,
+                   const xrsd_tables_t *trial_tables, int32_t n_xtal, void *stream) {
+  if (batch <= 0) return XRSD_OK;
+  if (!d_accepted) return fail(XRSD_EINVAL, "NULL pointer");
+  if ((d_dst == nullptr) != (d_src == nullptr)) return fail(XRSD_EINVAL, "slab source and destination go together");
+  if (d_dst) {
+    if (n_q < 1 || n_var < 1 || n_pops < 1 || n_pops > XRSD_MAX_POPS) return fail(XRSD_EINVAL, "n_q %d, n_var %d, n_pops %d", n_q, n_var, n_pops);
+    if (dst_stride < (int64_t)(n_var + n_pops) * n_q || src_stride < (int64_t)(1 + n_pops) * n_q)
+      return fail(XRSD_EINVAL, "slab strides too small for the slab layout");
+  }
+  if ((tables == nullptr) != (trial_tables == nullptr)) return fail(XRSD_EINVAL, "tables and trial tables go together");
+  if (tables) {
+    if (n_xtal < 1) return fail(XRSD_EINVAL, "n_xtal=%d", n_xtal);
+    if (tables->cap_shell != trial_tables->cap_shell || tables->n_pairs_max != trial_tables->n_pairs_max)
+      return fail(XRSD_EINVAL, "table sets of different capacities");
+  }
+  cudaError_t e = xrsd_launch_lm_accept(d_accepted, batch, d_dst, (long long)dst_stride, d_src, (long long)src_stride, n_q, n_var,
+                                        n_pops, tables, trial_tables, n_xtal, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "lm_accept_kernel");
   return XRSD_OK;
 }
 

@@ -23,10 +23,27 @@ struct FreeSet {
   int var_of[XRSD_MAX_FREE];    // variant index (>= 1) of a non-linear parameter, 0 for a linear one
   int pop_of[XRSD_MAX_FREE];    // linear parameter (an I0): index of its population, else -1
   int free_of_var[XRSD_MAX_FREE + 1];   // inverse of var_of
+  int vpop_of[XRSD_MAX_FREE];   // non-linear parameter used by ONE population (incl. what is tied to it): that population's
+                                // index -- its variant evaluates the population alone -- else -1 (whole system)
   int n_tie;                    // constraints "dst = scale * src + offset" (constraint_expr affine in one parameter)
   int tie_dst[XRSD_MAX_TIES], tie_src[XRSD_MAX_TIES];
   double tie_scale[XRSD_MAX_TIES], tie_off[XRSD_MAX_TIES];
 };
+
+// does population (or noise model) `p` read parameter slot `slot`?
+static bool pop_uses_slot(const xrsd_pop_t &p, int slot) {
+  if (p.kind == XRSD_POP_NONE) return false;
+  const int32_t scalars[] = {p.p_I0, p.p_r, p.p_sigma, p.p_rg, p.p_D, p.p_r_hard, p.p_v_fraction, p.p_flat_fraction,
+                             p.p_hwhm, p.p_hwhm_g, p.p_hwhm_l};
+  for (int32_t s : scalars)
+    if (s == slot) return true;
+  for (int i = 0; i < 6; ++i)
+    if (p.p_lat[i] == slot) return true;
+  for (int a = 0; a < XRSD_MAX_SPECIES; ++a)
+    for (int j = 0; j < 3; ++j)
+      if (p.p_uvw[a][j] == slot) return true;
+  return false;
+}
 
 // An I0 multiplies its whole population (scattering/__init__.py:48,64,66; system/noise.py:56-62), so
 // dI/dI0 = I_pop / I0 needs no extra evaluation: the base variant records the running total after
@@ -44,26 +61,40 @@ static FreeSet make_free_set(const xrsd_layout_t *L, const int32_t *free_idx, in
     F.tie_scale[t] = tie_coef ? tie_coef[2 * t] : 1.0;
     F.tie_off[t] = tie_coef ? tie_coef[2 * t + 1] : 0.0;
   }
-  for (int j = 0; j < XRSD_MAX_FREE; ++j) { F.pop_of[j] = -1; }
+  for (int j = 0; j < XRSD_MAX_FREE; ++j) { F.pop_of[j] = -1; F.vpop_of[j] = -1; }
   for (int j = 0; j < n_free; ++j) {
-    F.idx[j] = free_idx[j];
+    // free_idx[j] = -(slot + 1) asks for a finite-difference variant even if the parameter is an I0 (the caller does
+    // that when a system starts at I0 == 0, where I_pop / I0 carries no derivative)
+    const bool forced = free_idx[j] < 0;
+    const int slot = forced ? -free_idx[j] - 1 : free_idx[j];
+    F.idx[j] = slot;
     int pop = -1;
     if (L)
       for (int k = 0; k < L->n_pops; ++k)
-        if (L->pops[k].kind != XRSD_POP_NONE && L->pops[k].p_I0 == free_idx[j]) pop = k;
+        if (L->pops[k].kind != XRSD_POP_NONE && L->pops[k].p_I0 == slot) pop = k;
     // a slot shared by two populations (not produced by the lowering) would not be linear in one term
     int uses = 0;
     if (L)
-      for (int k = 0; k < L->n_pops; ++k) uses += (L->pops[k].p_I0 == free_idx[j]);
+      for (int k = 0; k < L->n_pops; ++k) uses += (L->pops[k].p_I0 == slot);
     bool tied = false;      // a parameter that drives another one is not linear in a single term
-    for (int t = 0; t < F.n_tie; ++t) tied = tied || (F.tie_src[t] == free_idx[j]);
-    if (pop >= 0 && uses == 1 && !tied) {
+    for (int t = 0; t < F.n_tie; ++t) tied = tied || (F.tie_src[t] == slot);
+    if (pop >= 0 && uses == 1 && !tied && !forced) {
       F.pop_of[j] = pop;
       F.var_of[j] = 0;
     } else {
       F.var_of[j] = F.n_var;
       F.free_of_var[F.n_var] = j;
       ++F.n_var;
+      // populations that see this parameter or anything tied to it
+      if (L) {
+        int users = 0, which = -1;
+        for (int k = 0; k < L->n_pops; ++k) {
+          bool u = pop_uses_slot(L->pops[k], slot);
+          for (int t = 0; t < F.n_tie; ++t) u = u || (F.tie_src[t] == slot && pop_uses_slot(L->pops[k], F.tie_dst[t]));
+          if (u) { ++users; which = k; }
+        }
+        if (users == 1) F.vpop_of[j] = which;
+      }
     }
   }
   return F;
@@ -72,6 +103,10 @@ static FreeSet make_free_set(const xrsd_layout_t *L, const int32_t *free_idx, in
 // weight and mask of one q-point (system/__init__.py:164-172)
 __device__ __forceinline__ bool fit_weight(const xrsd_objective_t &O, double qv, double Iobs, const double *dI, size_t k,
                                            double &w) {
+  if (O.prepared) {            // xrsd_objective_prepare did this once per fit: weight stream, -1 on masked points
+    w = dI[k];
+    return !(w < 0.0);
+  }
   const bool fit = (Iobs > 0.0) && (qv >= O.q_lo) && (qv <= O.q_hi);
   w = 1.0;
   if (O.error_weighted) {
@@ -81,6 +116,11 @@ __device__ __forceinline__ bool fit_weight(const xrsd_objective_t &O, double qv,
     w = w * (d * d);
   }
   return fit;
+}
+
+// f(I_obs) of the objective: the logarithm (or the value) of the observed intensity, or the prepared stream
+__device__ __forceinline__ double fit_target(const xrsd_objective_t &O, double Iobs) {
+  return (O.logI_weighted && !O.prepared) ? log(Iobs) : Iobs;
 }
 
 // Grid = batch x q-spans (same span policy as the intensity kernel).  Each CTA evaluates its span into
@@ -117,7 +157,7 @@ residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
     double d;
     if (O.logI_weighted) {
       fit = fit && (Ic > 0.0);
-      d = fit ? (log(Ic) - log(Io)) : 0.0;
+      d = fit ? (log(Ic) - fit_target(O, Io)) : 0.0;
     } else {
       d = Ic - Io;
     }
@@ -133,7 +173,7 @@ residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
     if (is_last) {
       __threadfence();
       const double n_ = __ldcg(&acc_g[2 * (size_t)b]), d_ = __ldcg(&acc_g[2 * (size_t)b + 1]);
-      chi2[b] = n_ / d_;
+      chi2[b] = (d_ == 0.0 && n_ == 0.0) ? 0.0 : n_ / d_;      // no point in the fit mask: the reference's compute_chi2 sums nothing -> 0.0
       acc_g[2 * (size_t)b] = 0.0;
       acc_g[2 * (size_t)b + 1] = 0.0;
       tickets[b] = 0;
@@ -195,8 +235,11 @@ jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *
   double *slab0 = Fvar + (size_t)b * n_slab * n_q;
   double *dst = slab0 + (size_t)v * n_q + q_begin;
   if (pattern_doubles == 0) I_sm = dst;
+  // a variant whose parameter belongs to one population evaluates that population alone (the reduction takes the
+  // difference against the base's own term for it, from the running totals)
+  const int only_pop = v > 0 ? F.vpop_of[F.free_of_var[v]] : -1;
   accumulate_system<2, RM, HX>(L, prm_s, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S, prm,
-                               v == 0 ? slab0 + (size_t)nv * n_q + q_begin : nullptr, n_q);
+                               v == 0 ? slab0 + (size_t)nv * n_q + q_begin : nullptr, n_q, only_pop);
   if (pattern_doubles != 0)
     for (int i = tid; i < q_count; i += EVAL_THREADS) dst[i] = I_sm[i];
 }
@@ -286,7 +329,7 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
       }
       if (!fit) { issue(it + JR_STAGES); continue; }
       const double f0 = O.logI_weighted ? log(I0v) : I0v;
-      const double fo = O.logI_weighted ? log(Io) : Io;
+      const double fo = fit_target(O, Io);
       const double res = f0 - fo;
       const double inv = O.logI_weighted ? 1.0 / I0v : 1.0;
       double D[NF];
@@ -295,7 +338,14 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
         double d = 0.0;
         if (j < nf) {
           if (F.var_of[j] > 0) {
-            d = Fs[F.var_of[j] * JR_THREADS] - I0v;
+            const int kv = F.vpop_of[j];
+            if (kv < 0) {
+              d = Fs[F.var_of[j] * JR_THREADS] - I0v;
+            } else {          // the variant slab holds population kv alone: difference against the base's term for it
+              double Ik = Fs[(nv + kv) * JR_THREADS];
+              if (kv > 0) Ik -= Fs[(nv + kv - 1) * JR_THREADS];
+              d = Fs[F.var_of[j] * JR_THREADS] - Ik;
+            }
           } else {
             const int kp = F.pop_of[j];
             double Ik = Fs[(nv + kp) * JR_THREADS];
@@ -372,7 +422,8 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  const double swt = __ldcg(&accb[NF * NF + NF + 1]);
+  double swt = __ldcg(&accb[NF * NF + NF + 1]);
+  if (swt == 0.0 && __ldcg(&accb[NF * NF + NF]) == 0.0) swt = 1.0;      // empty fit mask: chi2 = 0, no gradient (see residual_kernel)
   for (int e = tid; e < nf * nf; e += JR_THREADS) {
     const int j = e / nf, k = e - j * nf;
     const int jj = min(j, k), kk = max(j, k);
@@ -398,7 +449,7 @@ __global__ void lm_propose_kernel(const double *__restrict__ params, int ldp, in
                                   const double *__restrict__ JTJ, const double *__restrict__ JTr,
                                   const double *__restrict__ lambda, const double *__restrict__ lo,
                                   const double *__restrict__ hi, const uint8_t *__restrict__ active,
-                                  double *__restrict__ trial) {
+                                  double *__restrict__ trial, double max_rel_step) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
   const int nf = F.n_free;
@@ -452,8 +503,19 @@ __global__ void lm_propose_kernel(const double *__restrict__ params, int ldp, in
     g[i] = s / A[i][i];
   }
   for (int j = 0; j < nf; ++j) {
-    double v = p[F.idx[j]] + g[j];
+    double dj = g[j];
+    if (max_rel_step > 0.0) {
+      // relative trust region: one step changes a parameter by at most max_rel_step of its magnitude (a damped
+      // Gauss-Newton step far outside the linear range -- a peak width grown 100x -- costs a whole-pattern
+      // evaluation in the slow regime of the profile sum and is rejected anyway)
+      const double cap = max_rel_step * fmax(fabs(p[F.idx[j]]), 1.0e-300);
+      dj = fmin(fmax(dj, -cap), cap);
+    }
+    double v = p[F.idx[j]] + dj;
     const double l = lo[(size_t)b * nf + j], h = hi[(size_t)b * nf + j];
+    // a positive parameter is not put ON a zero lower bound (an I0 at exactly 0 has no derivative left): it shrinks
+    // by 1000x per step instead and reaches the bound geometrically
+    if (l == 0.0 && v <= 0.0 && p[F.idx[j]] > 0.0) v = 1.0e-3 * p[F.idx[j]];
     v = fmin(fmax(v, l), h);
     if (v == v) t[F.idx[j]] = v;
   }
@@ -484,6 +546,7 @@ __global__ void lm_update_kernel(double *__restrict__ params, int ldp, int batch
 // evaluation.  The resident LM loop uses it for the trial point, whose pattern the variants kernel has just left
 // in the second workspace.  One CTA per system; 2 (3 with dI) streams of 8 B per q-point and two logs.
 constexpr int CHI2_THREADS = 256;
+constexpr int COPY_THREADS = 256, COPY_CHUNK = 2048;
 __global__ void __launch_bounds__(CHI2_THREADS)
 pattern_chi2_kernel(const xrsd_objective_t O, const double *__restrict__ q, int n_q, const double *__restrict__ I, long long ld_I,
                     int batch, const double *__restrict__ Iobs, const double *__restrict__ dI, long long ld_obs,
@@ -504,7 +567,7 @@ pattern_chi2_kernel(const xrsd_objective_t O, const double *__restrict__ q, int 
     double d;
     if (O.logI_weighted) {
       fit = fit && (Ic > 0.0);
-      d = fit ? (log(Ic) - log(Io)) : 0.0;
+      d = fit ? (log(Ic) - fit_target(O, Io)) : 0.0;
     } else {
       d = Ic - Io;
     }
@@ -521,7 +584,185 @@ pattern_chi2_kernel(const xrsd_objective_t O, const double *__restrict__ q, int 
     double n_ = 0.0, d_ = 0.0;
 #pragma unroll
     for (int w = 0; w < CHI2_THREADS / 32; ++w) { n_ += red[0][w]; d_ += red[1][w]; }
-    chi2[b] = n_ / d_;
+    chi2[b] = (d_ == 0.0 && n_ == 0.0) ? 0.0 : n_ / d_;
+  }
+}
+
+// Once per fit: f(I_obs) and the weight of every point (system/__init__.py:164-172), so the kernels of the loop read two
+// streams instead of evaluating a logarithm, a square root and the q-range test per point and iteration.
+//   fo[r][i] = log(I_obs) (log mode, 0 where I_obs <= 0) or I_obs;   w[r][i] = the point's weight, -1 when masked out
+__global__ void __launch_bounds__(256)
+objective_prepare_kernel(const xrsd_objective_t O, const double *__restrict__ q, int n_q, const double *__restrict__ Iobs,
+                         const double *__restrict__ dI, long long ld_obs, int rows, double *__restrict__ fo,
+                         double *__restrict__ wt, long long ld_out) {
+  const int r = blockIdx.x;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n_q; i += gridDim.y * blockDim.x) {
+    const double Io = Iobs[(size_t)r * ld_obs + i];
+    double w;
+    const bool fit = fit_weight(O, q[i], Io, dI ? dI + (size_t)r * ld_obs : nullptr, i, w);
+    fo[(size_t)r * ld_out + i] = O.logI_weighted ? (Io > 0.0 ? log(Io) : 0.0) : Io;
+    wt[(size_t)r * ld_out + i] = fit ? w : -1.0;
+  }
+}
+
+// The trial point of one LM iteration: chi2 of its stored pattern (as pattern_chi2_kernel; or the value already in
+// chi2_trial when no pattern is given), then accept / reject for that system -- parameters, chi2, damping, the
+// flags the next launches are masked with, and the reason a system left the loop:
+//   reason 0 = still running, 1 = converged (relative change of chi2 <= ftol, or of every parameter <= xtol),
+//          2 = damping beyond lambda_max (no acceptable step left), 3 = objective not finite at the accepted point
+// A trial point whose reflection table could not be built (status != 0, e.g. the cell outgrew the candidate box of
+// this iteration) counts as chi2 = inf; flags[0] records that it happened.
+__global__ void __launch_bounds__(CHI2_THREADS)
+lm_trial_update_kernel(const xrsd_objective_t O, const double *__restrict__ q, int n_q, const double *__restrict__ I,
+                       long long ld_I, int batch, const double *__restrict__ Iobs, const double *__restrict__ dI,
+                       long long ld_obs, double *__restrict__ params, int ldp, const double *__restrict__ trial,
+                       double *__restrict__ chi2, double *__restrict__ chi2_trial, double *__restrict__ lambda,
+                       uint8_t *__restrict__ active, uint8_t *__restrict__ accepted, uint8_t *__restrict__ needjac,
+                       uint8_t *__restrict__ reason, int *__restrict__ n_accept, const xrsd_tables_t Tt, int n_xtal,
+                       int *__restrict__ flags, double up, double down, double ftol, double xtol, double lambda_max) {
+  __shared__ double red[2][CHI2_THREADS / 32];
+  __shared__ int take;
+  const int b = blockIdx.x;
+  if (b >= batch) return;
+  if (!active[b]) {
+    if (threadIdx.x == 0) { accepted[b] = 0; needjac[b] = 0; }
+    return;
+  }
+  if (I != nullptr) {
+    const double *pat = I + (size_t)b * ld_I;
+    const double *obs = Iobs + (size_t)b * ld_obs;
+    const double *err = dI ? dI + (size_t)b * ld_obs : nullptr;
+    double num = 0.0, den = 0.0;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n_q; i += CHI2_THREADS) {
+      const double Io = obs[i], Ic = pat[i];
+      double w;
+      bool fit = fit_weight(O, O.prepared ? 0.0 : q[i], Io, err, i, w);
+      double d;
+      if (O.logI_weighted) {
+        fit = fit && (Ic > 0.0);
+        d = fit ? (log(Ic) - fit_target(O, Io)) : 0.0;
+      } else {
+        d = Ic - Io;
+      }
+      if (fit) { num += (d * d) * w; den += w; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      num += __shfl_xor_sync(0xffffffffu, num, o);
+      den += __shfl_xor_sync(0xffffffffu, den, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = num; red[1][threadIdx.x >> 5] = den; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double c1;
+    if (I != nullptr) {
+      double n_ = 0.0, d_ = 0.0;
+#pragma unroll
+      for (int w = 0; w < CHI2_THREADS / 32; ++w) { n_ += red[0][w]; d_ += red[1][w]; }
+      c1 = (d_ > 0.0) ? n_ / d_ : INFINITY;       // a trial point with nothing left in the fit mask is not an improvement
+    } else {
+      c1 = chi2_trial[b];
+    }
+    if (n_xtal > 0 && Tt.status != nullptr) {
+      int st = 0;
+      for (int s = 0; s < n_xtal; ++s) {
+        const int t = b * n_xtal + s;
+        st |= Tt.status[Tt.table_of != nullptr ? Tt.table_of[t] : Tt.own_base + t];
+      }
+      if (st != 0) {
+        c1 = INFINITY;
+        if (flags != nullptr) atomicOr(&flags[0], st);
+      }
+    }
+    chi2_trial[b] = c1;
+    const double c0 = chi2[b];
+    // largest relative parameter change of the step
+    double rel = 0.0;
+    for (int k = 0; k < ldp; ++k) {
+      const double a = params[(size_t)b * ldp + k], t = trial[(size_t)b * ldp + k];
+      if (a != t) rel = fmax(rel, fabs(t - a) / fmax(fabs(a), 1.0e-300));
+    }
+    int acc = 0, why = 0;
+    if (c1 < c0) {   // false for NaN trials
+      acc = 1;
+      chi2[b] = c1;
+      lambda[b] = fmax(lambda[b] / down, 1.0e-12);
+      n_accept[b] += 1;
+      if ((c0 - c1) <= ftol * c0 || rel <= xtol) why = 1;
+    } else {
+      lambda[b] = lambda[b] * up;
+      if (c1 == c1 && c1 != INFINITY && (c1 - c0) <= ftol * c0 && rel > 0.0) why = 1;   // as good as the current point
+      else if (rel > 0.0 && rel <= xtol) why = 1;
+      else if (lambda[b] > lambda_max) why = 2;
+      if (!(c0 == c0) || c0 == INFINITY) why = 3;
+      if (c0 == 0.0) why = 1;                        // nothing left to improve (exact data, or an empty fit mask)
+    }
+    take = acc;
+    accepted[b] = (uint8_t)acc;
+    if (why) { active[b] = 0; reason[b] = (uint8_t)why; }
+    needjac[b] = (uint8_t)(acc && !why);
+  }
+  __syncthreads();
+  if (take)
+    for (int k = threadIdx.x; k < ldp; k += CHI2_THREADS) params[(size_t)b * ldp + k] = trial[(size_t)b * ldp + k];
+}
+
+// Accepted systems take over what the trial evaluation left behind: its pattern and running totals become the base
+// rows of the resident Jacobian workspace (slab s of the 1 + n_pops trial slabs goes to slab 0 or n_var + s - 1), and
+// its reflection tables become the system's tables -- for a shared table that is one row index, for an own table the
+// row's contents.  One launch, grid = batch x (slab chunks + n_xtal).
+__global__ void __launch_bounds__(COPY_THREADS)
+lm_accept_kernel(const uint8_t *__restrict__ accepted, int batch, double *__restrict__ dst, long long dst_stride,
+                 const double *__restrict__ src, long long src_stride, int n_q, int n_var, int n_pops, int chunks_per_slab,
+                 const xrsd_tables_t T, const xrsd_tables_t Tt, int n_xtal) {
+  const int per_sys = (dst != nullptr ? (1 + n_pops) * chunks_per_slab : 0) + n_xtal;
+  const int b = blockIdx.x / per_sys;
+  int c = blockIdx.x - b * per_sys;
+  if (b >= batch || !accepted[b]) return;
+  if (dst != nullptr) {
+    if (c < (1 + n_pops) * chunks_per_slab) {
+      const int s = c / chunks_per_slab, part = c - s * chunks_per_slab;
+      double *__restrict__ d = dst + (size_t)b * dst_stride + (size_t)(s == 0 ? 0 : n_var + s - 1) * n_q + (size_t)part * COPY_CHUNK;
+      const double *__restrict__ sp = src + (size_t)b * src_stride + (size_t)s * n_q + (size_t)part * COPY_CHUNK;
+      const int n = min(COPY_CHUNK, n_q - part * COPY_CHUNK);
+      double v[COPY_CHUNK / COPY_THREADS];
+#pragma unroll
+      for (int k = 0; k < COPY_CHUNK / COPY_THREADS; ++k) {
+        const int i = threadIdx.x + k * COPY_THREADS;
+        if (i < n) v[k] = sp[i];
+      }
+#pragma unroll
+      for (int k = 0; k < COPY_CHUNK / COPY_THREADS; ++k) {
+        const int i = threadIdx.x + k * COPY_THREADS;
+        if (i < n) d[i] = v[k];
+      }
+      return;
+    }
+    c -= (1 + n_pops) * chunks_per_slab;
+  }
+  // table slot c
+  const int t = b * n_xtal + c;
+  const int src_row = Tt.table_of != nullptr ? Tt.table_of[t] : Tt.own_base + t;
+  if (T.table_of != nullptr && Tt.n_shared > 0 && src_row >= Tt.shared_base) {
+    if (threadIdx.x == 0) T.table_of[t] = src_row;
+    return;
+  }
+  const int dst_row = T.own_base + t;
+  const int ns = min(Tt.n_shell[src_row], T.cap_shell);
+  const int32_t *sh = Tt.shell_hkl + (size_t)src_row * Tt.cap_shell * 4;
+  int32_t *dh = T.shell_hkl + (size_t)dst_row * T.cap_shell * 4;
+  for (int i = threadIdx.x; i < ns * 4; i += COPY_THREADS) dh[i] = sh[i];
+  const double *sg = Tt.shell_geo + (size_t)src_row * Tt.cap_shell * Tt.n_pairs_max;
+  double *dg = T.shell_geo + (size_t)dst_row * T.cap_shell * T.n_pairs_max;
+  for (int i = threadIdx.x; i < ns * T.n_pairs_max; i += COPY_THREADS) dg[i] = sg[i];
+  if (threadIdx.x == 0) {
+    T.n_shell[dst_row] = Tt.n_shell[src_row];
+    T.n_refl[dst_row] = Tt.n_refl[src_row];
+    T.n_all[dst_row] = Tt.n_all[src_row];
+    T.status[dst_row] = Tt.status[src_row];
+    if (T.table_of != nullptr) T.table_of[t] = dst_row;
   }
 }
 
@@ -529,7 +770,6 @@ pattern_chi2_kernel(const xrsd_objective_t O, const double *__restrict__ q, int 
 // copied).  The LM loop uses it for accepted steps: the trial pattern and its running totals become the base rows
 // of the resident Jacobian workspace.  Unflagged rows cost one byte read; flagged ones stream at HBM/L2 speed
 // (each CTA copies COPY_CHUNK doubles with 8 independent loads per thread in flight).
-constexpr int COPY_THREADS = 256, COPY_CHUNK = 2048;
 __global__ void __launch_bounds__(COPY_THREADS)
 copy_rows_masked_kernel(double *__restrict__ dst, long long dst_stride, const double *__restrict__ src, long long src_stride,
                         int row_len, int chunks, const uint8_t *__restrict__ mask) {
@@ -648,11 +888,11 @@ extern "C" cudaError_t xrsd_launch_lm_propose(const double *d_params, int ldp, i
                                               const int32_t *ties, const double *tie_coef, int n_tie,
                                               const double *d_JTJ, const double *d_JTr, const double *d_lambda,
                                               const double *d_lo, const double *d_hi, const uint8_t *d_active,
-                                              double *d_trial, cudaStream_t stream) {
+                                              double *d_trial, double max_rel_step, cudaStream_t stream) {
   const FreeSet F = xrsd::make_free_set(nullptr, free_idx, n_free, ties, tie_coef, n_tie);
   if (batch <= 0) return cudaSuccess;
   xrsd::lm_propose_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(d_params, ldp, batch, F, d_JTJ, d_JTr, d_lambda, d_lo, d_hi,
-                                                                   d_active, d_trial);
+                                                                   d_active, d_trial, max_rel_step);
   return cudaGetLastError();
 }
 
@@ -674,6 +914,47 @@ extern "C" cudaError_t xrsd_launch_copy_rows_masked(double *d_dst, long long dst
   if (row_len > 2147483647LL || chunks * n_rows > 2147483647LL) return cudaErrorInvalidConfiguration;
   xrsd::copy_rows_masked_kernel<<<(unsigned)(chunks * n_rows), xrsd::COPY_THREADS, 0, stream>>>(
       d_dst, dst_stride, d_src, src_stride, (int)row_len, (int)chunks, d_mask);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t xrsd_launch_objective_prepare(const xrsd_objective_t *obj, const double *d_q, int n_q, const double *d_Iobs,
+                                                     const double *d_dI, long long ld_obs, int rows, double *d_fo, double *d_w,
+                                                     long long ld_out, cudaStream_t stream) {
+  if (rows <= 0 || n_q <= 0) return cudaSuccess;
+  const dim3 grid((unsigned)rows, (unsigned)std::min(64, (n_q + 255) / 256));
+  xrsd::objective_prepare_kernel<<<grid, 256, 0, stream>>>(*obj, d_q, n_q, d_Iobs, d_dI, ld_obs, rows, d_fo, d_w, ld_out);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t xrsd_launch_lm_trial_update(const xrsd_objective_t *obj, const double *d_q, int n_q, const double *d_I,
+                                                   long long ld_I, int batch, const double *d_Iobs, const double *d_dI,
+                                                   long long ld_obs, double *d_params, int ldp, const double *d_trial,
+                                                   double *d_chi2, double *d_chi2_trial, double *d_lambda, uint8_t *d_active,
+                                                   uint8_t *d_accepted, uint8_t *d_needjac, uint8_t *d_reason, int *d_n_accept,
+                                                   const xrsd_tables_t *trial_tables, int n_xtal, int *d_flags, double up,
+                                                   double down, double ftol, double xtol, double lambda_max, cudaStream_t stream) {
+  if (batch <= 0) return cudaSuccess;
+  static const xrsd_tables_t none = {};
+  xrsd::lm_trial_update_kernel<<<batch, xrsd::CHI2_THREADS, 0, stream>>>(
+      *obj, d_q, n_q, d_I, ld_I, batch, d_Iobs, d_dI, ld_obs, d_params, ldp, d_trial, d_chi2, d_chi2_trial, d_lambda, d_active,
+      d_accepted, d_needjac, d_reason, d_n_accept, trial_tables ? *trial_tables : none, trial_tables ? n_xtal : 0, d_flags, up, down,
+      ftol, xtol, lambda_max);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t xrsd_launch_lm_accept(const uint8_t *d_accepted, int batch, double *d_dst, long long dst_stride,
+                                             const double *d_src, long long src_stride, int n_q, int n_var, int n_pops,
+                                             const xrsd_tables_t *tables, const xrsd_tables_t *trial_tables, int n_xtal,
+                                             cudaStream_t stream) {
+  static const xrsd_tables_t none = {};
+  if (!tables || !trial_tables) n_xtal = 0;
+  const int chunks = (n_q + xrsd::COPY_CHUNK - 1) / xrsd::COPY_CHUNK;
+  const long long per_sys = (d_dst ? (long long)(1 + n_pops) * chunks : 0) + n_xtal;
+  if (batch <= 0 || per_sys <= 0) return cudaSuccess;
+  if (per_sys * batch > 2147483647LL) return cudaErrorInvalidConfiguration;
+  xrsd::lm_accept_kernel<<<(unsigned)(per_sys * batch), xrsd::COPY_THREADS, 0, stream>>>(
+      d_accepted, batch, d_dst, dst_stride, d_src, src_stride, n_q, n_var, n_pops, chunks, tables ? *tables : none,
+      trial_tables ? *trial_tables : none, n_xtal);
   return cudaGetLastError();
 }
 

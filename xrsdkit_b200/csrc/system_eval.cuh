@@ -124,7 +124,9 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
                                   const double *__restrict__ q, int n_q, int q_begin, int q_count,
                                   double *__restrict__ I_sm, double *__restrict__ scratch, int scratch_doubles,
                                   EvalSharedT<HAS_XTAL> *S, const double *__restrict__ prm_topo = nullptr,
-                                  double *__restrict__ cum_out = nullptr, long long cum_stride = 0) {
+                                  double *__restrict__ cum_out = nullptr, long long cum_stride = 0, int only_pop = -1) {
+  // only_pop >= 0: evaluate that population (or the noise model, index 0) alone -- what a finite-difference variant
+  // needs when its parameter belongs to one population: the other terms cancel in the difference.
   // cum_out (optional, global memory): after population ip has been added, the running total of this
   // CTA's span is written to cum_out[ip * cum_stride + i].  The Jacobian uses the differences as the
   // per-population contributions, which give the derivatives of the linear parameters (I0) for free.
@@ -155,6 +157,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
   }
 
   for (int ip = 0; ip < L.n_pops; ++ip) {
+    if (only_pop >= 0 && ip != only_pop) continue;
     const xrsd_pop_t &pop = L.pops[ip];
     __syncthreads();
     bool wrote = false;                // this population stored per-q values for the whole span
@@ -351,7 +354,8 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
       } break;
       // ---------------------------------------------------------------- crystalline
       case XRSD_POP_CRYSTALLINE: if constexpr (HAS_XTAL) {
-        const int t = b * L.n_xtal + pop.table_slot;
+        const int t_own = b * L.n_xtal + pop.table_slot;
+        const int t = T.table_of != nullptr ? T.table_of[t_own] : T.own_base + t_own;      // storage row (xrsd_tables_t)
         const int n_shell = T.n_shell[t];
         if (n_shell <= 0) break;                                   // scattering/__init__.py:277-278
         wrote = true;

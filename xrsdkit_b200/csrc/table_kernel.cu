@@ -38,6 +38,7 @@ struct TableShared {
   int n_all, n_red, n_shell_raw, n_shell;
   int hmin[3], hmax[3];
   int status;
+  int grid_slot;           // >= 0: the candidate grid lives in region grid_slot of T.grid_scratch
   int scan_carry;
   int alive_cnt[3];        // rotating counters of the alive lists (one barrier per operation)
   double max_geo;
@@ -115,6 +116,9 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
   const int slot = t - b * L.n_xtal;
   if (b >= batch) return;
   if (active != nullptr && !active[b]) return;      // converged system of a fit: its table is left as it is
+  // storage row of this table; with shared rows only the CTA that claimed a row (table_key_kernel) builds it
+  if (T.table_of != nullptr && !T.build_flag[t]) return;
+  const int row = T.table_of != nullptr ? T.table_of[t] : T.own_base + t;
   int ipop = -1;
   for (int i = 0; i < L.n_pops; ++i)
     if (L.pops[i].kind == XRSD_POP_CRYSTALLINE && L.pops[i].table_slot == slot) ipop = i;
@@ -161,7 +165,17 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
       S.dim[i] = 2 * S.n[i] - 1;
       cells *= S.dim[i];
     }
-    if (cells > (long long)max_cells) { st |= XRSD_TABLE_GRID_OVERFLOW; cells = 0; }
+    S.grid_slot = -1;
+    if (cells > (long long)max_cells) {
+      // beyond the shared-memory budget: take one of the caller's global-memory regions, if there is one left
+      int gs = -1;
+      if (T.grid_scratch != nullptr && cells <= T.cap_grid_cells && cells < (1LL << 24)) {   // fast_div is exact below 2^24
+        gs = atomicAdd(T.grid_slot_counter, 1);
+        if (gs >= T.n_grid_slots) gs = -1;
+      }
+      if (gs < 0) { st |= XRSD_TABLE_GRID_OVERFLOW; cells = 0; }
+      S.grid_slot = gs;
+    }
     S.cells = (int)cells;
     S.rcp_d0 = 1.0f / (float)S.dim[0];
     S.rcp_d01 = 1.0f / ((float)S.dim[0] * (float)S.dim[1]);
@@ -175,13 +189,18 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
 
   auto finish = [&](int n_shell) {
     if (tid == 0) {
-      T.n_shell[t] = n_shell;
-      T.n_refl[t] = S.n_red;
-      T.n_all[t] = S.n_all;
-      T.status[t] = S.status;
+      T.n_shell[row] = n_shell;
+      T.n_refl[row] = S.n_red;
+      T.n_all[row] = S.n_all;
+      T.status[row] = S.status;
     }
   };
   if (S.status != 0) { finish(0); return; }
+  if (S.grid_slot >= 0)
+    grid = reinterpret_cast<uint16_t *>(T.grid_scratch) + (size_t)S.grid_slot * (size_t)T.cap_grid_cells;
+  // a cubic cell orders its reflections by the integer N = h^2+k^2+l^2 (exact), every other cell by the float |G|:
+  // ties inside a shell then fall in list order, which makes the whole table a function of the passing set alone
+  const bool int_keys = pop.lattice == XRSD_LAT_CUBIC;
 
   // ---- 1. candidates in the shell G_min < |G| <= G_max (scattering/__init__.py:275-276)
   {
@@ -291,7 +310,7 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
   // ---- 3. ordered compaction (l outer, k, h inner = cell order): each thread owns a contiguous
   //         run of cells, one block-wide scan of the per-thread counts gives the output offsets
   {
-    int32_t *out_refl = (T.refl_hkl && T.cap_refl > 0) ? T.refl_hkl + (size_t)t * T.cap_refl * 4 : nullptr;
+    int32_t *out_refl = (T.refl_hkl && T.cap_refl > 0) ? T.refl_hkl + (size_t)row * T.cap_refl * 4 : nullptr;
     const int run = (S.cells + TABLE_THREADS - 1) / TABLE_THREADS;
     const int c_lo = min(tid * run, S.cells), c_hi = min(c_lo + run, S.cells);
     int cnt = 0;
@@ -351,7 +370,7 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
     if (r < n_red) {
       int h, k, l;
       cell_to_hkl(S, list_cell[r], h, k, l);
-      keys[r] = g_norm(S.cell.b, (double)h, (double)k, (double)l);
+      keys[r] = int_keys ? (double)(h * h + k * k + l * l) : g_norm(S.cell.b, (double)h, (double)k, (double)l);
       sidx[r] = r;
     } else {
       keys[r] = INFINITY;
@@ -405,7 +424,7 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
   for (int r0 = 0; r0 < n_red; r0 += TABLE_THREADS) {
     const int r = r0 + tid;
     bool head = false;
-    if (r < n_red) head = (r == 0) || (keys[r] - keys[r - 1] > 8.9e-16 * keys[r]);
+    if (r < n_red) head = (r == 0) || (int_keys ? keys[r] != keys[r - 1] : keys[r] - keys[r - 1] > 8.9e-16 * keys[r]);
     int base;
     const int pos = block_flag_scan(S, head, base) + base;
     if (head && pos < cap_eff) seg_start[pos] = r;
@@ -424,8 +443,8 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
   const int n_raw = S.n_shell_raw;
   const int n_sp = pop.n_species;
   const int n_pairs = n_sp * (n_sp + 1) / 2;
-  int32_t *o_hkl = T.shell_hkl + (size_t)t * T.cap_shell * 4;
-  double *o_geo = T.shell_geo + (size_t)t * T.cap_shell * T.n_pairs_max;
+  int32_t *o_hkl = T.shell_hkl + (size_t)row * T.cap_shell * 4;
+  double *o_geo = T.shell_geo + (size_t)row * T.cap_shell * T.n_pairs_max;
 
   // per-shell geometric weights: sum_members mult * Re(G_a conj G_b)  (scattering/__init__.py:312-331)
   const bool staged = (long long)n_raw * n_pairs <= cap_eff;
@@ -437,6 +456,14 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
     int msum = 0;
     int h0 = 0, k0 = 0, l0 = 0;
     const int r_lo = seg_start[s], r_hi = seg_start[s + 1];
+    // members of a shell in list order (the reference's l, k, h order), whatever the rounding of their |G| was:
+    // the representative hkl and the summation order below do not depend on the cell edge (this thread owns the segment)
+    for (int r = r_lo + 1; r < r_hi; ++r) {
+      const int v = sidx[r];
+      int m = r - 1;
+      while (m >= r_lo && sidx[m] > v) { sidx[m + 1] = sidx[m]; --m; }
+      sidx[m + 1] = v;
+    }
     for (int r = r_lo; r < r_hi; ++r) {
       const int c = list_cell[sidx[r]];
       int h, k, l;
@@ -539,6 +566,51 @@ reflection_table_kernel(const __grid_constant__ xrsd_layout_t L, const double *_
   finish(S.scan_carry);
 }
 
+// One thread per table: which storage row does it use, and does this call have to build it?  (See xrsd_tables_t.)
+__global__ void table_key_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ params, int ldp,
+                                 int batch, const xrsd_tables_t T, const uint8_t *__restrict__ active) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= batch * L.n_xtal) return;
+  const int b = t / L.n_xtal, slot = t - b * L.n_xtal;
+  if (active != nullptr && !active[b]) return;
+  int ipop = -1;
+  for (int i = 0; i < L.n_pops; ++i)
+    if (L.pops[i].kind == XRSD_POP_CRYSTALLINE && L.pops[i].table_slot == slot) ipop = i;
+  if (ipop < 0) return;
+  const xrsd_pop_t &pop = L.pops[ipop];
+  int row = T.own_base + t;
+  uint8_t build = 1;
+  bool shareable = T.n_shared > 0 && T.shared_tag != nullptr && pop.lattice == XRSD_LAT_CUBIC;
+  for (int a = 0; a < pop.n_species; ++a)
+    for (int j = 0; j < 3; ++j) shareable = shareable && pop.p_uvw[a][j] < 0;     // free coordinates enter the weights
+  if (shareable) {
+    Cell cell;
+    make_cell(pop, params + (size_t)b * ldp, &cell);
+    const double bi = cell.b[0][0];
+    const bool diag = bi > 0.0 && cell.b[1][1] == bi && cell.b[2][2] == bi && cell.b[0][1] == 0.0 && cell.b[0][2] == 0.0 &&
+                      cell.b[1][0] == 0.0 && cell.b[1][2] == 0.0 && cell.b[2][0] == 0.0 && cell.b[2][1] == 0.0;
+    // the builder's own limits (scattering/__init__.py:248-268)
+    const double g_max = 1.0 / (2.0 * M_PI / pop.q_max);
+    const double g_min = pop.q_min > 0.0 ? 1.0 / (2.0 * M_PI / pop.q_min) : 0.0;
+    // |G| of (h,k,l) is bi*sqrt(N) to within a few ulp, however it is rounded: N passes `|G| <= g_max` for certain when
+    // N <= (g_max/bi)^2 (1 - 1e-13) and fails for certain above (1 + 1e-13); an integer inside the band is undecidable
+    const double x = g_max / bi, y = g_min / bi;
+    const double nf = x * x, mf = y * y;
+    const double n_lo = floor(nf * (1.0 - 1.0e-13)), n_hi = floor(nf * (1.0 + 1.0e-13));
+    const double m_lo = floor(mf * (1.0 - 1.0e-13)), m_hi = floor(mf * (1.0 + 1.0e-13));
+    if (diag && n_lo == n_hi && m_lo == m_hi && n_lo >= 0.0 && n_lo < (double)T.n_shared && m_lo < 2.0e9) {
+      const int key = (int)n_lo, tag = (int)m_lo + 1;
+      const int old = atomicCAS(&T.shared_tag[key], 0, tag);
+      if (old == 0 || old == tag) {
+        row = T.shared_base + key;
+        build = old == 0;
+      }
+    }
+  }
+  T.table_of[t] = row;
+  T.build_flag[t] = build;
+}
+
 }  // namespace xrsd
 
 extern "C" int64_t xrsd_table_scratch_bytes(int64_t cap_big) { return (int64_t)xrsd::xrsd_scratch_bytes(cap_big); }
@@ -560,6 +632,15 @@ extern "C" cudaError_t xrsd_launch_tables(const xrsd_layout_t *layout, const dou
   if (e != cudaSuccess) return e;
   const int n_tables = batch * layout->n_xtal;
   if (n_tables <= 0) return cudaSuccess;
+  if (tables->grid_scratch != nullptr) {
+    e = cudaMemsetAsync(tables->grid_slot_counter, 0, sizeof(int32_t), stream);
+    if (e != cudaSuccess) return e;
+  }
+  if (tables->table_of != nullptr) {
+    xrsd::table_key_kernel<<<(n_tables + 127) / 128, 128, 0, stream>>>(*layout, d_params, ldp, batch, *tables, d_active);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   xrsd::reflection_table_kernel<<<n_tables, xrsd::TABLE_THREADS, smem, stream>>>(*layout, d_params, ldp, batch, *tables,
                                                                                  max_cells, cap_list, d_active);
   return cudaGetLastError();

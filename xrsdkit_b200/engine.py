@@ -26,40 +26,92 @@ def _torch():
     return torch
 
 
-class TableSet(object):
-    """Device arrays of xrsd_tables_t for batch*n_xtal reflection tables."""
+SMEM_CELLS = 90000            # candidate cells the table builder keeps in shared memory (2 B each, beside its lists)
+GRID_SCRATCH_BYTES = 2 << 30  # global-memory budget for candidate boxes beyond that
 
-    def __init__(self, torch, device, n_tables, cap_shell, n_pairs, cap_refl=0):
+
+class TableStore(object):
+    """Device arrays behind xrsd_tables_t: n_views * n_tables own rows followed by n_shared shared rows
+    (include/xrsd_b200.h).  Views of one store (TableSet) share the shared rows: the accepted and the trial point of
+    a fit are two views, so a table built for one is there for the other."""
+
+    def __init__(self, torch, device, n_tables, cap_shell, n_pairs, cap_refl=0, n_views=1, n_shared=0):
+        self.torch, self.device = torch, device
         self.n_tables, self.cap_shell, self.n_pairs, self.cap_refl = n_tables, cap_shell, n_pairs, cap_refl
+        self.n_views, self.n_shared = n_views, n_shared
+        self.n_rows = n_rows = n_views * n_tables + n_shared
         i32, f64 = torch.int32, torch.float64
-        self.n_shell = torch.zeros(n_tables, dtype=i32, device=device)
-        self.n_refl = torch.zeros(n_tables, dtype=i32, device=device)
-        self.n_all = torch.zeros(n_tables, dtype=i32, device=device)
-        self.status = torch.zeros(n_tables, dtype=i32, device=device)
-        self.shell_hkl = torch.zeros((n_tables, cap_shell, 4), dtype=i32, device=device)
-        self.shell_geo = torch.zeros((n_tables, cap_shell, n_pairs), dtype=f64, device=device)
-        self.refl_hkl = torch.zeros((n_tables, cap_refl, 4), dtype=i32, device=device) if cap_refl else None
-        c = abi.Tables()
-        c.cap_shell, c.cap_refl, c.n_pairs_max = cap_shell, cap_refl, n_pairs
-        c.n_shell, c.n_refl, c.n_all, c.status = (self.n_shell.data_ptr(), self.n_refl.data_ptr(),
-                                                  self.n_all.data_ptr(), self.status.data_ptr())
-        c.shell_hkl, c.shell_geo = self.shell_hkl.data_ptr(), self.shell_geo.data_ptr()
-        c.refl_hkl = self.refl_hkl.data_ptr() if cap_refl else None
-        self.c = c
+        self.n_shell = torch.zeros(n_rows, dtype=i32, device=device)
+        self.n_refl = torch.zeros(n_rows, dtype=i32, device=device)
+        self.n_all = torch.zeros(n_rows, dtype=i32, device=device)
+        self.status = torch.zeros(n_rows, dtype=i32, device=device)
+        self.shell_hkl = torch.zeros((n_rows, cap_shell, 4), dtype=i32, device=device)
+        self.shell_geo = torch.zeros((n_rows, cap_shell, n_pairs), dtype=f64, device=device)
+        self.refl_hkl = torch.zeros((n_rows, cap_refl, 4), dtype=i32, device=device) if cap_refl else None
+        self.shared_tag = torch.zeros(max(1, n_shared), dtype=i32, device=device)
+        self.grid, self.grid_counter, self.grid_slots, self.grid_cells = None, torch.zeros(1, dtype=i32, device=device), 0, 0
+        self.big, self.cap_big, self.cap_list_hint = None, 0, 0
+        self.views = [TableSet(self, k) for k in range(n_views)]
 
-    def take_rows_from(self, other, rows):
-        """Overwrite the tables of the systems flagged in `rows` (bool [n_tables]) with `other`'s, in place (the
-        device pointers in self.c stay valid).  Used by the LM loop: an accepted trial step makes the trial tables
-        the system's tables, so nothing has to be rebuilt.  Returns False when the two sets are not congruent."""
-        if (other.n_tables, other.cap_shell, other.n_pairs) != (self.n_tables, self.cap_shell, self.n_pairs):
-            return False
-        for name in ("n_shell", "n_refl", "n_all", "status"):
-            a, b = getattr(self, name), getattr(other, name)
-            a.copy_(b.where(rows, a))
-        m3 = rows[:, None, None]
-        self.shell_hkl.copy_(other.shell_hkl.where(m3, self.shell_hkl))
-        self.shell_geo.copy_(other.shell_geo.where(m3, self.shell_geo))
-        return True
+    def reset_shared(self):
+        """Forget every shared row: the next build rebuilds the tables it needs."""
+        self.shared_tag.zero_()
+
+    def attach_grid(self, n_slots, cap_cells):
+        self.grid = self.torch.empty(int(n_slots) * int(cap_cells), dtype=self.torch.uint16, device=self.device)
+        self.grid_slots, self.grid_cells = int(n_slots), int(cap_cells)
+        for v in self.views:
+            v._fill()
+
+    def attach_big(self, cap_big, lib):
+        self.big = self.torch.empty(self.n_tables * int(lib.xrsd_table_scratch_bytes(cap_big)), dtype=self.torch.uint8,
+                                    device=self.device)
+        self.cap_big = int(cap_big)
+        for v in self.views:
+            v._fill()
+
+
+class TableSet(object):
+    """One view of a TableStore: batch*n_xtal tables, table t in storage row table_of[t]."""
+
+    def __init__(self, store, k):
+        self.store, self.k = store, k
+        self.n_tables, self.cap_shell, self.n_pairs, self.cap_refl = store.n_tables, store.cap_shell, store.n_pairs, store.cap_refl
+        self.own_base = k * store.n_tables
+        torch = store.torch
+        self.table_of = torch.arange(self.own_base, self.own_base + self.n_tables, dtype=torch.int32, device=store.device)
+        self.build_flag = torch.zeros(max(1, self.n_tables), dtype=torch.uint8, device=store.device)
+        self.c = abi.Tables()
+        self._fill()
+
+    def _fill(self):
+        st, c = self.store, self.c
+        c.cap_shell, c.cap_refl, c.n_pairs_max, c.cap_list_hint = st.cap_shell, st.cap_refl, st.n_pairs, st.cap_list_hint
+        c.n_shell, c.n_refl, c.n_all, c.status = (st.n_shell.data_ptr(), st.n_refl.data_ptr(), st.n_all.data_ptr(),
+                                                  st.status.data_ptr())
+        c.shell_hkl, c.shell_geo = st.shell_hkl.data_ptr(), st.shell_geo.data_ptr()
+        c.refl_hkl = st.refl_hkl.data_ptr() if st.cap_refl else None
+        c.big_scratch, c.cap_big = (st.big.data_ptr(), st.cap_big) if st.big is not None else (None, 0)
+        c.table_of, c.build_flag = self.table_of.data_ptr(), self.build_flag.data_ptr()
+        c.own_base, c.shared_base, c.n_shared = self.own_base, st.n_views * st.n_tables, st.n_shared
+        c.shared_tag = st.shared_tag.data_ptr()
+        c.grid_scratch = st.grid.data_ptr() if st.grid is not None else None
+        c.n_grid_slots, c.cap_grid_cells, c.grid_slot_counter = st.grid_slots, st.grid_cells, st.grid_counter.data_ptr()
+
+    def _rows(self):
+        return self.table_of.long()
+
+    # per-table values, gathered through table_of (checks and tests; the kernels follow table_of themselves)
+    n_shell = property(lambda self: self.store.n_shell[self._rows()])
+    n_refl = property(lambda self: self.store.n_refl[self._rows()])
+    n_all = property(lambda self: self.store.n_all[self._rows()])
+    status = property(lambda self: self.store.status[self._rows()])
+    shell_hkl = property(lambda self: self.store.shell_hkl[self._rows()])
+    shell_geo = property(lambda self: self.store.shell_geo[self._rows()])
+    refl_hkl = property(lambda self: self.store.refl_hkl[self._rows()] if self.store.refl_hkl is not None else None)
+
+    def shared_fraction(self):
+        return float((self.table_of >= self.store.n_views * self.store.n_tables).double().mean().item())
 
 
 class Engine(object):
@@ -93,14 +145,46 @@ class Engine(object):
         return n
 
     # -- reflection tables --------------------------------------------------------------
+    @staticmethod
+    def tables_shareable(layout):
+        """Every crystalline population is cubic and has no atomic coordinates among its parameters: its tables
+        depend on the cell edge only through the integer set of passing shells (xrsd_tables_t)."""
+        pops = layout.crystalline_pops()
+        return bool(pops) and all(p.lattice == abi.LAT_CUBIC and all(p.p_uvw[a][j] < 0 for a in range(p.n_species) for j in range(3))
+                                  for p in pops)
+
+    def new_table_store(self, layout, batch, max_cells, cap_shell=None, export_reflections=False, n_views=1, share=True,
+                        cap_list=0, cap_big=0):
+        has_ops = all(p.use_symmetry and p.n_ops > 0 for p in layout.crystalline_pops())
+        if cap_shell is None:
+            cap_shell = 128 if has_ops else 1024
+        n_shared = 0
+        if share and self.tables_shareable(layout):
+            half = (int(round(float(max_cells) ** (1.0 / 3.0))) + 1) // 2 + 1       # box half-width n: N <= 3 n^2
+            n_shared = min(3 * half * half + 2, 1 << 20)
+        st = TableStore(self.torch, self.device, batch * layout.n_xtal, cap_shell, self._n_pairs(layout),
+                        4096 if export_reflections else 0, n_views, n_shared)
+        st.cap_list_hint = cap_list
+        if cap_big:
+            st.attach_big(cap_big, self.lib)
+        if max_cells > SMEM_CELLS:
+            # boxes beyond shared memory: regions in global memory, as many as the budget allows (shared tables need
+            # one per distinct table, own tables one each)
+            want = st.n_tables if not n_shared else min(st.n_tables, n_shared)
+            st.attach_grid(max(1, min(want, GRID_SCRATCH_BYTES // (2 * int(max_cells)))), int(max_cells))
+        for v in st.views:
+            v._fill()
+        return st
+
     def build_tables(self, layout, d_params, batch, params_host=None, cap_shell=None, export_reflections=False,
-                     max_cells=None, check=True, reuse=None, active=None):
+                     max_cells=None, check=True, reuse=None, active=None, share=True):
         """Build the reflection tables of all crystalline populations for a batch.
 
-        `params_host` (numpy [batch, n_params]) is only used to bound the candidate box when
-        `max_cells` is not given.  With check=True the per-table status is read back (one small
-        device->host copy) and capacity overflows are retried with larger tables.  `reuse` is a
-        TableSet of the same shape to overwrite instead of allocating a new one."""
+        `params_host` (numpy [batch, n_params]) is only used to bound the candidate box when `max_cells` is not
+        given.  With check=True the status words are read back (one small device->host copy) and capacity
+        overflows are retried with larger tables.  `reuse` is a TableSet (a view of a TableStore) to overwrite
+        instead of allocating a new store; its shared rows built by earlier calls stay valid (reset_shared()
+        forgets them).  share=False gives every system its own table even where tables could be shared."""
         if layout.n_xtal == 0:
             return None
         torch = self.torch
@@ -108,51 +192,71 @@ class Engine(object):
             if params_host is None:
                 params_host = d_params.detach().cpu().numpy()
             max_cells = lowering.max_cells(layout, params_host)
-        has_ops = all(p.use_symmetry and p.n_ops > 0 for p in layout.crystalline_pops())
-        if cap_shell is None:
-            cap_shell = 128 if has_ops else 1024
         n_tables = batch * layout.n_xtal
         cap_refl = 4096 if export_reflections else 0
-        cap_list = 0
-        cap_big = 0
+        T = None
+        if reuse is not None and reuse.n_tables == n_tables and reuse.cap_refl == cap_refl and \
+                (cap_shell is None or reuse.cap_shell >= cap_shell) and \
+                (max_cells <= SMEM_CELLS or reuse.store.grid_cells >= max_cells) and (share or reuse.store.n_shared == 0):
+            T = reuse
+        cap_list, cap_big = 0, 0
         while True:
-            if reuse is not None and reuse.n_tables == n_tables and reuse.cap_refl == cap_refl and reuse.cap_shell >= cap_shell:
-                T, cap_shell = reuse, reuse.cap_shell
-            else:
-                T = TableSet(torch, self.device, n_tables, cap_shell, self._n_pairs(layout), cap_refl)
-            reuse = None
-            T.c.cap_list_hint = cap_list
-            if cap_big:
-                T.big = torch.empty(n_tables * int(self.lib.xrsd_table_scratch_bytes(cap_big)), dtype=torch.uint8, device=self.device)
-                T.c.big_scratch, T.c.cap_big = T.big.data_ptr(), cap_big
-            abi.check(self.lib.xrsd_reflection_tables(C.byref(layout.c), d_params.data_ptr(), d_params.shape[1], batch,
-                                                      C.byref(T.c), max_cells,
-                                                      active.data_ptr() if active is not None else None, self._stream()))
-            self.launches += 1
-            if not check:
+            if T is None:
+                k = reuse.k if reuse is not None else 0
+                nv = reuse.store.n_views if reuse is not None else 1
+                T = self.new_table_store(layout, batch, max_cells, cap_shell, export_reflections, nv, share, cap_list, cap_big).views[k]
+            cap_shell = T.cap_shell
+            mask, n_over_prev = active, None
+            while True:
+                abi.check(self.lib.xrsd_reflection_tables(C.byref(layout.c), d_params.data_ptr(), d_params.shape[1], batch,
+                                                          C.byref(T.c), min(int(max_cells), SMEM_CELLS),
+                                                          mask.data_ptr() if mask is not None else None, self._stream()))
+                self.launches += 2
+                if not check:
+                    return T
+                st_t = T.status.view(batch, layout.n_xtal)
+                if active is not None:
+                    st_t = st_t * active.to(torch.int32)[:, None]
+                bits = 0
+                if n_tables and int(st_t.max().item()) != 0:
+                    # OR of the status words (their maximum alone can hide a bit)
+                    flat = st_t.reshape(-1)
+                    seen = torch.stack([((flat & bit) != 0).any() for bit in (1, 2, 4, 8)]).cpu().tolist()
+                    bits = sum(bit for bit, on in zip((1, 2, 4, 8), seen) if on)
+                if bits == abi.TABLE_GRID_OVERFLOW and T.store.grid is not None and T.store.grid_cells >= max_cells:
+                    # more large boxes than global regions: the rest is built in further rounds
+                    over = ((st_t & abi.TABLE_GRID_OVERFLOW) != 0).any(dim=1)
+                    n_over = int(over.sum().item())
+                    if n_over_prev is None or n_over < n_over_prev:
+                        n_over_prev = n_over
+                        mask = over.to(torch.uint8)
+                        if T.store.n_shared:        # a shared row that found no region is claimed again in the next round
+                            base = T.store.n_views * T.store.n_tables
+                            rows = T.table_of.long().view(batch, layout.n_xtal)[over].reshape(-1)
+                            T.store.shared_tag[rows[rows >= base] - base] = 0
+                        continue
+                break
+            if bits == 0:
                 return T
-            st = int(T.status.max().item()) if n_tables else 0
-            if st == 0:
-                return T
-            if st & abi.TABLE_BAD_LATTICE:
+            if bits & abi.TABLE_BAD_LATTICE:
                 raise ValueError("degenerate lattice parameters (cell volume or edge is zero / not finite)")
-            if st & abi.TABLE_GRID_OVERFLOW:
-                raise abi.XrsdError("candidate hkl box exceeds the shared-memory budget (q_max * cell edge too large)")
-            if st & abi.TABLE_LIST_OVERFLOW:
+            if bits & abi.TABLE_GRID_OVERFLOW:
+                raise abi.XrsdError("candidate hkl box of more than %d cells: beyond the table builder's 2^24-cell limit "
+                                    "or the %d-byte global scratch budget" % (int(max_cells), GRID_SCRATCH_BYTES))
+            n_max = int(T.n_all.max().item())
+            if bits & abi.TABLE_LIST_OVERFLOW:
                 if cap_list < 4096:
                     cap_list = 4096
-                    continue
-                if not cap_big and cap_refl == 0:
+                elif not cap_big and cap_refl == 0 and n_max <= (1 << 18):
                     # large cell without usable symmetry: sort / shell arrays of those tables go to global memory
-                    n_max = int(T.n_all.max().item())
                     cap_big = 1 << max(13, (n_max - 1).bit_length())
-                    if cap_big <= (1 << 18):
-                        continue
-                raise abi.XrsdError("reduced reflection list too long (%d reflections in the shell)" % int(T.n_all.max().item()))
-            if st & abi.TABLE_SHELL_OVERFLOW and cap_shell < 65536:
+                else:
+                    raise abi.XrsdError("reduced reflection list too long (%d reflections in the shell)" % n_max)
+            elif bits & abi.TABLE_SHELL_OVERFLOW and cap_shell < 65536:
                 cap_shell *= 4
-                continue
-            raise abi.XrsdError("reflection table build failed with status %d" % st)
+            else:
+                raise abi.XrsdError("reflection table build failed with status %d" % bits)
+            T = None        # new store with the larger capacities
 
     # -- intensity ----------------------------------------------------------------------
     def intensity(self, layout, q, params, tables=None, out=None):
@@ -222,6 +326,23 @@ class Engine(object):
         o.q_lo, o.q_hi = float(q_range[0]), float(q_range[1])
         return o
 
+    def prepare_objective(self, obj, d_q, d_I, d_dI, ld_obs, batch):
+        """(objective marked prepared, f(I_obs) stream, weight stream) for a fit: the per-point logarithm, default
+        error estimate and mask tests of the objective are evaluated once instead of in every launch of the loop
+        (xrsd_objective_prepare).  The streams take the place of I_obs / dI in the residual, Jacobian and chi2 calls."""
+        n_q = d_q.shape[0]
+        rows = batch if ld_obs else 1
+        fo = self.torch.empty((rows, n_q) if ld_obs else (n_q,), dtype=self.torch.float64, device=self.device)
+        w = self.torch.empty_like(fo)
+        abi.check(self.lib.xrsd_objective_prepare(C.byref(obj), d_q.data_ptr(), n_q, d_I.data_ptr(),
+                                                  d_dI.data_ptr() if d_dI is not None else None, ld_obs, rows,
+                                                  fo.data_ptr(), w.data_ptr(), n_q, self._stream()))
+        self.launches += 1
+        op = abi.Objective()
+        C.memmove(C.byref(op), C.byref(obj), C.sizeof(abi.Objective))
+        op.prepared, op.has_dI = 1, 1
+        return op, fo, w
+
     def _obs(self, Iobs, dI, batch, n_q):
         """Device copies of the observed pattern(s) and their error estimates plus the row stride the
         kernels use: 0 when ONE pattern [n_q] is shared by the whole batch, n_q for one row per system.
@@ -249,11 +370,13 @@ class Engine(object):
         """Zero-initialised accumulator / ticket area of xrsd_residual_batch, kept per batch size (the layout
         of the area depends on it; the kernel leaves it zeroed after every launch)."""
         cache = self.__dict__.setdefault("_res_ws", {})
-        if batch not in cache:
-            cache.clear()
-            cache[batch] = self.torch.zeros(int(self.lib.xrsd_residual_workspace_bytes(batch)), dtype=self.torch.uint8,
-                                            device=self.device)
-        return cache[batch]
+        key = (batch, self.torch.cuda.current_stream(self.device).cuda_stream)      # launches on one stream are ordered
+        if key not in cache:
+            if len(cache) >= 8:
+                cache.pop(next(iter(cache)))
+            cache[key] = self.torch.zeros(int(self.lib.xrsd_residual_workspace_bytes(batch)), dtype=self.torch.uint8,
+                                          device=self.device)
+        return cache[key]
 
     def residual(self, layout, obj, q, params, Iobs, dI=None, tables=None, active=None, out=None):
         """chi2[b] of System.evaluate_residual for every parameter set of the batch."""
@@ -265,7 +388,8 @@ class Engine(object):
             d_p = d_p.unsqueeze(0)
         batch, n_q = d_p.shape[0], d_q.shape[0]
         d_I, d_dI, ld = self._obs(Iobs, dI, batch, n_q)
-        obj.has_dI = int(d_dI is not None)
+        if not obj.prepared:
+            obj.has_dI = int(d_dI is not None)
         if layout.n_xtal and tables is None:
             tables = self.build_tables(layout, d_p, batch, params_host=host_params)
         chi2 = out if out is not None else torch.empty(batch, dtype=torch.float64, device=self.device)
@@ -308,7 +432,7 @@ class Engine(object):
             out = (torch.empty((batch, nf, nf), dtype=torch.float64, device=self.device),
                    torch.empty((batch, nf), dtype=torch.float64, device=self.device),
                    torch.empty(batch, dtype=torch.float64, device=self.device))
-        idx = (C.c_int32 * nf)(*free_slots)
+        idx = (C.c_int32 * nf)(*free_slots) if nf else None
         tie_c, coef_c, n_tie = self.tie_array(ties)
         n_q = q.shape[0]
         if resident is not None:
@@ -328,30 +452,29 @@ class Engine(object):
             # HBM scratch for the variant patterns: chunk the batch so it stays under ~4 GB
             chunk = max(1, min(batch, int(4e9 // (8 * (nf + 1 + abi.MAX_POPS) * n_q))))
             need = int(self.lib.xrsd_jacobian_workspace_bytes(n_q, chunk, nf))
-            ws = getattr(self, "_jac_ws", None)
+            # one scratch per stream (launches of one stream are ordered; fits on different streams must not share it)
+            slot = self.__dict__.setdefault("_jac_ws", {}).setdefault(self.torch.cuda.current_stream(self.device).cuda_stream,
+                                                                     {"ws": None, "key": None})
+            ws = slot["ws"]
             if ws is None or ws.numel() < need:
                 ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
-                self._jac_ws = ws
-                self._jac_ws_key = None
-            if self._jac_ws_key != (n_q, chunk, nf):      # ticket area moves with the shape: re-zero it
+                slot["ws"], slot["key"] = ws, None
+            if slot["key"] != (n_q, chunk, nf):      # ticket area moves with the shape: re-zero it
                 ws.zero_()
-                self._jac_ws_key = (n_q, chunk, nf)
+                slot["key"] = (n_q, chunk, nf)
         nx = layout.n_xtal
         for lo in range(0, batch, chunk):
             hi = min(batch, lo + chunk)
             if hi - lo != chunk:
                 ws.zero_()
-                self._jac_ws_key = None
+                if resident is None:
+                    slot["key"] = None
             tc = None
             if tables is not None:
                 tc = abi.Tables()
                 C.memmove(C.byref(tc), C.byref(tables.c), C.sizeof(abi.Tables))
-                tc.n_shell = tables.n_shell.data_ptr() + 4 * lo * nx
-                tc.n_refl = tables.n_refl.data_ptr() + 4 * lo * nx
-                tc.n_all = tables.n_all.data_ptr() + 4 * lo * nx
-                tc.status = tables.status.data_ptr() + 4 * lo * nx
-                tc.shell_hkl = tables.shell_hkl.data_ptr() + 16 * lo * nx * tables.cap_shell
-                tc.shell_geo = tables.shell_geo.data_ptr() + 8 * lo * nx * tables.cap_shell * tables.n_pairs
+                tc.table_of = tables.table_of.data_ptr() + 4 * lo * nx      # rows are absolute: only the index moves
+                tc.build_flag = tables.build_flag.data_ptr() + lo * nx
             abi.check(self.lib.xrsd_jacobian_batch(
                 C.byref(layout.c), C.byref(obj), q.data_ptr(), n_q, d_params[lo:hi].data_ptr(), d_params.shape[1], hi - lo,
                 C.byref(tc) if tc is not None else None,

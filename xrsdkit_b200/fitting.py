@@ -25,13 +25,20 @@ from . import abi, engine as _engine, lowering
 
 
 class FitResult(object):
-    def __init__(self, params, chi2_init, chi2, n_iter, n_accept, active):
+    """params / chi2_init / chi2 / n_accept / active / reason per system.  reason: 0 = stopped by the iteration cap,
+    1 = converged (ftol / xtol), 2 = no acceptable step left (damping beyond lambda_max), 3 = objective not finite."""
+
+    def __init__(self, params, chi2_init, chi2, n_iter, n_accept, active, reason=None):
         self.params, self.chi2_init, self.chi2 = params, chi2_init, chi2
         self.n_iter, self.n_accept, self.active = n_iter, n_accept, active
+        self.reason = reason
 
     @property
     def converged(self):
-        return ~self.active
+        """True where the optimiser stopped on its tolerance (the reference reports lmfit's `success`)."""
+        if self.reason is None:
+            return ~self.active
+        return self.reason == 1
 
 
 def _apply_ties(params, ties):
@@ -42,22 +49,37 @@ def _apply_ties(params, ties):
 
 
 def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weighted=True, logI_weighted=True,
-                 q_range=(0., float('inf')), max_iter=30, ftol=1e-8, lambda0=1e-2, up=8.0, down=4.0,
+                 q_range=(0., float('inf')), max_iter=30, ftol=1e-8, xtol=1e-10, lambda0=1e-2, up=8.0, down=4.0,
                  lambda_max=1e10, rel_step=1e-6, lo=None, hi=None, eng=None, return_device=False, ties=None,
-                 resident_limit=24e9, min_group_rows=2048, table_growth=1.09, loop_cells=None):
+                 resident_limit=24e9, min_group_rows=2048, table_growth=1.09, loop_cells=None, max_rel_step=0.25,
+                 check_every=5, share_tables=True):
     """Fit every row of params0 ([batch, n_params]) to the matching row of Iobs ([batch, n_q] or [n_q]).
 
-    When the pattern slabs of the batch fit in `resident_limit` bytes, the loop keeps them on the device
-    between iterations: the trial evaluation writes its pattern (and per-population running totals) into a second
-    workspace, an accepted step copies those rows over the base rows, and the next Jacobian evaluates only the
-    perturbed variants -- one pattern evaluation per iteration and system less.  A larger batch is fitted in
-    row groups that fit (systems are independent; a group of `min_group_rows` systems or more still fills the
-    GPU many times over); if even such a group does not fit, or no free parameter is linear, the loop
-    re-evaluates the base inside every Jacobian (shared 4 GB scratch).
+    One iteration = one trial step per system; every launch is masked, and nothing but the kernels of
+    include/xrsd_b200.h runs inside the loop:
 
-    Crystalline layouts: the reflection tables of the trial points are built with the candidate box of the current
-    parameters grown by `table_growth` (see the comment at `near_cells` below; `loop_cells` sets the first box
-    explicitly); lattice steps beyond it are turned back and the box follows the accepted parameters.
+        jacobian        (systems whose last step was accepted: variants + reduction -> JTJ, JTr, chi2)
+        lm_propose      (damped solve, relative trust region, projection on the bounds -> trial parameters)
+        tables(trial)   (crystalline layouts; shared tables make this a key lookup after the first iterations)
+        trial pattern   (patterns-only variants launch: pattern + running totals in the trial workspace)
+        lm_trial_update (chi2 of the stored trial pattern, accept / reject, damping, flags)
+        lm_accept       (accepted systems: trial pattern -> base rows, trial tables -> the system's tables)
+
+    A rejected step leaves the parameters, and therefore the Jacobian, as they are: the next iteration only solves
+    again with more damping and evaluates the new trial point.  The host reads one flag word every `check_every`
+    iterations (all converged? a table outgrown?).
+
+    When the pattern slabs of the batch fit in `resident_limit` bytes they stay on the device for the whole fit;
+    a larger batch is fitted in row groups that fit (systems are independent; a group of `min_group_rows` systems
+    or more still fills the GPU many times over); if even such a group does not fit, the loop re-evaluates the
+    base inside every Jacobian (shared 4 GB scratch) and the trial point through the residual kernel.
+
+    Crystalline layouts whose tables cannot be shared build the trial tables with the candidate box of the current
+    parameters grown by `table_growth` (`loop_cells` sets the first box explicitly); lattice steps beyond it are
+    turned back and the box follows the accepted parameters (share_tables=False forces that path for any layout).
+    `max_rel_step` is the relative trust region of a step (see xrsd_lm_propose; on BASELINE config 5 -- start values
+    10 % off -- 0.25 takes the crystal systems from 30 % to 90 % success within 30 iterations,
+    profiles/r02b_fit_quality.json).
 
     Returns a FitResult of device tensors (return_device=True) or numpy arrays."""
     eng = eng or _engine.get_engine()
@@ -73,17 +95,15 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     if nf == 0:
         raise ValueError("no free parameters to fit")
     if nf > abi.MAX_FREE:
-        raise NotImplementedError("at most %d free parameters per system" % abi.MAX_FREE)
+        raise ValueError("at most %d free parameters per system (XRSD_MAX_FREE); this fit has %d" % (abi.MAX_FREE, nf))
     resident_limit = float(os.environ.get("XRSD_LM_RESIDENT_LIMIT", resident_limit))
-    # resident mode: a linear free parameter (an I0) makes "Jacobian with that one parameter" a plain evaluation
-    # of pattern + running totals + chi2, which is what the trial step needs
-    lin_slot = next((s for s in free_slots if eng.jacobian_variants(layout, [s], ties) == 1), None)
     n_rows, n_pts = (int(np.shape(params0)[0]) if np.ndim(params0) == 2 else 1), int(np.shape(q)[0])
+    n_pops = int(layout.c.n_pops)
 
     def resident_bytes(rows):
-        return int(lib.xrsd_jacobian_workspace_bytes(n_pts, rows, nf)) + int(lib.xrsd_jacobian_workspace_bytes(n_pts, rows, 1))
+        return int(lib.xrsd_jacobian_workspace_bytes(n_pts, rows, nf)) + int(lib.xrsd_jacobian_workspace_bytes(n_pts, rows, 0))
 
-    if lin_slot is not None and resident_bytes(n_rows) > resident_limit:
+    if resident_bytes(n_rows) > resident_limit:
         fit_rows = int(resident_limit // (resident_bytes(n_rows) / float(n_rows)))
         if fit_rows >= max(1, min_group_rows):
             n_groups = -(-n_rows // fit_rows)
@@ -95,15 +115,17 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
             parts = [lm_fit_batch(layout, q, rows_of(Iobs, a, min(a + step, n_rows)), params0[a:min(a + step, n_rows)],
                                   free_slots=free_slots, dI=rows_of(dI, a, min(a + step, n_rows)),
                                   error_weighted=error_weighted, logI_weighted=logI_weighted, q_range=q_range,
-                                  max_iter=max_iter, ftol=ftol, lambda0=lambda0, up=up, down=down, lambda_max=lambda_max,
+                                  max_iter=max_iter, ftol=ftol, xtol=xtol, lambda0=lambda0, up=up, down=down, lambda_max=lambda_max,
                                   rel_step=rel_step, lo=rows_of(lo, a, min(a + step, n_rows)),
                                   hi=rows_of(hi, a, min(a + step, n_rows)), eng=eng, return_device=return_device, ties=ties,
                                   resident_limit=resident_limit, min_group_rows=min_group_rows, table_growth=table_growth,
-                                  loop_cells=loop_cells)
+                                  loop_cells=loop_cells, max_rel_step=max_rel_step, check_every=check_every,
+                                  share_tables=share_tables)
                      for a in range(0, n_rows, step)]
             cat = torch.cat if return_device else np.concatenate
             return FitResult(cat([r.params for r in parts]), cat([r.chi2_init for r in parts]), cat([r.chi2 for r in parts]),
-                             max(r.n_iter for r in parts), cat([r.n_accept for r in parts]), cat([r.active for r in parts]))
+                             max(r.n_iter for r in parts), cat([r.n_accept for r in parts]), cat([r.active for r in parts]),
+                             cat([r.reason for r in parts]))
     d_q = eng.to_device(q)
     host_p0 = None if isinstance(params0, torch.Tensor) else np.atleast_2d(np.asarray(params0, dtype=np.float64))
     d_p = eng.to_device(params0 if host_p0 is None else host_p0).clone()
@@ -112,7 +134,8 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     batch, n_q = d_p.shape[0], d_q.shape[0]
     _apply_ties(d_p, ties)                      # lmfit evaluates the expression before the first objective call
     d_I, d_dI, ld_obs = eng._obs(Iobs, dI, batch, n_q)
-    obj = eng.objective(error_weighted, logI_weighted, q_range, has_dI=d_dI is not None)
+    obj_raw = eng.objective(error_weighted, logI_weighted, q_range, has_dI=d_dI is not None)
+    obj, d_fo, d_w = eng.prepare_objective(obj_raw, d_q, d_I, d_dI, ld_obs, batch)      # log / weights / mask once per fit
     blo, bhi = layout.bounds(free_slots)
     if lo is not None:
         blo = np.maximum(blo, lo)
@@ -120,31 +143,43 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         bhi = np.minimum(bhi, hi)
     d_lo = eng.to_device(np.broadcast_to(blo, (batch, nf)).copy())
     d_hi = eng.to_device(np.broadcast_to(bhi, (batch, nf)).copy())
+    u8 = torch.uint8
     d_lambda = torch.full((batch,), float(lambda0), dtype=torch.float64, device=eng.device)
-    d_active = torch.ones(batch, dtype=torch.uint8, device=eng.device)
+    d_active = torch.ones(batch, dtype=u8, device=eng.device)
+    d_needjac = torch.ones(batch, dtype=u8, device=eng.device)
+    d_accepted = torch.zeros(batch, dtype=u8, device=eng.device)
+    d_reason = torch.zeros(batch, dtype=u8, device=eng.device)
     d_nacc = torch.zeros(batch, dtype=torch.int32, device=eng.device)
-    d_trial = torch.empty_like(d_p)
+    d_flags = torch.zeros(2, dtype=torch.int32, device=eng.device)      # [0]: OR of trial-table status words met by the loop
+    d_trial = d_p.clone()
     d_chi2_t = torch.empty(batch, dtype=torch.float64, device=eng.device)
     jout = (torch.empty((batch, nf, nf), dtype=torch.float64, device=eng.device),
             torch.empty((batch, nf), dtype=torch.float64, device=eng.device),
-            torch.empty(batch, dtype=torch.float64, device=eng.device))
+            torch.full((batch,), float('inf'), dtype=torch.float64, device=eng.device))
+    # an I0 that starts at exactly 0 has no derivative in I_pop / I0: such parameters get a finite-difference variant
+    hp = host_p0 if host_p0 is not None else d_p.cpu().numpy()
+    jac_slots = [(-(s + 1) if (eng.jacobian_variants(layout, [s], ties) == 1 and bool(np.any(hp[:, s] == 0.0))) else s)
+                 for s in free_slots]
     idx = (C.c_int32 * nf)(*free_slots)
     # candidate-box bound that holds for the whole fit: lattice edges can grow up to their upper
     # bound or, if unbounded, 1.5x the start
     max_cells = None
+    tables = t_tables = None
+    shareable = False
     if layout.n_xtal:
-        hp = host_p0 if host_p0 is not None else d_p.cpu().numpy()
         grown = hp.copy()
         for j, s in enumerate(free_slots):
             grown[:, s] = np.where(np.isfinite(bhi[j]), np.minimum(bhi[j], 1.5 * np.abs(hp[:, s])), 1.5 * np.abs(hp[:, s]))
         max_cells = max(lowering.max_cells(layout, hp), lowering.max_cells(layout, grown))
-        max_cells = min(max_cells, 90000)
-        # The table kernel's shared memory (2 B per candidate cell) sets its occupancy: sized for 1.5x growth it runs
-        # one CTA per SM, twice as slow as with the box the systems actually need.  In-loop builds therefore use the
-        # box of the current parameters grown by `table_growth`; a trial step that does not fit is turned back like
-        # any bad step (chi2 = inf: lambda grows, the next step is shorter), and when that has happened to an active
-        # system the periodic flag read below re-centres the box on the parameters accepted so far, so a lattice
-        # that really has to grow by more than that does so in stages.
+        shareable = bool(share_tables) and eng.tables_shareable(layout)
+        if not shareable:
+            max_cells = min(max_cells, _engine.SMEM_CELLS)
+        # Tables that cannot be shared are rebuilt for every trial point, and the builder's shared memory (2 B per
+        # candidate cell) sets its occupancy: sized for 1.5x growth it runs one CTA per SM, twice as slow as with the
+        # box the systems actually need.  Those builds therefore use the box of the current parameters grown by
+        # `table_growth`; a trial step that does not fit is turned back like any bad step (chi2 = inf: lambda grows,
+        # the next step is shorter), and when that has happened the periodic flag read below re-centres the box on
+        # the parameters accepted so far, so a lattice that really has to grow by more than that does so in stages.
 
         def near_cells(now):
             near = now.copy()
@@ -152,100 +187,95 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
                 near[:, s] = np.minimum(grown[:, s], float(table_growth) * np.abs(now[:, s]))
             return min(max_cells, max(lowering.max_cells(layout, now), lowering.max_cells(layout, near)))
 
-        loop_cells = near_cells(hp) if loop_cells is None else min(max_cells, int(loop_cells))
-    tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells) if layout.n_xtal else None
-    chi2_init = None
-    t_tables = None
-    res_ws = eng.residual_workspace(batch)
+        if shareable:
+            loop_cells = max_cells
+        else:
+            loop_cells = near_cells(hp) if loop_cells is None else min(max_cells, int(loop_cells))
+        # accepted point and trial point are two views of one store: they share the shared rows
+        store = eng.new_table_store(layout, batch, max_cells, n_views=2, share=shareable)
+        tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=store.views[0], share=shareable)
+        store = tables.store
+        t_tables = store.views[1]
     stream = eng._stream()
     n_iter = 0
-    n_var = eng.jacobian_variants(layout, free_slots, ties)
-    persist = lin_slot is not None and resident_bytes(batch) <= resident_limit
+    n_var = eng.jacobian_variants(layout, jac_slots, ties)
+    persist = resident_bytes(batch) <= resident_limit
     key0, key1 = ("lm", id(d_p), 0), ("lm", id(d_p), 1)
-    # fits on one engine run one after the other: a workspace still registered here was left behind by a fit that
-    # ended in an exception
-    eng.release_resident(*[k for k in getattr(eng, "_jac_resident", {}) if isinstance(k, tuple) and k and k[0] == "lm"])
+    res_ws = None if persist else eng.residual_workspace(batch)
     base_valid = False
     tight = bool(layout.n_xtal) and loop_cells < max_cells
-    grid_seen = torch.zeros((), dtype=torch.int32, device=eng.device)
-    for it in range(max_iter):
-        n_iter = it + 1
-        _, _, d_chi2 = eng.jacobian(layout, obj, d_q, d_p, d_I, d_dI, ld_obs, free_slots, tables, rel_step, out=jout,
-                                    active=d_active if it > 0 else None, ties=ties,
-                                    resident=key0 if persist else None, base_ready=persist and base_valid)
-        base_valid = persist
-        if chi2_init is None:
-            chi2_init = d_chi2.clone()
-        abi.check(lib.xrsd_lm_propose(d_p.data_ptr(), d_p.shape[1], batch, idx, nf, tie_c, coef_c, n_tie, jout[0].data_ptr(), jout[1].data_ptr(),
-                                      d_lambda.data_ptr(), d_lo.data_ptr(), d_hi.data_ptr(), d_active.data_ptr(),
-                                      d_trial.data_ptr(), stream))
-        # in-loop table builds do not read their status back (no host sync); it is checked every 5 iterations
-        first = t_tables is None       # (re)allocation: checked build with the full box, which also sizes the capacities
-        t_tables = eng.build_tables(layout, d_trial, batch, max_cells=max_cells if first or not tight else loop_cells,
-                                    reuse=t_tables, check=first, active=None if first else d_active) if layout.n_xtal else None
-        if persist:     # pattern and running totals of the trial point, kept in the second resident workspace; its chi2
-            eng.jacobian(layout, obj, d_q, d_trial, None, None, 0, [lin_slot], t_tables, rel_step,
-                         active=d_active, ties=ties, resident=key1, patterns_only=True)
-            eng.pattern_chi2(obj, d_q, eng.jacobian_slabs(key1, layout, batch, n_q, 1)[:, 0], d_I, d_dI, ld_obs,
-                             out=d_chi2_t, active=d_active)
-        else:
-            abi.check(lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_trial.data_ptr(),
-                                              d_trial.shape[1], batch, C.byref(t_tables.c) if t_tables is not None else None,
-                                              d_I.data_ptr(), d_dI.data_ptr() if d_dI is not None else None, ld_obs,
-                                              d_chi2_t.data_ptr(), res_ws.data_ptr(), d_active.data_ptr(), stream))
-        if tight and not first:
-            over = ((t_tables.status.view(batch, layout.n_xtal) & abi.TABLE_GRID_OVERFLOW) != 0).any(dim=1) & d_active.bool()
-            d_chi2_t.masked_fill_(over, float('inf'))
-            grid_seen.add_(over.any().to(torch.int32))
-        if layout.n_xtal or persist:
-            nacc_before = d_nacc.clone()
-        abi.check(lib.xrsd_lm_update(d_p.data_ptr(), d_p.shape[1], batch, d_trial.data_ptr(), d_chi2.data_ptr(),
-                                     d_chi2_t.data_ptr(), d_lambda.data_ptr(), d_active.data_ptr(), d_nacc.data_ptr(),
-                                     float(up), float(down), float(ftol), float(lambda_max), stream))
-        eng.launches += 3
-        if persist:
-            # accepted systems now sit at `trial`: the trial pattern and running totals become their base rows
-            eng.take_slab_rows(key0, key1, layout, batch, n_q, n_var, d_nacc != nacc_before)
+    chi2_init = None
+    try:
+        for it in range(max_iter):
+            n_iter = it + 1
+            eng.jacobian(layout, obj, d_q, d_p, d_fo, d_w, ld_obs, jac_slots, tables, rel_step, out=jout, active=d_needjac,
+                         ties=ties, resident=key0 if persist else None, base_ready=persist and base_valid)
+            base_valid = persist
+            if chi2_init is None:
+                chi2_init = jout[2].clone()
+            abi.check(lib.xrsd_lm_propose(d_p.data_ptr(), d_p.shape[1], batch, idx, nf, tie_c, coef_c, n_tie, jout[0].data_ptr(),
+                                          jout[1].data_ptr(), d_lambda.data_ptr(), d_lo.data_ptr(), d_hi.data_ptr(),
+                                          d_active.data_ptr(), d_trial.data_ptr(), float(max_rel_step), stream))
+            if layout.n_xtal:       # in-loop builds do not read their status back; lm_trial_update looks at it on the device
+                eng.build_tables(layout, d_trial, batch, max_cells=loop_cells, reuse=t_tables, check=False, active=d_active)
+            trial_pat, ld_pat = None, 0
+            if persist:     # pattern and running totals of the trial point, kept in the second resident workspace
+                eng.jacobian(layout, obj, d_q, d_trial, None, None, 0, [], t_tables, rel_step, active=d_active, ties=ties,
+                             resident=key1, patterns_only=True)
+                slabs1 = eng.jacobian_slabs(key1, layout, batch, n_q, 1)
+                trial_pat, ld_pat = slabs1.data_ptr(), slabs1.stride(0)
+            else:
+                abi.check(lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_trial.data_ptr(),
+                                                  d_trial.shape[1], batch, C.byref(t_tables.c) if t_tables is not None else None,
+                                                  d_fo.data_ptr(), d_w.data_ptr(), ld_obs, d_chi2_t.data_ptr(), res_ws.data_ptr(),
+                                                  d_active.data_ptr(), stream))
+            abi.check(lib.xrsd_lm_trial_update(C.byref(obj), d_q.data_ptr(), n_q, trial_pat, ld_pat, batch, d_fo.data_ptr(),
+                                               d_w.data_ptr(), ld_obs, d_p.data_ptr(), d_p.shape[1], d_trial.data_ptr(),
+                                               jout[2].data_ptr(), d_chi2_t.data_ptr(), d_lambda.data_ptr(), d_active.data_ptr(),
+                                               d_accepted.data_ptr(), d_needjac.data_ptr(), d_reason.data_ptr(), d_nacc.data_ptr(),
+                                               C.byref(t_tables.c) if t_tables is not None else None, layout.n_xtal,
+                                               d_flags.data_ptr(), float(up), float(down), float(ftol), float(xtol),
+                                               float(lambda_max), stream))
+            if persist or layout.n_xtal:
+                ws0 = eng._jac_resident[key0][0] if persist else None
+                ws1 = eng._jac_resident[key1][0] if persist else None
+                abi.check(lib.xrsd_lm_accept(d_accepted.data_ptr(), batch,
+                                             ws0.data_ptr() if persist else None, (n_var + n_pops) * n_q,
+                                             ws1.data_ptr() if persist else None, (1 + n_pops) * n_q, n_q, n_var, n_pops,
+                                             C.byref(tables.c) if tables is not None else None,
+                                             C.byref(t_tables.c) if t_tables is not None else None, layout.n_xtal, stream))
+            eng.launches += 3 + (0 if persist else 1)
+            if it % check_every == check_every - 1:
+                d_flags[1:2].copy_(d_active.any().to(torch.int32).reshape(1))
+                st_seen, any_active = [int(v) for v in d_flags.cpu().tolist()]      # the only host sync of the loop
+                if st_seen & abi.TABLE_GRID_OVERFLOW and tight:
+                    # an active system proposed a cell beyond the near box and was turned back: re-centre the box
+                    loop_cells = near_cells(d_p.cpu().numpy())
+                    tight = loop_cells < max_cells
+                if st_seen & (abi.TABLE_LIST_OVERFLOW | abi.TABLE_SHELL_OVERFLOW):
+                    # a trial table outgrew the store's capacities (those trial points were turned back): move to a
+                    # larger store -- the checked build of the accepted points grows it further if it has to
+                    store = eng.new_table_store(layout, batch, max_cells, n_views=2, share=shareable,
+                                                cap_shell=store.cap_shell * (4 if st_seen & abi.TABLE_SHELL_OVERFLOW else 1),
+                                                cap_list=4096 if st_seen & abi.TABLE_LIST_OVERFLOW else store.cap_list_hint)
+                    tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=store.views[0], share=shareable)
+                    store = tables.store
+                    t_tables = store.views[1]
+                if st_seen:
+                    d_flags[0:1].zero_()
+                if not any_active:
+                    break
+        # final objective at the accepted parameters (raw objective: the same call a user makes)
         if layout.n_xtal:
-            # ... and their tables are the trial tables -- copy those rows (3 KB per system) instead of building
-            # them again
-            accepted = (d_nacc != nacc_before).repeat_interleave(layout.n_xtal)
-            if not tables.take_rows_from(t_tables, accepted):
-                tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=tables, check=False, active=d_active)
-        if it % 5 == 4:
-            zero = torch.zeros((), dtype=torch.int32, device=eng.device)
-            st_trial = zero if t_tables is None else \
-                ((t_tables.status & ~abi.TABLE_GRID_OVERFLOW) if tight else t_tables.status).max()
-            flags = torch.stack([d_active.any().to(torch.int32), tables.status.max() if tables is not None else zero,
-                                 st_trial, grid_seen])
-            any_active, st_a, st_b, outgrown = [int(v) for v in flags.cpu().tolist()]      # the only host sync of the loop
-            if tight and outgrown:
-                # an active system proposed a cell beyond the near box and was turned back: re-centre the box
-                loop_cells = near_cells(d_p.cpu().numpy())
-                tight = loop_cells < max_cells
-                grid_seen.zero_()
-                t_tables.status.bitwise_and_(~abi.TABLE_GRID_OVERFLOW)
-            if st_a or st_b:
-                # a table outgrew its storage since the last check: rebuild both sets with the checked
-                # (self-growing) path and resynchronise chi2 with the accepted parameters
-                tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells)
-                t_tables = None
-                base_valid = False          # the base rows were evaluated with the overflowed tables
-                d_chi2.copy_(eng.residual(layout, obj, d_q, d_p, d_I, d_dI, tables=tables))
-            if not any_active:
-                break
-    # final objective at the accepted parameters (tables rebuilt for every system: converged ones were
-    # skipped by the masked in-loop builds after their last accepted step)
-    if layout.n_xtal:
-        tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=tables)
-    chi2 = eng.residual(layout, obj, d_q, d_p, d_I, d_dI, tables=tables)
-    if persist:
+            tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=tables, share=shareable)
+        chi2 = eng.residual(layout, obj, d_q, d_p, d_fo, d_w, tables=tables)
+    finally:
         eng.release_resident(key0, key1)
-    res = FitResult(d_p, chi2_init, chi2, n_iter, d_nacc, d_active.bool())
+    res = FitResult(d_p, chi2_init, chi2, n_iter, d_nacc, d_active.bool(), d_reason)
     if return_device:
         return res
     return FitResult(d_p.cpu().numpy(), chi2_init.cpu().numpy(), chi2.cpu().numpy(), n_iter,
-                     d_nacc.cpu().numpy(), d_active.bool().cpu().numpy())
+                     d_nacc.cpu().numpy(), d_active.bool().cpu().numpy(), d_reason.cpu().numpy())
 
 
 def fit_system_inplace(system, q, I, dI=None, method='lm'):
