@@ -461,6 +461,8 @@ def roofline_entry(kernel, k_ms, flops_unit, survey_unit, units, hbm_bytes, fp64
                 "frac": hbm_bytes / (k_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_source": peaks_src,
                 "algorithmic_bytes_per_launch": hbm_bytes},
     }
+    if counts and counts.get("executed"):
+        out["executed"] = counts["executed"]
     if counts:
         out["traffic"] = counts.get("dram_bytes")
         if counts.get("fp64_flops"):
@@ -507,11 +509,12 @@ def dominant_kernel(eng, W, fp64_tflops, probe_ms, peaks, peaks_src):
         finally:
             eng.release_resident(key)
         fl, sv = W.xtal_flops_per_q(lay, W.P, W.q, W.tables)
-        # EXECUTED evaluations: n_var (base + one per non-linear parameter), each a crystalline pattern + Guinier-Porod
-        # (the I0 derivatives are analytic and cost nothing here)
-        return roofline_entry("xrsd::jacobian_variants_kernel<false,true>", k_ms, fl + 80.0, sv + 80.0, B * n_q * W.n_var,
-                              8.0 * B * n_q * (W.n_var + lay.c.n_pops), fp64_tflops, probe_ms, peaks, peaks_src,
-                              ncu_kernel_counts(name))
+        n_x, n_gp = executed_evaluations(lay, W.free)
+        # EXECUTED work per (system, q): the base pattern (crystal + Guinier-Porod) plus one evaluation of ITS population
+        # per non-linear parameter (a, hwhm_g, hwhm_l, r -> crystal; rg -> Guinier-Porod); the I0 derivatives are analytic
+        return roofline_entry("xrsd::jacobian_variants_kernel<false,true>", k_ms, n_x * fl + n_gp * 80.0, n_x * sv + n_gp * 80.0,
+                              B * n_q, 8.0 * B * n_q * (W.n_var + lay.c.n_pops), fp64_tflops, probe_ms, peaks, peaks_src,
+                              dict(ncu_kernel_counts(name) or {}, executed={"crystal_evaluations": n_x, "guinier_porod_evaluations": n_gp}))
     # cfg5: the dominant kernel of the fit is the same variants kernel, on the crystal group's layout
     g = W.groups[1]
     lay, n_q = g.lay, g.n_q
@@ -524,9 +527,26 @@ def dominant_kernel(eng, W, fp64_tflops, probe_ms, peaks, peaks_src):
         eng.release_resident(key)
     n_var = eng.jacobian_variants(lay, g.free)
     fl, sv = W.xtal_flops_per_q(lay, g.P, g.q, [tables])
+    n_x, n_gp = executed_evaluations(lay, g.free)
     return roofline_entry("xrsd::jacobian_variants_kernel<false,true> (crystal group of the fit: %d systems)" % g.B, k_ms,
-                          fl + 80.0, sv + 80.0, g.B * n_q * n_var, 8.0 * g.B * n_q * (n_var + lay.c.n_pops), fp64_tflops,
-                          probe_ms, peaks, peaks_src, ncu_kernel_counts("cfg5"))
+                          n_x * fl + n_gp * 80.0, n_x * sv + n_gp * 80.0, g.B * n_q, 8.0 * g.B * n_q * (n_var + lay.c.n_pops),
+                          fp64_tflops, probe_ms, peaks, peaks_src,
+                          dict(ncu_kernel_counts("cfg5") or {}, executed={"crystal_evaluations": n_x, "guinier_porod_evaluations": n_gp}))
+
+
+def executed_evaluations(lay, free):
+    """(crystalline, Guinier-Porod) population evaluations per system of one variants launch: the base pattern evaluates
+    every population; each non-linear free parameter re-evaluates the one population it belongs to."""
+    n_x, n_gp = 1, 1
+    for slot in free:
+        name = lay.names[slot]
+        if name.endswith("__I0"):
+            continue
+        if name.startswith("x__"):
+            n_x += 1
+        elif name.startswith("gp__"):
+            n_gp += 1
+    return n_x, n_gp
 
 
 def fit_quality(eng, W, nm_rows, with_nm=True):

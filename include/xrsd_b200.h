@@ -336,10 +336,12 @@ int xrsd_peak_profile(int32_t kind, double hwhm_or_hwhm_g, double hwhm_l, const 
  * tools/peak_math.py:87-123 (humpness), tools/__init__.py:83-102 (pearson); the reference calls it
  * after every fit (system/__init__.py:276).  q[n_q] is shared by the batch; pattern b is
  * d_I + b*ld_I; features of pattern b go to d_features + b*ld_features (>= 21 doubles).
- * 8 <= n_q <= XRSD_FEATURE_MAX_Q (the pattern is held in shared memory, 26 bytes per point).
- * Degenerate patterns give NaN features where the reference raises or warns. */
+ * Up to XRSD_FEATURE_MAX_Q points the pattern is held in shared memory (26 bytes per point); longer patterns (up to
+ * XRSD_FEATURE_MAX_Q_GLOBAL) use a stream-ordered global-memory working set inside the call -- same results, slower.
+ * n_q >= 8.  Degenerate patterns give NaN features where the reference raises or warns. */
 #define XRSD_N_FEATURES 21
 #define XRSD_FEATURE_MAX_Q 8192
+#define XRSD_FEATURE_MAX_Q_GLOBAL (1 << 22)
 int xrsd_feature_batch(const double *d_q, int32_t n_q, const double *d_I, int64_t ld_I, int32_t batch,
                        double *d_features, int64_t ld_features, void *stream);
 

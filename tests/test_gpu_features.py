@@ -71,7 +71,7 @@ def test_features_match_reference_outputs():
     print("worst feature error", worst, "reductions", worst_red, "over", len(cases), "patterns")
 
 
-@pytest.mark.parametrize("n", [8, 64, 560, 1001, 1024, 1800, 4096, 8192])   # 1800: dynamic + static smem straddles 48 KB
+@pytest.mark.parametrize("n", [8, 64, 560, 1001, 1024, 1800, 4096, 8192, 8193, 9000, 16384])   # 1800: dynamic + static smem straddles 48 KB; > 8192: global-memory working set
 def test_features_match_oracle_any_length(n):
     from oracle import xrsd_oracle as xo
     from xrsdkit_b200.tools import profiler
@@ -100,7 +100,5 @@ def test_profile_pattern_single_call_returns_reference_keys():
 
 def test_feature_batch_rejects_bad_sizes():
     from xrsdkit_b200.tools import profiler
-    with pytest.raises(ValueError):
-        profiler.profile_batch(np.linspace(0.1, 1, 9000), np.ones((1, 9000)))
     with pytest.raises(ValueError):
         profiler.profile_batch(np.linspace(0.1, 1, 4), np.ones((1, 4)))

@@ -85,8 +85,10 @@ def test_variant_slabs_of_one_population_parameters(eng):
     for v, name, pop in ((1, "x__a", 1), (2, "x__r", 1), (3, "gp__rg", 2)):
         P1 = P.copy()
         P1[:, lay.slot(name)] *= 1 + 1e-6
-        _, parts = eng.intensity_components(lay, d_q, eng.to_device(P1), tables=tables)      # tables held fixed
-        np.testing.assert_allclose(slabs[:, v].cpu().numpy(), parts[:, pop].cpu().numpy(), rtol=1e-12, atol=0)
+        tot, parts = eng.intensity_components(lay, d_q, eng.to_device(P1), tables=tables)      # tables held fixed
+        # (the components are differences of running totals: their absolute error is that of the total)
+        np.testing.assert_allclose(slabs[:, v].cpu().numpy(), parts[:, pop].cpu().numpy(), rtol=1e-12,
+                                   atol=4e-16 * float(tot.max()))
     # reference values: central differences of whole patterns with the tables held fixed
     Ib = eng.intensity(lay, d_q, d_p, tables=tables)
     w = d_I / d_I.sum(dim=1, keepdim=True)              # error_weighted with dI = sqrt(I): weights ~ I_obs, normalised
@@ -209,3 +211,62 @@ def test_fit_that_starts_at_the_optimum_of_exact_data_stops_at_once(eng):
     res = fitting.lm_fit_batch(lay, q, Iobs, truth, free, max_iter=12, eng=eng)      # starts AT the optimum of noiseless data
     assert np.all(res.n_accept == 0) and np.all(res.chi2 == 0.0) and res.converged.all() and res.n_iter <= 5
     np.testing.assert_array_equal(res.params, truth)
+
+
+def test_free_atomic_coordinate_is_fitted(eng):
+    """u_1 of a two-atom cubic cell, freed: the coordinate acts through the reflection tables only, so the default
+    fit (method 'lm') hands such systems to the batched Nelder-Mead mode instead of holding the parameter forever
+    (the finite-difference column of a table parameter is identically zero).  The coordinate must be recovered."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+
+    def V(x, fixed=False):
+        return {"value": x, "fixed": fixed}
+
+    s = System(x=dict(structure="crystalline", form="polyatomic",
+                      settings={"lattice": "P_cubic", "space_group": "Pm-3m", "q_max": 4.5, "n_atoms": 2,
+                                "symbol_0": "Cs", "symbol_1": "Cl", "use_symmetry": False},
+                      parameters=dict(a=V(4.12), hwhm_g=V(0.02), hwhm_l=V(0.01), I0=V(100.0),
+                                      u_1=V(0.5), v_1=V(0.5), w_1=V(0.5))),
+               noise={"model": "flat", "parameters": {"I0": V(0.01)}}, source_wavelength=0.8265617)
+    q = np.linspace(0.8, 4.5, 900)
+    lay = batch.layout_of(s, q)
+    u1, I0 = lay.slot("x__u_1"), lay.slot("x__I0")
+    assert u1 in lay.coordinate_slots()
+    n = 6
+    truth = np.tile(lay.values, (n, 1))
+    truth[:, u1] = np.linspace(0.40, 0.47, n)
+    Iobs = batch.compute_intensity_batch(lay, q, truth)
+    start = truth.copy()
+    start[:, u1] += 0.02
+    start[:, I0] *= 1.1
+    res = batch.fit_batch(lay, q, Iobs, start, free_slots=[u1, I0])
+    assert np.all(res.chi2 < 1e-4 * res.chi2_init), res.chi2 / res.chi2_init
+    np.testing.assert_allclose(res.params[:, u1], truth[:, u1], atol=2e-4)
+    np.testing.assert_allclose(res.params[:, I0], truth[:, I0], rtol=2e-3)
+
+
+def test_layout_refuses_another_q_grid(eng):
+    """A layout carries state of the grid it was lowered for (q_step, q0_is_zero, the q[-1] fallback of q_max): the
+    engine refuses a different grid instead of evaluating it with the wrong assumptions."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg2_system(System)
+    q = np.linspace(0.01, 0.5, 512)
+    lay = batch.layout_of(s, q)
+    P = cfg2_params(lay, 2)
+    batch.compute_intensity_batch(lay, q, P)
+    batch.compute_intensity_batch(lay, eng.to_device(q), P, device_out=True)
+    for other in (np.linspace(0.01, 0.5, 513), np.linspace(0.01, 0.6, 512), np.sort(np.random.RandomState(0).uniform(0.01, 0.5, 512))):
+        with pytest.raises(ValueError, match="another q grid"):
+            batch.compute_intensity_batch(lay, other, P)
+        with pytest.raises(ValueError, match="another q grid"):
+            batch.evaluate_residual_batch(lay, eng.to_device(other), np.ones((2, 512)), P)
+    # a layout lowered for a non-uniform grid makes no assumption about spacing: any grid with the same flags is fine
+    qn = np.sort(np.random.RandomState(1).uniform(0.01, 0.5, 300))
+    layn = batch.layout_of(s, qn)
+    a = batch.compute_intensity_batch(layn, q, P)
+    b = batch.compute_intensity_batch(lay, q, P)
+    np.testing.assert_allclose(a, b, rtol=1e-12)
+    with pytest.raises(ValueError, match="another q grid"):
+        batch.compute_intensity_batch(layn, np.linspace(0.0, 0.5, 100), P)          # q[0] == 0 changes q0_is_zero

@@ -388,7 +388,7 @@ def test_components_in_one_launch(golden_systems, eng):
         s = System(**m["system"])
         n0 = eng.launches
         parts = s.compute_intensity_components(q)
-        assert eng.launches - n0 <= 2
+        assert eng.launches - n0 <= 3          # (table key + table build) + one evaluation launch
         err, same = rel_err(parts["total"], arr[m["key"] + "_I"])
         assert same and err <= TOL_F64, m["name"]
         scale = np.nanmax(np.abs(arr[m["key"] + "_I"]))

@@ -150,7 +150,7 @@ def test_large_cells_at_default_settings_against_golden(eng):
                                       "hwhm_l": {"value": 2e-3}}), source_wavelength=0.8265617)
         assert s.populations["x"].settings["q_max"] == 1.0
         lay = lowering.lower_system(s, q)
-        T = eng.build_tables(lay, eng.to_device(lay.values[None, :]), 1, params_host=lay.values[None, :], export_reflections=True)
+        T = eng.build_tables(lay, eng.to_device(lay.values[None, :]), 1, params_host=lay.values[None, :], export_reflections=8192)
         assert T.store.grid is not None                                    # the box did not fit in shared memory
         n = int(T.n_refl[0].item())
         got = T.refl_hkl[0, :n].cpu().numpy()

@@ -501,8 +501,8 @@ int xrsd_feature_batch(const double *d_q, int32_t n_q, const double *d_I, int64_
   if (batch < 0) return fail(XRSD_EINVAL, "batch %d", batch);
   if (batch == 0) return XRSD_OK;
   if (!d_q || !d_I || !d_features) return fail(XRSD_EINVAL, "NULL pointer");
-  if (n_q < 8 || n_q > XRSD_FEATURE_MAX_Q)
-    return fail(XRSD_EINVAL, "n_q %d outside [8, %d]", n_q, XRSD_FEATURE_MAX_Q);
+  if (n_q < 8 || n_q > XRSD_FEATURE_MAX_Q_GLOBAL)
+    return fail(XRSD_EINVAL, "n_q %d outside [8, %d]", n_q, XRSD_FEATURE_MAX_Q_GLOBAL);
   if (ld_I < n_q || ld_features < XRSD_N_FEATURES) return fail(XRSD_EINVAL, "leading dimension too small");
   cudaError_t e = xrsd_launch_features(d_q, n_q, d_I, ld_I, batch, d_features, ld_features, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "feature_kernel");

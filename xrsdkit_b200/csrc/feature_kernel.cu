@@ -90,13 +90,18 @@ __device__ __forceinline__ double vertex_of(const Parabola &p) { return p.xbar -
 
 }  // namespace
 
+// IdxT: uint16 positions while the pattern fits in shared memory (n <= XRSD_FEATURE_MAX_Q); longer patterns keep the
+// same four arrays in a per-CTA region of global memory (`work`, L2-resident for the sizes met in practice) with 32-bit
+// positions -- same code, same results, slower.
+template <typename IdxT>
 __global__ void __launch_bounds__(512, 2)     // 64 registers: two CTAs per SM up to 4096 q-points (measured +19 %)
 feature_kernel(const double *__restrict__ q, int n, const double *__restrict__ I_all, int64_t ld_I, int batch,
-               double *__restrict__ feat, int64_t ld_f) {
+               double *__restrict__ feat, int64_t ld_f, double *__restrict__ work, size_t work_stride) {
   extern __shared__ __align__(16) double smem[];
   const size_t n_al = ((size_t)n + 1) & ~(size_t)1;      // regions start on 16-byte boundaries (double2 views)
-  double *I_s = smem, *A_s = smem + n_al, *B_s = smem + 2 * n_al;
-  unsigned short *idx_s = reinterpret_cast<unsigned short *>(smem + 3 * n_al);
+  double *base = work != nullptr ? work + (size_t)blockIdx.x * work_stride : smem;
+  double *I_s = base, *A_s = base + n_al, *B_s = base + 2 * n_al;
+  IdxT *idx_s = reinterpret_cast<IdxT *>(base + 3 * n_al);
   __shared__ RedScratch R;
   __shared__ int m_sh;
   const int tid = threadIdx.x, NT = blockDim.x;
@@ -261,7 +266,7 @@ feature_kernel(const double *__restrict__ q, int n, const double *__restrict__ I
       if (tid == NT - 1) m_sh = base + inc;
       int pos = base + inc - cnt;
       for (int i = lo; i < hi; ++i)
-        if (I_s[i] > 0.0) idx_s[pos++] = (unsigned short)i;
+        if (I_s[i] > 0.0) idx_s[pos++] = (IdxT)i;
       (void)nw;
       __syncthreads();
     }
@@ -418,15 +423,28 @@ extern "C" size_t xrsd_feature_smem_bytes_impl(int n_q) { return (((size_t)n_q +
 
 extern "C" cudaError_t xrsd_launch_features(const double *d_q, int n_q, const double *d_I, int64_t ld_I, int batch,
                                  double *d_feat, int64_t ld_f, cudaStream_t stream) {
-  const size_t smem = xrsd_feature_smem_bytes_impl(n_q);
-  // opt in on every launch: the attribute is per device and static shared memory counts against the 48 KB default too
-  cudaError_t e = cudaFuncSetAttribute(feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const int threads = n_q >= 2048 ? 512 : 256;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = batch < sms * 16 ? batch : sms * 16;
-  feature_kernel<<<grid, threads, smem, stream>>>(d_q, n_q, d_I, ld_I, batch, d_feat, ld_f);
-  return cudaGetLastError();
+  if (n_q <= XRSD_FEATURE_MAX_Q) {
+    const size_t smem = xrsd_feature_smem_bytes_impl(n_q);
+    // opt in on every launch: the attribute is per device and static shared memory counts against the 48 KB default too
+    cudaError_t e = cudaFuncSetAttribute(feature_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int threads = n_q >= 2048 ? 512 : 256;
+    const int grid = batch < sms * 16 ? batch : sms * 16;
+    feature_kernel<unsigned short><<<grid, threads, smem, stream>>>(d_q, n_q, d_I, ld_I, batch, d_feat, ld_f, nullptr, 0);
+    return cudaGetLastError();
+  }
+  // patterns beyond the shared-memory limit: the working set of every CTA in a stream-ordered global allocation
+  const size_t n_al = ((size_t)n_q + 1) & ~(size_t)1;
+  const size_t stride = 3 * n_al + (((size_t)n_q * sizeof(unsigned) + 15) / 16) * 2;       // doubles, 16-byte multiple
+  const int grid = batch < sms * 2 ? batch : sms * 2;
+  double *work = nullptr;
+  cudaError_t e = cudaMallocAsync((void **)&work, stride * sizeof(double) * (size_t)grid, stream);
+  if (e != cudaSuccess) return e;
+  feature_kernel<unsigned><<<grid, 512, 0, stream>>>(d_q, n_q, d_I, ld_I, batch, d_feat, ld_f, work, stride);
+  e = cudaGetLastError();
+  const cudaError_t e2 = cudaFreeAsync(work, stream);
+  return e != cudaSuccess ? e : e2;
 }

@@ -508,8 +508,9 @@ __global__ void lm_propose_kernel(const double *__restrict__ params, int ldp, in
       // relative trust region: one step changes a parameter by at most max_rel_step of its magnitude (a damped
       // Gauss-Newton step far outside the linear range -- a peak width grown 100x -- costs a whole-pattern
       // evaluation in the slow regime of the profile sum and is rejected anyway)
-      const double cap = max_rel_step * fmax(fabs(p[F.idx[j]]), 1.0e-300);
-      dj = fmin(fmax(dj, -cap), cap);
+      // (a parameter sitting at exactly 0 has no scale of its own: its first step is free)
+      const double cap = max_rel_step * fabs(p[F.idx[j]]);
+      if (cap > 0.0) dj = fmin(fmax(dj, -cap), cap);
     }
     double v = p[F.idx[j]] + dj;
     const double l = lo[(size_t)b * nf + j], h = hi[(size_t)b * nf + j];

@@ -138,6 +138,23 @@ class Engine(object):
             a = a.copy()
         return torch.from_numpy(a).to(self.device)
 
+    def check_grid(self, layout, q):
+        """The q passed with a layout must be the grid the layout was lowered for (SystemLayout.check_grid).  Host
+        arrays are checked on every call; a device tensor is read back once and remembered by address and version."""
+        if getattr(layout, "grid", None) is None:
+            return
+        if isinstance(q, self.torch.Tensor):
+            seen = layout.__dict__.setdefault("_grid_ok", set())
+            key = (q.data_ptr(), q.numel(), q._version)
+            if key in seen:
+                return
+            layout.check_grid(q.detach().cpu().numpy())
+            if len(seen) > 64:
+                seen.clear()
+            seen.add(key)
+        else:
+            layout.check_grid(np.asarray(q, dtype=np.float64))
+
     def _n_pairs(self, layout):
         n = 1
         for p in layout.crystalline_pops():
@@ -153,6 +170,13 @@ class Engine(object):
         return bool(pops) and all(p.lattice == abi.LAT_CUBIC and all(p.p_uvw[a][j] < 0 for a in range(p.n_species) for j in range(3))
                                   for p in pops)
 
+    @staticmethod
+    def _cap_refl(export_reflections):
+        """rows of refl_hkl per table: 0 (no export), 4096 (True) or the number given"""
+        if not export_reflections:
+            return 0
+        return 4096 if export_reflections is True else int(export_reflections)
+
     def new_table_store(self, layout, batch, max_cells, cap_shell=None, export_reflections=False, n_views=1, share=True,
                         cap_list=0, cap_big=0):
         has_ops = all(p.use_symmetry and p.n_ops > 0 for p in layout.crystalline_pops())
@@ -163,7 +187,7 @@ class Engine(object):
             half = (int(round(float(max_cells) ** (1.0 / 3.0))) + 1) // 2 + 1       # box half-width n: N <= 3 n^2
             n_shared = min(3 * half * half + 2, 1 << 20)
         st = TableStore(self.torch, self.device, batch * layout.n_xtal, cap_shell, self._n_pairs(layout),
-                        4096 if export_reflections else 0, n_views, n_shared)
+                        self._cap_refl(export_reflections), n_views, n_shared)
         st.cap_list_hint = cap_list
         if cap_big:
             st.attach_big(cap_big, self.lib)
@@ -184,7 +208,8 @@ class Engine(object):
         given.  With check=True the status words are read back (one small device->host copy) and capacity
         overflows are retried with larger tables.  `reuse` is a TableSet (a view of a TableStore) to overwrite
         instead of allocating a new store; its shared rows built by earlier calls stay valid (reset_shared()
-        forgets them).  share=False gives every system its own table even where tables could be shared."""
+        forgets them).  export_reflections (True = up to 4096 per table, or a number) also writes the reference's
+        reduced hkl list and multiplicities (refl_hkl), for parity checks.  share=False gives every system its own table even where tables could be shared."""
         if layout.n_xtal == 0:
             return None
         torch = self.torch
@@ -193,7 +218,7 @@ class Engine(object):
                 params_host = d_params.detach().cpu().numpy()
             max_cells = lowering.max_cells(layout, params_host)
         n_tables = batch * layout.n_xtal
-        cap_refl = 4096 if export_reflections else 0
+        cap_refl = self._cap_refl(export_reflections)
         T = None
         if reuse is not None and reuse.n_tables == n_tables and reuse.cap_refl == cap_refl and \
                 (cap_shell is None or reuse.cap_shell >= cap_shell) and \
@@ -247,7 +272,7 @@ class Engine(object):
             if bits & abi.TABLE_LIST_OVERFLOW:
                 if cap_list < 4096:
                     cap_list = 4096
-                elif not cap_big and cap_refl == 0 and n_max <= (1 << 18):
+                elif not cap_big and n_max <= (1 << 18):
                     # large cell without usable symmetry: sort / shell arrays of those tables go to global memory
                     cap_big = 1 << max(13, (n_max - 1).bit_length())
                 else:
@@ -262,6 +287,7 @@ class Engine(object):
     def intensity(self, layout, q, params, tables=None, out=None):
         """I[b, :] on the device.  q: [n_q]; params: [batch, n_params] (numpy or cuda tensors)."""
         torch = self.torch
+        self.check_grid(layout, q)
         d_q = self.to_device(q)
         host_params = None if isinstance(params, torch.Tensor) else np.atleast_2d(np.asarray(params, dtype=np.float64))
         d_p = self.to_device(params if host_params is None else host_params)
@@ -282,6 +308,7 @@ class Engine(object):
         """(I[b, :], parts[b, n_pops, :]) where parts[:, 0] is the noise term and parts[:, k] population k
         (layout order), all from one launch."""
         torch = self.torch
+        self.check_grid(layout, q)
         d_q = self.to_device(q)
         host_params = None if isinstance(params, torch.Tensor) else np.atleast_2d(np.asarray(params, dtype=np.float64))
         d_p = self.to_device(params if host_params is None else host_params)
@@ -381,6 +408,7 @@ class Engine(object):
     def residual(self, layout, obj, q, params, Iobs, dI=None, tables=None, active=None, out=None):
         """chi2[b] of System.evaluate_residual for every parameter set of the batch."""
         torch = self.torch
+        self.check_grid(layout, q)
         d_q = self.to_device(q)
         host_params = None if isinstance(params, torch.Tensor) else np.atleast_2d(np.asarray(params, dtype=np.float64))
         d_p = self.to_device(params if host_params is None else host_params)
@@ -424,6 +452,7 @@ class Engine(object):
         written to `out`; Iobs_dev may be None): with one linear free parameter that is the pattern and the running
         totals of every active system."""
         torch = self.torch
+        self.check_grid(layout, q)
         batch, nf = d_params.shape[0], len(free_slots)
         if patterns_only and (resident is None or base_ready):
             raise ValueError("patterns_only needs a resident workspace (and excludes base_ready)")

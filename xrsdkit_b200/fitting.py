@@ -96,6 +96,13 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         raise ValueError("no free parameters to fit")
     if nf > abi.MAX_FREE:
         raise ValueError("at most %d free parameters per system (XRSD_MAX_FREE); this fit has %d" % (abi.MAX_FREE, nf))
+    if layout.coordinate_slots() & set(free_slots):
+        # Free atomic coordinates (u_i, v_i, w_i of a polyatomic cell) act through the reflection tables, which the
+        # Jacobian variants hold fixed: their finite-difference columns would be identically zero and LM
+        # would never move them.  Such fits go to the batched Nelder-Mead mode, which rebuilds the tables for every
+        # evaluation -- the reference's own optimiser.
+        return nm_fit_batch(layout, q, Iobs, params0, free_slots=free_slots, dI=dI, error_weighted=error_weighted,
+                            logI_weighted=logI_weighted, q_range=q_range, eng=eng, return_device=return_device, ties=ties)
     resident_limit = float(os.environ.get("XRSD_LM_RESIDENT_LIMIT", resident_limit))
     n_rows, n_pts = (int(np.shape(params0)[0]) if np.ndim(params0) == 2 else 1), int(np.shape(q)[0])
     n_pops = int(layout.c.n_pops)
@@ -457,8 +464,9 @@ def nm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     p[:, fidx] = tr.to_external(ub)
     _apply_ties(p, ties)
     chi2 = F[rows, best]
-    res = FitResult(p, chi2_init, chi2, n_iter, torch.full((batch,), state['n_eval'], dtype=torch.int32, device=eng.device), ~done)
+    res = FitResult(p, chi2_init, chi2, n_iter, torch.full((batch,), state['n_eval'], dtype=torch.int32, device=eng.device), ~done,
+                    done.to(torch.uint8))
     if return_device:
         return res
     return FitResult(p.cpu().numpy(), chi2_init.cpu().numpy(), chi2.cpu().numpy(), n_iter, res.n_accept.cpu().numpy(),
-                     (~done).cpu().numpy())
+                     (~done).cpu().numpy(), done.to(torch.uint8).cpu().numpy())

@@ -52,6 +52,24 @@ class SystemLayout(object):
         self.records = records        # the parameter dicts (shared with the System, like flatten_params)
         self.n_params = len(names)
         self.n_xtal = c_layout.n_xtal
+        self.grid = None              # fingerprint of the q grid the layout was lowered for (set by lower_system)
+
+    def check_grid(self, q):
+        """Raise ValueError when `q` (numpy) is not the grid this layout was lowered for, in a way that matters: the
+        layout carries q_step (> 0: the kernels advance phases along a uniform grid and skip the ordering test),
+        q0_is_zero (the only zero the reference special-cases) and, for crystalline populations without an explicit
+        q_max, q[-1] (scattering/__init__.py:226)."""
+        g = self.grid
+        if g is None or len(q) == 0:
+            return
+        if g['q_step'] > 0.0:
+            same = len(q) == g['n'] and q[0] == g['q0'] and q[-1] == g['q_last'] and uniform_step(q) == g['q_step']
+        else:
+            same = bool(q[0] == 0) == g['q0_is_zero'] and \
+                (not g['uses_q_last'] or q[-1] == g['q_last'])
+        if not same:
+            raise ValueError("this layout was lowered for another q grid (%d points from %g to %g); lower the system again "
+                             "for the grid in use (batch.layout_of(system, q))" % (g['n'], g['q0'], g['q_last']))
 
     def slot(self, key):
         return self.names.index(key)
@@ -87,6 +105,17 @@ class SystemLayout(object):
         lo = np.array([-np.inf if self.records[i]['bounds'][0] is None else self.records[i]['bounds'][0] for i in slots], float)
         hi = np.array([np.inf if self.records[i]['bounds'][1] is None else self.records[i]['bounds'][1] for i in slots], float)
         return lo, hi
+
+    def coordinate_slots(self):
+        """Slots of the atomic coordinates u_i, v_i, w_i of polyatomic crystalline populations: they enter the
+        reflection tables (structure-factor phases), not the per-q evaluation."""
+        out = set()
+        for p in self.crystalline_pops():
+            for a in range(p.n_species):
+                for j in range(3):
+                    if p.p_uvw[a][j] >= 0:
+                        out.add(int(p.p_uvw[a][j]))
+        return out
 
     def crystalline_pops(self):
         return [p for p in self.c.pops[:self.c.n_pops] if p.kind == abi.POP_CRYSTALLINE]
@@ -341,7 +370,11 @@ def lower_system(system, q):
         L.pops[i] = p
     if not names:
         names, values, records = ['_unused'], [0.0], [dict(value=0.0, fixed=True, bounds=[None, None], constraint_expr=None)]
-    return SystemLayout(L, names, np.array(values, dtype=float), records)
+    lay = SystemLayout(L, names, np.array(values, dtype=float), records)
+    uses_q_last = any(not pop.settings.get('q_max') for pop in system.populations.values() if pop.structure == 'crystalline')
+    lay.grid = dict(n=len(q), q0=float(q[0]) if len(q) else 0.0, q_last=float(q[-1]) if len(q) else 0.0,
+                    q_step=float(L.q_step), q0_is_zero=bool(L.q0_is_zero), uses_q_last=bool(uses_q_last))
+    return lay
 
 
 class _Shell(object):
