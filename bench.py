@@ -437,12 +437,16 @@ class Work(object):
         return 60.0 * n_near + 17.0 * 60.0 * (ns - n_near) / 128.0 + 2.0 * 17.0 + 150.0, 205.0 * ns + 150.0
 
 
-def ncu_kernel_counts(workload):
+def ncu_kernel_counts(workload, batch=10000):
     """Per-launch figures of the dominant kernel from the committed ncu capture of this round (profiles/): DRAM
-    traffic and the FP64 thread-instruction counts (2 flop per DFMA, 1 per DADD / DMUL); None when absent."""
+    traffic and the FP64 thread-instruction counts (2 flop per DFMA, 1 per DADD / DMUL).  The captures were taken at
+    10^4 systems per launch: None for any other launch shape, or when the file is absent."""
     try:
         with open(os.path.join(ROOT, "profiles", "r02_ncu_counts.json")) as f:
-            return json.load(f).get(workload)
+            rec = json.load(f).get(workload)
+        if rec is None or batch != 10000:
+            return None
+        return {k: v for k, v in rec.items() if k != "all"}
     except Exception:
         return None
 
@@ -499,7 +503,7 @@ def dominant_kernel(eng, W, fp64_tflops, probe_ms, peaks, peaks_src):
         else:
             fl, sv = W.xtal_flops_per_q(lay, W.P, W.q, W.tables)
         return roofline_entry("xrsd::intensity_kernel<2,false,%s>" % ("true" if lay.n_xtal else "false"), k_ms, fl, sv,
-                              B * n_q, 8.0 * B * n_q, fp64_tflops, probe_ms, peaks, peaks_src, ncu_kernel_counts(name))
+                              B * n_q, 8.0 * B * n_q, fp64_tflops, probe_ms, peaks, peaks_src, ncu_kernel_counts(name, B))
     if name == "cfg4":
         lay, n_q = W.lay, W.n_q
         key = ("bench", id(W))
@@ -514,7 +518,7 @@ def dominant_kernel(eng, W, fp64_tflops, probe_ms, peaks, peaks_src):
         # per non-linear parameter (a, hwhm_g, hwhm_l, r -> crystal; rg -> Guinier-Porod); the I0 derivatives are analytic
         return roofline_entry("xrsd::jacobian_variants_kernel<false,true>", k_ms, n_x * fl + n_gp * 80.0, n_x * sv + n_gp * 80.0,
                               B * n_q, 8.0 * B * n_q * (W.n_var + lay.c.n_pops), fp64_tflops, probe_ms, peaks, peaks_src,
-                              dict(ncu_kernel_counts(name) or {}, executed={"crystal_evaluations": n_x, "guinier_porod_evaluations": n_gp}))
+                              dict(ncu_kernel_counts(name, B) or {}, executed={"crystal_evaluations": n_x, "guinier_porod_evaluations": n_gp}))
     # cfg5: the dominant kernel of the fit is the same variants kernel, on the crystal group's layout
     g = W.groups[1]
     lay, n_q = g.lay, g.n_q
@@ -531,7 +535,7 @@ def dominant_kernel(eng, W, fp64_tflops, probe_ms, peaks, peaks_src):
     return roofline_entry("xrsd::jacobian_variants_kernel<false,true> (crystal group of the fit: %d systems)" % g.B, k_ms,
                           n_x * fl + n_gp * 80.0, n_x * sv + n_gp * 80.0, g.B * n_q, 8.0 * g.B * n_q * (n_var + lay.c.n_pops),
                           fp64_tflops, probe_ms, peaks, peaks_src,
-                          dict(ncu_kernel_counts("cfg5") or {}, executed={"crystal_evaluations": n_x, "guinier_porod_evaluations": n_gp}))
+                          dict(ncu_kernel_counts("cfg5", g.B) or {}, executed={"crystal_evaluations": n_x, "guinier_porod_evaluations": n_gp}))
 
 
 def executed_evaluations(lay, free):

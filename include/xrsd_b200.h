@@ -224,8 +224,10 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
  * it; zeroing the whole workspace once is the simple way).  ties[n_tie][2] (HOST, may be NULL) are
  * constraints (dst slot, src slot) with tie_coef[n_tie][2] = (scale, offset) (HOST; NULL = identity):
  * params[dst] = scale * params[src] + offset -- constraint_expr values that are affine in one other
- * parameter (xrsdkit's own fitted systems use the plain name, "particle__r"); the tied slot follows
- * its source in every variant.  Reflection tables
+ * parameter (xrsdkit's own fitted systems use the plain name, "particle__r"); a dst given as -(slot + 1)
+ * ADDS its term to the slot instead (params[slot] += scale * params[src] + offset), so a linear combination of
+ * several parameters is a plain term followed by accumulating ones; terms are applied in order and the tied
+ * slot follows its sources in every variant.  Reflection tables
  * and the radius counts of size quadratures are held fixed inside one evaluation. */
 int64_t xrsd_jacobian_workspace_bytes(int32_t n_q, int32_t batch, int32_t n_free);
 int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj,

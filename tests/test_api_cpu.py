@@ -177,3 +177,38 @@ def test_affine_constraint_expressions_are_parsed_and_others_rejected():
                  "particle__r +", "particle__r if 1 else 2"):
         with pytest.raises(NotImplementedError):
             lowering.parse_affine_constraint(expr, names)
+
+
+def test_linear_combination_constraints_lower_to_ordered_terms():
+    """constraint_expr linear in SEVERAL parameters: parse_linear_constraint gives exact coefficients, and
+    SystemLayout.ties() lowers them to the ordered terms of xrsd_jacobian_batch (first term sets the slot, further
+    terms carry dst = -(slot + 1) and accumulate); _apply_ties reproduces the expression."""
+    from xrsdkit_b200 import fitting, lowering
+    from xrsdkit_b200.system import System
+    names = ["noise__I0", "core__r", "shell__t", "shell__a"]
+    terms, off = lowering.parse_linear_constraint("0.5*(core__r + shell__t) - shell__a/4 + 2", names)
+    assert dict(terms) == {1: 0.5, 2: 0.5, 3: -0.25} and off == 2.0
+    assert lowering.parse_linear_constraint("3.0", names) == ([], 3.0)
+    assert lowering.parse_linear_constraint("core__r - core__r + 1", names) == ([], 1.0)
+    for expr in ("core__r*shell__t", "core__r/shell__t", "core__r**2", "abs(core__r)", "core__r/0"):
+        with pytest.raises(NotImplementedError):
+            lowering.parse_linear_constraint(expr, names)
+    s = System(a=dict(structure="diffuse", form="spherical", parameters={"r": {"value": 10.0}}),
+               b=dict(structure="diffuse", form="spherical", parameters={"r": {"value": 20.0}}),
+               c=dict(structure="diffuse", form="spherical",
+                      parameters={"r": {"value": 1.0, "constraint_expr": "0.5*a__r + 0.25*b__r + 3"},
+                                  "I0": {"value": 1.0, "constraint_expr": "7.5"}}))
+    lay = lowering.lower_system(s, np.linspace(0.01, 0.5, 16))
+    ties = lay.ties()
+    cr, ci = lay.slot("c__r"), lay.slot("c__I0")
+    assert [lowering.tie_slot(t[0]) for t in ties] == [ci, cr, cr] or [lowering.tie_slot(t[0]) for t in ties] == [cr, cr, ci]
+    assert sum(1 for t in ties if t[0] < 0) == 1
+    P = np.tile(lay.values, (3, 1))
+    P[:, lay.slot("a__r")] = [10.0, 12.0, 14.0]
+    fitting._apply_ties(P, ties)
+    np.testing.assert_allclose(P[:, cr], 0.5 * np.array([10.0, 12.0, 14.0]) + 0.25 * 20.0 + 3.0, rtol=1e-15)
+    np.testing.assert_array_equal(P[:, ci], 7.5)
+    assert cr not in lay.free_slots() and ci not in lay.free_slots()
+    s.populations["a"].parameters["r"]["constraint_expr"] = "c__r"         # chained: a constrained parameter as a source
+    with pytest.raises(NotImplementedError):
+        lowering.lower_system(s, np.linspace(0.01, 0.5, 16)).ties()

@@ -229,6 +229,19 @@ def test_fit_with_equality_constraint(eng):
         assert out2.populations["superlattice"].parameters["r"]["value"] == pytest.approx(0.9 * rp2 + 1.0, rel=1e-14)
         assert rp2 == pytest.approx(33.0, rel=1e-2), method
         assert out2.fit_report["final_objective"] < 0.1 * out2.fit_report["initial_objective"], method
+    # a linear combination of two parameters: r_superlattice = 0.45 r_particle + 0.05 a
+    truth3 = make(33.0, 110.0, tie=False)
+    truth3.populations["superlattice"].parameters["r"]["value"] = 0.45 * 33.0 + 0.05 * 110.0
+    I3 = truth3.compute_intensity(q) * (1 + 0.01 * np.random.RandomState(10).randn(q.size))
+    start3 = make(34.5, 112.0)
+    start3.populations["superlattice"].parameters["r"]["constraint_expr"] = "0.45*particle__r + 0.05*superlattice__a"
+    for method in ("lm", "nelder-mead"):
+        out3 = fit(start3, q, I3, method=method)
+        rp3 = out3.populations["particle"].parameters["r"]["value"]
+        a3 = out3.populations["superlattice"].parameters["a"]["value"]
+        assert out3.populations["superlattice"].parameters["r"]["value"] == pytest.approx(0.45 * rp3 + 0.05 * a3, rel=1e-14)
+        assert rp3 == pytest.approx(33.0, rel=1e-2) and a3 == pytest.approx(110.0, rel=2e-3), method
+        assert out3.fit_report["final_objective"] < 0.1 * out3.fit_report["initial_objective"], method
     # anything beyond that needs lmfit's asteval: rejected, not silently ignored
     for expr in ("particle__r ** 2", "particle__r * superlattice__a", "sqrt(particle__r)", "nonsense__r"):
         start.populations["superlattice"].parameters["r"]["constraint_expr"] = expr

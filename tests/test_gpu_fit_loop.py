@@ -89,25 +89,25 @@ def test_variant_slabs_of_one_population_parameters(eng):
         # (the components are differences of running totals: their absolute error is that of the total)
         np.testing.assert_allclose(slabs[:, v].cpu().numpy(), parts[:, pop].cpu().numpy(), rtol=1e-12,
                                    atol=4e-16 * float(tot.max()))
-    # reference values: central differences of whole patterns with the tables held fixed
+    # reference values: the same forward differences taken on WHOLE patterns, tables held fixed
     Ib = eng.intensity(lay, d_q, d_p, tables=tables)
     w = d_I / d_I.sum(dim=1, keepdim=True)              # error_weighted with dI = sqrt(I): weights ~ I_obs, normalised
     r = Ib.log() - d_I.log()
     cols = []
     for name in names:
         h = 1e-6 * np.abs(P[:, lay.slot(name)])
-        Pp, Pm = P.copy(), P.copy()
+        Pp = P.copy()
         Pp[:, lay.slot(name)] += h
-        Pm[:, lay.slot(name)] -= h
-        dlog = (eng.intensity(lay, d_q, eng.to_device(Pp), tables=tables).log() - eng.intensity(lay, d_q, eng.to_device(Pm), tables=tables).log())
-        cols.append(dlog / eng.to_device(2 * h)[:, None])
+        hh = eng.to_device(Pp[:, lay.slot(name)] - P[:, lay.slot(name)])
+        dlog = eng.torch.log1p((eng.intensity(lay, d_q, eng.to_device(Pp), tables=tables) - Ib) / Ib)
+        cols.append(dlog / hh[:, None])
     J = eng.torch.stack(cols, dim=2)                    # [B, n_q, nf]
     JTJ = eng.torch.einsum("bq,bqi,bqj->bij", w, J, J)
     JTr = eng.torch.einsum("bq,bqi,bq->bi", w, J, r)
     scale = JTJ.diagonal(dim1=1, dim2=2).sqrt()
     np.testing.assert_allclose((out[0] / (scale[:, :, None] * scale[:, None, :])).cpu().numpy(),
-                               (JTJ / (scale[:, :, None] * scale[:, None, :])).cpu().numpy(), atol=2e-5)
-    np.testing.assert_allclose((out[1] / scale).cpu().numpy(), (JTr / scale).cpu().numpy(), atol=2e-5 * float((JTr / scale).abs().max()))
+                               (JTJ / (scale[:, :, None] * scale[:, None, :])).cpu().numpy(), atol=1e-5)
+    np.testing.assert_allclose((out[1] / scale).cpu().numpy(), (JTr / scale).cpu().numpy(), atol=1e-5 * float((JTr / scale).abs().max()))
 
 
 def test_empty_fit_mask_gives_zero_like_the_reference(eng):
@@ -166,7 +166,7 @@ def test_lm_moves_a_population_that_starts_at_zero_intensity(eng):
     Iobs0 = batch.compute_intensity_batch(lay, q, gone)
     res0 = batch.fit_batch(lay, q, Iobs0, truth, free_slots=free, max_iter=60)
     g = res0.params[:, lay.slot("gp__I0")]
-    assert np.all(g > 0) and np.all(g < 1e-6 * truth[:, lay.slot("gp__I0")])
+    assert np.all(g > 0) and np.all(g < 1e-4 * truth[:, lay.slot("gp__I0")])      # (the trust region allows -25 % per step)
 
 
 def test_stop_reasons_and_converged_flag(eng):
@@ -235,7 +235,7 @@ def test_free_atomic_coordinate_is_fitted(eng):
     assert u1 in lay.coordinate_slots()
     n = 6
     truth = np.tile(lay.values, (n, 1))
-    truth[:, u1] = np.linspace(0.40, 0.47, n)
+    truth[:, u1] = np.linspace(0.30, 0.42, n)        # (u and 1 - u give the same pattern: stay clear of 1/2)
     Iobs = batch.compute_intensity_batch(lay, q, truth)
     start = truth.copy()
     start[:, u1] += 0.02
@@ -270,3 +270,30 @@ def test_layout_refuses_another_q_grid(eng):
     np.testing.assert_allclose(a, b, rtol=1e-12)
     with pytest.raises(ValueError, match="another q grid"):
         batch.compute_intensity_batch(layn, np.linspace(0.0, 0.5, 100), P)          # q[0] == 0 changes q0_is_zero
+
+
+def test_rescale_I0_to_measured_pattern(eng, ref_tables):
+    """System.rescale_I0_to = the I0 rescaling at the end of the reference's system_from_prediction
+    (models/predict.py:372-378): every I0 times sum(I) / sum(I_computed), checked against that arithmetic on the oracle."""
+    from oracle import xrsd_oracle as orc
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg4_system(System)
+    q = np.linspace(0.01, 1.0, 1200)
+    I_meas = 37.5 * orc.system_intensity(q, s.to_dict(), **ref_tables) * (1 + 0.01 * np.random.RandomState(0).randn(len(q)))
+    want = np.sum(I_meas) / np.sum(orc.system_intensity(q, s.to_dict(), **ref_tables))
+    before = {k: r["value"] for k, r in s.flatten_params().items()}
+    f = s.rescale_I0_to(q, I_meas)
+    assert f == pytest.approx(want, rel=1e-12)
+    for k, r in s.flatten_params().items():
+        assert r["value"] == pytest.approx(before[k] * (want if k.endswith("__I0") else 1.0), rel=1e-12), k
+    assert np.sum(s.compute_intensity(q)) == pytest.approx(np.sum(I_meas), rel=1e-11)
+    lay = batch.layout_of(cfg4_system(System), q)
+    P = cfg4_params(lay, 5, seed=3)
+    scaled, fac = batch.rescale_I0_batch(lay, q, I_meas, P)
+    Ic = batch.compute_intensity_batch(lay, q, scaled)
+    np.testing.assert_allclose(Ic.sum(axis=1), np.sum(I_meas), rtol=1e-11)
+    i0 = [lay.slot(k) for k in ("noise__I0", "x__I0", "gp__I0")]
+    np.testing.assert_allclose(scaled[:, i0], P[:, i0] * fac[:, None], rtol=1e-14)
+    rest = [j for j in range(lay.n_params) if j not in i0]
+    np.testing.assert_array_equal(scaled[:, rest], P[:, rest])

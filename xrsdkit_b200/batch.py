@@ -60,6 +60,23 @@ def evaluate_residual_batch(layout, q, Iobs, params, dI=None, error_weighted=Tru
     return chi2 if device_out else chi2.cpu().numpy()
 
 
+def rescale_I0_batch(layout, q, I, params, eng=None):
+    """I0 rescaling of models/predict.py:372-378 for a batch: factor[b] = sum(I[b]) / sum(I_computed[b]) multiplies the
+    noise I0 and every population's I0 of row b (all populations are linear in their I0, so the rescaled systems
+    reproduce sum(I) exactly up to rounding).  I: [B, n_q] or [n_q].  Returns (rescaled params, factors) as numpy."""
+    eng = eng or _engine.get_engine()
+    d_p = eng.to_device(params)
+    if d_p.dim() == 1:
+        d_p = d_p.unsqueeze(0)
+    d_p = d_p.clone()
+    I_comp = eng.intensity(layout, q, d_p)
+    d_I = eng.to_device(I)
+    factor = d_I.reshape(-1, d_I.shape[-1]).sum(dim=1) / I_comp.sum(dim=1)
+    slots = [int(p.p_I0) for p in layout.c.pops[:layout.c.n_pops] if p.p_I0 >= 0]
+    d_p[:, slots] *= factor[:, None]
+    return d_p.cpu().numpy(), factor.cpu().numpy()
+
+
 def fit_batch(layout, q, Iobs, params0, method='lm', **kw):
     """Fit every row of params0.  method='lm' (default): batched Levenberg-Marquardt;
     method='nelder-mead': the reference's optimiser, batched, for like-for-like comparison."""

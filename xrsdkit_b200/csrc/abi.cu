@@ -343,8 +343,10 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   if (reduce && ld_obs != 0 && ld_obs < n_q) return fail(XRSD_EINVAL, "ld_obs < n_q");
   if (!(rel_step > 0.0)) return fail(XRSD_EINVAL, "rel_step must be > 0");
   if (n_tie < 0 || n_tie > XRSD_MAX_TIES || (n_tie > 0 && !ties)) return fail(XRSD_EINVAL, "n_tie=%d (max %d)", n_tie, XRSD_MAX_TIES);
-  for (int i = 0; i < 2 * n_tie; ++i)
-    if (ties[i] < 0 || ties[i] >= layout->n_params) return fail(XRSD_EINVAL, "ties[%d]=%d", i, ties[i]);
+  for (int i = 0; i < 2 * n_tie; ++i) {
+    const int slot = (ties[i] < 0 && i % 2 == 0) ? -ties[i] - 1 : ties[i];      // dst = -(slot + 1): accumulating term
+    if (slot < 0 || slot >= layout->n_params) return fail(XRSD_EINVAL, "ties[%d]=%d", i, ties[i]);
+  }
   int rm;
   const int scratch = scratch_doubles_for(layout, &rm);
   if (scratch < 0) return fail(XRSD_ECAPACITY, "size quadrature too fine for shared memory");
@@ -380,8 +382,10 @@ int xrsd_lm_propose(const double *d_params, int32_t ld_params, int32_t batch, co
   for (int i = 0; i < n_free; ++i)
     if ((free_idx[i] < 0 ? -free_idx[i] - 1 : free_idx[i]) >= ld_params) return fail(XRSD_EINVAL, "free_idx[%d]=%d", i, free_idx[i]);
   if (n_tie < 0 || n_tie > XRSD_MAX_TIES || (n_tie > 0 && !ties)) return fail(XRSD_EINVAL, "n_tie=%d (max %d)", n_tie, XRSD_MAX_TIES);
-  for (int i = 0; i < 2 * n_tie; ++i)
-    if (ties[i] < 0 || ties[i] >= ld_params) return fail(XRSD_EINVAL, "ties[%d]=%d", i, ties[i]);
+  for (int i = 0; i < 2 * n_tie; ++i) {
+    const int slot = (ties[i] < 0 && i % 2 == 0) ? -ties[i] - 1 : ties[i];
+    if (slot < 0 || slot >= ld_params) return fail(XRSD_EINVAL, "ties[%d]=%d", i, ties[i]);
+  }
   cudaError_t e = xrsd_launch_lm_propose(d_params, ld_params, batch, free_idx, n_free, ties, tie_coef, n_tie, d_JTJ, d_JTr, d_lambda, d_lo, d_hi,
                                          d_active, d_trial, max_rel_step, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "lm_propose_kernel");

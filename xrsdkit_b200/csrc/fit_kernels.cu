@@ -25,8 +25,9 @@ struct FreeSet {
   int free_of_var[XRSD_MAX_FREE + 1];   // inverse of var_of
   int vpop_of[XRSD_MAX_FREE];   // non-linear parameter used by ONE population (incl. what is tied to it): that population's
                                 // index -- its variant evaluates the population alone -- else -1 (whole system)
-  int n_tie;                    // constraints "dst = scale * src + offset" (constraint_expr affine in one parameter)
-  int tie_dst[XRSD_MAX_TIES], tie_src[XRSD_MAX_TIES];
+  int n_tie;                    // constraint terms, applied in order: "dst = scale * src + offset", or, with tie_add set,
+                                // "dst += scale * src + offset" (the further terms of a linear combination)
+  int tie_dst[XRSD_MAX_TIES], tie_src[XRSD_MAX_TIES], tie_add[XRSD_MAX_TIES];
   double tie_scale[XRSD_MAX_TIES], tie_off[XRSD_MAX_TIES];
 };
 
@@ -56,7 +57,8 @@ static FreeSet make_free_set(const xrsd_layout_t *L, const int32_t *free_idx, in
   F.n_var = 1;
   F.n_tie = (ties && n_tie > 0) ? std::min(n_tie, (int)XRSD_MAX_TIES) : 0;
   for (int t = 0; t < F.n_tie; ++t) {
-    F.tie_dst[t] = ties[2 * t];
+    F.tie_add[t] = ties[2 * t] < 0;                      // dst given as -(slot + 1): accumulate
+    F.tie_dst[t] = ties[2 * t] < 0 ? -ties[2 * t] - 1 : ties[2 * t];
     F.tie_src[t] = ties[2 * t + 1];
     F.tie_scale[t] = tie_coef ? tie_coef[2 * t] : 1.0;
     F.tie_off[t] = tie_coef ? tie_coef[2 * t + 1] : 0.0;
@@ -225,7 +227,7 @@ jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *
     const double p0 = prm[F.idx[j]];
     prm_s[F.idx[j]] = p0 + ((p0 != 0.0) ? fabs(p0) * rel_step : rel_step);
     for (int t = 0; t < F.n_tie; ++t)                                              // tied parameters move along
-      prm_s[F.tie_dst[t]] = fma(F.tie_scale[t], prm_s[F.tie_src[t]], F.tie_off[t]);
+      prm_s[F.tie_dst[t]] = fma(F.tie_scale[t], prm_s[F.tie_src[t]], F.tie_off[t] + (F.tie_add[t] ? prm_s[F.tie_dst[t]] : 0.0));
   }
   __syncthreads();
   const int q_begin = tile * q_per_cta;
@@ -520,7 +522,8 @@ __global__ void lm_propose_kernel(const double *__restrict__ params, int ldp, in
     v = fmin(fmax(v, l), h);
     if (v == v) t[F.idx[j]] = v;
   }
-  for (int k = 0; k < F.n_tie; ++k) t[F.tie_dst[k]] = fma(F.tie_scale[k], t[F.tie_src[k]], F.tie_off[k]);
+  for (int k = 0; k < F.n_tie; ++k)
+    t[F.tie_dst[k]] = fma(F.tie_scale[k], t[F.tie_src[k]], F.tie_off[k] + (F.tie_add[k] ? t[F.tie_dst[k]] : 0.0));
 }
 
 __global__ void lm_update_kernel(double *__restrict__ params, int ldp, int batch, const double *__restrict__ trial,

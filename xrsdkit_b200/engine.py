@@ -140,18 +140,16 @@ class Engine(object):
 
     def check_grid(self, layout, q):
         """The q passed with a layout must be the grid the layout was lowered for (SystemLayout.check_grid).  Host
-        arrays are checked on every call; a device tensor is read back once and remembered by address and version."""
+        arrays are checked on every call; a device tensor is read back once per tensor object and version."""
         if getattr(layout, "grid", None) is None:
             return
         if isinstance(q, self.torch.Tensor):
-            seen = layout.__dict__.setdefault("_grid_ok", set())
-            key = (q.data_ptr(), q.numel(), q._version)
-            if key in seen:
+            # remembered ON the tensor object (an address can be handed to another tensor by the caching allocator)
+            mark = (id(layout), q._version)
+            if getattr(q, "_xrsd_grid_ok", None) == mark:
                 return
             layout.check_grid(q.detach().cpu().numpy())
-            if len(seen) > 64:
-                seen.clear()
-            seen.add(key)
+            q._xrsd_grid_ok = mark
         else:
             layout.check_grid(np.asarray(q, dtype=np.float64))
 
@@ -472,7 +470,10 @@ class Engine(object):
             if ent is None or ent[0].numel() < need or ent[1] != (n_q, chunk, nf):
                 if base_ready:
                     raise RuntimeError("base_ready needs the resident workspace of a previous call with the same shape")
-                ent = (torch.zeros(need, dtype=torch.uint8, device=self.device), (n_q, chunk, nf))
+                # only the accumulator / ticket area behind the pattern slabs has to start at zero
+                ws_new = torch.empty(need, dtype=torch.uint8, device=self.device)
+                ws_new[int(chunk) * (nf + 1 + abi.MAX_POPS) * n_q * 8:].zero_()
+                ent = (ws_new, (n_q, chunk, nf))
                 store[resident] = ent
             ws = ent[0]
         else:

@@ -42,10 +42,14 @@ class FitResult(object):
 
 
 def _apply_ties(params, ties):
-    """params[..., dst] = scale * params[..., src] + offset for every constraint (dst, src[, scale, offset])."""
+    """params[..., dst] = scale * params[..., src] + offset for every constraint term (dst, src[, scale, offset]), in
+    order; a dst given as -(slot + 1) adds its term to the slot (further terms of a linear combination)."""
     for t in ties:
         scale, off = (t[2], t[3]) if len(t) >= 4 else (1.0, 0.0)
-        params[..., t[0]] = params[..., t[1]] * scale + off
+        if t[0] < 0:
+            params[..., -t[0] - 1] += params[..., t[1]] * scale + off
+        else:
+            params[..., t[0]] = params[..., t[1]] * scale + off
 
 
 def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weighted=True, logI_weighted=True,
@@ -89,7 +93,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         free_slots = layout.free_slots()
     if ties is None:
         ties = layout.ties()
-    free_slots = [s for s in free_slots if s not in [t[0] for t in ties]]      # a tied parameter is not varied
+    free_slots = [s for s in free_slots if s not in [lowering.tie_slot(t[0]) for t in ties]]      # a tied parameter is not varied
     tie_c, coef_c, n_tie = eng.tie_array(ties)
     nf = len(free_slots)
     if nf == 0:
@@ -305,7 +309,7 @@ def fit_system_inplace(system, q, I, dI=None, method='lm'):
         res = lm_fit_batch(lay, q, I, lay.values[None, :], free, max_iter=60, **kw)
     else:
         raise ValueError("unknown fit method %r" % (method,))
-    tied = [t[0] for t in lay.ties()]
+    tied = [lowering.tie_slot(t[0]) for t in lay.ties()]
     for slot, rec in enumerate(lay.records):
         if slot in free or slot in tied:
             rec['value'] = float(res.params[0, slot])
@@ -373,7 +377,7 @@ def nm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         free_slots = layout.free_slots()
     if ties is None:
         ties = layout.ties()
-    free_slots = [s for s in free_slots if s not in [t[0] for t in ties]]
+    free_slots = [s for s in free_slots if s not in [lowering.tie_slot(t[0]) for t in ties]]
     nf = len(free_slots)
     if nf == 0:
         raise ValueError("no free parameters to fit")

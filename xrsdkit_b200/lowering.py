@@ -80,24 +80,28 @@ class SystemLayout(object):
         return [i for i, r in enumerate(self.records) if not r.get('fixed') and not r.get('constraint_expr')]
 
     def ties(self):
-        """[(dst_slot, src_slot, scale, offset)] for parameters whose constraint_expr is affine in ONE other
-        parameter: value[dst] = scale * value[src] + offset.  'particle__r' -- the only form found in xrsdkit's
-        fitted systems -- gives (1, 0); '2*particle__r', 'particle__r + 5', '(shell__r - 3) / 2' work as well.
-        Anything else (several parameters, non-linear functions: the rest of lmfit's asteval language) is rejected
-        when a fit is requested."""
+        """Constraint terms [(dst, src, scale, offset)] for parameters whose constraint_expr is LINEAR in other parameters:
+        value[dst] = sum_k scale_k * value[src_k] + offset.  The first term of a constraint sets the slot, further
+        terms carry dst = -(slot + 1) and add to it (the convention of xrsd_jacobian_batch).  'particle__r' -- the only
+        form found in xrsdkit's fitted systems -- gives one term (1, 0); '2*particle__r', '(shell__r - 3) / 2',
+        'core__r + shell__t', '0.5*(a__r + b__r) + 1' work as well.  Anything non-linear (products of parameters,
+        functions: the rest of lmfit's asteval language) is rejected when a fit is requested."""
         out = []
         for i, r in enumerate(self.records):
             expr = r.get('constraint_expr')
             if not expr:
                 continue
-            src, scale, off = parse_affine_constraint(str(expr), self.names)
-            if src == i:
+            terms, off = parse_linear_constraint(str(expr), self.names)
+            if any(src == i for src, _ in terms):
                 raise NotImplementedError("constraint_expr %r refers to its own parameter" % expr)
-            out.append((i, src, scale, off))
+            if not terms:                                   # a constant: 0 * (any slot) + offset
+                terms = [(i, 0.0)]
+            for k, (src, scale) in enumerate(terms):
+                out.append((i if k == 0 else -(i + 1), src, scale, off if k == 0 else 0.0))
         if len(out) > abi.MAX_TIES:
-            raise NotImplementedError("at most %d constrained parameters per system" % abi.MAX_TIES)
-        dsts = [t[0] for t in out]
-        if any(t[1] in dsts for t in out):
+            raise NotImplementedError("at most %d constraint terms per system (XRSD_MAX_TIES)" % abi.MAX_TIES)
+        dsts = set(tie_slot(t[0]) for t in out)
+        if any(t[1] in dsts and t[2] != 0.0 for t in out):
             raise NotImplementedError("chained constraints (a constrained parameter used in another constraint_expr)")
         return out
 
@@ -261,51 +265,69 @@ def _lower_population(structure, form, settings, slots, q_last, table_slot):
     return p
 
 
-def parse_affine_constraint(expr, names):
-    """(source slot, scale, offset) of a constraint expression that is affine in exactly one parameter name;
-    raises NotImplementedError otherwise.  The expression is parsed with `ast` (numbers, one name, + - * /,
-    unary minus, parentheses) and evaluated at three points of the source to establish linearity."""
+def tie_slot(dst):
+    """slot of a constraint term's destination (-(slot + 1) marks an accumulating term)"""
+    return -dst - 1 if dst < 0 else dst
+
+
+def parse_linear_constraint(expr, names):
+    """([(source slot, coefficient), ...], offset) of a constraint expression that is linear in parameter names;
+    raises NotImplementedError otherwise.  The expression is parsed with `ast` (numbers, names, + - * /, unary
+    minus, parentheses) and evaluated symbolically as a linear form, so linearity is established exactly."""
     import ast
     try:
         tree = ast.parse(expr.strip(), mode='eval')
     except SyntaxError:
         raise NotImplementedError("constraint_expr %r is not an arithmetic expression" % expr)
-    used = set()
 
-    def ev(node, x):
+    def ev(node):           # -> (dict name -> coefficient, constant)
         if isinstance(node, ast.Expression):
-            return ev(node.body, x)
+            return ev(node.body)
         if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)) and not isinstance(node.value, bool):
-            return float(node.value)
+            return {}, float(node.value)
         if isinstance(node, ast.Name):
             if node.id not in names:
                 raise NotImplementedError("constraint_expr %r: unknown parameter %r" % (expr, node.id))
-            used.add(node.id)
-            return x
+            return {node.id: 1.0}, 0.0
         if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd)):
-            v = ev(node.operand, x)
-            return -v if isinstance(node.op, ast.USub) else v
-        if isinstance(node, ast.BinOp) and isinstance(node.op, (ast.Add, ast.Sub, ast.Mult, ast.Div)):
-            a, b = ev(node.left, x), ev(node.right, x)
-            if isinstance(node.op, ast.Add):
-                return a + b
-            if isinstance(node.op, ast.Sub):
-                return a - b
-            if isinstance(node.op, ast.Mult):
-                return a * b
-            return a / b
-        raise NotImplementedError("constraint_expr %r: only + - * / of numbers and one parameter are supported" % expr)
+            c, k = ev(node.operand)
+            sg = -1.0 if isinstance(node.op, ast.USub) else 1.0
+            return dict((n, sg * v) for n, v in c.items()), sg * k
+        if isinstance(node, ast.BinOp) and isinstance(node.op, (ast.Add, ast.Sub)):
+            (ca, ka), (cb, kb) = ev(node.left), ev(node.right)
+            sg = -1.0 if isinstance(node.op, ast.Sub) else 1.0
+            out = dict(ca)
+            for n, v in cb.items():
+                out[n] = out.get(n, 0.0) + sg * v
+            return out, ka + sg * kb
+        if isinstance(node, ast.BinOp) and isinstance(node.op, ast.Mult):
+            (ca, ka), (cb, kb) = ev(node.left), ev(node.right)
+            if ca and cb:
+                raise NotImplementedError("constraint_expr %r is not linear (a product of parameters)" % expr)
+            c, k, f = (ca, ka, kb) if ca else (cb, kb, ka)
+            return dict((n, v * f) for n, v in c.items()), k * f
+        if isinstance(node, ast.BinOp) and isinstance(node.op, ast.Div):
+            (ca, ka), (cb, kb) = ev(node.left), ev(node.right)
+            if cb:
+                raise NotImplementedError("constraint_expr %r is not linear (division by a parameter)" % expr)
+            if kb == 0.0:
+                raise NotImplementedError("constraint_expr %r divides by zero" % expr)
+            return dict((n, v / kb) for n, v in ca.items()), ka / kb
+        raise NotImplementedError("constraint_expr %r: only + - * / of numbers and parameter names are supported" % expr)
 
-    try:
-        f0, f1, f2 = ev(tree, 0.0), ev(tree, 1.0), ev(tree, 2.0)
-    except ZeroDivisionError:
-        raise NotImplementedError("constraint_expr %r is not affine in its parameter" % expr)
-    if len(used) != 1:
+    coefs, off = ev(tree)
+    if not np.isfinite([off] + list(coefs.values())).all():
+        raise NotImplementedError("constraint_expr %r does not evaluate to finite coefficients" % expr)
+    return [(names.index(n), float(v)) for n, v in coefs.items() if v != 0.0], float(off)
+
+
+def parse_affine_constraint(expr, names):
+    """(source slot, scale, offset) of a constraint expression that is affine in exactly ONE parameter name (kept for
+    callers of the round-1 interface); see parse_linear_constraint for the general linear form."""
+    terms, off = parse_linear_constraint(expr, names)
+    if len(terms) != 1:
         raise NotImplementedError("constraint_expr %r must name exactly one other parameter" % expr)
-    scale, off = f1 - f0, f0
-    if not np.isfinite([f0, f1, f2]).all() or abs((f2 - f0) - 2.0 * scale) > 1e-12 * max(1.0, abs(f2), abs(f0)):
-        raise NotImplementedError("constraint_expr %r is not affine in %s" % (expr, next(iter(used))))
-    return names.index(next(iter(used))), float(scale), float(off)
+    return terms[0][0], terms[0][1], off
 
 
 def uniform_step(q):

@@ -122,6 +122,20 @@ class System(object):
             out[name] = parts[0, k + 1].cpu().numpy()
         return out
 
+    def rescale_I0_to(self, q, I):
+        """Scale every I0 (noise model and populations) by sum(I) / sum(I_computed), in place: the last step of the
+        reference's system_from_prediction (models/predict.py:372-378), which brings a predicted System onto the
+        scale of the measured pattern before it is fitted.  Returns the factor."""
+        from .. import batch, lowering
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        lay = lowering.lower_system(self, q)
+        _, factor = batch.rescale_I0_batch(lay, q, np.asarray(I, dtype=float)[None, :], lay.values[None, :])
+        f = float(factor[0])
+        self.noise_model.parameters['I0']['value'] *= f
+        for pop in self.populations.values():
+            pop.parameters['I0']['value'] *= f
+        return f
+
     def evaluate_residual(self, q, I, dI=None, I_comp=None):
         """Scalar weighted chi^2 between the model and (q, I) (reference :134-187)."""
         from .. import engine, lowering
