@@ -105,8 +105,8 @@ typedef struct xrsd_layout {
   int32_t q0_is_zero;          /* q[0] == 0: the only zero the reference special-cases */
   double wavelength;
   double q_step;               /* > 0: q[i] == q[0] + i*q_step to within a few ulp (a linspace grid), which lets the
-                                  size-quadrature loop advance its starting phases by a rotation from one 256-point
-                                  span to the next instead of calling sincos, and tells the crystalline
+                                  size-quadrature loop advance its starting phases by a rotation from one pass over
+                                  the CTA's threads (256 q-points) to the next instead of calling sincos, and tells the crystalline
                                   branch that q is strictly ascending without testing it; 0: no assumption about q */
   xrsd_pop_t pops[XRSD_MAX_POPS];
 } xrsd_layout_t;
@@ -203,10 +203,12 @@ int xrsd_intensity_components_batch(const xrsd_layout_t *layout, const double *d
 
 /* chi2[b] of System.evaluate_residual for b < batch; d_Iobs / d_dI are [batch][ld_obs]
  * (ld_obs == 0 broadcasts one pattern to the whole batch).  I(q) is computed in the same
- * kernel (grid = batch x q-spans) and never written to memory; the spans of a system meet in
- * d_workspace (xrsd_residual_workspace_bytes(batch) bytes, zero before the first call, re-zeroed
- * by the kernel). */
-int64_t xrsd_residual_workspace_bytes(int32_t batch);
+ * kernel (grid = batch x q-spans) and never written to memory; the spans of a system leave their
+ * partial sums in d_workspace (xrsd_residual_workspace_bytes(batch, n_q) bytes; its ticket area must be
+ * zero before the first call -- zeroing the whole workspace once is the simple way -- and is left
+ * zero by the kernel) and the span that arrives last adds them up in span order, so the result
+ * is bit-identical from run to run. */
+int64_t xrsd_residual_workspace_bytes(int32_t batch, int32_t n_q);
 int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj,
                         const double *d_q, int32_t n_q, const double *d_params, int32_t ld_params,
                         int32_t batch, const xrsd_tables_t *tables,
@@ -219,9 +221,11 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
  * otherwise taken from the population's own pattern: needed where a system sits at I0 == 0); rel_step is the relative step (absolute for zero-valued
  * parameters).  Two launches: variants (grid = batch x evaluated variants x q-spans; an I0 is
  * linear and needs no variant) and a chunked reduction.  d_workspace holds
- * xrsd_jacobian_workspace_bytes() bytes; the accumulator / ticket area behind the variant slabs
- * must be zero before the FIRST call with a given (n_q, batch, n_free) (the reduction re-zeroes
- * it; zeroing the whole workspace once is the simple way).  ties[n_tie][2] (HOST, may be NULL) are
+ * xrsd_jacobian_workspace_bytes() bytes; the partial-sum / ticket area behind the variant slabs
+ * must be zero before the FIRST call with a given (n_q, batch, n_free) (the reduction leaves the
+ * tickets zero; zeroing the whole workspace once is the simple way).  The q-chunks of a system are
+ * added up in chunk order by the chunk that arrives last: JTJ, JTr and chi2 are bit-identical from
+ * run to run.  ties[n_tie][2] (HOST, may be NULL) are
  * constraints (dst slot, src slot) with tie_coef[n_tie][2] = (scale, offset) (HOST; NULL = identity):
  * params[dst] = scale * params[src] + offset -- constraint_expr values that are affine in one other
  * parameter (xrsdkit's own fitted systems use the plain name, "particle__r"); a dst given as -(slot + 1)

@@ -112,9 +112,18 @@ def test_lowering_errors():
                                             settings={"lattice": "hcp", "space_group": "Fm-3m"})), np.array([0.1]))
     with pytest.raises(KeyError):
         lowering.lower_system(System(x=dict(structure="diffuse", form="atomic", settings={"symbol": "Qq"})), np.array([0.1]))
-    with pytest.raises(NotImplementedError):
+    # fixed capacities of the engine (include/xrsd_b200.h): a ValueError that names the limit
+    with pytest.raises(ValueError, match="XRSD_MAX_SPECIES"):
         lowering.lower_system(System(x=dict(structure="crystalline", form="polyatomic", settings={"n_atoms": 5})),
                               np.array([0.1]))
+    many = dict(("p%d" % i, dict(structure="diffuse", form="spherical")) for i in range(6))
+    with pytest.raises(ValueError, match="XRSD_MAX_POPS"):
+        lowering.lower_system(System(**many), np.array([0.1]))
+    poly = dict(("x%d" % i, dict(structure="crystalline", form="polyatomic", settings={"n_atoms": 4, "lattice": "triclinic"}))
+                for i in range(4))
+    with pytest.raises(ValueError, match="XRSD_MAX_PARAMS"):
+        lowering.lower_system(System(**poly), np.array([0.1]))
+    assert issubclass(lowering.CapacityError, NotImplementedError)
 
 
 def test_shard_bounds_cover_and_balance():

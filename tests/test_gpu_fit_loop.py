@@ -297,3 +297,35 @@ def test_rescale_I0_to_measured_pattern(eng, ref_tables):
     np.testing.assert_allclose(scaled[:, i0], P[:, i0] * fac[:, None], rtol=1e-14)
     rest = [j for j in range(lay.n_params) if j not in i0]
     np.testing.assert_array_equal(scaled[:, rest], P[:, rest])
+
+
+def test_reductions_are_bit_identical_from_run_to_run(eng):
+    """chi2 of the residual kernel and JTJ / JTr / chi2 of the Jacobian reduction: the spans (chunks) of a system leave
+    partial sums that the last-arriving one adds up in span order, so 20 repeats of a small batch -- every pattern cut
+    into several spans that finish in a different order each time -- give the same bits."""
+    import torch
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    for make, params, names in ((cfg4_system, cfg4_params, ("noise__I0", "x__I0", "x__a", "x__hwhm_g", "x__r", "gp__I0", "gp__rg")),
+                                (cfg2_system, cfg2_params, ("noise__I0", "p__I0", "p__r", "p__sigma", "p__r_hard"))):
+        s = make(System)
+        q = np.linspace(0.01, 1.0 if make is cfg4_system else 0.5, 8192)
+        lay = batch.layout_of(s, q)
+        B = 3
+        P = params(lay, B, seed=8)
+        free = [lay.slot(k) for k in names]
+        obj = eng.objective(True, True, (0.0, float("inf")))
+        d_q, d_p = eng.to_device(q), eng.to_device(P * 1.01)
+        d_I = eng.intensity(lay, d_q, eng.to_device(P)) * (1 + 0.02 * eng.to_device(np.random.RandomState(1).randn(B, len(q))))
+        tables = eng.build_tables(lay, d_p, B, params_host=P * 1.01) if lay.n_xtal else None
+        first = None
+        for rep in range(20):
+            chi2 = eng.residual(lay, obj, d_q, d_p, d_I, tables=tables).clone()
+            JTJ, JTr, c2 = [t.clone() for t in eng.jacobian(lay, obj, d_q, d_p, d_I, None, len(q), free, tables)]
+            got = [chi2, JTJ, JTr, c2]
+            if first is None:
+                first = got
+                assert torch.isfinite(JTJ).all() and float(JTJ.abs().max()) > 0
+                np.testing.assert_allclose(c2.cpu().numpy(), chi2.cpu().numpy(), rtol=1e-12)
+            for a, b in zip(first, got):
+                assert torch.equal(a.view(torch.int64), b.view(torch.int64)), rep

@@ -72,7 +72,7 @@ _SIGNATURES = {
     "xrsd_intensity_batch": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, C.POINTER(Tables), vp, C.c_int64, vp]),
     "xrsd_intensity_components_batch": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, C.POINTER(Tables), vp, C.c_int64,
                                                   vp, vp]),
-    "xrsd_residual_workspace_bytes": (C.c_int64, [i32]),
+    "xrsd_residual_workspace_bytes": (C.c_int64, [i32, i32]),
     "xrsd_residual_batch": (C.c_int, [C.POINTER(Layout), C.POINTER(Objective), vp, i32, vp, i32, i32,
                                       C.POINTER(Tables), vp, vp, C.c_int64, vp, vp, vp, vp]),
     "xrsd_jacobian_workspace_bytes": (C.c_int64, [i32, i32, i32]),

@@ -113,7 +113,12 @@ def fit_mixed(groups, eng=None, **kw):
         except BaseException as e:      # re-raised in the calling thread
             errors.append(e)
 
-    threads = [threading.Thread(target=work, args=(k, g, torch.cuda.Stream(device=eng.device))) for k, g in enumerate(groups)]
+    # the streams live as long as the engine: the caching allocator keeps its blocks per stream, so fresh streams for
+    # every call would send every fit's workspaces (GBs) through cudaMalloc again
+    pool = eng.__dict__.setdefault("_mixed_streams", [])
+    while len(pool) < len(groups):
+        pool.append(torch.cuda.Stream(device=eng.device))
+    threads = [threading.Thread(target=work, args=(k, g, pool[k])) for k, g in enumerate(groups)]
     for t in threads:
         t.start()
     for t in threads:

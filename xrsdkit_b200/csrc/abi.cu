@@ -277,9 +277,14 @@ int xrsd_intensity_components_batch(const xrsd_layout_t *layout, const double *d
   return intensity_impl(layout, d_q, n_q, d_params, ld_params, batch, tables, d_I, ld_I, d_cum, stream);
 }
 
-int64_t xrsd_residual_workspace_bytes(int32_t batch) {
-  // per system: two FP64 accumulators (sum w d^2, sum w), then one ticket each; zero-initialised once
-  return (int64_t)batch * 16 + (((int64_t)batch * 4 + 255) & ~255LL);
+// partial sums (sum w d^2, sum w) per (system, span); spans are at least 512 q-points long (pick_q_per_cta)
+static int64_t residual_partial_bytes(int32_t batch, int32_t n_q) {
+  return (((int64_t)batch * (((int64_t)n_q + 511) / 512) * 16) + 255) & ~255LL;
+}
+
+int64_t xrsd_residual_workspace_bytes(int32_t batch, int32_t n_q) {
+  // the partial sums, then one ticket per system (zero before the first call; the kernel leaves them zero)
+  return residual_partial_bytes(batch, n_q) + (((int64_t)batch * 4 + 255) & ~255LL);
 }
 
 int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q, int32_t n_q,
@@ -299,7 +304,7 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   if (scratch < 0) return fail(XRSD_ECAPACITY, "size quadrature too fine for shared memory");
   const int per = pick_q_per_cta(n_q, batch, scratch, layout->n_xtal > 0);
   double *d_acc = (double *)d_workspace;
-  unsigned *d_tickets = (unsigned *)((char *)d_workspace + (int64_t)batch * 16);
+  unsigned *d_tickets = (unsigned *)((char *)d_workspace + residual_partial_bytes(batch, n_q));
   cudaError_t e = xrsd_launch_residual(layout, obj, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables,
                                        d_Iobs, (obj->has_dI || obj->prepared) ? d_dI : nullptr, (long long)ld_obs, d_chi2, per, scratch, rm, d_active,
                                        d_acc, d_tickets, (cudaStream_t)stream);
@@ -307,13 +312,17 @@ int xrsd_residual_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   return XRSD_OK;
 }
 
+// partial normal equations per (system, q-chunk): the reduction's grid holds at most batch + 4*148*2 chunks
+static int64_t jacobian_partial_bytes(int32_t batch, int32_t n_free) {
+  return ((((int64_t)batch + 4 * 148 * 2 + 1) * (int64_t)xrsd_jacobian_acc_doubles(n_free) * 8) + 255) & ~255LL;
+}
+
 int64_t xrsd_jacobian_workspace_bytes(int32_t n_q, int32_t batch, int32_t n_free) {
   // [batch][(n_free+1) variants + XRSD_MAX_POPS running totals][n_q] doubles (upper bound: linear
   // parameters need no variant slab), then per system the normal-equation accumulators and one ticket
   // (both zero-initialised by the caller once; the reduce kernel re-zeroes them)
   const int64_t fbytes = (int64_t)batch * (n_free + 1 + XRSD_MAX_POPS) * n_q * 8;
-  const int64_t abytes = (((int64_t)batch * (int64_t)xrsd_jacobian_acc_doubles(n_free) * 8) + 255) & ~255LL;
-  return fbytes + abytes + (((int64_t)batch * 4 + 255) & ~255LL);
+  return fbytes + jacobian_partial_bytes(batch, n_free) + (((int64_t)batch * 4 + 255) & ~255LL);
 }
 
 int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj, const double *d_q, int32_t n_q,
@@ -356,7 +365,7 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   if (xrsd_jacobian_smem(layout->n_params, n_free, per, scratch, nullptr) + kStaticSmemEval > (size_t)kMaxSmem)
     return fail(XRSD_ECAPACITY, "jacobian working set does not fit in shared memory");
   const int64_t fbytes = (int64_t)batch * (n_free + 1 + XRSD_MAX_POPS) * n_q * 8;
-  const int64_t abytes = (((int64_t)batch * (int64_t)xrsd_jacobian_acc_doubles(n_free) * 8) + 255) & ~255LL;
+  const int64_t abytes = jacobian_partial_bytes(batch, n_free);
   double *d_Fvar = (double *)d_workspace;
   double *d_acc = (double *)((char *)d_workspace + fbytes);
   unsigned *d_tickets = (unsigned *)((char *)d_workspace + fbytes + abytes);

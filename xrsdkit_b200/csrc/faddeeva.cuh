@@ -17,7 +17,7 @@
 //                 accuracy in the far Gaussian wings where Re w ~ y/(sqrt(pi) x^2) << 1.
 //
 // Measured against scipy 1.18.1 wofz on x in [0, 1e7], y in [1e-12, 1e6]: max relative
-// difference 5e-13 (at the |z| = 8 hand-over), typically 2e-14 (tests/test_faddeeva.py).
+// difference 5e-13 (at the |z| = 8 hand-over), typically 2e-14 (tests/test_gpu_parity.py::test_faddeeva_against_scipy).
 #pragma once
 #include <math.h>
 
@@ -155,19 +155,31 @@ __device__ __forceinline__ void voigt_table(double *tab, double *tmp, const doub
   __syncthreads();
 }
 
+// a_0/2 + sum_{k=1..16} a_k T_k(t), |t| <= 1, as TWO independent Clenshaw recurrences in u = 2 t^2 - 1 instead of one
+// in t:  T_2j(t) = T_j(u)  and  T_2j+1(t) = t W_j(u)  with W_j+1 = 2u W_j - W_j-1, W_0 = 1, W_1 = 2u - 1  (for which
+// the Clenshaw sum is b_0 - b_1).  Same operation count, half the dependency depth: these sums sit in loops that are
+// bound by the latency of the FP64 pipe, not its throughput (ncu: `wait` is the top stall reason).
+__device__ __forceinline__ double cheb17(const double *__restrict__ a, double t) {
+  static_assert(VOIGT_TAB_N == 17, "degree 16");
+  const double u2 = fma(4.0 * t, t, -2.0);               // 2u
+  double e1 = a[16], e2 = 0.0;                           // even chain: coefficients a_16, a_14, ..., a_2
+  double o1 = a[15], o2 = 0.0;                           // odd chain:  coefficients a_15, a_13, ..., a_1
+#pragma unroll
+  for (int j = 7; j >= 1; --j) {
+    const double e0 = fma(u2, e1, a[2 * j] - e2);
+    const double o0 = fma(u2, o1, a[2 * j - 1] - o2);
+    e2 = e1; e1 = e0;
+    o2 = o1; o1 = o0;
+  }
+  // even: a_0/2 + u e_1 - e_2;   odd: t (b_0 - b_1) with b_0 = o1 (after the last step), b_1 = o2
+  return fma(0.5 * u2, e1, 0.5 * a[0] - e2) + t * (o1 - o2);
+}
+
 __device__ __forceinline__ double rew_table(double x, const double *tab) {
   const double x2 = x + x;                               // 0 <= x < 8: interval k = floor(2x), t = 2(2x - k) - 1
   const int k = (int)x2;
   const double t = 2.0 * (x2 - (double)k) - 1.0;
-  const double *ck = tab + k * VOIGT_TAB_N;
-  double b1 = 0.0, b2 = 0.0;
-#pragma unroll
-  for (int j = VOIGT_TAB_N - 1; j >= 1; --j) {
-    const double b0 = fma(2.0 * t, b1, ck[j] - b2);
-    b2 = b1;
-    b1 = b0;
-  }
-  return fma(t, b1, 0.5 * ck[0] - b2);
+  return cheb17(tab + k * VOIGT_TAB_N, t);
 }
 
 // Re w(x + i y) with y = vc->y >= 0; `tab` (optional) is the pattern's near-branch table.

@@ -1,15 +1,17 @@
-// fit_kernels.cu -- batched fit objective, finite-difference normal equations and the
-// Levenberg-Marquardt step, one CTA (objective / Jacobian) or one thread (LM algebra) per
-// system.  I(q) is produced by accumulate_system() in shared memory and consumed in the same
-// kernel; it never goes to HBM.
+// fit_kernels.cu -- batched fit objective, finite-difference normal equations and the Levenberg-Marquardt loop
+// kernels: one CTA per (system, q-span) for the objective and the Jacobian variants, one CTA per system for the trial
+// point, one thread per system for the LM algebra.
 //
-//   residual_kernel  <- System.evaluate_residual, system/__init__.py:134-187, and
-//                       compute_chi2, tools/__init__.py:104-125 (scalar weighted chi^2,
-//                       including the reference's `wts *= dI**2` convention)
-//   jacobian_kernel  <- what one lmfit objective sweep would need (system/__init__.py:189-195
-//                       evaluates one parameter set per call; here n_free+1 sets per system)
-//   lm_*             <- replaces the lmfit Nelder-Mead driver of system/__init__.py:262-266
-//                       (no oracle in the reference; parity is defined on outcomes)
+//   residual_kernel          <- System.evaluate_residual, system/__init__.py:134-187, and compute_chi2,
+//                               tools/__init__.py:104-125 (scalar weighted chi^2, including the reference's
+//                               `wts *= dI**2` convention); I(q) is produced in shared memory and consumed in place
+//   jacobian_variants_kernel <- what one lmfit objective sweep would need (system/__init__.py:189-195 evaluates one
+//   jacobian_reduce_kernel      parameter set per call; here every perturbed pattern of every system in one launch);
+//                               the variant patterns go through an HBM workspace (resident for the whole fit)
+//   objective_prepare_kernel, lm_propose_kernel, lm_trial_update_kernel, lm_accept_kernel
+//                            <- replace the lmfit Nelder-Mead driver of system/__init__.py:262-266 (no oracle in the
+//                               reference; parity is defined on outcomes, and measured against batched Nelder-Mead
+//                               on the same systems in bench.py)
 #include <string.h>
 #include <algorithm>
 #include "system_eval.cuh"
@@ -25,6 +27,9 @@ struct FreeSet {
   int free_of_var[XRSD_MAX_FREE + 1];   // inverse of var_of
   int vpop_of[XRSD_MAX_FREE];   // non-linear parameter used by ONE population (incl. what is tied to it): that population's
                                 // index -- its variant evaluates the population alone -- else -1 (whole system)
+  // the reduction forms every difference quotient as  scale_j * ((slab[ra] - slab[rb]) + slab[rc]):  slab rows of
+  // the workspace, -1 = a row of zeros; scale_j = 1, or h / I0 for a linear parameter (lin_j set)
+  int ra[XRSD_MAX_FREE], rb[XRSD_MAX_FREE], rc[XRSD_MAX_FREE], lin_j[XRSD_MAX_FREE];
   int n_tie;                    // constraint terms, applied in order: "dst = scale * src + offset", or, with tie_add set,
                                 // "dst += scale * src + offset" (the further terms of a linear combination)
   int tie_dst[XRSD_MAX_TIES], tie_src[XRSD_MAX_TIES], tie_add[XRSD_MAX_TIES];
@@ -99,6 +104,23 @@ static FreeSet make_free_set(const xrsd_layout_t *L, const int32_t *free_idx, in
       }
     }
   }
+  for (int j = 0; j < XRSD_MAX_FREE; ++j) {
+    F.ra[j] = F.rb[j] = F.rc[j] = -1;
+    F.lin_j[j] = 0;
+    if (j >= n_free) continue;
+    const int nv = F.n_var;
+    if (F.var_of[j] > 0) {                  // variant slab minus the base's term: whole pattern, or one population's
+      F.ra[j] = F.var_of[j];
+      const int kv = F.vpop_of[j];
+      if (kv < 0) { F.rb[j] = 0; }
+      else { F.rb[j] = nv + kv; F.rc[j] = kv > 0 ? nv + kv - 1 : -1; }
+    } else {                                // linear: (h / I0) * the population's own term, from the running totals
+      const int kp = F.pop_of[j];
+      F.lin_j[j] = 1;
+      F.ra[j] = nv + kp;
+      F.rb[j] = kp > 0 ? nv + kp - 1 : -1;
+    }
+  }
   return F;
 }
 
@@ -167,17 +189,22 @@ residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
   }
   num = block_sum(num, &S);
   den = block_sum(den, &S);
+  // the spans of a system meet in partial sums kept per span and added up IN SPAN ORDER by whichever span arrives
+  // last: the result does not depend on the order of arrival (bit-identical from run to run)
   if (threadIdx.x == 0) {
-    atomicAdd(&acc_g[2 * (size_t)b], num);
-    atomicAdd(&acc_g[2 * (size_t)b + 1], den);
+    double *part = acc_g + 2 * ((size_t)b * n_tiles + tile);
+    part[0] = num;
+    part[1] = den;
     __threadfence();
     is_last = (atomicAdd(&tickets[b], 1u) == (unsigned)(n_tiles - 1));
     if (is_last) {
       __threadfence();
-      const double n_ = __ldcg(&acc_g[2 * (size_t)b]), d_ = __ldcg(&acc_g[2 * (size_t)b + 1]);
+      double n_ = 0.0, d_ = 0.0;
+      for (int t = 0; t < n_tiles; ++t) {
+        n_ += __ldcg(&acc_g[2 * ((size_t)b * n_tiles + t)]);
+        d_ += __ldcg(&acc_g[2 * ((size_t)b * n_tiles + t) + 1]);
+      }
       chi2[b] = (d_ == 0.0 && n_ == 0.0) ? 0.0 : n_ / d_;      // no point in the fit mask: the reference's compute_chi2 sums nothing -> 0.0
-      acc_g[2 * (size_t)b] = 0.0;
-      acc_g[2 * (size_t)b + 1] = 0.0;
       tickets[b] = 0;
     }
   }
@@ -197,7 +224,7 @@ residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
 //     writes the outputs.  (A first version reduced inside the variant kernel by the last-finishing
 //     CTA of each system: that serial tail cost 25 % of the whole Jacobian.)
 template <bool RM, bool HX>
-__global__ void __launch_bounds__(EVAL_THREADS, HX ? 10 : 6)   // measured on cfg4 (same box): 8 CTAs x 64 regs 11.8 ms, 10 x 48 (spills) 11.5, 12 x 40 14.4; 6 x 80 was 7 % behind 8
+__global__ void __launch_bounds__(EVAL_THREADS, HX ? 8 : 6)   // crystalline layouts, 10^4 cfg4 systems, same box: 8 CTAs x 64 registers 15.5 ms, 10 x 48 (spills) 16.1 (round 1: 11.8 / 11.5 per 4069 systems, 12 x 40 14.4, 6 x 80 7 % behind 8)
 jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ q, int n_q,
                          const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T, const FreeSet F,
                          double rel_step, double *__restrict__ Fvar, int q_per_cta, int n_tiles, int pattern_doubles,
@@ -286,21 +313,25 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
   const double *obs = Iobs + (size_t)b * ld_obs;
   const double *err = dI ? dI + (size_t)b * ld_obs : nullptr;
   const double *Fb = Fvar + (size_t)b * n_slab * n_q;
-  double step[NF], lin[NF];
+  double step[NF], scale[NF];
 #pragma unroll
   for (int j = 0; j < NF; ++j) {
     const double p0 = (j < nf) ? prm[F.idx[j]] : 1.0;
     step[j] = (p0 != 0.0) ? fabs(p0) * rel_step : rel_step;
-    lin[j] = (p0 != 0.0) ? step[j] / p0 : 0.0;     // h / I0 for a linear parameter
+    // h / I0 for a linear parameter (0 at I0 == 0: no derivative there, the caller forces a variant instead), else 1
+    scale[j] = (j >= nf) ? 0.0 : (F.lin_j[j] ? ((p0 != 0.0) ? step[j] / p0 : 0.0) : 1.0);
   }
   const int q_lo = chunk * chunk_q, q_hi = min(n_q, q_lo + chunk_q);
-  double *accb = acc_g + (size_t)b * NACC;
+  double *accb = acc_g + ((size_t)b * n_chunks + chunk) * NACC;      // this chunk's partial sums
   const int n_rows = n_slab + 1 + (err ? 1 : 0);
+  const int z_row = n_rows;                          // one more row per stage that stays zero: the "absent term" of a quotient
+  for (int i = tid; i < JR_STAGES * JR_THREADS; i += JR_THREADS)
+    ring[((size_t)(i / JR_THREADS) * (n_rows + 1) + z_row) * JR_THREADS + (i % JR_THREADS)] = 0.0;
   const int n_it = (q_hi - q_lo + JR_THREADS - 1) / JR_THREADS;
   auto issue = [&](int it) {             // stage the q-point of iteration `it` (if any); always closes a group
     const int i = q_lo + it * JR_THREADS + tid;
     if (it < n_it && i < q_hi) {
-      double *slot = ring + (size_t)(it % JR_STAGES) * n_rows * JR_THREADS + tid;
+      double *slot = ring + (size_t)(it % JR_STAGES) * (n_rows + 1) * JR_THREADS + tid;
       for (int r = 0; r < n_slab; ++r) cp_async8(slot + r * JR_THREADS, Fb + (size_t)r * n_q + i);
       cp_async8(slot + n_slab * JR_THREADS, obs + i);
       if (err) cp_async8(slot + (n_slab + 1) * JR_THREADS, err + i);
@@ -320,7 +351,7 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
     for (int it = 0; it < n_it; ++it) {
       cp_async_wait<JR_STAGES - 1>();                 // the group of iteration `it` has landed
       const int i = q_lo + it * JR_THREADS + tid;
-      const double *Fs = ring + (size_t)(it % JR_STAGES) * n_rows * JR_THREADS + tid;   // row r at Fs[r * JR_THREADS]
+      const double *Fs = ring + (size_t)(it % JR_STAGES) * (n_rows + 1) * JR_THREADS + tid;   // row r at Fs[r * JR_THREADS]
       bool fit = i < q_hi;
       double w = 0.0, Io = 0.0, I0v = 0.0;
       if (fit) {
@@ -334,35 +365,20 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
       const double fo = fit_target(O, Io);
       const double res = f0 - fo;
       const double inv = O.logI_weighted ? 1.0 / I0v : 1.0;
+      // difference quotients (times the step): scale_j * ((slab[ra] - slab[rb]) + slab[rc]), see FreeSet; in log mode
+      // log1p of the relative change -- no cancellation between two logarithms, and for the small changes a
+      // finite-difference step makes (|x| < 0.01) three terms of its series instead of a logarithm per parameter
       double D[NF];
 #pragma unroll
       for (int j = 0; j < NF; ++j) {
-        double d = 0.0;
-        if (j < nf) {
-          if (F.var_of[j] > 0) {
-            const int kv = F.vpop_of[j];
-            if (kv < 0) {
-              d = Fs[F.var_of[j] * JR_THREADS] - I0v;
-            } else {          // the variant slab holds population kv alone: difference against the base's term for it
-              double Ik = Fs[(nv + kv) * JR_THREADS];
-              if (kv > 0) Ik -= Fs[(nv + kv - 1) * JR_THREADS];
-              d = Fs[F.var_of[j] * JR_THREADS] - Ik;
-            }
-          } else {
-            const int kp = F.pop_of[j];
-            double Ik = Fs[(nv + kp) * JR_THREADS];
-            if (kp > 0) Ik -= Fs[(nv + kp - 1) * JR_THREADS];
-            d = lin[j] * Ik;
-          }
-          if (O.logI_weighted) {
-            const double x = d * inv;
-            if (!(x > -1.0)) d = 0.0;                                  // variant intensity <= 0: no information
-            else if (fabs(x) < 1.0e-3) d = x * fma(x, fma(x, fma(x, -0.25, 1.0 / 3.0), -0.5), 1.0);
-            else d = log1p(x);
-          }
-          if (!(d == d)) d = 0.0;
+        const int ia = (F.ra[j] < 0 ? z_row : F.ra[j]) * JR_THREADS, ib = (F.rb[j] < 0 ? z_row : F.rb[j]) * JR_THREADS,
+                  ic = (F.rc[j] < 0 ? z_row : F.rc[j]) * JR_THREADS;
+        double d = scale[j] * ((Fs[ia] - Fs[ib]) + Fs[ic]) * inv;
+        if (O.logI_weighted) {
+          if (fabs(d) < 1.0e-2) d = d * fma(d, fma(d, 1.0 / 3.0, -0.5), 1.0);      // |error| < x^4 / 4
+          else d = (d > -1.0) ? log1p(d) : 0.0;          // a variant intensity <= 0 carries no information (NaN: below)
         }
-        D[j] = d;
+        D[j] = (d == d) ? d : 0.0;
       }
       issue(it + JR_STAGES);                          // the slot is free again: refill it
       if (row0 == 0) { c2 = fma(w, res * res, c2); sw += w; }
@@ -412,38 +428,46 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
       }
       if (dst >= 0) {
         for (int wv = 0; wv < JR_THREADS / 32; ++wv) v += fold[wv][src];
-        atomicAdd(&accb[dst], v);
+        accb[dst] = v;
       }
     }
     __syncthreads();
   }
-  // ---- the last chunk of this system normalises and writes the outputs
+  // ---- the chunk that arrives last adds the partial sums of all chunks IN CHUNK ORDER (the result does not depend on
+  //      the order of arrival: bit-identical from run to run), normalises and writes the outputs
   __threadfence();
   __syncthreads();
   if (tid == 0) is_last = (atomicAdd(&tickets[b], 1u) == (unsigned)(n_chunks - 1));
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  double swt = __ldcg(&accb[NF * NF + NF + 1]);
-  if (swt == 0.0 && __ldcg(&accb[NF * NF + NF]) == 0.0) swt = 1.0;      // empty fit mask: chi2 = 0, no gradient (see residual_kernel)
+  const double *acc0 = acc_g + (size_t)b * n_chunks * NACC;
+  auto total = [&](int e) {
+    double v = 0.0;
+    for (int c = 0; c < n_chunks; ++c) v += __ldcg(&acc0[(size_t)c * NACC + e]);
+    return v;
+  };
+  double swt = total(NF * NF + NF + 1);
+  const double c2t = total(NF * NF + NF);
+  if (swt == 0.0 && c2t == 0.0) swt = 1.0;      // empty fit mask: chi2 = 0, no gradient (see residual_kernel)
   for (int e = tid; e < nf * nf; e += JR_THREADS) {
     const int j = e / nf, k = e - j * nf;
     const int jj = min(j, k), kk = max(j, k);
     double sj = 1.0, sk = 1.0;
 #pragma unroll
     for (int m = 0; m < NF; ++m) { if (m == jj) sj = step[m]; if (m == kk) sk = step[m]; }
-    JTJ[((size_t)b * nf + j) * nf + k] = __ldcg(&accb[jj * NF + kk]) / (sj * sk) / swt;
+    JTJ[((size_t)b * nf + j) * nf + k] = total(jj * NF + kk) / (sj * sk) / swt;
   }
   if (tid < nf) {
     double sj = 1.0;
 #pragma unroll
     for (int m = 0; m < NF; ++m) if (m == tid) sj = step[m];
-    JTr[(size_t)b * nf + tid] = __ldcg(&accb[NF * NF + tid]) / sj / swt;
+    JTr[(size_t)b * nf + tid] = total(NF * NF + tid) / sj / swt;
   }
-  if (tid == 0) chi2[b] = __ldcg(&accb[NF * NF + NF]) / swt;
-  __syncthreads();
-  for (int e = tid; e < NACC; e += JR_THREADS) accb[e] = 0.0;       // ready for the next launch
-  if (tid == 0) tickets[b] = 0;
+  if (tid == 0) {
+    chi2[b] = c2t / swt;
+    tickets[b] = 0;
+  }
 }
 
 // ---------------------------------------------------------------------------- LM algebra
@@ -871,7 +895,7 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
   const int chunk_q = (((n_q + chunks_per_sys - 1) / chunks_per_sys) + JR_THREADS - 1) / JR_THREADS * JR_THREADS;
   const int n_chunks = (n_q + chunk_q - 1) / chunk_q;
   if ((long long)batch * n_chunks > 2147483647LL) return cudaErrorInvalidConfiguration;
-  const size_t ring_bytes = (size_t)JR_STAGES * (F.n_var + layout->n_pops + 2) * JR_THREADS * sizeof(double);
+  const size_t ring_bytes = (size_t)JR_STAGES * (F.n_var + layout->n_pops + 3) * JR_THREADS * sizeof(double);
   // opt in on every launch (microseconds; the attribute is per device and static shared memory counts against the
   // 48 KB default too)
   e = n_free <= 8 ? cudaFuncSetAttribute(jacobian_reduce_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)

@@ -528,17 +528,9 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               const int i = i0 + tid;
               if (i >= i1) continue;
               const double qi = q[q_begin + i];
-              // Clenshaw for a_0/2 + sum_k a_k T_k(t), t in [-1, 1]
+              // a_0/2 + sum_k a_k T_k(t), t in [-1, 1] (two interleaved Clenshaw chains: faddeeva.cuh)
               const double t = (qi - S->run_c[run]) * S->run_invH[run];
-              const double *ck = S->cheb_coef + run * CHEB_N;
-              double b1 = 0.0, b2 = 0.0;
-#pragma unroll
-              for (int k = CHEB_N - 1; k >= 1; --k) {
-                const double b0 = fma(2.0 * t, b1, ck[k] - b2);
-                b2 = b1;
-                b1 = b0;
-              }
-              double a_sum = fma(t, b1, 0.5 * ck[0] - b2);
+              double a_sum = cheb17(S->cheb_coef + run * CHEB_N, t);
               const int s_lo = S->near_lo[run], s_hi = S->near_hi[run];
               for (int sl = s_lo; sl < s_hi; ++sl) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);

@@ -391,15 +391,15 @@ class Engine(object):
         assert tuple(d_I.shape) == shape
         return d_I, d_dI, (n_q if per_system else 0)
 
-    def residual_workspace(self, batch):
-        """Zero-initialised accumulator / ticket area of xrsd_residual_batch, kept per batch size (the layout
-        of the area depends on it; the kernel leaves it zeroed after every launch)."""
+    def residual_workspace(self, batch, n_q):
+        """Zero-initialised partial-sum / ticket area of xrsd_residual_batch, kept per shape (the layout of the area
+        depends on it; the kernel leaves the tickets zeroed after every launch)."""
         cache = self.__dict__.setdefault("_res_ws", {})
-        key = (batch, self.torch.cuda.current_stream(self.device).cuda_stream)      # launches on one stream are ordered
+        key = (batch, n_q, self.torch.cuda.current_stream(self.device).cuda_stream)      # launches on one stream are ordered
         if key not in cache:
             if len(cache) >= 8:
                 cache.pop(next(iter(cache)))
-            cache[key] = self.torch.zeros(int(self.lib.xrsd_residual_workspace_bytes(batch)), dtype=self.torch.uint8,
+            cache[key] = self.torch.zeros(int(self.lib.xrsd_residual_workspace_bytes(batch, n_q)), dtype=self.torch.uint8,
                                           device=self.device)
         return cache[key]
 
@@ -419,7 +419,7 @@ class Engine(object):
         if layout.n_xtal and tables is None:
             tables = self.build_tables(layout, d_p, batch, params_host=host_params)
         chi2 = out if out is not None else torch.empty(batch, dtype=torch.float64, device=self.device)
-        ws = self.residual_workspace(batch)
+        ws = self.residual_workspace(batch, n_q)
         abi.check(self.lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_p.data_ptr(),
                                                d_p.shape[1], batch, C.byref(tables.c) if tables is not None else None,
                                                d_I.data_ptr(), d_dI.data_ptr() if d_dI is not None else None, ld,

@@ -4,17 +4,12 @@ Replaces the optimiser loop of the reference's fit() (system/__init__.py:220-278
 Nelder-Mead, one full compute_intensity per simplex evaluation with the reflection table
 rebuilt every time).  The objective is the reference's scalar chi^2 (evaluate_residual); its
 residual vector r_i = sqrt(w_i / sum w) (f(I_model) - f(I_obs)), f = log or identity, is what
-LM linearises.  One iteration for the whole batch is five launches:
-
-    tables(params) -> jacobian (n_free+1 evaluations per system, fused to JTJ/JTr/chi2)
-    -> lm_propose (damped solve, projection on the bounds) -> tables(trial) + residual(trial)
-    -> lm_update (accept / reject, damping update, convergence flags)
-
-No host synchronisation is needed inside the loop except the reflection-table capacity check.
-With a linear free parameter (an I0) the loop keeps the base pattern on the device between iterations
-(see lm_fit_batch): the trial evaluation is then a patterns-only variants launch plus the chi2 of the stored
-pattern (xrsd_pattern_chi2_batch) instead of the residual kernel, accepted rows move into the base workspace
-(xrsd_copy_rows_masked) and the next Jacobian evaluates the perturbed variants only.
+LM linearises.  lm_fit_batch describes the loop: every launch of an iteration is one of the
+library's own kernels (Jacobian variants + reduction for the systems whose last step was
+accepted, damped solve with a relative trust region, shared reflection tables, trial pattern,
+fused chi2 / accept-reject, accepted rows taken over), the host reads one flag word every few
+iterations.  nm_fit_batch is the reference's own optimiser (Nelder-Mead), batched, for
+like-for-like comparison and for parameters LM cannot differentiate (atomic coordinates).
 """
 import ctypes as C
 import os
@@ -99,7 +94,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     if nf == 0:
         raise ValueError("no free parameters to fit")
     if nf > abi.MAX_FREE:
-        raise ValueError("at most %d free parameters per system (XRSD_MAX_FREE); this fit has %d" % (abi.MAX_FREE, nf))
+        raise lowering.CapacityError("at most %d free parameters per system (XRSD_MAX_FREE); this fit has %d" % (abi.MAX_FREE, nf))
     if layout.coordinate_slots() & set(free_slots):
         # Free atomic coordinates (u_i, v_i, w_i of a polyatomic cell) act through the reflection tables, which the
         # Jacobian variants hold fixed: their finite-difference columns would be identically zero and LM
@@ -212,7 +207,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     n_var = eng.jacobian_variants(layout, jac_slots, ties)
     persist = resident_bytes(batch) <= resident_limit
     key0, key1 = ("lm", id(d_p), 0), ("lm", id(d_p), 1)
-    res_ws = None if persist else eng.residual_workspace(batch)
+    res_ws = None if persist else eng.residual_workspace(batch, n_q)
     base_valid = False
     tight = bool(layout.n_xtal) and loop_cells < max_cells
     chi2_init = None

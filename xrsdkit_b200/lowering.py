@@ -42,6 +42,13 @@ _LATTICE_CLASS['triclinic'] = abi.LAT_TRICLINIC
 _LAT_SLOTS = ('a', 'b', 'c', 'alpha', 'beta', 'gamma')
 
 
+class CapacityError(ValueError, NotImplementedError):
+    """An input beyond one of the engine's fixed capacities (include/xrsd_b200.h: XRSD_MAX_POPS, XRSD_MAX_SPECIES,
+    XRSD_MAX_PARAMS, XRSD_MAX_FREE, XRSD_MAX_TIES); the message names the limit.  The reference has no such limits,
+    so this is a ValueError about the input as far as its callers are concerned (and a NotImplementedError for
+    callers of the round-1 interface)."""
+
+
 class SystemLayout(object):
     """ctypes layout + the parameter bookkeeping that goes with it."""
 
@@ -99,7 +106,7 @@ class SystemLayout(object):
             for k, (src, scale) in enumerate(terms):
                 out.append((i if k == 0 else -(i + 1), src, scale, off if k == 0 else 0.0))
         if len(out) > abi.MAX_TIES:
-            raise NotImplementedError("at most %d constraint terms per system (XRSD_MAX_TIES)" % abi.MAX_TIES)
+            raise CapacityError("at most %d constraint terms per system (XRSD_MAX_TIES); this system has %d" % (abi.MAX_TIES, len(out)))
         dsts = set(tie_slot(t[0]) for t in out)
         if any(t[1] in dsts and t[2] != 0.0 for t in out):
             raise NotImplementedError("chained constraints (a constrained parameter used in another constraint_expr)")
@@ -228,7 +235,8 @@ def _lower_population(structure, form, settings, slots, q_last, table_slot):
         elif form == 'polyatomic':
             n_at = settings['n_atoms']
             if n_at > abi.MAX_SPECIES:
-                raise NotImplementedError('polyatomic populations are limited to {} atoms per cell'.format(abi.MAX_SPECIES))
+                raise CapacityError('polyatomic populations are limited to {} atoms per cell (XRSD_MAX_SPECIES); '
+                                    'this one has {}'.format(abi.MAX_SPECIES, n_at))
             p.n_species = n_at
             for i in range(n_at):
                 p.species_form[i] = abi.FORM_ATOMIC
@@ -376,9 +384,11 @@ def lower_system(system, q):
             n_x += 1
         pops.append(lp)
     if len(pops) > abi.MAX_POPS:
-        raise NotImplementedError('a system layout holds at most {} populations'.format(abi.MAX_POPS - 1))
+        raise CapacityError('a system layout holds at most {} populations besides the noise model (XRSD_MAX_POPS = {}); '
+                            'this system has {}'.format(abi.MAX_POPS - 1, abi.MAX_POPS, len(pops) - 1))
     if len(names) > abi.MAX_PARAMS:
-        raise NotImplementedError('a system layout holds at most {} parameters'.format(abi.MAX_PARAMS))
+        raise CapacityError('a system layout holds at most {} parameters (XRSD_MAX_PARAMS); this system has {}'
+                            .format(abi.MAX_PARAMS, len(names)))
     L.n_pops = len(pops)
     L.n_params = max(1, len(names))
     L.n_xtal = n_x
