@@ -320,8 +320,10 @@ int xrsd_copy_rows_masked(double *d_dst, int64_t dst_stride, const double *d_src
  * populations make no copies at all: the kernel reads the parameters from and writes I(q) to mapped
  * pinned memory.
  * Threading: the d_* entry points above keep no state between calls (xrsd_last_error is per thread)
- * and may be called concurrently on different streams; this call and xrsd_release_workspace share one
- * process-wide workspace on the current device and serialise on a mutex. */
+ * and may be called concurrently on different streams; this call keeps one workspace (device scratch, mapped
+ * pinned staging buffer, a non-blocking stream of its own) per calling thread and device, selected by the
+ * thread's current device (cudaSetDevice): threads evaluate side by side without a lock, and a process may drive
+ * several GPUs.  xrsd_release_workspace frees the calling thread's workspaces; they also go when the thread ends. */
 int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int32_t n_q,
                               const double *params, int32_t ld_params, int32_t batch,
                               double *I_out, int64_t ld_I);

@@ -7,7 +7,6 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
-#include <mutex>
 #include <vector>
 #include "../../include/xrsd_b200.h"
 
@@ -558,7 +557,14 @@ int xrsd_probe_fp64_peak(double *tflops, double *elapsed_ms, void *stream) {
 
 // ------------------------------------------------------------------ host-buffer convenience path
 namespace {
+// One workspace per (calling thread, device): device scratch, a mapped pinned staging buffer and a non-blocking
+// stream of its own, so that the threads of a caller evaluate side by side (no process-wide lock, nothing on the
+// legacy default stream) and a process that drives several GPUs gets a workspace on each.  A thread's workspaces are
+// released by xrsd_release_workspace() or when the thread ends.
+constexpr int kMaxDevices = 32;
 struct Workspace {
+  int device = -1;
+  cudaStream_t stream = nullptr;
   void *base = nullptr;
   size_t bytes = 0;
   double *pinned = nullptr;
@@ -566,18 +572,55 @@ struct Workspace {
   size_t pinned_bytes = 0;
   std::vector<double> q_host;     // the grid currently resident at offset 0 of the workspace (skips its upload)
   bool q_valid = false;
-} g_ws;
-std::mutex g_ws_mutex;      // the host-buffer call and the release serialise on the one workspace
+  void release() {
+    if (device < 0) return;
+    int cur = -1;
+    const bool switched = cudaGetDevice(&cur) == cudaSuccess && cur != device && cudaSetDevice(device) == cudaSuccess;
+    q_valid = false;
+    if (pinned) cudaFreeHost(pinned);
+    pinned = nullptr;
+    pinned_dev = nullptr;
+    pinned_bytes = 0;
+    if (base) cudaFree(base);
+    base = nullptr;
+    bytes = 0;
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+    if (switched) cudaSetDevice(cur);
+    cudaGetLastError();           // at process exit the runtime may already be unloading: nothing to report
+    device = -1;
+  }
+  ~Workspace() { release(); }
+};
+struct ThreadWorkspaces { Workspace dev[kMaxDevices]; };
+thread_local ThreadWorkspaces t_ws;
+thread_local Workspace *ws_cur = nullptr;
+
+int ws_select() {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev < 0 || dev >= kMaxDevices) return fail(XRSD_EINVAL, "device ordinal %d beyond %d", dev, kMaxDevices - 1);
+  Workspace &w = t_ws.dev[dev];
+  if (w.device != dev) {
+    w.release();
+    e = cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { w.stream = nullptr; return cuda_fail(e, "cudaStreamCreate"); }
+    w.device = dev;
+  }
+  ws_cur = &w;
+  return XRSD_OK;
+}
 
 int ws_reserve(size_t bytes) {
-  if (bytes <= g_ws.bytes) return XRSD_OK;
-  if (g_ws.base) cudaFree(g_ws.base);
-  g_ws.base = nullptr;
-  g_ws.bytes = 0;
-  g_ws.q_valid = false;
-  cudaError_t e = cudaMalloc(&g_ws.base, bytes);
+  if (bytes <= ws_cur->bytes) return XRSD_OK;
+  if (ws_cur->base) cudaFree(ws_cur->base);
+  ws_cur->base = nullptr;
+  ws_cur->bytes = 0;
+  ws_cur->q_valid = false;
+  cudaError_t e = cudaMalloc(&ws_cur->base, bytes);
   if (e != cudaSuccess) return fail(XRSD_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
-  g_ws.bytes = bytes;
+  ws_cur->bytes = bytes;
   return XRSD_OK;
 }
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -587,16 +630,16 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 constexpr size_t kPinnedMax = 4u << 20;
 double *pinned_reserve(size_t bytes) {
   if (bytes > kPinnedMax) return nullptr;
-  if (bytes <= g_ws.pinned_bytes) return g_ws.pinned;
-  if (g_ws.pinned) cudaFreeHost(g_ws.pinned);
-  g_ws.pinned = nullptr;
-  g_ws.pinned_bytes = 0;
+  if (bytes <= ws_cur->pinned_bytes) return ws_cur->pinned;
+  if (ws_cur->pinned) cudaFreeHost(ws_cur->pinned);
+  ws_cur->pinned = nullptr;
+  ws_cur->pinned_bytes = 0;
   const size_t want = std::max(bytes, (size_t)256 << 10);
-  g_ws.pinned_dev = nullptr;
-  if (cudaHostAlloc((void **)&g_ws.pinned, want, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); g_ws.pinned = nullptr; return nullptr; }
-  g_ws.pinned_bytes = want;
-  if (cudaHostGetDevicePointer((void **)&g_ws.pinned_dev, g_ws.pinned, 0) != cudaSuccess) { cudaGetLastError(); g_ws.pinned_dev = nullptr; }
-  return g_ws.pinned;
+  ws_cur->pinned_dev = nullptr;
+  if (cudaHostAlloc((void **)&ws_cur->pinned, want, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); ws_cur->pinned = nullptr; return nullptr; }
+  ws_cur->pinned_bytes = want;
+  if (cudaHostGetDevicePointer((void **)&ws_cur->pinned_dev, ws_cur->pinned, 0) != cudaSuccess) { cudaGetLastError(); ws_cur->pinned_dev = nullptr; }
+  return ws_cur->pinned;
 }
 // Small non-crystalline calls skip both copies: the kernel reads the parameter rows from the mapped pinned buffer
 // and writes I(q) straight into it (staged mode writes every value once, coalesced: posted PCIe writes), so the
@@ -625,15 +668,8 @@ double xrsd_uniform_step(const double *q, int32_t n) {
 }
 
 void xrsd_release_workspace(void) {
-  std::lock_guard<std::mutex> lock(g_ws_mutex);
-  g_ws.q_valid = false;
-  if (g_ws.pinned) cudaFreeHost(g_ws.pinned);
-  g_ws.pinned = nullptr;
-  g_ws.pinned_dev = nullptr;
-  g_ws.pinned_bytes = 0;
-  if (g_ws.base) cudaFree(g_ws.base);
-  g_ws.base = nullptr;
-  g_ws.bytes = 0;
+  for (int d = 0; d < kMaxDevices; ++d) t_ws.dev[d].release();      // the calling thread's workspaces, every device
+  ws_cur = nullptr;
 }
 
 int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int32_t n_q, const double *params,
@@ -643,7 +679,8 @@ int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int3
   if (batch <= 0 || n_q <= 0) return XRSD_OK;
   if (!q || !params || !I_out) return fail(XRSD_EINVAL, "NULL host pointer");
   if (ld_I < n_q) return fail(XRSD_EINVAL, "ld_I < n_q");
-  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  rc = ws_select();
+  if (rc) return rc;
   const int n_x = layout->n_xtal;
   const size_t n_tab = (size_t)batch * n_x;
   const int cap_shell = 1024, n_pairs = XRSD_MAX_PAIRS;
@@ -660,25 +697,25 @@ int xrsd_intensity_batch_host(const xrsd_layout_t *layout, const double *q, int3
   const size_t o_sg = off; off += align256(n_tab * cap_shell * n_pairs * 8);
   rc = ws_reserve(off);
   if (rc) return rc;
-  char *base = (char *)g_ws.base;
-  cudaStream_t s = 0;
+  char *base = (char *)ws_cur->base;
+  cudaStream_t s = ws_cur->stream;
   // repeated calls on the same grid (the usual case: one measured pattern, many evaluations) skip the upload of q
   cudaError_t e = cudaSuccess;
-  const bool same_q = g_ws.q_valid && g_ws.q_host.size() == (size_t)n_q && memcmp(g_ws.q_host.data(), q, (size_t)n_q * 8) == 0;
+  const bool same_q = ws_cur->q_valid && ws_cur->q_host.size() == (size_t)n_q && memcmp(ws_cur->q_host.data(), q, (size_t)n_q * 8) == 0;
   if (!same_q) {
     e = cudaMemcpyAsync(base + o_q, q, (size_t)n_q * 8, cudaMemcpyHostToDevice, s);
-    g_ws.q_host.assign(q, q + n_q);
-    g_ws.q_valid = (e == cudaSuccess);
+    ws_cur->q_host.assign(q, q + n_q);
+    ws_cur->q_valid = (e == cudaSuccess);
   }
   const size_t p_bytes = (size_t)batch * ld_params * 8, I_bytes = (size_t)batch * n_q * 8;
   double *pin = pinned_reserve(align256(p_bytes) + I_bytes);
   if (pin) memcpy(pin, params, p_bytes);
-  const bool zero_copy = pin && g_ws.pinned_dev && n_x == 0 && I_bytes <= kZeroCopyMax && zero_copy_enabled();
+  const bool zero_copy = pin && ws_cur->pinned_dev && n_x == 0 && I_bytes <= kZeroCopyMax && zero_copy_enabled();
   if (e == cudaSuccess && !zero_copy)
     e = cudaMemcpyAsync(base + o_p, pin ? (const void *)pin : (const void *)params, p_bytes, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) { g_ws.q_valid = false; return cuda_fail(e, "H2D copy"); }
-  const double *d_par = zero_copy ? g_ws.pinned_dev : (const double *)(base + o_p);
-  double *d_out = zero_copy ? g_ws.pinned_dev + align256(p_bytes) / 8 : (double *)(base + o_I);
+  if (e != cudaSuccess) { ws_cur->q_valid = false; return cuda_fail(e, "H2D copy"); }
+  const double *d_par = zero_copy ? ws_cur->pinned_dev : (const double *)(base + o_p);
+  double *d_out = zero_copy ? ws_cur->pinned_dev + align256(p_bytes) / 8 : (double *)(base + o_I);
   xrsd_tables_t T = {};
   if (n_x) {
     T.cap_shell = cap_shell; T.cap_refl = 0; T.n_pairs_max = n_pairs;

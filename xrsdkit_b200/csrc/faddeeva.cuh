@@ -6,8 +6,8 @@
 // is CONSTANT for a whole pattern, so everything that depends on y alone is a
 // per-pattern table (VoigtConst) staged once in shared memory:
 //
-//   |z|^2 >= 64 : asymptotic series  w(z) ~ i/(sqrt(pi) z) * sum_k (2k-1)!!/(2 z^2)^k,
-//                 complex Horner in u = 1/z^2 with 3..12 terms chosen from |z|^2.
+//   |z|^2 >= 64 : asymptotic series  w(z) ~ i/(sqrt(pi) z) * sum_k (2k-1)!!/(2 z^2)^k, k <= 5, 7 or 12 by |z|^2;
+//                 its real part through a real three-term recurrence (rew_far).
 //   otherwise   : the exponential series of Zaghloul & Ali (ACM TOMS 38, 15 (2011),
 //                 Algorithm 916, eq. 13/14) with spacing a = 0.5183..., real part:
 //                   Re w = e^{-x^2} { [erfcx(y) - c y S1] cos(2xy) + c x sin(xy) sinc(xy)
@@ -54,54 +54,46 @@ __device__ __forceinline__ void voigt_constants(VoigtConst *vc, double y, int ti
   }
 }
 
-// asymptotic branch, |z|^2 >= 64:  w(z) ~ i/(sqrt(pi) z) P(u), P(u) = sum_k c_k u^k, u = 1/z^2,
-// c_k = (2k-1)!!/2^k, truncated where the first neglected term is < 1e-13 relative (5, 7 or 12 terms
-// by |z|^2).  P is evaluated in Estrin form: the dependency depth is 6..10 FP64 operations instead of
-// 2 per Horner step, which matters because this loop is latency- not throughput-bound (ncu: 45 % of
-// the stall samples were fixed-latency waits with the Horner form).
-struct Cplx { double r, i; };
-__device__ __forceinline__ Cplx c_lin(double c0, double c1, double ur, double ui) { return {fma(c1, ur, c0), c1 * ui}; }
-// a + u*b
-__device__ __forceinline__ Cplx c_fma(Cplx a, double ur, double ui, Cplx b) {
-  return {fma(ur, b.r, fma(-ui, b.i, a.r)), fma(ur, b.i, fma(ui, b.r, a.i))};
-}
-__device__ __forceinline__ void c_sqr(double ur, double ui, double &vr, double &vi) {
-  vr = fma(ur, ur, -(ui * ui));
-  vi = 2.0 * ur * ui;
-}
-
+// asymptotic branch, |z|^2 >= 64:  w(z) ~ i/(sqrt(pi) z) sum_k c_k / z^2k,  c_k = (2k-1)!!/2^k, truncated where the
+// first neglected term is < 1e-13 relative (k <= 5, 7 or 12 by |z|^2).  Only the real part is needed, and
+//     Re[i / z^(2k+1)] = Im(z^(2k+1)) / |z|^(4k+2) =: u_k
+// obeys a REAL three-term recurrence (z^2 and conj(z)^2 are the roots of its characteristic polynomial):
+//     u_k+1 = (2 Re z^2 / |z|^4) u_k - u_k-1 / |z|^4,     u_0 = y / |z|^2,  u_-1 = -y,
+// whose two solutions have equal modulus (errors grow linearly in k, no cancellation: every u_k carries the factor y
+// that makes the far wing of a narrow-Lorentzian Voigt profile small).  Three FP64 instructions per term -- product,
+// recurrence, accumulation with the coefficient as an immediate -- against four per term plus two-constant linear
+// factors for a complex Horner / Estrin evaluation of the same sum: 25 instead of 42 FP64 instructions for k <= 5
+// (this branch is ~40 % of the instructions of a crystalline pattern, profiles/r02_ncu_cfg3.txt), and the longer
+// truncations continue the same recurrence.  Max relative difference to scipy's wofz 1.5e-13 (at |z| = 8).
 __device__ __forceinline__ double rew_far(double x, double y, double z2) {
-  const double r2 = __drcp_rn(z2);
-  const double r4 = r2 * r2;
-  const double ur = fma(x, x, -(y * y)) * r4;   // u = 1/z^2 = conj(z)^2/|z|^4
-  const double ui = -2.0 * x * y * r4;
-  double u2r, u2i;
-  c_sqr(ur, ui, u2r, u2i);
-  const Cplx L0 = c_lin(1.0, 0.5, ur, ui), L1 = c_lin(0.75, 1.875, ur, ui), L2 = c_lin(6.5625, 29.53125, ur, ui);
-  Cplx P;
-  if (z2 >= 1024.0) {                          // 5 terms
-    P = c_fma(L0, u2r, u2i, c_fma(L1, u2r, u2i, L2));
-  } else {
-    double u4r, u4i;
-    c_sqr(u2r, u2i, u4r, u4i);
-    const Cplx L3 = c_lin(162.421875, 1055.7421875, ur, ui);
-    const Cplx A = c_fma(L0, u2r, u2i, L1);
-    const Cplx B = c_fma(L2, u2r, u2i, L3);
-    if (z2 >= 256.0) {                         // 7 terms
-      P = c_fma(A, u4r, u4i, B);
-    } else {                                   // 12 terms down to |z| = 8
-      double u8r, u8i;
-      c_sqr(u4r, u4i, u8r, u8i);
-      const Cplx L4 = c_lin(7918.06640625, 67303.564453125, ur, ui);
-      const Cplx L5 = c_lin(639383.8623046875, 6713530.554199219, ur, ui);
-      Cplx C = c_fma(L4, u2r, u2i, L5);
-      C.r = fma(u4r, 77205601.37329102, C.r);  // + c12 u^4 (inside the u^8 bracket)
-      C.i = fma(u4i, 77205601.37329102, C.i);
-      P = c_fma(c_fma(A, u4r, u4i, B), u8r, u8i, C);
+  // 1/|z|^2 for 64 <= |z|^2 < inf: the hardware seed (MUFU.RCP64H, ~2^-20) and two Newton steps -- what __drcp_rn
+  // does without its test and slow path for subnormal / huge arguments (4 of its 11 instructions)
+  double t;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(t) : "d"(z2));
+  {
+    double e = fma(-z2, t, 1.0);
+    e = fma(e, e, e);
+    t = fma(t, e, t);
+    e = fma(-z2, t, 1.0);
+    t = fma(t, e, t);
+  }
+  const double b = t * t;                               // 1/|z|^4
+  const double al = 2.0 * fma(x, x, -(y * y)) * b;      // 2 Re z^2 / |z|^4
+  double um = y * t;                                    // u_0
+  double u = fma(al, um, b * y);                        // u_1
+  double sum = fma(0.5, u, um);
+  double un;
+#define XRSD_FAR_TERM(ck) un = fma(al, u, -(b * um)); sum = fma(ck, un, sum); um = u; u = un;
+  XRSD_FAR_TERM(0.75) XRSD_FAR_TERM(1.875) XRSD_FAR_TERM(6.5625) XRSD_FAR_TERM(29.53125)
+  if (z2 < 1024.0) {
+    XRSD_FAR_TERM(162.421875) XRSD_FAR_TERM(1055.7421875)
+    if (z2 < 256.0) {                                   // down to |z| = 8
+      XRSD_FAR_TERM(7918.06640625) XRSD_FAR_TERM(67303.564453125) XRSD_FAR_TERM(639383.8623046875)
+      XRSD_FAR_TERM(6713530.554199219) XRSD_FAR_TERM(77205601.37329102)
     }
   }
-  // i/z = (y + i x)/|z|^2  ->  Re[(i/z) P] = (y Re P - x Im P)/|z|^2
-  return r2 * fma(y, P.r, -(x * P.i)) * 0.56418958354775628695;   // 1/sqrt(pi)
+#undef XRSD_FAR_TERM
+  return sum * 0.56418958354775628695;   // 1/sqrt(pi)
 }
 
 // exponential-series branch, |z|^2 < 64 (so |x| < 8).  x must be >= 0 (Re w is even in x).
@@ -182,13 +174,20 @@ __device__ __forceinline__ double rew_table(double x, const double *tab) {
   return cheb17(tab + k * VOIGT_TAB_N, t);
 }
 
-// Re w(x + i y) with y = vc->y >= 0; `tab` (optional) is the pattern's near-branch table.
+// Re w(x + i y) with y = vc->y > 0; `tab` (optional) is the pattern's near-branch table.  (y == 0 is the Gaussian
+// exp(-x^2): rew_any below; the crystalline sums route that case to the closed form before they get here.)
 __device__ __forceinline__ double rew(double x, const VoigtConst *vc, const double *tab = nullptr) {
   x = fabs(x);
   const double y = vc->y;
   const double z2 = fma(x, x, y * y);
-  if (z2 >= 64.0) return (y == 0.0) ? exp(-x * x) : rew_far(x, y, z2);
+  if (z2 >= 64.0) return rew_far(x, y, z2);
   return tab ? rew_table(x, tab) : rew_near(x, vc);
+}
+
+// any y >= 0
+__device__ __forceinline__ double rew_any(double x, const VoigtConst *vc, const double *tab = nullptr) {
+  if (vc->y == 0.0 && x * x >= 64.0) return exp(-x * x);
+  return rew(x, vc, tab);
 }
 
 }  // namespace xrsd

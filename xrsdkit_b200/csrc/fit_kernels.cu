@@ -168,8 +168,8 @@ residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
   if (active != nullptr && !active[b]) return;
   const int q_begin = tile * q_per_cta;
   const int q_count = min(q_per_cta, n_q - q_begin);
-  double *I_sm = smem_d;
-  double *scratch = smem_d + ((q_per_cta + 1) & ~1);
+  double *scratch = smem_d;                   // at the base: a compile-time address inside the profile loops
+  double *I_sm = smem_d + scratch_doubles;
   accumulate_system<2, RM, HX>(L, params + (size_t)b * ldp, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S);
   const double *obs = Iobs + (size_t)b * ld_obs + q_begin;
   const double *err = dI ? dI + (size_t)b * ld_obs + q_begin : nullptr;
@@ -223,8 +223,10 @@ residual_kernel(const __grid_constant__ xrsd_layout_t L, const xrsd_objective_t 
 //     per-system accumulator with FP64 atomics; the chunk that takes the last ticket normalises and
 //     writes the outputs.  (A first version reduced inside the variant kernel by the last-finishing
 //     CTA of each system: that serial tail cost 25 % of the whole Jacobian.)
+__host__ __device__ __forceinline__ int np_ceil2(int n) { return (n + 1) & ~1; }
+
 template <bool RM, bool HX>
-__global__ void __launch_bounds__(EVAL_THREADS, HX ? 8 : 6)   // crystalline layouts, 10^4 cfg4 systems, same box: 8 CTAs x 64 registers 15.5 ms, 10 x 48 (spills) 16.1 (round 1: 11.8 / 11.5 per 4069 systems, 12 x 40 14.4, 6 x 80 7 % behind 8)
+__global__ void __launch_bounds__(EVAL_THREADS, HX ? XRSD_HX_MIN_CTAS : 6)   // crystalline layouts, 10^4 cfg4 systems, same box: 8 CTAs x 64 registers 15.5 ms, 10 x 48 (spills) 16.1 (round 1: 11.8 / 11.5 per 4069 systems, 12 x 40 14.4, 6 x 80 7 % behind 8)
 jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ q, int n_q,
                          const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T, const FreeSet F,
                          double rel_step, double *__restrict__ Fvar, int q_per_cta, int n_tiles, int pattern_doubles,
@@ -243,9 +245,12 @@ jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *
   if (active != nullptr && !active[b]) return;
   if (skip_base && v == 0) return;            // base pattern and running totals are already in the workspace
   const int np = L.n_params;
-  double *I_sm = smem_d;
-  double *scratch = smem_d + pattern_doubles;
-  double *prm_s = scratch + scratch_doubles;
+  // shared memory: shell scratch at the base (a compile-time address), the parameter row, then -- staged mode only --
+  // the pattern span.  Direct mode is the crystalline instantiation (HX), see intensity_kernel.cu.
+  if ((pattern_doubles == 0) != HX) return;
+  double *scratch = smem_d;
+  double *prm_s = smem_d + scratch_doubles;
+  double *I_sm = prm_s + ((np_ceil2(L.n_params)));
   const double *prm = params + (size_t)b * ldp;
   for (int i = tid; i < np; i += EVAL_THREADS) prm_s[i] = prm[i];
   __syncthreads();
@@ -263,13 +268,13 @@ jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *
   // totals after each population
   double *slab0 = Fvar + (size_t)b * n_slab * n_q;
   double *dst = slab0 + (size_t)v * n_q + q_begin;
-  if (pattern_doubles == 0) I_sm = dst;
+  if constexpr (HX) I_sm = dst;
   // a variant whose parameter belongs to one population evaluates that population alone (the reduction takes the
   // difference against the base's own term for it, from the running totals)
   const int only_pop = v > 0 ? F.vpop_of[F.free_of_var[v]] : -1;
   accumulate_system<2, RM, HX>(L, prm_s, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S, prm,
                                v == 0 ? slab0 + (size_t)nv * n_q + q_begin : nullptr, n_q, only_pop);
-  if (pattern_doubles != 0)
+  if constexpr (!HX)
     for (int i = tid; i < q_count; i += EVAL_THREADS) dst[i] = I_sm[i];
 }
 
@@ -289,7 +294,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // n_free <= 8: capped at 128 registers (4 CTAs/SM; the compiler otherwise takes 232 for 2 -- measured +8 % on cfg4
 // with 140 bytes of spills); the 16-parameter instantiation spills 1.5 KB under that cap and keeps 2 CTAs/SM.
 template <int NF, int RB>
-__global__ void __launch_bounds__(JR_THREADS, NF <= 8 ? 4 : 2)
+#ifndef XRSD_JR_MIN_CTAS
+#define XRSD_JR_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(JR_THREADS, NF <= 8 ? XRSD_JR_MIN_CTAS : 2)
 jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__restrict__ q, int n_q,
                        const double *__restrict__ params, int ldp, int batch, const double *__restrict__ Iobs,
                        const double *__restrict__ dI, long long ld_obs, const FreeSet F, double rel_step,
@@ -303,6 +311,7 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
   // around 150 live accumulators (the first version was latency-bound at 0.45 TB/s).
   extern __shared__ __align__(16) double ring[];
   __shared__ double fold[JR_THREADS / 32][RB * NF + NF + 2];
+  __shared__ int4 dsc[NF];          // ring offsets (doubles) of the three slab rows of every difference quotient
   __shared__ int is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks;
@@ -327,6 +336,12 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
   const int z_row = n_rows;                          // one more row per stage that stays zero: the "absent term" of a quotient
   for (int i = tid; i < JR_STAGES * JR_THREADS; i += JR_THREADS)
     ring[((size_t)(i / JR_THREADS) * (n_rows + 1) + z_row) * JR_THREADS + (i % JR_THREADS)] = 0.0;
+  // the slab rows of each quotient as ring offsets, once per CTA: inside the loop the FreeSet lookups (constant bank
+  // load, test for the absent row, multiply -- per parameter and q-point) were 13 % of the kernel's instructions
+  if (tid < NF)
+    dsc[tid] = make_int4((F.ra[tid] < 0 ? z_row : F.ra[tid]) * JR_THREADS, (F.rb[tid] < 0 ? z_row : F.rb[tid]) * JR_THREADS,
+                         (F.rc[tid] < 0 ? z_row : F.rc[tid]) * JR_THREADS, 0);
+  __syncthreads();
   const int n_it = (q_hi - q_lo + JR_THREADS - 1) / JR_THREADS;
   auto issue = [&](int it) {             // stage the q-point of iteration `it` (if any); always closes a group
     const int i = q_lo + it * JR_THREADS + tid;
@@ -371,9 +386,8 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
       double D[NF];
 #pragma unroll
       for (int j = 0; j < NF; ++j) {
-        const int ia = (F.ra[j] < 0 ? z_row : F.ra[j]) * JR_THREADS, ib = (F.rb[j] < 0 ? z_row : F.rb[j]) * JR_THREADS,
-                  ic = (F.rc[j] < 0 ? z_row : F.rc[j]) * JR_THREADS;
-        double d = scale[j] * ((Fs[ia] - Fs[ib]) + Fs[ic]) * inv;
+        const int4 o = dsc[j];
+        double d = scale[j] * ((Fs[o.x] - Fs[o.y]) + Fs[o.z]) * inv;
         if (O.logI_weighted) {
           if (fabs(d) < 1.0e-2) d = d * fma(d, fma(d, 1.0 / 3.0, -0.5), 1.0);      // |error| < x^4 / 4
           else d = (d > -1.0) ? log1p(d) : 0.0;          // a variant intensity <= 0 carries no information (NaN: below)

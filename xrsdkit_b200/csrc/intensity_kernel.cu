@@ -8,10 +8,17 @@
 // Replaces System.compute_intensity, system/__init__.py:112-130.
 #include "system_eval.cuh"
 
+#ifndef XRSD_NX_MIN_CTAS
+#define XRSD_NX_MIN_CTAS 5      // layouts without crystalline populations: 96 registers
+#endif
+#ifndef XRSD_NX_QPT
+#define XRSD_NX_QPT 2           // q-points per thread and pass of the size-distribution loop
+#endif
+
 namespace xrsd {
 
 template <int QPT, bool RM, bool HX>
-__global__ void __launch_bounds__(EVAL_THREADS, HX ? 8 : 5)
+__global__ void __launch_bounds__(EVAL_THREADS, HX ? XRSD_HX_MIN_CTAS : XRSD_NX_MIN_CTAS)
 intensity_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ q, int n_q,
                  const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
                  double *__restrict__ I_out, long long ldI, int q_per_cta, int n_tiles, int scratch_doubles,
@@ -25,13 +32,18 @@ intensity_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restri
   const int q_begin = tile * q_per_cta;
   const int q_count = min(q_per_cta, n_q - q_begin);
   double *dst = I_out + (size_t)b * ldI + q_begin;
-  double *I_sm = direct ? dst : smem_d;
-  double *scratch = direct ? smem_d : smem_d + ((q_per_cta + 1) & ~1);
+  // direct mode == a layout with crystalline populations (HX): a compile-time fact, so the accumulation buffer has a
+  // known address space and the shell scratch sits at the base of the dynamic shared memory -- with `direct` as a
+  // run-time flag the compiler re-derived the scratch address inside the profile loops (9 % of the instructions of
+  // the cfg3 launch, profiles/sass_by_line.py on r02_cfg3)
+  if (direct != (HX ? 1 : 0)) return;
+  double *scratch = smem_d;
+  double *I_sm = HX ? dst : smem_d + scratch_doubles;
   // cum_out (optional): [batch][n_pops][n_q] running totals after the noise model and after each
   // population -- their differences are the per-population patterns (plot decomposition, I0 rescaling)
   accumulate_system<QPT, RM, HX>(L, params + (size_t)b * ldp, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S,
                                  nullptr, cum_out ? cum_out + (size_t)b * L.n_pops * n_q + q_begin : nullptr, n_q);
-  if (!direct)
+  if constexpr (!HX)
     for (int i = threadIdx.x; i < q_count; i += EVAL_THREADS) dst[i] = I_sm[i];
 }
 
@@ -77,7 +89,7 @@ extern "C" cudaError_t xrsd_launch_intensity(const xrsd_layout_t *layout, const 
   const int n_tiles = (n_q + q_per_cta - 1) / q_per_cta;
   const size_t smem = ((direct ? 0 : (size_t)((q_per_cta + 1) & ~1)) + (size_t)scratch_doubles) * sizeof(double);
   auto kern = radial_multi ? intensity_kernel<2, true, true>
-                           : (layout->n_xtal ? intensity_kernel<2, false, true> : intensity_kernel<2, false, false>);
+                           : (layout->n_xtal ? intensity_kernel<2, false, true> : intensity_kernel<XRSD_NX_QPT, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long long n_blocks = (long long)batch * n_tiles;

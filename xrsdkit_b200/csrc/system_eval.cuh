@@ -35,6 +35,9 @@ constexpr int SHELL_CHUNK = 128;
 
 // shared-memory working set of one CTA (besides the pattern buffer)
 constexpr int CHEB_N = 17;                       // Chebyshev nodes of the far-field interpolant (degree 16)
+#ifndef XRSD_HX_MIN_CTAS
+#define XRSD_HX_MIN_CTAS 8                        // resident CTAs per SM the crystalline kernels are compiled for (64 registers; 7 x 72 and 6 x 80 measured 4 % and 9 % slower)
+#endif
 constexpr int CHEB_ROUND = 16;                   // runs of EVAL_THREADS q-points handled between two barriers
                                                  // (measured: 8 -> 16 +3.5 %, 32 the same, 64 loses occupancy)
 
@@ -98,13 +101,20 @@ __device__ __forceinline__ double make_profile(Profile &P, int kind, double p0, 
   return 0.0;
 }
 
+// VOIGT is a compile-time property of the loops that call this (the crystalline branch is instantiated once for Voigt
+// profiles and once for the two closed forms): the kind test per (q, shell) evaluation was 5 % of the kernel's
+// instructions (profiles/sass_by_line.py on the cfg3 capture).
+template <bool VOIGT>
 __device__ __forceinline__ double profile_eval(const Profile &P, const VoigtConst *vc, double x, const double *vtab = nullptr) {
-  if (P.kind == XRSD_PROFILE_VOIGT) return rew(x * P.a, vc, vtab) * P.b;
+  if constexpr (VOIGT) return rew(x * P.a, vc, vtab) * P.b;
   if (P.kind == XRSD_PROFILE_GAUSSIAN) {
     const double u = x * P.a;
     return P.b * exp(-(u * u) * 0.6931471805599453);               // exp(-(x/h)**2 * ln 2)
   }
   return P.b / fma(x, x, P.a);
+}
+__device__ __forceinline__ double profile_eval(const Profile &P, const VoigtConst *vc, double x, const double *vtab = nullptr) {
+  return P.kind == XRSD_PROFILE_VOIGT ? rew_any(x * P.a, vc, vtab) * P.b : profile_eval<false>(P, vc, x, vtab);
 }
 
 // form factor of species `a` of a crystalline population at q
@@ -368,17 +378,25 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         const bool radial_multi = RADIAL_MULTI && radial && n_sp > 1;
         Profile P;
         if (tid == 0) make_cell(pop, prm, &S->cell);
-        if (pop.profile == XRSD_PROFILE_VOIGT) {
-          const double y = make_profile(P, pop.profile, prm[pop.p_hwhm_g], prm[pop.p_hwhm_l]);
+        // A Voigt profile of zero Lorentzian width IS the Gaussian of the same hwhm_g (Re w(x) = exp(-x^2) on the real
+        // axis; tools/peak_math.py:24-47 agree to rounding), so it takes the closed form: the Faddeeva code then never
+        // sees y == 0 and needs no test for it.
+        const bool voigt = pop.profile == XRSD_PROFILE_VOIGT && prm[pop.p_hwhm_l] != 0.0;
+        if (voigt) {
+          const double y = make_profile(P, XRSD_PROFILE_VOIGT, prm[pop.p_hwhm_g], prm[pop.p_hwhm_l]);
           voigt_constants(&S->vc, y, tid);
+        } else if (pop.profile == XRSD_PROFILE_VOIGT) {
+          make_profile(P, XRSD_PROFILE_GAUSSIAN, prm[pop.p_hwhm_g], 0.0);
         } else {
           make_profile(P, pop.profile, prm[pop.p_hwhm], 0.0);
         }
         __syncthreads();
+        auto body = [&](auto voigt_c) {
+        constexpr bool VG = decltype(voigt_c)::value;
         // pass A: normalisation I(0) = sum_s W0_s * profile(0 - q_s)   (scattering/__init__.py:305,331)
         double part = 0.0;
         // does any peak core (|q - q_s| < 8 sigma sqrt2, the Faddeeva near branch) reach into this span?
-        const bool voigt_near_possible = pop.profile == XRSD_PROFILE_VOIGT && S->vc.y < 8.0 && S->vc.y >= VOIGT_TAB_MIN_Y;
+        const bool voigt_near_possible = VG && S->vc.y < 8.0 && S->vc.y >= VOIGT_TAB_MIN_Y;
         const double core_reach = voigt_near_possible ? 8.0 / P.a : 0.0;
         const double span_lo = q_sorted ? q[q_begin] : -INFINITY, span_hi = q_sorted ? q[q_begin + q_count - 1] : INFINITY;
         bool core_here = false;
@@ -393,7 +411,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
           int ipq = 0;
           for (int a = 0; a < n_sp; ++a)
             for (int bb = a; bb < n_sp; ++bb, ++ipq) w0 += ((a == bb) ? 1.0 : 2.0) * sh_geo[(size_t)s * T.n_pairs_max + ipq];
-          part += ltz * w0 * profile_eval(P, &S->vc, 0.0 - qs);
+          part += ltz * w0 * profile_eval<VG>(P, &S->vc, 0.0 - qs);
           core_here = core_here || (qs > span_lo - core_reach && qs < span_hi + core_reach);
         }
         const double norm = block_sum(part, S);
@@ -466,13 +484,13 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         // nodes only and interpolated (degree 16: truncation < 1e-13 relative, tests/test_gpu_parity.py),
         // while the few near shells are summed directly.  This cuts the profile evaluations per q from
         // n_shell to about n_near + CHEB_N n_far / EVAL_THREADS.
-        const bool interp = stage_once && !radial_multi && q_sorted && pop.profile != XRSD_PROFILE_GAUSSIAN &&
+        const bool interp = stage_once && !radial_multi && q_sorted && P.kind != XRSD_PROFILE_GAUSSIAN &&
                             n_shell >= 8 && q_count >= 32;
         if (interp) {
           __syncthreads();
           stage_shells(0, n_shell);
           __syncthreads();
-          const double core = (pop.profile == XRSD_PROFILE_VOIGT) ? fmax(1.0, S->vc.y) / P.a : sqrt(P.a);
+          const double core = VG ? fmax(1.0, S->vc.y) / P.a : sqrt(P.a);
           // rounds of CHEB_ROUND runs: (1) node sums of all runs, (2) coefficients, (3) per-q evaluation;
           // three barriers per round instead of four per run
           for (int r0 = 0; r0 < q_count; r0 += CHEB_ROUND * EVAL_THREADS) {
@@ -490,7 +508,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               int lo = n_shell, hi = 0;
               for (int sl = g; sl < n_shell; sl += 2) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
-                if (fabs(sw.x - c) >= dn) part = fma(sw.y, profile_eval(P, &S->vc, xm - sw.x, vtab), part);
+                if (fabs(sw.x - c) >= dn) part = fma(sw.y, profile_eval<VG>(P, &S->vc, xm - sw.x, vtab), part);
                 else { lo = min(lo, sl); hi = max(hi, sl + 1); }
               }
               S->cheb_part[item] = part;
@@ -534,13 +552,13 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               const int s_lo = S->near_lo[run], s_hi = S->near_hi[run];
               for (int sl = s_lo; sl < s_hi; ++sl) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
-                a_sum = fma(sw.y, profile_eval(P, &S->vc, qi - sw.x, vtab), a_sum);
+                a_sum = fma(sw.y, profile_eval<VG>(P, &S->vc, qi - sw.x, vtab), a_sum);
               }
               finish_q(i, qi, a_sum);
             }
             __syncthreads();
           }
-          break;
+          return;
         }
         for (int off = 0; off < q_count; off += span) {
           double qv[QPT], acc[QPT];
@@ -570,14 +588,14 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               for (int sl = 0; sl < ns; ++sl) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
 #pragma unroll
-                for (int j = 0; j < QPT; ++j) acc[j] = fma(sw.y, profile_eval(P, &S->vc, qv[j] - sw.x, vtab), acc[j]);
+                for (int j = 0; j < QPT; ++j) acc[j] = fma(sw.y, profile_eval<VG>(P, &S->vc, qv[j] - sw.x, vtab), acc[j]);
               }
             } else {
               for (int sl = 0; sl < ns; ++sl) {
                 const double qs = scratch[sl * rec];
 #pragma unroll
                 for (int j = 0; j < QPT; ++j) {
-                  const double v = profile_eval(P, &S->vc, qv[j] - qs, vtab);
+                  const double v = profile_eval<VG>(P, &S->vc, qv[j] - qs, vtab);
 #pragma unroll
                   for (int k = 0; k < (RADIAL_MULTI ? XRSD_MAX_PAIRS : 1); ++k)
                     if (k < n_pairs) accp[j][k] = fma(scratch[sl * rec + 1 + k], v, accp[j][k]);
@@ -614,6 +632,8 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
             I_sm[i] = (fresh ? pending : I_sm[i]) + I0 * (pz * a_sum / norm);     // I0 * (pz*I/I0_norm)
           }
         }
+        };      // body
+        if (voigt) body(std::true_type{}); else body(std::false_type{});
       } break;
       default: break;
     }
