@@ -286,12 +286,14 @@ int xrsd_objective_prepare(const xrsd_objective_t *obj, const double *d_q, int32
  * systems need a new Jacobian (accepted and still running), d_reason[b] why a system left the loop: 1 = converged
  * (chi2 changed by <= ftol relative, or every parameter by <= xtol relative), 2 = lambda beyond lambda_max, 3 = objective
  * not finite; d_active[b] is cleared with it.  A trial point whose reflection tables (trial_tables, optional) carry a
- * non-zero status counts as chi2 = inf and ORs that status into d_flags[0] (optional). */
+ * non-zero status counts as chi2 = inf and ORs that status into d_flags[0]; a system that is still running after this
+ * update raises d_flags[1] to `tag` (atomic max), so a caller that passes the iteration number (from 1) reads "anything
+ * left to do?" from the same two words without a reduction launch (d_flags: two int32, optional). */
 int xrsd_lm_trial_update(const xrsd_objective_t *obj, const double *d_q, int32_t n_q, const double *d_I, int64_t ld_I,
                          int32_t batch, const double *d_Iobs, const double *d_dI, int64_t ld_obs, double *d_params,
                          int32_t ld_params, const double *d_trial, double *d_chi2, double *d_chi2_trial, double *d_lambda,
                          uint8_t *d_active, uint8_t *d_accepted, uint8_t *d_needjac, uint8_t *d_reason, int32_t *d_n_accept,
-                         const xrsd_tables_t *trial_tables, int32_t n_xtal, int32_t *d_flags, double up, double down,
+                         const xrsd_tables_t *trial_tables, int32_t n_xtal, int32_t *d_flags, int32_t tag, double up, double down,
                          double ftol, double xtol, double lambda_max, void *stream);
 
 /* Accepted systems (d_accepted[b] != 0) take over the trial evaluation: the 1 + n_pops slabs of the trial workspace

@@ -86,12 +86,12 @@ def test_argument_errors_without_touching_the_gpu():
     assert lib.xrsd_pattern_chi2_batch(ctypes.byref(Op), 1 << 20, 16, 1 << 21, 16, 2, 1 << 22, None, 16, 1 << 23, None, None) == abi.EINVAL
     assert b"prepared" in lib.xrsd_last_error()                                                    # prepared needs the weight stream
     args = [ctypes.byref(O), 1 << 20, 16, None, 0, 4, None, None, 0, 1 << 21, 6, 1 << 22, 1 << 23, 1 << 24, 1 << 25, 1 << 26,
-            1 << 27, 1 << 28, 1 << 29, 1 << 30, None, 0, None, 8.0, 4.0, 1e-8, 1e-10, 1e10, None]
+            1 << 27, 1 << 28, 1 << 29, 1 << 30, None, 0, None, 1, 8.0, 4.0, 1e-8, 1e-10, 1e10, None]
     bad = list(args)
     bad[15] = None                                                                                 # d_active
     assert lib.xrsd_lm_trial_update(*bad) == abi.EINVAL
     bad = list(args)
-    bad[23] = 1.0                                                                                  # up must be > 1
+    bad[24] = 1.0                                                                                  # up must be > 1
     assert lib.xrsd_lm_trial_update(*bad) == abi.EINVAL and b"up" in lib.xrsd_last_error()
     bad = list(args)
     bad[3], bad[4] = 1 << 19, 8                                                                    # a pattern, but ld_I < n_q and no I_obs

@@ -378,6 +378,38 @@ def test_far_field_interpolation_over_extreme_widths(ref_tables, eng):
         assert same_u and err_u <= TOL_F64, (trial, prof, pars, err_u)
 
 
+def test_voigt_with_zero_lorentzian_width(ref_tables, eng):
+    """hwhm_l == 0: the engine takes the Gaussian closed form for such a Voigt profile (csrc/system_eval.cuh), the
+    reference calls wofz on the real axis (tools/peak_math.py:38-47).  Interpolated path (sorted q), direct path
+    (shuffled q) and the stand-alone profile call.  With hwhm_g = 0.02 the I(0) normalisation of the reference is
+    carried by the extinct reflections (weights ~1e-31 of the allowed ones, Gaussian tails of the allowed ones underflow):
+    those shells are kept for such a system (lowering.py, prune_extinct)."""
+    from oracle import xrsd_oracle as orc
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200.tools import peak_math
+    rs = np.random.RandomState(5)
+    q = np.linspace(0.02, 0.9, 1536)
+    q_shuffled = q[rs.permutation(q.size)]
+    for hl in (0.0, 1e-9):          # 1e-9 is the reference's lower bound for hwhm_l (definitions.py:292)
+        for hg in (2e-2, 5e-2):
+            s = System(x=dict(structure="crystalline", form="spherical",
+                              settings={"lattice": "F_cubic", "space_group": "Fm-3m", "q_max": 0.9, "profile": "voigt"},
+                              parameters={"a": {"value": 41.0}, "r": {"value": 11.0}, "I0": {"value": 2.0},
+                                          "hwhm_g": {"value": hg}, "hwhm_l": {"value": hl}}),
+                       noise={"model": "flat", "parameters": {"I0": {"value": 1e-3}}}, source_wavelength=0.8265617)
+            for grid in (q, q_shuffled):
+                ref = orc.system_intensity(grid, s.to_dict(), **ref_tables)
+                err, same = rel_err(s.compute_intensity(grid), ref, floor_frac=0.0)
+                assert same and err <= TOL_F64, (hl, hg, err)
+    x = np.linspace(-0.2, 0.2, 4001)
+    from scipy.special import wofz
+    sigma = 4e-3 / np.sqrt(2 * np.log(2))
+    want = wofz(x / (sigma * np.sqrt(2))).real / (sigma * np.sqrt(2 * np.pi))
+    got = peak_math.voigt(x, 4e-3, 0.0)
+    ok = want > 1e-300
+    assert np.max(np.abs(got[ok] - want[ok]) / want[ok]) <= TOL_F64
+
+
 def test_components_in_one_launch(golden_systems, eng):
     """Per-population decomposition (noise, each population, total) from one launch against the reference's
     separate per-population evaluations."""

@@ -83,7 +83,7 @@ _SIGNATURES = {
     "xrsd_pattern_chi2_batch": (C.c_int, [C.POINTER(Objective), vp, i32, vp, C.c_int64, i32, vp, vp, C.c_int64, vp, vp, vp]),
     "xrsd_objective_prepare": (C.c_int, [C.POINTER(Objective), vp, i32, vp, vp, i64, i32, vp, vp, i64, vp]),
     "xrsd_lm_trial_update": (C.c_int, [C.POINTER(Objective), vp, i32, vp, i64, i32, vp, vp, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp,
-                                       vp, vp, C.POINTER(Tables), i32, vp, f64, f64, f64, f64, f64, vp]),
+                                       vp, vp, C.POINTER(Tables), i32, vp, i32, f64, f64, f64, f64, f64, vp]),
     "xrsd_lm_accept": (C.c_int, [vp, i32, vp, i64, vp, i64, i32, i32, i32, C.POINTER(Tables), C.POINTER(Tables), i32, vp]),
     "xrsd_copy_rows_masked": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int64, i32, vp, vp]),
     "xrsd_lm_propose": (C.c_int, [vp, i32, i32, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(f64), i32, vp, vp, vp, vp, vp, vp, vp, f64, vp]),

@@ -44,7 +44,7 @@ cudaError_t xrsd_launch_objective_prepare(const xrsd_objective_t *, const double
 cudaError_t xrsd_launch_lm_trial_update(const xrsd_objective_t *, const double *, int, const double *, long long, int,
                                         const double *, const double *, long long, double *, int, const double *, double *,
                                         double *, double *, uint8_t *, uint8_t *, uint8_t *, uint8_t *, int *,
-                                        const xrsd_tables_t *, int, int *, double, double, double, double, double, cudaStream_t);
+                                        const xrsd_tables_t *, int, int *, int, double, double, double, double, double, cudaStream_t);
 cudaError_t xrsd_launch_lm_accept(const uint8_t *, int, double *, long long, const double *, long long, int, int, int,
                                   const xrsd_tables_t *, const xrsd_tables_t *, int, cudaStream_t);
 }
@@ -441,8 +441,8 @@ int xrsd_lm_trial_update(const xrsd_objective_t *obj, const double *d_q, int32_t
                          int32_t batch, const double *d_Iobs, const double *d_dI, int64_t ld_obs, double *d_params,
                          int32_t ld_params, const double *d_trial, double *d_chi2, double *d_chi2_trial, double *d_lambda,
                          uint8_t *d_active, uint8_t *d_accepted, uint8_t *d_needjac, uint8_t *d_reason, int32_t *d_n_accept,
-                         const xrsd_tables_t *trial_tables, int32_t n_xtal, int32_t *d_flags, double up, double down,
-                         double ftol, double xtol, double lambda_max, void *stream) {
+                         const xrsd_tables_t *trial_tables, int32_t n_xtal, int32_t *d_flags, int32_t tag, double up,
+                         double down, double ftol, double xtol, double lambda_max, void *stream) {
   if (batch <= 0) return XRSD_OK;
   if (!obj || !d_params || !d_trial || !d_chi2 || !d_chi2_trial || !d_lambda || !d_active || !d_accepted || !d_needjac ||
       !d_reason || !d_n_accept)
@@ -458,7 +458,7 @@ int xrsd_lm_trial_update(const xrsd_objective_t *obj, const double *d_q, int32_t
   cudaError_t e = xrsd_launch_lm_trial_update(obj, d_q, n_q, d_I, (long long)ld_I, batch, d_Iobs,
                                               (obj->has_dI || obj->prepared) ? d_dI : nullptr, (long long)ld_obs, d_params, ld_params,
                                               d_trial, d_chi2, d_chi2_trial, d_lambda, d_active, d_accepted, d_needjac, d_reason,
-                                              d_n_accept, trial_tables, n_xtal, d_flags, up, down, ftol, xtol, lambda_max,
+                                              d_n_accept, trial_tables, n_xtal, d_flags, tag, up, down, ftol, xtol, lambda_max,
                                               (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "lm_trial_update_kernel");
   return XRSD_OK;

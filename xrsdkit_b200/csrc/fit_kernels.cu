@@ -661,7 +661,7 @@ lm_trial_update_kernel(const xrsd_objective_t O, const double *__restrict__ q, i
                        double *__restrict__ chi2, double *__restrict__ chi2_trial, double *__restrict__ lambda,
                        uint8_t *__restrict__ active, uint8_t *__restrict__ accepted, uint8_t *__restrict__ needjac,
                        uint8_t *__restrict__ reason, int *__restrict__ n_accept, const xrsd_tables_t Tt, int n_xtal,
-                       int *__restrict__ flags, double up, double down, double ftol, double xtol, double lambda_max) {
+                       int *__restrict__ flags, int tag, double up, double down, double ftol, double xtol, double lambda_max) {
   __shared__ double red[2][CHI2_THREADS / 32];
   __shared__ int take;
   const int b = blockIdx.x;
@@ -744,6 +744,7 @@ lm_trial_update_kernel(const xrsd_objective_t O, const double *__restrict__ q, i
     take = acc;
     accepted[b] = (uint8_t)acc;
     if (why) { active[b] = 0; reason[b] = (uint8_t)why; }
+    else if (flags != nullptr) atomicMax(&flags[1], tag);      // still running after iteration `tag`
     needjac[b] = (uint8_t)(acc && !why);
   }
   __syncthreads();
@@ -973,14 +974,14 @@ extern "C" cudaError_t xrsd_launch_lm_trial_update(const xrsd_objective_t *obj, 
                                                    long long ld_obs, double *d_params, int ldp, const double *d_trial,
                                                    double *d_chi2, double *d_chi2_trial, double *d_lambda, uint8_t *d_active,
                                                    uint8_t *d_accepted, uint8_t *d_needjac, uint8_t *d_reason, int *d_n_accept,
-                                                   const xrsd_tables_t *trial_tables, int n_xtal, int *d_flags, double up,
+                                                   const xrsd_tables_t *trial_tables, int n_xtal, int *d_flags, int tag, double up,
                                                    double down, double ftol, double xtol, double lambda_max, cudaStream_t stream) {
   if (batch <= 0) return cudaSuccess;
   static const xrsd_tables_t none = {};
   xrsd::lm_trial_update_kernel<<<batch, xrsd::CHI2_THREADS, 0, stream>>>(
       *obj, d_q, n_q, d_I, ld_I, batch, d_Iobs, d_dI, ld_obs, d_params, ldp, d_trial, d_chi2, d_chi2_trial, d_lambda, d_active,
-      d_accepted, d_needjac, d_reason, d_n_accept, trial_tables ? *trial_tables : none, trial_tables ? n_xtal : 0, d_flags, up, down,
-      ftol, xtol, lambda_max);
+      d_accepted, d_needjac, d_reason, d_n_accept, trial_tables ? *trial_tables : none, trial_tables ? n_xtal : 0, d_flags, tag, up,
+      down, ftol, xtol, lambda_max);
   return cudaGetLastError();
 }
 

@@ -487,18 +487,20 @@ class Engine(object):
                                                                      {"ws": None, "key": None})
             ws = slot["ws"]
             if ws is None or ws.numel() < need:
-                ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+                ws = torch.empty(need, dtype=torch.uint8, device=self.device)
                 slot["ws"], slot["key"] = ws, None
-            if slot["key"] != (n_q, chunk, nf):      # ticket area moves with the shape: re-zero it
-                ws.zero_()
-                slot["key"] = (n_q, chunk, nf)
         nx = layout.n_xtal
         for lo in range(0, batch, chunk):
             hi = min(batch, lo + chunk)
-            if hi - lo != chunk:
+            if resident is None:
+                # the partial-sum / ticket area sits behind the pattern slabs of THIS launch's row count and has to
+                # start at zero (the kernels leave it zeroed): when the shape changes only that tail is cleared,
+                # not the gigabytes of slabs in front of it
+                if slot["key"] != (n_q, hi - lo, nf):
+                    self._zero_jacobian_tail(ws, n_q, hi - lo, nf)
+                    slot["key"] = (n_q, hi - lo, nf)
+            elif hi - lo != chunk:
                 ws.zero_()
-                if resident is None:
-                    slot["key"] = None
             tc = None
             if tables is not None:
                 tc = abi.Tables()
@@ -515,6 +517,10 @@ class Engine(object):
                 ws.data_ptr(), (active.data_ptr() + lo) if active is not None else None, self._stream()))
             self.launches += 1 if patterns_only else 2
         return out
+
+    def _zero_jacobian_tail(self, ws, n_q, rows, nf):
+        head = int(rows) * (nf + 1 + abi.MAX_POPS) * int(n_q) * 8
+        ws[head:int(self.lib.xrsd_jacobian_workspace_bytes(n_q, rows, nf))].zero_()
 
     def pattern_chi2(self, obj, q, patterns, Iobs_dev, dI_dev, ld_obs, out=None, active=None):
         """chi2 of patterns that are already on the device: `patterns` is a [batch, n_q] float64 tensor whose rows may

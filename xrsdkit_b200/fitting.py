@@ -240,7 +240,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
                                                jout[2].data_ptr(), d_chi2_t.data_ptr(), d_lambda.data_ptr(), d_active.data_ptr(),
                                                d_accepted.data_ptr(), d_needjac.data_ptr(), d_reason.data_ptr(), d_nacc.data_ptr(),
                                                C.byref(t_tables.c) if t_tables is not None else None, layout.n_xtal,
-                                               d_flags.data_ptr(), float(up), float(down), float(ftol), float(xtol),
+                                               d_flags.data_ptr(), n_iter, float(up), float(down), float(ftol), float(xtol),
                                                float(lambda_max), stream))
             if persist or layout.n_xtal:
                 ws0 = eng._jac_resident[key0][0] if persist else None
@@ -252,8 +252,9 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
                                              C.byref(t_tables.c) if t_tables is not None else None, layout.n_xtal, stream))
             eng.launches += 3 + (0 if persist else 1)
             if it % check_every == check_every - 1:
-                d_flags[1:2].copy_(d_active.any().to(torch.int32).reshape(1))
-                st_seen, any_active = [int(v) for v in d_flags.cpu().tolist()]      # the only host sync of the loop
+                # the only host sync of the loop: [0] status bits met, [1] the last iteration that left a system running
+                st_seen, last_running = [int(v) for v in d_flags.cpu().tolist()]
+                any_active = last_running == n_iter
                 if st_seen & abi.TABLE_GRID_OVERFLOW and tight:
                     # an active system proposed a cell beyond the near box and was turned back: re-centre the box
                     loop_cells = near_cells(d_p.cpu().numpy())

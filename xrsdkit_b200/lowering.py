@@ -184,7 +184,7 @@ def _lower_noise(model, slots):
     return p
 
 
-def _lower_population(structure, form, settings, slots, q_last, table_slot):
+def _lower_population(structure, form, settings, slots, q_last, table_slot, parameters=None):
     """One population -> abi.Pop.  Mirrors the dispatcher scattering/__init__.py:12-66."""
     p = _blank_pop()
     p.p_I0 = slots['I0']
@@ -246,8 +246,12 @@ def _lower_population(structure, form, settings, slots, q_last, table_slot):
         p.table_slot = table_slot
         # extinct shells (|S|^2 ~ 1e-31 of the allowed ones) are dropped when the profile has
         # algebraic tails, where their contribution is < 1e-15 relative; kept for 'gaussian',
-        # whose tails underflow and would otherwise leave them as the only contribution
-        p.prune_extinct = 0 if settings['profile'] == 'gaussian' else 1
+        # whose tails underflow and would otherwise leave them as the only contribution -- and for a
+        # Voigt profile lowered with hwhm_l == 0, which IS that Gaussian (the reference's own lower bound
+        # for hwhm_l is 1e-9, definitions.py:292; batches keep the flag of the system they were lowered from)
+        gaussian_like = settings['profile'] == 'gaussian' or (
+            settings['profile'] == 'voigt' and parameters is not None and float(parameters['hwhm_l']['value']) == 0.0)
+        p.prune_extinct = 0 if gaussian_like else 1
         return p
     p.kind = abi.POP_NONCRYSTALLINE
     p.disordered = 1 if structure == 'disordered' else 0
@@ -379,7 +383,7 @@ def lower_system(system, q):
     n_x = 0
     for pop_name, pop in system.populations.items():
         slots = take(pop_name, pop.parameters)
-        lp = _lower_population(pop.structure, pop.form, pop.settings, slots, q[-1] if len(q) else 0.0, n_x)
+        lp = _lower_population(pop.structure, pop.form, pop.settings, slots, q[-1] if len(q) else 0.0, n_x, pop.parameters)
         if lp.kind == abi.POP_CRYSTALLINE:
             n_x += 1
         pops.append(lp)
