@@ -49,6 +49,9 @@ LM_ITERS = 30           # iteration cap                                         
 FLOPS_PER_PAIR_RNORMAL = 13.0
 FLOPS_PER_Q_OVERHEAD_CFG2 = 151.0        # PY brackets ~100, two divisions 20, three span-to-span rotations 18, epilogue ~13
 SURVEY_FLOPS_PER_SETQ_CFG2 = 2630.0      # SURVEY.md 8d convention (sincos per (q,r) pair)
+#   crystalline: one far-branch Voigt evaluation = reciprocal (5 FMA) + set-up (2 FMA, 5 mul) + 4 recurrence terms
+#   (mul + 2 FMA each) + scale, argument and accumulation (3 mul, 2 FMA) = 27 FP64 instructions, 47 flop
+VOIGT_FLOPS = 47.0
 
 WORKLOADS = {
     "cfg2": "cfg2: polydisperse spheres (r_normal, 50-pt quadrature) + hard_spheres S(q), 4096-pt q, 10k parameter sets per GPU",
@@ -434,19 +437,30 @@ class Work(object):
         core = np.maximum(1.0, hl / s2) * s2
         dn = np.maximum(4 * H, H + 12 * core)
         n_near = float(np.mean(np.minimum(ns, ns * 2 * dn / (q[-1] - q[0]))))
-        return 60.0 * n_near + 17.0 * 60.0 * (ns - n_near) / 128.0 + 2.0 * 17.0 + 150.0, 205.0 * ns + 150.0
+        return VOIGT_FLOPS * n_near + 17.0 * VOIGT_FLOPS * (ns - n_near) / 128.0 + 2.0 * 17.0 + 150.0, 205.0 * ns + 150.0
 
 
 def ncu_kernel_counts(workload, batch=10000):
     """Per-launch figures of the dominant kernel from the committed ncu capture of this round (profiles/): DRAM
-    traffic and the FP64 thread-instruction counts (2 flop per DFMA, 1 per DADD / DMUL).  The captures were taken at
-    10^4 systems per launch: None for any other launch shape, or when the file is absent."""
+    traffic and the FP64 thread-instruction counts (2 flop per DFMA, 1 per DADD / DMUL), for `batch` systems per launch
+    (the capture records how many systems its launch held); None when the file is absent."""
     try:
         with open(os.path.join(ROOT, "profiles", "r02_ncu_counts.json")) as f:
             rec = json.load(f).get(workload)
-        if rec is None or batch != 10000:
+        if rec is None:
             return None
-        return {k: v for k, v in rec.items() if k != "all"}
+        out = {k: v for k, v in rec.items() if k != "all"}
+        # the capture may hold fewer systems per launch than the timed launch (the public Jacobian call cuts the batch
+        # into <= 4 GB chunks): counts that scale with the systems are brought to the timed launch's size
+        n_cap = rec.get("systems_per_launch")
+        if n_cap and n_cap != batch:
+            for k in ("dram_bytes", "fp64_flops"):
+                if out.get(k) is not None:
+                    out[k] = out[k] * batch / float(n_cap)
+            out["scaled_from_systems"] = n_cap
+        elif not n_cap and batch != 10000:
+            return None
+        return out
     except Exception:
         return None
 
@@ -720,7 +734,7 @@ def run_gpu_arm(args):
     if args.workload == "cfg2" and world == 1 and not args.no_secondary:
         secondary = {}
         outs0 = W.outs[0]
-        for name, b2, st, wu in (("cfg3", args.batch, 5, 3), ("cfg4", args.batch, 3, 3), ("cfg5", args.fit_batch, 1, 1)):
+        for name, b2, st, wu in (("cfg3", args.batch, 5, 3), ("cfg4", args.batch, 3, 3), ("cfg5", args.fit_batch, 2, 2)):
             try:
                 w2, o2 = measure(eng, name, b2, 2000, st, wu, args, peaks, peaks_src, fp64_tflops, probe_ms,
                                  sampler=ClockSampler(local))

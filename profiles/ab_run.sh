@@ -4,7 +4,10 @@
 LIBS=${1:-"head main"}; WLS=${2:-"cfg3 cfg4"}; TAG=${3:-ab}
 mkdir -p gpurun_out
 for wl in $WLS; do for lib in $LIBS; do
-  if [ $lib = main ]; then unset XRSD_B200_LIB; else export XRSD_B200_LIB=$PWD/ab/libxrsd_$lib.so; fi
+  unset XRSD_JR_NO_MMA
+  if [ $lib = main ]; then unset XRSD_B200_LIB
+  elif [ $lib = nomma ]; then unset XRSD_B200_LIB; export XRSD_JR_NO_MMA=1      # in-tree library, register-accumulator reduction
+  else export XRSD_B200_LIB=$PWD/ab/libxrsd_$lib.so; fi
   python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu --no-secondary --no-nm 2>gpurun_out/ab_err.txt | python -c "
 import sys, json
 d = json.loads(sys.stdin.readline())

@@ -91,8 +91,12 @@ def main():
         top = [r for r in recs if pick in r["kernel"]]
         if top:
             r = top[0]
+            # CTAs per system of the captured launch: one whole-pattern CTA per pattern (cfg2, cfg3), one per executed
+            # variant (cfg4: base + 5 non-linear parameters)
+            per_sys = {"cfg2": 1, "cfg3": 1, "cfg4": 6}[tag]
             counts[tag] = {"dram_bytes": r["dram_bytes"], "fp64_flops": r.get("fp64_flops"), "fp64_pipe_pct": r["fp64_pipe_pct"],
                            "kernel_ms_under_ncu": r["ms"], "source": "profiles/r02_ncu_%s.txt" % tag,
+                           "systems_per_launch": int(round(r["grid"] / per_sys)),
                            "all": [{k: v for k, v in x.items()} for x in recs]}
     if "cfg4" in counts:
         counts["cfg5"] = dict(counts["cfg4"], source=counts["cfg4"]["source"] + " (same kernel; the cfg4 launch shape)")

@@ -12,6 +12,7 @@
 //                            <- replace the lmfit Nelder-Mead driver of system/__init__.py:262-266 (no oracle in the
 //                               reference; parity is defined on outcomes, and measured against batched Nelder-Mead
 //                               on the same systems in bench.py)
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "system_eval.cuh"
@@ -484,6 +485,219 @@ jacobian_reduce_kernel(int n_pops, const xrsd_objective_t O, const double *__res
   }
 }
 
+// ---------------------------------------------------------------------------- reduction on the FP64 tensor cores
+// JTJ = sum_q (w D)(D)^T is a rank-k update of an NF x NF matrix with k = n_q: GEMM-shaped work.  Accumulating it in
+// registers costs 46 accumulators per thread (n_free <= 8), which under any occupancy worth having left the compiler
+// re-deriving loop-invariant addresses in every iteration (a quarter of the instructions of the register version,
+// profiles/sass_by_line.py on the cfg4 capture, FP64 pipe 22 %).  Here every thread still forms the residual and the
+// difference quotients of ITS q-point, but hands them to the warp through a small shared-memory tile, and the warp
+// accumulates with mma.sync.m8n8k4.f64 (DMMA): A = (w D)^T as 8 parameters x 4 q-points, B = D as 4 q-points x 8
+// parameters, C = the 8 x 8 block of JTJ, two accumulator registers per thread; JTr is the first column of a second
+// product with B = (res, 0, ..., 0).  Tile layout V[row][(q % 4) * 8 + q / 4] with a row pitch of 34 doubles: row j < NF
+// holds D_j, row NF the residual, row NF + 1 the weight; a thread's eight operands of one row are contiguous (4 x
+// LDS.128, conflict-free), and so are the 32 stores of one row.  The sums of the four warps and of the q-chunks of a
+// system are added in a fixed order: bit-identical from run to run, as the register version.
+#ifndef XRSD_JM_STAGES
+#define XRSD_JM_STAGES 2
+#endif
+constexpr int JM_STAGES = XRSD_JM_STAGES;
+constexpr int JM_PITCH = 34;
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int NF>
+__global__ void __launch_bounds__(JR_THREADS, NF <= 8 ? 5 : 3)
+jacobian_reduce_mma_kernel(int n_pops, const xrsd_objective_t O, const double *__restrict__ q, int n_q,
+                           const double *__restrict__ params, int ldp, int batch, const double *__restrict__ Iobs,
+                           const double *__restrict__ dI, long long ld_obs, const FreeSet F, double rel_step,
+                           const double *__restrict__ Fvar, double *__restrict__ acc_g, unsigned *__restrict__ tickets,
+                           double *__restrict__ JTJ, double *__restrict__ JTr, double *__restrict__ chi2, int chunk_q,
+                           int n_chunks, const uint8_t *__restrict__ active) {
+  constexpr int NACC = NF * NF + NF + 2;          // same partial-sum layout as jacobian_reduce_kernel
+  constexpr int NB = NF / 8;                      // 8 x 8 blocks per side
+  constexpr int NWARP = JR_THREADS / 32;
+  extern __shared__ __align__(16) double ring[];  // [stage][row][thread], then the warps' tiles
+  __shared__ double fold[NWARP][NACC];
+  __shared__ int4 dsc[NF];
+  __shared__ int is_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks;
+  if (b >= batch) return;
+  if (active != nullptr && !active[b]) return;
+  const int nf = F.n_free, nv = F.n_var, n_slab = nv + n_pops;
+  const double *prm = params + (size_t)b * ldp;
+  const double *obs = Iobs + (size_t)b * ld_obs;
+  const double *err = dI ? dI + (size_t)b * ld_obs : nullptr;
+  const double *Fb = Fvar + (size_t)b * n_slab * n_q;
+  const int q_lo = chunk * chunk_q, q_hi = min(n_q, q_lo + chunk_q);
+  const int n_rows = n_slab + 1 + (err ? 1 : 0);
+  const int z_row = n_rows;
+  double *tile = ring + (size_t)JM_STAGES * (n_rows + 1) * JR_THREADS + (size_t)warp * (NF + 2) * JM_PITCH;
+  for (int i = tid; i < JM_STAGES * JR_THREADS; i += JR_THREADS)
+    ring[((size_t)(i / JR_THREADS) * (n_rows + 1) + z_row) * JR_THREADS + (i % JR_THREADS)] = 0.0;
+  if (tid < NF)
+    dsc[tid] = make_int4((F.ra[tid] < 0 ? z_row : F.ra[tid]) * JR_THREADS, (F.rb[tid] < 0 ? z_row : F.rb[tid]) * JR_THREADS,
+                         (F.rc[tid] < 0 ? z_row : F.rc[tid]) * JR_THREADS, 0);
+  __syncthreads();
+  double scale[NF];                  // h / I0 for a linear parameter (0 at I0 == 0), 1 for a variant slab, 0 beyond n_free
+#pragma unroll
+  for (int j = 0; j < NF; ++j) {
+    const double p0 = (j < nf) ? prm[F.idx[j]] : 1.0;
+    const double hstep = (p0 != 0.0) ? fabs(p0) * rel_step : rel_step;
+    scale[j] = (j >= nf) ? 0.0 : (F.lin_j[j] ? ((p0 != 0.0) ? hstep / p0 : 0.0) : 1.0);
+  }
+  const int n_it = (q_hi - q_lo + JR_THREADS - 1) / JR_THREADS;
+  auto issue = [&](int it) {
+    const int i = q_lo + it * JR_THREADS + tid;
+    if (it < n_it && i < q_hi) {
+      double *slot = ring + (size_t)(it % JM_STAGES) * (n_rows + 1) * JR_THREADS + tid;
+      for (int r = 0; r < n_slab; ++r) cp_async8(slot + r * JR_THREADS, Fb + (size_t)r * n_q + i);
+      cp_async8(slot + n_slab * JR_THREADS, obs + i);
+      if (err) cp_async8(slot + (n_slab + 1) * JR_THREADS, err + i);
+    }
+    cp_async_commit();
+  };
+  // this thread's place in the tile (store) and in the fragments (load)
+  const int st_col = (lane & 3) * 8 + (lane >> 2);          // q-point `lane` of the warp's 32
+  const int fm = lane >> 2, fk = lane & 3;                  // fragment row (parameter within a block) / q-point within a group of 4
+  double C[NB][NB][2], R[NB][2], c2 = 0.0, sw = 0.0;
+#pragma unroll
+  for (int x = 0; x < NB; ++x) {
+    R[x][0] = R[x][1] = 0.0;
+#pragma unroll
+    for (int y = 0; y < NB; ++y) C[x][y][0] = C[x][y][1] = 0.0;
+  }
+#pragma unroll
+  for (int st = 0; st < JM_STAGES; ++st) issue(st);
+  for (int it = 0; it < n_it; ++it) {
+    cp_async_wait<JM_STAGES - 1>();
+    const int i = q_lo + it * JR_THREADS + tid;
+    const double *Fs = ring + (size_t)(it % JM_STAGES) * (n_rows + 1) * JR_THREADS + tid;
+    bool fit = i < q_hi;
+    double w = 0.0, Io = 0.0, I0v = 0.0;
+    if (fit) {
+      Io = Fs[n_slab * JR_THREADS];
+      fit = fit_weight(O, q[i], Io, err ? Fs + (n_slab + 1) * JR_THREADS : nullptr, 0, w);
+      I0v = Fs[0];
+      if (O.logI_weighted) fit = fit && (I0v > 0.0);
+    }
+    double res = 0.0;
+    if (fit) {
+      const double f0 = O.logI_weighted ? log(I0v) : I0v;
+      res = f0 - fit_target(O, Io);
+      const double inv = O.logI_weighted ? 1.0 / I0v : 1.0;
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const int4 o = dsc[j];
+        double d = scale[j] * ((Fs[o.x] - Fs[o.y]) + Fs[o.z]) * inv;
+        if (O.logI_weighted) {
+          if (fabs(d) < 1.0e-2) d = d * fma(d, fma(d, 1.0 / 3.0, -0.5), 1.0);      // |error| < x^4 / 4
+          else d = (d > -1.0) ? log1p(d) : 0.0;          // a variant intensity <= 0 carries no information
+        }
+        tile[j * JM_PITCH + st_col] = (d == d) ? d : 0.0;
+      }
+      c2 = fma(w, res * res, c2);
+      sw += w;
+    } else {
+      w = 0.0;
+#pragma unroll
+      for (int j = 0; j < NF; ++j) tile[j * JM_PITCH + st_col] = 0.0;
+    }
+    tile[NF * JM_PITCH + st_col] = res;
+    tile[(NF + 1) * JM_PITCH + st_col] = w;
+    issue(it + JM_STAGES);
+    __syncwarp();
+    // fragments: eight groups of four q-points
+    double wq[8], rs[8];
+    {
+      const double2 *pw = reinterpret_cast<const double2 *>(tile + (NF + 1) * JM_PITCH + fk * 8);
+      const double2 *pr = reinterpret_cast<const double2 *>(tile + NF * JM_PITCH + fk * 8);
+#pragma unroll
+      for (int g2 = 0; g2 < 4; ++g2) {
+        const double2 a = pw[g2], r = pr[g2];
+        wq[2 * g2] = a.x; wq[2 * g2 + 1] = a.y;
+        rs[2 * g2] = (fm == 0) ? r.x : 0.0; rs[2 * g2 + 1] = (fm == 0) ? r.y : 0.0;
+      }
+    }
+    double xv[NB][8];
+#pragma unroll
+    for (int x = 0; x < NB; ++x) {
+      const double2 *px = reinterpret_cast<const double2 *>(tile + (x * 8 + fm) * JM_PITCH + fk * 8);
+#pragma unroll
+      for (int g2 = 0; g2 < 4; ++g2) {
+        const double2 a = px[g2];
+        xv[x][2 * g2] = a.x; xv[x][2 * g2 + 1] = a.y;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+#pragma unroll
+      for (int x = 0; x < NB; ++x) {
+        const double a = wq[g] * xv[x][g];
+#pragma unroll
+        for (int y = x; y < NB; ++y) dmma884(C[x][y][0], C[x][y][1], a, xv[y][g]);
+        dmma884(R[x][0], R[x][1], a, rs[g]);
+      }
+    }
+    __syncwarp();                          // the tile is free for the next iteration's stores
+  }
+  cp_async_wait<0>();
+  // ---- warp results -> fold[warp][NACC layout]; C[x][y] fragment: row x*8 + fm, columns y*8 + 2 fk + {0, 1}
+  for (int e = lane; e < NACC; e += 32) fold[warp][e] = 0.0;
+  __syncwarp();
+#pragma unroll
+  for (int x = 0; x < NB; ++x) {
+#pragma unroll
+    for (int y = x; y < NB; ++y) {
+      fold[warp][(x * 8 + fm) * NF + y * 8 + 2 * fk] = C[x][y][0];
+      fold[warp][(x * 8 + fm) * NF + y * 8 + 2 * fk + 1] = C[x][y][1];
+    }
+    if (fk == 0) fold[warp][NF * NF + x * 8 + fm] = R[x][0];      // column 0 of the second product
+  }
+  for (int o = 16; o > 0; o >>= 1) { c2 += __shfl_xor_sync(0xffffffffu, c2, o); sw += __shfl_xor_sync(0xffffffffu, sw, o); }
+  if (lane == 0) { fold[warp][NF * NF + NF] = c2; fold[warp][NF * NF + NF + 1] = sw; }
+  __syncthreads();
+  double *accb = acc_g + ((size_t)b * n_chunks + chunk) * NACC;
+  for (int e = tid; e < NACC; e += JR_THREADS) {
+    double v = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < NWARP; ++wv) v += fold[wv][e];
+    accb[e] = v;
+  }
+  // ---- last chunk of the system: chunks added in order, normalised, written (as jacobian_reduce_kernel)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(&tickets[b], 1u) == (unsigned)(n_chunks - 1));
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const double *acc0 = acc_g + (size_t)b * n_chunks * NACC;
+  auto total = [&](int e) {
+    double v = 0.0;
+    for (int c = 0; c < n_chunks; ++c) v += __ldcg(&acc0[(size_t)c * NACC + e]);
+    return v;
+  };
+  auto step_of = [&](int j) {
+    const double p0 = prm[F.idx[j]];
+    return (p0 != 0.0) ? fabs(p0) * rel_step : rel_step;
+  };
+  double swt = total(NF * NF + NF + 1);
+  const double c2t = total(NF * NF + NF);
+  if (swt == 0.0 && c2t == 0.0) swt = 1.0;
+  for (int e = tid; e < nf * nf; e += JR_THREADS) {
+    const int j = e / nf, k = e - j * nf;
+    const int jj = min(j, k), kk = max(j, k);
+    JTJ[((size_t)b * nf + j) * nf + k] = total(jj * NF + kk) / (step_of(jj) * step_of(kk)) / swt;
+  }
+  if (tid < nf) JTr[(size_t)b * nf + tid] = total(NF * NF + tid) / step_of(tid) / swt;
+  if (tid == 0) {
+    chi2[b] = c2t / swt;
+    tickets[b] = 0;
+  }
+}
+
 // ---------------------------------------------------------------------------- LM algebra
 __global__ void lm_propose_kernel(const double *__restrict__ params, int ldp, int batch, const FreeSet F,
                                   const double *__restrict__ JTJ, const double *__restrict__ JTr,
@@ -910,6 +1124,21 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
   const int chunk_q = (((n_q + chunks_per_sys - 1) / chunks_per_sys) + JR_THREADS - 1) / JR_THREADS * JR_THREADS;
   const int n_chunks = (n_q + chunk_q - 1) / chunk_q;
   if ((long long)batch * n_chunks > 2147483647LL) return cudaErrorInvalidConfiguration;
+  static const bool use_mma = getenv("XRSD_JR_NO_MMA") == nullptr;      // A/B switch: the register-accumulator version
+  if (use_mma) {
+    const int NFt = n_free <= 8 ? 8 : XRSD_MAX_FREE;
+    const size_t smem = ((size_t)JM_STAGES * (F.n_var + layout->n_pops + 3) * JR_THREADS + (size_t)(JR_THREADS / 32) * (NFt + 2) * JM_PITCH) *
+                        sizeof(double);
+    auto launch = [&](auto kern) -> cudaError_t {
+      cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (er != cudaSuccess) return er;
+      kern<<<batch * n_chunks, JR_THREADS, smem, stream>>>(layout->n_pops, *obj, d_q, n_q, d_params, ldp, batch, d_Iobs, d_dI, ld_obs, F,
+                                                          rel_step, d_Fvar, d_acc, d_tickets, d_JTJ, d_JTr, d_chi2, chunk_q, n_chunks,
+                                                          d_active);
+      return cudaGetLastError();
+    };
+    return n_free <= 8 ? launch(jacobian_reduce_mma_kernel<8>) : launch(jacobian_reduce_mma_kernel<XRSD_MAX_FREE>);
+  }
   const size_t ring_bytes = (size_t)JR_STAGES * (F.n_var + layout->n_pops + 3) * JR_THREADS * sizeof(double);
   // opt in on every launch (microseconds; the attribute is per device and static shared memory counts against the
   // 48 KB default too)
