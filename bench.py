@@ -755,6 +755,7 @@ def run_gpu_arm(args):
                 torch.cuda.empty_cache()
             except Exception as e:      # a secondary measurement must not take the headline down
                 secondary[name] = {"error": repr(e)}
+        secondary["cfg2_fp32"] = bench_fp32(eng, W)
         secondary["features"] = bench_features(eng, W, outs0, args)
         secondary["cfg1"] = bench_cfg1(args)
 
@@ -839,6 +840,24 @@ def bench_features(eng, W, pats0, args):
             out["cpu_patterns_per_s_1core"] = 2 / (time.perf_counter() - t0)
             out["max_rel_diff_vs_oracle"] = float(np.max(np.abs(f_out[:2].cpu().numpy() - ref_f)[:, :13] / np.abs(ref_f[:, :13])))
         return out
+    except Exception as e:
+        return {"error": repr(e)}
+
+
+def bench_fp32(eng, W):
+    """The optional single-precision path on the headline workload: same batch, FP32 size-distribution loops,
+    kernel-only rate and the largest relative difference to the FP64 result (the gate is 1e-5)."""
+    import torch
+    try:
+        ref = eng.intensity(W.lay, W.d_q, W.d_params[0]).clone()
+        out = torch.empty_like(ref)
+        eng.intensity(W.lay, W.d_q, W.d_params[0], out=out, precision="fp32")
+        diff = float(((out - ref).abs() / ref.abs()).max().item())
+        ms = time_kernel(lambda i: eng.intensity(W.lay, W.d_q, W.d_params[i % 4], out=W.outs[i % 2], precision="fp32"))
+        ms64 = time_kernel(lambda i: eng.intensity(W.lay, W.d_q, W.d_params[i % 4], out=W.outs[i % 2]))
+        return {"workload": WORKLOADS["cfg2"] + " -- optional FP32 path (xrsd_intensity_batch_f32)", "unit": "patterns/s",
+                "value": W.B / (ms * 1e-3), "kernel_ms": ms, "fp64_kernel_ms": ms64, "speedup_over_fp64": ms64 / ms,
+                "max_rel_diff_vs_fp64": diff, "gate": 1e-5, "dtype": "f32 loops, f64 per-q work and output"}
     except Exception as e:
         return {"error": repr(e)}
 

@@ -192,6 +192,16 @@ int xrsd_intensity_batch(const xrsd_layout_t *layout, const double *d_q, int32_t
                          const double *d_params, int32_t ld_params, int32_t batch,
                          const xrsd_tables_t *tables, double *d_I, int64_t ld_I, void *stream);
 
+/* The optional single-precision path (BASELINE.json north_star: "<= 1e-5 relative error in the optional FP32 path").
+ * Same arguments and FP64 output as xrsd_intensity_batch, for layouts WITHOUT crystalline populations (others:
+ * XRSD_EINVAL).  The O(n_q n_r) loop over a size distribution's radii runs in FP32 wherever q r >= 2 for a whole
+ * warp; everything done once per q-point (starting phases, small-argument radii, normalisation, hard-sphere factor,
+ * the sum over populations) stays FP64.  The reference has no such path; it is validated against
+ * xrsd_intensity_batch (tests/test_gpu_parity.py::test_single_precision_path). */
+int xrsd_intensity_batch_f32(const xrsd_layout_t *layout, const double *d_q, int32_t n_q,
+                             const double *d_params, int32_t ld_params, int32_t batch,
+                             double *d_I, int64_t ld_I, void *stream);
+
 /* Same launch, additionally writing the running totals d_cum[batch][layout.n_pops][n_q] after the
  * noise model (index 0) and after each population: differences of consecutive rows are the
  * per-population patterns.  <- the (2 + n_pop) separate evaluations of visualization/__init__.py:23-31

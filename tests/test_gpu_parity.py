@@ -410,6 +410,45 @@ def test_voigt_with_zero_lorentzian_width(ref_tables, eng):
     assert np.max(np.abs(got[ok] - want[ok]) / want[ok]) <= TOL_F64
 
 
+def test_single_precision_path(eng):
+    """The optional FP32 path of BASELINE.json's north_star (<= 1e-5 relative): there is no reference for it, so it
+    is held against the FP64 engine -- on the cfg2 parameter distribution (polydisperse spheres with hard-sphere
+    S(q): no zeros, plain relative error), on quadratures of other widths / steps, on a layout that mixes several
+    non-crystalline populations, and on a non-uniform q grid.  Layouts with crystalline populations are refused."""
+    from xrsdkit_b200 import batch
+    from xrsdkit_b200.system import System
+    s = cfg2_system(System)
+    q = np.linspace(0.01, 0.5, 4096)
+    lay = batch.layout_of(s, q)
+    P = cfg2_params(lay, 512, seed=31)
+    I64 = batch.compute_intensity_batch(lay, q, P)
+    I32 = batch.compute_intensity_batch(lay, q, P, precision="fp32")
+    rel = np.abs(I32 - I64) / np.abs(I64)
+    assert np.isfinite(I32).all() and rel.max() <= 1e-5, rel.max()
+    assert rel.max() > 0.0                                   # it really is another arithmetic
+    # other quadratures, q down to where every radius takes the small-argument branch, and a non-uniform grid
+    rs = np.random.RandomState(9)
+    for width, step, grid in ((2.5, 0.02, np.linspace(1e-3, 0.6, 1500)), (4.0, 0.1, np.sort(rs.uniform(0.005, 0.8, 1200))),
+                              (1.0, 0.05, np.linspace(0.2, 2.0, 777))):
+        t = System(a=dict(structure="diffuse", form="spherical",
+                          settings={"distribution": "r_normal", "sampling_width": width, "sampling_step": step},
+                          parameters={"r": {"value": 35.0}, "sigma": {"value": 0.12}, "I0": {"value": 3.0}}),
+                   b=dict(structure="diffuse", form="guinier_porod", parameters={"rg": {"value": 6.0}, "I0": {"value": 0.5}}),
+                   c=dict(structure="disordered", form="spherical",
+                          settings={"distribution": "r_normal", "sampling_width": 2.5, "sampling_step": 0.1},
+                          parameters={"r": {"value": 12.0}, "sigma": {"value": 0.2}, "r_hard": {"value": 14.0},
+                                      "v_fraction": {"value": 0.2}, "I0": {"value": 1.0}}),
+                   noise={"model": "flat", "parameters": {"I0": {"value": 1e-4}}})
+        lt = batch.layout_of(t, grid)
+        a64 = batch.compute_intensity_batch(lt, grid, lt.values[None, :])
+        a32 = batch.compute_intensity_batch(lt, grid, lt.values[None, :], precision="fp32")
+        assert np.max(np.abs(a32 - a64) / np.abs(a64)) <= 1e-5, (width, step)
+    x = cfg3_system(System)
+    qx = np.linspace(0.05, 1.0, 600)
+    with pytest.raises(ValueError):
+        batch.compute_intensity_batch(batch.layout_of(x, qx), qx, batch.layout_of(x, qx).values[None, :], precision="fp32")
+
+
 def test_components_in_one_launch(golden_systems, eng):
     """Per-population decomposition (noise, each population, total) from one launch against the reference's
     separate per-population evaluations."""

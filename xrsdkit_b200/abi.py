@@ -70,6 +70,7 @@ _SIGNATURES = {
     "xrsd_table_scratch_bytes": (C.c_int64, [C.c_int64]),
     "xrsd_reflection_tables": (C.c_int, [C.POINTER(Layout), vp, i32, i32, C.POINTER(Tables), i32, vp, vp]),
     "xrsd_intensity_batch": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, C.POINTER(Tables), vp, C.c_int64, vp]),
+    "xrsd_intensity_batch_f32": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, vp, C.c_int64, vp]),
     "xrsd_intensity_components_batch": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, C.POINTER(Tables), vp, C.c_int64,
                                                   vp, vp]),
     "xrsd_residual_workspace_bytes": (C.c_int64, [i32, i32]),

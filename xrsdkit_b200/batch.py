@@ -45,10 +45,11 @@ def bind_to_gpu_numa(device_index):
     return None
 
 
-def compute_intensity_batch(layout, q, params, device_out=False, eng=None):
-    """I[b, :] for every row of params ([B, n_params]).  numpy out unless device_out."""
+def compute_intensity_batch(layout, q, params, device_out=False, eng=None, precision="fp64"):
+    """I[b, :] for every row of params ([B, n_params]).  numpy out unless device_out.  precision="fp32": the optional
+    single-precision path (size-distribution loops in FP32, within 1e-5 of the default; no crystalline populations)."""
     eng = eng or _engine.get_engine()
-    I = eng.intensity(layout, q, params)
+    I = eng.intensity(layout, q, params, precision=precision)
     return I if device_out else I.cpu().numpy()
 
 

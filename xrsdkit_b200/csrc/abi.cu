@@ -16,7 +16,7 @@ int64_t xrsd_table_scratch_bytes(int64_t cap_big);
 cudaError_t xrsd_launch_tables(const xrsd_layout_t *, const double *, int, int, const xrsd_tables_t *, int, int, const uint8_t *,
                                cudaStream_t);
 cudaError_t xrsd_launch_intensity(const xrsd_layout_t *, const double *, int, const double *, int, int, const xrsd_tables_t *,
-                                  double *, long long, int, int, int, double *, int, cudaStream_t);
+                                  double *, long long, int, int, int, double *, int, int, cudaStream_t);
 cudaError_t xrsd_launch_fp64_probe(double *, int, int, cudaStream_t);
 cudaError_t xrsd_launch_profile(int, double, double, const double *, int, double *, cudaStream_t);
 cudaError_t xrsd_launch_features(const double *, int, const double *, int64_t, int, double *, int64_t, cudaStream_t);
@@ -100,7 +100,7 @@ int scratch_doubles_for(const xrsd_layout_t *L, int *radial_multi) {
     if (p.kind == XRSD_POP_NONCRYSTALLINE && p.form == XRSD_FORM_SPHERE_R_NORMAL) {
       const double n = ceil(2.0 * p.sampling_width / p.sampling_step) + 2.0;
       if (!(n >= 1.0) || n > 12000.0) return -1;
-      need = std::max(need, 2 * (int)n);
+      need = std::max(need, 3 * (int)n);        // (r_i, rho_i) as doubles, then as float2 for the single-precision path
     }
     if (p.kind == XRSD_POP_CRYSTALLINE && p.sf_radial && p.n_species > 1) {
       *radial_multi = 1;
@@ -243,9 +243,11 @@ static int pick_direct_span(int n_q, long long units) {
 
 static int intensity_impl(const xrsd_layout_t *layout, const double *d_q, int32_t n_q, const double *d_params,
                           int32_t ld_params, int32_t batch, const xrsd_tables_t *tables, double *d_I, int64_t ld_I,
-                          double *d_cum, void *stream) {
+                          double *d_cum, void *stream, int single_precision_loops = 0) {
   int rc = check_layout(layout);
   if (rc) return rc;
+  if (single_precision_loops && layout->n_xtal > 0)
+    return fail(XRSD_EINVAL, "the single-precision path covers layouts without crystalline populations");
   if (batch <= 0 || n_q <= 0) return XRSD_OK;
   rc = check_tables(layout, tables);
   if (rc) return rc;
@@ -258,9 +260,15 @@ static int intensity_impl(const xrsd_layout_t *layout, const double *d_q, int32_
   const int direct = layout->n_xtal > 0;
   const int per = direct ? pick_direct_span(n_q, batch) : pick_q_per_cta(n_q, batch, scratch, false);
   cudaError_t e = xrsd_launch_intensity(layout, d_q, n_q, d_params, ld_params, batch, tables ? tables : &kNoTables, d_I,
-                                        (long long)ld_I, per, scratch, rm, d_cum, direct, (cudaStream_t)stream);
+                                        (long long)ld_I, per, scratch, rm, d_cum, direct, single_precision_loops,
+                                        (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "intensity_kernel");
   return XRSD_OK;
+}
+
+int xrsd_intensity_batch_f32(const xrsd_layout_t *layout, const double *d_q, int32_t n_q, const double *d_params,
+                             int32_t ld_params, int32_t batch, double *d_I, int64_t ld_I, void *stream) {
+  return intensity_impl(layout, d_q, n_q, d_params, ld_params, batch, nullptr, d_I, ld_I, nullptr, stream, 1);
 }
 
 int xrsd_intensity_batch(const xrsd_layout_t *layout, const double *d_q, int32_t n_q, const double *d_params,

@@ -17,7 +17,7 @@
 
 namespace xrsd {
 
-template <int QPT, bool RM, bool HX>
+template <int QPT, bool RM, bool HX, bool F32 = false>
 __global__ void __launch_bounds__(EVAL_THREADS, HX ? XRSD_HX_MIN_CTAS : XRSD_NX_MIN_CTAS)
 intensity_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restrict__ q, int n_q,
                  const double *__restrict__ params, int ldp, int batch, const xrsd_tables_t T,
@@ -41,7 +41,7 @@ intensity_kernel(const __grid_constant__ xrsd_layout_t L, const double *__restri
   double *I_sm = HX ? dst : smem_d + scratch_doubles;
   // cum_out (optional): [batch][n_pops][n_q] running totals after the noise model and after each
   // population -- their differences are the per-population patterns (plot decomposition, I0 rescaling)
-  accumulate_system<QPT, RM, HX>(L, params + (size_t)b * ldp, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S,
+  accumulate_system<QPT, RM, HX, F32>(L, params + (size_t)b * ldp, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S,
                                  nullptr, cum_out ? cum_out + (size_t)b * L.n_pops * n_q + q_begin : nullptr, n_q);
   if constexpr (!HX)
     for (int i = threadIdx.x; i < q_count; i += EVAL_THREADS) dst[i] = I_sm[i];
@@ -84,12 +84,16 @@ extern "C" cudaError_t xrsd_launch_profile(int kind, double p0, double p1, const
 extern "C" cudaError_t xrsd_launch_intensity(const xrsd_layout_t *layout, const double *d_q, int n_q, const double *d_params,
                                              int ldp, int batch, const xrsd_tables_t *tables, double *d_I, long long ldI,
                                              int q_per_cta, int scratch_doubles, int radial_multi, double *d_cum,
-                                             int direct, cudaStream_t stream) {
+                                             int direct, int single_precision_loops, cudaStream_t stream) {
   using namespace xrsd;
   const int n_tiles = (n_q + q_per_cta - 1) / q_per_cta;
   const size_t smem = ((direct ? 0 : (size_t)((q_per_cta + 1) & ~1)) + (size_t)scratch_doubles) * sizeof(double);
   auto kern = radial_multi ? intensity_kernel<2, true, true>
                            : (layout->n_xtal ? intensity_kernel<2, false, true> : intensity_kernel<XRSD_NX_QPT, false, false>);
+  if (single_precision_loops) {
+    if (layout->n_xtal) return cudaErrorInvalidValue;      // the caller refuses such layouts before it gets here
+    kern = intensity_kernel<XRSD_NX_QPT, false, false, true>;
+  }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long long n_blocks = (long long)batch * n_tiles;

@@ -32,6 +32,9 @@ namespace xrsd {
 
 constexpr int EVAL_THREADS = 128;
 constexpr int SHELL_CHUNK = 128;
+#ifndef XRSD_F32_MIN_X
+#define XRSD_F32_MIN_X 2.0      // single-precision path: smallest q r that continues in FP32
+#endif
 
 // shared-memory working set of one CTA (besides the pattern buffer)
 constexpr int CHEB_N = 17;                       // Chebyshev nodes of the far-field interpolant (degree 16)
@@ -129,7 +132,7 @@ __device__ __forceinline__ int pair_index(int n_sp, int a, int b) { return a * n
 // Accumulate I(q) of system `b` for q[q_begin .. q_begin+q_count) into I_sm[0 .. q_count).
 // All EVAL_THREADS threads of the CTA must call this.  `scratch` holds scratch_doubles doubles.
 // ------------------------------------------------------------------------------------------
-template <int QPT, bool RADIAL_MULTI, bool HAS_XTAL = true>
+template <int QPT, bool RADIAL_MULTI, bool HAS_XTAL = true, bool F32 = false>
 __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restrict__ prm, const xrsd_tables_t &T, int b,
                                   const double *__restrict__ q, int n_q, int q_begin, int q_count,
                                   double *__restrict__ I_sm, double *__restrict__ scratch, int scratch_doubles,
@@ -227,7 +230,8 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               const double hi_t = __dadd_rn(r0t, __dmul_rn(pop.sampling_width, srt));
               len_t = ceil(__dsub_rn(hi_t, lo_t) / drt);
             }
-            n_r = (len_t > 0.0) ? (int)fmin(len_t, (double)(scratch_doubles / 2)) : 0;
+            // the scratch holds 3 doubles per radius: (r_i, rho_i) as doubles, then -- single-precision path -- as float2
+            n_r = (len_t > 0.0) ? (int)fmin(len_t, (double)(scratch_doubles / 3)) : 0;
             dstep = __dsub_rn(__dadd_rn(r_min, dr), r_min);
             r_first = r_min;
             const double two_s2 = 2.0 * (sigma_r * sigma_r);
@@ -237,6 +241,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               const double rho = exp(-1.0 * ((r0 - ri) * (r0 - ri)) / two_s2);
               scratch[2 * i] = ri;
               scratch[2 * i + 1] = rho;
+              if constexpr (F32) reinterpret_cast<float2 *>(scratch + 2 * n_r)[i] = make_float2((float)ri, (float)rho);
               const double r3 = ri * ri * ri;
               part += rho * (r3 * r3);
             }
@@ -314,6 +319,51 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
                 c[j] = fma(c[j], cd[j], -(s[j] * sd[j]));
                 s[j] = sn;
               }
+            }
+            if constexpr (F32) {
+              // The optional single-precision path (BASELINE north_star: <= 1e-5 relative).  Radii with q r >= XRSD_F32_MIN_X for
+              // the whole warp -- where t = sin x - x cos x is O(x) and an absolute error of a few 1e-6 in sin / cos
+              // does no harm -- continue the SAME recurrence in FP32: 8 FP32 instructions per (q, r) pair on the
+              // full-rate pipe instead of 8 FP64.  Everything else stays FP64: the radii below that (t cancels like
+              // x^3/3 there), the starting phases and their span-to-span carry (an FP32 product q r is off by 4e-6 rad
+              // at x = 35), the normalisation, the Percus-Yevick factor, the accumulation of the populations.
+              for (; i < n_r; ++i) {       // phase B64: FP64 recurrence up to q r = 2
+                const double2 rr = *reinterpret_cast<const double2 *>(scratch + 2 * i);
+                if (!(qmin_t * rr.x < XRSD_F32_MIN_X)) break;
+#pragma unroll
+                for (int j = 0; j < QPT; ++j) {
+                  const double x = qv[j] * rr.x;
+                  const double t = fma(-x, c[j], s[j]);
+                  acc[j] = fma(rr.y, t * t, acc[j]);
+                  const double sn = fma(s[j], cd[j], c[j] * sd[j]);
+                  c[j] = fma(c[j], cd[j], -(s[j] * sd[j]));
+                  s[j] = sn;
+                }
+              }
+              float sf[QPT], cf[QPT], sdf[QPT], cdf[QPT], accf[QPT], qf[QPT];
+#pragma unroll
+              for (int j = 0; j < QPT; ++j) {
+                sf[j] = (float)s[j]; cf[j] = (float)c[j]; sdf[j] = (float)sd[j]; cdf[j] = (float)cd[j];
+                qf[j] = (float)qv[j];
+                accf[j] = 0.0f;
+              }
+              const float2 *rec32 = reinterpret_cast<const float2 *>(scratch + 2 * n_r);
+#pragma unroll 2
+              for (; i < n_r; ++i) {       // phase B32
+                const float2 rw = rec32[i];
+                const float rf = rw.x, wf = rw.y;
+#pragma unroll
+                for (int j = 0; j < QPT; ++j) {
+                  const float x = qf[j] * rf;
+                  const float t = fmaf(-x, cf[j], sf[j]);
+                  accf[j] = fmaf(wf, t * t, accf[j]);
+                  const float sn = fmaf(sf[j], cdf[j], cf[j] * sdf[j]);
+                  cf[j] = fmaf(cf[j], cdf[j], -(sf[j] * sdf[j]));
+                  sf[j] = sn;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < QPT; ++j) acc[j] += (double)accf[j];
             }
             // phase B: pure recurrence, 8 DP instructions per (q, r)
 #pragma unroll 2

@@ -282,8 +282,12 @@ class Engine(object):
             T = None        # new store with the larger capacities
 
     # -- intensity ----------------------------------------------------------------------
-    def intensity(self, layout, q, params, tables=None, out=None):
-        """I[b, :] on the device.  q: [n_q]; params: [batch, n_params] (numpy or cuda tensors)."""
+    def intensity(self, layout, q, params, tables=None, out=None, precision="fp64"):
+        """I[b, :] on the device.  q: [n_q]; params: [batch, n_params] (numpy or cuda tensors).
+        precision="fp32" selects the optional single-precision path (xrsd_intensity_batch_f32: size-distribution
+        loops in FP32, <= 1e-5 relative to the default; layouts without crystalline populations only)."""
+        if precision not in ("fp64", "fp32"):
+            raise ValueError("precision must be 'fp64' or 'fp32'")
         torch = self.torch
         self.check_grid(layout, q)
         d_q = self.to_device(q)
@@ -296,6 +300,11 @@ class Engine(object):
             out = torch.empty((batch, n_q), dtype=torch.float64, device=self.device)
         if layout.n_xtal and tables is None:
             tables = self.build_tables(layout, d_p, batch, params_host=host_params)
+        if precision == "fp32":
+            abi.check(self.lib.xrsd_intensity_batch_f32(C.byref(layout.c), d_q.data_ptr(), n_q, d_p.data_ptr(), d_p.shape[1],
+                                                        batch, out.data_ptr(), out.shape[1], self._stream()))
+            self.launches += 1
+            return out
         abi.check(self.lib.xrsd_intensity_batch(C.byref(layout.c), d_q.data_ptr(), n_q, d_p.data_ptr(), d_p.shape[1], batch,
                                                 C.byref(tables.c) if tables is not None else None,
                                                 out.data_ptr(), out.shape[1], self._stream()))
