@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define XRSD_ABI_VERSION 4
+#define XRSD_ABI_VERSION 5
 
 #define XRSD_MAX_POPS 6      /* noise model + up to 5 populations per system layout   */
 #define XRSD_MAX_SPECIES 4   /* species (atoms) per crystalline population             */
@@ -269,12 +269,14 @@ int32_t xrsd_jacobian_n_variants(const xrsd_layout_t *layout, const int32_t *fre
 
 /* One damped Gauss-Newton (Levenberg-Marquardt) proposal per system:
  * solve (JTJ + lambda*diag(JTJ)) delta = -JTr, limit every component to max_rel_step * |parameter| (a relative
- * trust region; 0 = no limit), project onto [lo, hi], write trial params. */
+ * trust region; 0 = no limit), project onto [lo, hi], write trial params.  d_iter (optional): a device counter the launch
+ * increments -- the number of the iteration it opens, which xrsd_lm_trial_update(tag = 0) reads from d_flags[2]; with it
+ * the launches of an iteration carry no host-side iteration number and can be replayed as a CUDA graph. */
 int xrsd_lm_propose(const double *d_params, int32_t ld_params, int32_t batch,
                     const int32_t *free_idx, int32_t n_free, const int32_t *ties, const double *tie_coef,
                     int32_t n_tie, const double *d_JTJ, const double *d_JTr, const double *d_lambda,
                     const double *d_lo, const double *d_hi, const uint8_t *d_active,
-                    double *d_trial, double max_rel_step, void *stream);
+                    double *d_trial, double max_rel_step, int32_t *d_iter, void *stream);
 /* Accept/reject: where chi2_trial < chi2 copy trial -> params, lambda /= down, else lambda *= up;
  * clears `active` for systems whose relative improvement fell below ftol or that hit lambda_max. */
 int xrsd_lm_update(double *d_params, int32_t ld_params, int32_t batch,
@@ -297,14 +299,49 @@ int xrsd_objective_prepare(const xrsd_objective_t *obj, const double *d_q, int32
  * (chi2 changed by <= ftol relative, or every parameter by <= xtol relative), 2 = lambda beyond lambda_max, 3 = objective
  * not finite; d_active[b] is cleared with it.  A trial point whose reflection tables (trial_tables, optional) carry a
  * non-zero status counts as chi2 = inf and ORs that status into d_flags[0]; a system that is still running after this
- * update raises d_flags[1] to `tag` (atomic max), so a caller that passes the iteration number (from 1) reads "anything
- * left to do?" from the same two words without a reduction launch (d_flags: two int32, optional). */
+ * update raises d_flags[1] to `tag` (atomic max; tag = 0: to d_flags[2], the counter xrsd_lm_propose keeps), so a caller
+ * reads "anything left to do?" from these words without a reduction launch (d_flags: three int32, optional). */
 int xrsd_lm_trial_update(const xrsd_objective_t *obj, const double *d_q, int32_t n_q, const double *d_I, int64_t ld_I,
                          int32_t batch, const double *d_Iobs, const double *d_dI, int64_t ld_obs, double *d_params,
                          int32_t ld_params, const double *d_trial, double *d_chi2, double *d_chi2_trial, double *d_lambda,
                          uint8_t *d_active, uint8_t *d_accepted, uint8_t *d_needjac, uint8_t *d_reason, int32_t *d_n_accept,
                          const xrsd_tables_t *trial_tables, int32_t n_xtal, int32_t *d_flags, int32_t tag, double up, double down,
                          double ftol, double xtol, double lambda_max, void *stream);
+
+/* One WHOLE iteration of the resident loop in one call -- what xrsdkit_b200/fitting.py issues per iteration, from C, so
+ * that the host cost of an iteration is one foreign call instead of eight (an iteration of a 2000-system batch is about a
+ * millisecond of GPU work):
+ *   xrsd_jacobian_batch (mode = XRSD_JAC_FULL on the first iteration, which also copies chi2 -> d_chi2_init; BASE_READY
+ *   afterwards; masked by d_needjac) -> xrsd_lm_propose (counts the iteration in d_flags[2]) -> xrsd_reflection_tables of
+ *   the trial point (layouts with crystalline populations; box `loop_cells`) -> xrsd_jacobian_batch(PATTERNS_ONLY) into
+ *   the trial workspace -> xrsd_lm_trial_update (tag = 0) -> xrsd_lm_accept.
+ * All pointers except layout / obj / index arrays / tables are device memory; obj must be a PREPARED objective
+ * (d_fo / d_w are the streams of xrsd_objective_prepare); d_ws_base / d_ws_trial are workspaces of
+ * xrsd_jacobian_workspace_bytes(n_q, batch, n_free) and (n_q, batch, 0) bytes whose partial-sum areas start zeroed. */
+typedef struct xrsd_lm_state {
+  const xrsd_layout_t *layout;
+  const xrsd_objective_t *obj;
+  const double *d_q;
+  int32_t n_q, ld_params;
+  double *d_params, *d_trial;              /* [batch][ld_params] accepted / trial parameters */
+  int32_t batch, n_free;
+  const double *d_fo, *d_w;                /* prepared objective streams */
+  int64_t ld_obs;
+  const int32_t *free_idx;                 /* [n_free] parameter slots (xrsd_lm_propose) */
+  const int32_t *jac_idx;                  /* [n_free] the same, -(slot + 1) where a variant is forced (xrsd_jacobian_batch) */
+  const int32_t *ties;
+  const double *tie_coef;
+  int32_t n_tie, n_var, n_pops, loop_cells;
+  double rel_step, max_rel_step, up, down, ftol, xtol, lambda_max;
+  double *d_JTJ, *d_JTr, *d_chi2, *d_chi2_trial, *d_chi2_init, *d_lambda;
+  const double *d_lo, *d_hi;
+  uint8_t *d_active, *d_accepted, *d_needjac, *d_reason;
+  int32_t *d_n_accept, *d_flags;           /* d_flags: three int32, see xrsd_lm_trial_update */
+  const xrsd_tables_t *tables, *trial_tables;
+  void *d_ws_base, *d_ws_trial;
+} xrsd_lm_state_t;
+int xrsd_lm_iteration(const xrsd_lm_state_t *state, int32_t base_ready, void *stream);
+int32_t xrsd_sizeof_lm_state(void);      /* sizeof(xrsd_lm_state_t) as compiled, for bindings */
 
 /* Accepted systems (d_accepted[b] != 0) take over the trial evaluation: the 1 + n_pops slabs of the trial workspace
  * (pattern, running totals; see xrsd_jacobian_n_variants) go to slab 0 and slabs n_var.. of the base workspace

@@ -31,7 +31,7 @@ def test_struct_mirror_matches_library():
     lib.xrsd_struct_sizes(*[ctypes.byref(s) for s in sizes])
     assert [s.value for s in sizes] == [ctypes.sizeof(abi.Pop), ctypes.sizeof(abi.Layout), ctypes.sizeof(abi.Tables),
                                         ctypes.sizeof(abi.Objective)]
-    assert lib.xrsd_abi_version() == abi.ABI_VERSION == 4
+    assert lib.xrsd_abi_version() == abi.ABI_VERSION == 5
     assert lib.xrsd_table_smem_bytes(10, 10, 10) > 2 * 19 ** 3
 
 
@@ -104,7 +104,7 @@ def test_argument_errors_without_touching_the_gpu():
     assert b"stride" in lib.xrsd_last_error()
     assert lib.xrsd_lm_accept(1 << 20, 4, 1 << 21, 64, None, 64, 16, 2, 2, None, None, 0, None) == abi.EINVAL
     assert lib.xrsd_lm_accept(1 << 20, 0, None, 0, None, 0, 16, 2, 2, None, None, 0, None) == abi.OK
-    rc = lib.xrsd_lm_propose(1 << 20, 6, 2, free, 2, None, None, 0, 1 << 21, 1 << 22, 1 << 23, 1 << 24, 1 << 25, None, 1 << 26, -1.0, None)
+    rc = lib.xrsd_lm_propose(1 << 20, 6, 2, free, 2, None, None, 0, 1 << 21, 1 << 22, 1 << 23, 1 << 24, 1 << 25, None, 1 << 26, -1.0, None, None)
     assert rc == abi.EINVAL and b"max_rel_step" in lib.xrsd_last_error()
 
 

@@ -22,7 +22,7 @@ OK, EINVAL, ECUDA, ECAPACITY, ENOMEM = 0, -1, -2, -3, -4
 
 i32, f64 = C.c_int32, C.c_double
 N_FEATURES, FEATURE_MAX_Q = 21, 8192
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class Pop(C.Structure):
@@ -62,6 +62,21 @@ class Objective(C.Structure):
 
 vp = C.c_void_p
 i64 = C.c_int64
+
+
+class LmState(C.Structure):
+    """xrsd_lm_state_t: everything one Levenberg-Marquardt iteration of a resident fit touches (xrsd_lm_iteration)."""
+    _fields_ = [("layout", C.POINTER(Layout)), ("obj", C.POINTER(Objective)), ("d_q", vp), ("n_q", i32), ("ld_params", i32),
+                ("d_params", vp), ("d_trial", vp), ("batch", i32), ("n_free", i32), ("d_fo", vp), ("d_w", vp), ("ld_obs", i64),
+                ("free_idx", C.POINTER(i32)), ("jac_idx", C.POINTER(i32)), ("ties", C.POINTER(i32)), ("tie_coef", C.POINTER(f64)),
+                ("n_tie", i32), ("n_var", i32), ("n_pops", i32), ("loop_cells", i32),
+                ("rel_step", f64), ("max_rel_step", f64), ("up", f64), ("down", f64), ("ftol", f64), ("xtol", f64), ("lambda_max", f64),
+                ("d_JTJ", vp), ("d_JTr", vp), ("d_chi2", vp), ("d_chi2_trial", vp), ("d_chi2_init", vp), ("d_lambda", vp),
+                ("d_lo", vp), ("d_hi", vp), ("d_active", vp), ("d_accepted", vp), ("d_needjac", vp), ("d_reason", vp),
+                ("d_n_accept", vp), ("d_flags", vp), ("tables", C.POINTER(Tables)), ("trial_tables", C.POINTER(Tables)),
+                ("d_ws_base", vp), ("d_ws_trial", vp)]
+
+
 _SIGNATURES = {
     "xrsd_last_error": (C.c_char_p, []),
     "xrsd_abi_version": (C.c_int, []),
@@ -85,9 +100,11 @@ _SIGNATURES = {
     "xrsd_objective_prepare": (C.c_int, [C.POINTER(Objective), vp, i32, vp, vp, i64, i32, vp, vp, i64, vp]),
     "xrsd_lm_trial_update": (C.c_int, [C.POINTER(Objective), vp, i32, vp, i64, i32, vp, vp, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp,
                                        vp, vp, C.POINTER(Tables), i32, vp, i32, f64, f64, f64, f64, f64, vp]),
+    "xrsd_lm_iteration": (C.c_int, [C.POINTER(LmState), i32, vp]),
+    "xrsd_sizeof_lm_state": (i32, []),
     "xrsd_lm_accept": (C.c_int, [vp, i32, vp, i64, vp, i64, i32, i32, i32, C.POINTER(Tables), C.POINTER(Tables), i32, vp]),
     "xrsd_copy_rows_masked": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int64, i32, vp, vp]),
-    "xrsd_lm_propose": (C.c_int, [vp, i32, i32, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(f64), i32, vp, vp, vp, vp, vp, vp, vp, f64, vp]),
+    "xrsd_lm_propose": (C.c_int, [vp, i32, i32, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(f64), i32, vp, vp, vp, vp, vp, vp, vp, f64, vp, vp]),
     "xrsd_lm_update": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, vp, f64, f64, f64, f64, vp]),
     "xrsd_intensity_batch_host": (C.c_int, [C.POINTER(Layout), vp, i32, vp, i32, i32, vp, C.c_int64]),
     "xrsd_release_workspace": (None, []),
@@ -118,7 +135,7 @@ def load():
     sizes = [i32() for _ in range(4)]
     lib.xrsd_struct_sizes(*[C.byref(s) for s in sizes])
     mine = [C.sizeof(Pop), C.sizeof(Layout), C.sizeof(Tables), C.sizeof(Objective)]
-    if [s.value for s in sizes] != mine:
+    if [s.value for s in sizes] != mine or lib.xrsd_sizeof_lm_state() != C.sizeof(LmState):
         raise ImportError("xrsdkit_b200: struct layout mismatch between abi.py %r and the library %r"
                           % (mine, [s.value for s in sizes]))
     if lib.xrsd_abi_version() != ABI_VERSION:

@@ -36,7 +36,7 @@ cudaError_t xrsd_launch_copy_rows_masked(double *, long long, const double *, lo
                                          cudaStream_t);
 int xrsd_jacobian_count_variants(const xrsd_layout_t *, const int32_t *, int, const int32_t *, int);
 cudaError_t xrsd_launch_lm_propose(const double *, int, int, const int32_t *, int, const int32_t *, const double *, int, const double *, const double *,
-                                   const double *, const double *, const double *, const uint8_t *, double *, double, cudaStream_t);
+                                   const double *, const double *, const double *, const uint8_t *, double *, double, int *, cudaStream_t);
 cudaError_t xrsd_launch_lm_update(double *, int, int, const double *, double *, const double *, double *, uint8_t *, int *,
                                   double, double, double, double, cudaStream_t);
 cudaError_t xrsd_launch_objective_prepare(const xrsd_objective_t *, const double *, int, const double *, const double *, long long,
@@ -174,6 +174,8 @@ int xrsd_struct_sizes(int32_t *sp, int32_t *sl, int32_t *st, int32_t *so) {
   if (so) *so = (int32_t)sizeof(xrsd_objective_t);
   return XRSD_OK;
 }
+
+int32_t xrsd_sizeof_lm_state(void) { return (int32_t)sizeof(xrsd_lm_state_t); }
 
 int64_t xrsd_table_smem_bytes(int32_t n1, int32_t n2, int32_t n3) {
   const int64_t cells = (int64_t)(2 * n1 - 1) * (2 * n2 - 1) * (2 * n3 - 1);
@@ -391,7 +393,7 @@ int32_t xrsd_jacobian_n_variants(const xrsd_layout_t *layout, const int32_t *fre
 
 int xrsd_lm_propose(const double *d_params, int32_t ld_params, int32_t batch, const int32_t *free_idx, int32_t n_free,
                     const int32_t *ties, const double *tie_coef, int32_t n_tie, const double *d_JTJ, const double *d_JTr, const double *d_lambda, const double *d_lo, const double *d_hi,
-                    const uint8_t *d_active, double *d_trial, double max_rel_step, void *stream) {
+                    const uint8_t *d_active, double *d_trial, double max_rel_step, int32_t *d_iter, void *stream) {
   if (n_free < 1 || n_free > XRSD_MAX_FREE) return fail(XRSD_EINVAL, "n_free=%d (max %d)", n_free, XRSD_MAX_FREE);
   if (!(max_rel_step >= 0.0)) return fail(XRSD_EINVAL, "max_rel_step must be >= 0 (0 = no limit)");
   if (!d_params || !free_idx || !d_JTJ || !d_JTr || !d_lambda || !d_lo || !d_hi || !d_trial) return fail(XRSD_EINVAL, "NULL pointer");
@@ -403,7 +405,7 @@ int xrsd_lm_propose(const double *d_params, int32_t ld_params, int32_t batch, co
     if (slot < 0 || slot >= ld_params) return fail(XRSD_EINVAL, "ties[%d]=%d", i, ties[i]);
   }
   cudaError_t e = xrsd_launch_lm_propose(d_params, ld_params, batch, free_idx, n_free, ties, tie_coef, n_tie, d_JTJ, d_JTr, d_lambda, d_lo, d_hi,
-                                         d_active, d_trial, max_rel_step, (cudaStream_t)stream);
+                                         d_active, d_trial, max_rel_step, d_iter, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "lm_propose_kernel");
   return XRSD_OK;
 }
@@ -494,6 +496,44 @@ int xrsd_lm_accept(const uint8_t *d_accepted, int32_t batch, double *d_dst, int6
   if (e != cudaSuccess) return cuda_fail(e, "lm_accept_kernel");
   return XRSD_OK;
 }
+
+int xrsd_lm_iteration(const xrsd_lm_state_t *st, int32_t base_ready, void *stream) {
+  if (!st || !st->layout || !st->obj) return fail(XRSD_EINVAL, "NULL state / layout / objective");
+  if (!st->obj->prepared) return fail(XRSD_EINVAL, "xrsd_lm_iteration needs a prepared objective");
+  if (!st->d_ws_base || !st->d_ws_trial || !st->d_flags || !st->d_chi2_init) return fail(XRSD_EINVAL, "NULL workspace / flags");
+  const int n_x = st->layout->n_xtal;
+  if (n_x > 0 && (!st->tables || !st->trial_tables)) return fail(XRSD_EINVAL, "crystalline layout without tables");
+  int rc = xrsd_jacobian_batch(st->layout, st->obj, st->d_q, st->n_q, st->d_params, st->ld_params, st->batch, st->tables, st->d_fo,
+                               st->d_w, st->ld_obs, st->jac_idx, st->n_free, st->ties, st->tie_coef, st->n_tie, st->rel_step,
+                               base_ready ? XRSD_JAC_BASE_READY : XRSD_JAC_FULL, st->d_JTJ, st->d_JTr, st->d_chi2, st->d_ws_base,
+                               st->d_needjac, stream);
+  if (rc) return rc;
+  if (!base_ready) {
+    cudaError_t e = cudaMemcpyAsync(st->d_chi2_init, st->d_chi2, (size_t)st->batch * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "chi2_init copy");
+  }
+  rc = xrsd_lm_propose(st->d_params, st->ld_params, st->batch, st->free_idx, st->n_free, st->ties, st->tie_coef, st->n_tie, st->d_JTJ,
+                       st->d_JTr, st->d_lambda, st->d_lo, st->d_hi, st->d_active, st->d_trial, st->max_rel_step, st->d_flags + 2, stream);
+  if (rc) return rc;
+  if (n_x > 0) {
+    rc = xrsd_reflection_tables(st->layout, st->d_trial, st->ld_params, st->batch, st->trial_tables, st->loop_cells, st->d_active, stream);
+    if (rc) return rc;
+  }
+  rc = xrsd_jacobian_batch(st->layout, st->obj, st->d_q, st->n_q, st->d_trial, st->ld_params, st->batch, st->trial_tables, nullptr,
+                           nullptr, 0, nullptr, 0, st->ties, st->tie_coef, st->n_tie, st->rel_step, XRSD_JAC_PATTERNS_ONLY, nullptr,
+                           nullptr, nullptr, st->d_ws_trial, st->d_active, stream);
+  if (rc) return rc;
+  const int64_t ld_trial = (int64_t)(1 + st->n_pops) * st->n_q;
+  rc = xrsd_lm_trial_update(st->obj, st->d_q, st->n_q, (const double *)st->d_ws_trial, ld_trial, st->batch, st->d_fo, st->d_w, st->ld_obs,
+                            st->d_params, st->ld_params, st->d_trial, st->d_chi2, st->d_chi2_trial, st->d_lambda, st->d_active,
+                            st->d_accepted, st->d_needjac, st->d_reason, st->d_n_accept, n_x > 0 ? st->trial_tables : nullptr, n_x,
+                            st->d_flags, 0, st->up, st->down, st->ftol, st->xtol, st->lambda_max, stream);
+  if (rc) return rc;
+  return xrsd_lm_accept(st->d_accepted, st->batch, (double *)st->d_ws_base, (int64_t)(st->n_var + st->n_pops) * st->n_q,
+                        (const double *)st->d_ws_trial, ld_trial, st->n_q, st->n_var, st->n_pops, n_x > 0 ? st->tables : nullptr,
+                        n_x > 0 ? st->trial_tables : nullptr, n_x, stream);
+}
+
 
 int xrsd_copy_rows_masked(double *d_dst, int64_t dst_stride, const double *d_src, int64_t src_stride, int64_t row_len,
                           int32_t n_rows, const uint8_t *d_mask, void *stream) {

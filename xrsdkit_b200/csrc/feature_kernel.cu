@@ -14,6 +14,7 @@
 // pattern and 168 bytes out; the arithmetic is dominated by the windowed correlations
 // (n x 101).
 #include <cuda_runtime.h>
+#include "launch_util.cuh"
 #include <math.h>
 #include <stdint.h>
 
@@ -429,7 +430,7 @@ extern "C" cudaError_t xrsd_launch_features(const double *d_q, int n_q, const do
   if (n_q <= XRSD_FEATURE_MAX_Q) {
     const size_t smem = xrsd_feature_smem_bytes_impl(n_q);
     // opt in on every launch: the attribute is per device and static shared memory counts against the 48 KB default too
-    cudaError_t e = cudaFuncSetAttribute(feature_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = xrsd::allow_max_dynamic_smem(feature_kernel<unsigned short>);
     if (e != cudaSuccess) return e;
     const int threads = n_q >= 2048 ? 512 : 256;
     const int grid = batch < sms * 16 ? batch : sms * 16;

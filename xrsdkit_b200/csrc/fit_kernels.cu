@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include "launch_util.cuh"
 #include "system_eval.cuh"
 
 namespace xrsd {
@@ -703,8 +704,9 @@ __global__ void lm_propose_kernel(const double *__restrict__ params, int ldp, in
                                   const double *__restrict__ JTJ, const double *__restrict__ JTr,
                                   const double *__restrict__ lambda, const double *__restrict__ lo,
                                   const double *__restrict__ hi, const uint8_t *__restrict__ active,
-                                  double *__restrict__ trial, double max_rel_step) {
+                                  double *__restrict__ trial, double max_rel_step, int *__restrict__ iter_counter) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0 && iter_counter != nullptr) iter_counter[0] += 1;      // the iteration this launch opens (read by lm_trial_update)
   if (b >= batch) return;
   const int nf = F.n_free;
   const double *p = params + (size_t)b * ldp;
@@ -958,7 +960,7 @@ lm_trial_update_kernel(const xrsd_objective_t O, const double *__restrict__ q, i
     take = acc;
     accepted[b] = (uint8_t)acc;
     if (why) { active[b] = 0; reason[b] = (uint8_t)why; }
-    else if (flags != nullptr) atomicMax(&flags[1], tag);      // still running after iteration `tag`
+    else if (flags != nullptr) atomicMax(&flags[1], tag > 0 ? tag : flags[2]);      // still running after this iteration
     needjac[b] = (uint8_t)(acc && !why);
   }
   __syncthreads();
@@ -1062,7 +1064,7 @@ extern "C" cudaError_t xrsd_launch_residual(const xrsd_layout_t *layout, const x
   const size_t smem = ((size_t)((q_per_cta + 1) & ~1) + (size_t)scratch_doubles) * sizeof(double);
   auto kern = radial_multi ? residual_kernel<true, true>
                            : (layout->n_xtal ? residual_kernel<false, true> : residual_kernel<false, false>);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = allow_max_dynamic_smem(kern);
   if (e != cudaSuccess) return e;
   if (batch <= 0) return cudaSuccess;
   const int n_tiles = (n_q + q_per_cta - 1) / q_per_cta;
@@ -1104,7 +1106,7 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
   const size_t smem = xrsd_jacobian_smem(layout->n_params, n_free, q_per_cta, scratch_doubles, &pat);
   auto kern = radial_multi ? jacobian_variants_kernel<true, true>
                            : (layout->n_xtal ? jacobian_variants_kernel<false, true> : jacobian_variants_kernel<false, false>);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = allow_max_dynamic_smem(kern);
   if (e != cudaSuccess) return e;
   if (batch <= 0) return cudaSuccess;
   if (q_per_cta < 0) q_per_cta = -q_per_cta;
@@ -1130,7 +1132,7 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
     const size_t smem = ((size_t)JM_STAGES * (F.n_var + layout->n_pops + 3) * JR_THREADS + (size_t)(JR_THREADS / 32) * (NFt + 2) * JM_PITCH) *
                         sizeof(double);
     auto launch = [&](auto kern) -> cudaError_t {
-      cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t er = allow_max_dynamic_smem(kern);
       if (er != cudaSuccess) return er;
       kern<<<batch * n_chunks, JR_THREADS, smem, stream>>>(layout->n_pops, *obj, d_q, n_q, d_params, ldp, batch, d_Iobs, d_dI, ld_obs, F,
                                                           rel_step, d_Fvar, d_acc, d_tickets, d_JTJ, d_JTr, d_chi2, chunk_q, n_chunks,
@@ -1142,8 +1144,7 @@ extern "C" cudaError_t xrsd_launch_jacobian(const xrsd_layout_t *layout, const x
   const size_t ring_bytes = (size_t)JR_STAGES * (F.n_var + layout->n_pops + 3) * JR_THREADS * sizeof(double);
   // opt in on every launch (microseconds; the attribute is per device and static shared memory counts against the
   // 48 KB default too)
-  e = n_free <= 8 ? cudaFuncSetAttribute(jacobian_reduce_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes)
-                  : cudaFuncSetAttribute(jacobian_reduce_kernel<XRSD_MAX_FREE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes);
+  e = n_free <= 8 ? allow_max_dynamic_smem(jacobian_reduce_kernel<8, 8>) : allow_max_dynamic_smem(jacobian_reduce_kernel<XRSD_MAX_FREE, 4>);
   if (e != cudaSuccess) return e;
   if (n_free <= 8)
     jacobian_reduce_kernel<8, 8><<<batch * n_chunks, JR_THREADS, ring_bytes, stream>>>(
@@ -1160,11 +1161,11 @@ extern "C" cudaError_t xrsd_launch_lm_propose(const double *d_params, int ldp, i
                                               const int32_t *ties, const double *tie_coef, int n_tie,
                                               const double *d_JTJ, const double *d_JTr, const double *d_lambda,
                                               const double *d_lo, const double *d_hi, const uint8_t *d_active,
-                                              double *d_trial, double max_rel_step, cudaStream_t stream) {
+                                              double *d_trial, double max_rel_step, int *d_iter, cudaStream_t stream) {
   const FreeSet F = xrsd::make_free_set(nullptr, free_idx, n_free, ties, tie_coef, n_tie);
   if (batch <= 0) return cudaSuccess;
   xrsd::lm_propose_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(d_params, ldp, batch, F, d_JTJ, d_JTr, d_lambda, d_lo, d_hi,
-                                                                   d_active, d_trial, max_rel_step);
+                                                                   d_active, d_trial, max_rel_step, d_iter);
   return cudaGetLastError();
 }
 

@@ -6,6 +6,7 @@
 // not tied to shared memory and one CTA can take a whole pattern -- the per-population prologue
 // (cell, shells, Voigt tables) is then paid once per pattern instead of once per 2048 q-points.
 // Replaces System.compute_intensity, system/__init__.py:112-130.
+#include "launch_util.cuh"
 #include "system_eval.cuh"
 
 #ifndef XRSD_NX_MIN_CTAS
@@ -94,7 +95,7 @@ extern "C" cudaError_t xrsd_launch_intensity(const xrsd_layout_t *layout, const 
     if (layout->n_xtal) return cudaErrorInvalidValue;      // the caller refuses such layouts before it gets here
     kern = intensity_kernel<XRSD_NX_QPT, false, false, true>;
   }
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = xrsd::allow_max_dynamic_smem(kern);
   if (e != cudaSuccess) return e;
   const long long n_blocks = (long long)batch * n_tiles;
   if (n_blocks <= 0) return cudaSuccess;

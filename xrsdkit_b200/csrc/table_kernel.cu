@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "lattice.cuh"
+#include "launch_util.cuh"
 
 namespace xrsd {
 
@@ -628,7 +629,7 @@ extern "C" cudaError_t xrsd_launch_tables(const xrsd_layout_t *layout, const dou
                                           const xrsd_tables_t *tables, int max_cells, int cap_list,
                                           const uint8_t *d_active, cudaStream_t stream) {
   const size_t smem = (size_t)xrsd_table_smem_layout(max_cells, cap_list);
-  cudaError_t e = cudaFuncSetAttribute(xrsd::reflection_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = xrsd::allow_max_dynamic_smem(xrsd::reflection_table_kernel);
   if (e != cudaSuccess) return e;
   const int n_tables = batch * layout->n_xtal;
   if (n_tables <= 0) return cudaSuccess;

@@ -129,6 +129,15 @@ class Engine(object):
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
+    def capture_stream(self):
+        """A side stream per host thread for CUDA-graph captures (capture is not allowed on the default stream)."""
+        import threading
+        pool = self.__dict__.setdefault("_capture_streams", {})
+        key = threading.get_ident()
+        if key not in pool:
+            pool[key] = self.torch.cuda.Stream(device=self.device)
+        return pool[key]
+
     def to_device(self, arr):
         torch = self.torch
         if isinstance(arr, torch.Tensor):
@@ -473,18 +482,7 @@ class Engine(object):
         n_q = q.shape[0]
         if resident is not None:
             chunk = batch
-            need = int(self.lib.xrsd_jacobian_workspace_bytes(n_q, chunk, nf))
-            store = self.__dict__.setdefault("_jac_resident", {})
-            ent = store.get(resident)
-            if ent is None or ent[0].numel() < need or ent[1] != (n_q, chunk, nf):
-                if base_ready:
-                    raise RuntimeError("base_ready needs the resident workspace of a previous call with the same shape")
-                # only the accumulator / ticket area behind the pattern slabs has to start at zero
-                ws_new = torch.empty(need, dtype=torch.uint8, device=self.device)
-                ws_new[int(chunk) * (nf + 1 + abi.MAX_POPS) * n_q * 8:].zero_()
-                ent = (ws_new, (n_q, chunk, nf))
-                store[resident] = ent
-            ws = ent[0]
+            ws = self.resident_workspace(resident, n_q, chunk, nf, must_exist=base_ready)
         else:
             if base_ready:
                 raise ValueError("base_ready requires a resident workspace")
@@ -526,6 +524,22 @@ class Engine(object):
                 ws.data_ptr(), (active.data_ptr() + lo) if active is not None else None, self._stream()))
             self.launches += 1 if patterns_only else 2
         return out
+
+    def resident_workspace(self, key, n_q, rows, nf, must_exist=False):
+        """The Jacobian workspace kept under `key` (created on first use: pattern slabs, then the zeroed partial-sum /
+        ticket area) for `rows` systems and `nf` free parameters."""
+        need = int(self.lib.xrsd_jacobian_workspace_bytes(n_q, rows, nf))
+        store = self.__dict__.setdefault("_jac_resident", {})
+        ent = store.get(key)
+        if ent is None or ent[0].numel() < need or ent[1] != (n_q, rows, nf):
+            if must_exist:
+                raise RuntimeError("base_ready needs the resident workspace of a previous call with the same shape")
+            # only the accumulator / ticket area behind the pattern slabs has to start at zero
+            ws_new = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+            ws_new[int(rows) * (nf + 1 + abi.MAX_POPS) * n_q * 8:].zero_()
+            ent = (ws_new, (n_q, rows, nf))
+            store[key] = ent
+        return ent[0]
 
     def _zero_jacobian_tail(self, ws, n_q, rows, nf):
         head = int(rows) * (nf + 1 + abi.MAX_POPS) * int(n_q) * 8

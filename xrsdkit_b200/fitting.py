@@ -65,8 +65,10 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         lm_accept       (accepted systems: trial pattern -> base rows, trial tables -> the system's tables)
 
     A rejected step leaves the parameters, and therefore the Jacobian, as they are: the next iteration only solves
-    again with more damping and evaluates the new trial point.  The host reads one flag word every `check_every`
-    iterations (all converged? a table outgrown?).
+    again with more damping and evaluates the new trial point.  The host reads three flag words every `check_every`
+    iterations (all converged? a table outgrown?).  Nothing in an iteration depends on host state (the iteration number
+    lives on the device, xrsd_lm_propose counts it), so a resident fit issues each iteration through ONE native call
+    (xrsd_lm_iteration).
 
     When the pattern slabs of the batch fit in `resident_limit` bytes they stay on the device for the whole fit;
     a larger batch is fitted in row groups that fit (systems are independent; a group of `min_group_rows` systems
@@ -156,7 +158,6 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     d_accepted = torch.zeros(batch, dtype=u8, device=eng.device)
     d_reason = torch.zeros(batch, dtype=u8, device=eng.device)
     d_nacc = torch.zeros(batch, dtype=torch.int32, device=eng.device)
-    d_flags = torch.zeros(2, dtype=torch.int32, device=eng.device)      # [0]: OR of trial-table status words met by the loop
     d_trial = d_p.clone()
     d_chi2_t = torch.empty(batch, dtype=torch.float64, device=eng.device)
     jout = (torch.empty((batch, nf, nf), dtype=torch.float64, device=eng.device),
@@ -208,57 +209,106 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
     persist = resident_bytes(batch) <= resident_limit
     key0, key1 = ("lm", id(d_p), 0), ("lm", id(d_p), 1)
     res_ws = None if persist else eng.residual_workspace(batch, n_q)
-    base_valid = False
     tight = bool(layout.n_xtal) and loop_cells < max_cells
-    chi2_init = None
+    d_flags = torch.zeros(3, dtype=torch.int32, device=eng.device)      # [0] trial-table status bits met, [1] last iteration that
+                                                                          # left a system running, [2] iteration counter (device side)
+    state = dict(base_valid=False)
+
+    def iteration():
+        """The launches of one iteration (see the docstring).  Nothing in here depends on the iteration number or
+        reads anything back, so from the second iteration on the same sequence is replayed as a CUDA graph."""
+        eng.jacobian(layout, obj, d_q, d_p, d_fo, d_w, ld_obs, jac_slots, tables, rel_step, out=jout, active=d_needjac,
+                     ties=ties, resident=key0 if persist else None, base_ready=persist and state['base_valid'])
+        state['base_valid'] = persist
+        if state.get('chi2_init') is None:          # first iteration only (never inside a graph capture)
+            state['chi2_init'] = jout[2].clone()
+        abi.check(lib.xrsd_lm_propose(d_p.data_ptr(), d_p.shape[1], batch, idx, nf, tie_c, coef_c, n_tie, jout[0].data_ptr(),
+                                      jout[1].data_ptr(), d_lambda.data_ptr(), d_lo.data_ptr(), d_hi.data_ptr(),
+                                      d_active.data_ptr(), d_trial.data_ptr(), float(max_rel_step),
+                                      d_flags.data_ptr() + 8, eng._stream()))
+        if layout.n_xtal:       # in-loop builds do not read their status back; lm_trial_update looks at it on the device
+            eng.build_tables(layout, d_trial, batch, max_cells=loop_cells, reuse=t_tables, check=False, active=d_active)
+        trial_pat, ld_pat = None, 0
+        if persist:     # pattern and running totals of the trial point, kept in the second resident workspace
+            eng.jacobian(layout, obj, d_q, d_trial, None, None, 0, [], t_tables, rel_step, active=d_active, ties=ties,
+                         resident=key1, patterns_only=True)
+            slabs1 = eng.jacobian_slabs(key1, layout, batch, n_q, 1)
+            trial_pat, ld_pat = slabs1.data_ptr(), slabs1.stride(0)
+        else:
+            abi.check(lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_trial.data_ptr(),
+                                              d_trial.shape[1], batch, C.byref(t_tables.c) if t_tables is not None else None,
+                                              d_fo.data_ptr(), d_w.data_ptr(), ld_obs, d_chi2_t.data_ptr(), res_ws.data_ptr(),
+                                              d_active.data_ptr(), eng._stream()))
+        abi.check(lib.xrsd_lm_trial_update(C.byref(obj), d_q.data_ptr(), n_q, trial_pat, ld_pat, batch, d_fo.data_ptr(),
+                                           d_w.data_ptr(), ld_obs, d_p.data_ptr(), d_p.shape[1], d_trial.data_ptr(),
+                                           jout[2].data_ptr(), d_chi2_t.data_ptr(), d_lambda.data_ptr(), d_active.data_ptr(),
+                                           d_accepted.data_ptr(), d_needjac.data_ptr(), d_reason.data_ptr(), d_nacc.data_ptr(),
+                                           C.byref(t_tables.c) if t_tables is not None else None, layout.n_xtal,
+                                           d_flags.data_ptr(), 0, float(up), float(down), float(ftol), float(xtol),
+                                           float(lambda_max), eng._stream()))
+        if persist or layout.n_xtal:
+            ws0 = eng._jac_resident[key0][0] if persist else None
+            ws1 = eng._jac_resident[key1][0] if persist else None
+            abi.check(lib.xrsd_lm_accept(d_accepted.data_ptr(), batch,
+                                         ws0.data_ptr() if persist else None, (n_var + n_pops) * n_q,
+                                         ws1.data_ptr() if persist else None, (1 + n_pops) * n_q, n_q, n_var, n_pops,
+                                         C.byref(tables.c) if tables is not None else None,
+                                         C.byref(t_tables.c) if t_tables is not None else None, layout.n_xtal, eng._stream()))
+        eng.launches += 3 + (0 if persist else 1)
+
+    # Resident fits run the iteration natively: ONE call (xrsd_lm_iteration) issues the launches listed above from C, so a
+    # small batch, whose iteration is a millisecond of GPU work, does not pay the host time of eight ctypes calls.
+    # (Replaying the iteration as a CUDA graph was tried: capture + instantiation per fit cost more than they saved.)
+    native = None
+    if persist:
+        ws0 = eng.resident_workspace(key0, n_q, batch, nf)
+        ws1 = eng.resident_workspace(key1, n_q, batch, 0)
+        state['chi2_init'] = torch.empty(batch, dtype=torch.float64, device=eng.device)
+        native = abi.LmState()
+        native.layout, native.obj = C.pointer(layout.c), C.pointer(obj)
+        native.d_q, native.n_q = d_q.data_ptr(), n_q
+        native.d_params, native.ld_params, native.batch, native.d_trial = d_p.data_ptr(), d_p.shape[1], batch, d_trial.data_ptr()
+        native.d_fo, native.d_w, native.ld_obs = d_fo.data_ptr(), d_w.data_ptr(), ld_obs
+        jidx = (C.c_int32 * nf)(*jac_slots)
+        native.free_idx, native.jac_idx, native.n_free = C.cast(idx, C.POINTER(C.c_int32)), C.cast(jidx, C.POINTER(C.c_int32)), nf
+        native.ties = C.cast(tie_c, C.POINTER(C.c_int32)) if n_tie else None
+        native.tie_coef = C.cast(coef_c, C.POINTER(C.c_double)) if n_tie else None
+        native.n_tie = n_tie
+        native.rel_step, native.max_rel_step = float(rel_step), float(max_rel_step)
+        native.up, native.down, native.ftol, native.xtol, native.lambda_max = float(up), float(down), float(ftol), float(xtol), float(lambda_max)
+        native.d_JTJ, native.d_JTr, native.d_chi2, native.d_chi2_trial = jout[0].data_ptr(), jout[1].data_ptr(), jout[2].data_ptr(), d_chi2_t.data_ptr()
+        native.d_lambda, native.d_lo, native.d_hi = d_lambda.data_ptr(), d_lo.data_ptr(), d_hi.data_ptr()
+        native.d_active, native.d_accepted, native.d_needjac, native.d_reason = (d_active.data_ptr(), d_accepted.data_ptr(),
+                                                                                   d_needjac.data_ptr(), d_reason.data_ptr())
+        native.d_n_accept, native.d_flags = d_nacc.data_ptr(), d_flags.data_ptr()
+        native.d_ws_base, native.d_ws_trial = ws0.data_ptr(), ws1.data_ptr()
+        native.d_chi2_init = state['chi2_init'].data_ptr()
+        native.n_var, native.n_pops = n_var, n_pops
+
+        def refresh_native():
+            native.tables = C.pointer(tables.c) if tables is not None else None
+            native.trial_tables = C.pointer(t_tables.c) if t_tables is not None else None
+            native.loop_cells = min(int(loop_cells), _engine.SMEM_CELLS) if layout.n_xtal else 0
+        refresh_native()
+        per_iter = 6 + (2 if layout.n_xtal else 0)
     try:
         for it in range(max_iter):
             n_iter = it + 1
-            eng.jacobian(layout, obj, d_q, d_p, d_fo, d_w, ld_obs, jac_slots, tables, rel_step, out=jout, active=d_needjac,
-                         ties=ties, resident=key0 if persist else None, base_ready=persist and base_valid)
-            base_valid = persist
-            if chi2_init is None:
-                chi2_init = jout[2].clone()
-            abi.check(lib.xrsd_lm_propose(d_p.data_ptr(), d_p.shape[1], batch, idx, nf, tie_c, coef_c, n_tie, jout[0].data_ptr(),
-                                          jout[1].data_ptr(), d_lambda.data_ptr(), d_lo.data_ptr(), d_hi.data_ptr(),
-                                          d_active.data_ptr(), d_trial.data_ptr(), float(max_rel_step), stream))
-            if layout.n_xtal:       # in-loop builds do not read their status back; lm_trial_update looks at it on the device
-                eng.build_tables(layout, d_trial, batch, max_cells=loop_cells, reuse=t_tables, check=False, active=d_active)
-            trial_pat, ld_pat = None, 0
-            if persist:     # pattern and running totals of the trial point, kept in the second resident workspace
-                eng.jacobian(layout, obj, d_q, d_trial, None, None, 0, [], t_tables, rel_step, active=d_active, ties=ties,
-                             resident=key1, patterns_only=True)
-                slabs1 = eng.jacobian_slabs(key1, layout, batch, n_q, 1)
-                trial_pat, ld_pat = slabs1.data_ptr(), slabs1.stride(0)
+            if native is not None:
+                abi.check(lib.xrsd_lm_iteration(C.byref(native), 1 if it else 0, eng._stream()))
+                eng.launches += per_iter
             else:
-                abi.check(lib.xrsd_residual_batch(C.byref(layout.c), C.byref(obj), d_q.data_ptr(), n_q, d_trial.data_ptr(),
-                                                  d_trial.shape[1], batch, C.byref(t_tables.c) if t_tables is not None else None,
-                                                  d_fo.data_ptr(), d_w.data_ptr(), ld_obs, d_chi2_t.data_ptr(), res_ws.data_ptr(),
-                                                  d_active.data_ptr(), stream))
-            abi.check(lib.xrsd_lm_trial_update(C.byref(obj), d_q.data_ptr(), n_q, trial_pat, ld_pat, batch, d_fo.data_ptr(),
-                                               d_w.data_ptr(), ld_obs, d_p.data_ptr(), d_p.shape[1], d_trial.data_ptr(),
-                                               jout[2].data_ptr(), d_chi2_t.data_ptr(), d_lambda.data_ptr(), d_active.data_ptr(),
-                                               d_accepted.data_ptr(), d_needjac.data_ptr(), d_reason.data_ptr(), d_nacc.data_ptr(),
-                                               C.byref(t_tables.c) if t_tables is not None else None, layout.n_xtal,
-                                               d_flags.data_ptr(), n_iter, float(up), float(down), float(ftol), float(xtol),
-                                               float(lambda_max), stream))
-            if persist or layout.n_xtal:
-                ws0 = eng._jac_resident[key0][0] if persist else None
-                ws1 = eng._jac_resident[key1][0] if persist else None
-                abi.check(lib.xrsd_lm_accept(d_accepted.data_ptr(), batch,
-                                             ws0.data_ptr() if persist else None, (n_var + n_pops) * n_q,
-                                             ws1.data_ptr() if persist else None, (1 + n_pops) * n_q, n_q, n_var, n_pops,
-                                             C.byref(tables.c) if tables is not None else None,
-                                             C.byref(t_tables.c) if t_tables is not None else None, layout.n_xtal, stream))
-            eng.launches += 3 + (0 if persist else 1)
+                iteration()
             if it % check_every == check_every - 1:
                 # the only host sync of the loop: [0] status bits met, [1] the last iteration that left a system running
-                st_seen, last_running = [int(v) for v in d_flags.cpu().tolist()]
-                any_active = last_running == n_iter
+                st_seen, last_running, n_done = [int(v) for v in d_flags.cpu().tolist()]
+                any_active = last_running == n_done
                 if st_seen & abi.TABLE_GRID_OVERFLOW and tight:
                     # an active system proposed a cell beyond the near box and was turned back: re-centre the box
                     loop_cells = near_cells(d_p.cpu().numpy())
                     tight = loop_cells < max_cells
+                    if native is not None:
+                        refresh_native()
                 if st_seen & (abi.TABLE_LIST_OVERFLOW | abi.TABLE_SHELL_OVERFLOW):
                     # a trial table outgrew the store's capacities (those trial points were turned back): move to a
                     # larger store -- the checked build of the accepted points grows it further if it has to
@@ -268,6 +318,8 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
                     tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=store.views[0], share=shareable)
                     store = tables.store
                     t_tables = store.views[1]
+                    if native is not None:
+                        refresh_native()
                 if st_seen:
                     d_flags[0:1].zero_()
                 if not any_active:
@@ -278,6 +330,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         chi2 = eng.residual(layout, obj, d_q, d_p, d_fo, d_w, tables=tables)
     finally:
         eng.release_resident(key0, key1)
+    chi2_init = state['chi2_init']
     res = FitResult(d_p, chi2_init, chi2, n_iter, d_nacc, d_active.bool(), d_reason)
     if return_device:
         return res
