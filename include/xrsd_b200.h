@@ -44,7 +44,22 @@ extern "C" {
 #define XRSD_MAX_OPS 9       /* symmetry operations per point group (m-3m has 9)       */
 #define XRSD_MAX_PARAMS 64   /* flat parameter slots per system                        */
 #define XRSD_MAX_FREE 16     /* free (fitted) parameters per system                    */
-#define XRSD_MAX_TIES 8      /* equality constraints between parameters per system     */
+#define XRSD_MAX_TIES 48     /* constraint terms (linear terms and expression-program words) per system */
+/* Constraint terms as the `ties` (int32 pairs) / `tie_coef` (double pairs) arguments carry them, applied in order:
+ *   (dst, src, scale, offset), dst >= 0, src >= 0      p[dst]  = scale * p[src] + offset
+ *   (-(dst + 1), src, scale, offset)                   p[dst] += scale * p[src] + offset      (further terms of a sum)
+ *   (dst, -1, scale, offset)                           p[dst]  = scale * (top of the expression stack) + offset; stack cleared
+ *   (-(XRSD_TIE_WORD + op), arg, value, 0)             a word of a postfix expression program over a stack of
+ *                                                      XRSD_TIE_STACK values: PUSHC pushes `value`, PUSHP pushes p[arg], the
+ *                                                      binary words replace the two top values (a below b) by a (op) b,
+ *                                                      the unary ones the top value.  <- lmfit / asteval constraint_expr */
+#define XRSD_TIE_WORD 1000
+#define XRSD_TIE_OP0 10      /* internal: program words are kept as XRSD_TIE_OP0 + op */
+#define XRSD_TIE_STACK 8
+enum { XRSD_TIE_PUSHC = 0, XRSD_TIE_PUSHP = 1, XRSD_TIE_ADD = 2, XRSD_TIE_SUB = 3, XRSD_TIE_MUL = 4, XRSD_TIE_DIV = 5,
+       XRSD_TIE_POW = 6, XRSD_TIE_MIN = 7, XRSD_TIE_MAX = 8, XRSD_TIE_NEG = 9, XRSD_TIE_SQRT = 10, XRSD_TIE_EXP = 11,
+       XRSD_TIE_LOG = 12, XRSD_TIE_LOG10 = 13, XRSD_TIE_SIN = 14, XRSD_TIE_COS = 15, XRSD_TIE_TAN = 16, XRSD_TIE_ABS = 17,
+       XRSD_TIE_ASIN = 18, XRSD_TIE_ACOS = 19, XRSD_TIE_ATAN = 20 };
 
 /* xrsd_pop_t.kind */
 enum { XRSD_POP_NONE = 0, XRSD_POP_NOISE_FLAT = 1, XRSD_POP_NOISE_LOW_Q = 2,

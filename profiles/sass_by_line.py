@@ -43,7 +43,7 @@ def sass_counts(rep, kernel_re, launch=0):
 
 
 def line_table(stem, func_sub):
-    lib = os.path.join(ROOT, "xrsdkit_b200", "libxrsd_b200.so")
+    lib = os.path.abspath(os.environ.get("XRSD_B200_LIB") or os.path.join(ROOT, "xrsdkit_b200", "libxrsd_b200.so"))      # the build that was profiled
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", stem, lib], cwd=tmp, capture_output=True)
     cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]

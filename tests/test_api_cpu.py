@@ -221,3 +221,55 @@ def test_linear_combination_constraints_lower_to_ordered_terms():
     s.populations["a"].parameters["r"]["constraint_expr"] = "c__r"         # chained: a constrained parameter as a source
     with pytest.raises(NotImplementedError):
         lowering.lower_system(s, np.linspace(0.01, 0.5, 16)).ties()
+
+
+def test_nonlinear_constraints_compile_to_expression_programs():
+    """Any arithmetic constraint_expr (lmfit hands the string to asteval, reference system/__init__.py:197-209):
+    compile_constraint gives a postfix program whose host interpreter (_apply_ties, the twin of the device one)
+    reproduces Python's own evaluation of the expression, on numpy arrays and on torch tensors."""
+    import math
+    import torch
+    from xrsdkit_b200 import abi, fitting, lowering
+    from xrsdkit_b200.system import System
+    names = ["noise__I0", "a__r", "b__r", "c__r"]
+    rs = np.random.RandomState(3)
+    vals = rs.uniform(0.5, 3.0, (5, 4))
+    env = dict(sqrt=np.sqrt, exp=np.exp, log=np.log, log10=np.log10, sin=np.sin, cos=np.cos, tan=np.tan, arcsin=np.arcsin,
+               arccos=np.arccos, arctan=np.arctan, abs=np.abs, min=np.minimum, max=np.maximum, pi=np.pi, e=np.e)
+    for expr in ("a__r*b__r", "a__r/b__r + 1", "a__r**2 - 3*b__r", "sqrt(a__r*b__r)/2", "exp(-a__r) + log(b__r)*log10(b__r)",
+                 "sin(a__r)*cos(b__r) - tan(a__r/4)", "arcsin(a__r/4) + arccos(b__r/4) + arctan(a__r)", "abs(a__r - b__r)",
+                 "min(a__r, b__r)*max(a__r, 2)", "2*pi*a__r/(b__r + e)", "-(a__r + b__r)**0.5", "(a__r + 1)*(b__r + 2)*(a__r + 3)*(b__r + 4)",
+                 "sqrt(2)*a__r*b__r"):
+        words = lowering.compile_constraint(expr, names)
+        ties = words + [(3, -1, 1.0, 0.0)]
+        want = eval(expr, dict(env, **{n: vals[:, i] for i, n in enumerate(names)}))
+        P = vals.copy()
+        fitting._apply_ties(P, ties)
+        np.testing.assert_allclose(P[:, 3], want, rtol=1e-14, err_msg=expr)
+        T = torch.tensor(vals)
+        fitting._apply_ties(T, ties)
+        np.testing.assert_allclose(T[:, 3].numpy(), want, rtol=1e-14, err_msg=expr)
+    assert lowering.compile_constraint("sqrt(2)*3", names) == [(-abi.TIE_WORD, 0, math.sqrt(2) * 3, 0.0)]       # constants fold
+    for expr in ("a__r if a__r > 1 else 2", "a__r.real", "unknown__r*a__r", "a__r +", "a__r % 2", "erf(a__r)"):
+        with pytest.raises(NotImplementedError):
+            lowering.compile_constraint(expr, names)
+    deep = "a__r*(b__r + a__r*(b__r + a__r*(b__r + a__r*(b__r + a__r*(b__r + a__r*(b__r + a__r*(b__r + a__r*(b__r + a__r))))))))"
+    with pytest.raises(ValueError):
+        lowering.compile_constraint(deep, names)
+    # through the layout: a non-linear expression becomes program words closed by a store term; linear ones stay linear
+    s = System(a=dict(structure="diffuse", form="spherical", parameters={"r": {"value": 10.0}}),
+               b=dict(structure="diffuse", form="spherical", parameters={"r": {"value": 20.0}}),
+               c=dict(structure="diffuse", form="spherical",
+                      parameters={"r": {"value": 1.0, "constraint_expr": "sqrt(a__r*b__r)"},
+                                  "I0": {"value": 1.0, "constraint_expr": "2*a__r"}}))
+    lay = lowering.lower_system(s, np.linspace(0.01, 0.5, 16))
+    ties = lay.ties()
+    assert lowering.tied_slots(ties) == {lay.slot("c__r"), lay.slot("c__I0")}
+    assert sum(1 for t in ties if t[0] <= -abi.TIE_WORD) == 4 and sum(1 for t in ties if t[1] == -1) == 1
+    P = np.tile(lay.values, (2, 1))
+    fitting._apply_ties(P, ties)
+    np.testing.assert_allclose(P[:, lay.slot("c__r")], np.sqrt(200.0), rtol=1e-15)
+    np.testing.assert_allclose(P[:, lay.slot("c__I0")], 20.0, rtol=1e-15)
+    s.populations["c"].parameters["r"]["constraint_expr"] = "c__r*a__r"
+    with pytest.raises(NotImplementedError):
+        lowering.lower_system(s, np.linspace(0.01, 0.5, 16)).ties()

@@ -242,8 +242,30 @@ def test_fit_with_equality_constraint(eng):
         assert out3.populations["superlattice"].parameters["r"]["value"] == pytest.approx(0.45 * rp3 + 0.05 * a3, rel=1e-14)
         assert rp3 == pytest.approx(33.0, rel=1e-2) and a3 == pytest.approx(110.0, rel=2e-3), method
         assert out3.fit_report["final_objective"] < 0.1 * out3.fit_report["initial_objective"], method
-    # anything beyond that needs lmfit's asteval: rejected, not silently ignored
-    for expr in ("particle__r ** 2", "particle__r * superlattice__a", "sqrt(particle__r)", "nonsense__r"):
+    # a NON-LINEAR expression (compiled to an expression program, evaluated on the device wherever the parameters
+    # change): r_superlattice = sqrt(particle__r * superlattice__a) / 2
+    truth4 = make(33.0, 110.0, tie=False)
+    truth4.populations["superlattice"].parameters["r"]["value"] = np.sqrt(33.0 * 110.0) / 2
+    I4 = truth4.compute_intensity(q) * (1 + 0.01 * np.random.RandomState(11).randn(q.size))
+    start4 = make(34.5, 112.0)
+    start4.populations["superlattice"].parameters["r"]["constraint_expr"] = "sqrt(particle__r * superlattice__a) / 2"
+    for method in ("lm", "nelder-mead"):
+        out4 = fit(start4, q, I4, method=method)
+        rp4 = out4.populations["particle"].parameters["r"]["value"]
+        a4 = out4.populations["superlattice"].parameters["a"]["value"]
+        assert out4.populations["superlattice"].parameters["r"]["value"] == pytest.approx(np.sqrt(rp4 * a4) / 2, rel=1e-14)
+        assert rp4 == pytest.approx(33.0, rel=1e-2) and a4 == pytest.approx(110.0, rel=2e-3), method
+        assert out4.fit_report["final_objective"] < 0.1 * out4.fit_report["initial_objective"], method
+    # the program path and the linear path are the same function when the expression happens to be linear:
+    # "0.9*particle__r + 1" written with a product and a quotient of parameters takes the program path
+    start5 = make(34.5, 112.0)
+    start5.populations["superlattice"].parameters["r"]["constraint_expr"] = "0.9*particle__r*superlattice__a/superlattice__a + 1"
+    out5 = fit(start5, q, I2)
+    out2 = fit(start2, q, I2)
+    for pop, par in (("particle", "r"), ("superlattice", "a"), ("superlattice", "r"), ("superlattice", "I0")):
+        assert out5.populations[pop].parameters[par]["value"] == pytest.approx(out2.populations[pop].parameters[par]["value"], rel=1e-6)
+    # what is not arithmetic is rejected, not silently ignored
+    for expr in ("particle__r if particle__r > 1 else 2", "nonsense__r", "particle__r.real", "particle__r +"):
         start.populations["superlattice"].parameters["r"]["constraint_expr"] = expr
         with pytest.raises(NotImplementedError):
             fit(start, q, I)

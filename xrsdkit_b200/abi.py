@@ -8,7 +8,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("XRSD_B200_LIB") or os.path.join(HERE, "libxrsd_b200.so")   # override: A/B timing of two builds
 
-MAX_POPS, MAX_SPECIES, MAX_PAIRS, MAX_OPS, MAX_PARAMS, MAX_FREE, MAX_TIES = 6, 4, 10, 9, 64, 16, 8
+MAX_POPS, MAX_SPECIES, MAX_PAIRS, MAX_OPS, MAX_PARAMS, MAX_FREE, MAX_TIES = 6, 4, 10, 9, 64, 16, 48
+TIE_WORD, TIE_STACK = 1000, 8      # expression-program words of the constraint terms (include/xrsd_b200.h)
+TIE_OPS = ['pushc', 'pushp', 'add', 'sub', 'mul', 'div', 'pow', 'min', 'max', 'neg', 'sqrt', 'exp', 'log', 'log10', 'sin', 'cos',
+           'tan', 'abs', 'asin', 'acos', 'atan']
 
 POP_NONE, POP_NOISE_FLAT, POP_NOISE_LOW_Q, POP_NONCRYSTALLINE, POP_CRYSTALLINE = range(5)
 FORM_ATOMIC, FORM_SPHERE, FORM_SPHERE_R_NORMAL, FORM_GUINIER_POROD = range(4)

@@ -91,6 +91,34 @@ int check_layout(const xrsd_layout_t *L) {
   return XRSD_OK;
 }
 
+// constraint terms (include/xrsd_b200.h, XRSD_MAX_TIES): slots in range, program words known, stack never over- or underrun
+int check_ties(const int32_t *ties, int n_tie, int n_params) {
+  int depth = 0;
+  for (int t = 0; t < n_tie; ++t) {
+    const int d = ties[2 * t], a = ties[2 * t + 1];
+    if (d <= -XRSD_TIE_WORD) {
+      const int op = -d - XRSD_TIE_WORD;
+      if (op > XRSD_TIE_ATAN) return fail(XRSD_EINVAL, "ties[%d]: unknown expression word %d", 2 * t, op);
+      if (op == XRSD_TIE_PUSHP && (a < 0 || a >= n_params)) return fail(XRSD_EINVAL, "ties[%d]=%d", 2 * t + 1, a);
+      if (op <= XRSD_TIE_PUSHP) ++depth;
+      else if (op <= XRSD_TIE_MAX) { if (depth < 2) return fail(XRSD_EINVAL, "ties[%d]: expression stack underrun", 2 * t); --depth; }
+      else if (depth < 1) return fail(XRSD_EINVAL, "ties[%d]: expression stack underrun", 2 * t);
+      if (depth > XRSD_TIE_STACK) return fail(XRSD_ECAPACITY, "constraint expression deeper than %d values (XRSD_TIE_STACK)", XRSD_TIE_STACK);
+      continue;
+    }
+    const int dst = d < 0 ? -d - 1 : d;
+    if (dst >= n_params) return fail(XRSD_EINVAL, "ties[%d]=%d", 2 * t, d);
+    if (a == -1 && d >= 0) {                          // store from the stack
+      if (depth != 1) return fail(XRSD_EINVAL, "ties[%d]: a store needs exactly one value on the expression stack", 2 * t);
+      depth = 0;
+    } else if (a < 0 || a >= n_params) {
+      return fail(XRSD_EINVAL, "ties[%d]=%d", 2 * t + 1, a);
+    }
+  }
+  if (depth != 0) return fail(XRSD_EINVAL, "constraint expression without a closing store term");
+  return XRSD_OK;
+}
+
 // scratch doubles accumulate_system() needs for this layout
 int scratch_doubles_for(const xrsd_layout_t *L, int *radial_multi) {
   int need = 2 * 128 + 2;
@@ -361,10 +389,8 @@ int xrsd_jacobian_batch(const xrsd_layout_t *layout, const xrsd_objective_t *obj
   if (reduce && ld_obs != 0 && ld_obs < n_q) return fail(XRSD_EINVAL, "ld_obs < n_q");
   if (!(rel_step > 0.0)) return fail(XRSD_EINVAL, "rel_step must be > 0");
   if (n_tie < 0 || n_tie > XRSD_MAX_TIES || (n_tie > 0 && !ties)) return fail(XRSD_EINVAL, "n_tie=%d (max %d)", n_tie, XRSD_MAX_TIES);
-  for (int i = 0; i < 2 * n_tie; ++i) {
-    const int slot = (ties[i] < 0 && i % 2 == 0) ? -ties[i] - 1 : ties[i];      // dst = -(slot + 1): accumulating term
-    if (slot < 0 || slot >= layout->n_params) return fail(XRSD_EINVAL, "ties[%d]=%d", i, ties[i]);
-  }
+  rc = check_ties(ties, n_tie, layout->n_params);
+  if (rc) return rc;
   int rm;
   const int scratch = scratch_doubles_for(layout, &rm);
   if (scratch < 0) return fail(XRSD_ECAPACITY, "size quadrature too fine for shared memory");
@@ -400,9 +426,9 @@ int xrsd_lm_propose(const double *d_params, int32_t ld_params, int32_t batch, co
   for (int i = 0; i < n_free; ++i)
     if ((free_idx[i] < 0 ? -free_idx[i] - 1 : free_idx[i]) >= ld_params) return fail(XRSD_EINVAL, "free_idx[%d]=%d", i, free_idx[i]);
   if (n_tie < 0 || n_tie > XRSD_MAX_TIES || (n_tie > 0 && !ties)) return fail(XRSD_EINVAL, "n_tie=%d (max %d)", n_tie, XRSD_MAX_TIES);
-  for (int i = 0; i < 2 * n_tie; ++i) {
-    const int slot = (ties[i] < 0 && i % 2 == 0) ? -ties[i] - 1 : ties[i];
-    if (slot < 0 || slot >= ld_params) return fail(XRSD_EINVAL, "ties[%d]=%d", i, ties[i]);
+  {
+    const int rc_t = check_ties(ties, n_tie, ld_params);
+    if (rc_t) return rc_t;
   }
   cudaError_t e = xrsd_launch_lm_propose(d_params, ld_params, batch, free_idx, n_free, ties, tie_coef, n_tie, d_JTJ, d_JTr, d_lambda, d_lo, d_hi,
                                          d_active, d_trial, max_rel_step, d_iter, (cudaStream_t)stream);

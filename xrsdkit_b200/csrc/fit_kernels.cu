@@ -32,9 +32,12 @@ struct FreeSet {
   // the reduction forms every difference quotient as  scale_j * ((slab[ra] - slab[rb]) + slab[rc]):  slab rows of
   // the workspace, -1 = a row of zeros; scale_j = 1, or h / I0 for a linear parameter (lin_j set)
   int ra[XRSD_MAX_FREE], rb[XRSD_MAX_FREE], rc[XRSD_MAX_FREE], lin_j[XRSD_MAX_FREE];
-  int n_tie;                    // constraint terms, applied in order: "dst = scale * src + offset", or, with tie_add set,
-                                // "dst += scale * src + offset" (the further terms of a linear combination)
+  int n_tie;                    // constraint terms, applied in order (apply_ties below).  tie_add: 0 "dst = scale * src + offset",
+                                // 1 "dst += scale * src + offset" (the further terms of a linear combination), 2 "dst = scale *
+                                // (top of the expression stack) + offset", >= XRSD_TIE_OP0: a word of an expression program
+                                // (non-linear constraint_expr: push parameter tie_src / push constant tie_scale / operator)
   int tie_dst[XRSD_MAX_TIES], tie_src[XRSD_MAX_TIES], tie_add[XRSD_MAX_TIES];
+  int tie_to[XRSD_MAX_TIES];    // the slot a term that READS parameter tie_src feeds (-1: the term reads no parameter)
   double tie_scale[XRSD_MAX_TIES], tie_off[XRSD_MAX_TIES];
 };
 
@@ -64,11 +67,29 @@ static FreeSet make_free_set(const xrsd_layout_t *L, const int32_t *free_idx, in
   F.n_var = 1;
   F.n_tie = (ties && n_tie > 0) ? std::min(n_tie, (int)XRSD_MAX_TIES) : 0;
   for (int t = 0; t < F.n_tie; ++t) {
-    F.tie_add[t] = ties[2 * t] < 0;                      // dst given as -(slot + 1): accumulate
-    F.tie_dst[t] = ties[2 * t] < 0 ? -ties[2 * t] - 1 : ties[2 * t];
+    const int d = ties[2 * t];
     F.tie_src[t] = ties[2 * t + 1];
     F.tie_scale[t] = tie_coef ? tie_coef[2 * t] : 1.0;
     F.tie_off[t] = tie_coef ? tie_coef[2 * t + 1] : 0.0;
+    F.tie_to[t] = -1;
+    if (d <= -XRSD_TIE_WORD) {                           // a word of an expression program: -(XRSD_TIE_WORD + op)
+      F.tie_add[t] = XRSD_TIE_OP0 + (-d - XRSD_TIE_WORD);
+      F.tie_dst[t] = -1;
+    } else if (d < 0) {                                  // dst given as -(slot + 1): accumulate
+      F.tie_add[t] = 1;
+      F.tie_dst[t] = -d - 1;
+      F.tie_to[t] = F.tie_dst[t];
+    } else {                                             // src >= 0: linear term; src == -1: the value on the stack
+      F.tie_add[t] = F.tie_src[t] < 0 ? 2 : 0;
+      F.tie_dst[t] = d;
+      if (F.tie_src[t] >= 0) F.tie_to[t] = d;
+    }
+  }
+  // the parameters an expression program pushes feed the slot its closing "store" term sets
+  for (int t = F.n_tie - 1, to = -1; t >= 0; --t) {
+    if (F.tie_add[t] == 2) to = F.tie_dst[t];
+    else if (F.tie_add[t] < XRSD_TIE_OP0) to = -1;
+    else if (F.tie_add[t] == XRSD_TIE_OP0 + XRSD_TIE_PUSHP) F.tie_to[t] = to;
   }
   for (int j = 0; j < XRSD_MAX_FREE; ++j) { F.pop_of[j] = -1; F.vpop_of[j] = -1; }
   for (int j = 0; j < n_free; ++j) {
@@ -86,7 +107,7 @@ static FreeSet make_free_set(const xrsd_layout_t *L, const int32_t *free_idx, in
     if (L)
       for (int k = 0; k < L->n_pops; ++k) uses += (L->pops[k].p_I0 == slot);
     bool tied = false;      // a parameter that drives another one is not linear in a single term
-    for (int t = 0; t < F.n_tie; ++t) tied = tied || (F.tie_src[t] == slot);
+    for (int t = 0; t < F.n_tie; ++t) tied = tied || (F.tie_to[t] >= 0 && F.tie_src[t] == slot);
     if (pop >= 0 && uses == 1 && !tied && !forced) {
       F.pop_of[j] = pop;
       F.var_of[j] = 0;
@@ -99,7 +120,7 @@ static FreeSet make_free_set(const xrsd_layout_t *L, const int32_t *free_idx, in
         int users = 0, which = -1;
         for (int k = 0; k < L->n_pops; ++k) {
           bool u = pop_uses_slot(L->pops[k], slot);
-          for (int t = 0; t < F.n_tie; ++t) u = u || (F.tie_src[t] == slot && pop_uses_slot(L->pops[k], F.tie_dst[t]));
+          for (int t = 0; t < F.n_tie; ++t) u = u || (F.tie_to[t] >= 0 && F.tie_src[t] == slot && pop_uses_slot(L->pops[k], F.tie_to[t]));
           if (u) { ++users; which = k; }
         }
         if (users == 1) F.vpop_of[j] = which;
@@ -124,6 +145,59 @@ static FreeSet make_free_set(const xrsd_layout_t *L, const int32_t *free_idx, in
     }
   }
   return F;
+}
+
+// The constraint terms of a system, in order, on one parameter row (System.fit hands `constraint_expr` strings to
+// lmfit, system/__init__.py:197-209, which evaluates them with asteval after every change of the free parameters).
+// Linear expressions are one fused multiply-add per term; anything else was compiled by the host
+// (xrsdkit_b200/lowering.py: compile_constraint) into a postfix program over a small value stack.
+__device__ __forceinline__ void apply_ties(const FreeSet &F, double *p) {
+  double st[XRSD_TIE_STACK];
+  int sp = 0;
+  for (int t = 0; t < F.n_tie; ++t) {
+    const int op = F.tie_add[t];
+    if (op == 0) { p[F.tie_dst[t]] = fma(F.tie_scale[t], p[F.tie_src[t]], F.tie_off[t]); continue; }
+    if (op == 1) { p[F.tie_dst[t]] = fma(F.tie_scale[t], p[F.tie_src[t]], F.tie_off[t] + p[F.tie_dst[t]]); continue; }
+    if (op == 2) { p[F.tie_dst[t]] = fma(F.tie_scale[t], sp > 0 ? st[sp - 1] : 0.0, F.tie_off[t]); sp = 0; continue; }
+    const int w = op - XRSD_TIE_OP0;
+    if (w == XRSD_TIE_PUSHC) { if (sp < XRSD_TIE_STACK) st[sp++] = F.tie_scale[t]; continue; }
+    if (w == XRSD_TIE_PUSHP) { if (sp < XRSD_TIE_STACK) st[sp++] = p[F.tie_src[t]]; continue; }
+    if (w >= XRSD_TIE_ADD && w <= XRSD_TIE_MAX) {         // binary: a (op) b with b on top
+      if (sp < 2) continue;
+      const double b = st[--sp], a = st[sp - 1];
+      double r;
+      switch (w) {
+        case XRSD_TIE_ADD: r = a + b; break;
+        case XRSD_TIE_SUB: r = a - b; break;
+        case XRSD_TIE_MUL: r = a * b; break;
+        case XRSD_TIE_DIV: r = a / b; break;
+        case XRSD_TIE_POW: r = pow(a, b); break;
+        case XRSD_TIE_MIN: r = fmin(a, b); break;
+        default: r = fmax(a, b); break;
+      }
+      st[sp - 1] = r;
+      continue;
+    }
+    if (sp < 1) continue;
+    const double a = st[sp - 1];
+    double r = a;
+    switch (w) {
+      case XRSD_TIE_NEG: r = -a; break;
+      case XRSD_TIE_SQRT: r = sqrt(a); break;
+      case XRSD_TIE_EXP: r = exp(a); break;
+      case XRSD_TIE_LOG: r = log(a); break;
+      case XRSD_TIE_LOG10: r = log10(a); break;
+      case XRSD_TIE_SIN: r = sin(a); break;
+      case XRSD_TIE_COS: r = cos(a); break;
+      case XRSD_TIE_TAN: r = tan(a); break;
+      case XRSD_TIE_ABS: r = fabs(a); break;
+      case XRSD_TIE_ASIN: r = asin(a); break;
+      case XRSD_TIE_ACOS: r = acos(a); break;
+      case XRSD_TIE_ATAN: r = atan(a); break;
+      default: break;
+    }
+    st[sp - 1] = r;
+  }
 }
 
 // weight and mask of one q-point (system/__init__.py:164-172)
@@ -260,8 +334,7 @@ jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *
     const int j = F.free_of_var[v];
     const double p0 = prm[F.idx[j]];
     prm_s[F.idx[j]] = p0 + ((p0 != 0.0) ? fabs(p0) * rel_step : rel_step);
-    for (int t = 0; t < F.n_tie; ++t)                                              // tied parameters move along
-      prm_s[F.tie_dst[t]] = fma(F.tie_scale[t], prm_s[F.tie_src[t]], F.tie_off[t] + (F.tie_add[t] ? prm_s[F.tie_dst[t]] : 0.0));
+    apply_ties(F, prm_s);                                                         // tied parameters move along
   }
   __syncthreads();
   const int q_begin = tile * q_per_cta;
@@ -776,8 +849,7 @@ __global__ void lm_propose_kernel(const double *__restrict__ params, int ldp, in
     v = fmin(fmax(v, l), h);
     if (v == v) t[F.idx[j]] = v;
   }
-  for (int k = 0; k < F.n_tie; ++k)
-    t[F.tie_dst[k]] = fma(F.tie_scale[k], t[F.tie_src[k]], F.tie_off[k] + (F.tie_add[k] ? t[F.tie_dst[k]] : 0.0));
+  apply_ties(F, t);
 }
 
 __global__ void lm_update_kernel(double *__restrict__ params, int ldp, int batch, const double *__restrict__ trial,

@@ -37,11 +37,40 @@ class FitResult(object):
 
 
 def _apply_ties(params, ties):
-    """params[..., dst] = scale * params[..., src] + offset for every constraint term (dst, src[, scale, offset]), in
-    order; a dst given as -(slot + 1) adds its term to the slot (further terms of a linear combination)."""
+    """The constraint terms of SystemLayout.ties() on a parameter matrix (numpy array or torch tensor, [..., n_params]),
+    in order -- the host-side twin of apply_ties() in csrc/fit_kernels.cu: linear terms dst = scale * src + offset
+    (dst given as -(slot + 1): dst += ...), and the words of postfix expression programs over a value stack."""
+    if not ties:
+        return
+    is_np = isinstance(params, np.ndarray)
+    xp = np
+    if not is_np:
+        import torch as xp
+    f1 = {'neg': lambda a: -a, 'sqrt': xp.sqrt, 'exp': xp.exp, 'log': xp.log, 'log10': xp.log10, 'sin': xp.sin, 'cos': xp.cos,
+          'tan': xp.tan, 'abs': xp.abs, 'asin': xp.arcsin if is_np else xp.asin, 'acos': xp.arccos if is_np else xp.acos,
+          'atan': xp.arctan if is_np else xp.atan}
+    f2 = {'add': lambda a, b: a + b, 'sub': lambda a, b: a - b, 'mul': lambda a, b: a * b, 'div': lambda a, b: a / b,
+          'pow': lambda a, b: a ** b, 'min': xp.minimum, 'max': xp.maximum}
+    one = params[..., 0] * 0.0 + 1.0            # constants are pushed as arrays so that every function applies
+    stack = []
     for t in ties:
         scale, off = (t[2], t[3]) if len(t) >= 4 else (1.0, 0.0)
-        if t[0] < 0:
+        if t[0] <= -abi.TIE_WORD:
+            op = abi.TIE_OPS[-t[0] - abi.TIE_WORD]
+            if op == 'pushc':
+                stack.append(one * scale)
+            elif op == 'pushp':
+                stack.append(params[..., t[1]] * 1.0)
+            elif op in f2:
+                b = stack.pop()
+                a = stack.pop()
+                stack.append(f2[op](a, b))
+            else:
+                stack.append(f1[op](stack.pop()))
+        elif t[1] < 0:                          # store the value of the expression
+            params[..., t[0]] = stack.pop() * scale + off
+            stack = []
+        elif t[0] < 0:
             params[..., -t[0] - 1] += params[..., t[1]] * scale + off
         else:
             params[..., t[0]] = params[..., t[1]] * scale + off
@@ -90,7 +119,7 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         free_slots = layout.free_slots()
     if ties is None:
         ties = layout.ties()
-    free_slots = [s for s in free_slots if s not in [lowering.tie_slot(t[0]) for t in ties]]      # a tied parameter is not varied
+    free_slots = [s for s in free_slots if s not in lowering.tied_slots(ties)]      # a tied parameter is not varied
     tie_c, coef_c, n_tie = eng.tie_array(ties)
     nf = len(free_slots)
     if nf == 0:
@@ -358,7 +387,7 @@ def fit_system_inplace(system, q, I, dI=None, method='lm'):
         res = lm_fit_batch(lay, q, I, lay.values[None, :], free, max_iter=60, **kw)
     else:
         raise ValueError("unknown fit method %r" % (method,))
-    tied = [lowering.tie_slot(t[0]) for t in lay.ties()]
+    tied = lowering.tied_slots(lay.ties())
     for slot, rec in enumerate(lay.records):
         if slot in free or slot in tied:
             rec['value'] = float(res.params[0, slot])
@@ -426,7 +455,7 @@ def nm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         free_slots = layout.free_slots()
     if ties is None:
         ties = layout.ties()
-    free_slots = [s for s in free_slots if s not in [lowering.tie_slot(t[0]) for t in ties]]
+    free_slots = [s for s in free_slots if s not in lowering.tied_slots(ties)]
     nf = len(free_slots)
     if nf == 0:
         raise ValueError("no free parameters to fit")

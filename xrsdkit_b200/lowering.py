@@ -87,18 +87,28 @@ class SystemLayout(object):
         return [i for i, r in enumerate(self.records) if not r.get('fixed') and not r.get('constraint_expr')]
 
     def ties(self):
-        """Constraint terms [(dst, src, scale, offset)] for parameters whose constraint_expr is LINEAR in other parameters:
-        value[dst] = sum_k scale_k * value[src_k] + offset.  The first term of a constraint sets the slot, further
-        terms carry dst = -(slot + 1) and add to it (the convention of xrsd_jacobian_batch).  'particle__r' -- the only
-        form found in xrsdkit's fitted systems -- gives one term (1, 0); '2*particle__r', '(shell__r - 3) / 2',
-        'core__r + shell__t', '0.5*(a__r + b__r) + 1' work as well.  Anything non-linear (products of parameters,
-        functions: the rest of lmfit's asteval language) is rejected when a fit is requested."""
+        """Constraint terms for parameters that carry a constraint_expr, in the convention of xrsd_jacobian_batch
+        (include/xrsd_b200.h, XRSD_MAX_TIES).  An expression that is LINEAR in other parameters gives
+        (dst, src, scale, offset) terms: value[dst] = sum_k scale_k * value[src_k] + offset, the first term sets the slot,
+        further terms carry dst = -(slot + 1) and add to it; 'particle__r' -- the only form found in xrsdkit's fitted
+        systems -- gives one term (1, 0); '2*particle__r', '(shell__r - 3) / 2', 'core__r + shell__t' likewise.  Any
+        other arithmetic expression of lmfit's asteval language -- products and quotients of parameters, powers, sqrt,
+        exp, log, log10, sin, cos, tan, arcsin, arccos, arctan, abs, min, max, pi, e -- is compiled into a postfix program
+        (compile_constraint): words (-(TIE_WORD + op), slot, constant, 0) closed by a store term (dst, -1, 1, 0)."""
         out = []
         for i, r in enumerate(self.records):
             expr = r.get('constraint_expr')
             if not expr:
                 continue
-            terms, off = parse_linear_constraint(str(expr), self.names)
+            try:
+                terms, off = parse_linear_constraint(str(expr), self.names)
+            except NotLinear:
+                words = compile_constraint(str(expr), self.names)
+                if any(w[0] == -(abi.TIE_WORD + abi.TIE_OPS.index('pushp')) and w[1] == i for w in words):
+                    raise NotImplementedError("constraint_expr %r refers to its own parameter" % expr)
+                out.extend(words)
+                out.append((i, -1, 1.0, 0.0))
+                continue
             if any(src == i for src, _ in terms):
                 raise NotImplementedError("constraint_expr %r refers to its own parameter" % expr)
             if not terms:                                   # a constant: 0 * (any slot) + offset
@@ -107,8 +117,8 @@ class SystemLayout(object):
                 out.append((i if k == 0 else -(i + 1), src, scale, off if k == 0 else 0.0))
         if len(out) > abi.MAX_TIES:
             raise CapacityError("at most %d constraint terms per system (XRSD_MAX_TIES); this system has %d" % (abi.MAX_TIES, len(out)))
-        dsts = set(tie_slot(t[0]) for t in out)
-        if any(t[1] in dsts and t[2] != 0.0 for t in out):
+        dsts = tied_slots(out)
+        if any(tie_reads(t) is not None and tie_reads(t) in dsts and (t[0] <= -abi.TIE_WORD or t[2] != 0.0) for t in out):
             raise NotImplementedError("chained constraints (a constrained parameter used in another constraint_expr)")
         return out
 
@@ -278,8 +288,111 @@ def _lower_population(structure, form, settings, slots, q_last, table_slot, para
 
 
 def tie_slot(dst):
-    """slot of a constraint term's destination (-(slot + 1) marks an accumulating term)"""
+    """slot of a constraint term's destination (-(slot + 1) marks an accumulating term); None for a program word"""
+    if dst <= -abi.TIE_WORD:
+        return None
     return -dst - 1 if dst < 0 else dst
+
+
+def tied_slots(ties):
+    """the slots some constraint term sets"""
+    return set(tie_slot(t[0]) for t in ties) - {None}
+
+
+def tie_reads(term):
+    """the parameter slot a constraint term reads, or None (constants, operators, the store term of a program)"""
+    if term[0] <= -abi.TIE_WORD:
+        return term[1] if -term[0] - abi.TIE_WORD == abi.TIE_OPS.index('pushp') else None
+    return term[1] if term[1] >= 0 else None
+
+
+class NotLinear(NotImplementedError):
+    """raised by parse_linear_constraint for a well-formed expression that is not linear in the parameters"""
+
+
+_FUNCS = {'sqrt': 'sqrt', 'exp': 'exp', 'log': 'log', 'ln': 'log', 'log10': 'log10', 'sin': 'sin', 'cos': 'cos', 'tan': 'tan',
+          'abs': 'abs', 'fabs': 'abs', 'absolute': 'abs', 'arcsin': 'asin', 'asin': 'asin', 'arccos': 'acos', 'acos': 'acos',
+          'arctan': 'atan', 'atan': 'atan'}
+_FUNCS2 = {'min': 'min', 'minimum': 'min', 'max': 'max', 'maximum': 'max', 'pow': 'pow', 'power': 'pow'}
+_CONSTS = {'pi': np.pi, 'e': np.e}
+
+
+def compile_constraint(expr, names):
+    """A constraint expression as a postfix program: [(-(TIE_WORD + op), slot, constant, 0.0), ...] (abi.TIE_OPS).
+    Numbers, parameter names, pi / e, + - * / **, unary minus, and the functions listed in SystemLayout.ties();
+    constant sub-expressions are folded.  Raises NotImplementedError for anything else (comparisons, conditionals,
+    attribute access, ...: the part of asteval's language that is not arithmetic)."""
+    import ast
+    import math
+    try:
+        tree = ast.parse(expr.strip(), mode='eval')
+    except SyntaxError:
+        raise NotImplementedError("constraint_expr %r is not an arithmetic expression" % expr)
+    OP = dict((n, -(abi.TIE_WORD + k)) for k, n in enumerate(abi.TIE_OPS))
+    fold1 = {'neg': lambda a: -a, 'sqrt': math.sqrt, 'exp': math.exp, 'log': math.log, 'log10': math.log10, 'sin': math.sin,
+             'cos': math.cos, 'tan': math.tan, 'abs': abs, 'asin': math.asin, 'acos': math.acos, 'atan': math.atan}
+    fold2 = {'add': lambda a, b: a + b, 'sub': lambda a, b: a - b, 'mul': lambda a, b: a * b, 'div': lambda a, b: a / b,
+             'pow': lambda a, b: a ** b, 'min': min, 'max': max}
+
+    def const_of(words):
+        return words[0][2] if len(words) == 1 and words[0][0] == OP['pushc'] else None
+
+    def unary(name, a):
+        ca = const_of(a)
+        if ca is not None:
+            try:
+                return [(OP['pushc'], 0, float(fold1[name](ca)), 0.0)]
+            except (ValueError, OverflowError, ZeroDivisionError):
+                pass
+        return a + [(OP[name], 0, 0.0, 0.0)]
+
+    def binary(name, a, b):
+        ca, cb = const_of(a), const_of(b)
+        if ca is not None and cb is not None:
+            try:
+                return [(OP['pushc'], 0, float(fold2[name](ca, cb)), 0.0)]
+            except (ValueError, OverflowError, ZeroDivisionError):
+                pass
+        return a + b + [(OP[name], 0, 0.0, 0.0)]
+
+    def ev(node):
+        if isinstance(node, ast.Expression):
+            return ev(node.body)
+        if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)) and not isinstance(node.value, bool):
+            return [(OP['pushc'], 0, float(node.value), 0.0)]
+        if isinstance(node, ast.Name):
+            if node.id in names:
+                return [(OP['pushp'], names.index(node.id), 0.0, 0.0)]
+            if node.id in _CONSTS:
+                return [(OP['pushc'], 0, float(_CONSTS[node.id]), 0.0)]
+            raise NotImplementedError("constraint_expr %r: unknown parameter %r" % (expr, node.id))
+        if isinstance(node, ast.UnaryOp) and isinstance(node.op, ast.UAdd):
+            return ev(node.operand)
+        if isinstance(node, ast.UnaryOp) and isinstance(node.op, ast.USub):
+            return unary('neg', ev(node.operand))
+        if isinstance(node, ast.BinOp):
+            name = {ast.Add: 'add', ast.Sub: 'sub', ast.Mult: 'mul', ast.Div: 'div', ast.Pow: 'pow'}.get(type(node.op))
+            if name is None:
+                raise NotImplementedError("constraint_expr %r: operator %s is not supported" % (expr, type(node.op).__name__))
+            return binary(name, ev(node.left), ev(node.right))
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and not node.keywords:
+            fn = node.func.id
+            if fn in _FUNCS and len(node.args) == 1:
+                return unary(_FUNCS[fn], ev(node.args[0]))
+            if fn in _FUNCS2 and len(node.args) == 2:
+                return binary(_FUNCS2[fn], ev(node.args[0]), ev(node.args[1]))
+            raise NotImplementedError("constraint_expr %r: function %s() is not supported" % (expr, fn))
+        raise NotImplementedError("constraint_expr %r: only arithmetic on numbers and parameter names is supported" % expr)
+
+    words = ev(tree)
+    depth = peak = 0
+    for w in words:
+        op = abi.TIE_OPS[-w[0] - abi.TIE_WORD]
+        depth += 1 if op in ('pushc', 'pushp') else (-1 if op in fold2 else 0)
+        peak = max(peak, depth)
+    if peak > abi.TIE_STACK:
+        raise CapacityError("constraint_expr %r needs an expression stack of %d values (XRSD_TIE_STACK = %d)" % (expr, peak, abi.TIE_STACK))
+    return words
 
 
 def parse_linear_constraint(expr, names):
@@ -298,6 +411,8 @@ def parse_linear_constraint(expr, names):
         if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)) and not isinstance(node.value, bool):
             return {}, float(node.value)
         if isinstance(node, ast.Name):
+            if node.id in _CONSTS and node.id not in names:
+                return {}, float(_CONSTS[node.id])
             if node.id not in names:
                 raise NotImplementedError("constraint_expr %r: unknown parameter %r" % (expr, node.id))
             return {node.id: 1.0}, 0.0
@@ -315,17 +430,17 @@ def parse_linear_constraint(expr, names):
         if isinstance(node, ast.BinOp) and isinstance(node.op, ast.Mult):
             (ca, ka), (cb, kb) = ev(node.left), ev(node.right)
             if ca and cb:
-                raise NotImplementedError("constraint_expr %r is not linear (a product of parameters)" % expr)
+                raise NotLinear("constraint_expr %r is not linear (a product of parameters)" % expr)
             c, k, f = (ca, ka, kb) if ca else (cb, kb, ka)
             return dict((n, v * f) for n, v in c.items()), k * f
         if isinstance(node, ast.BinOp) and isinstance(node.op, ast.Div):
             (ca, ka), (cb, kb) = ev(node.left), ev(node.right)
             if cb:
-                raise NotImplementedError("constraint_expr %r is not linear (division by a parameter)" % expr)
+                raise NotLinear("constraint_expr %r is not linear (division by a parameter)" % expr)
             if kb == 0.0:
                 raise NotImplementedError("constraint_expr %r divides by zero" % expr)
             return dict((n, v / kb) for n, v in ca.items()), ka / kb
-        raise NotImplementedError("constraint_expr %r: only + - * / of numbers and parameter names are supported" % expr)
+        raise NotLinear("constraint_expr %r: only + - * / of numbers and parameter names are linear" % expr)
 
     coefs, off = ev(tree)
     if not np.isfinite([off] + list(coefs.values())).all():
