@@ -198,9 +198,10 @@ def fit(sys, q, I, dI=None, error_weighted=None, logI_weighted=None, q_range=Non
     converged / initial_objective / final_objective / fit_snr -- but the optimiser is the
     batched GPU Levenberg-Marquardt of xrsdkit_b200.fitting (batch of one) instead of
     lmfit's Nelder-Mead; method='nelder-mead' runs the reference's algorithm (scipy's Nelder-Mead
-    coefficients, lmfit's bound transform) on the same GPU objective.  A constraint_expr that is affine in one other parameter
-    ('particle__r', '2*particle__r + 1') is kept as a tie dst = scale*src + offset; other expressions raise
-    NotImplementedError.  The reference
+    coefficients, lmfit's bound transform) on the same GPU objective.  A constraint_expr ('particle__r',
+    '2*a__r + b__r - 3', 'sqrt(a__r*b__r)/2': any arithmetic expression of other parameters) is honoured exactly as
+    lmfit does -- re-evaluated whenever the free parameters change (lowering.SystemLayout.ties); conditionals,
+    comparisons and constraints on constrained parameters raise NotImplementedError.  The reference
     stores `error_weighted` into logI_weighted here (a bug, :255-256); this keeps the
     documented meaning."""
     from .. import fitting
