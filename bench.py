@@ -920,7 +920,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--batch", type=int, default=10000, help="parameter sets (systems) per GPU per pass")
     ap.add_argument("--fit-batch", type=int, default=16384, help="systems of the secondary cfg5 measurement (half sphere, half crystal)")
-    ap.add_argument("--gather-batch", type=int, default=8192, help="fits per rank of the gathered cfg5 measurement (N > 1)")
+    ap.add_argument("--gather-batch", type=int, default=125000,
+                    help="fits per rank of the gathered cfg5 measurement (N > 1); the default makes 8 ranks BASELINE config 5: 10^6 fits")
     ap.add_argument("--nm-rows", type=int, default=1024, help="systems per kind also fitted by batched Nelder-Mead (quality comparison)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline samples")
     ap.add_argument("--no-nm", action="store_true", help="skip the Nelder-Mead comparison of the fit workloads")
