@@ -110,6 +110,44 @@ def test_variant_slabs_of_one_population_parameters(eng):
     np.testing.assert_allclose((out[1] / scale).cpu().numpy(), (JTr / scale).cpu().numpy(), atol=1e-5 * float((JTr / scale).abs().max()))
 
 
+def test_hard_sphere_variants_with_a_resident_base(eng):
+    """r_hard and v_fraction act through S(q) alone: with a resident base (XRSD_JAC_BASE_READY, every LM iteration after
+    the first) their variant slabs are I_pop * S'(q) / S(q) from the stored running totals instead of a fresh
+    size-distribution loop.  The slabs and the normal equations must equal those of the full evaluation."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg2_system(System)
+    for q in (np.linspace(0.0, 0.5, 1111), np.sort(np.random.RandomState(4).uniform(0.004, 0.6, 900))):
+        lay = batch.layout_of(s, q)
+        B = 7
+        P = cfg2_params(lay, B, seed=5)
+        names = ("noise__I0", "p__I0", "p__r", "p__sigma", "p__r_hard", "p__v_fraction")
+        free = [lay.slot(k) for k in names]
+        obj = eng.objective(True, True, (0.0, float("inf")))
+        d_q, d_p = eng.to_device(q), eng.to_device(P)
+        d_I = eng.intensity(lay, d_q, d_p) * (1 + 0.02 * eng.to_device(np.random.RandomState(2).randn(B, len(q))))
+        key = ("t", "hs")
+        full = [t.clone() for t in eng.jacobian(lay, obj, d_q, d_p, d_I, None, len(q), free, None, resident=key)]
+        n_var = eng.jacobian_variants(lay, free)
+        assert n_var == 5                                   # base, r, sigma, r_hard, v_fraction
+        slabs_full = eng.jacobian_slabs(key, lay, B, len(q), n_var).clone()
+        ready = [t.clone() for t in eng.jacobian(lay, obj, d_q, d_p, d_I, None, len(q), free, None, resident=key, base_ready=True)]
+        slabs_ready = eng.jacobian_slabs(key, lay, B, len(q), n_var).clone()
+        eng.release_resident(key)
+        a, b = slabs_full.cpu().numpy(), slabs_ready.cpu().numpy()
+        fin = np.isfinite(a[:, 3:5])
+        assert np.array_equal(fin, np.isfinite(b[:, 3:5]))
+        # the population's term comes out of a difference of running totals: absolute error of the total's rounding
+        tol = 1e-12 * np.abs(a[:, 3:5]) + 8e-16 * np.nanmax(np.abs(a[:, 0]), axis=1)[:, None, None]
+        assert np.all(np.abs(a[:, 3:5] - b[:, 3:5])[fin] <= tol[fin])
+        np.testing.assert_array_equal(a[:, 1:3], b[:, 1:3])                 # r and sigma: the same evaluation in both modes
+        scale = full[0].diagonal(dim1=1, dim2=2).sqrt()
+        np.testing.assert_allclose((ready[0] / (scale[:, :, None] * scale[:, None, :])).cpu().numpy(),
+                                   (full[0] / (scale[:, :, None] * scale[:, None, :])).cpu().numpy(), atol=1e-6)
+        np.testing.assert_allclose((ready[1] / scale).cpu().numpy(), (full[1] / scale).cpu().numpy(),
+                                   atol=1e-6 * float((full[1] / scale).abs().max()))
+
+
 def test_empty_fit_mask_gives_zero_like_the_reference(eng):
     """No q-point inside q_range (or no positive observation): compute_chi2 sums over nothing and returns 0.0
     (tools/__init__.py:104-125); the kernels must not return 0/0."""

@@ -29,6 +29,9 @@ struct FreeSet {
   int free_of_var[XRSD_MAX_FREE + 1];   // inverse of var_of
   int vpop_of[XRSD_MAX_FREE];   // non-linear parameter used by ONE population (incl. what is tied to it): that population's
                                 // index -- its variant evaluates the population alone -- else -1 (whole system)
+  int sf_only[XRSD_MAX_FREE];   // 1: the parameter is r_hard or v_fraction of a disordered population and drives nothing
+                                // else -- it acts through the hard-sphere factor S(q) alone, so with a resident base its
+                                // variant is I_pop * S'(q) / S(q) and needs no size-distribution loop
   // the reduction forms every difference quotient as  scale_j * ((slab[ra] - slab[rb]) + slab[rc]):  slab rows of
   // the workspace, -1 = a row of zeros; scale_j = 1, or h / I0 for a linear parameter (lin_j set)
   int ra[XRSD_MAX_FREE], rb[XRSD_MAX_FREE], rc[XRSD_MAX_FREE], lin_j[XRSD_MAX_FREE];
@@ -124,6 +127,12 @@ static FreeSet make_free_set(const xrsd_layout_t *L, const int32_t *free_idx, in
           if (u) { ++users; which = k; }
         }
         if (users == 1) F.vpop_of[j] = which;
+        if (users == 1 && !tied && which > 0) {
+          const xrsd_pop_t &pp = L->pops[which];
+          if (pp.kind == XRSD_POP_NONCRYSTALLINE && pp.disordered && (slot == pp.p_r_hard || slot == pp.p_v_fraction) &&
+              pp.p_r_hard != pp.p_v_fraction && slot != pp.p_I0 && slot != pp.p_r && slot != pp.p_sigma && slot != pp.p_rg && slot != pp.p_D)
+            F.sf_only[j] = 1;
+        }
       }
     }
   }
@@ -347,6 +356,30 @@ jacobian_variants_kernel(const __grid_constant__ xrsd_layout_t L, const double *
   // a variant whose parameter belongs to one population evaluates that population alone (the reduction takes the
   // difference against the base's own term for it, from the running totals)
   const int only_pop = v > 0 ? F.vpop_of[F.free_of_var[v]] : -1;
+  if constexpr (!HX) {
+    // A hard-sphere parameter (r_hard, v_fraction) acts through S(q) alone: I_pop = I0 S(q) <ff^2>(q).  With a resident
+    // base (the running totals of the unperturbed system are in the workspace) its variant is the base's own term
+    // times S'(q) / S(q) -- two Percus-Yevick evaluations per q-point instead of the size-distribution loop.
+    if (v > 0 && skip_base && F.sf_only[F.free_of_var[v]]) {
+      const xrsd_pop_t &pop = L.pops[only_pop];
+      const HSConst h0 = hs_constants(prm[pop.p_r_hard], prm[pop.p_v_fraction]);
+      const HSConst h1 = hs_constants(prm_s[pop.p_r_hard], prm_s[pop.p_v_fraction]);
+      const double *tot_hi = slab0 + (size_t)(nv + only_pop) * n_q + q_begin;
+      const double *tot_lo = slab0 + (size_t)(nv + only_pop - 1) * n_q + q_begin;
+      const bool same_d = h0.d == h1.d;
+      const double f0 = 1.0 - h0.nc0, f1 = 1.0 - h1.nc0;
+      for (int i = tid; i < q_count; i += EVAL_THREADS) {
+        const double qi = q[q_begin + i];
+        const bool q0 = L.q0_is_zero && (q_begin + i == 0);
+        double s0, c0, s1, c1;
+        sincos(qi * h0.d, &s0, &c0);
+        if (same_d) { s1 = s0; c1 = c0; } else sincos(qi * h1.d, &s1, &c1);
+        const double d0 = 1.0 - hard_sphere_nc(qi, h0, q0, s0, c0), d1 = 1.0 - hard_sphere_nc(qi, h1, q0, s1, c1);
+        dst[i] = (tot_hi[i] - tot_lo[i]) * ((f1 * d0) / (f0 * d1));      // I_pop S'/S,  S = (1 - nc0) / (1 - nc)
+      }
+      return;
+    }
+  }
   accumulate_system<2, RM, HX>(L, prm_s, T, b, q, n_q, q_begin, q_count, I_sm, scratch, scratch_doubles, &S, prm,
                                v == 0 ? slab0 + (size_t)nv * n_q + q_begin : nullptr, n_q, only_pop);
   if constexpr (!HX)
