@@ -13,6 +13,7 @@ LIST="ncu --metrics gpu__time_duration.sum --clock-control none --csv"
 
 C2="python bench.py --steps 2 --warmup 3 --no-cpu --no-secondary"
 $C2 > $O/r02_plain_cfg2.json 2> $O/r02_plain_cfg2.err && {
+  $LIST -c 400 --log-file $O/r02_launches_cfg2.csv $C2 > $O/r02_ncu_list_cfg2.log 2>&1
   $NCU -k regex:intensity_kernel -s 40 -c 1 -f -o $O/r02_cfg2 $C2 > $O/r02_ncu_cfg2.log 2>&1
 }
 C3="python bench.py --workload cfg3 --steps 2 --warmup 3 --no-cpu --no-secondary"
