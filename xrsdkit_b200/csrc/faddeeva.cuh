@@ -129,7 +129,12 @@ static __device__ __noinline__ double rew_near(double x, const VoigtConst *vc) {
 constexpr int VOIGT_TAB_N = 17;          // nodes per interval (= CHEB_N of system_eval.cuh: shares its cosine table)
 constexpr int VOIGT_TAB_INTERVALS = 16;
 constexpr double VOIGT_TAB_MIN_Y = 1.0e-4;     // below: e^{-x^2} dominates out to x ~ 4.5 and the table loses relative accuracy
-constexpr int VOIGT_TAB_DOUBLES = VOIGT_TAB_N * VOIGT_TAB_INTERVALS;
+constexpr int VOIGT_TAB_DOUBLES = VOIGT_TAB_N * VOIGT_TAB_INTERVALS;      // nodes of one table build
+// A coefficient row is stored as 18 doubles c[0..17] with c[k + 1] = a_k (c[0] unused): the pairs (a_2j-1, a_2j) the
+// two Clenshaw chains consume together are then 16-byte aligned and come with ONE LDS.128 each -- 9 loads per
+// evaluation instead of 17 (the coefficient loads were 5 % of a crystalline pattern's instructions).
+constexpr int CHEB_ROW = 18;
+constexpr int VOIGT_TAB_STORE = CHEB_ROW * VOIGT_TAB_INTERVALS;
 
 // Cooperative build (all `nthreads` threads): cos_tab[k*N + m] = cos(pi k (m + 1/2)/N); tmp holds
 // VOIGT_TAB_DOUBLES doubles; tab receives the coefficients (a_0 .. a_16 per interval, a_0 not yet halved).
@@ -145,7 +150,7 @@ __device__ __forceinline__ void voigt_table(double *tab, double *tmp, const doub
     double a = 0.0;
 #pragma unroll
     for (int m = 0; m < VOIGT_TAB_N; ++m) a = fma(tmp[k * VOIGT_TAB_N + m], cos_tab[j * VOIGT_TAB_N + m], a);
-    tab[it] = a * (2.0 / VOIGT_TAB_N) * XRSD_SQRT_PI;      // the table holds sqrt(pi) Re w, like rew_far_raw (see rew_raw)
+    tab[k * CHEB_ROW + 1 + j] = a * (2.0 / VOIGT_TAB_N) * XRSD_SQRT_PI;      // the table holds sqrt(pi) Re w, like rew_far_raw (see rew_raw)
   }
   __syncthreads();
 }
@@ -154,27 +159,31 @@ __device__ __forceinline__ void voigt_table(double *tab, double *tmp, const doub
 // in t:  T_2j(t) = T_j(u)  and  T_2j+1(t) = t W_j(u)  with W_j+1 = 2u W_j - W_j-1, W_0 = 1, W_1 = 2u - 1  (for which
 // the Clenshaw sum is b_0 - b_1).  Same operation count, half the dependency depth: these sums sit in loops that are
 // bound by the latency of the FP64 pipe, not its throughput (ncu: `wait` is the top stall reason).
-__device__ __forceinline__ double cheb17(const double *__restrict__ a, double t) {
+__device__ __forceinline__ double cheb17(const double *__restrict__ c, double t) {
   static_assert(VOIGT_TAB_N == 17, "degree 16");
+  // c: a coefficient row in the CHEB_ROW layout (c[k + 1] = a_k), 16-byte aligned
+  const double2 *c2 = reinterpret_cast<const double2 *>(c);
   const double u2 = fma(4.0 * t, t, -2.0);               // 2u
-  double e1 = a[16], e2 = 0.0;                           // even chain: coefficients a_16, a_14, ..., a_2
-  double o1 = a[15], o2 = 0.0;                           // odd chain:  coefficients a_15, a_13, ..., a_1
+  const double2 top = c2[8];                             // (a_15, a_16)
+  double e1 = top.y, e2 = 0.0;                           // even chain: coefficients a_16, a_14, ..., a_2
+  double o1 = top.x, o2 = 0.0;                           // odd chain:  coefficients a_15, a_13, ..., a_1
 #pragma unroll
   for (int j = 7; j >= 1; --j) {
-    const double e0 = fma(u2, e1, a[2 * j] - e2);
-    const double o0 = fma(u2, o1, a[2 * j - 1] - o2);
+    const double2 p = c2[j];                             // (a_2j-1, a_2j)
+    const double e0 = fma(u2, e1, p.y - e2);
+    const double o0 = fma(u2, o1, p.x - o2);
     e2 = e1; e1 = e0;
     o2 = o1; o1 = o0;
   }
   // even: a_0/2 + u e_1 - e_2;   odd: t (b_0 - b_1) with b_0 = o1 (after the last step), b_1 = o2
-  return fma(0.5 * u2, e1, 0.5 * a[0] - e2) + t * (o1 - o2);
+  return fma(0.5 * u2, e1, 0.5 * c[1] - e2) + t * (o1 - o2);
 }
 
 __device__ __forceinline__ double rew_table(double x, const double *tab) {
   const double x2 = x + x;                               // 0 <= x < 8: interval k = floor(2x), t = 2(2x - k) - 1
   const int k = (int)x2;
   const double t = 2.0 * (x2 - (double)k) - 1.0;
-  return cheb17(tab + k * VOIGT_TAB_N, t);
+  return cheb17(tab + k * CHEB_ROW, t);
 }
 
 // Re w(x + i y) with y = vc->y > 0.  (y == 0 is the Gaussian exp(-x^2): rew_any below; the crystalline sums route that

@@ -50,10 +50,10 @@ constexpr int CHEB_ROUND = XRSD_CHEB_ROUND;                   // runs of EVAL_TH
 struct ChebShared {                               // only in kernels that can meet a crystalline population
   double cheb_cos[CHEB_N * CHEB_N];              // cos(pi k (m + 1/2) / N)
   double cheb_part[2 * CHEB_ROUND * CHEB_N];     // node sums, two shell-parity halves per node
-  double cheb_coef[CHEB_ROUND * CHEB_N];
+  alignas(16) double cheb_coef[CHEB_ROUND * CHEB_ROW];   // rows in the CHEB_ROW layout of cheb17 (faddeeva.cuh)
   int near_lo[CHEB_ROUND], near_hi[CHEB_ROUND];
   double run_c[CHEB_ROUND], run_invH[CHEB_ROUND];   // centre and 1/half-width of each run of the round
-  double voigt_tab[VOIGT_TAB_DOUBLES];           // near-branch Faddeeva table of the current population (faddeeva.cuh)
+  alignas(16) double voigt_tab[VOIGT_TAB_STORE];   // near-branch Faddeeva table of the current population (faddeeva.cuh)
 };
 static_assert(VOIGT_TAB_N == CHEB_N, "the Voigt table shares the far-field cosine table");
 static_assert(VOIGT_TAB_DOUBLES <= 2 * CHEB_ROUND * CHEB_N, "cheb_part doubles as the table's node buffer");
@@ -590,7 +590,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               double ak = 0.0;
 #pragma unroll
               for (int m = 0; m < CHEB_N; ++m) ak = fma(pa[m] + pa[CHEB_N + m], S->cheb_cos[k * CHEB_N + m], ak);
-              S->cheb_coef[item] = ak * (2.0 / CHEB_N);
+              S->cheb_coef[run * CHEB_ROW + 1 + k] = ak * (2.0 / CHEB_N);
             }
             __syncthreads();
             // (3) one q-point per thread and run
@@ -601,7 +601,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               const double qi = q[q_begin + i];
               // a_0/2 + sum_k a_k T_k(t), t in [-1, 1] (two interleaved Clenshaw chains: faddeeva.cuh)
               const double t = (qi - S->run_c[run]) * S->run_invH[run];
-              double a_sum = cheb17(S->cheb_coef + run * CHEB_N, t);
+              double a_sum = cheb17(S->cheb_coef + run * CHEB_ROW, t);
               const int s_lo = S->near_lo[run], s_hi = S->near_hi[run];
               for (int sl = s_lo; sl < s_hi; ++sl) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
