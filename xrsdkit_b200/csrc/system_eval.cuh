@@ -119,6 +119,17 @@ __device__ __forceinline__ double profile_eval(const Profile &P, const VoigtCons
   }
   return P.b / fma(x, x, P.a);
 }
+// the same for an argument known to lie in the far branch (|z|^2 >= 64): the shells a far-field node sum runs over are
+// at least 12 core widths from every node, so the branch test of rew_raw is not needed there
+template <bool VOIGT>
+__device__ __forceinline__ double profile_far(const Profile &P, const VoigtConst *vc, double x) {
+  if constexpr (VOIGT) {
+    const double a = fabs(x * P.a), y = vc->y;
+    return rew_far_raw(a, y, fma(a, a, y * y));
+  } else {
+    return profile_eval<false>(P, vc, x);
+  }
+}
 __device__ __forceinline__ double profile_eval(const Profile &P, const VoigtConst *vc, double x, const double *vtab = nullptr) {
   return P.kind == XRSD_PROFILE_VOIGT ? rew_any(x * P.a, vc) * P.b : profile_eval<false>(P, vc, x, vtab);
 }
@@ -555,13 +566,13 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               const int i0 = r0 + run * EVAL_THREADS, i1 = min(q_count, i0 + EVAL_THREADS);
               const double qa = q[q_begin + i0], qb = q[q_begin + i1 - 1];
               const double c = 0.5 * (qa + qb), H = 0.5 * (qb - qa);
-              const double dn = fmax(4.0 * H, H + 12.0 * core);
+              const double dn = fmax(4.0 * H, H + 12.0 * core);     // far: >= 12 core widths from every node, |z|^2 >= 144
               const double xm = fma(H, S->cheb_cos[CHEB_N + m], c);       // row k=1: cos(pi (m+1/2)/N)
               double part = 0.0;
               int lo = n_shell, hi = 0;
               for (int sl = g; sl < n_shell; sl += 2) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
-                if (fabs(sw.x - c) >= dn) part = fma(sw.y, profile_eval<VG>(P, &S->vc, xm - sw.x, vtab), part);
+                if (fabs(sw.x - c) >= dn) part = fma(sw.y, profile_far<VG>(P, &S->vc, xm - sw.x), part);
                 else { lo = min(lo, sl); hi = max(hi, sl + 1); }
               }
               S->cheb_part[item] = part;
