@@ -51,8 +51,10 @@ struct ChebShared {                               // only in kernels that can me
   double cheb_cos[CHEB_N * CHEB_N];              // cos(pi k (m + 1/2) / N)
   double cheb_part[2 * CHEB_ROUND * CHEB_N];     // node sums, two shell-parity halves per node
   alignas(16) double cheb_coef[CHEB_ROUND * CHEB_ROW];   // rows in the CHEB_ROW layout of cheb17 (faddeeva.cuh)
-  int near_lo[CHEB_ROUND], near_hi[CHEB_ROUND];
-  double run_c[CHEB_ROUND], run_invH[CHEB_ROUND];   // centre and 1/half-width of each run of the round
+  // per run of a round, double-buffered by round parity (the next round's entries are prepared while this round's
+  // points are evaluated): the contiguous range [near_lo, near_hi) of shells summed directly, centre, half-width, 1/half-width
+  int near_lo[2][CHEB_ROUND], near_hi[2][CHEB_ROUND];
+  double run_c[2][CHEB_ROUND], run_H[2][CHEB_ROUND], run_invH[2][CHEB_ROUND];
   alignas(16) double voigt_tab[VOIGT_TAB_STORE];   // near-branch Faddeeva table of the current population (faddeeva.cuh)
 };
 static_assert(VOIGT_TAB_N == CHEB_N, "the Voigt table shares the far-field cosine table");
@@ -555,45 +557,50 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
           stage_shells(0, n_shell);
           __syncthreads();
           const double core = VG ? fmax(1.0, S->vc.y) / P.a : sqrt(P.a);
-          // rounds of CHEB_ROUND runs: (1) node sums of all runs, (2) coefficients, (3) per-q evaluation;
-          // three barriers per round instead of four per run
-          for (int r0 = 0; r0 < q_count; r0 += CHEB_ROUND * EVAL_THREADS) {
-            const int n_run = min(CHEB_ROUND, (q_count - r0 + EVAL_THREADS - 1) / EVAL_THREADS);
-            // (1) item = (run, node m, shell parity g)
-            for (int item = tid; item < n_run * CHEB_N * 2; item += EVAL_THREADS) {
-              const int run = item / (2 * CHEB_N), rem = item - run * 2 * CHEB_N;
-              const int g = rem / CHEB_N, m = rem - g * CHEB_N;
+          // rounds of CHEB_ROUND runs: (0) near range of every run, (1) node sums of all runs, (2) coefficients,
+          // (3) per-q evaluation; three barriers per round instead of four per run
+          auto prepare_round = [&](int r0, int buf) {       // (0): one thread per run; the table is sorted by |G|, so the
+            const int n_run = min(CHEB_ROUND, (q_count - r0 + EVAL_THREADS - 1) / EVAL_THREADS);      // near shells are one range
+            if (tid < n_run) {
+              const int run = tid;
               const int i0 = r0 + run * EVAL_THREADS, i1 = min(q_count, i0 + EVAL_THREADS);
               const double qa = q[q_begin + i0], qb = q[q_begin + i1 - 1];
               const double c = 0.5 * (qa + qb), H = 0.5 * (qb - qa);
               const double dn = fmax(4.0 * H, H + 12.0 * core);     // far: >= 12 core widths from every node, |z|^2 >= 144
-              const double xm = fma(H, S->cheb_cos[CHEB_N + m], c);       // row k=1: cos(pi (m+1/2)/N)
-              double part = 0.0;
               int lo = n_shell, hi = 0;
-              for (int sl = g; sl < n_shell; sl += 2) {
+              for (int sl = 0; sl < n_shell; ++sl)
+                if (fabs(scratch[2 * sl] - c) < dn) { lo = min(lo, sl); hi = max(hi, sl + 1); }
+              if (hi == 0) lo = hi = n_shell;               // no near shell: everything is far
+              S->near_lo[buf][run] = lo;
+              S->near_hi[buf][run] = hi;
+              S->run_c[buf][run] = c;
+              S->run_H[buf][run] = H;
+              S->run_invH[buf][run] = (H > 0.0) ? 1.0 / H : 0.0;
+            }
+          };
+          prepare_round(0, 0);
+          __syncthreads();
+          int buf = 0;
+          for (int r0 = 0; r0 < q_count; r0 += CHEB_ROUND * EVAL_THREADS, buf ^= 1) {
+            const int n_run = min(CHEB_ROUND, (q_count - r0 + EVAL_THREADS - 1) / EVAL_THREADS);
+            // (1) item = (run, node m, shell parity g): the far shells below and above the near range, no test per shell
+            for (int item = tid; item < n_run * CHEB_N * 2; item += EVAL_THREADS) {
+              const int run = item / (2 * CHEB_N), rem = item - run * 2 * CHEB_N;
+              const int g = rem / CHEB_N, m = rem - g * CHEB_N;
+              const double xm = fma(S->run_H[buf][run], S->cheb_cos[CHEB_N + m], S->run_c[buf][run]);   // row k=1: cos(pi (m+1/2)/N)
+              const int lo = S->near_lo[buf][run], hi = S->near_hi[buf][run];
+              double part = 0.0;
+              for (int sl = g; sl < lo; sl += 2) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
-                if (fabs(sw.x - c) >= dn) part = fma(sw.y, profile_far<VG>(P, &S->vc, xm - sw.x), part);
-                else { lo = min(lo, sl); hi = max(hi, sl + 1); }
+                part = fma(sw.y, profile_far<VG>(P, &S->vc, xm - sw.x), part);
+              }
+              for (int sl = hi + ((hi ^ g) & 1); sl < n_shell; sl += 2) {
+                const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
+                part = fma(sw.y, profile_far<VG>(P, &S->vc, xm - sw.x), part);
               }
               S->cheb_part[item] = part;
-              // near shells form one contiguous range (the table is sorted by |G|); even-parity half here
-              if (m == 0 && g == 0) { S->near_lo[run] = lo; S->near_hi[run] = hi; }
             }
             __syncthreads();
-            if (tid < n_run) {           // merge the odd-parity half of the near range
-              const int run = tid;
-              int lo = S->near_lo[run], hi = S->near_hi[run];
-              const int i0 = r0 + run * EVAL_THREADS, i1 = min(q_count, i0 + EVAL_THREADS);
-              const double qa = q[q_begin + i0], qb = q[q_begin + i1 - 1];
-              const double c = 0.5 * (qa + qb), H = 0.5 * (qb - qa);
-              const double dn = fmax(4.0 * H, H + 12.0 * core);
-              for (int sl = 1; sl < n_shell; sl += 2)
-                if (fabs(scratch[2 * sl] - c) < dn) { lo = min(lo, sl); hi = max(hi, sl + 1); }
-              S->near_lo[run] = lo;
-              S->near_hi[run] = hi;
-              S->run_c[run] = c;
-              S->run_invH[run] = (H > 0.0) ? 1.0 / H : 0.0;
-            }
             // (2) coefficient (run, k): a_k = 2/N sum_m B_m cos(pi k (m+1/2)/N)
             for (int item = tid; item < n_run * CHEB_N; item += EVAL_THREADS) {
               const int run = item / CHEB_N, k = item - run * CHEB_N;
@@ -603,6 +610,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               for (int m = 0; m < CHEB_N; ++m) ak = fma(pa[m] + pa[CHEB_N + m], S->cheb_cos[k * CHEB_N + m], ak);
               S->cheb_coef[run * CHEB_ROW + 1 + k] = ak * (2.0 / CHEB_N);
             }
+            if (r0 + CHEB_ROUND * EVAL_THREADS < q_count) prepare_round(r0 + CHEB_ROUND * EVAL_THREADS, buf ^ 1);
             __syncthreads();
             // (3) one q-point per thread and run
             for (int run = 0; run < n_run; ++run) {
@@ -611,9 +619,9 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               if (i >= i1) continue;
               const double qi = q[q_begin + i];
               // a_0/2 + sum_k a_k T_k(t), t in [-1, 1] (two interleaved Clenshaw chains: faddeeva.cuh)
-              const double t = (qi - S->run_c[run]) * S->run_invH[run];
+              const double t = (qi - S->run_c[buf][run]) * S->run_invH[buf][run];
               double a_sum = cheb17(S->cheb_coef + run * CHEB_ROW, t);
-              const int s_lo = S->near_lo[run], s_hi = S->near_hi[run];
+              const int s_lo = S->near_lo[buf][run], s_hi = S->near_hi[buf][run];
               for (int sl = s_lo; sl < s_hi; ++sl) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
                 a_sum = fma(sw.y, profile_eval<VG>(P, &S->vc, qi - sw.x, vtab), a_sum);
