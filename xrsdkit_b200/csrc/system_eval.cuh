@@ -42,10 +42,10 @@ constexpr int CHEB_N = 17;                       // Chebyshev nodes of the far-f
 #define XRSD_HX_MIN_CTAS 8                        // resident CTAs per SM the crystalline kernels are compiled for (64 registers; 7 x 72 and 6 x 80 measured 4 % and 9 % slower)
 #endif
 #ifndef XRSD_CHEB_ROUND
-#define XRSD_CHEB_ROUND 16
+#define XRSD_CHEB_ROUND 32
 #endif
 constexpr int CHEB_ROUND = XRSD_CHEB_ROUND;                   // runs of EVAL_THREADS q-points handled between two barriers
-                                                 // (measured: 8 -> 16 +3.5 %, 32 the same, 64 loses occupancy)
+                                                 // (measured: 8 -> 16 +3.5 %, 16 -> 32 +1.7 % since the loops got leaner, 64 loses occupancy: -6 %)
 
 struct ChebShared {                               // only in kernels that can meet a crystalline population
   double cheb_cos[CHEB_N * CHEB_N];              // cos(pi k (m + 1/2) / N)
