@@ -32,6 +32,10 @@ namespace xrsd {
 
 constexpr int EVAL_THREADS = 128;
 constexpr int SHELL_CHUNK = 128;
+#ifndef XRSD_RNORMAL_UNROLL
+#define XRSD_RNORMAL_UNROLL 8     // radii per trip of the size-distribution loop (cfg2, same box: 1 -> 1.69 ms, 2 -> 1.53, 4 -> 1.49, 8 -> 1.48)
+#endif
+constexpr int RNORMAL_UNROLL = XRSD_RNORMAL_UNROLL;
 #ifndef XRSD_F32_MIN_X
 #define XRSD_F32_MIN_X 2.0      // single-precision path: smallest q r that continues in FP32
 #endif
@@ -382,7 +386,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               for (int j = 0; j < QPT; ++j) acc[j] += (double)accf[j];
             }
             // phase B: pure recurrence, 8 DP instructions per (q, r)
-#pragma unroll 2
+#pragma unroll RNORMAL_UNROLL
             for (; i < n_r; ++i) {
               const double2 rr = *reinterpret_cast<const double2 *>(scratch + 2 * i);
 #pragma unroll
