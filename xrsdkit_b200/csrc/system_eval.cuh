@@ -33,7 +33,7 @@ namespace xrsd {
 constexpr int EVAL_THREADS = 128;
 constexpr int SHELL_CHUNK = 128;
 #ifndef XRSD_RNORMAL_UNROLL
-#define XRSD_RNORMAL_UNROLL 8     // radii per trip of the size-distribution loop (cfg2, same box: 1 -> 1.69 ms, 2 -> 1.53, 4 -> 1.49, 8 -> 1.48)
+#define XRSD_RNORMAL_UNROLL 16    // radii per trip of the size-distribution loop (cfg2, same box: 1 -> 1.69 ms, 2 -> 1.53, 4 -> 1.49, 8 -> 1.48, 16 -> 1.46, 25 -> 1.47, 32 -> 1.50)
 #endif
 constexpr int RNORMAL_UNROLL = XRSD_RNORMAL_UNROLL;
 #ifndef XRSD_F32_MIN_X
