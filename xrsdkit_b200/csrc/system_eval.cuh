@@ -368,7 +368,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
                 accf[j] = 0.0f;
               }
               const float2 *rec32 = reinterpret_cast<const float2 *>(scratch + 2 * n_r);
-#pragma unroll 2
+#pragma unroll RNORMAL_UNROLL
               for (; i < n_r; ++i) {       // phase B32
                 const float2 rw = rec32[i];
                 const float rf = rw.x, wf = rw.y;
