@@ -106,6 +106,24 @@ def test_argument_errors_without_touching_the_gpu():
     assert lib.xrsd_lm_accept(1 << 20, 0, None, 0, None, 0, 16, 2, 2, None, None, 0, None) == abi.OK
     rc = lib.xrsd_lm_propose(1 << 20, 6, 2, free, 2, None, None, 0, 1 << 21, 1 << 22, 1 << 23, 1 << 24, 1 << 25, None, 1 << 26, -1.0, None, None)
     assert rc == abi.EINVAL and b"max_rel_step" in lib.xrsd_last_error()
+    # the whole-iteration entry point checks its state before it launches anything
+    assert lib.xrsd_sizeof_lm_state() == ctypes.sizeof(abi.LmState)
+    assert lib.xrsd_lm_iteration(None, 0, None) == abi.EINVAL
+    st = abi.LmState()
+    L1, O1 = abi.Layout(), abi.Objective()
+    st.layout, st.obj = ctypes.pointer(L1), ctypes.pointer(O1)
+    assert lib.xrsd_lm_iteration(ctypes.byref(st), 0, None) == abi.EINVAL and b"prepared" in lib.xrsd_last_error()
+    O1.prepared = 1
+    assert lib.xrsd_lm_iteration(ctypes.byref(st), 0, None) == abi.EINVAL and b"workspace" in lib.xrsd_last_error()
+    # constraint terms: a program word must be known and the expression stack must balance
+    tw = abi.TIE_WORD
+    for words, msg in (([-(tw + 99), 0], b"unknown expression word"), ([-(tw + 2), 0], b"underrun"),
+                       ([-(tw + 1), 0, -(tw + 1), 1], b"closing store"), ([0, -1], b"exactly one value")):
+        arr = (ctypes.c_int32 * len(words))(*words)
+        coef = (ctypes.c_double * len(words))(*([0.0] * len(words)))
+        rc = lib.xrsd_lm_propose(1 << 20, 6, 2, free, 2, arr, coef, len(words) // 2, 1 << 21, 1 << 22, 1 << 23, 1 << 24, 1 << 25, None,
+                                 1 << 26, 0.25, None, None)
+        assert rc == abi.EINVAL and msg in lib.xrsd_last_error(), (words, lib.xrsd_last_error())
 
 
 def test_uniform_step_host_helper_matches_its_numpy_statement():
