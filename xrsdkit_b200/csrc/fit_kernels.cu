@@ -645,8 +645,8 @@ jacobian_reduce_mma_kernel(int n_pops, const xrsd_objective_t O, const double *_
   for (int i = tid; i < JM_STAGES * JR_THREADS; i += JR_THREADS)
     ring[((size_t)(i / JR_THREADS) * (n_rows + 1) + z_row) * JR_THREADS + (i % JR_THREADS)] = 0.0;
   if (tid < NF)
-    dsc[tid] = make_int4((F.ra[tid] < 0 ? z_row : F.ra[tid]) * JR_THREADS, (F.rb[tid] < 0 ? z_row : F.rb[tid]) * JR_THREADS,
-                         (F.rc[tid] < 0 ? z_row : F.rc[tid]) * JR_THREADS, 0);
+    dsc[tid] = make_int4((F.ra[tid] < 0 ? z_row : F.ra[tid]) * JR_THREADS * 8, (F.rb[tid] < 0 ? z_row : F.rb[tid]) * JR_THREADS * 8,
+                         (F.rc[tid] < 0 ? z_row : F.rc[tid]) * JR_THREADS * 8, 0);      // BYTE offsets into the thread's stage
   __syncthreads();
   double scale[NF];                  // h / I0 for a linear parameter (0 at I0 == 0), 1 for a variant slab, 0 beyond n_free
 #pragma unroll
@@ -695,13 +695,18 @@ jacobian_reduce_mma_kernel(int n_pops, const xrsd_objective_t O, const double *_
       const double f0 = O.logI_weighted ? log(I0v) : I0v;
       res = f0 - fit_target(O, Io);
       const double inv = O.logI_weighted ? 1.0 / I0v : 1.0;
+      const char *Fb8 = reinterpret_cast<const char *>(Fs);
+      auto at = [&](int byte_off) { return *reinterpret_cast<const double *>(Fb8 + byte_off); };
 #pragma unroll
       for (int j = 0; j < NF; ++j) {
         const int4 o = dsc[j];
-        double d = scale[j] * ((Fs[o.x] - Fs[o.y]) + Fs[o.z]) * inv;
+        double d = scale[j] * ((at(o.x) - at(o.y)) + at(o.z)) * inv;
         if (O.logI_weighted) {
-          if (fabs(d) < 1.0e-2) d = d * fma(d, fma(d, 1.0 / 3.0, -0.5), 1.0);      // |error| < x^4 / 4
-          else d = (d > -1.0) ? log1p(d) : 0.0;          // a variant intensity <= 0 carries no information
+          // log1p of the relative change: three terms of its series for the small changes a finite-difference step
+          // makes (|error| < x^4 / 4), the library function otherwise -- selected without a branch around the series
+          const double ser = d * fma(d, fma(d, 1.0 / 3.0, -0.5), 1.0);
+          if (!(fabs(d) < 1.0e-2)) d = (d > -1.0) ? log1p(d) : 0.0;      // rare; a variant intensity <= 0 carries no information
+          else d = ser;
         }
         tile[j * JM_PITCH + st_col] = (d == d) ? d : 0.0;
       }
