@@ -122,11 +122,12 @@ static __device__ __noinline__ double rew_near(double x, const VoigtConst *vc) {
 }
 
 // Per-pattern table of the near branch: y is fixed, so Re w(x + i y), 0 <= x < 8, is ONE smooth function of
-// x for the whole pattern.  It is tabulated as a degree-16 Chebyshev expansion on each of 16 intervals of
-// width 1/2 (17 x 16 evaluations of rew_near per pattern instead of one per (q, shell) pair near a peak
+// x for the whole pattern.  It is tabulated as a degree-13 Chebyshev expansion on each of 16 intervals of
+// width 1/2 (14 x 16 evaluations of rew_near per pattern instead of one per (q, shell) pair near a peak
 // core); max relative deviation from scipy's wofz 6e-14 for y in [1e-4, 8) (narrow intervals keep the
 // dynamic range of e^{-x^2} inside one interval small, so the error stays relative).
-constexpr int VOIGT_TAB_N = 17;          // nodes per interval (= CHEB_N of system_eval.cuh: shares its cosine table)
+constexpr int VOIGT_TAB_N = 14;          // nodes per interval (degree 13: as accurate as degree 16 here -- 4e-14 for y >= 1e-4 --
+                                         // and 14 x 16 = 224 node evaluations are two passes of 128 threads, 17 x 16 were three)
 constexpr int VOIGT_TAB_INTERVALS = 16;
 constexpr double VOIGT_TAB_MIN_Y = 1.0e-4;     // below: e^{-x^2} dominates out to x ~ 4.5 and the table loses relative accuracy
 constexpr int VOIGT_TAB_DOUBLES = VOIGT_TAB_N * VOIGT_TAB_INTERVALS;      // nodes of one table build
@@ -134,7 +135,7 @@ constexpr int VOIGT_TAB_DOUBLES = VOIGT_TAB_N * VOIGT_TAB_INTERVALS;      // nod
 // two Clenshaw chains consume together are then 16-byte aligned and come with ONE LDS.128 each -- 9 loads per
 // evaluation instead of 17 (the coefficient loads were 5 % of a crystalline pattern's instructions).
 constexpr int CHEB_ROW = 18;
-constexpr int VOIGT_TAB_STORE = CHEB_ROW * VOIGT_TAB_INTERVALS;
+constexpr int VOIGT_TAB_STORE = VOIGT_TAB_N * VOIGT_TAB_INTERVALS;        // table rows: c[k] = a_k, 14 doubles (16-byte multiples)
 
 // Cooperative build (all `nthreads` threads): cos_tab[k*N + m] = cos(pi k (m + 1/2)/N); tmp holds
 // VOIGT_TAB_DOUBLES doubles; tab receives the coefficients (a_0 .. a_16 per interval, a_0 not yet halved).
@@ -150,7 +151,7 @@ __device__ __forceinline__ void voigt_table(double *tab, double *tmp, const doub
     double a = 0.0;
 #pragma unroll
     for (int m = 0; m < VOIGT_TAB_N; ++m) a = fma(tmp[k * VOIGT_TAB_N + m], cos_tab[j * VOIGT_TAB_N + m], a);
-    tab[k * CHEB_ROW + 1 + j] = a * (2.0 / VOIGT_TAB_N) * XRSD_SQRT_PI;      // the table holds sqrt(pi) Re w, like rew_far_raw (see rew_raw)
+    tab[k * VOIGT_TAB_N + j] = a * (2.0 / VOIGT_TAB_N) * XRSD_SQRT_PI;      // the table holds sqrt(pi) Re w, like rew_far_raw (see rew_raw)
   }
   __syncthreads();
 }
@@ -160,7 +161,6 @@ __device__ __forceinline__ void voigt_table(double *tab, double *tmp, const doub
 // the Clenshaw sum is b_0 - b_1).  Same operation count, half the dependency depth: these sums sit in loops that are
 // bound by the latency of the FP64 pipe, not its throughput (ncu: `wait` is the top stall reason).
 __device__ __forceinline__ double cheb17(const double *__restrict__ c, double t) {
-  static_assert(VOIGT_TAB_N == 17, "degree 16");
   // c: a coefficient row in the CHEB_ROW layout (c[k + 1] = a_k), 16-byte aligned
   const double2 *c2 = reinterpret_cast<const double2 *>(c);
   const double u2 = fma(4.0 * t, t, -2.0);               // 2u
@@ -179,11 +179,33 @@ __device__ __forceinline__ double cheb17(const double *__restrict__ c, double t)
   return fma(0.5 * u2, e1, 0.5 * c[1] - e2) + t * (o1 - o2);
 }
 
+// a_0/2 + sum_{k=1..13} a_k T_k(t) for a row c[k] = a_k of 14 coefficients (16-byte aligned): the same two chains,
+// (a_2j, a_2j+1) per LDS.128 -- the rows of the near-branch Voigt table
+__device__ __forceinline__ double cheb14(const double *__restrict__ c, double t) {
+  static_assert(VOIGT_TAB_N == 14, "degree 13");
+  const double2 *c2 = reinterpret_cast<const double2 *>(c);
+  const double u2 = fma(4.0 * t, t, -2.0);               // 2u
+  double2 p = c2[6];
+  double e1 = p.x, e2 = 0.0;                             // even chain: a_12, a_10, ..., a_2, then a_0 / 2
+  double o1 = p.y, o2 = 0.0;                             // odd chain:  a_13, a_11, ..., a_1
+#pragma unroll
+  for (int j = 5; j >= 1; --j) {
+    p = c2[j];
+    const double e0 = fma(u2, e1, p.x - e2);
+    const double o0 = fma(u2, o1, p.y - o2);
+    e2 = e1; e1 = e0;
+    o2 = o1; o1 = o0;
+  }
+  p = c2[0];
+  const double d0 = fma(u2, o1, p.y - o2);               // the odd chain has one more coefficient
+  return fma(0.5 * u2, e1, 0.5 * p.x - e2) + t * (d0 - o1);
+}
+
 __device__ __forceinline__ double rew_table(double x, const double *tab) {
   const double x2 = x + x;                               // 0 <= x < 8: interval k = floor(2x), t = 2(2x - k) - 1
   const int k = (int)x2;
   const double t = 2.0 * (x2 - (double)k) - 1.0;
-  return cheb17(tab + k * CHEB_ROW, t);
+  return cheb14(tab + k * VOIGT_TAB_N, t);
 }
 
 // Re w(x + i y) with y = vc->y > 0.  (y == 0 is the Gaussian exp(-x^2): rew_any below; the crystalline sums route that

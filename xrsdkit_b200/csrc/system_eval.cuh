@@ -53,6 +53,7 @@ constexpr int CHEB_ROUND = XRSD_CHEB_ROUND;                   // runs of EVAL_TH
 
 struct ChebShared {                               // only in kernels that can meet a crystalline population
   double cheb_cos[CHEB_N * CHEB_N];              // cos(pi k (m + 1/2) / N)
+  double vt_cos[VOIGT_TAB_N * VOIGT_TAB_N];      // the same for the nodes of the Voigt near-branch table
   double cheb_part[2 * CHEB_ROUND * CHEB_N];     // node sums, two shell-parity halves per node
   alignas(16) double cheb_coef[CHEB_ROUND * CHEB_ROW];   // rows in the CHEB_ROW layout of cheb17 (faddeeva.cuh)
   // per run of a round, double-buffered by round parity (the next round's entries are prepared while this round's
@@ -61,7 +62,6 @@ struct ChebShared {                               // only in kernels that can me
   double run_c[2][CHEB_ROUND], run_H[2][CHEB_ROUND], run_invH[2][CHEB_ROUND];
   alignas(16) double voigt_tab[VOIGT_TAB_STORE];   // near-branch Faddeeva table of the current population (faddeeva.cuh)
 };
-static_assert(VOIGT_TAB_N == CHEB_N, "the Voigt table shares the far-field cosine table");
 static_assert(VOIGT_TAB_DOUBLES <= 2 * CHEB_ROUND * CHEB_N, "cheb_part doubles as the table's node buffer");
 struct NoCheb {};
 
@@ -187,6 +187,8 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
     }
     for (int i = tid; i < CHEB_N * CHEB_N; i += EVAL_THREADS)
       S->cheb_cos[i] = cospi((double)(i / CHEB_N) * ((double)(i % CHEB_N) + 0.5) / (double)CHEB_N);
+    for (int i = tid; i < VOIGT_TAB_N * VOIGT_TAB_N; i += EVAL_THREADS)
+      S->vt_cos[i] = cospi((double)(i / VOIGT_TAB_N) * ((double)(i % VOIGT_TAB_N) + 0.5) / (double)VOIGT_TAB_N);
   }
 
   for (int ip = 0; ip < L.n_pops; ++ip) {
@@ -487,7 +489,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         const double norm = block_sum(part, S);
         const double *vtab = nullptr;
         if (voigt_near_possible && __syncthreads_or(core_here)) {
-          voigt_table(S->voigt_tab, S->cheb_part, S->cheb_cos, &S->vc, tid, EVAL_THREADS);
+          voigt_table(S->voigt_tab, S->cheb_part, S->vt_cos, &S->vc, tid, EVAL_THREADS);
           vtab = S->voigt_tab;
         }
         // pass B: chunks of shells staged as (q_s, W_s[...]) in scratch
