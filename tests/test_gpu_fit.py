@@ -262,9 +262,11 @@ def test_fit_with_equality_constraint(eng):
     start5.populations["superlattice"].parameters["r"]["constraint_expr"] = "0.9*particle__r*superlattice__a/superlattice__a + 1"
     out5 = fit(start5, q, I2)
     out2 = fit(start2, q, I2)
-    for pop, par in (("particle", "r"), ("superlattice", "a"), ("superlattice", "r"), ("superlattice", "I0")):
-        # (two converged fits of the same objective: they agree to the optimiser's tolerance, not to rounding)
-        assert out5.populations[pop].parameters[par]["value"] == pytest.approx(out2.populations[pop].parameters[par]["value"], rel=1e-4)
+    # (two converged fits of the same objective: they agree to the optimiser's tolerance, not to rounding -- the
+    # objective to 1e-3, the well-determined parameters to 1e-3, the weakly determined intensity scale to 1e-2)
+    assert out5.fit_report["final_objective"] == pytest.approx(out2.fit_report["final_objective"], rel=1e-3)
+    for pop, par, tol in (("particle", "r", 1e-3), ("superlattice", "a", 1e-3), ("superlattice", "r", 1e-3), ("superlattice", "I0", 1e-2)):
+        assert out5.populations[pop].parameters[par]["value"] == pytest.approx(out2.populations[pop].parameters[par]["value"], rel=tol)
     # what is not arithmetic is rejected, not silently ignored
     for expr in ("particle__r if particle__r > 1 else 2", "nonsense__r", "particle__r.real", "particle__r +"):
         start.populations["superlattice"].parameters["r"]["constraint_expr"] = expr
