@@ -274,6 +274,36 @@ def test_fit_with_equality_constraint(eng):
             fit(start, q, I)
 
 
+def test_lattice_scan_before_the_fit(eng):
+    """fitting.scan_start: crystal systems whose lattice edge starts 8-10 % off sit in another basin of the objective
+    (peaks displaced by many widths) and the LM loop fails on most of them; a coarse scan of `a` over the start
+    +-12 % puts them back, and the same loop then recovers the truth."""
+    from xrsdkit_b200.system import System
+    from xrsdkit_b200 import batch
+    s = cfg4_system(System)
+    q = np.linspace(0.01, 1.0, 2048)
+    lay = batch.layout_of(s, q)
+    B = 48
+    P = cfg4_params(lay, B, seed=77)
+    rs = np.random.RandomState(3)
+    Iobs = batch.compute_intensity_batch(lay, q, P) * (1 + 0.02 * rs.randn(B, len(q)))
+    start = P.copy()
+    ia = lay.slot("x__a")
+    start[:, ia] *= 1 + rs.choice([-1.0, 1.0], B) * rs.uniform(0.085, 0.1, B)
+    free = [lay.slot(k) for k in ("noise__I0", "x__I0", "x__a", "x__hwhm_g", "x__hwhm_l", "x__r", "gp__I0", "gp__rg")]
+    chi2_truth = batch.evaluate_residual_batch(lay, q, Iobs, P)
+    plain = batch.fit_batch(lay, q, Iobs, start, free_slots=free, max_iter=30)
+    ok_plain = np.mean(plain.chi2 <= 1.01 * chi2_truth)
+    scanned = batch.scan_start(lay, q, Iobs, start, "x__a", rel_window=0.12, n_points=25)
+    assert np.all(np.abs(scanned[:, ia].cpu().numpy() / P[:, ia] - 1) < 0.012)          # within one grid step of the truth
+    other = [k for k in range(lay.n_params) if k != ia]
+    np.testing.assert_array_equal(scanned.cpu().numpy()[:, other], start[:, other])      # nothing else moved
+    after = batch.fit_batch(lay, q, Iobs, scanned, free_slots=free, max_iter=30)
+    ok_after = np.mean(after.chi2 <= 1.01 * chi2_truth)
+    assert ok_after >= 0.95 and ok_after > ok_plain, (ok_plain, ok_after)
+    np.testing.assert_allclose(after.params[after.chi2 <= 1.01 * chi2_truth][:, ia], P[after.chi2 <= 1.01 * chi2_truth][:, ia], rtol=2e-3)
+
+
 def test_nelder_mead_like_for_like(eng):
     """The reference's optimiser (Nelder-Mead on the scalar objective, lmfit's bound transform), batched:
     reaches the same optimum as the LM fitter on noisy sphere data, and agrees with scipy's Nelder-Mead run

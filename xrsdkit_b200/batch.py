@@ -88,6 +88,12 @@ def fit_batch(layout, q, Iobs, params0, method='lm', **kw):
     return fitting.lm_fit_batch(layout, q, Iobs, params0, **kw)
 
 
+def scan_start(layout, q, Iobs, params0, name, rel_window=0.1, n_points=21, **kw):
+    """Coarse scan of one parameter (by name, e.g. 'x__a': the lattice edge) before a fit; returns the improved start
+    parameters (device tensor) for fit_batch.  See fitting.scan_start."""
+    return fitting.scan_start(layout, q, Iobs, params0, layout.slot(name), rel_window=rel_window, n_points=n_points, **kw)
+
+
 def fit_mixed(groups, eng=None, **kw):
     """Fit a batch that mixes system layouts (BASELINE config 5: sphere and crystal systems side by side).
 
