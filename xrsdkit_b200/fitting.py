@@ -232,7 +232,6 @@ def lm_fit_batch(layout, q, Iobs, params0, free_slots=None, dI=None, error_weigh
         tables = eng.build_tables(layout, d_p, batch, max_cells=max_cells, reuse=store.views[0], share=shareable)
         store = tables.store
         t_tables = store.views[1]
-    stream = eng._stream()
     n_iter = 0
     n_var = eng.jacobian_variants(layout, jac_slots, ties)
     persist = resident_bytes(batch) <= resident_limit
