@@ -52,6 +52,7 @@ SURVEY_FLOPS_PER_SETQ_CFG2 = 2630.0      # SURVEY.md 8d convention (sincos per (
 #   crystalline: one far-branch Voigt evaluation = reciprocal (3 FMA) + set-up (2 FMA, 5 mul) + 4 recurrence terms
 #   (mul + 2 FMA each) + argument and accumulation (1 mul, 2 FMA) = 23 FP64 instructions, 41 flop
 VOIGT_FLOPS = 41.0
+FAR_NODES = 15.0         # Chebyshev nodes of the far-field interpolant per run of 128 q-points (csrc/system_eval.cuh, CHEB_N)
 
 WORKLOADS = {
     "cfg2": "cfg2: polydisperse spheres (r_normal, 50-pt quadrature) + hard_spheres S(q), 4096-pt q, 10k parameter sets per GPU",
@@ -427,7 +428,7 @@ class Work(object):
     # ---- algorithmic FP64 work ----
     def xtal_flops_per_q(self, lay, P, q, tables):
         """flop per (pattern, q) of ONE crystalline evaluation as built (far-field interpolation: per q only the shells
-        within dn = max(4H, H + 12 core widths) of its 128-point run are evaluated directly, the rest through 17 Chebyshev
+        within dn = max(4H, H + 12 core widths) of its 128-point run are evaluated directly, the rest through 15 Chebyshev
         nodes per run), and by the SURVEY 8d convention (205 per shell and q)."""
         n_q = len(q)
         ns = float(np.mean([float(t.n_shell.float().mean().item()) for t in tables]))
@@ -437,7 +438,7 @@ class Work(object):
         core = np.maximum(1.0, hl / s2) * s2
         dn = np.maximum(4 * H, H + 12 * core)
         n_near = float(np.mean(np.minimum(ns, ns * 2 * dn / (q[-1] - q[0]))))
-        return VOIGT_FLOPS * n_near + 17.0 * VOIGT_FLOPS * (ns - n_near) / 128.0 + 2.0 * 17.0 + 150.0, 205.0 * ns + 150.0
+        return VOIGT_FLOPS * n_near + FAR_NODES * VOIGT_FLOPS * (ns - n_near) / 128.0 + 2.0 * FAR_NODES + 150.0, 205.0 * ns + 150.0
 
 
 def ncu_kernel_counts(workload, batch=10000):

@@ -160,15 +160,17 @@ __device__ __forceinline__ void voigt_table(double *tab, double *tmp, const doub
 // in t:  T_2j(t) = T_j(u)  and  T_2j+1(t) = t W_j(u)  with W_j+1 = 2u W_j - W_j-1, W_0 = 1, W_1 = 2u - 1  (for which
 // the Clenshaw sum is b_0 - b_1).  Same operation count, half the dependency depth: these sums sit in loops that are
 // bound by the latency of the FP64 pipe, not its throughput (ncu: `wait` is the top stall reason).
-__device__ __forceinline__ double cheb17(const double *__restrict__ c, double t) {
+template <int N>       // N odd: coefficients a_0 .. a_(N-1)
+__device__ __forceinline__ double cheb_row(const double *__restrict__ c, double t) {
+  static_assert(N % 2 == 1 && N + 1 <= CHEB_ROW, "odd number of coefficients in a CHEB_ROW row");
   // c: a coefficient row in the CHEB_ROW layout (c[k + 1] = a_k), 16-byte aligned
   const double2 *c2 = reinterpret_cast<const double2 *>(c);
   const double u2 = fma(4.0 * t, t, -2.0);               // 2u
-  const double2 top = c2[8];                             // (a_15, a_16)
-  double e1 = top.y, e2 = 0.0;                           // even chain: coefficients a_16, a_14, ..., a_2
-  double o1 = top.x, o2 = 0.0;                           // odd chain:  coefficients a_15, a_13, ..., a_1
+  const double2 top = c2[(N - 1) / 2];                   // (a_(N-2), a_(N-1))
+  double e1 = top.y, e2 = 0.0;                           // even chain: coefficients a_(N-1), a_(N-3), ..., a_2
+  double o1 = top.x, o2 = 0.0;                           // odd chain:  coefficients a_(N-2), a_(N-4), ..., a_1
 #pragma unroll
-  for (int j = 7; j >= 1; --j) {
+  for (int j = (N - 3) / 2; j >= 1; --j) {
     const double2 p = c2[j];                             // (a_2j-1, a_2j)
     const double e0 = fma(u2, e1, p.y - e2);
     const double o0 = fma(u2, o1, p.x - o2);
@@ -178,6 +180,7 @@ __device__ __forceinline__ double cheb17(const double *__restrict__ c, double t)
   // even: a_0/2 + u e_1 - e_2;   odd: t (b_0 - b_1) with b_0 = o1 (after the last step), b_1 = o2
   return fma(0.5 * u2, e1, 0.5 * c[1] - e2) + t * (o1 - o2);
 }
+__device__ __forceinline__ double cheb17(const double *__restrict__ c, double t) { return cheb_row<17>(c, t); }
 
 // a_0/2 + sum_{k=1..13} a_k T_k(t) for a row c[k] = a_k of 14 coefficients (16-byte aligned): the same two chains,
 // (a_2j, a_2j+1) per LDS.128 -- the rows of the near-branch Voigt table

@@ -41,7 +41,12 @@ constexpr int RNORMAL_UNROLL = XRSD_RNORMAL_UNROLL;
 #endif
 
 // shared-memory working set of one CTA (besides the pattern buffer)
-constexpr int CHEB_N = 17;                       // Chebyshev nodes of the far-field interpolant (degree 16)
+#ifndef XRSD_CHEB_N
+#define XRSD_CHEB_N 15
+#endif
+constexpr int CHEB_N = XRSD_CHEB_N;              // Chebyshev nodes of the far-field interpolant (degree CHEB_N - 1; odd).
+                                                 // Same box, cfg3 kernel and worst golden parity: 17 nodes 2.10 ms / 8.9e-14,
+                                                 // 15 nodes 1.98 ms / 2.8e-13, 13 nodes 1.89 ms / 1.8e-11 (gate: 1e-10)
 #ifndef XRSD_HX_MIN_CTAS
 #define XRSD_HX_MIN_CTAS 8                        // resident CTAs per SM the crystalline kernels are compiled for (64 registers; 7 x 72 and 6 x 80 measured 4 % and 9 % slower)
 #endif
@@ -552,8 +557,8 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         // ---- far-field interpolation path ------------------------------------------------------
         // For a run of EVAL_THREADS consecutive q-points (centre c, half-width H) every shell with
         // |q_s - c| >= max(4 H, H + 12 core widths) is "far": the sum of all far shells is smooth over
-        // the run (nearest singular structure >= 3 H from its edge: Bernstein parameter rho >= 7.9, rho^-17 < 1e-15), so it is evaluated at CHEB_N Chebyshev
-        // nodes only and interpolated (degree 16: truncation < 1e-13 relative, tests/test_gpu_parity.py),
+        // the run (nearest singular structure >= 3 H from its edge: Bernstein parameter rho >= 7.9, rho^-15 = 3.6e-14), so it is evaluated at CHEB_N Chebyshev
+        // nodes only and interpolated (degree 14: worst golden parity 2.8e-13, tests/test_gpu_parity.py),
         // while the few near shells are summed directly.  This cuts the profile evaluations per q from
         // n_shell to about n_near + CHEB_N n_far / EVAL_THREADS.
         const bool interp = stage_once && !radial_multi && q_sorted && P.kind != XRSD_PROFILE_GAUSSIAN &&
@@ -626,7 +631,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               const double qi = q[q_begin + i];
               // a_0/2 + sum_k a_k T_k(t), t in [-1, 1] (two interleaved Clenshaw chains: faddeeva.cuh)
               const double t = (qi - S->run_c[buf][run]) * S->run_invH[buf][run];
-              double a_sum = cheb17(S->cheb_coef + run * CHEB_ROW, t);
+              double a_sum = cheb_row<CHEB_N>(S->cheb_coef + run * CHEB_ROW, t);
               const int s_lo = S->near_lo[buf][run], s_hi = S->near_hi[buf][run];
               for (int sl = s_lo; sl < s_hi; ++sl) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
