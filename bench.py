@@ -783,6 +783,7 @@ def run_gpu_arm(args):
         secondary["cfg2_fp32"] = bench_fp32(eng, W)
         secondary["features"] = bench_features(eng, W, outs0, args)
         secondary["cfg1"] = bench_cfg1(args)
+        secondary["cfg1_batched"] = bench_cfg1_batched(eng, peaks, peaks_src, fp64_tflops)
 
     line = {
         "metric": head["metric"], "value": head["value"], "unit": head["unit"], "n_gpus": world, "steps": steps,
@@ -914,6 +915,48 @@ def bench_cfg1(args):
             out["cpu_kind"] = be.kind
             out["max_rel_diff_vs_cpu"] = float(np.max(np.abs(I1 - Ir) / np.abs(Ir)))
         return out
+    except Exception as e:
+        return {"error": repr(e)}
+
+
+def bench_cfg1_batched(eng, peaks, peaks_src, fp64_tflops, B=100000):
+    """SURVEY 8d's batched variant of cfg1: B = 10^5 dilute single-size sphere systems, r ~ U(5, 60), 2000 q -- about
+    60 flop (one sincos) per 8-byte I(q) value written, i.e. the one workload of the path near the HBM / FP64 ridge
+    instead of far on the compute side; reported against both ceilings."""
+    import torch
+    try:
+        from xrsdkit_b200.system import System
+        from xrsdkit_b200 import batch as xb
+        s1 = System(p=dict(structure="diffuse", form="spherical", parameters={"r": {"value": 20.0}, "I0": {"value": 1.0}}))
+        q1 = np.linspace(0.001, 0.5, 2000)
+        lay = xb.layout_of(s1, q1)
+        rs = np.random.RandomState(1001)
+        mats = []
+        for _ in range(2):
+            P = np.tile(lay.values, (B, 1))
+            P[:, lay.slot("p__r")] = rs.uniform(5.0, 60.0, B)
+            mats.append(eng.to_device(P))
+        d_q = eng.to_device(q1)
+        outs = [torch.empty((B, len(q1)), dtype=torch.float64, device=eng.device) for _ in range(2)]
+        ms = time_kernel(lambda i: eng.intensity(lay, d_q, mats[i % 2], out=outs[i % 2]), reps=5)
+        nbytes = 8.0 * B * len(q1)
+        # parity of a few rows against the closed form the reference evaluates (form_factors.py:20-28), in numpy
+        rows = [0, B // 2, B - 1]
+        got = eng.intensity(lay, d_q, mats[0][rows].contiguous()).cpu().numpy()
+        r = mats[0][rows, lay.slot("p__r")].cpu().numpy()[:, None]
+        x = q1[None, :] * r
+        ff = 3.0 * (np.sin(x) - x * np.cos(x)) / x ** 3
+        ref = float(lay.values[lay.slot("noise__I0")]) + 1.0 * ff ** 2
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return {"workload": "cfg1 batched: %d dilute sphere systems (r ~ U(5, 60)), 2000-pt q, one launch; every pass writes "
+                            "%.1f GB of patterns (L2 is 126 MB)" % (B, nbytes / 1e9),
+                "unit": "patterns/s", "value": B / (ms * 1e-3), "kernel_ms": ms,
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                             "frac": gbs / peaks.get("hbm_gbs", 6650.0), "peak_source": peaks_src,
+                             "algorithmic_bytes_per_launch": nbytes,
+                             "note": "write-only stream; MEASURED_PEAKS' figure is a copy (read + write)",
+                             "fp64_frac_survey_convention": 60.0 * B * len(q1) / (ms * 1e-3) / 1e12 / fp64_tflops},
+                "max_rel_diff_vs_closed_form": float(np.max(np.abs(got - ref) / np.abs(ref)))}
     except Exception as e:
         return {"error": repr(e)}
 
