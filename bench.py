@@ -52,6 +52,9 @@ SURVEY_FLOPS_PER_SETQ_CFG2 = 2630.0      # SURVEY.md 8d convention (sincos per (
 #   crystalline: one far-branch Voigt evaluation = reciprocal (3 FMA) + set-up (2 FMA, 5 mul) + 4 recurrence terms
 #   (mul + 2 FMA each) + argument and accumulation (1 mul, 2 FMA) = 23 FP64 instructions, 41 flop
 VOIGT_FLOPS = 41.0
+#   near-branch Voigt evaluation through the pattern's table (|z| < 8): interval and argument 4, u = 2t^2 - 1 and two
+#   Horner chains of 6 FMA, t O + E, accumulation: 17 FP64 instructions, 31 flop
+VOIGT_TABLE_FLOPS = 31.0
 FAR_NODES = 15.0         # Chebyshev nodes of the far-field interpolant per run of 128 q-points (csrc/system_eval.cuh, CHEB_N)
 
 WORKLOADS = {
@@ -437,8 +440,12 @@ class Work(object):
         s2 = hg / np.sqrt(2 * np.log(2)) * np.sqrt(2)
         core = np.maximum(1.0, hl / s2) * s2
         dn = np.maximum(4 * H, H + 12 * core)
-        n_near = float(np.mean(np.minimum(ns, ns * 2 * dn / (q[-1] - q[0]))))
-        return VOIGT_FLOPS * n_near + FAR_NODES * VOIGT_FLOPS * (ns - n_near) / 128.0 + 2.0 * FAR_NODES + 150.0, 205.0 * ns + 150.0
+        n_near = np.minimum(ns, ns * 2 * dn / (q[-1] - q[0]))
+        # the part of the near range within |z| < 8 (8 s2 of the peak) takes the table branch, the rest the far branch
+        near_flops = float(np.mean(n_near * (VOIGT_FLOPS + (VOIGT_TABLE_FLOPS - VOIGT_FLOPS) * np.minimum(1.0, 8.0 * s2 / dn))))
+        n_near = float(np.mean(n_near))
+        # per q besides the shells: the interpolant (15 FMA + 2) = 2 FAR_NODES + 2 flop ... and ~150 for the rest
+        return near_flops + FAR_NODES * VOIGT_FLOPS * (ns - n_near) / 128.0 + 2.0 * FAR_NODES + 150.0, 205.0 * ns + 150.0
 
 
 def ncu_kernel_counts(workload, batch=10000):

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libxrsd_b200.so")
 SOURCES = ["abi.cu", "intensity_kernel.cu", "table_kernel.cu", "fit_kernels.cu", "feature_kernel.cu"]
-HEADERS = ["forms.cuh", "faddeeva.cuh", "lattice.cuh", "system_eval.cuh", "launch_util.cuh", os.path.join("..", "..", "include", "xrsd_b200.h")]
+HEADERS = ["forms.cuh", "faddeeva.cuh", "lattice.cuh", "system_eval.cuh", "cheb_matrices.cuh", "launch_util.cuh", os.path.join("..", "..", "include", "xrsd_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("XRSD_NVCC_EXTRA", "").split()   # e.g. -DEXPERIMENT for A/B builds
 

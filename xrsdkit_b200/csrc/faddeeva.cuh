@@ -131,84 +131,75 @@ constexpr int VOIGT_TAB_N = 14;          // nodes per interval (degree 13: as ac
 constexpr int VOIGT_TAB_INTERVALS = 16;
 constexpr double VOIGT_TAB_MIN_Y = 1.0e-4;     // below: e^{-x^2} dominates out to x ~ 4.5 and the table loses relative accuracy
 constexpr int VOIGT_TAB_DOUBLES = VOIGT_TAB_N * VOIGT_TAB_INTERVALS;      // nodes of one table build
-// A coefficient row is stored as 18 doubles c[0..17] with c[k + 1] = a_k (c[0] unused): the pairs (a_2j-1, a_2j) the
-// two Clenshaw chains consume together are then 16-byte aligned and come with ONE LDS.128 each -- 9 loads per
-// evaluation instead of 17 (the coefficient loads were 5 % of a crystalline pattern's instructions).
+// A far-field coefficient row is stored with a pitch of 18 doubles (16-byte aligned): pairs (e_j, o_j), ONE LDS.128
+// per pair -- 8 loads per evaluation (the coefficient loads were 5 % of a crystalline pattern's instructions).
 constexpr int CHEB_ROW = 18;
-constexpr int VOIGT_TAB_STORE = VOIGT_TAB_N * VOIGT_TAB_INTERVALS;        // table rows: c[k] = a_k, 14 doubles (16-byte multiples)
+constexpr int VOIGT_TAB_STORE = VOIGT_TAB_N * VOIGT_TAB_INTERVALS;        // table rows: (e_0, o_0, ..., e_6, o_6), 14 doubles (16-byte multiples)
 
-// Cooperative build (all `nthreads` threads): cos_tab[k*N + m] = cos(pi k (m + 1/2)/N); tmp holds
-// VOIGT_TAB_DOUBLES doubles; tab receives the coefficients (a_0 .. a_16 per interval, a_0 not yet halved).
-__device__ __forceinline__ void voigt_table(double *tab, double *tmp, const double *cos_tab, const VoigtConst *vc,
+// Cooperative build (all `nthreads` threads): mat / nodes = XRSD_VT_M / XRSD_VT_NODES of cheb_matrices.cuh (node values ->
+// even / odd power-series coefficients in u = 2 t^2 - 1, rows e_0, o_0, e_1, o_1, ...); tmp holds VOIGT_TAB_DOUBLES
+// doubles; tab receives, per interval, the row (e_0, o_0, ..., e_6, o_6) that eo14() evaluates.
+__device__ __forceinline__ void voigt_table(double *tab, double *tmp, const double *mat, const double *nodes, const VoigtConst *vc,
                                             int tid, int nthreads) {
   for (int it = tid; it < VOIGT_TAB_DOUBLES; it += nthreads) {
     const int k = it / VOIGT_TAB_N, m = it - k * VOIGT_TAB_N;
-    tmp[it] = rew_near(0.5 * ((double)k + 0.5 + 0.5 * cos_tab[VOIGT_TAB_N + m]), vc);
+    tmp[it] = rew_near(0.5 * ((double)k + 0.5 + 0.5 * nodes[m]), vc);
   }
   __syncthreads();
   for (int it = tid; it < VOIGT_TAB_DOUBLES; it += nthreads) {
     const int k = it / VOIGT_TAB_N, j = it - k * VOIGT_TAB_N;
     double a = 0.0;
 #pragma unroll
-    for (int m = 0; m < VOIGT_TAB_N; ++m) a = fma(tmp[k * VOIGT_TAB_N + m], cos_tab[j * VOIGT_TAB_N + m], a);
-    tab[k * VOIGT_TAB_N + j] = a * (2.0 / VOIGT_TAB_N) * XRSD_SQRT_PI;      // the table holds sqrt(pi) Re w, like rew_far_raw (see rew_raw)
+    for (int m = 0; m < VOIGT_TAB_N; ++m) a = fma(tmp[k * VOIGT_TAB_N + m], mat[j * VOIGT_TAB_N + m], a);
+    tab[k * VOIGT_TAB_N + j] = a * XRSD_SQRT_PI;      // the table holds sqrt(pi) Re w, like rew_far_raw (see rew_raw)
   }
   __syncthreads();
 }
 
-// a_0/2 + sum_{k=1..16} a_k T_k(t), |t| <= 1, as TWO independent Clenshaw recurrences in u = 2 t^2 - 1 instead of one
-// in t:  T_2j(t) = T_j(u)  and  T_2j+1(t) = t W_j(u)  with W_j+1 = 2u W_j - W_j-1, W_0 = 1, W_1 = 2u - 1  (for which
-// the Clenshaw sum is b_0 - b_1).  Same operation count, half the dependency depth: these sums sit in loops that are
-// bound by the latency of the FP64 pipe, not its throughput (ncu: `wait` is the top stall reason).
-template <int N>       // N odd: coefficients a_0 .. a_(N-1)
-__device__ __forceinline__ double cheb_row(const double *__restrict__ c, double t) {
-  static_assert(N % 2 == 1 && N + 1 <= CHEB_ROW, "odd number of coefficients in a CHEB_ROW row");
-  // c: a coefficient row in the CHEB_ROW layout (c[k + 1] = a_k), 16-byte aligned
+// The interpolants are evaluated as E(u) + t O(u), u = 2 t^2 - 1, |t| <= 1: two independent Horner chains over the
+// even / odd power-series coefficients the matrices of cheb_matrices.cuh produce straight from the node values (one FMA
+// per coefficient; the Clenshaw form of the same interpolant, two chains in u as well, took an FMA and a subtraction
+// per coefficient -- 33 against 15 FP64 instructions for 15 coefficients).  A row holds (e_0, o_0, e_1, o_1, ...),
+// 16-byte aligned, so every LDS.128 feeds both chains.  These sums sit in loops bound by the FP64 pipe.
+template <int N>       // N = 15: e_0 .. e_7, o_0 .. o_6 (c[15] is never read)
+__device__ __forceinline__ double far_poly(const double *__restrict__ c, double t) {
+  static_assert(N == 15 && N + 1 <= CHEB_ROW, "15 coefficients in a CHEB_ROW row");
   const double2 *c2 = reinterpret_cast<const double2 *>(c);
-  const double u2 = fma(4.0 * t, t, -2.0);               // 2u
-  const double2 top = c2[(N - 1) / 2];                   // (a_(N-2), a_(N-1))
-  double e1 = top.y, e2 = 0.0;                           // even chain: coefficients a_(N-1), a_(N-3), ..., a_2
-  double o1 = top.x, o2 = 0.0;                           // odd chain:  coefficients a_(N-2), a_(N-4), ..., a_1
+  const double u = fma(2.0 * t, t, -1.0);
+  double E = c2[7].x;                                    // e_7
+  double2 p = c2[6];
+  double O = p.y;                                        // o_6
+  E = fma(E, u, p.x);
 #pragma unroll
-  for (int j = (N - 3) / 2; j >= 1; --j) {
-    const double2 p = c2[j];                             // (a_2j-1, a_2j)
-    const double e0 = fma(u2, e1, p.y - e2);
-    const double o0 = fma(u2, o1, p.x - o2);
-    e2 = e1; e1 = e0;
-    o2 = o1; o1 = o0;
+  for (int j = 5; j >= 0; --j) {
+    p = c2[j];
+    E = fma(E, u, p.x);
+    O = fma(O, u, p.y);
   }
-  // even: a_0/2 + u e_1 - e_2;   odd: t (b_0 - b_1) with b_0 = o1 (after the last step), b_1 = o2
-  return fma(0.5 * u2, e1, 0.5 * c[1] - e2) + t * (o1 - o2);
+  return fma(t, O, E);
 }
-__device__ __forceinline__ double cheb17(const double *__restrict__ c, double t) { return cheb_row<17>(c, t); }
 
-// a_0/2 + sum_{k=1..13} a_k T_k(t) for a row c[k] = a_k of 14 coefficients (16-byte aligned): the same two chains,
-// (a_2j, a_2j+1) per LDS.128 -- the rows of the near-branch Voigt table
-__device__ __forceinline__ double cheb14(const double *__restrict__ c, double t) {
+// the rows of the near-branch Voigt table: (e_0, o_0, ..., e_6, o_6)
+__device__ __forceinline__ double eo14(const double *__restrict__ c, double t) {
   static_assert(VOIGT_TAB_N == 14, "degree 13");
   const double2 *c2 = reinterpret_cast<const double2 *>(c);
-  const double u2 = fma(4.0 * t, t, -2.0);               // 2u
+  const double u = fma(2.0 * t, t, -1.0);
   double2 p = c2[6];
-  double e1 = p.x, e2 = 0.0;                             // even chain: a_12, a_10, ..., a_2, then a_0 / 2
-  double o1 = p.y, o2 = 0.0;                             // odd chain:  a_13, a_11, ..., a_1
+  double E = p.x, O = p.y;
 #pragma unroll
-  for (int j = 5; j >= 1; --j) {
+  for (int j = 5; j >= 0; --j) {
     p = c2[j];
-    const double e0 = fma(u2, e1, p.x - e2);
-    const double o0 = fma(u2, o1, p.y - o2);
-    e2 = e1; e1 = e0;
-    o2 = o1; o1 = o0;
+    E = fma(E, u, p.x);
+    O = fma(O, u, p.y);
   }
-  p = c2[0];
-  const double d0 = fma(u2, o1, p.y - o2);               // the odd chain has one more coefficient
-  return fma(0.5 * u2, e1, 0.5 * p.x - e2) + t * (d0 - o1);
+  return fma(t, O, E);
 }
 
 __device__ __forceinline__ double rew_table(double x, const double *tab) {
   const double x2 = x + x;                               // 0 <= x < 8: interval k = floor(2x), t = 2(2x - k) - 1
   const int k = (int)x2;
   const double t = 2.0 * (x2 - (double)k) - 1.0;
-  return cheb14(tab + k * VOIGT_TAB_N, t);
+  return eo14(tab + k * VOIGT_TAB_N, t);
 }
 
 // Re w(x + i y) with y = vc->y > 0.  (y == 0 is the Gaussian exp(-x^2): rew_any below; the crystalline sums route that

@@ -25,6 +25,7 @@
 #include <type_traits>
 #include "../../include/xrsd_b200.h"
 #include "faddeeva.cuh"
+#include "cheb_matrices.cuh"
 #include "forms.cuh"
 #include "lattice.cuh"
 
@@ -41,12 +42,9 @@ constexpr int RNORMAL_UNROLL = XRSD_RNORMAL_UNROLL;
 #endif
 
 // shared-memory working set of one CTA (besides the pattern buffer)
-#ifndef XRSD_CHEB_N
-#define XRSD_CHEB_N 15
-#endif
-constexpr int CHEB_N = XRSD_CHEB_N;              // Chebyshev nodes of the far-field interpolant (degree CHEB_N - 1; odd).
-                                                 // Same box, cfg3 kernel and worst golden parity: 17 nodes 2.10 ms / 8.9e-14,
-                                                 // 15 nodes 1.98 ms / 2.8e-13, 13 nodes 1.89 ms / 1.8e-11 (gate: 1e-10)
+constexpr int CHEB_N = 15;                       // Chebyshev nodes of the far-field interpolant (degree 14; cheb_matrices.cuh is
+                                                 // generated for this N).  Same box, cfg3 kernel and worst golden parity: 17 nodes
+                                                 // 2.10 ms / 8.9e-14, 15 nodes 1.98 ms / 2.8e-13, 13 nodes 1.89 ms / 1.8e-11 (gate: 1e-10)
 #ifndef XRSD_HX_MIN_CTAS
 #define XRSD_HX_MIN_CTAS 8                        // resident CTAs per SM the crystalline kernels are compiled for (64 registers; 7 x 72 and 6 x 80 measured 4 % and 9 % slower)
 #endif
@@ -57,10 +55,12 @@ constexpr int CHEB_ROUND = XRSD_CHEB_ROUND;                   // runs of EVAL_TH
                                                  // (measured: 8 -> 16 +3.5 %, 16 -> 32 +1.7 % since the loops got leaner, 64 loses occupancy: -6 %)
 
 struct ChebShared {                               // only in kernels that can meet a crystalline population
-  double cheb_cos[CHEB_N * CHEB_N];              // cos(pi k (m + 1/2) / N)
-  double vt_cos[VOIGT_TAB_N * VOIGT_TAB_N];      // the same for the nodes of the Voigt near-branch table
+  double cheb_cos[CHEB_N * CHEB_N];              // XRSD_FAR_M: node sums -> even / odd power-series coefficients (cheb_matrices.cuh)
+  double cheb_node[CHEB_N];                      // the nodes cos(pi (m + 1/2) / N)
+  double vt_cos[VOIGT_TAB_N * VOIGT_TAB_N];      // XRSD_VT_M: the same for the nodes of the Voigt near-branch table
+  double vt_node[VOIGT_TAB_N];
   double cheb_part[2 * CHEB_ROUND * CHEB_N];     // node sums, two shell-parity halves per node
-  alignas(16) double cheb_coef[CHEB_ROUND * CHEB_ROW];   // rows in the CHEB_ROW layout of cheb17 (faddeeva.cuh)
+  alignas(16) double cheb_coef[CHEB_ROUND * CHEB_ROW];   // rows (e_0, o_0, e_1, ...) of far_poly (faddeeva.cuh)
   // per run of a round, double-buffered by round parity (the next round's entries are prepared while this round's
   // points are evaluated): the contiguous range [near_lo, near_hi) of shells summed directly, centre, half-width, 1/half-width
   int near_lo[2][CHEB_ROUND], near_hi[2][CHEB_ROUND];
@@ -190,10 +190,10 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
       for (int i = tid; i + 1 < q_count; i += EVAL_THREADS) mine = mine && (q[q_begin + i] < q[q_begin + i + 1]);
       q_sorted = __syncthreads_and(mine) != 0;
     }
-    for (int i = tid; i < CHEB_N * CHEB_N; i += EVAL_THREADS)
-      S->cheb_cos[i] = cospi((double)(i / CHEB_N) * ((double)(i % CHEB_N) + 0.5) / (double)CHEB_N);
-    for (int i = tid; i < VOIGT_TAB_N * VOIGT_TAB_N; i += EVAL_THREADS)
-      S->vt_cos[i] = cospi((double)(i / VOIGT_TAB_N) * ((double)(i % VOIGT_TAB_N) + 0.5) / (double)VOIGT_TAB_N);
+    for (int i = tid; i < CHEB_N * CHEB_N; i += EVAL_THREADS) S->cheb_cos[i] = XRSD_FAR_M[i];
+    for (int i = tid; i < VOIGT_TAB_N * VOIGT_TAB_N; i += EVAL_THREADS) S->vt_cos[i] = XRSD_VT_M[i];
+    if (tid < CHEB_N) S->cheb_node[tid] = XRSD_FAR_NODES[tid];
+    if (tid >= 32 && tid < 32 + VOIGT_TAB_N) S->vt_node[tid - 32] = XRSD_VT_NODES[tid - 32];
   }
 
   for (int ip = 0; ip < L.n_pops; ++ip) {
@@ -494,7 +494,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
         const double norm = block_sum(part, S);
         const double *vtab = nullptr;
         if (voigt_near_possible && __syncthreads_or(core_here)) {
-          voigt_table(S->voigt_tab, S->cheb_part, S->vt_cos, &S->vc, tid, EVAL_THREADS);
+          voigt_table(S->voigt_tab, S->cheb_part, S->vt_cos, S->vt_node, &S->vc, tid, EVAL_THREADS);
           vtab = S->voigt_tab;
         }
         // pass B: chunks of shells staged as (q_s, W_s[...]) in scratch
@@ -598,7 +598,7 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
             for (int item = tid; item < n_run * CHEB_N * 2; item += EVAL_THREADS) {
               const int run = item / (2 * CHEB_N), rem = item - run * 2 * CHEB_N;
               const int g = rem / CHEB_N, m = rem - g * CHEB_N;
-              const double xm = fma(S->run_H[buf][run], S->cheb_cos[CHEB_N + m], S->run_c[buf][run]);   // row k=1: cos(pi (m+1/2)/N)
+              const double xm = fma(S->run_H[buf][run], S->cheb_node[m], S->run_c[buf][run]);
               const int lo = S->near_lo[buf][run], hi = S->near_hi[buf][run];
               double part = 0.0;
               for (int sl = g; sl < lo; sl += 2) {
@@ -612,14 +612,14 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               S->cheb_part[item] = part;
             }
             __syncthreads();
-            // (2) coefficient (run, k): a_k = 2/N sum_m B_m cos(pi k (m+1/2)/N)
+            // (2) coefficient (run, k) of the even / odd power series in u = 2 t^2 - 1: row k of XRSD_FAR_M times the node sums
             for (int item = tid; item < n_run * CHEB_N; item += EVAL_THREADS) {
               const int run = item / CHEB_N, k = item - run * CHEB_N;
               const double *pa = S->cheb_part + run * 2 * CHEB_N;
               double ak = 0.0;
 #pragma unroll
               for (int m = 0; m < CHEB_N; ++m) ak = fma(pa[m] + pa[CHEB_N + m], S->cheb_cos[k * CHEB_N + m], ak);
-              S->cheb_coef[run * CHEB_ROW + 1 + k] = ak * (2.0 / CHEB_N);
+              S->cheb_coef[run * CHEB_ROW + k] = ak;
             }
             if (r0 + CHEB_ROUND * EVAL_THREADS < q_count) prepare_round(r0 + CHEB_ROUND * EVAL_THREADS, buf ^ 1);
             __syncthreads();
@@ -629,9 +629,9 @@ __device__ void accumulate_system(const xrsd_layout_t &L, const double *__restri
               const int i = i0 + tid;
               if (i >= i1) continue;
               const double qi = q[q_begin + i];
-              // a_0/2 + sum_k a_k T_k(t), t in [-1, 1] (two interleaved Clenshaw chains: faddeeva.cuh)
+              // the interpolant at t in [-1, 1] (two Horner chains in u: faddeeva.cuh)
               const double t = (qi - S->run_c[buf][run]) * S->run_invH[buf][run];
-              double a_sum = cheb_row<CHEB_N>(S->cheb_coef + run * CHEB_ROW, t);
+              double a_sum = far_poly<CHEB_N>(S->cheb_coef + run * CHEB_ROW, t);
               const int s_lo = S->near_lo[buf][run], s_hi = S->near_hi[buf][run];
               for (int sl = s_lo; sl < s_hi; ++sl) {
                 const double2 sw = *reinterpret_cast<const double2 *>(scratch + 2 * sl);
