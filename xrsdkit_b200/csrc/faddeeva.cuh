@@ -60,12 +60,13 @@ __device__ __forceinline__ void voigt_constants(VoigtConst *vc, double y, int ti
 // obeys a REAL three-term recurrence (z^2 and conj(z)^2 are the roots of its characteristic polynomial):
 //     u_k+1 = (2 Re z^2 / |z|^4) u_k - u_k-1 / |z|^4,     u_0 = y / |z|^2,  u_-1 = -y,
 // whose two solutions have equal modulus (errors grow linearly in k, no cancellation: every u_k carries the factor y
-// that makes the far wing of a narrow-Lorentzian Voigt profile small).  Three FP64 instructions per term -- product,
-// recurrence, accumulation with the coefficient as an immediate -- against four per term plus two-constant linear
-// factors for a complex Horner / Estrin evaluation of the same sum: 25 instead of 42 FP64 instructions for k <= 5
-// (this branch is ~40 % of the instructions of a crystalline pattern, profiles/r02_ncu_cfg3.txt), and the longer
-// truncations continue the same recurrence.  Max relative difference to scipy's wofz 1.5e-13 (at |z| = 8).
-__device__ __forceinline__ double rew_far_raw(double x, double y, double z2) {
+// that makes the far wing of a narrow-Lorentzian Voigt profile small).  The sum is taken by Clenshaw's backward
+// recurrence over that three-term relation: two FMAs per term with the coefficient as an immediate (forming the u_k and
+// accumulating c_k u_k took three FP64 instructions per term, a complex Horner / Estrin evaluation four plus
+// two-constant linear factors), and 2 Re z^2 / |z|^4 = 2 t - 4 y^2 t^2 needs x no more: 18 FP64 instructions for k <= 5
+// (24 before; this branch is ~40 % of the instructions of a crystalline pattern, profiles/r02_ncu_cfg3.txt).
+// Max relative difference to scipy's wofz 1.3e-13 (at |z| = 8, the truncation), the same as the forward form.
+__device__ __forceinline__ double rew_far_raw(double /* x: enters through z2 only */, double y, double z2) {
   // Returns sqrt(pi) Re w (the caller scales, or -- in a ratio of profile sums -- does not have to).
   // 1/|z|^2 for 64 <= |z|^2 < inf: the hardware seed (MUFU.RCP64H, relative error <= 1e-6) and ONE third-order step
   // e <- e + e^2, t <- t + t e: error e^3 ~ 1e-18 plus rounding -- measured 1.11e-16 over 4e6 arguments in
@@ -79,22 +80,32 @@ __device__ __forceinline__ double rew_far_raw(double x, double y, double z2) {
     t = fma(t, e, t);
   }
   const double b = t * t;                               // 1/|z|^4
-  const double al = 2.0 * fma(x, x, -(y * y)) * b;      // 2 Re z^2 / |z|^4
-  double um = y * t;                                    // u_0
-  double u = fma(al, um, b * y);                        // u_1
-  double sum = fma(0.5, u, um);
-  double un;
-#define XRSD_FAR_TERM(ck) un = fma(al, u, -(b * um)); sum = fma(ck, un, sum); um = u; u = un;
-  XRSD_FAR_TERM(0.75) XRSD_FAR_TERM(1.875) XRSD_FAR_TERM(6.5625) XRSD_FAR_TERM(29.53125)
+  // al = 2 Re z^2 / |z|^4 with Re z^2 = |z|^2 - 2 y^2:  2 t - 4 y^2 b  (x does not enter again)
+  const double al = fma(-4.0 * (y * y), b, t + t);
+  // S = sum_k c_k u_k, c_k = (2k-1)!! / 2^k, by Clenshaw's backward recurrence for u_k+1 = al u_k - b u_k-1:
+  //     B_k = c_k + al B_k+1 - b B_k+2,      S = B_0 u_0 + B_1 (u_1 - al u_0) = y (B_0 t + B_1 b)
+  // -- two FMAs per term where forming u_k and accumulating c_k u_k took a product and two FMAs; the B_k are dominated
+  // by their c_k (al, b <= 2/64), so nothing cancels.  The truncation (k <= 5 / 7 / 12 by |z|^2) sets where the chain starts.
+  double B1, B2;                                        // B_k+1, B_k+2
+#define XRSD_FAR_STEP(ck) { const double Bn = fma(al, B1, fma(-b, B2, ck)); B2 = B1; B1 = Bn; }
   if (z2 < 1024.0) {
-    XRSD_FAR_TERM(162.421875) XRSD_FAR_TERM(1055.7421875)
-    if (z2 < 256.0) {                                   // down to |z| = 8
-      XRSD_FAR_TERM(7918.06640625) XRSD_FAR_TERM(67303.564453125) XRSD_FAR_TERM(639383.8623046875)
-      XRSD_FAR_TERM(6713530.554199219) XRSD_FAR_TERM(77205601.37329102)
+    if (z2 < 256.0) {                                   // down to |z| = 8: k = 12 .. 8
+      B2 = 77205601.37329102;
+      B1 = fma(al, B2, 6713530.554199219);
+      XRSD_FAR_STEP(639383.8623046875) XRSD_FAR_STEP(67303.564453125) XRSD_FAR_STEP(7918.06640625)
+      XRSD_FAR_STEP(1055.7421875) XRSD_FAR_STEP(162.421875)
+    } else {                                            // k = 7, 6
+      B2 = 1055.7421875;
+      B1 = fma(al, B2, 162.421875);
     }
+    XRSD_FAR_STEP(29.53125) XRSD_FAR_STEP(6.5625)
+  } else {                                              // k = 5, 4
+    B2 = 29.53125;
+    B1 = fma(al, B2, 6.5625);
   }
-#undef XRSD_FAR_TERM
-  return sum;
+  XRSD_FAR_STEP(1.875) XRSD_FAR_STEP(0.75) XRSD_FAR_STEP(0.5) XRSD_FAR_STEP(1.0)
+#undef XRSD_FAR_STEP
+  return y * fma(B2, b, B1 * t);                        // B1 = B_0, B2 = B_1
 }
 constexpr double XRSD_INV_SQRT_PI = 0.56418958354775628695, XRSD_SQRT_PI = 1.7724538509055160273;
 __device__ __forceinline__ double rew_far(double x, double y, double z2) { return rew_far_raw(x, y, z2) * XRSD_INV_SQRT_PI; }
