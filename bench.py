@@ -49,9 +49,10 @@ LM_ITERS = 30           # iteration cap                                         
 FLOPS_PER_PAIR_RNORMAL = 13.0
 FLOPS_PER_Q_OVERHEAD_CFG2 = 151.0        # PY brackets ~100, two divisions 20, three span-to-span rotations 18, epilogue ~13
 SURVEY_FLOPS_PER_SETQ_CFG2 = 2630.0      # SURVEY.md 8d convention (sincos per (q,r) pair)
-#   crystalline: one far-branch Voigt evaluation = reciprocal (3 FMA) + set-up (2 FMA, 5 mul) + 4 recurrence terms
-#   (mul + 2 FMA each) + argument and accumulation (1 mul, 2 FMA) = 23 FP64 instructions, 41 flop
-VOIGT_FLOPS = 41.0
+#   crystalline: one far-branch Voigt evaluation = reciprocal (3 FMA) + set-up (mul, add, FMA) + Clenshaw chain of the
+#   asymptotic series (9 FMA at k <= 5) + finish (2 mul, FMA) + argument and accumulation (1 mul, 2 FMA) = 21 FP64
+#   instructions, 37 flop (23 instructions / 41 flop with the forward recurrence used until r02h)
+VOIGT_FLOPS = 37.0
 #   near-branch Voigt evaluation through the pattern's table (|z| < 8): interval and argument 4, u = 2t^2 - 1 and two
 #   Horner chains of 6 FMA, t O + E, accumulation: 17 FP64 instructions, 31 flop
 VOIGT_TABLE_FLOPS = 31.0
